@@ -1,0 +1,193 @@
+"""oracle.gen_golden -- TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz.
+
+Runs the reference's UNMODIFIED ``controller_mpc`` + ``optimizer_mppi`` / ``optimizer_rpgd`` /
+``optimizer_cem_tf`` files (imported from /root/reference through the shims in oracle/refharness) on
+torch-CPU fp32 with the build's pinned predictor / cost spec and INJECTED noise, and stores inputs +
+outputs as small fixtures.  Must be run in the build container (needs /root/reference):
+
+    python -m oracle.gen_golden            # writes tests/golden/*.npz
+
+Each fixture holds: the case config (json), the per-tick states, the noise seed (noise is regenerated from
+``numpy.random.default_rng(seed)`` by oracle.replay_rng.ReplayRNG; a checksum of the draws is stored), and
+the reference's outputs per tick.
+"""
+from __future__ import annotations
+
+import copy
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+# ------------------------------------------------------------------------------------------------
+# case table.  C1..C4 = BASELINE.json configs (reduced N where a fixture would be too large).
+# ------------------------------------------------------------------------------------------------
+MPPI_BASE = dict(seed=42, mpc_horizon=50, mpc_timestep=0.02, num_rollouts=2000, cc_weight=1.0, R=1.0, LBD=100.0,
+                 NU=1000.0, SQRTRHOINV=0.03, period_interpolation_inducing_points=10)
+CEM_BASE = dict(seed=42, mpc_horizon=50, mpc_timestep=0.02, cem_outer_it=3, cem_initial_action_stdev=0.5,
+                num_rollouts=4096, cem_stdev_min=0.01, cem_best_k=64, warmup=False, warmup_iterations=250)
+RPGD_BASE = dict(seed=42, mpc_horizon=50, mpc_timestep=0.02, SAMPLING_DISTRIBUTION="uniform",
+                 period_interpolation_inducing_points=10, learning_rate=0.05, adam_beta_1=0.9, adam_beta_2=0.999,
+                 adam_epsilon=1.0e-8, gradmax_clip=5, rtol=1.0e-3, num_rollouts=32, opt_keep_k_ratio=0.25,
+                 outer_its=2, resamp_per=10, sample_stdev=0.5, sample_mean=0.0, sample_whole_control_space=True,
+                 uniform_dist_min=-1.0, uniform_dist_max=1.0, shift_previous=1, warmup=False, warmup_iterations=250)
+
+
+def _c(base, **kw):
+    d = copy.deepcopy(base)
+    d.update(kw)
+    return d
+
+
+CASES = {
+    # name: (optimizer, predictor_spec, cost, optimizer-config, ticks, keep_rollouts)
+    "mppi_c1_n64": ("mppi", "ODE", "default", _c(MPPI_BASE, num_rollouts=64), 4, True),
+    "mppi_c1_n2000": ("mppi", "ODE", "default", _c(MPPI_BASE), 3, False),
+    "mppi_h100_n256": ("mppi", "ODE", "default", _c(MPPI_BASE, num_rollouts=256, mpc_horizon=100), 3, False),
+    "mppi_h43_p10_n64": ("mppi", "ODE", "default", _c(MPPI_BASE, num_rollouts=64, mpc_horizon=43), 2, True),
+    "mppi_h20_p1_n96": ("mppi", "ODE", "default", _c(MPPI_BASE, num_rollouts=96, mpc_horizon=20,
+                                                      period_interpolation_inducing_points=1), 2, False),
+    "mppi_lbd1_n512": ("mppi", "ODE", "default", _c(MPPI_BASE, num_rollouts=512, LBD=1.0, SQRTRHOINV=0.1), 3, False),
+    "cem_c2_n256_k16": ("cem-tf", "ODE", "default", _c(CEM_BASE, num_rollouts=256, cem_best_k=16), 3, True),
+    "cem_c2_n4096_k64": ("cem-tf", "ODE", "default", _c(CEM_BASE), 2, False),
+    "cem_warmup_n128": ("cem-tf", "ODE", "default", _c(CEM_BASE, num_rollouts=128, cem_best_k=8, warmup=True,
+                                                       warmup_iterations=5, mpc_horizon=30), 2, False),
+    "rpgd_c3": ("rpgd", "ODE", "quadratic_boundary_grad", _c(RPGD_BASE), 12, True),
+    "rpgd_normal_shift2": ("rpgd", "ODE", "quadratic_boundary_grad",
+                           _c(RPGD_BASE, SAMPLING_DISTRIBUTION="normal", shift_previous=2, resamp_per=3,
+                              num_rollouts=48, mpc_horizon=35, outer_its=3), 7, False),
+    "rpgd_warmup_n64": ("rpgd", "ODE", "quadratic_boundary_grad",
+                        _c(RPGD_BASE, num_rollouts=64, warmup=True, warmup_iterations=6, resamp_per=2,
+                           period_interpolation_inducing_points=5), 4, False),
+    "mppi_mlp_c4_n256": ("mppi", "Dense-6IN-128H1-128H2-5OUT-0", "default",
+                         _c(MPPI_BASE, num_rollouts=256, mpc_horizon=100), 2, False),
+    "mppi_mlp_h50_n64": ("mppi", "Dense-6IN-128H1-128H2-5OUT-0", "default",
+                         _c(MPPI_BASE, num_rollouts=64, mpc_horizon=50), 2, True),
+}
+NOISE_SEED = 1
+STATE_SEED = 0
+MLP_SEED = 2
+
+
+def run_reference_case(name: str) -> dict:
+    """Execute one case through the unmodified reference.  Requires enter_workspace() to have been called."""
+    import torch
+    torch.set_num_threads(1)  # deterministic reduction order for the fixtures
+    from oracle import spec
+    from oracle.replay_rng import ReplayRNG
+    from SI_Toolkit.Predictors import predictor_wrapper as pw
+    import yaml
+
+    opt_name, pred_spec, cost_name, cfg, ticks, keep_rollouts = CASES[name]
+
+    # controller config is read at controller construction time (reference Controllers/__init__.py:39)
+    cc = dict(mpc=dict(optimizer=opt_name, predictor_specification=pred_spec, cost_function_specification=cost_name,
+                       computation_library="tensorflow" if opt_name == "cem-tf" else "pytorch", device="cpu",
+                       controller_logging=True, calculate_optimal_trajectory=False))
+    with open(os.path.join("Control_Toolkit_ASF", "config_controllers.yml"), "w") as f:
+        yaml.safe_dump(cc, f)
+
+    if pred_spec.startswith("Dense"):
+        pw.MLP_REGISTRY[pred_spec] = spec.MLPWeights.random_init(MLP_SEED)
+
+    from Control_Toolkit.Controllers import controller_mpc as cm  # noqa: the reference module
+    cm.config_optimizers[opt_name] = copy.deepcopy(cfg)  # optimizer kwargs (module-global dict loaded at import)
+
+    ctrl = cm.controller_mpc(
+        environment_name="CartPole",
+        control_limits=(np.array([-1.0], np.float32), np.array([1.0], np.float32)),
+        initial_environment_attributes={"target_position": 0.0, "target_equilibrium": 1.0},
+    )
+    ctrl.configure(optimizer_name=opt_name, predictor_specification=pred_spec)
+    opt = ctrl.optimizer
+    rng = ReplayRNG(NOISE_SEED)
+    opt.rng = rng
+    opt.optimizer_reset()  # RPGD draws its initial population here; re-done so it comes from the replay rng
+    if opt_name == "rpgd":
+        # reference quirk: optimizer_rpgd.py:416 logs the PREVIOUS u, which is the python float 0.0 on the first
+        # tick (Optimizers/__init__.py:35) and has no .copy() (Controllers/__init__.py:177) -> give it a numpy 0.
+        opt.u = np.float32(0.0)
+
+    if opt_name == "cem-tf":
+        import tensorflow as tfshim
+        argsort_log = []
+        _orig = tfshim.argsort
+
+        def _logging_argsort(x, axis=-1):
+            r = _orig(x, axis)
+            argsort_log.append(r.numpy().copy())
+            return r
+
+        tfshim.argsort = _logging_argsort
+
+    states = spec.synthetic_states(ticks, STATE_SEED)
+    out = {"config": np.array(json.dumps(dict(case=name, optimizer=opt_name, predictor=pred_spec, cost=cost_name,
+                                              cfg=cfg, ticks=ticks, noise_seed=NOISE_SEED, state_seed=STATE_SEED,
+                                              mlp_seed=MLP_SEED))),
+           "states": states}
+    if opt_name == "rpgd":
+        out["Q_init"] = opt.Q_tf.numpy().copy()
+
+    for t in range(ticks):
+        u = ctrl.step(states[t], time=0.02 * t)
+        out[f"u_{t}"] = np.asarray(u, np.float32).reshape(-1)
+        lv = opt.logging_values
+        if opt_name == "mppi":
+            out[f"u_nom_{t}"] = opt.u_nom.numpy().copy()
+            out[f"J_{t}"] = np.asarray(lv["J_logged"]).copy()
+        elif opt_name == "cem-tf":
+            out[f"dist_mue_{t}"] = opt.dist_mue.numpy().copy()
+            out[f"stdev_{t}"] = opt.stdev.numpy().copy()
+            out[f"J_{t}"] = np.asarray(lv["J_logged"]).copy()  # costs of the LAST outer iteration
+            k = cfg["cem_best_k"]
+            out[f"elite_idx_{t}"] = np.stack([a[:k] for a in argsort_log]).astype(np.int64)  # [iters, k]
+            out[f"sorted_gap_{t}"] = np.array([float(np.sort(np.asarray(lv["J_logged"]))[k] -
+                                                      np.sort(np.asarray(lv["J_logged"]))[k - 1])], np.float32)
+            argsort_log.clear()
+        elif opt_name == "rpgd":
+            step, m, v = opt.opt.get_weights()
+            out[f"Q_{t}"] = opt.Q_tf.numpy().copy()
+            out[f"adam_m_{t}"] = np.asarray(m).copy()
+            out[f"adam_v_{t}"] = np.asarray(v).copy()
+            out[f"adam_step_{t}"] = np.array([int(step)], np.int64)
+            out[f"ages_{t}"] = opt.trajectory_ages.numpy().copy()
+            out[f"J_{t}"] = np.asarray(lv["J_logged"]).copy()
+            out[f"u_nom_{t}"] = np.asarray(opt.optimal_control_sequence).copy()
+        if keep_rollouts and t == 0:
+            out["Q_logged_0"] = np.asarray(lv["Q_logged"]).copy()
+            out["rollouts_0"] = np.asarray(lv["rollout_trajectories_logged"]).copy()
+
+    out["noise_blocks"] = np.array(json.dumps(rng.blocks))
+    # checksum of the full noise stream, to detect a numpy Generator stream change on another box
+    chk = ReplayRNG(NOISE_SEED, as_torch=False)
+    acc = 0.0
+    for kind, shape in rng.blocks:
+        acc += float(np.sum(chk.standard_draws(kind, shape).astype(np.float64)))
+    out["noise_checksum"] = np.array([acc], np.float64)
+
+    if opt_name == "cem-tf":
+        tfshim.argsort = _orig
+    return out
+
+
+def main(argv=None):
+    from oracle.refharness.workspace import enter_workspace
+    names = (argv or sys.argv[1:]) or list(CASES)
+    enter_workspace()
+    import logging
+    logging.disable(logging.INFO)
+    os.makedirs(GOLDEN, exist_ok=True)
+    for name in names:
+        out = run_reference_case(name)
+        path = os.path.join(GOLDEN, f"{name}.npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)  u0={out['u_0']}")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,86 @@
+"""oracle.mppi -- TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Standalone torch-CPU fp32 restatement of the reference's MPPI tick, following
+``/root/reference/Optimizers/optimizer_mppi.py`` line by line (cited per statement) with the interpolation of
+``others/Interpolator.py:53-84,97-106`` and the trajectory cost of ``Cost_Functions/__init__.py:74-93``.
+Pinned against the unmodified reference file through tests/golden/mppi_*.npz (tests/test_oracle_golden.py).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import spec
+
+
+def interpolation_matrix(horizon: int, period: int, nu: int = 1) -> np.ndarray:
+    """reference others/Interpolator.py:53-77 -> W [n_ind, H] (nu folded away: identical for every control)."""
+    n_ind = int(math.ceil((horizon - 1) / period) + 1)  # Interpolator.py:79-84
+    mat = np.zeros(((n_ind - 1) * period + 1, n_ind), dtype=np.float32)
+    block = np.zeros((period, 2), dtype=np.float32)
+    for j in range(period):
+        block[j, 0] = period - j
+        block[j, 1] = j
+    for i in range(n_ind - 1):
+        mat[i * period:(i + 1) * period, i:i + 2] = block
+    mat[-1, -1] = 1
+    mat = mat[:horizon, :] / np.float32(period)  # fp32 division, Interpolator.py:74
+    return np.ascontiguousarray(mat.T)  # [n_ind, H]
+
+
+class MPPIOracle:
+    def __init__(self, predictor, cost: spec.CostParams, *, mpc_horizon, num_rollouts, cc_weight, R, LBD, NU,
+                 SQRTRHOINV, period_interpolation_inducing_points, mpc_timestep=0.02,
+                 action_low=-1.0, action_high=1.0, **_ignored):
+        self.predictor = predictor
+        self.cost = cost
+        self.H = int(mpc_horizon)
+        self.N = int(num_rollouts)
+        self.cc_weight = torch.tensor(cc_weight, dtype=torch.float32)  # optimizer_mppi.py:155 (to_tensor)
+        self.R = torch.tensor(R, dtype=torch.float32)  # :92
+        self.LBD = float(LBD)  # :93 (python float)
+        self.NU = torch.tensor(NU, dtype=torch.float32)  # :94
+        self.period = int(period_interpolation_inducing_points)
+        self.W = torch.from_numpy(interpolation_matrix(self.H, self.period))  # [n_ind, H]
+        self.n_ind = self.W.shape[0]
+        # :130  SQRTRHODTINV = fp32( SQRTRHOINV * (1/sqrt(dt)) ) evaluated in float64
+        self.SQRTRHODTINV = torch.tensor(np.array(SQRTRHOINV) * (1 / np.sqrt(mpc_timestep)), dtype=torch.float32)
+        self.low = torch.tensor([action_low], dtype=torch.float32)
+        self.high = torch.tensor([action_high], dtype=torch.float32)
+        self.reset()
+
+    def reset(self):
+        # optimizer_mppi.py:227-231
+        self.u_nom = 0.5 * (self.low + self.high) * torch.ones([1, self.H, 1])
+        self.u = 0.0
+        self.last = {}
+
+    def _interpolate(self, y):  # y [N, n_ind, 1] -> [N, H, 1]; Interpolator.py:97-106 (batched matmul per control)
+        return torch.matmul(y.permute(2, 0, 1), self.W[None]).permute(1, 2, 0)
+
+    def step(self, s: np.ndarray, rng) -> np.ndarray:
+        s = torch.as_tensor(np.asarray(s), dtype=torch.float32).reshape(1, -1)  # :208-209
+        u_old = self.u
+        s = s.repeat(self.N, 1)  # :182
+        u_nom = torch.cat([self.u_nom[:, 1:, :], self.u_nom[:, -1:, :]], 1)  # :184
+        delta_u = rng.normal([self.N, self.n_ind, 1], dtype=torch.float32) * self.SQRTRHODTINV  # :173-175
+        delta_u = self._interpolate(delta_u)  # :177
+        u_run = u_nom.repeat(self.N, 1, 1) + delta_u  # :186
+        u_run = torch.minimum(torch.maximum(u_run, self.low), self.high)  # :187
+        rollout = self.predictor.predict_core(s, u_run)  # :188
+        total = spec.trajectory_cost(rollout, u_run, u_old, self.cost)  # :159
+        # :154-155 mppi_correction_cost (evaluation order as written)
+        corr = torch.sum(self.cc_weight * (0.5 * (1 - 1.0 / self.NU) * self.R * (delta_u ** 2)
+                                           + self.R * u_run * delta_u + 0.5 * self.R * (u_run ** 2)), (1, 2))
+        S = total + corr  # :160
+        rho = torch.amin(S, 0)  # :164
+        exp_s = torch.exp(-1.0 / self.LBD * (S - rho))  # :165
+        a = torch.sum(exp_s, 0)  # :166
+        b = torch.sum(exp_s[:, None, None] * delta_u, 0) / a  # :167
+        u_nom = torch.minimum(torch.maximum(u_nom + b, self.low), self.high)  # :190
+        self.u_nom = u_nom
+        self.u = u_nom[0, 0, :].squeeze().numpy().copy()  # :191,212
+        self.last = dict(J=S.numpy(), Q=u_run.numpy(), rollouts=rollout.numpy(), delta_u=delta_u.numpy())
+        return self.u

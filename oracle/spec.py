@@ -1,0 +1,280 @@
+"""oracle.spec -- TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+The build's pinned written specification of the arithmetic the reference delegates to code that is
+NOT under /root/reference (**parity unpinned**):
+
+* the CartPole next-state ODE behind ``PredictorWrapper.predict_core``
+  (call sites: reference ``Optimizers/optimizer_mppi.py:188``, ``optimizer_cem_tf.py:57``,
+  ``optimizer_rpgd.py:300``),
+* the CartPole cost classes loaded by ``Cost_Functions/cost_function_wrapper.py:59-66``
+  (``default`` for MPPI/CEM, ``quadratic_boundary_grad`` for RPGD), evaluated through
+  ``Cost_Functions/__init__.py:49-93`` (stage cost shift, mean over H+1),
+* the 6->128->128->5 tanh MLP autoregressive predictor of config C4.
+
+Everything is fp32 torch-CPU, written one elementary operation at a time in the order the formulas
+are stated, so the CUDA kernels can follow the same op order.  All *compound constants* are evaluated
+in float64 on the host and rounded once to fp32 (``CartPoleParams.f32``); the CUDA side receives the
+same rounded constants through the C-ABI.
+
+State layout (alphabetical, upstream convention): [angle, angleD, angle_cos, angle_sin, position, positionD].
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+ANGLE, ANGLED, ANGLE_COS, ANGLE_SIN, POSITION, POSITIOND = range(6)
+NUM_STATES = 6
+NUM_CONTROLS = 1
+
+
+def _f32(x: float) -> float:
+    """Round a python double once to fp32 and return it as a python float."""
+    return float(np.float32(x))
+
+
+@dataclass
+class CartPoleParams:
+    # physical constants [UPSTREAM-RECALL, pinned here]
+    k: float = 1.0 / 3.0
+    M: float = 0.230
+    m: float = 0.087
+    L: float = 0.395 / 2.0
+    g: float = 9.81
+    J_fric: float = 2.5e-4
+    M_fric: float = 4.77
+    u_max: float = 2.62
+    TrackHalfLength: float = 0.198
+    # integration
+    dt: float = 0.02
+    intermediate_steps: int = 1
+
+    def f32(self) -> dict:
+        """Compound constants, float64 -> one rounding to fp32.  Same list as include/ctk_b200.h::ctk_ode_params."""
+        h = self.dt / self.intermediate_steps
+        return dict(
+            u_max=_f32(self.u_max),
+            kp1_Mm=_f32((self.k + 1.0) * (self.M + self.m)),
+            m=_f32(self.m),
+            neg_M_fric=_f32(-self.M_fric),
+            neg_J_fric=_f32(-self.J_fric),
+            mg=_f32(self.m * self.g),
+            L=_f32(self.L),
+            kp1=_f32(self.k + 1.0),
+            mL=_f32(self.m * self.L),
+            g=_f32(self.g),
+            kp1L=_f32((self.k + 1.0) * self.L),
+            h=_f32(h),
+        )
+
+
+@dataclass
+class CostParams:
+    """Weights of the CartPole cost classes.  quadratic_boundary_grad values are the ones visible at
+    reference ``Control_Toolkit_ASF_Template/config_cost_function.yml:11-18``; ``default`` reuses them
+    (its own are not visible anywhere in the reference)."""
+    name: str = "default"  # "default" | "quadratic_boundary_grad"
+    dd_weight: float = 600.0
+    ep_weight: float = 20000.0
+    ekp_weight: float = 80.0  # quadratic_boundary_grad only
+    cc_weight: float = 1.0
+    ccrc_weight: float = 1.0
+    R: float = 1.0
+    MAX_COST: float = 0.0  # reference Cost_Functions/__init__.py:13-15,63-64
+    TrackHalfLength: float = 0.198
+    target_position: float = 0.0
+    target_equilibrium: float = 1.0
+
+    def f32(self) -> dict:
+        thl = self.TrackHalfLength
+        return dict(
+            dd_weight=_f32(self.dd_weight),
+            ep_weight=_f32(self.ep_weight),
+            ekp_weight=_f32(self.ekp_weight),
+            cc_weight=_f32(self.cc_weight),
+            ccrc_weight=_f32(self.ccrc_weight),
+            R=_f32(self.R),
+            MAX_COST=_f32(self.MAX_COST),
+            two_thl=_f32(2.0 * thl),
+            thl_095=_f32(0.95 * thl),
+            thl_005=_f32(0.05 * thl),
+            thl_09=_f32(0.9 * thl),
+            thl_01=_f32(0.1 * thl),
+            target_position=_f32(self.target_position),
+            target_equilibrium=_f32(self.target_equilibrium),
+        )
+
+
+# ----------------------------------------------------------------------------------------------
+# CartPole ODE (explicit Euler on (angle, angleD, position, positionD) with the OLD derivatives)
+# ----------------------------------------------------------------------------------------------
+def cartpole_step(s: torch.Tensor, Q: torch.Tensor, c: dict, intermediate_steps: int = 1) -> torch.Tensor:
+    """One predictor step.  s [N,6] fp32, Q [N,1] fp32 in [-1,1]; returns the next state [N,6]."""
+    angle, angleD, ca, sa, pos, posD = s.unbind(dim=1)
+    u = c["u_max"] * Q[:, 0]
+    h = c["h"]
+    for _ in range(intermediate_steps):
+        A = c["kp1_Mm"] - c["m"] * (ca * ca)
+        F = c["neg_M_fric"] * posD
+        T = c["neg_J_fric"] * angleD
+        posDD = (
+            c["mg"] * sa * ca
+            + (T * ca) / c["L"]
+            + c["kp1"] * (-(c["mL"] * (angleD * angleD) * sa) + F + u)
+        ) / A
+        angleDD = (c["g"] * sa + posDD * ca + T / c["mL"]) / c["kp1L"]
+        angle = angle + angleD * h
+        angleD = angleD + angleDD * h
+        pos = pos + posD * h
+        posD = posD + posDD * h
+        ca = torch.cos(angle)
+        sa = torch.sin(angle)
+        angle = torch.atan2(sa, ca)  # wrap to (-pi, pi]
+    return torch.stack([angle, angleD, ca, sa, pos, posD], dim=1)
+
+
+class ODEPredictor:
+    """``predict_core(s[N,6], Q[N,H,1]) -> [N,H+1,6]`` including s_0 (shape pinned by reference
+    ``optimizer_cem_tf.py:70``)."""
+
+    num_states = NUM_STATES
+    num_control_inputs = NUM_CONTROLS
+
+    def __init__(self, params: CartPoleParams | None = None):
+        self.params = params or CartPoleParams()
+        self.c = self.params.f32()
+
+    def predict_core(self, s: torch.Tensor, Q: torch.Tensor) -> torch.Tensor:
+        out = [s]
+        for t in range(Q.shape[1]):
+            s = cartpole_step(s, Q[:, t, :], self.c, self.params.intermediate_steps)
+            out.append(s)
+        return torch.stack(out, dim=1)
+
+
+# ----------------------------------------------------------------------------------------------
+# MLP autoregressive predictor (config C4)
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class MLPWeights:
+    """Dense 6->H1 tanh -> H2 tanh -> 5 linear.  Row-major [in, out] matrices (y = x @ W + b)."""
+    W1: np.ndarray
+    b1: np.ndarray
+    W2: np.ndarray
+    b2: np.ndarray
+    W3: np.ndarray
+    b3: np.ndarray
+
+    @staticmethod
+    def random_init(seed: int = 2, hidden: int = 128, gain: float = 1.0) -> "MLPWeights":
+        """weights N(0, 1/fan_in), biases 0, default_rng(2)."""
+        rng = np.random.default_rng(seed)
+
+        def w(i, o):
+            return (rng.standard_normal((i, o)) * gain / math.sqrt(i)).astype(np.float32)
+
+        return MLPWeights(
+            W1=w(6, hidden), b1=np.zeros(hidden, np.float32),
+            W2=w(hidden, hidden), b2=np.zeros(hidden, np.float32),
+            W3=w(hidden, 5), b3=np.zeros(5, np.float32),
+        )
+
+
+class MLPPredictor:
+    """net input  = [Q, angleD, angle_cos, angle_sin, position, positionD]   (normalisation = identity)
+    net output = next [angleD, angle_cos, angle_sin, position, positionD]; angle = atan2(sin, cos)."""
+
+    num_states = NUM_STATES
+    num_control_inputs = NUM_CONTROLS
+
+    def __init__(self, weights: MLPWeights):
+        self.w = weights
+        self.t = {k: torch.from_numpy(np.ascontiguousarray(getattr(weights, k))) for k in ("W1", "b1", "W2", "b2", "W3", "b3")}
+
+    def step(self, s: torch.Tensor, Q: torch.Tensor) -> torch.Tensor:
+        x = torch.cat([Q, s[:, 1:]], dim=1)  # [N,6]
+        h1 = torch.tanh(x @ self.t["W1"] + self.t["b1"])
+        h2 = torch.tanh(h1 @ self.t["W2"] + self.t["b2"])
+        y = h2 @ self.t["W3"] + self.t["b3"]  # [N,5]
+        angle = torch.atan2(y[:, 2], y[:, 1])
+        return torch.cat([angle[:, None], y], dim=1)
+
+    def predict_core(self, s: torch.Tensor, Q: torch.Tensor) -> torch.Tensor:
+        out = [s]
+        for t in range(Q.shape[1]):
+            s = self.step(s, Q[:, t, :])
+            out.append(s)
+        return torch.stack(out, dim=1)
+
+
+# ----------------------------------------------------------------------------------------------
+# Cost functions
+# ----------------------------------------------------------------------------------------------
+def _distance_difference_cost(position, c):
+    return ((position - c["target_position"]) / c["two_thl"]) ** 2 + (
+        (torch.abs(position) > c["thl_095"]).to(torch.float32)
+        * 1.0e9
+        * ((torch.abs(position) - c["thl_095"]) / c["thl_005"]) ** 2
+    )
+
+
+def _E_pot_cost(angle, c):
+    return c["target_equilibrium"] * 0.25 * (1.0 - torch.cos(angle)) ** 2
+
+
+def _CC_cost(u, c):
+    return c["R"] * torch.sum(u ** 2, 2)
+
+
+def _control_change_rate_cost(u, u_prev):
+    u_prev_vec = torch.cat([torch.ones((u.shape[0], 1, u.shape[2]), dtype=u.dtype) * u_prev, u[:, :-1, :]], 1)
+    return torch.sum((u - u_prev_vec) ** 2, 2)
+
+
+def stage_cost(states: torch.Tensor, inputs: torch.Tensor, previous_input, cp: CostParams) -> torch.Tensor:
+    """``_get_stage_cost``: states [N,H,6], inputs [N,H,1], previous_input scalar/0-d -> [N,H]."""
+    c = cp.f32()
+    previous_input = torch.as_tensor(previous_input, dtype=torch.float32)
+    dd = c["dd_weight"] * _distance_difference_cost(states[:, :, POSITION], c)
+    ep = c["ep_weight"] * _E_pot_cost(states[:, :, ANGLE], c)
+    cc = c["cc_weight"] * _CC_cost(inputs, c)
+    ccrc = c["ccrc_weight"] * _control_change_rate_cost(inputs, previous_input)
+    if cp.name == "default":
+        return dd + ep + cc + ccrc
+    elif cp.name == "quadratic_boundary_grad":
+        ekp = c["ekp_weight"] * states[:, :, ANGLED] ** 2
+        border = (torch.abs(states[:, :, POSITION]) > c["thl_09"]).to(torch.float32) * 1.0e7
+        return dd + ep + ekp + cc + ccrc + border
+    raise ValueError(f"unknown cost function {cp.name}")
+
+
+def terminal_cost(terminal_states: torch.Tensor, cp: CostParams) -> torch.Tensor:
+    c = cp.f32()
+    return 10000.0 * (
+        (torch.abs(terminal_states[:, ANGLE]) > 0.2)
+        | (torch.abs(terminal_states[:, POSITION] - c["target_position"]) > c["thl_01"])
+    ).to(torch.float32)
+
+
+def trajectory_cost(state_horizon: torch.Tensor, inputs: torch.Tensor, previous_input, cp: CostParams) -> torch.Tensor:
+    """Restates reference ``Cost_Functions/__init__.py:74-93``:
+    mean over H+1 of [stage costs (s_0..s_{H-1} with u_0..u_{H-1}) - MAX_COST, terminal cost(s_H)]."""
+    sc = stage_cost(state_horizon[:, :-1, :], inputs, previous_input, cp) - cp.f32()["MAX_COST"]
+    tc = terminal_cost(state_horizon[:, -1, :], cp).reshape(-1, 1)
+    return torch.mean(torch.cat([sc, tc], 1), 1)
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic inputs
+# ----------------------------------------------------------------------------------------------
+def synthetic_states(n: int, seed: int = 0) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    angle = rng.uniform(-math.pi, math.pi, n)
+    angleD = rng.uniform(-5.0, 5.0, n)
+    position = rng.uniform(-0.15, 0.15, n)
+    positionD = rng.uniform(-0.5, 0.5, n)
+    s = np.stack([angle, angleD, np.cos(angle), np.sin(angle), position, positionD], 1)
+    return s.astype(np.float32)

@@ -1,0 +1,86 @@
+"""CPU tests: the standalone oracle restatements (oracle/mppi.py, cem.py, rpgd.py) against the golden vectors
+produced by the reference's UNMODIFIED files (oracle/gen_golden.py).  Both run torch-CPU fp32 with the same op
+order, so agreement is expected at rounding level; tolerance 2e-6 relative (fixtures were generated
+single-threaded, the test may run with several threads -> different reduction order)."""
+import numpy as np
+import pytest
+
+from helpers import golden_names, load_golden, make_oracle, rel_err, replay
+
+TOL = 2e-6
+
+
+def test_noise_stream_checksum():
+    from oracle.replay_rng import ReplayRNG
+    for name in golden_names():
+        z, meta = load_golden(name)
+        import json
+        r = ReplayRNG(meta["noise_seed"], as_torch=False)
+        acc = 0.0
+        for kind, shape in json.loads(str(z["noise_blocks"])):
+            acc += float(np.sum(r.standard_draws(kind, shape).astype(np.float64)))
+        assert abs(acc - float(z["noise_checksum"][0])) < 1e-6, name
+
+
+@pytest.mark.parametrize("name", golden_names("mppi_"))
+def test_mppi_oracle_matches_reference(name):
+    z, meta = load_golden(name)
+    o = make_oracle(meta)
+    rng = replay(meta)
+    for t in range(meta["ticks"]):
+        u = o.step(z["states"][t], rng)
+        assert rel_err(u, z[f"u_{t}"]) < TOL
+        assert rel_err(o.u_nom.numpy(), z[f"u_nom_{t}"]) < TOL
+        assert rel_err(o.last["J"], z[f"J_{t}"]) < TOL
+        if t == 0 and "rollouts_0" in z:
+            assert rel_err(o.last["rollouts"], z["rollouts_0"]) < TOL
+            assert rel_err(o.last["Q"], z["Q_logged_0"]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names("cem_"))
+def test_cem_oracle_matches_reference(name):
+    z, meta = load_golden(name)
+    o = make_oracle(meta)
+    rng = replay(meta)
+    for t in range(meta["ticks"]):
+        u = o.step(z["states"][t], rng)
+        np.testing.assert_array_equal(o.last["elite_idx"], z[f"elite_idx_{t}"])
+        assert rel_err(u, z[f"u_{t}"]) < TOL
+        assert rel_err(o.dist_mue.numpy(), z[f"dist_mue_{t}"]) < TOL
+        assert rel_err(o.stdev.numpy(), z[f"stdev_{t}"]) < TOL
+        assert rel_err(o.last["J"], z[f"J_{t}"]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names("rpgd_"))
+def test_rpgd_oracle_matches_reference(name):
+    z, meta = load_golden(name)
+    o = make_oracle(meta)
+    rng = replay(meta)
+    o.reset(rng)
+    assert rel_err(o.Q.numpy(), z["Q_init"]) == 0.0
+    for t in range(meta["ticks"]):
+        u = o.step(z["states"][t], rng)
+        assert rel_err(u, z[f"u_{t}"]) < TOL, (t, u, z[f"u_{t}"])
+        assert rel_err(o.Q.numpy(), z[f"Q_{t}"]) < TOL
+        assert rel_err(o.m.numpy(), z[f"adam_m_{t}"]) < 1e-5
+        assert rel_err(o.v.numpy(), z[f"adam_v_{t}"]) < 1e-5
+        assert o.adam_step == int(z[f"adam_step_{t}"][0])
+        np.testing.assert_array_equal(o.ages.numpy(), z[f"ages_{t}"])
+        assert rel_err(o.last["J"], z[f"J_{t}"]) < TOL
+        assert rel_err(o.last["u_nom"], z[f"u_nom_{t}"]) < TOL
+
+
+def test_rpgd_keras_vs_torch_adam_form():
+    """SURVEY.md 8a row a10 expected the Keras-form and torch-form Adam (eps placement: eps vs eps*sqrt(1-b2^t))
+    to agree within 1e-5.  Measured here: they do NOT where |g| ~ 1e-6 (late-horizon controls), the population
+    differs by up to ~3e-3 relative after one tick.  Both forms are therefore implemented and parity-tested
+    separately (torch form vs the unmodified reference file, Keras form vs this oracle); this test only pins the
+    size of the gap so a change in either form is noticed."""
+    z, meta = load_golden("rpgd_c3")
+    o = make_oracle(meta, adam_form="keras")
+    rng = replay(meta)
+    o.reset(rng)
+    for t in range(3):
+        u = o.step(z["states"][t], rng)
+        assert rel_err(u, z[f"u_{t}"]) < 5e-2
+        assert rel_err(o.Q.numpy(), z[f"Q_{t}"]) < 5e-2
