@@ -1,0 +1,246 @@
+"""template_optimizer for the B200 backend.
+
+Mirrors the reference's plugin interface (reference Optimizers/__init__.py:10-79): same constructor contract, same
+``configure(num_states, num_control_inputs, default_configure, **kwargs)``, abstract ``step`` / ``optimizer_reset``,
+``optimizer_name`` property and ``logging_values`` dict.  What differs is underneath: instead of a computation library
+evaluating ``predict_core`` + ``get_trajectory_cost`` op by op, a C handle (libctk_b200.so) owns the optimizer state on
+the GPU and runs the whole tick as fused CUDA kernels.
+
+Noise: ``self.rng`` is ``None`` by default -> counter-based Philox4x32-10 generated in-kernel from ``seed``.
+Assigning an object with ``standard_draws(kind, shape) -> np.ndarray`` (e.g. oracle.replay_rng.ReplayRNG in the tests)
+switches to injected-noise mode: the same standard draws the reference would consume through ``rng.normal`` /
+``rng.uniform`` are uploaded and consumed by the kernels (SURVEY.md section 8c noise-injection contract).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from datetime import datetime
+from typing import Tuple
+
+import numpy as np
+
+from .. import _lib as L
+from .. import specs
+
+
+class template_optimizer:
+    # kept for signature compatibility; this backend does not dispatch on a computation library
+    supported_computation_libraries = (object,)
+    _OPT = None  # L.OPT_*
+
+    def __init__(
+        self,
+        predictor,
+        cost_function,
+        control_limits: "Tuple[np.ndarray, np.ndarray]",
+        optimizer_logging: bool,
+        seed: int,
+        num_rollouts: int,
+        mpc_horizon: int,
+        computation_library=None,
+        **kwargs,
+    ) -> None:
+        self.lib = computation_library
+        self.num_rollouts = int(num_rollouts)
+        self.mpc_horizon = int(mpc_horizon)
+        self.cost_function = cost_function
+        self.u = 0.0
+        self.predictor = predictor
+        self.num_states = None
+        self.num_control_inputs = None
+        self.action_low, self.action_high = (np.atleast_1d(np.asarray(a, dtype=np.float32)) for a in control_limits)
+        if seed is None:  # reference others/globals_and_utils.py:87-91
+            seed = int((datetime.now() - datetime(1970, 1, 1)).total_seconds() * 1000.0)
+        self.seed = int(seed)
+        self.rng = None  # None -> in-kernel Philox; object with standard_draws() -> injected noise
+        self.logging_values = {}
+        self.optimizer_logging = bool(optimizer_logging)
+        # backend options (not in the reference; all optional)
+        self.device = int(kwargs.pop("device_index", 0))
+        self.freeze_previous_input = bool(kwargs.pop("freeze_previous_input", False))
+        self.mlp_engine = str(kwargs.pop("mlp_engine", "simt"))
+        self.shard = kwargs.pop("shard", None)  # control_toolkit_b200.distributed.ShardPlan or None
+        self.environment_name = kwargs.pop("environment_name", None)
+        self._h = None
+        self._cost_spec = None
+        self._cost_live = (None, None)
+        self._dt = None
+
+    # -- reference API -----------------------------------------------------------------------------------------
+    def configure(self, num_states: int, num_control_inputs: int, default_configure: bool = True, **kwargs) -> None:
+        self.num_states = num_states
+        self.num_control_inputs = num_control_inputs
+        if default_configure:
+            self.optimizer_reset()
+
+    def step(self, s: np.ndarray, time=None):
+        raise NotImplementedError("Implement this function in a subclass.")
+
+    def optimizer_reset(self):
+        raise NotImplementedError("Implement this function in a subclass.")
+
+    @property
+    def optimizer_name(self):
+        name = self.__class__.__name__
+        if name != "template_optimizer":
+            return name.replace("optimizer_", "").replace("_", "-").lower()
+        else:
+            raise AttributeError()
+
+    # -- backend plumbing --------------------------------------------------------------------------------------
+    def _fill_config(self, cfg: L.ctk_config) -> None:
+        """Subclasses add their optimizer-specific fields."""
+        raise NotImplementedError
+
+    def _environment(self) -> str:
+        return (self.environment_name or getattr(self.cost_function, "environment_name", None) or "CartPole")
+
+    def _live_targets(self):
+        vp = getattr(self.cost_function, "variable_parameters", None)
+        tp = float(getattr(vp, "target_position", 0.0)) if vp is not None else 0.0
+        te = float(getattr(vp, "target_equilibrium", 1.0)) if vp is not None else 1.0
+        return tp, te
+
+    def _create_backend(self, dt: float, predictor_specification: str) -> None:
+        if dt is None or predictor_specification is None:
+            raise ValueError(f"{self.__class__.__name__} requires dt and predictor_specification to be passed.")
+        lib = L.load()
+        env = self._environment()
+        cost_name = getattr(self.cost_function, "cost_function_name", None) or "default"
+        overrides = dict(specs.cost_overrides_from_yaml(env, cost_name))
+        overrides.update(getattr(self.cost_function, "weights", None) or {})
+        self._cost_spec = specs.resolve_cost(env, cost_name, overrides)
+        pred_kind, pred_spec = specs.resolve_predictor(env, predictor_specification)
+        ode_spec = pred_spec if pred_kind == L.PRED_ODE else specs.ODE_REGISTRY.get(env, specs.CartPoleODE())
+        self._dt = float(dt)
+
+        cfg = L.ctk_config()
+        cfg.abi_version = L.CTK_ABI_VERSION
+        cfg.optimizer = self._OPT
+        cfg.predictor = pred_kind
+        cfg.device = self.device
+        n_glob = self.num_rollouts
+        if self.shard is not None:
+            cfg.num_rollouts, cfg.rollout_offset = self.shard.local_count(n_glob), self.shard.local_offset(n_glob)
+        else:
+            cfg.num_rollouts, cfg.rollout_offset = n_glob, 0
+        cfg.num_rollouts_global = n_glob
+        cfg.mpc_horizon = self.mpc_horizon
+        cfg.num_states = int(self.num_states)
+        cfg.num_control_inputs = int(self.num_control_inputs)
+        if self.action_low.size != 1 or self.action_high.size != 1:
+            raise ValueError("only single-input environments have registered CUDA functors")
+        cfg.action_low, cfg.action_high = float(self.action_low[0]), float(self.action_high[0])
+        cfg.seed = self.seed & 0xFFFFFFFFFFFFFFFF
+        cfg.logging = int(self.optimizer_logging)
+        cfg.freeze_previous_input = int(self.freeze_previous_input)
+        cfg.mlp_engine = {"simt": L.MLP_SIMT, "tcgen05": L.MLP_TCGEN05}[self.mlp_engine]
+        self._fill_config(cfg)
+
+        tp, te = self._live_targets()
+        self._cost_live = (tp, te)
+        ode_c, cost_c = ode_spec.to_c(self._dt), self._cost_spec.to_c(tp, te)
+        if self._h is not None:
+            lib.ctk_destroy(self._h)
+            self._h = None
+        h = C.c_void_p()
+        L.check(lib.ctk_create(C.byref(cfg), C.byref(ode_c), C.byref(cost_c), C.byref(h)))
+        self._h = h
+        self._cfg = cfg
+        self._n_local = int(cfg.num_rollouts)
+        if pred_kind == L.PRED_MLP:
+            self._mlp_keepalive = pred_spec
+            w = pred_spec.to_c()
+            L.check(lib.ctk_set_mlp_weights(self._h, C.byref(w)))
+        self._u_buf = np.zeros(1, np.float32)
+
+    def _require_backend(self):
+        if self._h is None:
+            raise RuntimeError(f"{self.__class__.__name__}.configure() has not been called")
+        return L.load()
+
+    def _refresh_live_cost(self, lib) -> None:
+        """target_position / target_equilibrium may change between ticks (controller update_attributes,
+        reference Controllers/__init__.py:106-107)."""
+        live = self._live_targets()
+        if live != self._cost_live:
+            c = self._cost_spec.to_c(*live)
+            L.check(lib.ctk_set_cost_params(self._h, C.byref(c)))
+            self._cost_live = live
+
+    def _feed_noise(self, lib, blocks) -> None:
+        """blocks: list of (kind, shape) standard-draw blocks this call will consume, in order."""
+        if self.rng is None:
+            return
+        if not hasattr(self.rng, "standard_draws"):
+            raise TypeError("optimizer.rng must be None (in-kernel Philox) or provide standard_draws(kind, shape)")
+        for kind, shape in blocks:
+            z = np.ascontiguousarray(self.rng.standard_draws(kind, shape), dtype=np.float32).ravel()
+            L.check(lib.ctk_push_injected_noise(self._h, L.fptr(z), z.size))
+
+    def _tick(self, lib, s: np.ndarray) -> np.ndarray:
+        s32 = np.ascontiguousarray(np.asarray(s, dtype=np.float32).reshape(-1))
+        if s32.size != 6:
+            raise ValueError(f"state must have {6} entries, got {s32.size}")
+        if self.shard is not None and self.shard.world_size > 1:
+            return self.shard.run_tick(self, lib, s32)
+        L.check(lib.ctk_step(self._h, L.fptr(s32), L.fptr(self._u_buf)))
+        return self._u_buf.copy()
+
+    # -- state / logs ------------------------------------------------------------------------------------------
+    def _get_state(self, which: int, shape) -> np.ndarray:
+        lib = self._require_backend()
+        out = np.empty(int(np.prod(shape)), np.float32)
+        L.check(lib.ctk_get_state(self._h, which, L.fptr(out), out.size))
+        return out.reshape(shape)
+
+    def _set_state(self, which: int, value) -> None:
+        lib = self._require_backend()
+        a = np.ascontiguousarray(np.asarray(value, dtype=np.float32)).ravel()
+        L.check(lib.ctk_set_state(self._h, which, L.fptr(a), a.size))
+
+    def _get_counter(self, which: int) -> int:
+        lib = self._require_backend()
+        v = C.c_int64()
+        L.check(lib.ctk_get_counter(self._h, which, C.byref(v)))
+        return int(v.value)
+
+    def _set_counter(self, which: int, value: int) -> None:
+        lib = self._require_backend()
+        L.check(lib.ctk_set_counter(self._h, which, int(value)))
+
+    def _get_log(self, which: int, shape, dtype=np.float32) -> np.ndarray:
+        lib = self._require_backend()
+        out = np.empty(int(np.prod(shape)), dtype)
+        L.check(lib.ctk_get_log(self._h, which, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out.reshape(shape)
+
+    @property
+    def gpu_launches(self) -> int:
+        lib = self._require_backend()
+        v = C.c_int64()
+        L.check(lib.ctk_get_launch_count(self._h, C.byref(v)))
+        return int(v.value)
+
+    def rollout_single(self, s: np.ndarray, Q: np.ndarray):
+        """Nominal rollout of one control sequence -> (trajectory [1,H+1,ns], summed stage cost)."""
+        lib = self._require_backend()
+        s32 = np.ascontiguousarray(np.asarray(s, np.float32).reshape(-1))
+        q32 = np.ascontiguousarray(np.asarray(Q, np.float32).reshape(-1))
+        traj = np.empty((self.mpc_horizon + 1) * 6, np.float32)
+        summed = np.zeros(1, np.float32)
+        L.check(lib.ctk_rollout_single(self._h, L.fptr(s32), L.fptr(q32), L.fptr(traj), L.fptr(summed)))
+        return traj.reshape(1, self.mpc_horizon + 1, 6), summed
+
+    def close(self):
+        if self._h is not None:
+            try:
+                L.load().ctk_destroy(self._h)
+            finally:
+                self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,129 @@
+// ctk_args.cuh -- plain argument blocks shared by the host-side engine (ctk_engine.cu) and the kernel translation
+// units.  No device code here.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#include "ctk_math.cuh"
+
+namespace ctk {
+
+enum : uint32_t { STREAM_MPPI = 0, STREAM_CEM = 1, STREAM_RPGD_INIT = 2, STREAM_RPGD_RESAMPLE = 3 };
+
+struct NoiseSrc {
+  const float* inj;   // != nullptr: injected standard draws, row-major [N_global, per_rollout]; else Philox
+  uint32_t key0, key1;  // seed
+  uint32_t tick;        // counter word 2
+  uint32_t stream;      // counter word 3 (STREAM_* + sub-iteration << 8)
+  int per_rollout;      // draws per rollout in this block of noise
+  int uniform;          // 0: N(0,1)  1: U[0,1)
+};
+
+struct MlpDev {
+  int hidden;              // <= 128, multiple of 16
+  const float* blob;       // device: W1[6][hid] | b1[hid] | W2[hid][hid] | b2[hid] | W3T[5][hid] | b3[8]
+  int blob_floats;
+};
+
+__host__ __device__ inline int mlp_blob_floats(int hid) { return 6 * hid + hid + hid * hid + hid + 5 * hid + 8; }
+
+struct MppiArgs {
+  int N, off, H, period, n_ind;  // local rollouts, global id offset, horizon, inducing-point period / count
+  const float* s0;               // [6] device
+  const float* u_nom;            // [H] device, UNSHIFTED state of the previous tick (shift applied on read, :184)
+  const float* u_prev;           // [1] device, previous_input of the cost (self.u, :211)
+  NoiseSrc noise;                // per_rollout = n_ind
+  float stdev, lo, hi;           // SQRTRHODTINV (:130), control limits
+  float coef_du2, R, half_R, cc_weight, neg_inv_lbd;  // :154-155, :165
+  OdeC ode;
+  CostC cost;
+  MlpDev mlp;
+  float* J;                      // [N] out: total MPPI cost S
+  float* partials;               // [gridDim.x][2 + n_ind] out: rho_b, a_b, b_z[n_ind]
+  float* log_traj_soa;           // [(H+1)][6][N] or null
+  float* log_Q_soa;              // [H][N] or null
+};
+
+// K2: combine `cnt` softmin records [rho, a, b_z[n_ind]] (block partials or per-shard records) into one record;
+// if fin.enable, finish the tick: u_nom <- clip(shift(u_nom) + interp(b_z) * stdev / a)  (optimizer_mppi.py:190-191)
+struct MppiFinalize {
+  int enable;
+  int H, period, n_ind;
+  float stdev, lo, hi, neg_inv_lbd;
+  float* u_nom;   // [H] in/out
+  float* u_prev;  // [1] out (unless frozen)
+  float* u_out;   // [1] out or null
+  int freeze_prev;
+};
+
+struct CemArgs {
+  int N, off, H;
+  const float* s0;      // [6]
+  const float* mu;      // [H] dist_mue
+  const float* sd;      // [H] stdev
+  const float* u_prev;  // [1]
+  NoiseSrc noise;       // per_rollout = H
+  float lo, hi;
+  OdeC ode;
+  CostC cost;
+  MlpDev mlp;
+  float* J;             // [N]
+  float* log_traj_soa;  // [(H+1)][6][N] or null
+  float* log_Q_soa;     // [H][N] or null
+};
+
+struct CemRefitArgs {
+  int H, k, cnt;             // cnt candidate keys (num_shards * k, each shard's list sorted or not)
+  const uint64_t* cand;      // [cnt] (ordered cost, global id)
+  NoiseSrc noise;            // the SAME noise block the rollouts consumed: elite Q rows are regenerated, never stored
+  float lo, hi;
+  float* mu;                 // [H] in/out
+  float* sd;                 // [H] in/out
+  int last;                  // 1: apply the post-loop clip/shift of optimizer_cem_tf.py:99-102
+  float sd_min, sd_init;
+  float* u_prev;             // [1]
+  float* u_out;              // [1] or null
+  int freeze_prev;
+  int32_t* elite_idx_out;    // [k] global ids, best first (log) or null
+};
+
+struct RpgdGradArgs {
+  int N, H, iters;
+  const float* s0;      // [6]
+  const float* u_prev;  // [1] previous_input (self.u)
+  float* Q;             // [H][N] in/out
+  float* m;             // [H][N] in/out
+  float* v;             // [H][N] in/out
+  float lo, hi;
+  float lr, gradmax_clip;
+  double beta1, beta2, eps;
+  long long adam_step0;  // global step counter before this tick's first gradient step
+  int adam_form;         // 0 Keras, 1 torch
+  OdeC ode;
+  CostC cost;
+  float* J;              // [N] cost of the final (get_action) rollout
+  float* log_traj_soa;   // [(H+1)][6][N] or null
+};
+
+struct RpgdSelectArgs {
+  int N, H, k, period, n_ind;
+  int shift_previous;
+  int resample;            // count % resamp_per == 0
+  const float* J;          // [N]
+  const float *Q, *m, *v;  // [H][N] current
+  const float* ages;       // [N]
+  float *Qn, *mn, *vn;     // [H][N] next
+  float* agesn;            // [N]
+  NoiseSrc noise;          // resample draws, per_rollout = n_ind, rows 0..N-k-1
+  int dist;                // 0 normal, 1 uniform
+  float s_mean, s_std, s_min, s_max, lo, hi;
+  float* u_nom_out;        // [H] Q[best_idx[0]] BEFORE the shift (optimal_control_sequence, :426)
+  float* u_prev;           // [1]
+  float* u_out;            // [1] or null
+  int freeze_prev;
+  int32_t* best_idx_out;   // [k]
+};
+
+constexpr int TOPK_THREADS = 1024;  // keys per top-k block
+
+}  // namespace ctk

@@ -1,0 +1,47 @@
+// ctk_cem.cu -- translation unit owning the CEM kernels (K3 rollout, K4 top-k levels, K5 refit).
+#include "ctk_kernels_cem.cuh"
+#include "ctk_launch.h"
+
+namespace ctk {
+
+template <class Pred, int KIND, bool LOG>
+static cudaError_t launch_cem_t(int nblocks, size_t smem, cudaStream_t st, const CemArgs& a) {
+  auto k = cem_rollout_kernel<Pred, KIND, LOG>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k<<<nblocks, 128, smem, st>>>(a);
+  return cudaGetLastError();
+}
+template <class Pred>
+static cudaError_t launch_cem_p(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemArgs& a) {
+  if (kind == 0) return log ? launch_cem_t<Pred, 0, true>(nblocks, smem, st, a) : launch_cem_t<Pred, 0, false>(nblocks, smem, st, a);
+  return log ? launch_cem_t<Pred, 1, true>(nblocks, smem, st, a) : launch_cem_t<Pred, 1, false>(nblocks, smem, st, a);
+}
+cudaError_t launch_cem_rollout(int pred, int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemArgs& a) {
+  return pred == 0 ? launch_cem_p<OdePred>(kind, log, nblocks, smem, st, a) : launch_cem_p<MlpSimtPred>(kind, log, nblocks, smem, st, a);
+}
+// Level 0: keys from costs (global index = off + i).  Each block sorts 1024 keys and emits its k smallest.
+// Level >0: same on candidate keys.  out has gridDim.x * k keys.
+__global__ void __launch_bounds__(TOPK_THREADS) topk_level_kernel(const float* __restrict__ cost, const uint64_t* __restrict__ keys_in,
+                                                                   int n, int off, int k, uint64_t* __restrict__ out) {
+  __shared__ uint64_t sh[TOPK_THREADS];
+  const int i = blockIdx.x * TOPK_THREADS + threadIdx.x;
+  uint64_t key = KEY_MAX;
+  if (i < n) key = (cost != nullptr) ? make_key(cost[i], (uint32_t)(off + i)) : keys_in[i];
+  key = block_bitonic_sort(key, sh);
+  if (threadIdx.x < k) out[(size_t)blockIdx.x * k + threadIdx.x] = key;
+}
+
+cudaError_t launch_topk_level(const float* cost, const uint64_t* keys_in, int n, int off, int k, uint64_t* out, cudaStream_t st) {
+  const int nb = (n + TOPK_THREADS - 1) / TOPK_THREADS;
+  topk_level_kernel<<<nb, TOPK_THREADS, 0, st>>>(cost, keys_in, n, off, k, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_cem_refit(const CemRefitArgs& a, cudaStream_t st) {
+  cem_refit_kernel<<<1, TOPK_THREADS, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace ctk

@@ -1,0 +1,132 @@
+// ctk_device.cuh -- device-only helpers: Philox4x32-10 counter-based noise (K0), injected-noise loader,
+// warp-shuffle block reductions, ordered keys for top-k.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ctk_args.cuh"
+
+namespace ctk {
+
+// ----------------------------------------------------------------------------------------------------------
+// K0: Philox4x32-10 (Salmon et al. 2011), the generator behind tf.random.Generator.from_seed
+// (reference others/globals_and_utils.py:95-97).  Counter words: (draw block, global rollout id, tick, stream).
+// TF's exact stream cannot be reproduced offline, so parity is defined under injected noise only; this
+// generator is validated statistically (tests/test_philox.py) and against a numpy Philox restatement.
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+// four consecutive standard draws (index 4*blk .. 4*blk+3) of global rollout n
+__device__ __forceinline__ void noise4(const NoiseSrc& ns, uint32_t n_global, uint32_t blk, float out[4]) {
+  if (ns.inj != nullptr) {
+    const float* row = ns.inj + (size_t)n_global * ns.per_rollout;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = (int)blk * 4 + q;
+      out[q] = (i < ns.per_rollout) ? __ldg(row + i) : 0.0f;
+    }
+    return;
+  }
+  const uint4 r = philox4x32_10(make_uint4(blk, n_global, ns.tick, ns.stream), make_uint2(ns.key0, ns.key1));
+  if (ns.uniform) {
+    out[0] = (float)(r.x >> 8) * 5.9604644775390625e-8f;  // [0,1), 24 bits
+    out[1] = (float)(r.y >> 8) * 5.9604644775390625e-8f;
+    out[2] = (float)(r.z >> 8) * 5.9604644775390625e-8f;
+    out[3] = (float)(r.w >> 8) * 5.9604644775390625e-8f;
+  } else {
+    // Box-Muller on (0,1] x [-0.5,0.5): statistical quality only (no parity requirement on this branch)
+    const float u1 = fmaf((float)(r.x >> 8), 5.9604644775390625e-8f, 5.9604644775390625e-8f);
+    const float u3 = fmaf((float)(r.z >> 8), 5.9604644775390625e-8f, 5.9604644775390625e-8f);
+    const float a2 = ((float)(int32_t)r.y) * 1.4629180792671596e-9f;  // 2*pi * y / 2^32 in [-pi, pi)
+    const float a4 = ((float)(int32_t)r.w) * 1.4629180792671596e-9f;
+    const float r1 = sqrtf(-2.0f * __logf(u1));
+    const float r3 = sqrtf(-2.0f * __logf(u3));
+    float s2, c2, s4, c4;
+    __sincosf(a2, &s2, &c2);
+    __sincosf(a4, &s4, &c4);
+    out[0] = r1 * c2;
+    out[1] = r1 * s2;
+    out[2] = r3 * c4;
+    out[3] = r3 * s4;
+  }
+}
+
+// single draw i of rollout n (slow path, used where draws are needed one at a time)
+__device__ __forceinline__ float noise1(const NoiseSrc& ns, uint32_t n_global, int i) {
+  if (ns.inj != nullptr) return __ldg(ns.inj + (size_t)n_global * ns.per_rollout + i);
+  float z[4];
+  noise4(ns, n_global, (uint32_t)(i >> 2), z);
+  const int q = i & 3;
+  return q == 0 ? z[0] : (q == 1 ? z[1] : (q == 2 ? z[2] : z[3]));
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// reductions
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide min / sum for blockDim.x <= 1024 (multiple of 32); scratch >= 32 floats; result broadcast to all threads
+__device__ __forceinline__ float block_min(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_min(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? scratch[lane] : INFINITY;
+  return warp_min(r);
+}
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? scratch[lane] : 0.0f;
+  return warp_sum(r);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// ordered 64-bit key (cost, index): ascending cost, ties -> lower index first (tf.argsort == top_k(-x) semantics)
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t o) {
+  const uint32_t b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  return __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t make_key(float cost, uint32_t idx) {
+  if (cost != cost) cost = INFINITY;  // NaN sorts last
+  if (cost == 0.0f) cost = 0.0f;      // -0 == +0
+  return ((uint64_t)float_to_ordered(cost) << 32) | idx;
+}
+constexpr uint64_t KEY_MAX = ~0ull;
+
+// interpolation weights of reference others/Interpolator.py:63-74: (step - j)/step and j/step in fp32
+__device__ __forceinline__ void interp_weights(int j, int period, float* w0, float* w1) {
+  *w0 = (float)(period - j) / (float)period;
+  *w1 = (float)j / (float)period;
+}
+
+}  // namespace ctk

@@ -1,0 +1,777 @@
+// ctk_engine.cu -- the C ABI of libctk_b200.so (include/ctk_b200.h): handle, device buffers, per-tick launch
+// sequences for MPPI / CEM / RPGD.  No torch types, no CPU fallback: every entry point fails if CUDA does.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ctk_b200.h"
+#include "ctk_derive.h"
+#include "ctk_launch.h"
+#include "ctk_mlp_tc.cuh"
+
+using namespace ctk;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t _e = (call);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return fail(CTK_ECUDA, std::string(#call) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                                 std::to_string(__LINE__) + ")");                                    \
+  } while (0)
+#define REQ(cond, msg) \
+  do {                 \
+    if (!(cond)) return fail(CTK_EINVAL, std::string("invalid argument: ") + (msg)); \
+  } while (0)
+
+struct ctk_handle {
+  ctk_config cfg;
+  OdeC ode;
+  CostC cost;
+  MlpDev mlp;
+  cudaStream_t stream = nullptr;
+  int N = 0, NG = 0, off = 0, H = 0, period = 1, n_ind = 0, nblocks = 0;
+  // common
+  float *d_s0 = nullptr, *d_u_prev = nullptr, *d_u_out = nullptr, *d_J = nullptr;
+  float *h_pin = nullptr;  // pinned staging: s[8] | u[8]
+  // mppi
+  float *d_u_nom = nullptr, *d_partials = nullptr, *d_record = nullptr;
+  // cem
+  float *d_mu = nullptr, *d_sd = nullptr;
+  uint64_t *d_keys[2] = {nullptr, nullptr};
+  int32_t* d_elite_idx = nullptr;
+  int elite_log_cap = 0, elite_log_rows = 0;
+  int cem_it = 0, cem_iters = 0, cem_cand = 0;
+  uint64_t* cem_cand_ptr = nullptr;
+  NoiseSrc cem_noise{};
+  // rpgd
+  float *d_Q[2] = {nullptr, nullptr}, *d_m[2] = {nullptr, nullptr}, *d_v[2] = {nullptr, nullptr}, *d_ages[2] = {nullptr, nullptr};
+  int cur = 0;
+  float *d_unom_log = nullptr, *d_ages_log = nullptr, *d_Q_log = nullptr;
+  int32_t* d_best_idx = nullptr;
+  // logs
+  float *d_log_traj_soa = nullptr, *d_log_Q_soa = nullptr, *d_log_tmp = nullptr;
+  // injected noise queue
+  float* d_inj = nullptr;
+  size_t inj_cap = 0, inj_size = 0, inj_pos = 0;
+  // mlp
+  float* d_mlp = nullptr;
+  MlpTcDev mlp_tc{};
+  // counters
+  int64_t count = 0, adam_step = 0, tick = 0, launches = 0;
+  bool was_reset = false;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t dalloc(T** p, size_t n) {
+  cudaError_t e = cudaMalloc((void**)p, (n ? n : 1) * sizeof(T));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, (n ? n : 1) * sizeof(T));
+  return e;
+}
+
+// Noise source for one consumer: the next rows*per_rollout injected draws if the queue is non-empty (error if it
+// holds fewer), else in-kernel Philox.
+static int make_noise(ctk_handle* h, uint32_t stream_id, int per_rollout, int uniform, size_t rows, NoiseSrc* out) {
+  NoiseSrc ns{};
+  ns.key0 = (uint32_t)(h->cfg.seed & 0xffffffffull);
+  ns.key1 = (uint32_t)(h->cfg.seed >> 32);
+  ns.tick = (uint32_t)h->tick;
+  ns.stream = stream_id;
+  ns.per_rollout = per_rollout;
+  ns.uniform = uniform;
+  ns.inj = nullptr;
+  const size_t need = rows * (size_t)per_rollout;
+  if (h->inj_size > h->inj_pos && need > 0) {
+    if (h->inj_size - h->inj_pos < need)
+      return fail(CTK_EINVAL, "injected-noise queue holds " + std::to_string(h->inj_size - h->inj_pos) + " draws, this consumer needs " +
+                                  std::to_string(need));
+    ns.inj = h->d_inj + h->inj_pos;
+    h->inj_pos += need;
+  }
+  *out = ns;
+  return CTK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// lifecycle
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" const char* ctk_last_error(void) { return g_err.c_str(); }
+extern "C" int ctk_abi_version(void) { return CTK_ABI_VERSION; }
+
+extern "C" int ctk_destroy(ctk_handle* h) {
+  if (!h) return CTK_OK;
+  cudaSetDevice(h->cfg.device);
+  float* fp[] = {h->d_s0, h->d_u_prev, h->d_u_out, h->d_J, h->d_u_nom, h->d_partials, h->d_record, h->d_mu, h->d_sd,
+                 h->d_Q[0], h->d_Q[1], h->d_m[0], h->d_m[1], h->d_v[0], h->d_v[1], h->d_ages[0], h->d_ages[1],
+                 h->d_unom_log, h->d_ages_log, h->d_Q_log, h->d_log_traj_soa, h->d_log_Q_soa, h->d_log_tmp, h->d_inj, h->d_mlp};
+  for (float* p : fp) if (p) cudaFree(p);
+  if (h->d_keys[0]) cudaFree(h->d_keys[0]);
+  if (h->d_keys[1]) cudaFree(h->d_keys[1]);
+  if (h->d_elite_idx) cudaFree(h->d_elite_idx);
+  if (h->d_best_idx) cudaFree(h->d_best_idx);
+  mlp_tc_free(h->mlp_tc);
+  if (h->h_pin) cudaFreeHost(h->h_pin);
+  delete h;
+  return CTK_OK;
+}
+
+extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, const ctk_cost_params* cost, ctk_handle** out) {
+  REQ(cfg && ode && cost && out, "null pointer");
+  REQ(cfg->abi_version == CTK_ABI_VERSION, "abi_version mismatch");
+  REQ(cfg->optimizer >= CTK_OPT_MPPI && cfg->optimizer <= CTK_OPT_RPGD, "unknown optimizer");
+  REQ(cfg->predictor == CTK_PRED_ODE || cfg->predictor == CTK_PRED_MLP, "unknown predictor");
+  REQ(cfg->num_states == 6 && cfg->num_control_inputs == 1,
+      "only the registered CartPole environment (6 states, 1 control) has device functors");
+  REQ(cfg->num_rollouts >= 1 && cfg->mpc_horizon >= 1, "num_rollouts and mpc_horizon must be >= 1");
+  REQ(cfg->num_rollouts_global >= cfg->num_rollouts && cfg->rollout_offset >= 0 &&
+          cfg->rollout_offset + cfg->num_rollouts <= cfg->num_rollouts_global, "bad shard geometry");
+  REQ(cost->kind == CTK_COST_DEFAULT || cost->kind == CTK_COST_QUADRATIC_BOUNDARY_GRAD, "unregistered cost function");
+  REQ(cfg->action_low <= cfg->action_high, "action_low > action_high");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  REQ(cfg->device >= 0 && cfg->device < ndev, "no such CUDA device");
+  CU(cudaSetDevice(cfg->device));
+
+  ctk_handle* h = new ctk_handle();
+  h->cfg = *cfg;
+  h->N = cfg->num_rollouts; h->NG = cfg->num_rollouts_global; h->off = cfg->rollout_offset; h->H = cfg->mpc_horizon;
+  derive_ode(*ode, h->ode);
+  derive_cost(*cost, h->H, h->cost);
+  h->mlp = MlpDev{0, nullptr, 0};
+  h->nblocks = (h->N + 127) / 128;
+  const int N = h->N, H = h->H;
+  int rc = CTK_OK;
+  auto A = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && rc == CTK_OK) rc = fail(CTK_ECUDA, std::string("cudaMalloc ") + what + ": " + cudaGetErrorString(e));
+  };
+  A(dalloc(&h->d_s0, 8), "s0"); A(dalloc(&h->d_u_prev, 1), "u_prev"); A(dalloc(&h->d_u_out, 4), "u_out");
+  A(dalloc(&h->d_J, (size_t)N), "J");
+  A(cudaMallocHost((void**)&h->h_pin, 16 * sizeof(float)), "pinned");
+  if (cfg->logging) {
+    A(dalloc(&h->d_log_traj_soa, (size_t)(H + 1) * 6 * N), "log_traj");
+    A(dalloc(&h->d_log_Q_soa, (size_t)H * N), "log_Q");
+    A(dalloc(&h->d_log_tmp, (size_t)(H + 1) * 6 * N), "log_tmp");
+  }
+  if (cfg->optimizer == CTK_OPT_MPPI || cfg->optimizer == CTK_OPT_RPGD) {
+    h->period = cfg->period_interpolation_inducing_points;
+    if (h->period < 1) { ctk_destroy(h); return fail(CTK_EINVAL, "period_interpolation_inducing_points must be >= 1"); }
+    h->n_ind = (int)std::ceil((double)(H - 1) / (double)h->period) + 1;  // Interpolator.py:79-84
+  }
+  if (cfg->optimizer == CTK_OPT_MPPI) {
+    A(dalloc(&h->d_u_nom, (size_t)H), "u_nom");
+    A(dalloc(&h->d_partials, (size_t)h->nblocks * (h->n_ind + 2)), "partials");
+    A(dalloc(&h->d_record, (size_t)(h->n_ind + 2)), "record");
+  } else if (cfg->optimizer == CTK_OPT_CEM) {
+    if (!(cfg->cem_best_k >= 1 && cfg->cem_best_k <= 512 && cfg->cem_best_k <= cfg->num_rollouts_global && H <= 1024 && cfg->cem_outer_it >= 1)) {
+      ctk_destroy(h);
+      return fail(CTK_EINVAL, "CEM needs 1 <= cem_best_k <= min(512, num_rollouts), mpc_horizon <= 1024, cem_outer_it >= 1");
+    }
+    A(dalloc(&h->d_mu, (size_t)H), "mu"); A(dalloc(&h->d_sd, (size_t)H), "sd");
+    const size_t nk = (size_t)((N + 1023) / 1024) * cfg->cem_best_k + 1024;
+    A(dalloc(&h->d_keys[0], nk), "keys0"); A(dalloc(&h->d_keys[1], nk), "keys1");
+    int iters = cfg->cem_outer_it;
+    if (cfg->cem_warmup && cfg->cem_warmup_iterations > iters) iters = cfg->cem_warmup_iterations;
+    h->elite_log_cap = iters;
+    A(dalloc(&h->d_elite_idx, (size_t)iters * cfg->cem_best_k), "elite_idx");
+  } else {
+    if (!(N <= 1024 && cfg->rpgd_keep_k >= 1 && cfg->rpgd_keep_k <= N && N == h->NG && cfg->predictor == CTK_PRED_ODE &&
+          ode->intermediate_steps <= 1 && cfg->rpgd_shift_previous >= 0)) {
+      ctk_destroy(h);
+      return fail(CTK_EINVAL, "RPGD needs num_rollouts <= 1024 (replicas only, no sharding), the ODE predictor with "
+                              "intermediate_steps == 1 and 1 <= keep_k <= num_rollouts");
+    }
+    for (int i = 0; i < 2; ++i) {
+      A(dalloc(&h->d_Q[i], (size_t)N * H), "Q"); A(dalloc(&h->d_m[i], (size_t)N * H), "m");
+      A(dalloc(&h->d_v[i], (size_t)N * H), "v"); A(dalloc(&h->d_ages[i], (size_t)N), "ages");
+    }
+    A(dalloc(&h->d_unom_log, (size_t)H), "unom_log"); A(dalloc(&h->d_ages_log, (size_t)N), "ages_log");
+    A(dalloc(&h->d_Q_log, (size_t)N * H), "Q_log");
+    A(dalloc(&h->d_best_idx, (size_t)N), "best_idx");
+  }
+  if (rc != CTK_OK) { std::string keep = g_err; ctk_destroy(h); g_err = keep; return rc; }
+  *out = h;
+  return CTK_OK;
+}
+
+extern "C" int ctk_set_stream(ctk_handle* h, void* s) { REQ(h, "null handle"); h->stream = (cudaStream_t)s; return CTK_OK; }
+extern "C" int ctk_set_cost_params(ctk_handle* h, const ctk_cost_params* c) {
+  REQ(h && c, "null pointer");
+  REQ(c->kind == CTK_COST_DEFAULT || c->kind == CTK_COST_QUADRATIC_BOUNDARY_GRAD, "unregistered cost function");
+  derive_cost(*c, h->H, h->cost);
+  return CTK_OK;
+}
+extern "C" int ctk_set_ode_params(ctk_handle* h, const ctk_ode_params* o) {
+  REQ(h && o, "null pointer");
+  REQ(!(h->cfg.optimizer == CTK_OPT_RPGD && o->intermediate_steps > 1), "RPGD adjoint supports intermediate_steps == 1");
+  derive_ode(*o, h->ode);
+  return CTK_OK;
+}
+
+extern "C" int ctk_set_mlp_weights(ctk_handle* h, const ctk_mlp_weights* w) {
+  REQ(h && w && w->W1 && w->b1 && w->W2 && w->b2 && w->W3 && w->b3, "null pointer");
+  REQ(w->hidden >= 16 && w->hidden <= 128 && w->hidden % 16 == 0, "hidden must be a multiple of 16 in [16,128]");
+  CU(cudaSetDevice(h->cfg.device));
+  const int hid = w->hidden, nf = mlp_blob_floats(hid);
+  std::vector<float> blob((size_t)nf, 0.0f);
+  float* p = blob.data();
+  memcpy(p, w->W1, sizeof(float) * 6 * hid); p += 6 * hid;
+  memcpy(p, w->b1, sizeof(float) * hid); p += hid;
+  memcpy(p, w->W2, sizeof(float) * hid * hid); p += hid * hid;
+  memcpy(p, w->b2, sizeof(float) * hid); p += hid;
+  for (int k = 0; k < 5; ++k) for (int j = 0; j < hid; ++j) p[k * hid + j] = w->W3[j * 5 + k];  // W3T[5][hid]
+  p += 5 * hid;
+  memcpy(p, w->b3, sizeof(float) * 5);
+  if (h->d_mlp) { cudaFree(h->d_mlp); h->d_mlp = nullptr; }
+  CU(dalloc(&h->d_mlp, (size_t)nf));
+  CU(cudaMemcpy(h->d_mlp, blob.data(), sizeof(float) * nf, cudaMemcpyHostToDevice));
+  h->mlp = MlpDev{hid, h->d_mlp, nf};
+  if (h->cfg.mlp_engine == CTK_MLP_TCGEN05) {
+    std::string err;
+    if (!mlp_tc_upload(h->mlp_tc, w, err)) return fail(CTK_ECUDA, "mlp_tc_upload: " + err);
+  }
+  return CTK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// noise queue
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int ctk_push_injected_noise(ctk_handle* h, const float* z, size_t n) {
+  REQ(h && (z || n == 0), "null pointer");
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->inj_pos == h->inj_size) h->inj_pos = h->inj_size = 0;  // fully consumed: rewind
+  if (h->inj_size + n > h->inj_cap) {
+    // grow; pending kernels may still read the old buffer -> sync first
+    CU(cudaStreamSynchronize(h->stream));
+    const size_t cap = (h->inj_size + n) * 2;
+    float* nb = nullptr;
+    CU(cudaMalloc((void**)&nb, cap * sizeof(float)));
+    if (h->inj_size) CU(cudaMemcpy(nb, h->d_inj, h->inj_size * sizeof(float), cudaMemcpyDeviceToDevice));
+    if (h->d_inj) cudaFree(h->d_inj);
+    h->d_inj = nb;
+    h->inj_cap = cap;
+  }
+  CU(cudaMemcpyAsync(h->d_inj + h->inj_size, z, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->inj_size += n;
+  return CTK_OK;
+}
+extern "C" int ctk_clear_injected_noise(ctk_handle* h) {
+  REQ(h, "null handle");
+  h->inj_pos = h->inj_size = 0;
+  return CTK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// reset
+// ---------------------------------------------------------------------------------------------------------------
+static RpgdSelectArgs rpgd_sample_args(ctk_handle* h, NoiseSrc ns) {
+  RpgdSelectArgs a{};
+  a.N = h->N; a.H = h->H; a.k = h->cfg.rpgd_keep_k; a.period = h->period; a.n_ind = h->n_ind;
+  a.shift_previous = h->cfg.rpgd_shift_previous;
+  a.noise = ns; a.dist = h->cfg.rpgd_distribution;
+  a.s_mean = h->cfg.rpgd_sample_mean; a.s_std = h->cfg.rpgd_sample_stdev;
+  a.s_min = h->cfg.rpgd_sample_min; a.s_max = h->cfg.rpgd_sample_max;
+  a.lo = h->cfg.action_low; a.hi = h->cfg.action_high;
+  return a;
+}
+
+extern "C" int ctk_reset(ctk_handle* h) {
+  REQ(h, "null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  const float mid = 0.5f * (h->cfg.action_low + h->cfg.action_high);
+  std::vector<float> tmp((size_t)h->H, mid);
+  CU(cudaMemsetAsync(h->d_u_prev, 0, sizeof(float), h->stream));  // self.u = 0.0 (Optimizers/__init__.py:35)
+  if (h->cfg.optimizer == CTK_OPT_MPPI) {
+    CU(cudaMemcpyAsync(h->d_u_nom, tmp.data(), sizeof(float) * h->H, cudaMemcpyHostToDevice, h->stream));
+  } else if (h->cfg.optimizer == CTK_OPT_CEM) {
+    CU(cudaMemcpyAsync(h->d_mu, tmp.data(), sizeof(float) * h->H, cudaMemcpyHostToDevice, h->stream));
+    std::vector<float> sd((size_t)h->H, h->cfg.cem_initial_action_stdev);
+    CU(cudaMemcpyAsync(h->d_sd, sd.data(), sizeof(float) * h->H, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->cem_it = 0;
+  } else {
+    NoiseSrc ns{};
+    int rcn = make_noise(h, STREAM_RPGD_INIT, h->n_ind, h->cfg.rpgd_distribution == CTK_DIST_UNIFORM, (size_t)h->N, &ns);
+    if (rcn != CTK_OK) return rcn;
+    RpgdSelectArgs a = rpgd_sample_args(h, ns);
+    h->cur = 0;
+    a.Qn = h->d_Q[0]; a.mn = h->d_m[0]; a.vn = h->d_v[0]; a.agesn = h->d_ages[0];
+    h->launches++;
+    CU(launch_rpgd_init(a, h->stream));
+    h->adam_step = 0;
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  h->count = 0;
+  h->was_reset = true;
+  return CTK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the tick
+// ---------------------------------------------------------------------------------------------------------------
+static size_t pred_smem_floats(ctk_handle* h) { return mppi_pred_smem_floats(h->cfg.predictor == CTK_PRED_MLP ? 1 : 0, h->mlp); }
+
+static int mppi_local(ctk_handle* h, const float* s_dev, bool finalize, float* u_out_dev) {
+  NoiseSrc ns{};
+  int rcn = make_noise(h, STREAM_MPPI, h->n_ind, 0, (size_t)h->NG, &ns);
+  if (rcn != CTK_OK) return rcn;
+  const ctk_config& c = h->cfg;
+  const bool tc = (c.predictor == CTK_PRED_MLP && c.mlp_engine == CTK_MLP_TCGEN05);
+  MppiArgs a{};
+  a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
+  a.s0 = s_dev; a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = ns;
+  a.stdev = c.mppi_stdev; a.lo = c.action_low; a.hi = c.action_high;
+  a.coef_du2 = c.mppi_coef_du2; a.R = c.mppi_R; a.half_R = c.mppi_half_R; a.cc_weight = c.mppi_cc_weight;
+  a.neg_inv_lbd = c.mppi_neg_inv_LBD;
+  a.ode = h->ode; a.cost = h->cost; a.mlp = h->mlp;
+  a.J = h->d_J; a.partials = h->d_partials;
+  a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
+  const bool log = c.logging != 0;
+  int nparts = h->nblocks;
+  if (tc) {
+    std::string err;
+    if (!mlp_tc_launch_mppi(h->mlp_tc, a, h->cost.kind, log, h->stream, &nparts, &h->launches, err))
+      return fail(CTK_ECUDA, "mlp tcgen05 launch: " + err);
+  } else {
+    size_t smem = sizeof(float) * ((size_t)h->H + 2 * h->period + 32 + 4 * (h->n_ind + 1) + pred_smem_floats(h));
+    h->launches++;
+    cudaError_t e = launch_mppi_rollout(c.predictor == CTK_PRED_ODE ? 0 : 1, h->cost.kind, log, h->nblocks, smem, h->stream, a);
+    if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("mppi_rollout_kernel: ") + cudaGetErrorString(e));
+  }
+  MppiFinalize fin{};
+  fin.enable = finalize ? 1 : 0;
+  fin.H = h->H; fin.period = h->period; fin.n_ind = h->n_ind; fin.stdev = c.mppi_stdev; fin.lo = c.action_low; fin.hi = c.action_high;
+  fin.neg_inv_lbd = c.mppi_neg_inv_LBD; fin.u_nom = h->d_u_nom; fin.u_prev = h->d_u_prev; fin.u_out = u_out_dev;
+  fin.freeze_prev = c.freeze_previous_input;
+  h->launches++;
+  CU(launch_mppi_combine(h->d_partials, nparts, h->n_ind, c.mppi_neg_inv_LBD, h->d_record, fin, h->stream));
+  return CTK_OK;
+}
+
+static int mppi_finish(ctk_handle* h, const float* gathered, int G, float* u_out_dev) {
+  const ctk_config& c = h->cfg;
+  MppiFinalize fin{};
+  fin.enable = 1;
+  fin.H = h->H; fin.period = h->period; fin.n_ind = h->n_ind; fin.stdev = c.mppi_stdev; fin.lo = c.action_low; fin.hi = c.action_high;
+  fin.neg_inv_lbd = c.mppi_neg_inv_LBD; fin.u_nom = h->d_u_nom; fin.u_prev = h->d_u_prev; fin.u_out = u_out_dev;
+  fin.freeze_prev = c.freeze_previous_input;
+  h->launches++;
+  CU(launch_mppi_combine(gathered, G, h->n_ind, c.mppi_neg_inv_LBD, nullptr, fin, h->stream));
+  return CTK_OK;
+}
+
+// CEM: rollouts + local top-k candidates.  to_k: reduce to exactly k keys (sharded exchange record).
+static int cem_local(ctk_handle* h, const float* s_dev, bool to_k) {
+  const ctk_config& c = h->cfg;
+  if (h->cem_it == 0) {
+    h->cem_iters = (c.cem_warmup && h->count == 0) ? c.cem_warmup_iterations : c.cem_outer_it;  // optimizer_cem_tf.py:92
+    if (h->cem_iters < 1) return fail(CTK_EINVAL, "CEM iteration count < 1");
+    h->elite_log_rows = 0;
+  }
+  NoiseSrc ns{};
+  int rcn = make_noise(h, STREAM_CEM | ((uint32_t)h->cem_it << 8), h->H, 0, (size_t)h->NG, &ns);
+  if (rcn != CTK_OK) return rcn;
+  h->cem_noise = ns;
+  CemArgs a{};
+  a.N = h->N; a.off = h->off; a.H = h->H; a.s0 = s_dev; a.mu = h->d_mu; a.sd = h->d_sd; a.u_prev = h->d_u_prev; a.noise = ns;
+  a.lo = c.action_low; a.hi = c.action_high; a.ode = h->ode; a.cost = h->cost; a.mlp = h->mlp; a.J = h->d_J;
+  a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
+  const size_t smem = sizeof(float) * (2 * (size_t)h->H + pred_smem_floats(h));
+  h->launches++;
+  cudaError_t e = launch_cem_rollout(c.predictor == CTK_PRED_ODE ? 0 : 1, h->cost.kind, c.logging != 0, h->nblocks, smem, h->stream, a);
+  if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("cem_rollout_kernel: ") + cudaGetErrorString(e));
+  // K4: hierarchical bitonic top-k
+  const int k = c.cem_best_k;
+  int n = h->N, lvl = 0;
+  const float* cost = h->d_J;
+  const uint64_t* kin = nullptr;
+  while (true) {
+    const int nb = (n + TOPK_THREADS - 1) / TOPK_THREADS;
+    uint64_t* outk = h->d_keys[lvl & 1];
+    h->launches++;
+    CU(launch_topk_level(cost, kin, n, h->off, k, outk, h->stream));
+    n = nb * k; cost = nullptr; kin = outk; ++lvl;
+    if (n <= TOPK_THREADS && (!to_k || nb == 1)) break;
+  }
+  h->cem_cand = n;
+  h->cem_cand_ptr = const_cast<uint64_t*>(kin);
+  return CTK_OK;
+}
+
+static int cem_finish(ctk_handle* h, const uint64_t* cand, int cnt, float* u_out_dev) {
+  const ctk_config& c = h->cfg;
+  REQ(cnt >= c.cem_best_k && cnt <= TOPK_THREADS, "CEM candidate count must be in [k, 1024]");
+  CemRefitArgs a{};
+  a.H = h->H; a.k = c.cem_best_k; a.cnt = cnt; a.cand = cand; a.noise = h->cem_noise; a.lo = c.action_low; a.hi = c.action_high;
+  a.mu = h->d_mu; a.sd = h->d_sd; a.last = (h->cem_it == h->cem_iters - 1) ? 1 : 0;
+  a.sd_min = c.cem_stdev_min; a.sd_init = c.cem_initial_action_stdev;
+  a.u_prev = h->d_u_prev; a.u_out = u_out_dev; a.freeze_prev = c.freeze_previous_input;
+  a.elite_idx_out = (h->elite_log_rows < h->elite_log_cap) ? h->d_elite_idx + (size_t)h->elite_log_rows * c.cem_best_k : nullptr;
+  h->launches++;
+  CU(launch_cem_refit(a, h->stream));
+  if (a.elite_idx_out) h->elite_log_rows++;
+  h->cem_it++;
+  if (a.last) { h->cem_it = 0; h->count++; }
+  return CTK_OK;
+}
+
+static int rpgd_local(ctk_handle* h, const float* s_dev) {
+  const ctk_config& c = h->cfg;
+  const int iters = (h->count == 0) ? c.rpgd_first_iter_count : c.rpgd_outer_its;  // optimizer_rpgd.py:397-400
+  RpgdGradArgs a{};
+  a.N = h->N; a.H = h->H; a.iters = iters; a.s0 = s_dev; a.u_prev = h->d_u_prev;
+  a.Q = h->d_Q[h->cur]; a.m = h->d_m[h->cur]; a.v = h->d_v[h->cur];
+  a.lo = c.action_low; a.hi = c.action_high; a.lr = c.rpgd_learning_rate; a.gradmax_clip = c.rpgd_gradmax_clip;
+  a.beta1 = c.rpgd_beta_1; a.beta2 = c.rpgd_beta_2; a.eps = c.rpgd_epsilon; a.adam_step0 = h->adam_step; a.adam_form = c.rpgd_adam_form;
+  a.ode = h->ode; a.cost = h->cost; a.J = h->d_J; a.log_traj_soa = h->d_log_traj_soa;
+  const int B = 32;
+  const size_t smem = sizeof(float) * (size_t)h->H * B * 8;
+  const bool log = c.logging != 0;
+  if (smem > 227 * 1024) return fail(CTK_EINVAL, "RPGD: mpc_horizon too large for the shared-memory tape (max 227)");
+  h->launches++;
+  CU(launch_rpgd_grad(h->cost.kind, log, (h->N + B - 1) / B, B, smem, h->stream, a));
+  h->adam_step += iters;
+  return CTK_OK;
+}
+
+static int rpgd_finish(ctk_handle* h, float* u_out_dev) {
+  const ctk_config& c = h->cfg;
+  const int resample = (h->count % c.rpgd_resamp_per == 0) ? 1 : 0;  // optimizer_rpgd.py:449
+  NoiseSrc ns{};
+  if (resample && h->N - c.rpgd_keep_k > 0) {
+    int rcn = make_noise(h, STREAM_RPGD_RESAMPLE, h->n_ind, c.rpgd_distribution == CTK_DIST_UNIFORM, (size_t)(h->N - c.rpgd_keep_k), &ns);
+    if (rcn != CTK_OK) return rcn;
+  }
+  RpgdSelectArgs a = rpgd_sample_args(h, ns);
+  a.resample = resample;
+  a.J = h->d_J; a.Q = h->d_Q[h->cur]; a.m = h->d_m[h->cur]; a.v = h->d_v[h->cur]; a.ages = h->d_ages[h->cur];
+  const int nx = h->cur ^ 1;
+  a.Qn = h->d_Q[nx]; a.mn = h->d_m[nx]; a.vn = h->d_v[nx]; a.agesn = h->d_ages[nx];
+  a.u_nom_out = h->d_unom_log; a.u_prev = h->d_u_prev; a.u_out = u_out_dev; a.freeze_prev = c.freeze_previous_input;
+  a.best_idx_out = h->d_best_idx;
+  if (c.logging) {  // Q_logged / trajectory_ages_logged are the values BEFORE the warm-start update (:413-415)
+    CU(cudaMemcpyAsync(h->d_Q_log, h->d_Q[h->cur], sizeof(float) * h->N * h->H, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_ages_log, h->d_ages[h->cur], sizeof(float) * h->N, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  h->launches++;
+  CU(launch_rpgd_select(a, h->stream));
+  h->cur = nx;
+  h->count++;
+  return CTK_OK;
+}
+
+extern "C" int ctk_step_local(ctk_handle* h, const float* s_dev) {
+  REQ(h && s_dev, "null pointer");
+  if (!h->was_reset) return fail(CTK_ESTATE, "ctk_step before ctk_reset");
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->cfg.predictor == CTK_PRED_MLP && h->mlp.blob == nullptr) return fail(CTK_ESTATE, "MLP predictor without weights");
+  int rc;
+  switch (h->cfg.optimizer) {
+    case CTK_OPT_MPPI:
+      h->tick++;
+      rc = mppi_local(h, s_dev, false, nullptr);
+      return rc;
+    case CTK_OPT_CEM:
+      if (h->cem_it == 0) h->tick++;
+      rc = cem_local(h, s_dev, true);
+      if (rc != CTK_OK) return rc;
+      return (h->cem_it < h->cem_iters - 1) ? 1 : 0;
+    default:
+      h->tick++;
+      return rpgd_local(h, s_dev);
+  }
+}
+
+extern "C" int ctk_partials(ctk_handle* h, float** dev_ptr, size_t* n_floats) {
+  REQ(h && dev_ptr && n_floats, "null pointer");
+  if (h->cfg.optimizer == CTK_OPT_MPPI) { *dev_ptr = h->d_record; *n_floats = (size_t)h->n_ind + 2; }
+  else if (h->cfg.optimizer == CTK_OPT_CEM) { *dev_ptr = (float*)h->cem_cand_ptr; *n_floats = 2 * (size_t)h->cfg.cem_best_k; }
+  else { *dev_ptr = nullptr; *n_floats = 0; }
+  return CTK_OK;
+}
+
+extern "C" int ctk_step_finish(ctk_handle* h, const float* gathered, int G, float* u_out_dev) {
+  REQ(h && G >= 1, "null handle or num_shards < 1");
+  CU(cudaSetDevice(h->cfg.device));
+  switch (h->cfg.optimizer) {
+    case CTK_OPT_MPPI:
+      REQ(gathered, "null gathered records");
+      return mppi_finish(h, gathered, G, u_out_dev);
+    case CTK_OPT_CEM:
+      REQ(gathered, "null gathered records");
+      return cem_finish(h, (const uint64_t*)gathered, G * h->cfg.cem_best_k, u_out_dev);
+    default:
+      REQ(G == 1, "RPGD is replicas-only");
+      return rpgd_finish(h, u_out_dev);
+  }
+}
+
+extern "C" int ctk_step(ctk_handle* h, const float* s_host, float* u_out_host) {
+  REQ(h && s_host && u_out_host, "null pointer");
+  if (!h->was_reset) return fail(CTK_ESTATE, "ctk_step before ctk_reset");
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->cfg.predictor == CTK_PRED_MLP && h->mlp.blob == nullptr) return fail(CTK_ESTATE, "MLP predictor without weights");
+  memcpy(h->h_pin, s_host, sizeof(float) * 6);
+  CU(cudaMemcpyAsync(h->d_s0, h->h_pin, sizeof(float) * 6, cudaMemcpyHostToDevice, h->stream));
+  int rc = CTK_OK;
+  if (h->cfg.optimizer == CTK_OPT_MPPI) {
+    h->tick++;
+    rc = mppi_local(h, h->d_s0, true, h->d_u_out);
+  } else if (h->cfg.optimizer == CTK_OPT_CEM) {
+    h->tick++;
+    do {
+      rc = cem_local(h, h->d_s0, false);
+      if (rc != CTK_OK) break;
+      rc = cem_finish(h, h->cem_cand_ptr, h->cem_cand, h->d_u_out);
+    } while (rc == CTK_OK && h->cem_it != 0);
+  } else {
+    h->tick++;
+    rc = rpgd_local(h, h->d_s0);
+    if (rc == CTK_OK) rc = rpgd_finish(h, h->d_u_out);
+  }
+  if (rc != CTK_OK) return rc;
+  CU(cudaMemcpyAsync(h->h_pin + 8, h->d_u_out, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  u_out_host[0] = h->h_pin[8];
+  return CTK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// state / counters / logs
+// ---------------------------------------------------------------------------------------------------------------
+static int transpose_dev(ctk_handle* h, const float* in, float* out, int R, int C) {
+  h->launches++;
+  CU(launch_transpose(in, out, R, C, h->stream));
+  return CTK_OK;
+}
+
+static int state_ptr(ctk_handle* h, int which, float** p, size_t* n, bool* tmajor) {
+  *tmajor = false;
+  const size_t H = h->H, N = h->N;
+  switch (which) {
+    case CTK_STATE_U_NOM: *p = h->d_u_nom; *n = H; break;
+    case CTK_STATE_CEM_MU: *p = h->d_mu; *n = H; break;
+    case CTK_STATE_CEM_STD: *p = h->d_sd; *n = H; break;
+    case CTK_STATE_RPGD_Q: *p = h->d_Q[h->cur]; *n = N * H; *tmajor = true; break;
+    case CTK_STATE_RPGD_M: *p = h->d_m[h->cur]; *n = N * H; *tmajor = true; break;
+    case CTK_STATE_RPGD_V: *p = h->d_v[h->cur]; *n = N * H; *tmajor = true; break;
+    case CTK_STATE_RPGD_AGES: *p = h->d_ages[h->cur]; *n = N; break;
+    case CTK_STATE_U_PREV: *p = h->d_u_prev; *n = 1; break;
+    default: return fail(CTK_EINVAL, "unknown state id");
+  }
+  if (*p == nullptr) return fail(CTK_EINVAL, "state not present for this optimizer");
+  return CTK_OK;
+}
+
+extern "C" int ctk_get_state(ctk_handle* h, int which, float* dst, size_t n) {
+  REQ(h && dst, "null pointer");
+  CU(cudaSetDevice(h->cfg.device));
+  float* p; size_t cnt; bool tm;
+  int rc = state_ptr(h, which, &p, &cnt, &tm);
+  if (rc != CTK_OK) return rc;
+  REQ(n == cnt, "size mismatch");
+  if (tm) {
+    float* tmp = nullptr;
+    CU(cudaMalloc((void**)&tmp, cnt * sizeof(float)));
+    rc = transpose_dev(h, p, tmp, h->H, h->N);  // [H][N] -> [N][H]
+    if (rc == CTK_OK) {
+      cudaError_t e = cudaMemcpyAsync(dst, tmp, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+      cudaFree(tmp);
+      CU(e);
+    } else cudaFree(tmp);
+    return rc;
+  }
+  CU(cudaMemcpyAsync(dst, p, cnt * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return CTK_OK;
+}
+
+extern "C" int ctk_set_state(ctk_handle* h, int which, const float* src, size_t n) {
+  REQ(h && src, "null pointer");
+  CU(cudaSetDevice(h->cfg.device));
+  float* p; size_t cnt; bool tm;
+  int rc = state_ptr(h, which, &p, &cnt, &tm);
+  if (rc != CTK_OK) return rc;
+  REQ(n == cnt, "size mismatch");
+  if (tm) {
+    float* tmp = nullptr;
+    CU(cudaMalloc((void**)&tmp, cnt * sizeof(float)));
+    cudaError_t e = cudaMemcpyAsync(tmp, src, cnt * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) { rc = transpose_dev(h, tmp, p, h->N, h->H); e = cudaStreamSynchronize(h->stream); }
+    cudaFree(tmp);
+    CU(e);
+    return rc;
+  }
+  CU(cudaMemcpyAsync(p, src, cnt * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return CTK_OK;
+}
+
+extern "C" int ctk_get_counter(ctk_handle* h, int which, int64_t* v) {
+  REQ(h && v, "null pointer");
+  switch (which) {
+    case CTK_COUNTER_COUNT: *v = h->count; break;
+    case CTK_COUNTER_ADAM_STEP: *v = h->adam_step; break;
+    case CTK_COUNTER_TICK: *v = h->tick; break;
+    default: return fail(CTK_EINVAL, "unknown counter id");
+  }
+  return CTK_OK;
+}
+extern "C" int ctk_set_counter(ctk_handle* h, int which, int64_t v) {
+  REQ(h, "null pointer");
+  switch (which) {
+    case CTK_COUNTER_COUNT: h->count = v; break;
+    case CTK_COUNTER_ADAM_STEP: h->adam_step = v; break;
+    case CTK_COUNTER_TICK: h->tick = v; break;
+    default: return fail(CTK_EINVAL, "unknown counter id");
+  }
+  return CTK_OK;
+}
+extern "C" int ctk_get_launch_count(ctk_handle* h, int64_t* v) { REQ(h && v, "null pointer"); *v = h->launches; return CTK_OK; }
+
+extern "C" int ctk_get_log(ctk_handle* h, int which, void* dst, size_t nbytes) {
+  REQ(h && dst, "null pointer");
+  CU(cudaSetDevice(h->cfg.device));
+  const size_t N = h->N, H = h->H;
+  const void* src = nullptr;
+  size_t need = 0;
+  switch (which) {
+    case CTK_LOG_J: src = h->d_J; need = N * 4; break;
+    case CTK_LOG_Q:
+      REQ(h->cfg.logging, "logging disabled");
+      if (h->cfg.optimizer == CTK_OPT_RPGD) { int rc = transpose_dev(h, h->d_Q_log, h->d_log_tmp, (int)H, (int)N); if (rc) return rc; }
+      else { int rc = transpose_dev(h, h->d_log_Q_soa, h->d_log_tmp, (int)H, (int)N); if (rc) return rc; }
+      src = h->d_log_tmp; need = N * H * 4; break;
+    case CTK_LOG_ROLLOUTS: {
+      REQ(h->cfg.logging, "logging disabled");
+      int rc = transpose_dev(h, h->d_log_traj_soa, h->d_log_tmp, (int)((H + 1) * 6), (int)N);
+      if (rc) return rc;
+      src = h->d_log_tmp; need = N * (H + 1) * 6 * 4; break;
+    }
+    case CTK_LOG_ELITE_IDX:
+      if (h->cfg.optimizer == CTK_OPT_CEM) { src = h->d_elite_idx; need = (size_t)h->elite_log_rows * h->cfg.cem_best_k * 4; }
+      else if (h->cfg.optimizer == CTK_OPT_RPGD) { src = h->d_best_idx; need = (size_t)h->cfg.rpgd_keep_k * 4; }
+      else return fail(CTK_EINVAL, "no elite log for MPPI");
+      break;
+    case CTK_LOG_U_NOM:
+      REQ(h->cfg.optimizer == CTK_OPT_RPGD, "u_nom log is RPGD only (use CTK_STATE_U_NOM for MPPI)");
+      src = h->d_unom_log; need = H * 4; break;
+    case CTK_LOG_AGES:
+      REQ(h->cfg.optimizer == CTK_OPT_RPGD && h->cfg.logging, "ages log needs RPGD with logging");
+      src = h->d_ages_log; need = N * 4; break;
+    default: return fail(CTK_EINVAL, "unknown log id");
+  }
+  REQ(nbytes == need, "size mismatch (expected " + std::to_string(need) + " bytes)");
+  CU(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return CTK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// nominal single rollout (predict_optimal_trajectory)
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int ctk_rollout_single(ctk_handle* h, const float* s_host, const float* Q_host, float* traj_host, float* summed) {
+  REQ(h && s_host && Q_host && traj_host, "null pointer");
+  CU(cudaSetDevice(h->cfg.device));
+  const int H = h->H;
+  float* d = nullptr;
+  const size_t n = 8 + H + (size_t)(H + 1) * 6 + 1;
+  CU(cudaMalloc((void**)&d, n * sizeof(float)));
+  float *d_s = d, *d_Q = d + 8, *d_traj = d_Q + H, *d_sum = d_traj + (size_t)(H + 1) * 6;
+  cudaError_t e = cudaMemcpyAsync(d_s, s_host, 6 * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_Q, Q_host, H * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    h->launches++;
+    e = launch_single_rollout(h->cfg.predictor == CTK_PRED_ODE ? 0 : 1, d_s, d_Q, H, h->ode, h->cost, h->mlp, h->d_u_prev, d_traj,
+                              d_sum, h->stream);
+  }
+  std::vector<float> tmp((size_t)(H + 1) * 6 + 1);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tmp.data(), d_traj, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  CU(e);
+  memcpy(traj_host, tmp.data(), sizeof(float) * (size_t)(H + 1) * 6);
+  if (summed) *summed = tmp.back();
+  return CTK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// utilities
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int ctk_fp32_peak(int device, double* tflops, double* clk_mhz) {
+  REQ(tflops, "null pointer");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  float* d = nullptr;
+  CU(cudaMalloc((void**)&d, sizeof(float) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    CU(cudaEventRecord(e0));
+    CU(launch_fma_peak(d, blocks, threads, iters, nullptr));
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double fl = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  if (clk_mhz) *clk_mhz = best * 1e12 / (2.0 * 128.0 * prop.multiProcessorCount) / 1e6;  // implied FFMA issue clock
+  return CTK_OK;
+}
+
+extern "C" int ctk_philox_fill(int device, uint64_t seed, int kind, float* dst, size_t n) {
+  REQ(dst, "null pointer");
+  CU(cudaSetDevice(device));
+  float* d = nullptr;
+  CU(cudaMalloc((void**)&d, sizeof(float) * (n ? n : 1)));
+  NoiseSrc ns{};
+  ns.inj = nullptr; ns.key0 = (uint32_t)seed; ns.key1 = (uint32_t)(seed >> 32); ns.tick = 1; ns.stream = STREAM_MPPI;
+  ns.per_rollout = 16; ns.uniform = kind;
+  cudaError_t e = launch_philox_fill(ns, d, n, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpy(dst, d, sizeof(float) * n, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CU(e);
+  return CTK_OK;
+}
+
+extern "C" int ctk_topk(int device, const float* cost_host, int n, int k, int32_t* idx_out) {
+  REQ(cost_host && idx_out && n >= 1 && k >= 1 && k <= n && k <= 512, "need 1 <= k <= min(n, 512)");
+  CU(cudaSetDevice(device));
+  float* d_c = nullptr; uint64_t *d_k0 = nullptr, *d_k1 = nullptr;
+  const size_t nk = (size_t)((n + 1023) / 1024) * k + 1024;
+  CU(cudaMalloc((void**)&d_c, sizeof(float) * n));
+  CU(cudaMalloc((void**)&d_k0, sizeof(uint64_t) * nk));
+  CU(cudaMalloc((void**)&d_k1, sizeof(uint64_t) * nk));
+  cudaError_t e = cudaMemcpy(d_c, cost_host, sizeof(float) * n, cudaMemcpyHostToDevice);
+  uint64_t* bufs[2] = {d_k0, d_k1};
+  int cnt = n, lvl = 0; const float* cost = d_c; const uint64_t* kin = nullptr;
+  while (e == cudaSuccess) {
+    const int nb = (cnt + TOPK_THREADS - 1) / TOPK_THREADS;
+    e = launch_topk_level(cost, kin, cnt, 0, k, bufs[lvl & 1], nullptr);
+    kin = bufs[lvl & 1]; cost = nullptr; cnt = nb * k; ++lvl;
+    if (nb == 1) break;
+  }
+  std::vector<uint64_t> keys((size_t)k);
+  if (e == cudaSuccess) e = cudaMemcpy(keys.data(), kin, sizeof(uint64_t) * k, cudaMemcpyDeviceToHost);
+  cudaFree(d_c); cudaFree(d_k0); cudaFree(d_k1);
+  CU(e);
+  for (int i = 0; i < k; ++i) idx_out[i] = (int32_t)(keys[i] & 0xffffffffu);
+  return CTK_OK;
+}

@@ -1,0 +1,120 @@
+// ctk_kernels_cem.cuh -- K3 fused sample -> rollout -> cost for CEM, K5 elite merge + refit (+ post-loop shift).
+// Replaces reference optimizer_cem_tf.py:54-80 (update_distribution) and :99-102 (post-loop) for one tick.
+#pragma once
+#include "ctk_device.cuh"
+#include "ctk_predictor.cuh"
+#include "ctk_topk.cuh"
+
+namespace ctk {
+
+// Q[n,t] = clip(mu_t + z * sd_t): optimizer_cem_tf.py:64-66 (tf.multiply then add, separately rounded)
+__device__ __forceinline__ float cem_sample(float mu, float sd, float z, float lo, float hi) {
+  return fminf(fmaxf(__fadd_rn(mu, __fmul_rn(z, sd)), lo), hi);
+}
+
+template <class Pred, int KIND, bool LOG>
+__global__ void __launch_bounds__(128) cem_rollout_kernel(const CemArgs a) {
+  extern __shared__ float smem[];
+  float* sh_mu = smem;         // [H]
+  float* sh_sd = smem + a.H;   // [H]
+  for (int t = threadIdx.x; t < a.H; t += blockDim.x) {
+    sh_mu[t] = a.mu[t];
+    sh_sd[t] = a.sd[t];
+  }
+  Pred pred(a.ode, a.mlp, smem + 2 * a.H);
+  __syncthreads();
+
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = n < a.N;
+  if (!active && !Pred::kCooperative) return;
+  const uint32_t ng = (uint32_t)(a.off + (active ? n : 0));
+
+  State z;
+  z.th = a.s0[0]; z.om = a.s0[1]; z.c = a.s0[2]; z.s = a.s0[3]; z.x = a.s0[4]; z.v = a.s0[5];
+  float cosang = cosf(z.th);
+  float u_last = a.u_prev[0];
+  float jsum = 0.0f;
+  for (int t0 = 0; t0 < a.H; t0 += 4) {
+    float zz[4];
+    noise4(a.noise, ng, (uint32_t)(t0 >> 2), zz);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = t0 + q;
+      if (t < a.H) {
+        const float u = cem_sample(sh_mu[t], sh_sd[t], zz[q], a.lo, a.hi);
+        if (LOG && active) {
+          float* p = a.log_traj_soa + (size_t)t * 6 * a.N + n;
+          p[0] = z.th; p[a.N] = z.om; p[2 * a.N] = z.c; p[3 * a.N] = z.s; p[4 * (size_t)a.N] = z.x; p[5 * (size_t)a.N] = z.v;
+          a.log_Q_soa[(size_t)t * a.N + n] = u;
+        }
+        jsum += stage_cost<KIND>(z, cosang, u, u_last, a.cost);
+        pred.step(z, u);
+        cosang = pred.cos_angle(z);
+        u_last = u;
+      }
+    }
+  }
+  if (!active) return;
+  if (LOG) {
+    float* p = a.log_traj_soa + (size_t)a.H * 6 * a.N + n;
+    p[0] = z.th; p[a.N] = z.om; p[2 * a.N] = z.c; p[3 * a.N] = z.s; p[4 * (size_t)a.N] = z.x; p[5 * (size_t)a.N] = z.v;
+  }
+  a.J[n] = (jsum + terminal_cost(z, a.cost)) / (float)(a.H + 1);
+}
+
+// One block of 1024 threads: merge candidates -> global top-k (bitonic), regenerate elite Q, refit mu / sd.
+__global__ void __launch_bounds__(TOPK_THREADS) cem_refit_kernel(const CemRefitArgs a) {
+  __shared__ uint64_t sh[TOPK_THREADS];
+  __shared__ uint32_t sh_elite[TOPK_THREADS];
+  uint64_t key = (threadIdx.x < a.cnt) ? a.cand[threadIdx.x] : KEY_MAX;
+  key = block_bitonic_sort(key, sh);
+  if (threadIdx.x < a.k) {
+    sh_elite[threadIdx.x] = (uint32_t)(key & 0xffffffffu);
+    if (a.elite_idx_out != nullptr) a.elite_idx_out[threadIdx.x] = (int32_t)(key & 0xffffffffu);
+  }
+  __syncthreads();
+
+  // column t: elite_Q[e, t] for e = 0..k-1 (rank order); mean then population std (tf.math.reduce_std)
+  float new_mu = 0.0f, new_sd = 0.0f, first_q = 0.0f;
+  const int t = threadIdx.x;
+  if (t < a.H) {
+    const float mu = a.mu[t], sd = a.sd[t];
+    float acc = 0.0f;
+    for (int e = 0; e < a.k; ++e) {
+      const float q = cem_sample(mu, sd, noise1(a.noise, sh_elite[e], t), a.lo, a.hi);
+      if (e == 0) first_q = q;
+      acc += q;
+    }
+    new_mu = acc / (float)a.k;
+    float var = 0.0f;
+    for (int e = 0; e < a.k; ++e) {
+      const float q = cem_sample(mu, sd, noise1(a.noise, sh_elite[e], t), a.lo, a.hi);
+      const float d = q - new_mu;
+      var = fmaf(d, d, var);
+    }
+    new_sd = sqrtf(var / (float)a.k);
+  }
+  __syncthreads();  // every column has read the old mu / sd
+  if (t < a.H) {
+    if (!a.last) {
+      a.mu[t] = new_mu;
+      a.sd[t] = new_sd;
+    } else {
+      // :99-102  stdev = clip(stdev, min, 1e8); shift left, append initial stdev / mid-range mean; u = elite_Q[0,0]
+      const float sdc = fminf(fmaxf(new_sd, a.sd_min), 1.0e8f);
+      if (t > 0) {
+        a.mu[t - 1] = new_mu;
+        a.sd[t - 1] = sdc;
+      } else {
+        if (!a.freeze_prev) a.u_prev[0] = first_q;
+        if (a.u_out != nullptr) a.u_out[0] = first_q;
+      }
+      if (t == a.H - 1) {
+        a.mu[t] = (a.lo + a.hi) * 0.5f;
+        a.sd[t] = a.sd_init;
+      }
+    }
+  }
+}
+
+}  // namespace ctk

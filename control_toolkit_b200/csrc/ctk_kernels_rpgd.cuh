@@ -1,0 +1,180 @@
+// ctk_kernels_rpgd.cuh -- K6/K7 forward tape + reverse-mode adjoint + Adam, K8 select / shift / resample.
+// Replaces reference optimizer_rpgd.py:306-338 (grad_step), :340-380 (get_action) and :443-516 (warm start /
+// resampling / Adam-moment bookkeeping) for one tick.  Population arrays are stored t-major ([H][N]) on the device so
+// that one-thread-per-trajectory access is coalesced; the C-ABI transposes to the reference's [N,H,nu].
+#pragma once
+#include "ctk_device.cuh"
+#include "ctk_topk.cuh"
+
+namespace ctk {
+
+// One thread = one trajectory.  Shared memory per thread: q[H], g[H], tape[H][6].
+template <int KIND, bool LOG>
+__global__ void __launch_bounds__(32) rpgd_grad_kernel(const RpgdGradArgs a) {
+  extern __shared__ float smem[];
+  const int B = blockDim.x, tid = threadIdx.x;
+  float* sq = smem;                    // [H][B]
+  float* sg = sq + (size_t)a.H * B;    // [H][B]
+  float* tp = sg + (size_t)a.H * B;    // [H][6][B]
+  const int n = blockIdx.x * B + tid;
+  if (n >= a.N) return;
+  const float u_prev = a.u_prev[0];
+  const float w = a.cost.inv_Hp1;
+  State z0;
+  z0.th = a.s0[0]; z0.om = a.s0[1]; z0.c = a.s0[2]; z0.s = a.s0[3]; z0.x = a.s0[4]; z0.v = a.s0[5];
+  const float cos0 = cosf(z0.th);
+
+  for (int t = 0; t < a.H; ++t) sq[t * B + tid] = a.Q[(size_t)t * a.N + n];
+
+  for (int it = 0; it < a.iters; ++it) {
+    // ---- forward, storing the state tape (optimizer_rpgd.py:310-312 under the tape) ----
+    State z = z0;
+    for (int t = 0; t < a.H; ++t) {
+      float* p = tp + (size_t)t * 6 * B + tid;
+      p[0] = z.th; p[B] = z.om; p[2 * B] = z.c; p[3 * B] = z.s; p[4 * B] = z.x; p[5 * B] = z.v;
+      ode_step(z, sq[t * B + tid], a.ode);
+    }
+    // ---- reverse: lambda_H = d(terminal)/ds = 0 (indicator); dJ/dQ_t (optimizer_rpgd.py:314) ----
+    Adj lam = {0.f, 0.f, 0.f, 0.f};
+    float nrm2 = 0.0f;
+    for (int t = a.H - 1; t >= 0; --t) {
+      const float* p = tp + (size_t)t * 6 * B + tid;
+      State zt;
+      zt.th = p[0]; zt.om = p[B]; zt.c = p[2 * B]; zt.s = p[3 * B]; zt.x = p[4 * B]; zt.v = p[5 * B];
+      const float u = sq[t * B + tid];
+      float g = ode_step_adjoint(zt, u, a.ode, lam);
+      const float up = (t > 0) ? sq[(t - 1) * B + tid] : u_prev;
+      const float un = (t < a.H - 1) ? sq[(t + 1) * B + tid] : 0.0f;
+      g += stage_cost_adjoint_u(u, up, un, t < a.H - 1, a.cost, w);
+      sg[t * B + tid] = g;
+      nrm2 = fmaf(g, g, nrm2);
+      if (t > 0) stage_cost_adjoint_state<KIND>(zt, zt.c, zt.s, a.cost, w, lam);
+    }
+    // ---- clip_by_norm over the trajectory (:315), Adam (:317), box clip (:319) ----
+    const float l2 = sqrtf(nrm2);
+    const float den = fmaxf(l2, a.gradmax_clip);
+    const double step = (double)(a.adam_step0 + it + 1);
+    const double bc1d = 1.0 - pow(a.beta1, step), bc2d = 1.0 - pow(a.beta2, step);
+    const float b1 = (float)a.beta1, b2 = (float)a.beta2;
+    const float omb1 = (float)(1.0 - a.beta1), omb2 = (float)(1.0 - a.beta2);
+    const float bc1 = (float)bc1d, bc2 = (float)bc2d, eps = (float)a.eps;
+    const float alpha = (float)((double)a.lr * sqrt(bc2d) / bc1d);  // Keras step size
+    for (int t = 0; t < a.H; ++t) {
+      const float g = sg[t * B + tid] * a.gradmax_clip / den;
+      const size_t gi = (size_t)t * a.N + n;
+      float mm = a.m[gi], vv = a.v[gi];
+      float q = sq[t * B + tid];
+      if (a.adam_form == 1) {
+        // torch form, reference optimizer_rpgd.py:56-82
+        mm = fmaf(g, omb1, mm * b1);
+        vv = fmaf(g * g, omb2, vv * b2);
+        q = q - (a.lr * (mm / bc1)) / (sqrtf(vv / bc2) + eps);
+      } else {
+        // Keras form: m += (g-m)(1-b1); v += (g^2-v)(1-b2); var -= alpha * m / (sqrt(v)+eps)
+        mm = fmaf(g - mm, omb1, mm);
+        vv = fmaf(g * g - vv, omb2, vv);
+        q = q - (alpha * mm) / (sqrtf(vv) + eps);
+      }
+      q = fminf(fmaxf(q, a.lo), a.hi);
+      a.m[gi] = mm;
+      a.v[gi] = vv;
+      sq[t * B + tid] = q;
+    }
+  }
+
+  // ---- get_action rollout (:342): cost of the updated population ----
+  State z = z0;
+  float cosang = cos0, u_last = u_prev, jsum = 0.0f;
+  for (int t = 0; t < a.H; ++t) {
+    const float u = sq[t * B + tid];
+    a.Q[(size_t)t * a.N + n] = u;
+    if (LOG) {
+      float* p = a.log_traj_soa + (size_t)t * 6 * a.N + n;
+      p[0] = z.th; p[a.N] = z.om; p[2 * a.N] = z.c; p[3 * a.N] = z.s; p[4 * (size_t)a.N] = z.x; p[5 * (size_t)a.N] = z.v;
+    }
+    jsum += stage_cost<KIND>(z, cosang, u, u_last, a.cost);
+    ode_step(z, u, a.ode);
+    cosang = z.c;
+    u_last = u;
+  }
+  if (LOG) {
+    float* p = a.log_traj_soa + (size_t)a.H * 6 * a.N + n;
+    p[0] = z.th; p[a.N] = z.om; p[2 * a.N] = z.c; p[3 * a.N] = z.s; p[4 * (size_t)a.N] = z.x; p[5 * (size_t)a.N] = z.v;
+  }
+  a.J[n] = (jsum + terminal_cost(z, a.cost)) / (float)(a.H + 1);
+}
+
+// sample_actions (:275-296) for one new row at horizon step t: clip(z*scale+offset) on inducing points, interpolate
+__device__ __forceinline__ float rpgd_sample_point(const RpgdSelectArgs& a, uint32_t row, int i) {
+  const float z = noise1(a.noise, row, i);
+  const float y = a.dist == 0 ? __fadd_rn(__fmul_rn(z, a.s_std), a.s_mean) : __fadd_rn(__fmul_rn(z, a.s_max - a.s_min), a.s_min);
+  return fminf(fmaxf(y, a.lo), a.hi);
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS) rpgd_select_kernel(const RpgdSelectArgs a) {
+  __shared__ uint64_t sh[TOPK_THREADS];
+  __shared__ int sh_best[TOPK_THREADS];
+  const int tid = threadIdx.x;
+  uint64_t key = (tid < a.N) ? make_key(a.J[tid], (uint32_t)tid) : KEY_MAX;
+  key = block_bitonic_sort(key, sh);  // argsort (:345), stable by index
+  if (tid < a.k) {
+    sh_best[tid] = (int)(key & 0xffffffffu);
+    a.best_idx_out[tid] = sh_best[tid];
+  }
+  __syncthreads();
+  const int best = sh_best[0];
+  for (int t = tid; t < a.H; t += blockDim.x) a.u_nom_out[t] = a.Q[(size_t)t * a.N + best];  // :426
+  if (tid == 0) {
+    const float u = a.Q[best];
+    if (!a.freeze_prev) a.u_prev[0] = u;
+    if (a.u_out != nullptr) a.u_out[0] = u;
+  }
+  const int nnew = a.resample ? a.N - a.k : 0;
+  for (int idx = tid; idx < a.N * a.H; idx += blockDim.x) {
+    const int t = idx / a.N, n = idx - t * a.N;
+    float q, mm, vv;
+    if (n < nnew) {
+      // fresh sample (:451-453): interpolate clipped inducing points (Interpolator.py:97-106)
+      const int seg = t / a.period, j = t - seg * a.period;
+      float w0, w1;
+      interp_weights(j, a.period, &w0, &w1);
+      const float y0 = rpgd_sample_point(a, (uint32_t)n, seg);
+      const float y1 = (j > 0) ? rpgd_sample_point(a, (uint32_t)n, seg + 1) : 0.0f;
+      q = fmaf(y1, w1, __fmul_rn(y0, w0));
+      mm = 0.0f;
+      vv = 0.0f;
+    } else {
+      const int src = a.resample ? sh_best[n - nnew] : n;  // gather in best order (:454) or identity
+      const int ts = min(t + a.shift_previous, a.H - 1);   // :376-379 shift, repeat the last
+      q = a.Q[(size_t)ts * a.N + src];
+      // Adam moments: always shifted by ONE with zero fill (:462-513)
+      mm = (t + 1 < a.H) ? a.m[(size_t)(t + 1) * a.N + src] : 0.0f;
+      vv = (t + 1 < a.H) ? a.v[(size_t)(t + 1) * a.N + src] : 0.0f;
+    }
+    a.Qn[idx] = q;
+    a.mn[idx] = mm;
+    a.vn[idx] = vv;
+  }
+  for (int n = tid; n < a.N; n += blockDim.x) {
+    const float age = (n < nnew) ? 0.0f : a.ages[a.resample ? sh_best[n - nnew] : n];
+    a.agesn[n] = age + 1.0f;  // :514
+  }
+}
+
+// initial population (optimizer_reset :540): all N rows sampled; Adam state zeroed
+__global__ void rpgd_init_kernel(const RpgdSelectArgs a) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < a.N * a.H; idx += gridDim.x * blockDim.x) {
+    const int t = idx / a.N, n = idx - t * a.N;
+    const int seg = t / a.period, j = t - seg * a.period;
+    float w0, w1;
+    interp_weights(j, a.period, &w0, &w1);
+    const float y0 = rpgd_sample_point(a, (uint32_t)n, seg);
+    const float y1 = (j > 0) ? rpgd_sample_point(a, (uint32_t)n, seg + 1) : 0.0f;
+    a.Qn[idx] = fmaf(y1, w1, __fmul_rn(y0, w0));
+    a.mn[idx] = 0.0f;
+    a.vn[idx] = 0.0f;
+    if (t == 0) a.agesn[n] = 0.0f;
+  }
+}
+
+}  // namespace ctk

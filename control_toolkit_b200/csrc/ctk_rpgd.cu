@@ -1,0 +1,54 @@
+// ctk_rpgd.cu -- translation unit owning the RPGD kernels (K6/K7 grad steps, K8 select/resample, init) and utilities.
+#include "ctk_kernels_rpgd.cuh"
+#include "ctk_launch.h"
+
+namespace ctk {
+
+cudaError_t launch_rpgd_grad(int kind, bool log, int nblocks, int block, size_t smem, cudaStream_t st, const RpgdGradArgs& a) {
+  void (*k)(const RpgdGradArgs) = nullptr;
+  if (kind == 0) k = log ? rpgd_grad_kernel<0, true> : rpgd_grad_kernel<0, false>;
+  else k = log ? rpgd_grad_kernel<1, true> : rpgd_grad_kernel<1, false>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k<<<nblocks, block, smem, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_rpgd_select(const RpgdSelectArgs& a, cudaStream_t st) {
+  rpgd_select_kernel<<<1, TOPK_THREADS, 0, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_rpgd_init(const RpgdSelectArgs& a, cudaStream_t st) {
+  rpgd_init_kernel<<<(a.N * a.H + 255) / 256, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// FP32 FMA-chain microbenchmark: 8 independent chains per thread, 16x unrolled
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+cudaError_t launch_fma_peak(float* out, int blocks, int threads, int iters, cudaStream_t st) {
+  fma_peak_kernel<<<blocks, threads, 0, st>>>(out, iters, 0.999f, 0.001f);
+  return cudaGetLastError();
+}
+
+__global__ void philox_fill_kernel(NoiseSrc ns, float* out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = noise1(ns, (uint32_t)(i / ns.per_rollout), (int)(i % ns.per_rollout));
+}
+cudaError_t launch_philox_fill(const NoiseSrc& ns, float* out, size_t n, cudaStream_t st) {
+  philox_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ns, out, n);
+  return cudaGetLastError();
+}
+
+}  // namespace ctk

@@ -1,0 +1,178 @@
+"""Registry of the environments / predictors / cost functions that have DEVICE functors.
+
+The reference's contract is "any Python subclass of cost_function_base" loaded by name
+(reference Cost_Functions/cost_function_wrapper.py:59-66) and "any predictor_specification" resolved by SI_Toolkit
+(reference Controllers/controller_mpc.py:67-73).  A fused CUDA rollout needs device code, so this backend keeps a
+registry ``(environment_name, name) -> device functor id + parameter block`` and fails loudly (ValueError) for
+anything unregistered -- there is no Python/CPU fallback.
+
+Constants are the build's pinned spec (DESIGN.md "Spec").  Compound constants are evaluated in
+float64 and rounded once to fp32, exactly as oracle/spec.py does (the two are written independently and compared in
+tests/test_host_logic.py).
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass, field, replace
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _f32(x) -> float:
+    return float(np.float32(x))
+
+
+@dataclass
+class CartPoleODE:
+    """CartPole Euler ODE parameters [UPSTREAM-RECALL of CartPoleSimulation, pinned]."""
+    k: float = 1.0 / 3.0
+    M: float = 0.230
+    m: float = 0.087
+    L: float = 0.395 / 2.0
+    g: float = 9.81
+    J_fric: float = 2.5e-4
+    M_fric: float = 4.77
+    u_max: float = 2.62
+    intermediate_steps: int = 1
+
+    def to_c(self, dt: float) -> L.ctk_ode_params:
+        h = dt / self.intermediate_steps
+        p = L.ctk_ode_params()
+        p.u_max = _f32(self.u_max)
+        p.kp1_Mm = _f32((self.k + 1.0) * (self.M + self.m))
+        p.m = _f32(self.m)
+        p.neg_M_fric = _f32(-self.M_fric)
+        p.neg_J_fric = _f32(-self.J_fric)
+        p.mg = _f32(self.m * self.g)
+        p.L = _f32(self.L)
+        p.kp1 = _f32(self.k + 1.0)
+        p.mL = _f32(self.m * self.L)
+        p.g = _f32(self.g)
+        p.kp1L = _f32((self.k + 1.0) * self.L)
+        p.h = _f32(h)
+        p.intermediate_steps = int(self.intermediate_steps)
+        return p
+
+
+@dataclass
+class CartPoleCost:
+    """Weights of the CartPole cost classes (quadratic_boundary_grad values: reference
+    Control_Toolkit_ASF_Template/config_cost_function.yml:11-18; `default` reuses them)."""
+    kind: int = L.COST_DEFAULT
+    dd_weight: float = 600.0
+    ep_weight: float = 20000.0
+    ekp_weight: float = 80.0
+    cc_weight: float = 1.0
+    ccrc_weight: float = 1.0
+    R: float = 1.0
+    MAX_COST: float = 0.0
+    TrackHalfLength: float = 0.198
+
+    def to_c(self, target_position: float = 0.0, target_equilibrium: float = 1.0) -> L.ctk_cost_params:
+        thl = self.TrackHalfLength
+        p = L.ctk_cost_params()
+        p.kind = int(self.kind)
+        p.dd_weight, p.ep_weight, p.ekp_weight = _f32(self.dd_weight), _f32(self.ep_weight), _f32(self.ekp_weight)
+        p.cc_weight, p.ccrc_weight, p.R, p.MAX_COST = _f32(self.cc_weight), _f32(self.ccrc_weight), _f32(self.R), _f32(self.MAX_COST)
+        p.two_thl, p.thl_095, p.thl_005 = _f32(2.0 * thl), _f32(0.95 * thl), _f32(0.05 * thl)
+        p.thl_09, p.thl_01 = _f32(0.9 * thl), _f32(0.1 * thl)
+        p.target_position, p.target_equilibrium = _f32(target_position), _f32(target_equilibrium)
+        return p
+
+
+# (environment_name, cost_function_name) -> prototype
+COST_REGISTRY = {
+    ("CartPole", "default"): CartPoleCost(kind=L.COST_DEFAULT),
+    ("CartPole", "quadratic_boundary_grad"): CartPoleCost(kind=L.COST_QUADRATIC_BOUNDARY_GRAD),
+}
+ODE_REGISTRY = {"CartPole": CartPoleODE()}
+_WEIGHT_KEYS = ("dd_weight", "ep_weight", "ekp_weight", "cc_weight", "ccrc_weight", "R")
+
+
+def resolve_cost(environment_name: str, cost_function_name: str, overrides: dict | None = None) -> CartPoleCost:
+    key = (str(environment_name), str(cost_function_name).replace("-", "_"))
+    if key not in COST_REGISTRY:
+        raise ValueError(f"cost function {key[1]!r} of environment {key[0]!r} has no registered CUDA functor "
+                         f"(registered: {sorted(COST_REGISTRY)}); this backend has no Python/CPU fallback")
+    proto = COST_REGISTRY[key]
+    ov = {k: float(v) for k, v in (overrides or {}).items() if k in _WEIGHT_KEYS}
+    return replace(proto, **ov)
+
+
+def cost_overrides_from_yaml(environment_name: str, cost_function_name: str, path: str | None = None) -> dict:
+    """Weights from ``Control_Toolkit_ASF/config_cost_function.yml`` (CWD-relative, like the reference loads it at
+    Cost_Functions/cost_function_wrapper.py:14), if that file and section exist."""
+    path = path or os.path.join("Control_Toolkit_ASF", "config_cost_function.yml")
+    if not os.path.isfile(path):
+        return {}
+    import yaml
+    with open(path) as f:
+        cfg = yaml.safe_load(f) or {}
+    return dict((cfg.get(environment_name) or {}).get(cost_function_name) or {})
+
+
+@dataclass
+class MLPSpec:
+    """Dense 6 -> hidden tanh -> hidden tanh -> 5 autoregressive predictor (config C4).  Row-major [in,out]."""
+    W1: np.ndarray
+    b1: np.ndarray
+    W2: np.ndarray
+    b2: np.ndarray
+    W3: np.ndarray
+    b3: np.ndarray
+
+    def __post_init__(self):
+        for k in ("W1", "b1", "W2", "b2", "W3", "b3"):
+            setattr(self, k, np.ascontiguousarray(getattr(self, k), dtype=np.float32))
+        hid = self.W1.shape[1]
+        if self.W1.shape != (6, hid) or self.W2.shape != (hid, hid) or self.W3.shape != (hid, 5) \
+                or self.b1.shape != (hid,) or self.b2.shape != (hid,) or self.b3.shape != (5,):
+            raise ValueError("MLP predictor must be 6 -> hidden -> hidden -> 5")
+        if hid % 16 or not 16 <= hid <= 128:
+            raise ValueError("MLP hidden width must be a multiple of 16 in [16, 128]")
+
+    @property
+    def hidden(self) -> int:
+        return int(self.W1.shape[1])
+
+    @staticmethod
+    def random_init(seed: int = 2, hidden: int = 128) -> "MLPSpec":
+        """weights N(0, 1/fan_in), biases 0, numpy default_rng(seed)."""
+        rng = np.random.default_rng(seed)
+
+        def w(i, o):
+            return (rng.standard_normal((i, o)) / math.sqrt(i)).astype(np.float32)
+
+        return MLPSpec(w(6, hidden), np.zeros(hidden, np.float32), w(hidden, hidden), np.zeros(hidden, np.float32),
+                       w(hidden, 5), np.zeros(5, np.float32))
+
+    def to_c(self) -> L.ctk_mlp_weights:
+        w = L.ctk_mlp_weights()
+        w.hidden = self.hidden
+        for k in ("W1", "b1", "W2", "b2", "W3", "b3"):
+            setattr(w, k, L.fptr(getattr(self, k)))
+        return w
+
+
+MLP_REGISTRY: dict[str, MLPSpec] = {}
+
+
+def register_mlp(predictor_specification: str, spec: MLPSpec) -> None:
+    """Make a network predictor available under a predictor_specification name (e.g. 'Dense-6IN-128H1-128H2-5OUT-0')."""
+    MLP_REGISTRY[str(predictor_specification)] = spec
+
+
+def resolve_predictor(environment_name: str, predictor_specification: str):
+    """-> (PRED_ODE, CartPoleODE) or (PRED_MLP, MLPSpec).  ValueError if nothing is registered."""
+    name = str(predictor_specification)
+    if name.startswith("ODE"):
+        if environment_name not in ODE_REGISTRY:
+            raise ValueError(f"environment {environment_name!r} has no registered CUDA ODE (registered: {sorted(ODE_REGISTRY)})")
+        return L.PRED_ODE, ODE_REGISTRY[environment_name]
+    if name in MLP_REGISTRY:
+        return L.PRED_MLP, MLP_REGISTRY[name]
+    raise ValueError(f"predictor_specification {name!r} is neither 'ODE' nor a registered network "
+                     f"(register_mlp); registered networks: {sorted(MLP_REGISTRY)}")

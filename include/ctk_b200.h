@@ -1,0 +1,190 @@
+/* ctk_b200.h -- C ABI of libctk_b200.so: the B200 (sm_100a) backend for the batched MPC rollout hot path of
+ * SensorsINI/Control_Toolkit (MPPI / CEM / RPGD + the predictor and cost they drive).
+ *
+ * The reference is pure Python; its "FFI" for this path is the Python optimizer plugin interface
+ *   template_optimizer.__init__/configure/step/optimizer_reset      (reference Optimizers/__init__.py:13-71)
+ * as called by controller_mpc                                          (reference Controllers/controller_mpc.py:56-109).
+ * Every entry point below cites the reference call it replaces.  The Python classes in
+ * control_toolkit_b200/Optimizers/ bind these symbols with ctypes (the same mechanism the reference itself uses to
+ * call C at Controllers/controller_C.py:222-248); INTEGRATION.md shows the binding.
+ *
+ * Conventions: plain pointers and sizes only; all arrays are fp32 unless stated; "host" pointers are ordinary host
+ * memory (pinned or not), "dev" pointers are device memory on the handle's device.  Every function returns 0 on
+ * success or a negative CTK_E* code; ctk_last_error() returns a thread-local message.  There is no CPU fallback:
+ * if no CUDA device is usable, ctk_create fails.
+ */
+#ifndef CTK_B200_H
+#define CTK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTK_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------------------------- */
+#define CTK_OK 0
+#define CTK_EINVAL (-1)   /* bad argument / unsupported configuration (Python raises ValueError)                 */
+#define CTK_ECUDA (-2)    /* CUDA runtime error (Python raises RuntimeError)                                     */
+#define CTK_ESTATE (-3)   /* call made in the wrong state (e.g. step before reset)                               */
+
+/* ---- enums -------------------------------------------------------------------------------------------------- */
+enum { CTK_OPT_MPPI = 0, CTK_OPT_CEM = 1, CTK_OPT_RPGD = 2 };            /* optimizer_mppi / optimizer_cem_tf / optimizer_rpgd */
+enum { CTK_PRED_ODE = 0, CTK_PRED_MLP = 1 };                             /* predictor_specification "ODE" / "Dense-..."        */
+enum { CTK_COST_DEFAULT = 0, CTK_COST_QUADRATIC_BOUNDARY_GRAD = 1 };     /* cost_function_specification                         */
+enum { CTK_DIST_NORMAL = 0, CTK_DIST_UNIFORM = 1 };                      /* RPGD SAMPLING_DISTRIBUTION                          */
+enum { CTK_ADAM_KERAS = 0, CTK_ADAM_TORCH = 1 };                         /* reference optimizer_rpgd.py:34-43 vs :56-82         */
+enum { CTK_MLP_SIMT = 0, CTK_MLP_TCGEN05 = 1 };                          /* MLP predictor engine                                */
+
+/* which = state arrays (get/set).  Layouts are the reference's: [1,H,nu] or [N,H,nu] row-major.                 */
+enum {
+  CTK_STATE_U_NOM = 0,      /* MPPI u_nom [H]            (optimizer_mppi.py:227-231)                              */
+  CTK_STATE_CEM_MU = 1,     /* CEM dist_mue [H]          (optimizer_cem_tf.py:114)                                */
+  CTK_STATE_CEM_STD = 2,    /* CEM stdev [H]             (optimizer_cem_tf.py:115)                                */
+  CTK_STATE_RPGD_Q = 3,     /* RPGD Q_tf [N,H]           (optimizer_rpgd.py:540-544)                              */
+  CTK_STATE_RPGD_M = 4,     /* Adam m [N,H]              (optimizer_rpgd.py:84-131)                               */
+  CTK_STATE_RPGD_V = 5,     /* Adam v [N,H]                                                                       */
+  CTK_STATE_RPGD_AGES = 6,  /* trajectory_ages [N]       (optimizer_rpgd.py:548)                                  */
+  CTK_STATE_U_PREV = 7      /* self.u, the previous_input of the cost [1] (Optimizers/__init__.py:35)             */
+};
+/* which = integer counters */
+enum { CTK_COUNTER_COUNT = 0,      /* optimizer.count   (optimizer_cem_tf.py:116, optimizer_rpgd.py:545)          */
+       CTK_COUNTER_ADAM_STEP = 1,  /* Adam global step  (optimizer_rpgd.py:59)                                    */
+       CTK_COUNTER_TICK = 2 };     /* number of step() calls since create (Philox counter word)                   */
+/* which = logs of the LAST tick (only filled when cfg.logging != 0; reference optimizer_mppi.py:214-218)         */
+enum {
+  CTK_LOG_Q = 0,          /* Q_logged [N,H,nu]                                                                    */
+  CTK_LOG_J = 1,          /* J_logged [N]        (always available, logging or not)                               */
+  CTK_LOG_ROLLOUTS = 2,   /* rollout_trajectories_logged [N,H+1,ns]                                               */
+  CTK_LOG_ELITE_IDX = 3,  /* int32 [iters_of_last_tick, k] global rollout ids of the elites, best first (CEM);
+                             [k] best_idx (RPGD)                                                                   */
+  CTK_LOG_U_NOM = 4,      /* optimal_control_sequence [H] of the last tick (RPGD u_nom, optimizer_rpgd.py:426)    */
+  CTK_LOG_AGES = 5        /* trajectory_ages_logged [N] (RPGD, ages before the update, optimizer_rpgd.py:415)     */
+};
+
+/* ---- parameter blocks (compound constants evaluated in float64 on the host, rounded once to fp32) ------------ */
+typedef struct ctk_ode_params {   /* CartPole Euler ODE; replaces PredictorWrapper.predict_core for "ODE"        */
+  float u_max, kp1_Mm, m, neg_M_fric, neg_J_fric, mg, L, kp1, mL, g, kp1L, h;
+  int32_t intermediate_steps;
+} ctk_ode_params;
+
+typedef struct ctk_cost_params {  /* CartPole cost classes; replaces CostFunctionWrapper.get_trajectory_cost     */
+  int32_t kind;                   /* CTK_COST_*                                                                  */
+  float dd_weight, ep_weight, ekp_weight, cc_weight, ccrc_weight, R, MAX_COST;
+  float two_thl, thl_095, thl_005, thl_09, thl_01;
+  float target_position, target_equilibrium;   /* live environment attributes (controller update_attributes)     */
+} ctk_cost_params;
+
+typedef struct ctk_mlp_weights {  /* Dense 6 -> hidden tanh -> hidden tanh -> 5 ; row-major [in,out]; host ptrs  */
+  int32_t hidden;
+  const float *W1, *b1, *W2, *b2, *W3, *b3;
+} ctk_mlp_weights;
+
+typedef struct ctk_config {
+  int32_t abi_version;            /* = CTK_ABI_VERSION                                                           */
+  int32_t optimizer;              /* CTK_OPT_*                                                                   */
+  int32_t predictor;              /* CTK_PRED_*                                                                  */
+  int32_t device;                 /* CUDA device ordinal                                                         */
+  /* template_optimizer ctor (reference Optimizers/__init__.py:13-50) */
+  int32_t num_rollouts;           /* rollouts evaluated by THIS handle (local shard)                             */
+  int32_t num_rollouts_global;    /* total over all shards (== num_rollouts when not sharded)                    */
+  int32_t rollout_offset;         /* global id of local rollout 0 (Philox counters use global ids)               */
+  int32_t mpc_horizon;
+  int32_t num_states;             /* 6                                                                           */
+  int32_t num_control_inputs;     /* 1                                                                           */
+  float action_low, action_high;
+  uint64_t seed;
+  int32_t logging;                /* optimizer_logging                                                           */
+  int32_t freeze_previous_input;  /* 1: previous_input frozen at 0 (TF graph-trace semantics)   */
+  int32_t period_interpolation_inducing_points;  /* MPPI, RPGD                                                   */
+  /* MPPI (reference optimizer_mppi.py:16-34,130,154-168); fp32 coefficients precomputed by the host in the
+     reference's evaluation order */
+  float mppi_coef_du2;            /* fp32(fp32(0.5*(1-1/NU))*R)                                                  */
+  float mppi_R;                   /* R                                                                           */
+  float mppi_half_R;              /* fp32(0.5*R)                                                                 */
+  float mppi_cc_weight;
+  float mppi_neg_inv_LBD;         /* fp32(-1.0/LBD)                                                              */
+  float mppi_stdev;               /* SQRTRHODTINV = fp32(SQRTRHOINV/sqrt(dt))                                    */
+  /* CEM (reference optimizer_cem_tf.py:16-34) */
+  int32_t cem_outer_it, cem_best_k, cem_warmup, cem_warmup_iterations;
+  float cem_initial_action_stdev, cem_stdev_min;
+  /* RPGD (reference optimizer_rpgd.py:148-179) */
+  int32_t rpgd_outer_its, rpgd_first_iter_count, rpgd_resamp_per, rpgd_shift_previous, rpgd_keep_k;
+  int32_t rpgd_distribution;      /* CTK_DIST_*                                                                  */
+  int32_t rpgd_adam_form;         /* CTK_ADAM_*                                                                  */
+  float rpgd_sample_mean, rpgd_sample_stdev, rpgd_sample_min, rpgd_sample_max;
+  float rpgd_learning_rate, rpgd_gradmax_clip;
+  double rpgd_beta_1, rpgd_beta_2, rpgd_epsilon;
+  int32_t mlp_engine;             /* CTK_MLP_*                                                                   */
+  int32_t reserved[7];
+} ctk_config;
+
+typedef struct ctk_handle ctk_handle;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------------------- */
+/* replaces Optimizer(**kwargs) + optimizer.configure(...)  (controller_mpc.py:56-65,84-89)                       */
+int ctk_create(const ctk_config *cfg, const ctk_ode_params *ode, const ctk_cost_params *cost, ctk_handle **out);
+int ctk_destroy(ctk_handle *h);
+/* replaces optimizer.optimizer_reset()  (controller_mpc.py:108-109; optimizer_mppi.py:227-231,
+   optimizer_cem_tf.py:113-117, optimizer_rpgd.py:527-548).  RPGD draws its initial population here.             */
+int ctk_reset(ctk_handle *h);
+/* live cost / environment parameters (controller update_attributes, Controllers/__init__.py:106-107)            */
+int ctk_set_cost_params(ctk_handle *h, const ctk_cost_params *cost);
+int ctk_set_ode_params(ctk_handle *h, const ctk_ode_params *ode);
+int ctk_set_mlp_weights(ctk_handle *h, const ctk_mlp_weights *w);
+/* run subsequent work on this cudaStream_t (0 = legacy default stream)                                          */
+int ctk_set_stream(ctk_handle *h, void *cuda_stream);
+
+/* ---- noise -------------------------------------------------------------------------------------------------- */
+/* Injected-noise mode (verification): queue n standard draws z (N(0,1) or U[0,1), exactly the numbers a replay
+   rng hands the reference at optimizer_mppi.py:173 / optimizer_cem_tf.py:64 / optimizer_rpgd.py:277,284), consumed
+   in order by the following reset()/step() calls.  The buffer holds the draws of the GLOBAL population
+   ([num_rollouts_global, ...]); a shard reads its own rows.  When the queue is empty the kernels generate
+   Philox4x32-10 noise in-kernel (counter = draw block, global rollout id, tick, stream id; key = seed).          */
+int ctk_push_injected_noise(ctk_handle *h, const float *z_host, size_t n);
+int ctk_clear_injected_noise(ctk_handle *h);
+
+/* ---- the hot path ------------------------------------------------------------------------------------------- */
+/* replaces optimizer.step(s, time) (controller_mpc.py:104): one full tick, host in / host out.
+   s_host [num_states]; u_out_host [num_control_inputs].                                                          */
+int ctk_step(ctk_handle *h, const float *s_host, float *u_out_host);
+/* The same tick split for sharded (multi-GPU) use and for device-resident timing:
+   ctk_step_local   : sample + rollout + cost + local reduction; asynchronous on the handle's stream; s_dev [ns].
+   ctk_partials     : device pointer / float count of this shard's exchange record
+                      (MPPI: [rho, a, b_z[n_ind]];  CEM: k x [cost, global id(as float bits), Q[H]]).
+   ctk_step_finish  : combine `num_shards` records (laid out contiguously, device memory) and update the optimizer
+                      state identically on every shard; writes u to u_out_dev [nu] (device) if not NULL.
+   CEM runs cem_outer_it local/finish pairs per tick: ctk_step_local returns 1 while more iterations remain.      */
+int ctk_step_local(ctk_handle *h, const float *s_dev);
+int ctk_partials(ctk_handle *h, float **dev_ptr, size_t *n_floats);
+int ctk_step_finish(ctk_handle *h, const float *gathered_dev, int num_shards, float *u_out_dev);
+
+/* ---- state / logs ------------------------------------------------------------------------------------------- */
+int ctk_get_state(ctk_handle *h, int which, float *dst_host, size_t n);
+int ctk_set_state(ctk_handle *h, int which, const float *src_host, size_t n);
+int ctk_get_counter(ctk_handle *h, int which, int64_t *value);
+int ctk_set_counter(ctk_handle *h, int which, int64_t value);
+int ctk_get_log(ctk_handle *h, int which, void *dst_host, size_t n_bytes);
+/* number of CUDA kernels this handle has launched since create (bench.py "gpu_launches")                         */
+int ctk_get_launch_count(ctk_handle *h, int64_t *value);
+/* standalone nominal rollout of one control sequence (reference optimizer_mppi.py:199-202 predict_optimal_trajectory,
+   optimizer_rpgd.py:382-386): s_host [ns], Q_host [H] -> traj_host [H+1, ns], summed stage cost (may be NULL).     */
+int ctk_rollout_single(ctk_handle *h, const float *s_host, const float *Q_host, float *traj_host, float *summed_stage_cost);
+
+/* ---- utilities ---------------------------------------------------------------------------------------------- */
+const char *ctk_last_error(void);
+int ctk_abi_version(void);
+/* FP32 FMA-chain microbenchmark used as the measured FP32 roofline denominator (TFLOP/s)                         */
+int ctk_fp32_peak(int device, double *tflops, double *sm_clock_mhz_est);
+/* Philox self-test: fill dst_host with n standard normals (kind 0) / uniforms (kind 1) exactly as the kernels draw */
+int ctk_philox_fill(int device, uint64_t seed, int kind, float *dst_host, size_t n);
+/* standalone top-k (ties -> lower index), the kernel behind tf.argsort(...)[:k] (optimizer_cem_tf.py:73-74)      */
+int ctk_topk(int device, const float *cost_host, int n, int k, int32_t *idx_out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTK_B200_H */

@@ -1,0 +1,71 @@
+"""CPU tests of the per-rollout arithmetic the kernels run (control_toolkit_b200/csrc/ctk_math.cuh), compiled for the
+host as a TEST-ONLY twin (tests/host_twin): ODE step + cost vs the oracle spec, and the hand-derived RPGD adjoint vs
+the oracle's torch autograd.  The twin is not a product path -- the product never loads it."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import spec
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def twin():
+    sys.path.insert(0, os.path.join(HERE, "host_twin"))
+    import build_twin
+    lib = C.CDLL(build_twin.build())
+    return lib
+
+
+def _params(cost_name, dt=0.02):
+    from control_toolkit_b200 import specs, _lib as L
+    ode = specs.CartPoleODE().to_c(dt)
+    cost = specs.resolve_cost("CartPole", cost_name).to_c(0.0, 1.0)
+    return ode, cost
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+@pytest.mark.parametrize("cost_name", ["default", "quadratic_boundary_grad"])
+def test_rollout_and_cost_match_spec(twin, cost_name):
+    N, H = 64, 50
+    rng = np.random.default_rng(3)
+    for s0 in spec.synthetic_states(4, seed=5):
+        Q = rng.uniform(-1, 1, (N, H)).astype(np.float32)
+        ode, cost = _params(cost_name)
+        J = np.zeros(N, np.float32)
+        traj = np.zeros((N, H + 1, 6), np.float32)
+        twin.twin_rollout_cost(_fp(s0), _fp(Q), N, H, C.byref(ode), C.byref(cost), C.c_float(0.3), _fp(J), _fp(traj))
+        pred = spec.ODEPredictor()
+        ro = pred.predict_core(torch.from_numpy(np.tile(s0, (N, 1))), torch.from_numpy(Q[..., None]))
+        Jo = spec.trajectory_cost(ro, torch.from_numpy(Q[..., None]), 0.3, spec.CostParams(name=cost_name)).numpy()
+        for c in range(6):
+            scale = max(np.abs(ro[..., c].numpy()).max(), 1e-6)
+            assert np.abs(traj[..., c] - ro[..., c].numpy()).max() / scale < 2e-4
+        assert np.max(np.abs(J - Jo) / (np.abs(Jo) + 1e-3)) < 1e-4
+
+
+@pytest.mark.parametrize("cost_name", ["default", "quadratic_boundary_grad"])
+def test_adjoint_matches_autograd(twin, cost_name):
+    N, H = 32, 50
+    rng = np.random.default_rng(4)
+    for s0 in spec.synthetic_states(4, seed=6):
+        Q = rng.uniform(-1, 1, (N, H)).astype(np.float32)
+        ode, cost = _params(cost_name)
+        g = np.zeros((N, H), np.float32)
+        twin.twin_grad(_fp(s0), _fp(Q), N, H, C.byref(ode), C.byref(cost), C.c_float(-0.2), _fp(g))
+        Qt = torch.from_numpy(Q[..., None]).clone().requires_grad_(True)
+        ro = spec.ODEPredictor().predict_core(torch.from_numpy(np.tile(s0, (N, 1))), Qt)
+        spec.trajectory_cost(ro, Qt, -0.2, spec.CostParams(name=cost_name)).sum().backward()
+        go = Qt.grad[..., 0].numpy()
+        for n in range(N):
+            scale = np.abs(go[n]).max()
+            assert np.abs(g[n] - go[n]).max() / scale < 2e-4, (n, np.abs(g[n] - go[n]).max(), scale)
