@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- rollout-steps/s of the batched MPC rollout hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload mppi_ode_1m|...]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Own arm ("ours"): one step = one MPPI tick (sample -> rollout -> cost -> softmin update) over the configured rollout
+population.  Default workload = BASELINE.json configs[4]: MPPI, 1,000,000 rollouts x horizon 100, ODE CartPole,
+in-kernel Philox noise, sharded by sample over the N GPUs ("strong" scaling: the population is fixed at 1M).
+  value    : N_global*H / device time per tick, states already resident in HBM, CUDA events on the launching stream,
+             max over ranks.
+  e2e      : the same metric through the public plugin API (controller_mpc.step with a HOST state, H2D + D2H inside).
+  roofline : the fused rollout kernel (K1) against the measured FP32 FMA-chain peak (the kernel is FP32-pipe bound:
+             < 1 byte of HBM traffic per rollout-step), algorithmic 80 FLOP per rollout-step.
+  cpu_baseline : the oracle port of the reference's MPPI (torch-CPU fp32, all host threads) on a bounded sample.
+Reference arm (--impl reference): the same oracle port timed on the host cores, K steps of a bounded sample each.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+FLOP_PER_ROLLOUT_STEP = {"mppi_ode": 80.0, "cem_ode": 65.0}  # SURVEY.md 8d convention, re-derived in DESIGN.md
+MPPI_CFG = dict(seed=42, mpc_timestep=0.02, cc_weight=1.0, R=1.0, LBD=100.0, NU=1000.0, SQRTRHOINV=0.03,
+                period_interpolation_inducing_points=10)
+WORKLOADS = {
+    # name: (optimizer, predictor, cost, N_global, H)
+    "mppi_ode_1m": ("mppi", "ODE", "default", 1_000_000, 100),   # BASELINE configs[4] (the metric's config)
+    "mppi_ode_c1": ("mppi", "ODE", "default", 2000, 50),         # configs[0]
+    "mppi_mlp_c4": ("mppi", "Dense-6IN-128H1-128H2-5OUT-0", "default", 65536, 100),  # configs[3]
+}
+
+
+def synthetic_states(n, seed=0):
+    rng = np.random.default_rng(seed)
+    angle = rng.uniform(-np.pi, np.pi, n)
+    s = np.stack([angle, rng.uniform(-5, 5, n), np.cos(angle), np.sin(angle), rng.uniform(-0.15, 0.15, n),
+                  rng.uniform(-0.5, 0.5, n)], 1)
+    return s.astype(np.float32)
+
+
+class ClockSampler:
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md).  The timed region of this bench
+    is only a few milliseconds, so NVML is polled from a thread (~1 kHz) instead of `nvidia-smi -lms`."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, device):
+        self.device, self.samples, self.bits, self._stop, self.t, self.err = device, [], 0, False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa
+            self.nv, self.err = None, repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception as e:  # noqa
+                self.err = repr(e)
+                break
+            time.sleep(0.0005)
+
+    def start(self):
+        if self.nv is not None:
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+
+    def stop(self):
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
+        self._stop = True
+        self.t.join(timeout=2)
+        reasons = sorted(n for b, n in self.REASONS.items() if self.bits & b)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.samples), "reasons": reasons}
+
+
+def build_controller(workload, shard=None, device=0, logging=False, n_override=None):
+    import control_toolkit_b200 as ctk
+    from control_toolkit_b200.Controllers.controller_mpc import controller_mpc
+    opt_name, pred, cost, N, H = WORKLOADS[workload]
+    N = n_override or N
+    if pred.startswith("Dense"):
+        ctk.register_mlp(pred, ctk.MLPSpec.random_init(2))
+    cfg = dict(MPPI_CFG, mpc_horizon=H, num_rollouts=N, shard=shard, device_index=device)
+    ctrl = controller_mpc("CartPole", (np.array([-1.0], np.float32), np.array([1.0], np.float32)),
+                          {"target_position": 0.0, "target_equilibrium": 1.0},
+                          config_controller=dict(optimizer=opt_name, predictor_specification=pred, cost_function_specification=cost,
+                                                 controller_logging=logging, calculate_optimal_trajectory=False),
+                          config_optimizers={opt_name: cfg}, config_cost_function={"cost_function_name_default": "default"})
+    ctrl.configure(optimizer_name=opt_name, predictor_specification=pred)
+    return ctrl, N, H
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's MPPI on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_mppi_rate(workload, n_sample, ticks, warm=1):
+    """rollout-steps/s of oracle.mppi.MPPIOracle (restatement of reference optimizer_mppi.py, torch-CPU fp32)."""
+    import torch
+    from oracle import spec
+    from oracle.mppi import MPPIOracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    _, pred, cost, _, H = WORKLOADS[workload]
+    predictor = spec.ODEPredictor() if pred == "ODE" else spec.MLPPredictor(spec.MLPWeights.random_init(2))
+    o = MPPIOracle(predictor, spec.CostParams(name=cost), mpc_horizon=H, num_rollouts=n_sample,
+                   **{k: v for k, v in MPPI_CFG.items() if k != "seed"})
+    g = torch.Generator().manual_seed(42)
+
+    class _Rng:  # the reference's torch rng duck type (others/globals_and_utils.py:61-82)
+        @staticmethod
+        def normal(shape, dtype=torch.float32, mean=0.0, stddev=1.0):
+            return torch.normal(mean=mean, std=stddev, size=tuple(shape), generator=g, dtype=dtype)
+
+    states = synthetic_states(ticks + warm, 0)
+    times = []
+    for t in range(ticks + warm):
+        t0 = time.perf_counter()
+        o.step(states[t], _Rng)
+        if t >= warm:
+            times.append(time.perf_counter() - t0)
+    return n_sample * H / statistics.mean(times), statistics.mean(times), torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    _, _, _, N, H = WORKLOADS[args.workload]
+    n_sample = min(N, args.cpu_sample)
+    rate, sec, threads = cpu_mppi_rate(args.workload, n_sample, args.steps, args.warmup)
+    sample = f"{args.steps} ticks of {n_sample} rollouts x H={H} (of {N}) per step, oracle port of optimizer_mppi.py, torch-CPU fp32"
+    line = {"impl": "reference", "metric": "rollout-steps/s", "value": rate, "unit": "rollout-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "optimizer": "mppi", "num_rollouts": N, "mpc_horizon": H, "predictor": WORKLOADS[args.workload][1]},
+            "cpu_baseline": {"value": rate, "unit": "rollout-steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "rollout-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from control_toolkit_b200 import _lib as L
+    from control_toolkit_b200.distributed import ShardPlan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    lib = L.load()
+    plan = ShardPlan(rank, world)
+    ctrl, N, H = build_controller(args.workload, shard=plan if world > 1 else None, device=local_rank, n_override=args.rollouts)
+    opt = ctrl.optimizer
+    plan.attach(opt, lib)  # handle runs on torch's current stream (events + NCCL ordering)
+    K, W = args.steps, args.warmup
+    states = torch.from_numpy(synthetic_states(K + W, 0)).to(dev)
+    u_dev = torch.zeros(4, dtype=torch.float32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def tick(i):
+        plan.run_tick_device(opt, lib, states[i].data_ptr(), u_dev.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        tick(i)
+    barrier()
+    # ---- device-resident timing: one CUDA-event pair per tick, L2 flushed between ticks ----
+    L.check(lib.ctk_enable_kernel_timing(opt._h, 1))
+    launches0 = opt.gpu_launches
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(K):
+        flush.zero_()
+        ev[i][0].record()
+        tick(W + i)
+        ev[i][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    per_tick_ms = [a.elapsed_time(b) for a, b in ev]
+    launches = opt.gpu_launches - launches0
+    ms_sum, n_k = C.c_double(), C.c_int64()
+    L.check(lib.ctk_get_kernel_timing(opt._h, C.byref(ms_sum), C.byref(n_k)))
+    L.check(lib.ctk_enable_kernel_timing(opt._h, 0))
+    total_ms = torch.tensor([sum(per_tick_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(total_ms.item()) / K
+    value = N * H / (ms_per_step * 1e-3)
+
+    # ---- e2e through the public plugin API: host state in, host control out, every step ----
+    host_states = synthetic_states(K + W, 1)
+    for i in range(min(W, 3)):
+        ctrl.step(host_states[i])
+    barrier()
+    lat = []
+    t0 = time.perf_counter()
+    for i in range(K):
+        t1 = time.perf_counter()
+        ctrl.step(host_states[W + i])
+        lat.append(time.perf_counter() - t1)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = N * H * K / float(e2e_s.item())
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (K1 fused rollout), measured live above ----
+        k1_ms = ms_sum.value / max(n_k.value, 1)
+        n_local = opt._n_local
+        flop = FLOP_PER_ROLLOUT_STEP["mppi_ode"] * n_local * H
+        peak, clk = C.c_double(), C.c_double()
+        L.check(lib.ctk_fp32_peak(local_rank, C.byref(peak), C.byref(clk)))
+        achieved = flop / (k1_ms * 1e-3) / 1e12
+        roofline = {"bound": "fp32", "kernel": "mppi_rollout_kernel<OdePred>", "achieved": achieved, "peak": peak.value,
+                    "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None, "traffic": None,
+                    "peak_source": "measured live: FP32 FMA-chain microbenchmark (ctk_fp32_peak), implied FFMA clock %.0f MHz; "
+                                   "theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5" % clk.value,
+                    "flop_per_rollout_step": FLOP_PER_ROLLOUT_STEP["mppi_ode"], "kernel_ms": k1_ms,
+                    "kernel_share_of_tick": k1_ms / ms_per_step,
+                    "hbm": {"algorithmic_bytes_per_launch": 4.0 * n_local, "achieved_gbs": 4.0 * n_local / (k1_ms * 1e-3) / 1e9,
+                            "peak_gbs": json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"]
+                            if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else 6650.0}}
+        # ---- CPU baseline: oracle port on a bounded sample of the same workload ----
+        n_sample = min(N, args.cpu_sample)
+        rate, sec, threads = cpu_mppi_rate(args.workload, n_sample, 2, 1)
+        cpu = {"value": rate, "unit": "rollout-steps/s", "cores": threads, "kind": "port",
+               "sample": f"2 ticks of {n_sample} rollouts x H={H} (of {N}); oracle port of reference optimizer_mppi.py, torch-CPU fp32; "
+                         f"{sec:.2f} s/tick"}
+        line = {"metric": "rollout-steps/s", "value": value, "unit": "rollout-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": args.workload, "optimizer": "mppi", "num_rollouts": N, "mpc_horizon": H,
+                           "predictor": WORKLOADS[args.workload][1], "cost": "default", "noise": "in-kernel Philox4x32-10",
+                           "parallelism": f"rollouts sharded over {world} GPU(s), one all-gather of {H // 10 + 3} floats per tick",
+                           "l2": "flushed between timed ticks (256 MiB memset); inputs are 24 B per tick"},
+                "e2e": {"value": e2e_value, "unit": "rollout-steps/s", "h2d_bytes_per_step": 24, "d2h_bytes_per_step": 4 + 4 * H,
+                        "p50_step_latency_ms": statistics.median(lat) * 1e3, "api": "controller_mpc.step(s_host) -> u_host"},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+                "wall_s_timed_region": wall}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mppi_ode_1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--rollouts", type=int, default=None, help="override the global rollout count")
+    ap.add_argument("--cpu-sample", type=int, default=100_000, help="rollouts per CPU-baseline tick (bounded sample)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,6 +27,15 @@ struct MlpDev {
 
 __host__ __device__ inline int mlp_blob_floats(int hid) { return 6 * hid + hid + hid * hid + hid + 5 * hid + 8; }
 
+// Loop-invariant constants of the rollout kernels live in DEVICE memory (handle-owned) and are read once per thread
+// with volatile loads: sm_100 FP instructions take no constant-bank operands and ptxas re-issues LDC/LDCU inside the
+// rollout loop for kernel-parameter constants (18 issue slots per rollout-step, seen in SASS); a volatile global load
+// cannot be rematerialised, so the values stay in registers.
+struct DevConsts {
+  FwdK fwd;
+  CostC cost;
+};
+
 struct MppiArgs {
   int N, off, H, period, n_ind;  // local rollouts, global id offset, horizon, inducing-point period / count
   const float* s0;               // [6] device
@@ -34,12 +43,13 @@ struct MppiArgs {
   const float* u_prev;           // [1] device, previous_input of the cost (self.u, :211)
   NoiseSrc noise;                // per_rollout = n_ind
   float stdev, lo, hi;           // SQRTRHODTINV (:130), control limits
-  float coef_du2, R, half_R, cc_weight, neg_inv_lbd;  // :154-155, :165
-  OdeC ode;
-  CostC cost;
+  float k_du2, k_udu, k_uu, neg_inv_lbd;  // :154-155 pre-multiplied by cc_weight; :165
+  int stash;                     // 1: keep each rollout's draws in shared memory for the softmin record (else regenerate)
+  const DevConsts* kc;           // device: forward ODE + cost constants
+  const float* kx;               // device: {lo, hi, k_du2, k_udu}
   MlpDev mlp;
   float* J;                      // [N] out: total MPPI cost S
-  float* partials;               // [gridDim.x][2 + n_ind] out: rho_b, a_b, b_z[n_ind]
+  float* partials;               // [iterations][gridDim.x][2 + n_ind] out: rho_b, a_b, b_z[n_ind]
   float* log_traj_soa;           // [(H+1)][6][N] or null
   float* log_Q_soa;              // [H][N] or null
 };
@@ -64,8 +74,7 @@ struct CemArgs {
   const float* u_prev;  // [1]
   NoiseSrc noise;       // per_rollout = H
   float lo, hi;
-  OdeC ode;
-  CostC cost;
+  const DevConsts* kc;  // device: forward ODE + cost constants
   MlpDev mlp;
   float* J;             // [N]
   float* log_traj_soa;  // [(H+1)][6][N] or null
@@ -99,7 +108,8 @@ struct RpgdGradArgs {
   double beta1, beta2, eps;
   long long adam_step0;  // global step counter before this tick's first gradient step
   int adam_form;         // 0 Keras, 1 torch
-  OdeC ode;
+  OdeC ode;              // adjoint constants
+  FwdK fwd;              // forward constants
   CostC cost;
   float* J;              // [N] cost of the final (get_action) rollout
   float* log_traj_soa;   // [(H+1)][6][N] or null

@@ -72,6 +72,42 @@ __device__ __forceinline__ float noise1(const NoiseSrc& ns, uint32_t n_global, i
 }
 
 // ----------------------------------------------------------------------------------------------------------
+// Loop-invariant constants, loaded once per thread from device memory with volatile loads (see DevConsts).
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float vld(const float* p) { return *reinterpret_cast<const volatile float*>(p); }
+__device__ __forceinline__ FwdK load_fwd(const DevConsts* kc) {
+  const FwdK* f = &kc->fwd;
+  FwdK r;
+  r.K1p = vld(&f->K1p); r.kp1L = vld(&f->kp1L); r.cF = vld(&f->cF); r.cU = vld(&f->cU); r.g = vld(&f->g);
+  r.cTl = vld(&f->cTl); r.kTm = vld(&f->kTm); r.h = vld(&f->h); r.hk = vld(&f->hk);
+  r.k0s = vld(&f->k0s); r.k0c = vld(&f->k0c);
+  r.isteps = f->isteps;
+  return r;
+}
+__device__ __forceinline__ CostC load_cost(const DevConsts* kc) {
+  const CostC* c = &kc->cost;
+  CostC r = *c;  // cold fields (terminal cost, shift, adjoint weights): ordinary loads
+  r.target_position = vld(&c->target_position); r.thl_095 = vld(&c->thl_095); r.k_dd = vld(&c->k_dd);
+  r.k_bar = vld(&c->k_bar); r.k_ep = vld(&c->k_ep); r.k_cc = vld(&c->k_cc); r.k_ccrc = vld(&c->k_ccrc);
+  if (r.kind == 1) { r.k_ekp = vld(&c->k_ekp); r.thl_09 = vld(&c->thl_09); r.k_border = vld(&c->k_border); }
+  return r;
+}
+
+// shared-memory loads through an explicit 32-bit shared address (one register, bumped by the caller): avoids the
+// per-iteration generic->shared base recomputation ptxas otherwise re-issues inside the rollout loop
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+
+// ----------------------------------------------------------------------------------------------------------
 // reductions
 // ----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

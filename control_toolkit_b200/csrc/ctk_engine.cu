@@ -35,10 +35,14 @@ static int fail(int code, const std::string& msg) {
 struct ctk_handle {
   ctk_config cfg;
   OdeC ode;
+  FwdK fwd;
   CostC cost;
   MlpDev mlp;
+  DevConsts* d_kc = nullptr;  // device copy of {fwd, cost}
+  float* d_kx = nullptr;      // device: {lo, hi, k_du2, k_udu}
   cudaStream_t stream = nullptr;
   int N = 0, NG = 0, off = 0, H = 0, period = 1, n_ind = 0, nblocks = 0;
+  int mppi_grid = 0, mppi_block = 0, mppi_iters = 0, mppi_stash = 0, num_sms = 0;
   // common
   float *d_s0 = nullptr, *d_u_prev = nullptr, *d_u_out = nullptr, *d_J = nullptr;
   float *h_pin = nullptr;  // pinned staging: s[8] | u[8]
@@ -68,13 +72,54 @@ struct ctk_handle {
   // counters
   int64_t count = 0, adam_step = 0, tick = 0, launches = 0;
   bool was_reset = false;
+  // optional CUDA-event timing of the dominant (rollout) kernel, for bench.py's live roofline measurement
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;  // pairs
+  size_t ev_used = 0;
+};
+
+struct KernelTimer {  // records an event pair around the dominant kernel launch when timing is enabled
+  ctk_handle* h;
+  bool on;
+  explicit KernelTimer(ctk_handle* hh) : h(hh), on(false) {
+    if (!h->timing) return;
+    if (h->ev_used + 2 > h->ev.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      h->ev.push_back(a);
+      h->ev.push_back(b);
+    }
+    on = cudaEventRecord(h->ev[h->ev_used], h->stream) == cudaSuccess;
+  }
+  ~KernelTimer() {
+    if (on) {
+      cudaEventRecord(h->ev[h->ev_used + 1], h->stream);
+      h->ev_used += 2;
+    }
+  }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+static cudaError_t upload_consts(ctk_handle* h);
+
 template <typename T>
 static cudaError_t dalloc(T** p, size_t n) {
   cudaError_t e = cudaMalloc((void**)p, (n ? n : 1) * sizeof(T));
   if (e == cudaSuccess) e = cudaMemset(*p, 0, (n ? n : 1) * sizeof(T));
+  return e;
+}
+
+static cudaError_t upload_consts(ctk_handle* h) {
+  DevConsts kc;
+  kc.fwd = h->fwd;
+  kc.cost = h->cost;
+  const ctk_config& c = h->cfg;
+  const float kx[4] = {c.action_low, c.action_high, (float)((double)c.mppi_cc_weight * (double)c.mppi_coef_du2),
+                       (float)((double)c.mppi_cc_weight * (double)c.mppi_R)};
+  // the stream may still run kernels that read the old constants: order the copies on it
+  cudaError_t e = cudaMemcpyAsync(h->d_kc, &kc, sizeof(kc), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->d_kx, kx, sizeof(kx), cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);  // kc / kx are stack variables
   return e;
 }
 
@@ -114,11 +159,14 @@ extern "C" int ctk_destroy(ctk_handle* h) {
                  h->d_Q[0], h->d_Q[1], h->d_m[0], h->d_m[1], h->d_v[0], h->d_v[1], h->d_ages[0], h->d_ages[1],
                  h->d_unom_log, h->d_ages_log, h->d_Q_log, h->d_log_traj_soa, h->d_log_Q_soa, h->d_log_tmp, h->d_inj, h->d_mlp};
   for (float* p : fp) if (p) cudaFree(p);
+  if (h->d_kc) cudaFree(h->d_kc);
+  if (h->d_kx) cudaFree(h->d_kx);
   if (h->d_keys[0]) cudaFree(h->d_keys[0]);
   if (h->d_keys[1]) cudaFree(h->d_keys[1]);
   if (h->d_elite_idx) cudaFree(h->d_elite_idx);
   if (h->d_best_idx) cudaFree(h->d_best_idx);
   mlp_tc_free(h->mlp_tc);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   delete h;
   return CTK_OK;
@@ -145,6 +193,7 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
   h->cfg = *cfg;
   h->N = cfg->num_rollouts; h->NG = cfg->num_rollouts_global; h->off = cfg->rollout_offset; h->H = cfg->mpc_horizon;
   derive_ode(*ode, h->ode);
+  derive_fwd(*ode, h->fwd);
   derive_cost(*cost, h->H, h->cost);
   h->mlp = MlpDev{0, nullptr, 0};
   h->nblocks = (h->N + 127) / 128;
@@ -155,6 +204,8 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
   };
   A(dalloc(&h->d_s0, 8), "s0"); A(dalloc(&h->d_u_prev, 1), "u_prev"); A(dalloc(&h->d_u_out, 4), "u_out");
   A(dalloc(&h->d_J, (size_t)N), "J");
+  A(cudaMalloc((void**)&h->d_kc, sizeof(DevConsts)), "consts");
+  A(dalloc(&h->d_kx, 4), "kx");
   A(cudaMallocHost((void**)&h->h_pin, 16 * sizeof(float)), "pinned");
   if (cfg->logging) {
     A(dalloc(&h->d_log_traj_soa, (size_t)(H + 1) * 6 * N), "log_traj");
@@ -167,8 +218,23 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
     h->n_ind = (int)std::ceil((double)(H - 1) / (double)h->period) + 1;  // Interpolator.py:79-84
   }
   if (cfg->optimizer == CTK_OPT_MPPI) {
+    // K1 geometry: one CTA per SM, block sized so that every thread runs the same number of rollouts (no tail wave)
+    cudaDeviceProp prop;
+    A(cudaGetDeviceProperties(&prop, cfg->device), "props");
+    h->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+    const int maxb = mppi_max_block_threads(cfg->predictor == CTK_PRED_ODE ? 0 : 1);
+    const long long slots = (long long)h->num_sms * maxb;
+    const int r = (int)((N + slots - 1) / slots);                                  // rollouts per thread
+    int T = (int)(((((long long)N + (long long)r * h->num_sms - 1) / ((long long)r * h->num_sms)) + 31) / 32 * 32);
+    if (T > maxb) T = maxb;
+    if (T < 32) T = 32;
+    h->mppi_block = T;
+    h->mppi_grid = (int)std::min<long long>(h->num_sms, ((long long)N + (long long)T * r - 1) / ((long long)T * r));
+    if (h->mppi_grid < 1) h->mppi_grid = 1;
+    h->mppi_iters = (int)((N + (long long)h->mppi_grid * T - 1) / ((long long)h->mppi_grid * T));
+    h->mppi_stash = ((size_t)h->n_ind * T * sizeof(float) <= 160 * 1024) ? 1 : 0;
     A(dalloc(&h->d_u_nom, (size_t)H), "u_nom");
-    A(dalloc(&h->d_partials, (size_t)h->nblocks * (h->n_ind + 2)), "partials");
+    A(dalloc(&h->d_partials, (size_t)h->mppi_grid * h->mppi_iters * (h->n_ind + 2)), "partials");
     A(dalloc(&h->d_record, (size_t)(h->n_ind + 2)), "record");
   } else if (cfg->optimizer == CTK_OPT_CEM) {
     if (!(cfg->cem_best_k >= 1 && cfg->cem_best_k <= 512 && cfg->cem_best_k <= cfg->num_rollouts_global && H <= 1024 && cfg->cem_outer_it >= 1)) {
@@ -197,6 +263,7 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
     A(dalloc(&h->d_Q_log, (size_t)N * H), "Q_log");
     A(dalloc(&h->d_best_idx, (size_t)N), "best_idx");
   }
+  if (rc == CTK_OK) A(upload_consts(h), "upload_consts");
   if (rc != CTK_OK) { std::string keep = g_err; ctk_destroy(h); g_err = keep; return rc; }
   *out = h;
   return CTK_OK;
@@ -207,12 +274,17 @@ extern "C" int ctk_set_cost_params(ctk_handle* h, const ctk_cost_params* c) {
   REQ(h && c, "null pointer");
   REQ(c->kind == CTK_COST_DEFAULT || c->kind == CTK_COST_QUADRATIC_BOUNDARY_GRAD, "unregistered cost function");
   derive_cost(*c, h->H, h->cost);
+  CU(cudaSetDevice(h->cfg.device));
+  CU(upload_consts(h));
   return CTK_OK;
 }
 extern "C" int ctk_set_ode_params(ctk_handle* h, const ctk_ode_params* o) {
   REQ(h && o, "null pointer");
   REQ(!(h->cfg.optimizer == CTK_OPT_RPGD && o->intermediate_steps > 1), "RPGD adjoint supports intermediate_steps == 1");
   derive_ode(*o, h->ode);
+  derive_fwd(*o, h->fwd);
+  CU(cudaSetDevice(h->cfg.device));
+  CU(upload_consts(h));
   return CTK_OK;
 }
 
@@ -330,21 +402,28 @@ static int mppi_local(ctk_handle* h, const float* s_dev, bool finalize, float* u
   a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
   a.s0 = s_dev; a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = ns;
   a.stdev = c.mppi_stdev; a.lo = c.action_low; a.hi = c.action_high;
-  a.coef_du2 = c.mppi_coef_du2; a.R = c.mppi_R; a.half_R = c.mppi_half_R; a.cc_weight = c.mppi_cc_weight;
+  // :154-155 constants pre-multiplied by cc_weight (k_du2, k_udu live in d_kx); the 0.5 R u^2 term shares u^2 with the
+  // cost's own cc term (k_cc)
+  a.k_du2 = 0.f; a.k_udu = 0.f;
+  a.k_uu = (float)((double)c.mppi_cc_weight * (double)c.mppi_half_R);
   a.neg_inv_lbd = c.mppi_neg_inv_LBD;
-  a.ode = h->ode; a.cost = h->cost; a.mlp = h->mlp;
+  a.stash = h->mppi_stash;
+  a.kc = h->d_kc; a.kx = h->d_kx; a.mlp = h->mlp;
   a.J = h->d_J; a.partials = h->d_partials;
   a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
   const bool log = c.logging != 0;
-  int nparts = h->nblocks;
+  int nparts = h->mppi_grid * h->mppi_iters;
   if (tc) {
     std::string err;
     if (!mlp_tc_launch_mppi(h->mlp_tc, a, h->cost.kind, log, h->stream, &nparts, &h->launches, err))
       return fail(CTK_ECUDA, "mlp tcgen05 launch: " + err);
   } else {
-    size_t smem = sizeof(float) * ((size_t)h->H + 2 * h->period + 32 + 4 * (h->n_ind + 1) + pred_smem_floats(h));
+    size_t smem = sizeof(float) * ((size_t)((h->H + 1) & ~1) + 2 * h->period + 32 + 32 * (h->n_ind + 1) +
+                                   (h->mppi_stash ? (size_t)h->n_ind * h->mppi_block : 0) + pred_smem_floats(h));
     h->launches++;
-    cudaError_t e = launch_mppi_rollout(c.predictor == CTK_PRED_ODE ? 0 : 1, h->cost.kind, log, h->nblocks, smem, h->stream, a);
+    KernelTimer kt(h);
+    cudaError_t e = launch_mppi_rollout(c.predictor == CTK_PRED_ODE ? 0 : 1, h->cost.kind, log, h->mppi_grid, h->mppi_block, smem,
+                                        h->stream, a);
     if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("mppi_rollout_kernel: ") + cudaGetErrorString(e));
   }
   MppiFinalize fin{};
@@ -383,11 +462,15 @@ static int cem_local(ctk_handle* h, const float* s_dev, bool to_k) {
   h->cem_noise = ns;
   CemArgs a{};
   a.N = h->N; a.off = h->off; a.H = h->H; a.s0 = s_dev; a.mu = h->d_mu; a.sd = h->d_sd; a.u_prev = h->d_u_prev; a.noise = ns;
-  a.lo = c.action_low; a.hi = c.action_high; a.ode = h->ode; a.cost = h->cost; a.mlp = h->mlp; a.J = h->d_J;
+  a.lo = c.action_low; a.hi = c.action_high; a.kc = h->d_kc; a.mlp = h->mlp; a.J = h->d_J;
   a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
   const size_t smem = sizeof(float) * (2 * (size_t)h->H + pred_smem_floats(h));
   h->launches++;
-  cudaError_t e = launch_cem_rollout(c.predictor == CTK_PRED_ODE ? 0 : 1, h->cost.kind, c.logging != 0, h->nblocks, smem, h->stream, a);
+  cudaError_t e;
+  {
+    KernelTimer kt(h);
+    e = launch_cem_rollout(c.predictor == CTK_PRED_ODE ? 0 : 1, h->cost.kind, c.logging != 0, h->nblocks, smem, h->stream, a);
+  }
   if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("cem_rollout_kernel: ") + cudaGetErrorString(e));
   // K4: hierarchical bitonic top-k
   const int k = c.cem_best_k;
@@ -432,13 +515,16 @@ static int rpgd_local(ctk_handle* h, const float* s_dev) {
   a.Q = h->d_Q[h->cur]; a.m = h->d_m[h->cur]; a.v = h->d_v[h->cur];
   a.lo = c.action_low; a.hi = c.action_high; a.lr = c.rpgd_learning_rate; a.gradmax_clip = c.rpgd_gradmax_clip;
   a.beta1 = c.rpgd_beta_1; a.beta2 = c.rpgd_beta_2; a.eps = c.rpgd_epsilon; a.adam_step0 = h->adam_step; a.adam_form = c.rpgd_adam_form;
-  a.ode = h->ode; a.cost = h->cost; a.J = h->d_J; a.log_traj_soa = h->d_log_traj_soa;
+  a.ode = h->ode; a.fwd = h->fwd; a.cost = h->cost; a.J = h->d_J; a.log_traj_soa = h->d_log_traj_soa;
   const int B = 32;
   const size_t smem = sizeof(float) * (size_t)h->H * B * 8;
   const bool log = c.logging != 0;
   if (smem > 227 * 1024) return fail(CTK_EINVAL, "RPGD: mpc_horizon too large for the shared-memory tape (max 227)");
   h->launches++;
-  CU(launch_rpgd_grad(h->cost.kind, log, (h->N + B - 1) / B, B, smem, h->stream, a));
+  {
+    KernelTimer kt(h);
+    CU(launch_rpgd_grad(h->cost.kind, log, (h->N + B - 1) / B, B, smem, h->stream, a));
+  }
   h->adam_step += iters;
   return CTK_OK;
 }
@@ -637,6 +723,27 @@ extern "C" int ctk_set_counter(ctk_handle* h, int which, int64_t v) {
   }
   return CTK_OK;
 }
+extern "C" int ctk_enable_kernel_timing(ctk_handle* h, int on) {
+  REQ(h, "null handle");
+  h->timing = on != 0;
+  h->ev_used = 0;
+  return CTK_OK;
+}
+extern "C" int ctk_get_kernel_timing(ctk_handle* h, double* ms_sum, int64_t* n) {
+  REQ(h && ms_sum && n, "null pointer");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+    tot += ms;
+  }
+  *ms_sum = tot;
+  *n = (int64_t)(h->ev_used / 2);
+  h->ev_used = 0;
+  return CTK_OK;
+}
 extern "C" int ctk_get_launch_count(ctk_handle* h, int64_t* v) { REQ(h && v, "null pointer"); *v = h->launches; return CTK_OK; }
 
 extern "C" int ctk_get_log(ctk_handle* h, int which, void* dst, size_t nbytes) {
@@ -692,7 +799,7 @@ extern "C" int ctk_rollout_single(ctk_handle* h, const float* s_host, const floa
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_Q, Q_host, H * sizeof(float), cudaMemcpyHostToDevice, h->stream);
   if (e == cudaSuccess) {
     h->launches++;
-    e = launch_single_rollout(h->cfg.predictor == CTK_PRED_ODE ? 0 : 1, d_s, d_Q, H, h->ode, h->cost, h->mlp, h->d_u_prev, d_traj,
+    e = launch_single_rollout(h->cfg.predictor == CTK_PRED_ODE ? 0 : 1, d_s, d_Q, H, h->d_kc, h->mlp, h->d_u_prev, d_traj,
                               d_sum, h->stream);
   }
   std::vector<float> tmp((size_t)(H + 1) * 6 + 1);

@@ -21,7 +21,8 @@ __global__ void __launch_bounds__(128) cem_rollout_kernel(const CemArgs a) {
     sh_mu[t] = a.mu[t];
     sh_sd[t] = a.sd[t];
   }
-  Pred pred(a.ode, a.mlp, smem + 2 * a.H);
+  Pred pred(a.kc, a.mlp, smem + 2 * a.H);
+  const CostC cost = load_cost(a.kc);
   __syncthreads();
 
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -31,7 +32,7 @@ __global__ void __launch_bounds__(128) cem_rollout_kernel(const CemArgs a) {
 
   State z;
   z.th = a.s0[0]; z.om = a.s0[1]; z.c = a.s0[2]; z.s = a.s0[3]; z.x = a.s0[4]; z.v = a.s0[5];
-  float cosang = cosf(z.th);
+  float omc = 1.0f - cosf(z.th);
   float u_last = a.u_prev[0];
   float jsum = 0.0f;
   for (int t0 = 0; t0 < a.H; t0 += 4) {
@@ -47,9 +48,8 @@ __global__ void __launch_bounds__(128) cem_rollout_kernel(const CemArgs a) {
           p[0] = z.th; p[a.N] = z.om; p[2 * a.N] = z.c; p[3 * a.N] = z.s; p[4 * (size_t)a.N] = z.x; p[5 * (size_t)a.N] = z.v;
           a.log_Q_soa[(size_t)t * a.N + n] = u;
         }
-        jsum += stage_cost<KIND>(z, cosang, u, u_last, a.cost);
-        pred.step(z, u);
-        cosang = pred.cos_angle(z);
+        jsum += stage_cost<KIND>(z, omc, u, u_last, cost);
+        pred.step(z, u, omc);
         u_last = u;
       }
     }
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128) cem_rollout_kernel(const CemArgs a) {
     float* p = a.log_traj_soa + (size_t)a.H * 6 * a.N + n;
     p[0] = z.th; p[a.N] = z.om; p[2 * a.N] = z.c; p[3 * a.N] = z.s; p[4 * (size_t)a.N] = z.x; p[5 * (size_t)a.N] = z.v;
   }
-  a.J[n] = (jsum + terminal_cost(z, a.cost)) / (float)(a.H + 1);
+  a.J[n] = (jsum + terminal_cost(z, cost)) - cost.shift;
 }
 
 // One block of 1024 threads: merge candidates -> global top-k (bitonic), regenerate elite Q, refit mu / sd.

@@ -7,123 +7,164 @@
 namespace ctk {
 
 // One rollout step shared by the segment loops: interpolated perturbation, clip, stage cost, MPPI correction, predictor.
-template <class Pred, int KIND, bool LOG>
-__device__ __forceinline__ void mppi_step(const MppiArgs& a, Pred& pred, State& z, float& cosang, float& u_last,
-                                          float& jsum, float& corr, float u_nom_t, float y0, float y1, float w0,
-                                          float w1, int t, int n, bool active) {
+// acc accumulates  mean-scaled stage cost + MPPI correction  (S = J + corr, optimizer_mppi.py:160) in one register.
+struct MppiK {  // loop-invariant scalars of K1, register-resident
+  float lo, hi, k_du2, k_udu;
+};
+
+// One rollout step: interpolated perturbation, clip, stage cost, MPPI correction, predictor.
+// acc accumulates  mean-scaled stage cost + MPPI correction  (S = J + corr, optimizer_mppi.py:160) in one register.
+template <class Pred, int KIND, bool LOG, bool SINGLE>
+__device__ __forceinline__ void mppi_step(const MppiArgs& a, const CostC& cost, const MppiK& k, Pred& pred, State& z, float& omc,
+                                          float& u_last, float& acc, float u_nom_t, float y0, float y1, float2 w, int t, int n,
+                                          bool active) {
   // Interpolator.py:97-106: delta_u[t] = sum_i y_i W[i,t]  (two non-zero terms)
-  const float du = fmaf(y1, w1, __fmul_rn(y0, w0));
-  const float u = fminf(fmaxf(__fadd_rn(u_nom_t, du), a.lo), a.hi);  // :186-187
+  const float du = fmaf(y1, w.y, __fmul_rn(y0, w.x));
+  const float u = fminf(fmaxf(__fadd_rn(u_nom_t, du), k.lo), k.hi);  // :186-187
   if (LOG && active) {
     float* p = a.log_traj_soa + (size_t)t * 6 * a.N + n;
     p[0] = z.th; p[a.N] = z.om; p[2 * a.N] = z.c; p[3 * a.N] = z.s; p[4 * (size_t)a.N] = z.x; p[5 * (size_t)a.N] = z.v;
     a.log_Q_soa[(size_t)t * a.N + n] = u;
   }
-  jsum += stage_cost<KIND>(z, cosang, u, u_last, a.cost);
-  // :154-155  cc_weight * (0.5(1-1/NU) R du^2 + R u du + 0.5 R u^2)
-  corr = fmaf(a.cc_weight, fmaf(a.coef_du2, du * du, fmaf(a.R * u, du, a.half_R * (u * u))), corr);
-  pred.step(z, u);
-  cosang = pred.cos_angle(z);
+  // cost.k_cc here carries  k_cc(cost) + cc_weight * 0.5 R  (both multiply u^2; merged by the caller)
+  stage_cost_acc<KIND>(acc, z, omc, u, u_last, cost);
+  // :154-155  cc_weight * (0.5(1-1/NU) R du^2 + R u du [+ 0.5 R u^2 merged above]) = du * (k_udu u + k_du2 du)
+  acc = fmaf(du, fmaf(k.k_du2, du, k.k_udu * u), acc);
+  if (SINGLE) pred.substep(z, u, omc); else pred.step(z, u, omc);
   u_last = u;
 }
 
+// K1.  One CTA per SM slot, grid-stride over rollouts (host sizes grid x block so that every thread runs the same
+// number of rollouts: no tail wave).  Per rollout iteration the block emits one softmin record [rho, a, b_z[n_ind]].
 template <class Pred, int KIND, bool LOG>
-__global__ void __launch_bounds__(128) mppi_rollout_kernel(const MppiArgs a) {
+__global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const MppiArgs a) {
   extern __shared__ float smem[];
   float* sh_unom = smem;                 // [H] shifted nominal
-  float* sh_w0 = sh_unom + a.H;          // [period]
-  float* sh_w1 = sh_w0 + a.period;       // [period]
-  float* sh_red = sh_w1 + a.period;      // [32] reduction scratch
-  float* sh_part = sh_red + 32;          // [4][n_ind + 1]
+  float2* sh_w = reinterpret_cast<float2*>(smem + ((a.H + 1) & ~1));  // [period] interpolation weights (w0, w1)
+  float* sh_red = reinterpret_cast<float*>(sh_w + a.period);          // [32] reduction scratch
+  float* sh_part = sh_red + 32;          // [32][n_ind + 1]
+  float* sh_z = sh_part + 32 * (a.n_ind + 1);  // [n_ind][blockDim] stash of this rollout's standard draws (if a.stash)
+  float* sh_pred = sh_z + (a.stash ? (size_t)a.n_ind * blockDim.x : 0);
 
   for (int t = threadIdx.x; t < a.H; t += blockDim.x) sh_unom[t] = a.u_nom[min(t + 1, a.H - 1)];
-  for (int j = threadIdx.x; j < a.period; j += blockDim.x) interp_weights(j, a.period, &sh_w0[j], &sh_w1[j]);
-  Pred pred(a.ode, a.mlp, sh_part + 4 * (a.n_ind + 1));
+  for (int j = threadIdx.x; j < a.period; j += blockDim.x) interp_weights(j, a.period, &sh_w[j].x, &sh_w[j].y);
+  Pred pred(a.kc, a.mlp, sh_pred);
+  CostC cost = load_cost(a.kc);
+  cost.k_cc += a.k_uu;  // the cost's own R u^2 term and the correction's 0.5 R u^2 share one FMA
+  const float* kx = a.kx;  // device copy of {lo, hi, k_du2, k_udu} (register-resident like the other constants)
+  const MppiK k = {vld(kx), vld(kx + 1), vld(kx + 2), vld(kx + 3)};
+  const float stdev = a.stdev;
+  const bool single = pred.single_substep();
   __syncthreads();
 
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = n < a.N;
-  const uint32_t ng = (uint32_t)(a.off + (active ? n : 0));
-
-  float S = INFINITY;
-  if (active || Pred::kCooperative) {
-    State z;
-    z.th = a.s0[0]; z.om = a.s0[1]; z.c = a.s0[2]; z.s = a.s0[3]; z.x = a.s0[4]; z.v = a.s0[5];
-    float cosang = cosf(z.th);  // spec: E_pot uses cos(angle); for t >= 1 the state's own cosine is that value
-    float u_last = a.u_prev[0];
-    float jsum = 0.0f, corr = 0.0f;
-    const int nlog = active ? n : 0;
-
-    float zz[4];
-    noise4(a.noise, ng, 0, zz);
-    float y_prev = __fmul_rn(zz[0], a.stdev);  // :173-175  normal * stdev (before interpolation)
-    int i = 1;                                  // next inducing point
-    int t = 0;
-    const int nblk = (a.n_ind + 3) >> 2;
-    for (int blk = 0; blk < nblk; ++blk) {
-      if (blk > 0) noise4(a.noise, ng, blk, zz);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (blk == 0 && q == 0) continue;
-        if (i >= a.n_ind) break;
-        const float y_cur = __fmul_rn(zz[q], a.stdev);
-        const int t_end = min(i * a.period, a.H);
-        for (int j = 0; t < t_end; ++t, ++j)
-          mppi_step<Pred, KIND, LOG>(a, pred, z, cosang, u_last, jsum, corr, sh_unom[t], y_prev, y_cur, sh_w0[j],
-                                     sh_w1[j], t, nlog, active);
-        y_prev = y_cur;
-        ++i;
-      }
-    }
-    // tail: t == (n_ind-1)*period == H-1 sits exactly on the last inducing point (weight 1)
-    for (; t < a.H; ++t)
-      mppi_step<Pred, KIND, LOG>(a, pred, z, cosang, u_last, jsum, corr, sh_unom[t], y_prev, 0.0f, 1.0f, 0.0f, t, nlog,
-                                 active);
-
-    if (LOG && active) {
-      float* p = a.log_traj_soa + (size_t)a.H * 6 * a.N + n;
-      p[0] = z.th; p[a.N] = z.om; p[2 * a.N] = z.c; p[3 * a.N] = z.s; p[4 * (size_t)a.N] = z.x; p[5 * (size_t)a.N] = z.v;
-    }
-    // Cost_Functions/__init__.py:90-92: mean over H+1 of [stage costs, terminal cost]; optimizer_mppi.py:160
-    const float Jt = (jsum + terminal_cost(z, a.cost)) / (float)(a.H + 1);
-    S = Jt + corr;
-    if (active) a.J[n] = S; else S = INFINITY;
-  }
-
-  // ---- block softmin partials (optimizer_mppi.py:163-168, restated per block; exact combine in K2) ----
-  const float rho_b = block_min(S, sh_red);
-  const float e = (active && S < INFINITY) ? expf((S - rho_b) * a.neg_inv_lbd) : 0.0f;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
   const int P = a.n_ind + 1;
-  {
-    const float ws = warp_sum(e);
-    if (lane == 0) sh_part[w * P] = ws;
-  }
+  const int stride = gridDim.x * blockDim.x;
   const int nblk = (a.n_ind + 3) >> 2;
-  for (int blk = 0; blk < nblk; ++blk) {
-    float zz[4];
-    noise4(a.noise, ng, blk, zz);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int i = blk * 4 + q;
-      if (i < a.n_ind) {
-        const float ws = warp_sum(e * zz[q]);
+  const State z0 = {a.s0[0], a.s0[1], a.s0[2], a.s0[3], a.s0[4], a.s0[5]};
+  const float omc0 = 1.0f - cosf(z0.th);  // spec: E_pot uses cos(angle); for t >= 1 the state carries 1 - cos
+  const float u_prev0 = a.u_prev[0];
+  float* sz = sh_z + tid;
+  const uint32_t a_unom = smem_u32(sh_unom), a_w = smem_u32(sh_w);
+
+  int iter = 0;
+  for (int base = blockIdx.x * blockDim.x; base < a.N; base += stride, ++iter) {
+    const int n = base + tid;
+    const bool active = n < a.N;
+    const uint32_t ng = (uint32_t)(a.off + (active ? n : 0));
+    float S = INFINITY;
+    if (active || Pred::kCooperative) {
+      State z = z0;
+      float omc = omc0, u_last = u_prev0, acc = 0.0f;
+      const int nlog = active ? n : 0;
+      // inducing-point draws arrive four at a time (one Philox block); zq is a rotating window, zq[0] = next draw
+      float zq[4];
+      noise4(a.noise, ng, 0, zq);
+      if (a.stash) sz[0] = zq[0];
+      float y_prev = __fmul_rn(zq[0], stdev);  // :173-175  normal * stdev (before interpolation)
+      zq[0] = zq[1]; zq[1] = zq[2]; zq[2] = zq[3];
+      int have = 3, nextblk = 1, i = 1;  // i = next inducing point to load
+      uint32_t pu = a_unom;
+      int t = 0;
+      while (t < a.H) {
+        // segment [t, t + cnt): interpolate between inducing points i-1 (y_prev) and i (y_cur)
+        float y_cur = 0.0f;  // past the last inducing point only j == 0 (weight 1 on y_prev) is ever evaluated
+        if (i < a.n_ind) {
+          if (have == 0) {
+            noise4(a.noise, ng, (uint32_t)nextblk, zq);
+            ++nextblk;
+            have = 4;
+          }
+          if (a.stash) sz[(size_t)i * blockDim.x] = zq[0];
+          y_cur = __fmul_rn(zq[0], stdev);
+          zq[0] = zq[1]; zq[1] = zq[2]; zq[2] = zq[3];
+          --have; ++i;
+        }
+        const int cnt = min(a.period, a.H - t);
+        uint32_t pw = a_w;
+        if (single) {
+#pragma unroll 2
+          for (int j = 0; j < cnt; ++j, pu += 4, pw += 8)
+            mppi_step<Pred, KIND, LOG, true>(a, cost, k, pred, z, omc, u_last, acc, lds_f32(pu), y_prev, y_cur, lds_f32x2(pw),
+                                             t + j, nlog, active);
+        } else {
+#pragma unroll 1
+          for (int j = 0; j < cnt; ++j, pu += 4, pw += 8)
+            mppi_step<Pred, KIND, LOG, false>(a, cost, k, pred, z, omc, u_last, acc, lds_f32(pu), y_prev, y_cur, lds_f32x2(pw),
+                                              t + j, nlog, active);
+        }
+        t += cnt;
+        y_prev = y_cur;
+      }
+
+      if (LOG && active) {
+        float* p = a.log_traj_soa + (size_t)a.H * 6 * a.N + n;
+        p[0] = z.th; p[a.N] = z.om; p[2 * a.N] = z.c; p[3 * a.N] = z.s; p[4 * (size_t)a.N] = z.x; p[5 * (size_t)a.N] = z.v;
+      }
+      // Cost_Functions/__init__.py:90-92 (mean over H+1 incl. the terminal cost, constants pre-scaled) ; optimizer_mppi.py:160
+      S = (acc + terminal_cost(z, cost)) - cost.shift;
+      if (active) a.J[n] = S; else S = INFINITY;
+    }
+
+    // ---- block softmin record (optimizer_mppi.py:163-168 restated per block; exact combine in K2) ----
+    const float rho_b = block_min(S, sh_red);
+    const float e = (active && S < INFINITY) ? expf((S - rho_b) * a.neg_inv_lbd) : 0.0f;
+    {
+      const float ws = warp_sum(e);
+      if (lane == 0) sh_part[w * P] = ws;
+    }
+    if (a.stash) {
+      for (int i = 0; i < a.n_ind; ++i) {
+        const float ws = warp_sum(e * sz[(size_t)i * blockDim.x]);
         if (lane == 0) sh_part[w * P + 1 + i] = ws;
       }
+    } else {
+      for (int blk = 0; blk < nblk; ++blk) {
+        float zz[4];
+        noise4(a.noise, ng, blk, zz);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = blk * 4 + q;
+          if (i < a.n_ind) {
+            const float ws = warp_sum(e * zz[q]);
+            if (lane == 0) sh_part[w * P + 1 + i] = ws;
+          }
+        }
+      }
     }
+    __syncthreads();
+    float* out = a.partials + ((size_t)iter * gridDim.x + blockIdx.x) * (P + 1);
+    for (int c = tid; c < P; c += blockDim.x) {
+      float s = 0.0f;
+      for (int ww = 0; ww < nw; ++ww) s += sh_part[ww * P + c];
+      out[1 + c] = s;
+    }
+    if (tid == 0) out[0] = rho_b;
+    __syncthreads();
   }
-  __syncthreads();
-  const int nw = blockDim.x >> 5;
-  float* out = a.partials + (size_t)blockIdx.x * (P + 1);
-  for (int c = threadIdx.x; c < P; c += blockDim.x) {
-    float acc = 0.0f;
-    for (int ww = 0; ww < nw; ++ww) acc += sh_part[ww * P + c];
-    out[1 + c] = acc;
-  }
-  if (threadIdx.x == 0) out[0] = rho_b;
 }
 
-__global__ void __launch_bounds__(256) mppi_combine_kernel(const float* __restrict__ in, int cnt, int n_ind,
+__global__ void __launch_bounds__(1024) mppi_combine_kernel(const float* __restrict__ in, int cnt, int n_ind,
                                                            float neg_inv_lbd, float* __restrict__ record_out,
                                                            const MppiFinalize fin) {
   extern __shared__ float smem[];

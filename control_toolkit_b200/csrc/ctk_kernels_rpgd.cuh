@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(32) rpgd_grad_kernel(const RpgdGradArgs a) {
   const float w = a.cost.inv_Hp1;
   State z0;
   z0.th = a.s0[0]; z0.om = a.s0[1]; z0.c = a.s0[2]; z0.s = a.s0[3]; z0.x = a.s0[4]; z0.v = a.s0[5];
-  const float cos0 = cosf(z0.th);
+  const float omc0 = 1.0f - cosf(z0.th);
 
   for (int t = 0; t < a.H; ++t) sq[t * B + tid] = a.Q[(size_t)t * a.N + n];
 
@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(32) rpgd_grad_kernel(const RpgdGradArgs a) {
     for (int t = 0; t < a.H; ++t) {
       float* p = tp + (size_t)t * 6 * B + tid;
       p[0] = z.th; p[B] = z.om; p[2 * B] = z.c; p[3 * B] = z.s; p[4 * B] = z.x; p[5 * B] = z.v;
-      ode_step(z, sq[t * B + tid], a.ode);
+      float omc_unused;
+      ode_step(z, sq[t * B + tid], a.fwd, omc_unused);
     }
     // ---- reverse: lambda_H = d(terminal)/ds = 0 (indicator); dJ/dQ_t (optimizer_rpgd.py:314) ----
     Adj lam = {0.f, 0.f, 0.f, 0.f};
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(32) rpgd_grad_kernel(const RpgdGradArgs a) {
 
   // ---- get_action rollout (:342): cost of the updated population ----
   State z = z0;
-  float cosang = cos0, u_last = u_prev, jsum = 0.0f;
+  float omc = omc0, u_last = u_prev, jsum = 0.0f;
   for (int t = 0; t < a.H; ++t) {
     const float u = sq[t * B + tid];
     a.Q[(size_t)t * a.N + n] = u;
@@ -92,16 +93,15 @@ __global__ void __launch_bounds__(32) rpgd_grad_kernel(const RpgdGradArgs a) {
       float* p = a.log_traj_soa + (size_t)t * 6 * a.N + n;
       p[0] = z.th; p[a.N] = z.om; p[2 * a.N] = z.c; p[3 * a.N] = z.s; p[4 * (size_t)a.N] = z.x; p[5 * (size_t)a.N] = z.v;
     }
-    jsum += stage_cost<KIND>(z, cosang, u, u_last, a.cost);
-    ode_step(z, u, a.ode);
-    cosang = z.c;
+    jsum += stage_cost<KIND>(z, omc, u, u_last, a.cost);
+    ode_step(z, u, a.fwd, omc);
     u_last = u;
   }
   if (LOG) {
     float* p = a.log_traj_soa + (size_t)a.H * 6 * a.N + n;
     p[0] = z.th; p[a.N] = z.om; p[2 * a.N] = z.c; p[3 * a.N] = z.s; p[4 * (size_t)a.N] = z.x; p[5 * (size_t)a.N] = z.v;
   }
-  a.J[n] = (jsum + terminal_cost(z, a.cost)) / (float)(a.H + 1);
+  a.J[n] = (jsum + terminal_cost(z, a.cost)) - a.cost.shift;
 }
 
 // sample_actions (:275-296) for one new row at horizon step t: clip(z*scale+offset) on inducing points, interpolate

@@ -8,7 +8,8 @@
 namespace ctk {
 
 // pred: 0 ODE, 1 MLP (SIMT engine); kind: cost class; log: write SoA trajectory logs
-cudaError_t launch_mppi_rollout(int pred, int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const MppiArgs& a);
+cudaError_t launch_mppi_rollout(int pred, int kind, bool log, int nblocks, int block, size_t smem, cudaStream_t st, const MppiArgs& a);
+int mppi_max_block_threads(int pred);
 cudaError_t launch_mppi_combine(const float* in, int cnt, int n_ind, float neg_inv_lbd, float* record_out,
                                 const MppiFinalize& fin, cudaStream_t st);
 cudaError_t launch_transpose(const float* in, float* out, int R, int C, cudaStream_t st);
@@ -22,8 +23,7 @@ cudaError_t launch_rpgd_grad(int kind, bool log, int nblocks, int block, size_t 
 cudaError_t launch_rpgd_select(const RpgdSelectArgs& a, cudaStream_t st);
 cudaError_t launch_rpgd_init(const RpgdSelectArgs& a, cudaStream_t st);
 
-cudaError_t launch_single_rollout(int pred, const float* s0, const float* Q, int H, const OdeC& ode, const CostC& cost,
-                                  const MlpDev& mlp, const float* u_prev, float* traj, float* summed, cudaStream_t st);
+cudaError_t launch_single_rollout(int pred, const float* s0, const float* Q, int H, const DevConsts* kc, const MlpDev& mlp, const float* u_prev, float* traj, float* summed, cudaStream_t st);
 cudaError_t launch_fma_peak(float* out, int blocks, int threads, int iters, cudaStream_t st);
 cudaError_t launch_philox_fill(const NoiseSrc& ns, float* out, size_t n, cudaStream_t st);
 

@@ -16,11 +16,20 @@
 
 namespace ctk {
 
-// Device-side constant blocks (derived on the host from ctk_ode_params / ctk_cost_params in float64).
+// Device-side constant blocks (derived on the host from ctk_ode_params / ctk_cost_params in float64, ctk_derive.h).
 struct OdeC {
   float u_max, kp1_Mm, m, neg_M_fric, neg_J_fric, mg, inv_L, kp1, mL, inv_mL, g, inv_kp1L, h;
+  float kTl, kTm, hk;  // neg_J_fric/L, neg_J_fric/(m L), h/((k+1) L): merged forward constants
   // adjoint-only compounds
   float two_m, two_kp1_mL, kp1_neg_M_fric, g_inv_kp1L, inv_mL_kp1L;
+  int isteps;
+};
+
+// Forward-pass constants of the ODE, divided through by the pole mass m (9 instead of 12, and u_max folded in):
+//   vd = num / A,  num/m = cF v + cU Q - (kp1L w^2) s + g s c + (cTl w) c,   A/m = K1p - c^2
+struct FwdK {
+  float K1p, kp1L, cF, cU, g, cTl, kTm, h, hk;
+  float k0s, k0c;  // leading sincos_half coefficients (register-resident copies)
   int isteps;
 };
 
@@ -29,7 +38,9 @@ struct CostC {
   float dd_weight, ep_weight, ekp_weight, cc_weight, ccrc_weight, R, MAX_COST;
   float inv_two_thl, thl_095, inv_thl_005, thl_09, thl_01;
   float target_position, target_equilibrium;
-  float inv_Hp1;  // 1/(H+1) for the adjoint scaling
+  float inv_Hp1;  // 1/(H+1): the trajectory cost is a MEAN over H+1 terms (Cost_Functions/__init__.py:92)
+  // forward constants, pre-multiplied by 1/(H+1) so the rollout accumulates the mean directly
+  float k_dd, k_bar, k_ep, k_ekp, k_cc, k_ccrc, k_border, k_term, shift;
 };
 
 struct State {
@@ -48,69 +59,103 @@ CTK_HD float wrap_angle(float th) {
   return fmaf(-k, kTwoPiLo, th);
 }
 
-CTK_HD void sincos_acc(float x, float* s, float* c) {
-#ifdef __CUDA_ARCH__
-  sincosf(x, s, c);
+// sin, cos and 1-cos of an angle in [-pi, pi] without range reduction, quadrant logic or branches: minimax
+// polynomials (max error 4.3e-9 / 2.2e-10 before rounding) for sqrt(2) sin(x), sqrt(2) cos(x) at the HALF angle
+// x = th/2, written in the variable x' = th/sqrt(2); then sin th = sh ch, 1 - cos th = sh^2, cos th = 1 - sh^2.
+// 15 FP32-pipe instructions, no MUFU.  k0s / k0c: the two leading coefficients, passed in so that callers can keep them
+// register-resident (an FFMA takes only one immediate).
+constexpr float kSinHalfLead = 1.6282471904105478e-07f;
+constexpr float kCosHalfLead = -1.1513114017702719e-08f;
+CTK_HD void sincos_half(float th, float* s, float* c, float* omc, float k0s = kSinHalfLead, float k0c = kCosHalfLead) {
+#if defined(CTK_ACCURATE_SINCOS) && defined(__CUDA_ARCH__)
+  sincosf(th, s, c);
+  *omc = 1.0f - *c;
+  return;
+#endif
+  const float x = 0.70710678118654752f * th;
+  const float t = x * x;
+  float ps = fmaf(t, k0s, -2.4761327949818224e-05f);
+  ps = fmaf(t, ps, 0.002083262661471963f);
+  ps = fmaf(t, ps, -0.08333329111337662f);
+  const float sh = fmaf(x * t, ps, x);  // sqrt(2) sin(th/2)
+  float pc = fmaf(t, k0c, 2.1885084606765304e-06f);
+  pc = fmaf(t, pc, -0.0002455138601362705f);
+  pc = fmaf(t, pc, 0.01473138015717268f);
+  pc = fmaf(t, pc, -0.3535533845424652f);
+  const float ch = fmaf(t, pc, 1.4142135381698608f);  // sqrt(2) cos(th/2)
+  *omc = sh * sh;
+  *c = fmaf(-sh, sh, 1.0f);
+  *s = sh * ch;
+}
+
+CTK_HD float fast_rcp(float a) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));  // 1 MUFU, <= 1 ulp; a = A is in [0.33, 0.43]
+  return r;
 #else
-  *s = sinf(x);
-  *c = cosf(x);
+  return 1.0f / a;
 #endif
 }
 
-CTK_HD float fast_div(float a, float b) {
-#ifdef __CUDA_ARCH__
-  return __fdividef(a, b);  // <= 2 ulp; b = A is in [0.33, 0.43]
-#else
-  return a / b;
-#endif
+// One Euler sub-step with the OLD derivatives, then wrap, c = cos, s = sin.  omc returns 1 - cos(angle) of the new
+// state (the E_pot cost term needs it).  17 + 4 + 17 FP32-pipe instructions + 1 MUFU.
+CTK_HD void ode_substep(State& z, float Q, const FwdK& p, float& omc) {
+  const float w2 = z.om * z.om;
+  const float gs = p.g * z.s;
+  float n = p.cF * z.v;
+  n = fmaf(p.cU, Q, n);
+  n = fmaf(-(p.kp1L * w2), z.s, n);
+  n = fmaf(gs, z.c, n);
+  n = fmaf(p.cTl * z.om, z.c, n);
+  const float Ap = fmaf(-z.c, z.c, p.K1p);
+  const float vd = n * fast_rcp(Ap);
+  const float X = fmaf(vd, z.c, fmaf(p.kTm, z.om, gs));
+  z.th = fmaf(z.om, p.h, z.th);
+  z.om = fmaf(X, p.hk, z.om);
+  z.x = fmaf(z.v, p.h, z.x);
+  z.v = fmaf(vd, p.h, z.v);
+  z.th = wrap_angle(z.th);
+  sincos_half(z.th, &z.s, &z.c, &omc, p.k0s, p.k0c);
 }
 
-// One predictor step s_{t+1} = f(s_t, Q).  Explicit Euler with the OLD derivatives, then c = cos, s = sin, wrap.
-CTK_HD void ode_step(State& z, float Q, const OdeC& p) {
-  const float u = p.u_max * Q;
-  for (int i = 0; i < p.isteps; ++i) {
-    const float A = fmaf(-p.m, z.c * z.c, p.kp1_Mm);
-    const float F = p.neg_M_fric * z.v;
-    const float T = p.neg_J_fric * z.om;
-    const float inner = (F + u) - (p.mL * (z.om * z.om)) * z.s;
-    const float num = fmaf(p.kp1, inner, fmaf(p.mg * z.s, z.c, (T * z.c) * p.inv_L));
-    const float vd = fast_div(num, A);
-    const float wd = (fmaf(p.g, z.s, fmaf(vd, z.c, T * p.inv_mL))) * p.inv_kp1L;
-    z.th = fmaf(z.om, p.h, z.th);
-    z.om = fmaf(wd, p.h, z.om);
-    z.x = fmaf(z.v, p.h, z.x);
-    z.v = fmaf(vd, p.h, z.v);
-    z.th = wrap_angle(z.th);
-    sincos_acc(z.th, &z.s, &z.c);
-  }
+// One predictor step s_{t+1} = f(s_t, Q): intermediate_steps Euler sub-steps of h = dt / intermediate_steps.
+CTK_HD void ode_step(State& z, float Q, const FwdK& p, float& omc) {
+  ode_substep(z, Q, p, omc);
+  for (int i = 1; i < p.isteps; ++i) ode_substep(z, Q, p, omc);  // headline config: isteps == 1, loop not taken
 }
 
-// Stage cost l(s_t, u_t, u_{t-1}) - MAX_COST.  cos_angle = cos(angle) (the state's own cosine for t >= 1).
+// acc += (stage cost l(s_t, u_t, u_{t-1})) / (H+1), without the MAX_COST shift (applied once per trajectory:
+// CostC::shift).  omc = 1 - cos(angle).
 template <int KIND>
-CTK_HD float stage_cost(const State& z, float cos_angle, float u, float u_prev, const CostC& k) {
-  const float d = (z.x - k.target_position) * k.inv_two_thl;
+CTK_HD void stage_cost_acc(float& acc, const State& z, float omc, float u, float u_prev, const CostC& k) {
+  const float d = z.x - k.target_position;
   const float ax = fabsf(z.x);
-  const float e = (ax - k.thl_095) * k.inv_thl_005;
-  float dd = d * d;
-  dd += (ax > k.thl_095) ? (1.0e9f * e) * e : 0.0f;
-  const float omc = 1.0f - cos_angle;
-  const float ep = (k.target_equilibrium * 0.25f) * (omc * omc);
+  const float e = fmaxf(ax - k.thl_095, 0.0f);  // == indicator(|x| > 0.95 THL) * (|x| - 0.95 THL)
   const float du = u - u_prev;
-  float l = k.dd_weight * dd;
-  l = fmaf(k.ep_weight, ep, l);
-  if (KIND == 1) l = fmaf(k.ekp_weight, z.om * z.om, l);
-  l = fmaf(k.cc_weight * k.R, u * u, l);
-  l = fmaf(k.ccrc_weight, du * du, l);
-  if (KIND == 1) l += (ax > k.thl_09) ? 1.0e7f : 0.0f;
-  return l - k.MAX_COST;
+  acc = fmaf(k.k_dd * d, d, acc);
+  acc = fmaf(k.k_bar * e, e, acc);
+  acc = fmaf(k.k_ep * omc, omc, acc);
+  if (KIND == 1) acc = fmaf(k.k_ekp * z.om, z.om, acc);
+  acc = fmaf(k.k_cc * u, u, acc);
+  acc = fmaf(k.k_ccrc * du, du, acc);
+  if (KIND == 1) acc += (ax > k.thl_09) ? k.k_border : 0.0f;
 }
 
-CTK_HD float stage_cost_dyn(int kind, const State& z, float cos_angle, float u, float u_prev, const CostC& k) {
-  return kind == 0 ? stage_cost<0>(z, cos_angle, u, u_prev, k) : stage_cost<1>(z, cos_angle, u, u_prev, k);
+template <int KIND>
+CTK_HD float stage_cost(const State& z, float omc, float u, float u_prev, const CostC& k) {
+  float l = 0.0f;
+  stage_cost_acc<KIND>(l, z, omc, u, u_prev, k);
+  return l;
 }
 
+CTK_HD float stage_cost_dyn(int kind, const State& z, float omc, float u, float u_prev, const CostC& k) {
+  return kind == 0 ? stage_cost<0>(z, omc, u, u_prev, k) : stage_cost<1>(z, omc, u, u_prev, k);
+}
+
+// terminal cost / (H+1)
 CTK_HD float terminal_cost(const State& z, const CostC& k) {
-  return (fabsf(z.th) > 0.2f || fabsf(z.x - k.target_position) > k.thl_01) ? 10000.0f : 0.0f;
+  return (fabsf(z.th) > 0.2f || fabsf(z.x - k.target_position) > k.thl_01) ? k.k_term : 0.0f;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -130,7 +175,7 @@ CTK_HD float ode_step_adjoint(const State& z /*state before the step*/, float Q,
   const float F = p.neg_M_fric * z.v;
   const float inner = (F + u) - (p.mL * (z.om * z.om)) * z.s;
   const float num = fmaf(p.kp1, inner, fmaf(p.mg * z.s, z.c, (T * z.c) * p.inv_L));
-  const float invA = 1.0f / A;
+  const float invA = fast_rcp(A);
   const float vd = num * invA;
 
   const float gwd = lam.om * p.h;                             // d/d(wd)

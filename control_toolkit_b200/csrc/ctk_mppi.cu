@@ -5,29 +5,31 @@
 namespace ctk {
 
 template <class Pred, int KIND, bool LOG>
-static cudaError_t launch_mppi_t(int nblocks, size_t smem, cudaStream_t st, const MppiArgs& a) {
+static cudaError_t launch_mppi_t(int nblocks, int block, size_t smem, cudaStream_t st, const MppiArgs& a) {
   auto k = mppi_rollout_kernel<Pred, KIND, LOG>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  k<<<nblocks, 128, smem, st>>>(a);
+  k<<<nblocks, block, smem, st>>>(a);
   return cudaGetLastError();
 }
 template <class Pred>
-static cudaError_t launch_mppi_p(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const MppiArgs& a) {
-  if (kind == 0) return log ? launch_mppi_t<Pred, 0, true>(nblocks, smem, st, a) : launch_mppi_t<Pred, 0, false>(nblocks, smem, st, a);
-  return log ? launch_mppi_t<Pred, 1, true>(nblocks, smem, st, a) : launch_mppi_t<Pred, 1, false>(nblocks, smem, st, a);
+static cudaError_t launch_mppi_p(int kind, bool log, int nblocks, int block, size_t smem, cudaStream_t st, const MppiArgs& a) {
+  if (kind == 0) return log ? launch_mppi_t<Pred, 0, true>(nblocks, block, smem, st, a) : launch_mppi_t<Pred, 0, false>(nblocks, block, smem, st, a);
+  return log ? launch_mppi_t<Pred, 1, true>(nblocks, block, smem, st, a) : launch_mppi_t<Pred, 1, false>(nblocks, block, smem, st, a);
 }
-cudaError_t launch_mppi_rollout(int pred, int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const MppiArgs& a) {
-  return pred == 0 ? launch_mppi_p<OdePred>(kind, log, nblocks, smem, st, a) : launch_mppi_p<MlpSimtPred>(kind, log, nblocks, smem, st, a);
+cudaError_t launch_mppi_rollout(int pred, int kind, bool log, int nblocks, int block, size_t smem, cudaStream_t st, const MppiArgs& a) {
+  return pred == 0 ? launch_mppi_p<OdePred>(kind, log, nblocks, block, smem, st, a)
+                   : launch_mppi_p<MlpSimtPred>(kind, log, nblocks, block, smem, st, a);
 }
+int mppi_max_block_threads(int pred) { return pred == 0 ? OdePred::kMaxThreads : MlpSimtPred::kMaxThreads; }
 size_t mppi_pred_smem_floats(int pred, const MlpDev& m) { return pred == 0 ? 0 : MlpSimtPred::smem_floats(m); }
 
 cudaError_t launch_mppi_combine(const float* in, int cnt, int n_ind, float neg_inv_lbd, float* record_out,
                                 const MppiFinalize& fin, cudaStream_t st) {
   const size_t sm = sizeof(float) * (32 + 2 + n_ind + (fin.enable ? fin.H : 0));
-  mppi_combine_kernel<<<1, 256, sm, st>>>(in, cnt, n_ind, neg_inv_lbd, record_out, fin);
+  mppi_combine_kernel<<<1, 1024, sm, st>>>(in, cnt, n_ind, neg_inv_lbd, record_out, fin);
   return cudaGetLastError();
 }
 
@@ -39,32 +41,31 @@ cudaError_t launch_transpose(const float* in, float* out, int R, int C, cudaStre
 
 // nominal single rollout (reference optimizer_mppi.py:199-202 predict_optimal_trajectory, optimizer_rpgd.py:382-386)
 template <class Pred>
-__global__ void single_rollout_kernel(const float* s0, const float* Q, int H, OdeC ode, CostC cost, MlpDev mlp,
+__global__ void single_rollout_kernel(const float* s0, const float* Q, int H, const DevConsts* kc, MlpDev mlp,
                                       const float* u_prev, float* traj, float* summed) {
   extern __shared__ float smem[];
-  Pred pred(ode, mlp, smem);
+  Pred pred(kc, mlp, smem);
+  const CostC cost = kc->cost;
   __syncthreads();
   if (threadIdx.x != 0) return;
   State z;
   z.th = s0[0]; z.om = s0[1]; z.c = s0[2]; z.s = s0[3]; z.x = s0[4]; z.v = s0[5];
-  float cosang = cosf(z.th), ul = u_prev[0], sum = 0.0f;
+  float omc = 1.0f - cosf(z.th), ul = u_prev[0], sum = 0.0f;
   for (int t = 0; t <= H; ++t) {
     float* p = traj + t * 6;
     p[0] = z.th; p[1] = z.om; p[2] = z.c; p[3] = z.s; p[4] = z.x; p[5] = z.v;
     if (t == H) break;
     const float u = Q[t];
-    sum += stage_cost_dyn(cost.kind, z, cosang, u, ul, cost);  // get_summed_stage_cost (Cost_Functions/__init__.py:71-72)
-    pred.step(z, u);
-    cosang = pred.cos_angle(z);
+    sum += stage_cost_dyn(cost.kind, z, omc, u, ul, cost);  // get_summed_stage_cost (Cost_Functions/__init__.py:71-72)
+    pred.step(z, u, omc);
     ul = u;
   }
-  summed[0] = sum;
+  summed[0] = (sum - cost.shift) * (float)(H + 1);  // the device constants carry the 1/(H+1) of the trajectory mean
 }
 
-cudaError_t launch_single_rollout(int pred, const float* s0, const float* Q, int H, const OdeC& ode, const CostC& cost,
-                                  const MlpDev& mlp, const float* u_prev, float* traj, float* summed, cudaStream_t st) {
+cudaError_t launch_single_rollout(int pred, const float* s0, const float* Q, int H, const DevConsts* kc, const MlpDev& mlp, const float* u_prev, float* traj, float* summed, cudaStream_t st) {
   if (pred == 0) {
-    single_rollout_kernel<OdePred><<<1, 32, 0, st>>>(s0, Q, H, ode, cost, mlp, u_prev, traj, summed);
+    single_rollout_kernel<OdePred><<<1, 32, 0, st>>>(s0, Q, H, kc, mlp, u_prev, traj, summed);
     return cudaGetLastError();
   }
   const size_t smem = sizeof(float) * MlpSimtPred::smem_floats(mlp);
@@ -73,7 +74,7 @@ cudaError_t launch_single_rollout(int pred, const float* s0, const float* Q, int
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  k<<<1, 128, smem, st>>>(s0, Q, H, ode, cost, mlp, u_prev, traj, summed);
+  k<<<1, 128, smem, st>>>(s0, Q, H, kc, mlp, u_prev, traj, summed);
   return cudaGetLastError();
 }
 

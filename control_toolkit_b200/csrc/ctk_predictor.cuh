@@ -5,16 +5,23 @@
 //                 shared memory).  Numerical anchor for the tcgen05 engine (ctk_mlp_tc.cuh).
 #pragma once
 #include "ctk_args.cuh"
+#include "ctk_device.cuh"
 
 namespace ctk {
 
 struct OdePred {
   static constexpr bool kCooperative = false;
-  const OdeC& p;
-  __device__ __forceinline__ OdePred(const OdeC& ode, const MlpDev&, float*) : p(ode) {}
-  __device__ __forceinline__ void step(State& z, float u) const { ode_step(z, u, p); }
-  // cos(angle) of the E_pot cost: the ODE state carries it (angle = wrap of the integrated angle)
-  __device__ __forceinline__ float cos_angle(const State& z) const { return z.c; }
+#ifndef CTK_ODE_MAX_THREADS
+#define CTK_ODE_MAX_THREADS 1024
+#endif
+  static constexpr int kMaxThreads = CTK_ODE_MAX_THREADS;
+  const FwdK p;  // forward constants, register-resident (ctk_device.cuh load_fwd)
+  __device__ __forceinline__ OdePred(const DevConsts* kc, const MlpDev&, float*) : p(load_fwd(kc)) {}
+  // omc = 1 - cos(angle) of the new state (E_pot cost term)
+  __device__ __forceinline__ void step(State& z, float u, float& omc) const { ode_step(z, u, p, omc); }
+  // intermediate_steps == 1 fast path (no sub-step loop in the rollout's inner loop)
+  __device__ __forceinline__ void substep(State& z, float u, float& omc) const { ode_substep(z, u, p, omc); }
+  __device__ __forceinline__ bool single_substep() const { return p.isteps == 1; }
   static size_t smem_floats(const MlpDev&) { return 0; }
 };
 
@@ -31,9 +38,10 @@ __device__ __forceinline__ float tanh_acc(float x) {
 
 struct MlpSimtPred {
   static constexpr bool kCooperative = false;
+  static constexpr int kMaxThreads = 128;
   int hid;
   const float *W1, *b1, *W2, *b2, *W3T, *b3;  // shared memory
-  __device__ __forceinline__ MlpSimtPred(const OdeC&, const MlpDev& m, float* sm) {
+  __device__ __forceinline__ MlpSimtPred(const DevConsts*, const MlpDev& m, float* sm) {
     // 16-byte align the weight block
     float* base = (float*)(((uintptr_t)sm + 15) & ~(uintptr_t)15);
     hid = m.hidden;
@@ -47,10 +55,12 @@ struct MlpSimtPred {
     // caller issues __syncthreads() after construction
   }
   static size_t smem_floats(const MlpDev& m) { return (size_t)m.blob_floats + 4; }
+  __device__ __forceinline__ void substep(State& z, float u, float& omc) const { step(z, u, omc); }
+  __device__ __forceinline__ bool single_substep() const { return false; }
 
   // net input [Q, angleD, cos, sin, position, positionD] -> next [angleD, cos, sin, position, positionD];
   // angle = atan2(sin, cos)  (oracle/spec.py MLPPredictor.step)
-  __device__ __noinline__ void step(State& z, float u) const {
+  __device__ __noinline__ void step(State& z, float u, float& omc) const {
     constexpr int HMAX = 128;
     float h1[HMAX];
     const float x[6] = {u, z.om, z.c, z.s, z.x, z.v};
@@ -95,9 +105,9 @@ struct MlpSimtPred {
     z.x = y[3] + b3[3];
     z.v = y[4] + b3[4];
     z.th = atan2f(z.s, z.c);
+    // the network's (cos, sin) outputs are not normalised: cos(atan2(s, c)) = c / hypot(s, c)
+    omc = 1.0f - z.c * rsqrtf(fmaf(z.c, z.c, z.s * z.s));
   }
-  // the network's (cos, sin) outputs are not normalised: cos(atan2(s, c)) = c / hypot(s, c)
-  __device__ __forceinline__ float cos_angle(const State& z) const { return z.c * rsqrtf(fmaf(z.c, z.c, z.s * z.s)); }
 };
 
 }  // namespace ctk

@@ -1,0 +1,112 @@
+"""Sharding of the rollout population over the GPUs of one box (one process per GPU, torch.distributed / NCCL).
+
+The path shards naturally by sample: rank r evaluates the global rollout ids
+[offset_r, offset_r + count_r).  Philox counters and the injected-noise buffer are indexed by GLOBAL id, so the
+sampled population is independent of the number of shards.  Per tick the only exchange is
+
+* MPPI : one all-gather of the per-shard softmin record [rho_r, a_r, b_z,r[n_ind]]   (n_ind + 2 floats),
+* CEM  : per outer iteration one all-gather of k (ordered-cost, global-id) keys       (2k floats); the elite control
+         rows are regenerated from the counter-based noise on every rank, never sent,
+* RPGD : none (replicas only).
+
+Every rank then runs the same combine/update kernel on the gathered records, so the optimizer state stays replicated.
+torch.distributed is plumbing only (rendezvous + the NCCL all-gather on the handle's stream).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def shard_geometry(n_global: int, rank: int, world_size: int):
+    """Contiguous split; the first (n_global % world_size) ranks get one extra rollout.  -> (offset, count)"""
+    base, rem = divmod(int(n_global), int(world_size))
+    count = base + (1 if rank < rem else 0)
+    offset = rank * base + min(rank, rem)
+    return offset, count
+
+
+class _DevArray:
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class ShardPlan:
+    def __init__(self, rank: int = 0, world_size: int = 1, group=None):
+        self.rank, self.world_size, self.group = int(rank), int(world_size), group
+        self._bufs = {}
+
+    @staticmethod
+    def from_env():
+        """One process per GPU launched by torchrun: RANK / WORLD_SIZE from the environment."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return ShardPlan(dist.get_rank(), dist.get_world_size())
+        return ShardPlan(0, 1)
+
+    def local_count(self, n_global: int) -> int:
+        return shard_geometry(n_global, self.rank, self.world_size)[1]
+
+    def local_offset(self, n_global: int) -> int:
+        return shard_geometry(n_global, self.rank, self.world_size)[0]
+
+    # -- exchange -------------------------------------------------------------------------------------------------
+    def all_gather(self, record):
+        """record: 1-D torch tensor (CUDA under NCCL, CPU under gloo) -> [world_size * len(record)] tensor."""
+        import torch
+        import torch.distributed as dist
+        key = (record.device, record.numel(), record.dtype)
+        out = self._bufs.get(key)
+        if out is None:
+            out = torch.empty(self.world_size * record.numel(), dtype=record.dtype, device=record.device)
+            self._bufs[key] = out
+        if self.world_size == 1:
+            out.copy_(record)
+        else:
+            dist.all_gather_into_tensor(out, record, group=self.group)
+        return out
+
+    # -- one sharded tick through the C ABI -----------------------------------------------------------------------
+    def attach(self, opt, lib) -> None:
+        """Run the handle on torch's current stream so the NCCL all-gather is ordered with the kernels."""
+        import torch
+        torch.cuda.set_device(opt.device)
+        L.check(lib.ctk_set_stream(opt._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        opt._shard_attached = True
+
+    def run_tick_device(self, opt, lib, s_dev_ptr: int, u_dev_ptr: int) -> None:
+        """Asynchronous sharded tick: s and u stay on the device (used by bench.py's device-resident timing)."""
+        import torch
+        while True:
+            more = L.check(lib.ctk_step_local(opt._h, C.c_void_p(s_dev_ptr)))
+            ptr, n = C.c_void_p(), C.c_size_t()
+            L.check(lib.ctk_partials(opt._h, C.byref(ptr), C.byref(n)))
+            if n.value:
+                rec = torch.as_tensor(_DevArray(ptr.value, n.value), device=f"cuda:{opt.device}")
+                gathered = self.all_gather(rec)
+                gptr = gathered.data_ptr()
+            else:
+                gptr = 0
+            L.check(lib.ctk_step_finish(opt._h, C.c_void_p(gptr), self.world_size if n.value else 1, C.c_void_p(u_dev_ptr)))
+            if not more:
+                break
+
+    def run_tick(self, opt, lib, s32: np.ndarray) -> np.ndarray:
+        """Sharded tick with host in / host out (the optimizer plugin's step())."""
+        import torch
+        if not getattr(opt, "_shard_attached", False):
+            self.attach(opt, lib)
+        dev = f"cuda:{opt.device}"
+        if not hasattr(opt, "_s_pin"):
+            opt._s_pin = torch.empty(6, dtype=torch.float32).pin_memory()
+            opt._s_dev = torch.empty(6, dtype=torch.float32, device=dev)
+            opt._u_dev = torch.zeros(4, dtype=torch.float32, device=dev)
+        opt._s_pin.copy_(torch.from_numpy(s32))
+        opt._s_dev.copy_(opt._s_pin, non_blocking=True)
+        self.run_tick_device(opt, lib, opt._s_dev.data_ptr(), opt._u_dev.data_ptr())
+        return opt._u_dev[:1].cpu().numpy()

@@ -170,6 +170,11 @@ int ctk_set_counter(ctk_handle *h, int which, int64_t value);
 int ctk_get_log(ctk_handle *h, int which, void *dst_host, size_t n_bytes);
 /* number of CUDA kernels this handle has launched since create (bench.py "gpu_launches")                         */
 int ctk_get_launch_count(ctk_handle *h, int64_t *value);
+/* CUDA-event timing of the dominant kernel of a tick (the fused rollout kernel: K1 MPPI, K3 CEM, K6/K7 RPGD), used by
+   bench.py for roofline.achieved.  enable(on) resets the accumulator; get() synchronises the stream and returns the
+   summed duration and the number of timed launches since enable().                                                */
+int ctk_enable_kernel_timing(ctk_handle *h, int on);
+int ctk_get_kernel_timing(ctk_handle *h, double *ms_sum, int64_t *n_launches);
 /* standalone nominal rollout of one control sequence (reference optimizer_mppi.py:199-202 predict_optimal_trajectory,
    optimizer_rpgd.py:382-386): s_host [ns], Q_host [H] -> traj_host [H+1, ns], summed stage cost (may be NULL).     */
 int ctk_rollout_single(ctk_handle *h, const float *s_host, const float *Q_host, float *traj_host, float *summed_stage_cost);

@@ -17,7 +17,8 @@ from . import spec
 class CEMOracle:
     def __init__(self, predictor, cost: spec.CostParams, *, mpc_horizon, num_rollouts, cem_outer_it,
                  cem_initial_action_stdev, cem_stdev_min, cem_best_k, warmup=False, warmup_iterations=0,
-                 action_low=-1.0, action_high=1.0, **_ignored):
+                 action_low=-1.0, action_high=1.0, dtype=torch.float32, **_ignored):
+        self.dtype = dtype
         self.predictor = predictor
         self.cost = cost
         self.H, self.N = int(mpc_horizon), int(num_rollouts)
@@ -26,24 +27,24 @@ class CEMOracle:
         self.std_min = float(cem_stdev_min)
         self.k = int(cem_best_k)
         self.warmup, self.warmup_iterations = bool(warmup), int(warmup_iterations)
-        self.low = torch.tensor([action_low], dtype=torch.float32)
-        self.high = torch.tensor([action_high], dtype=torch.float32)
+        self.low = torch.tensor([action_low], dtype=dtype)
+        self.high = torch.tensor([action_high], dtype=dtype)
         self.reset()
 
     def reset(self):  # optimizer_cem_tf.py:113-117
-        self.dist_mue = (self.low + self.high) * 0.5 * torch.ones([1, self.H, 1])
-        self.stdev = self.init_std * torch.ones([1, self.H, 1])
+        self.dist_mue = (self.low + self.high) * 0.5 * torch.ones([1, self.H, 1], dtype=self.dtype)
+        self.stdev = float(np.float32(self.init_std)) * torch.ones([1, self.H, 1], dtype=self.dtype)
         self.count = 0
         self.u = 0.0
         self.last = {}
 
     def step(self, s: np.ndarray, rng) -> np.ndarray:
-        s = torch.as_tensor(np.tile(np.asarray(s, np.float32), (self.N, 1)))  # :86-87
+        s = torch.as_tensor(np.tile(np.asarray(s, np.float32), (self.N, 1))).to(self.dtype)  # :86-87
         iterations = self.warmup_iterations if self.warmup and self.count == 0 else self.outer_it  # :92
         elite_log = []
         for _ in range(iterations):  # :93-94 -> update_distribution :61-80
             Q = self.dist_mue.repeat(self.N, 1, 1) + torch.mul(
-                rng.normal(shape=(self.N, self.H, 1), dtype=torch.float32), self.stdev)  # :64-65
+                rng.normal(shape=(self.N, self.H, 1), dtype=torch.float32).to(self.dtype), self.stdev)  # :64-65
             Q = torch.minimum(torch.maximum(Q, self.low), self.high)  # :66
             rollout = self.predictor.predict_core(s, Q)  # :57
             traj_cost = spec.trajectory_cost(rollout, Q, self.u, self.cost)  # :58
@@ -55,10 +56,10 @@ class CEMOracle:
             self.stdev = torch.sqrt(torch.mean((elite_Q - mu) * (elite_Q - mu), dim=0, keepdim=True))  # :78
             elite_log.append(best_idx.numpy().copy())
         # :99-102
-        self.stdev = torch.minimum(torch.maximum(self.stdev, torch.tensor(self.std_min)), torch.tensor(1.0e8))
-        self.stdev = torch.cat([self.stdev[:, 1:, :], self.init_std * torch.ones((1, 1, 1))], dim=1)
+        self.stdev = torch.minimum(torch.maximum(self.stdev, torch.tensor(float(np.float32(self.std_min)), dtype=self.dtype)), torch.tensor(1.0e8, dtype=self.dtype))
+        self.stdev = torch.cat([self.stdev[:, 1:, :], float(np.float32(self.init_std)) * torch.ones((1, 1, 1), dtype=self.dtype)], dim=1)
         self.u = elite_Q[0, 0, :].squeeze().numpy().copy()
-        self.dist_mue = torch.cat([self.dist_mue[:, 1:, :], (self.low + self.high) * 0.5 * torch.ones((1, 1, 1))], dim=1)
+        self.dist_mue = torch.cat([self.dist_mue[:, 1:, :], (self.low + self.high) * 0.5 * torch.ones((1, 1, 1), dtype=self.dtype)], dim=1)
         self.last = dict(J=traj_cost.numpy(), Q=Q.numpy(), rollouts=rollout.numpy(), elite_idx=np.stack(elite_log))
         self.count += 1  # :110
         return self.u

@@ -33,27 +33,28 @@ def interpolation_matrix(horizon: int, period: int, nu: int = 1) -> np.ndarray:
 class MPPIOracle:
     def __init__(self, predictor, cost: spec.CostParams, *, mpc_horizon, num_rollouts, cc_weight, R, LBD, NU,
                  SQRTRHOINV, period_interpolation_inducing_points, mpc_timestep=0.02,
-                 action_low=-1.0, action_high=1.0, **_ignored):
+                 action_low=-1.0, action_high=1.0, dtype=torch.float32, **_ignored):
+        self.dtype = dtype  # torch.float64 gives the exact-arithmetic 'truth' used to measure the fp32 noise floor
         self.predictor = predictor
         self.cost = cost
         self.H = int(mpc_horizon)
         self.N = int(num_rollouts)
-        self.cc_weight = torch.tensor(cc_weight, dtype=torch.float32)  # optimizer_mppi.py:155 (to_tensor)
-        self.R = torch.tensor(R, dtype=torch.float32)  # :92
+        self.cc_weight = torch.tensor(cc_weight, dtype=dtype)  # optimizer_mppi.py:155 (to_tensor)
+        self.R = torch.tensor(R, dtype=dtype)  # :92
         self.LBD = float(LBD)  # :93 (python float)
-        self.NU = torch.tensor(NU, dtype=torch.float32)  # :94
+        self.NU = torch.tensor(NU, dtype=dtype)  # :94
         self.period = int(period_interpolation_inducing_points)
-        self.W = torch.from_numpy(interpolation_matrix(self.H, self.period))  # [n_ind, H]
+        self.W = torch.from_numpy(interpolation_matrix(self.H, self.period)).to(dtype)  # [n_ind, H]
         self.n_ind = self.W.shape[0]
         # :130  SQRTRHODTINV = fp32( SQRTRHOINV * (1/sqrt(dt)) ) evaluated in float64
-        self.SQRTRHODTINV = torch.tensor(np.array(SQRTRHOINV) * (1 / np.sqrt(mpc_timestep)), dtype=torch.float32)
-        self.low = torch.tensor([action_low], dtype=torch.float32)
-        self.high = torch.tensor([action_high], dtype=torch.float32)
+        self.SQRTRHODTINV = torch.tensor(np.float32(np.array(SQRTRHOINV) * (1 / np.sqrt(mpc_timestep))), dtype=dtype)
+        self.low = torch.tensor([action_low], dtype=dtype)
+        self.high = torch.tensor([action_high], dtype=dtype)
         self.reset()
 
     def reset(self):
         # optimizer_mppi.py:227-231
-        self.u_nom = 0.5 * (self.low + self.high) * torch.ones([1, self.H, 1])
+        self.u_nom = 0.5 * (self.low + self.high) * torch.ones([1, self.H, 1], dtype=self.dtype)
         self.u = 0.0
         self.last = {}
 
@@ -61,11 +62,11 @@ class MPPIOracle:
         return torch.matmul(y.permute(2, 0, 1), self.W[None]).permute(1, 2, 0)
 
     def step(self, s: np.ndarray, rng) -> np.ndarray:
-        s = torch.as_tensor(np.asarray(s), dtype=torch.float32).reshape(1, -1)  # :208-209
+        s = torch.as_tensor(np.asarray(s, np.float32)).to(self.dtype).reshape(1, -1)  # :208-209
         u_old = self.u
         s = s.repeat(self.N, 1)  # :182
         u_nom = torch.cat([self.u_nom[:, 1:, :], self.u_nom[:, -1:, :]], 1)  # :184
-        delta_u = rng.normal([self.N, self.n_ind, 1], dtype=torch.float32) * self.SQRTRHODTINV  # :173-175
+        delta_u = rng.normal([self.N, self.n_ind, 1], dtype=torch.float32).to(self.dtype) * self.SQRTRHODTINV  # :173-175
         delta_u = self._interpolate(delta_u)  # :177
         u_run = u_nom.repeat(self.N, 1, 1) + delta_u  # :186
         u_run = torch.minimum(torch.maximum(u_run, self.low), self.high)  # :187

@@ -21,37 +21,38 @@ class RPGDOracle:
                  sample_mean, sample_whole_control_space, uniform_dist_min, uniform_dist_max, resamp_per,
                  period_interpolation_inducing_points, SAMPLING_DISTRIBUTION, shift_previous, warmup,
                  warmup_iterations, learning_rate, opt_keep_k_ratio, gradmax_clip, adam_beta_1, adam_beta_2,
-                 adam_epsilon, action_low=-1.0, action_high=1.0, adam_form="torch", **_ignored):
+                 adam_epsilon, action_low=-1.0, action_high=1.0, adam_form="torch", dtype=torch.float32, **_ignored):
+        self.dtype = dtype
         self.predictor, self.cost = predictor, cost
         self.H, self.N = int(mpc_horizon), int(num_rollouts)
         self.outer_its = int(outer_its)
-        self.low = torch.tensor([action_low], dtype=torch.float32)
-        self.high = torch.tensor([action_high], dtype=torch.float32)
-        self.sample_stdev = torch.tensor(sample_stdev, dtype=torch.float32)
-        self.sample_mean = torch.tensor(sample_mean, dtype=torch.float32)
+        self.low = torch.tensor([action_low], dtype=dtype)
+        self.high = torch.tensor([action_high], dtype=dtype)
+        self.sample_stdev = torch.tensor(float(np.float32(sample_stdev)), dtype=dtype)
+        self.sample_mean = torch.tensor(float(np.float32(sample_mean)), dtype=dtype)
         if sample_whole_control_space:  # :200-205
             self.sample_min, self.sample_max = self.low.clone(), self.high.clone()
         else:
-            self.sample_min = torch.tensor(uniform_dist_min, dtype=torch.float32)
-            self.sample_max = torch.tensor(uniform_dist_max, dtype=torch.float32)
+            self.sample_min = torch.tensor(float(np.float32(uniform_dist_min)), dtype=dtype)
+            self.sample_max = torch.tensor(float(np.float32(uniform_dist_max)), dtype=dtype)
         self.resamp_per = int(resamp_per)
         self.shift_previous = int(shift_previous)
         self.first_iter_count = int(warmup_iterations) if warmup else self.outer_its  # :219-221
         self.k = int(max(int(num_rollouts * opt_keep_k_ratio), 1))  # :213
-        self.gradmax_clip = torch.tensor(gradmax_clip, dtype=torch.float32)
+        self.gradmax_clip = torch.tensor(float(np.float32(gradmax_clip)), dtype=dtype)
         self.dist = SAMPLING_DISTRIBUTION
         self.lr, self.b1, self.b2, self.eps = learning_rate, adam_beta_1, adam_beta_2, adam_epsilon
         self.adam_form = adam_form
-        self.W = torch.from_numpy(interpolation_matrix(self.H, int(period_interpolation_inducing_points)))
+        self.W = torch.from_numpy(interpolation_matrix(self.H, int(period_interpolation_inducing_points))).to(dtype)
         self.n_ind = self.W.shape[0]
         self.Q = None
 
     # -- :275-296 -----------------------------------------------------------------------------------
     def sample_actions(self, rng, batch):
         if self.dist == "normal":
-            Qn = rng.normal([batch, self.n_ind, 1], mean=self.sample_mean, stddev=self.sample_stdev, dtype=torch.float32)
+            Qn = rng.normal([batch, self.n_ind, 1], mean=self.sample_mean.float(), stddev=self.sample_stdev.float(), dtype=torch.float32).to(self.dtype)
         elif self.dist == "uniform":
-            Qn = rng.uniform([batch, self.n_ind, 1], minval=self.sample_min, maxval=self.sample_max, dtype=torch.float32)
+            Qn = rng.uniform([batch, self.n_ind, 1], minval=self.sample_min.float(), maxval=self.sample_max.float(), dtype=torch.float32).to(self.dtype)
         else:
             raise ValueError(f"RPGD cannot interpret sampling type {self.dist}")
         Qn = torch.minimum(torch.maximum(Qn, self.low), self.high)
@@ -61,7 +62,7 @@ class RPGDOracle:
         self.Q = self.sample_actions(rng, self.N).clone()
         self.count = 0
         self.adam_step, self.m, self.v = 0, None, None
-        self.ages = torch.zeros((self.N,))
+        self.ages = torch.zeros((self.N,), dtype=self.dtype)
         self.u = np.float32(0.0)
         self.last = {}
 
@@ -97,7 +98,7 @@ class RPGDOracle:
         return torch.minimum(torch.maximum(Qn, self.low), self.high), traj_cost.detach()
 
     def step(self, s: np.ndarray, rng) -> np.ndarray:
-        s = torch.as_tensor(np.tile(np.asarray(s, np.float32), (self.N, 1)))  # :393-394
+        s = torch.as_tensor(np.tile(np.asarray(s, np.float32), (self.N, 1))).to(self.dtype)  # :393-394
         iters = self.first_iter_count if self.count == 0 else self.outer_its  # :397-400
         for _ in range(iters):  # :404-406
             self.Q, _ = self.grad_step(s, self.Q)
@@ -114,14 +115,14 @@ class RPGDOracle:
             if self.count % self.resamp_per == 0:  # :449-495
                 Qres = self.sample_actions(rng, self.N - self.k)
                 Qn = torch.cat([Qres, torch.index_select(Qn, 0, best_idx)], 0)
-                self.ages = torch.cat([torch.zeros((self.N - self.k,)), torch.index_select(self.ages, 0, best_idx)], 0)
-                wk1 = torch.cat([torch.index_select(m_t, 0, best_idx)[:, 1:, :], torch.zeros([self.k, 1, 1])], 1)
-                wk2 = torch.cat([torch.index_select(v_t, 0, best_idx)[:, 1:, :], torch.zeros([self.k, 1, 1])], 1)
-                z = torch.zeros([self.N - self.k, self.H, 1])
+                self.ages = torch.cat([torch.zeros((self.N - self.k,), dtype=self.dtype), torch.index_select(self.ages, 0, best_idx)], 0)
+                wk1 = torch.cat([torch.index_select(m_t, 0, best_idx)[:, 1:, :], torch.zeros([self.k, 1, 1], dtype=self.dtype)], 1)
+                wk2 = torch.cat([torch.index_select(v_t, 0, best_idx)[:, 1:, :], torch.zeros([self.k, 1, 1], dtype=self.dtype)], 1)
+                z = torch.zeros([self.N - self.k, self.H, 1], dtype=self.dtype)
                 self.m, self.v = torch.cat([z, wk1], 0), torch.cat([z, wk2], 0)
             else:  # :496-513
-                self.m = torch.cat([m_t[:, 1:, :], torch.zeros([self.N, 1, 1])], 1)
-                self.v = torch.cat([v_t[:, 1:, :], torch.zeros([self.N, 1, 1])], 1)
+                self.m = torch.cat([m_t[:, 1:, :], torch.zeros([self.N, 1, 1], dtype=self.dtype)], 1)
+                self.v = torch.cat([v_t[:, 1:, :], torch.zeros([self.N, 1, 1], dtype=self.dtype)], 1)
             self.ages = self.ages + 1  # :514
             self.Q = Qn.clone()  # :515
             self.count += 1  # :516

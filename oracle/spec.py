@@ -190,9 +190,9 @@ class MLPPredictor:
     num_states = NUM_STATES
     num_control_inputs = NUM_CONTROLS
 
-    def __init__(self, weights: MLPWeights):
+    def __init__(self, weights: MLPWeights, dtype=torch.float32):
         self.w = weights
-        self.t = {k: torch.from_numpy(np.ascontiguousarray(getattr(weights, k))) for k in ("W1", "b1", "W2", "b2", "W3", "b3")}
+        self.t = {k: torch.from_numpy(np.ascontiguousarray(getattr(weights, k))).to(dtype) for k in ("W1", "b1", "W2", "b2", "W3", "b3")}
 
     def step(self, s: torch.Tensor, Q: torch.Tensor) -> torch.Tensor:
         x = torch.cat([Q, s[:, 1:]], dim=1)  # [N,6]
@@ -215,7 +215,7 @@ class MLPPredictor:
 # ----------------------------------------------------------------------------------------------
 def _distance_difference_cost(position, c):
     return ((position - c["target_position"]) / c["two_thl"]) ** 2 + (
-        (torch.abs(position) > c["thl_095"]).to(torch.float32)
+        (torch.abs(position) > c["thl_095"]).to(position.dtype)
         * 1.0e9
         * ((torch.abs(position) - c["thl_095"]) / c["thl_005"]) ** 2
     )
@@ -237,7 +237,7 @@ def _control_change_rate_cost(u, u_prev):
 def stage_cost(states: torch.Tensor, inputs: torch.Tensor, previous_input, cp: CostParams) -> torch.Tensor:
     """``_get_stage_cost``: states [N,H,6], inputs [N,H,1], previous_input scalar/0-d -> [N,H]."""
     c = cp.f32()
-    previous_input = torch.as_tensor(previous_input, dtype=torch.float32)
+    previous_input = torch.as_tensor(previous_input).to(states.dtype)
     dd = c["dd_weight"] * _distance_difference_cost(states[:, :, POSITION], c)
     ep = c["ep_weight"] * _E_pot_cost(states[:, :, ANGLE], c)
     cc = c["cc_weight"] * _CC_cost(inputs, c)
@@ -246,7 +246,7 @@ def stage_cost(states: torch.Tensor, inputs: torch.Tensor, previous_input, cp: C
         return dd + ep + cc + ccrc
     elif cp.name == "quadratic_boundary_grad":
         ekp = c["ekp_weight"] * states[:, :, ANGLED] ** 2
-        border = (torch.abs(states[:, :, POSITION]) > c["thl_09"]).to(torch.float32) * 1.0e7
+        border = (torch.abs(states[:, :, POSITION]) > c["thl_09"]).to(states.dtype) * 1.0e7
         return dd + ep + ekp + cc + ccrc + border
     raise ValueError(f"unknown cost function {cp.name}")
 
@@ -256,7 +256,7 @@ def terminal_cost(terminal_states: torch.Tensor, cp: CostParams) -> torch.Tensor
     return 10000.0 * (
         (torch.abs(terminal_states[:, ANGLE]) > 0.2)
         | (torch.abs(terminal_states[:, POSITION] - c["target_position"]) > c["thl_01"])
-    ).to(torch.float32)
+    ).to(terminal_states.dtype)
 
 
 def trajectory_cost(state_horizon: torch.Tensor, inputs: torch.Tensor, previous_input, cp: CostParams) -> torch.Tensor:

@@ -14,37 +14,38 @@ extern "C" {
 // J[n] = trajectory cost of rollout n; traj (optional) [N][H+1][6]
 void twin_rollout_cost(const float* s0, const float* Q, int N, int H, const ctk_ode_params* op, const ctk_cost_params* cp,
                        float u_prev, float* J, float* traj) {
-  OdeC ode; CostC cost;
-  derive_ode(*op, ode);
+  FwdK ode; CostC cost;
+  derive_fwd(*op, ode);
   derive_cost(*cp, H, cost);
   for (int n = 0; n < N; ++n) {
     State z{s0[0], s0[1], s0[2], s0[3], s0[4], s0[5]};
-    float cosang = cosf(z.th), ul = u_prev, sum = 0.f;
+    float omc = 1.0f - cosf(z.th), ul = u_prev, sum = 0.f;
     for (int t = 0; t < H; ++t) {
       if (traj) { float* p = traj + ((size_t)n * (H + 1) + t) * 6; p[0]=z.th; p[1]=z.om; p[2]=z.c; p[3]=z.s; p[4]=z.x; p[5]=z.v; }
       const float u = Q[(size_t)n * H + t];
-      sum += stage_cost_dyn(cost.kind, z, cosang, u, ul, cost);
-      ode_step(z, u, ode);
-      cosang = z.c;
+      sum += stage_cost_dyn(cost.kind, z, omc, u, ul, cost);
+      ode_step(z, u, ode, omc);
       ul = u;
     }
     if (traj) { float* p = traj + ((size_t)n * (H + 1) + H) * 6; p[0]=z.th; p[1]=z.om; p[2]=z.c; p[3]=z.s; p[4]=z.x; p[5]=z.v; }
-    J[n] = (sum + terminal_cost(z, cost)) / (float)(H + 1);
+    J[n] = (sum + terminal_cost(z, cost)) - cost.shift;
   }
 }
 
 // grad[n][t] = dJ_n/dQ[n][t] by the same forward-tape + adjoint sweep as rpgd_grad_kernel
 void twin_grad(const float* s0, const float* Q, int N, int H, const ctk_ode_params* op, const ctk_cost_params* cp,
                float u_prev, float* grad) {
-  OdeC ode; CostC cost;
+  OdeC ode; FwdK fwd; CostC cost;
   derive_ode(*op, ode);
+  derive_fwd(*op, fwd);
   derive_cost(*cp, H, cost);
   const float w = cost.inv_Hp1;
   State* tape = new State[H];
   for (int n = 0; n < N; ++n) {
     const float* q = Q + (size_t)n * H;
     State z{s0[0], s0[1], s0[2], s0[3], s0[4], s0[5]};
-    for (int t = 0; t < H; ++t) { tape[t] = z; ode_step(z, q[t], ode); }
+    float omc_unused;
+    for (int t = 0; t < H; ++t) { tape[t] = z; ode_step(z, q[t], fwd, omc_unused); }
     Adj lam{0.f, 0.f, 0.f, 0.f};
     for (int t = H - 1; t >= 0; --t) {
       const State& zt = tape[t];
