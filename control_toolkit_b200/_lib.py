@@ -97,6 +97,7 @@ SYMBOLS = {
     "ctk_last_error": (C.c_char_p, []),
     "ctk_abi_version": (C.c_int, []),
     "ctk_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ctk_fp32_microbench": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "ctk_philox_fill": (C.c_int, [C.c_int, C.c_uint64, C.c_int, _FP, C.c_size_t]),
     "ctk_topk": (C.c_int, [C.c_int, _FP, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
 }

@@ -36,6 +36,17 @@ struct DevConsts {
   CostC cost;
 };
 
+// The 12 constants that appear as the multiplier / addend of an FMA whose other two sources are registers.  They are
+// passed as KERNEL PARAMETERS (constant bank -> LDCU -> uniform registers) so those FMAs read only two vector
+// registers; an FMA with three distinct vector-register sources issues at ~58 % rate on sm_100 (register-file read
+// bandwidth, measured with ctk_fp32_microbench).  The remaining constants only feed 2-operand instructions and live in
+// vector registers (DevConsts).
+struct alignas(16) HotUK {
+  float k_dd, k_bar, k_ep, k_cc;
+  float k_ccrc, k_du2, k_udu, cU;
+  float kTm, h, hk, K1p;
+};
+
 struct MppiArgs {
   int N, off, H, period, n_ind;  // local rollouts, global id offset, horizon, inducing-point period / count
   const float* s0;               // [6] device
@@ -47,9 +58,10 @@ struct MppiArgs {
   int stash;                     // 1: keep each rollout's draws in shared memory for the softmin record (else regenerate)
   const DevConsts* kc;           // device: forward ODE + cost constants
   const float* kx;               // device: {lo, hi, k_du2, k_udu}
+  HotUK uk;                      // uniform-register constants (see HotUK)
   MlpDev mlp;
   float* J;                      // [N] out: total MPPI cost S
-  float* partials;               // [iterations][gridDim.x][2 + n_ind] out: rho_b, a_b, b_z[n_ind]
+  float* partials;               // [gridDim.x][2 + n_ind] out: rho_b, a_b, b_z[n_ind]
   float* log_traj_soa;           // [(H+1)][6][N] or null
   float* log_Q_soa;              // [H][N] or null
 };

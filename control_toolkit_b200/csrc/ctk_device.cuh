@@ -86,10 +86,14 @@ __device__ __forceinline__ FwdK load_fwd(const DevConsts* kc) {
 }
 __device__ __forceinline__ CostC load_cost(const DevConsts* kc) {
   const CostC* c = &kc->cost;
-  CostC r = *c;  // cold fields (terminal cost, shift, adjoint weights): ordinary loads
+  CostC r;
+  r.kind = c->kind;
+  // hot (per rollout-step) constants
   r.target_position = vld(&c->target_position); r.thl_095 = vld(&c->thl_095); r.k_dd = vld(&c->k_dd);
   r.k_bar = vld(&c->k_bar); r.k_ep = vld(&c->k_ep); r.k_cc = vld(&c->k_cc); r.k_ccrc = vld(&c->k_ccrc);
-  if (r.kind == 1) { r.k_ekp = vld(&c->k_ekp); r.thl_09 = vld(&c->thl_09); r.k_border = vld(&c->k_border); }
+  r.k_ekp = vld(&c->k_ekp); r.thl_09 = vld(&c->thl_09); r.k_border = vld(&c->k_border);
+  // cold (per rollout) constants
+  r.thl_01 = c->thl_01; r.k_term = c->k_term; r.shift = c->shift;
   return r;
 }
 

@@ -229,10 +229,17 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
     if (T > maxb) T = maxb;
     if (T < 32) T = 32;
     h->mppi_block = T;
-    h->mppi_grid = (int)std::min<long long>(h->num_sms, ((long long)N + (long long)T * r - 1) / ((long long)T * r));
+    h->mppi_grid = (int)std::min<long long>(h->num_sms, ((long long)N + T - 1) / T);  // every SM gets a CTA
     if (h->mppi_grid < 1) h->mppi_grid = 1;
     h->mppi_iters = (int)((N + (long long)h->mppi_grid * T - 1) / ((long long)h->mppi_grid * T));
-    h->mppi_stash = ((size_t)h->n_ind * T * sizeof(float) <= 160 * 1024) ? 1 : 0;
+    h->mppi_stash = ((size_t)h->n_ind * T * sizeof(float) <= 96 * 1024) ? 1 : 0;
+    if ((size_t)h->n_ind * T * sizeof(float) > 100 * 1024) {  // accumulator array must fit: shrink the block
+      T = (int)((100 * 1024 / sizeof(float) / (size_t)h->n_ind) / 32 * 32);
+      if (T < 32) { ctk_destroy(h); return fail(CTK_EINVAL, "MPPI: too many inducing points for the shared-memory accumulators"); }
+      h->mppi_block = T;
+      h->mppi_grid = (int)std::min<long long>(h->num_sms, ((long long)N + T - 1) / T);
+      h->mppi_stash = 0;
+    }
     A(dalloc(&h->d_u_nom, (size_t)H), "u_nom");
     A(dalloc(&h->d_partials, (size_t)h->mppi_grid * h->mppi_iters * (h->n_ind + 2)), "partials");
     A(dalloc(&h->d_record, (size_t)(h->n_ind + 2)), "record");
@@ -408,18 +415,24 @@ static int mppi_local(ctk_handle* h, const float* s_dev, bool finalize, float* u
   a.k_uu = (float)((double)c.mppi_cc_weight * (double)c.mppi_half_R);
   a.neg_inv_lbd = c.mppi_neg_inv_LBD;
   a.stash = h->mppi_stash;
+  a.uk.k_dd = h->cost.k_dd; a.uk.k_bar = h->cost.k_bar; a.uk.k_ep = h->cost.k_ep; a.uk.k_cc = h->cost.k_cc + a.k_uu;
+  a.uk.k_ccrc = h->cost.k_ccrc;
+  a.uk.k_du2 = (float)((double)c.mppi_cc_weight * (double)c.mppi_coef_du2);
+  a.uk.k_udu = (float)((double)c.mppi_cc_weight * (double)c.mppi_R);
+  a.uk.cU = h->fwd.cU; a.uk.kTm = h->fwd.kTm; a.uk.h = h->fwd.h; a.uk.hk = h->fwd.hk; a.uk.K1p = h->fwd.K1p;
   a.kc = h->d_kc; a.kx = h->d_kx; a.mlp = h->mlp;
   a.J = h->d_J; a.partials = h->d_partials;
   a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
   const bool log = c.logging != 0;
-  int nparts = h->mppi_grid * h->mppi_iters;
+  int nparts = h->mppi_grid;
   if (tc) {
     std::string err;
     if (!mlp_tc_launch_mppi(h->mlp_tc, a, h->cost.kind, log, h->stream, &nparts, &h->launches, err))
       return fail(CTK_ECUDA, "mlp tcgen05 launch: " + err);
   } else {
     size_t smem = sizeof(float) * ((size_t)((h->H + 1) & ~1) + 2 * h->period + 32 + 32 * (h->n_ind + 1) +
-                                   (h->mppi_stash ? (size_t)h->n_ind * h->mppi_block : 0) + pred_smem_floats(h));
+                                   (h->mppi_stash ? (size_t)h->n_ind * h->mppi_block : 0) + (size_t)h->n_ind * h->mppi_block +
+                                   pred_smem_floats(h));
     h->launches++;
     KernelTimer kt(h);
     cudaError_t e = launch_mppi_rollout(c.predictor == CTK_PRED_ODE ? 0 : 1, h->cost.kind, log, h->mppi_grid, h->mppi_block, smem,
@@ -840,6 +853,38 @@ extern "C" int ctk_fp32_peak(int device, double* tflops, double* clk_mhz) {
   cudaFree(d);
   *tflops = best;
   if (clk_mhz) *clk_mhz = best * 1e12 / (2.0 * 128.0 * prop.multiProcessorCount) / 1e6;  // implied FFMA issue clock
+  return CTK_OK;
+}
+
+// warp-instructions per second per SMSP-cycle for an FP32 instruction mix (variant: see fp32_micro_kernel)
+extern "C" int ctk_fp32_microbench(int device, int variant, double* ginstr_per_s) {
+  REQ(ginstr_per_s && variant >= 1 && variant <= 5, "variant in 1..5");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2048;
+  float *d = nullptr, *seed = nullptr;
+  CU(cudaMalloc((void**)&d, sizeof(float) * blocks * threads));
+  CU(cudaMalloc((void**)&seed, sizeof(float) * 64));
+  float hs[64];
+  for (int i = 0; i < 64; ++i) hs[i] = 0.5f + 0.001f * i;
+  CU(cudaMemcpy(seed, hs, sizeof(hs), cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(e0));
+    CU(launch_fp32_micro(variant, d, blocks, threads, iters, seed, nullptr));
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    const double ninstr = 64.0 * iters * (double)blocks * threads;  // thread-instructions
+    if (rep > 0) best = std::max(best, ninstr / (ms * 1e-3) / 1e9);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d); cudaFree(seed);
+  *ginstr_per_s = best;
   return CTK_OK;
 }
 

@@ -29,13 +29,15 @@ __device__ __forceinline__ void mppi_step(const MppiArgs& a, const CostC& cost, 
   // cost.k_cc here carries  k_cc(cost) + cc_weight * 0.5 R  (both multiply u^2; merged by the caller)
   stage_cost_acc<KIND>(acc, z, omc, u, u_last, cost);
   // :154-155  cc_weight * (0.5(1-1/NU) R du^2 + R u du [+ 0.5 R u^2 merged above]) = du * (k_udu u + k_du2 du)
-  acc = fmaf(du, fmaf(k.k_du2, du, k.k_udu * u), acc);
+  acc = fmaf(du * du, k.k_du2, acc);
+  acc = fmaf(u * du, k.k_udu, acc);
   if (SINGLE) pred.substep(z, u, omc); else pred.step(z, u, omc);
   u_last = u;
 }
 
 // K1.  One CTA per SM slot, grid-stride over rollouts (host sizes grid x block so that every thread runs the same
-// number of rollouts: no tail wave).  Per rollout iteration the block emits one softmin record [rho, a, b_z[n_ind]].
+// number of rollouts: no tail wave).  Each thread keeps an online softmin over its rollouts; the block emits ONE record
+// [rho, a, b_z[n_ind]] at the end (a single block-wide reduction per launch).
 template <class Pred, int KIND, bool LOG>
 __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const MppiArgs a) {
   extern __shared__ float smem[];
@@ -44,15 +46,19 @@ __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const M
   float* sh_red = reinterpret_cast<float*>(sh_w + a.period);          // [32] reduction scratch
   float* sh_part = sh_red + 32;          // [32][n_ind + 1]
   float* sh_z = sh_part + 32 * (a.n_ind + 1);  // [n_ind][blockDim] stash of this rollout's standard draws (if a.stash)
-  float* sh_pred = sh_z + (a.stash ? (size_t)a.n_ind * blockDim.x : 0);
+  float* sh_acc = sh_z + (a.stash ? (size_t)a.n_ind * blockDim.x : 0);  // [n_ind][blockDim] per-thread sum_n e_n z_n,i
+  float* sh_pred = sh_acc + (size_t)a.n_ind * blockDim.x;
 
   for (int t = threadIdx.x; t < a.H; t += blockDim.x) sh_unom[t] = a.u_nom[min(t + 1, a.H - 1)];
   for (int j = threadIdx.x; j < a.period; j += blockDim.x) interp_weights(j, a.period, &sh_w[j].x, &sh_w[j].y);
   Pred pred(a.kc, a.mlp, sh_pred);
+  pred.use_uniform(a.uk);
   CostC cost = load_cost(a.kc);
-  cost.k_cc += a.k_uu;  // the cost's own R u^2 term and the correction's 0.5 R u^2 share one FMA
-  const float* kx = a.kx;  // device copy of {lo, hi, k_du2, k_udu} (register-resident like the other constants)
-  const MppiK k = {vld(kx), vld(kx + 1), vld(kx + 2), vld(kx + 3)};
+  // FMA-multiplier weights come from kernel parameters (uniform registers); uk.k_cc already carries
+  // k_cc(cost) + cc_weight * 0.5 R: the cost's own R u^2 term and the correction's 0.5 R u^2 share one FMA
+  cost.k_dd = a.uk.k_dd; cost.k_bar = a.uk.k_bar; cost.k_ep = a.uk.k_ep; cost.k_cc = a.uk.k_cc; cost.k_ccrc = a.uk.k_ccrc;
+  const float* kx = a.kx;  // device copy of {lo, hi}
+  const MppiK k = {vld(kx), vld(kx + 1), a.uk.k_du2, a.uk.k_udu};
   const float stdev = a.stdev;
   const bool single = pred.single_substep();
   __syncthreads();
@@ -65,10 +71,13 @@ __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const M
   const float omc0 = 1.0f - cosf(z0.th);  // spec: E_pot uses cos(angle); for t >= 1 the state carries 1 - cos
   const float u_prev0 = a.u_prev[0];
   float* sz = sh_z + tid;
+  float* sa = sh_acc + tid;
+  for (int i = 0; i < a.n_ind; ++i) sa[(size_t)i * blockDim.x] = 0.0f;
+  // per-thread online softmin over this thread's rollouts: rho_t = running min, a_t = sum e, sa[i] = sum e z_i
+  float rho_t = INFINITY, a_t = 0.0f;
   const uint32_t a_unom = smem_u32(sh_unom), a_w = smem_u32(sh_w);
 
-  int iter = 0;
-  for (int base = blockIdx.x * blockDim.x; base < a.N; base += stride, ++iter) {
+  for (int base = blockIdx.x * blockDim.x; base < a.N; base += stride) {
     const int n = base + tid;
     const bool active = n < a.N;
     const uint32_t ng = (uint32_t)(a.off + (active ? n : 0));
@@ -126,42 +135,54 @@ __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const M
       if (active) a.J[n] = S; else S = INFINITY;
     }
 
-    // ---- block softmin record (optimizer_mppi.py:163-168 restated per block; exact combine in K2) ----
-    const float rho_b = block_min(S, sh_red);
-    const float e = (active && S < INFINITY) ? expf((S - rho_b) * a.neg_inv_lbd) : 0.0f;
-    {
-      const float ws = warp_sum(e);
-      if (lane == 0) sh_part[w * P] = ws;
-    }
-    if (a.stash) {
-      for (int i = 0; i < a.n_ind; ++i) {
-        const float ws = warp_sum(e * sz[(size_t)i * blockDim.x]);
-        if (lane == 0) sh_part[w * P + 1 + i] = ws;
-      }
-    } else {
-      for (int blk = 0; blk < nblk; ++blk) {
-        float zz[4];
-        noise4(a.noise, ng, blk, zz);
+    // ---- per-thread online softmin (optimizer_mppi.py:163-168 restated incrementally; exact combine in K2) ----
+    if (active && S < INFINITY) {
+      const float rho_n = fminf(rho_t, S);
+      const float so = (rho_t < INFINITY) ? __expf((rho_t - rho_n) * a.neg_inv_lbd) : 0.0f;  // rescale the old sums
+      const float sn = __expf((S - rho_n) * a.neg_inv_lbd);
+      a_t = fmaf(a_t, so, sn);
+      rho_t = rho_n;
+      if (a.stash) {
+        for (int i = 0; i < a.n_ind; ++i) {
+          const size_t o = (size_t)i * blockDim.x;
+          sa[o] = fmaf(sa[o], so, sn * sz[o]);
+        }
+      } else {
+        for (int blk = 0; blk < nblk; ++blk) {
+          float zz[4];
+          noise4(a.noise, ng, blk, zz);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int i = blk * 4 + q;
-          if (i < a.n_ind) {
-            const float ws = warp_sum(e * zz[q]);
-            if (lane == 0) sh_part[w * P + 1 + i] = ws;
+          for (int q = 0; q < 4; ++q) {
+            const int i = blk * 4 + q;
+            if (i < a.n_ind) {
+              const size_t o = (size_t)i * blockDim.x;
+              sa[o] = fmaf(sa[o], so, sn * zz[q]);
+            }
           }
         }
       }
     }
-    __syncthreads();
-    float* out = a.partials + ((size_t)iter * gridDim.x + blockIdx.x) * (P + 1);
-    for (int c = tid; c < P; c += blockDim.x) {
-      float s = 0.0f;
-      for (int ww = 0; ww < nw; ++ww) s += sh_part[ww * P + c];
-      out[1 + c] = s;
-    }
-    if (tid == 0) out[0] = rho_b;
-    __syncthreads();
   }
+
+  // ---- one block softmin record [rho_b, a_b, b_z[n_ind]] ----
+  const float rho_b = block_min(rho_t, sh_red);
+  const float sc = (rho_t < INFINITY) ? expf((rho_t - rho_b) * a.neg_inv_lbd) : 0.0f;
+  {
+    const float ws = warp_sum(a_t * sc);
+    if (lane == 0) sh_part[w * P] = ws;
+  }
+  for (int i = 0; i < a.n_ind; ++i) {
+    const float ws = warp_sum(sa[(size_t)i * blockDim.x] * sc);
+    if (lane == 0) sh_part[w * P + 1 + i] = ws;
+  }
+  __syncthreads();
+  float* out = a.partials + (size_t)blockIdx.x * (P + 1);
+  for (int c = tid; c < P; c += blockDim.x) {
+    float s = 0.0f;
+    for (int ww = 0; ww < nw; ++ww) s += sh_part[ww * P + c];
+    out[1 + c] = s;
+  }
+  if (tid == 0) out[0] = rho_b;
 }
 
 __global__ void __launch_bounds__(1024) mppi_combine_kernel(const float* __restrict__ in, int cnt, int n_ind,

@@ -25,6 +25,7 @@ cudaError_t launch_rpgd_init(const RpgdSelectArgs& a, cudaStream_t st);
 
 cudaError_t launch_single_rollout(int pred, const float* s0, const float* Q, int H, const DevConsts* kc, const MlpDev& mlp, const float* u_prev, float* traj, float* summed, cudaStream_t st);
 cudaError_t launch_fma_peak(float* out, int blocks, int threads, int iters, cudaStream_t st);
+cudaError_t launch_fp32_micro(int variant, float* out, int blocks, int threads, int iters, const float* seed, cudaStream_t st);
 cudaError_t launch_philox_fill(const NoiseSrc& ns, float* out, size_t n, cudaStream_t st);
 
 }  // namespace ctk

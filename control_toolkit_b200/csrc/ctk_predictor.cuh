@@ -15,8 +15,10 @@ struct OdePred {
 #define CTK_ODE_MAX_THREADS 1024
 #endif
   static constexpr int kMaxThreads = CTK_ODE_MAX_THREADS;
-  const FwdK p;  // forward constants, register-resident (ctk_device.cuh load_fwd)
+  FwdK p;  // forward constants, register-resident (ctk_device.cuh load_fwd)
   __device__ __forceinline__ OdePred(const DevConsts* kc, const MlpDev&, float*) : p(load_fwd(kc)) {}
+  // take the FMA-multiplier constants from kernel parameters (uniform registers) instead of vector registers
+  __device__ __forceinline__ void use_uniform(const HotUK& u) { p.cU = u.cU; p.kTm = u.kTm; p.h = u.h; p.hk = u.hk; p.K1p = u.K1p; }
   // omc = 1 - cos(angle) of the new state (E_pot cost term)
   __device__ __forceinline__ void step(State& z, float u, float& omc) const { ode_step(z, u, p, omc); }
   // intermediate_steps == 1 fast path (no sub-step loop in the rollout's inner loop)
@@ -57,6 +59,7 @@ struct MlpSimtPred {
   static size_t smem_floats(const MlpDev& m) { return (size_t)m.blob_floats + 4; }
   __device__ __forceinline__ void substep(State& z, float u, float& omc) const { step(z, u, omc); }
   __device__ __forceinline__ bool single_substep() const { return false; }
+  __device__ __forceinline__ void use_uniform(const HotUK&) {}
 
   // net input [Q, angleD, cos, sin, position, positionD] -> next [angleD, cos, sin, position, positionD];
   // angle = atan2(sin, cos)  (oracle/spec.py MLPPredictor.step)

@@ -41,6 +41,47 @@ cudaError_t launch_fma_peak(float* out, int blocks, int threads, int iters, cuda
   return cudaGetLastError();
 }
 
+// FP32 issue-rate microbenchmarks (DESIGN.md "what the FP32 pipe can actually issue"): 8 independent chains/thread.
+//  1: FFMA with three distinct REGISTER sources   2: FMUL reg,reg   3: FADD reg,reg   4: FFMA(3 reg) + FMUL alternating
+//  5: FFMA reg,reg,imm-free mix resembling the rollout body (2 FFMA : 1 FMUL : 0.25 FADD), all register operands
+template <int V>
+__global__ void __launch_bounds__(256) fp32_micro_kernel(float* out, int iters, const float* __restrict__ seed) {
+  float x[8], y[8], z[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    x[i] = seed[(threadIdx.x + i) & 63];
+    y[i] = seed[(threadIdx.x + 8 + i) & 63] * 1e-3f + 0.999f;
+    z[i] = seed[(threadIdx.x + 16 + i) & 63] * 1e-3f;
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (V == 1) x[i] = fmaf(x[i], y[i], z[i]);
+        if (V == 2) x[i] = x[i] * y[i];
+        if (V == 3) x[i] = x[i] + z[i];
+        if (V == 4) { if (u & 1) x[i] = fmaf(x[i], y[i], z[i]); else x[i] = x[i] * y[i]; }
+        if (V == 5) { if ((u & 3) == 3) x[i] = x[i] * y[(i + 1) & 7]; else x[i] = fmaf(x[i], y[i], z[(i + u) & 7]); }
+      }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+cudaError_t launch_fp32_micro(int variant, float* out, int blocks, int threads, int iters, const float* seed, cudaStream_t st) {
+  switch (variant) {
+    case 1: fp32_micro_kernel<1><<<blocks, threads, 0, st>>>(out, iters, seed); break;
+    case 2: fp32_micro_kernel<2><<<blocks, threads, 0, st>>>(out, iters, seed); break;
+    case 3: fp32_micro_kernel<3><<<blocks, threads, 0, st>>>(out, iters, seed); break;
+    case 4: fp32_micro_kernel<4><<<blocks, threads, 0, st>>>(out, iters, seed); break;
+    default: fp32_micro_kernel<5><<<blocks, threads, 0, st>>>(out, iters, seed); break;
+  }
+  return cudaGetLastError();
+}
+
 __global__ void philox_fill_kernel(NoiseSrc ns, float* out, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

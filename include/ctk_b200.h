@@ -184,6 +184,9 @@ const char *ctk_last_error(void);
 int ctk_abi_version(void);
 /* FP32 FMA-chain microbenchmark used as the measured FP32 roofline denominator (TFLOP/s)                         */
 int ctk_fp32_peak(int device, double *tflops, double *sm_clock_mhz_est);
+/* FP32 issue-rate microbenchmark: G thread-instructions/s for an instruction mix (1 FFMA with three register sources,
+   2 FMUL, 3 FADD, 4 FFMA+FMUL alternating, 5 rollout-like mix); ctk_fp32_peak uses the uniform-operand FFMA form.       */
+int ctk_fp32_microbench(int device, int variant, double *ginstr_per_s);
 /* Philox self-test: fill dst_host with n standard normals (kind 0) / uniforms (kind 1) exactly as the kernels draw */
 int ctk_philox_fill(int device, uint64_t seed, int kind, float *dst_host, size_t n);
 /* standalone top-k (ties -> lower index), the kernel behind tf.argsort(...)[:k] (optimizer_cem_tf.py:73-74)      */

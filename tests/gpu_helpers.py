@@ -13,7 +13,7 @@ def has_cuda():
         return False
 
 
-def make_controller(meta, logging=True, rng="replay", **optimizer_over):
+def make_controller(meta, logging=True, rng="replay", shard=None, **optimizer_over):
     import control_toolkit_b200 as ctk
     from control_toolkit_b200.Controllers.controller_mpc import controller_mpc
 
@@ -21,6 +21,8 @@ def make_controller(meta, logging=True, rng="replay", **optimizer_over):
         ctk.register_mlp(meta["predictor"], ctk.MLPSpec.random_init(meta["mlp_seed"]))
     cfg = dict(meta["cfg"])
     cfg.update(optimizer_over)
+    if shard is not None:
+        cfg["shard"] = shard
     ctrl = controller_mpc(
         environment_name="CartPole",
         control_limits=(np.array([-1.0], np.float32), np.array([1.0], np.float32)),

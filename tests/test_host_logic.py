@@ -1,0 +1,101 @@
+"""CPU tests of the host-side logic of the plugin layer: registry / naming / config plumbing, parameter derivation
+(independently written in control_toolkit_b200/specs.py and oracle/spec.py), shard geometry."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import spec as ospec
+
+
+def test_ode_and_cost_constants_agree_with_oracle_spec():
+    from control_toolkit_b200 import specs
+    c = specs.CartPoleODE().to_c(0.02)
+    o = ospec.CartPoleParams(dt=0.02).f32()
+    for k, v in o.items():
+        assert float(getattr(c, k)) == v, k
+    for name in ("default", "quadratic_boundary_grad"):
+        cc = specs.resolve_cost("CartPole", name).to_c(0.05, 1.0)
+        oc = ospec.CostParams(name=name, target_position=0.05).f32()
+        for k, v in oc.items():
+            assert float(getattr(cc, k)) == v, (name, k)
+
+
+def test_registry_fails_loudly_for_unregistered_names():
+    from control_toolkit_b200 import specs
+    with pytest.raises(ValueError, match="no registered CUDA functor"):
+        specs.resolve_cost("CartPole", "quadratic_boundary_nonconvex")
+    with pytest.raises(ValueError):
+        specs.resolve_cost("Pendulum", "default")
+    with pytest.raises(ValueError):
+        specs.resolve_predictor("CartPole", "GRU-6IN-32H1-32H2-5OUT-0")
+    assert specs.resolve_cost("CartPole", "quadratic-boundary-grad").kind == 1  # '-' <-> '_' like the reference
+
+
+def test_optimizer_discovery_by_name():
+    """reference others/globals_and_utils.py:103-133: 'cem-tf' -> file optimizer_cem_tf.py, class optimizer_cem_tf."""
+    import control_toolkit_b200 as ctk
+    for key, cls in (("mppi", "optimizer_mppi"), ("cem-tf", "optimizer_cem_tf"), ("rpgd", "optimizer_rpgd")):
+        C = ctk.import_optimizer_by_name(key)
+        assert C.__name__ == cls
+        assert C.__mro__[1].__name__ == "template_optimizer"
+    with pytest.raises(ValueError, match="not found"):
+        ctk.import_optimizer_by_name("rpgd-tf")  # the stale template key
+
+
+def test_optimizer_constructor_contract():
+    """Same ctor kwargs as the reference (mpc_timestep arrives through **kwargs), optimizer_name property, u init."""
+    import control_toolkit_b200 as ctk
+    lim = (np.array([-1.0]), np.array([1.0]))
+    M = ctk.import_optimizer_by_name("mppi")
+    o = M(predictor=ctk.PredictorWrapper(), cost_function=ctk.CostFunctionWrapper(), control_limits=lim, computation_library=None,
+          seed=None, cc_weight=1.0, R=1.0, LBD=100.0, mpc_horizon=35, num_rollouts=3500, NU=1000.0, SQRTRHOINV=0.03,
+          period_interpolation_inducing_points=10, optimizer_logging=False, calculate_optimal_trajectory=False, mpc_timestep=0.02)
+    assert o.optimizer_name == "mppi" and o.u == 0.0 and o.num_rollouts == 3500 and o.mpc_horizon == 35
+    assert isinstance(o.seed, int)  # seed None -> datetime seed (reference globals_and_utils.py:87-91)
+    with pytest.raises(RuntimeError, match="configure"):
+        o.step(np.zeros(6))
+    R = ctk.import_optimizer_by_name("rpgd")
+    with pytest.raises(ValueError, match="sampling type"):
+        R(predictor=ctk.PredictorWrapper(), cost_function=ctk.CostFunctionWrapper(), control_limits=lim, SAMPLING_DISTRIBUTION="cauchy")
+    r = R(predictor=ctk.PredictorWrapper(), cost_function=ctk.CostFunctionWrapper(), control_limits=lim, num_rollouts=32,
+          opt_keep_k_ratio=0.25, warmup=True, warmup_iterations=7, outer_its=2)
+    assert r.opt_keep_k == 8 and r.first_iter_count == 7 and r.optimizer_name == "rpgd"
+    with pytest.raises(ValueError, match="dt and predictor_specification"):
+        r.configure(num_states=6, num_control_inputs=1)
+
+
+def test_mppi_host_constants_follow_reference_evaluation_order():
+    """optimizer_mppi.py:130,154-155,165: fp32 coefficients as the reference's fp32 tensor ops produce them."""
+    import torch
+    import control_toolkit_b200 as ctk
+    from control_toolkit_b200 import _lib as L
+    M = ctk.import_optimizer_by_name("mppi")
+    o = M(predictor=ctk.PredictorWrapper(), cost_function=ctk.CostFunctionWrapper(), control_limits=(np.array([-1.0]), np.array([1.0])),
+          NU=1000.0, R=1.3, LBD=37.0, SQRTRHOINV=0.03, cc_weight=0.7)
+    o.SQRTRHODTINV = np.float32(np.array(0.03) * (1 / np.sqrt(0.02)))
+    cfg = L.ctk_config()
+    o._fill_config(cfg)
+    NU, R = torch.tensor(1000.0), torch.tensor(1.3)
+    assert cfg.mppi_coef_du2 == float(0.5 * (1 - 1.0 / NU) * R)
+    assert cfg.mppi_half_R == float(0.5 * R)
+    assert cfg.mppi_neg_inv_LBD == float(torch.tensor(-1.0 / 37.0, dtype=torch.float32))
+    assert cfg.mppi_stdev == float(torch.tensor(np.array(0.03) * (1 / np.sqrt(0.02)), dtype=torch.float32))
+
+
+def test_shard_geometry_partitions_the_population():
+    from control_toolkit_b200.distributed import shard_geometry
+    for n in (1, 7, 2000, 4096, 1_000_000, 1_000_003):
+        for w in (1, 2, 3, 4, 8):
+            parts = [shard_geometry(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0
+            assert sum(c for _, c in parts) == n
+            for (o0, c0), (o1, _) in zip(parts, parts[1:]):
+                assert o0 + c0 == o1
+            assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def test_interpolation_inducing_point_count():
+    """reference others/Interpolator.py:79-84"""
+    for H, p, n in ((50, 10, 6), (100, 10, 11), (43, 10, 6), (20, 1, 20), (35, 10, 5), (41, 10, 5), (1, 10, 1)):
+        assert int(math.ceil((H - 1) / p) + 1) == n
