@@ -27,7 +27,15 @@ import sys
 import threading
 import time
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1 to every worker; the CPU baseline / reference arm (rank 0 only) must be allowed to
+# use all host cores, and the variable is read when numpy / torch are imported -- so fix it up before those imports.
+if os.environ.get("RANK", "0") == "0" and os.environ.get("OMP_NUM_THREADS", "") in ("", "1"):
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+# Keep stdout clean for the ONE JSON line: libraries (e.g. the NCCL version banner) write to fd 1.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+import numpy as np  # noqa: E402
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
@@ -42,6 +50,11 @@ WORKLOADS = {
     "mppi_ode_c1": ("mppi", "ODE", "default", 2000, 50),         # configs[0]
     "mppi_mlp_c4": ("mppi", "Dense-6IN-128H1-128H2-5OUT-0", "default", 65536, 100),  # configs[3]
 }
+
+
+def _emit(line: dict) -> None:
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
 
 
 def synthetic_states(n, seed=0):
@@ -159,7 +172,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": rate, "unit": "rollout-steps/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "rollout-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -276,7 +289,7 @@ def run_ours(args):
                         "p50_step_latency_ms": statistics.median(lat) * 1e3, "api": "controller_mpc.step(s_host) -> u_host"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "wall_s_timed_region": wall}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
