@@ -85,6 +85,11 @@ SYMBOLS = {
     "ctk_step_local": (C.c_int, [_H, C.c_void_p]),
     "ctk_partials": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "ctk_step_finish": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p]),
+    "ctk_step_device": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    "ctk_exchange_export": (C.c_int, [_H, C.c_void_p]),
+    "ctk_exchange_connect": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
+    "ctk_exchange_mailbox": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
+    "ctk_exchange_connect_ptrs": (C.c_int, [_H, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
     "ctk_get_state": (C.c_int, [_H, C.c_int, _FP, C.c_size_t]),
     "ctk_set_state": (C.c_int, [_H, C.c_int, _FP, C.c_size_t]),
     "ctk_get_counter": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int64)]),

@@ -25,7 +25,7 @@ struct MlpDev {
   int blob_floats;
 };
 
-__host__ __device__ inline int mlp_blob_floats(int hid) { return 6 * hid + hid + hid * hid + hid + 5 * hid + 8; }
+CTK_HD int mlp_blob_floats(int hid) { return 6 * hid + hid + hid * hid + hid + 5 * hid + 8; }
 
 // Loop-invariant constants of the rollout kernels live in DEVICE memory (handle-owned) and are read once per thread
 // with volatile loads: sm_100 FP instructions take no constant-bank operands and ptxas re-issues LDC/LDCU inside the
@@ -47,6 +47,27 @@ struct alignas(16) HotUK {
   float kTm, h, hk, K1p;
 };
 
+// ----------------------------------------------------------------------------------------------------------------
+// In-kernel tick finish (K2 fused into the rollout kernel): the LAST block to retire combines the block records,
+// optionally exchanges the shard record with the peer GPUs through NVLink peer stores into their mailboxes
+// (value + sequence number packed in one 8-byte store: no fence, one NVLink traversal), and updates u_nom / u.
+// Replaces reference optimizer_mppi.py:163-168,190-191 (+ the cross-shard weighted-sum exchange of SURVEY 8e).
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int CTK_MAX_PEERS = 8;
+struct MppiFuse {
+  int mode;                  // 0: block records only (legacy K2 launch follows)  1: + shard record  2: + finalize
+  int world, rank;           // shards taking part in the exchange (1: no exchange)
+  unsigned int seq;          // exchange sequence number of this tick (monotonic, never 0)
+  unsigned int* ticket;      // device counter (self-resetting): blocks retired
+  float* record_out;         // [2 + n_ind] shard record (mode >= 1)
+  unsigned long long* mbox_local;                 // [2][world][2 + n_ind] (value, seq) pairs written by the peers
+  unsigned long long* mbox_peer[CTK_MAX_PEERS];   // peers' mailboxes (mbox_peer[rank] == mbox_local)
+  float* u_nom;              // [H] in/out
+  float* u_prev;             // [1] out (unless frozen)
+  float* u_out;              // [2] out: u, exchange status (0 ok, 1 timeout)
+  int freeze_prev;
+};
+
 struct MppiArgs {
   int N, off, H, period, n_ind;  // local rollouts, global id offset, horizon, inducing-point period / count
   const float* s0;               // [6] device
@@ -64,6 +85,7 @@ struct MppiArgs {
   float* partials;               // [gridDim.x][2 + n_ind] out: rho_b, a_b, b_z[n_ind]
   float* log_traj_soa;           // [(H+1)][6][N] or null
   float* log_Q_soa;              // [H][N] or null
+  MppiFuse fuse;                 // in-kernel tick finish (see MppiFuse)
 };
 
 // K2: combine `cnt` softmin records [rho, a, b_z[n_ind]] (block partials or per-shard records) into one record;
@@ -76,6 +98,35 @@ struct MppiFinalize {
   float* u_prev;  // [1] out (unless frozen)
   float* u_out;   // [1] out or null
   int freeze_prev;
+};
+
+// Uniform-register constants of the scaled-variable CartPole rollout (K1 for the ODE predictor, ctk_kernels_mppi_ode.cuh).
+// State variables carried per rollout:  T = angle/sqrt(2),  W = beta*angleD (beta = sqrt((k+1)L/g)),  c, s,  x,
+// V = (cF/g)*positionD.  With them one Euler step is 12 FP32 instructions + wrap (3) + half-angle sincos (14) + 1 MUFU.
+struct OdeHot {
+  // dynamics
+  float cUg, cTl2, kTm2, K1p, h_T, h_W, h_x, h_V;
+  // state scaling (prologue / logs / terminal cost)
+  float beta, inv_beta, cFg, inv_cFg;
+  // stage cost, pre-multiplied by 1/(H+1); kA/kB/kC: u * (kA u + kB u_prev + kC du) merges the cost's cc and ccrc terms
+  // with the MPPI correction (optimizer_mppi.py:154-155)
+  float k_dd, k_bar, k_ep, k_ekp2, kA, kB, kC, k_du2, k_ccrc;
+  float target, thl_095, thl_09, k_border, thl_01, k_term, shift;
+  float lo, hi, stdev, neg_inv_lbd;
+};
+
+struct MppiOdeArgs {
+  int N, off, H, period, n_ind;
+  const float* s0;      // [6]
+  const float* u_nom;   // [H] unshifted
+  const float* u_prev;  // [1]
+  NoiseSrc noise;
+  OdeHot k;
+  float* J;             // [N]
+  float* partials;      // [gridDim.x][2 + n_ind]
+  float* log_traj_soa;  // [(H+1)][6][N] or null
+  float* log_Q_soa;     // [H][N] or null
+  MppiFuse fuse;
 };
 
 struct CemArgs {

@@ -4,7 +4,9 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -43,6 +45,20 @@ struct ctk_handle {
   cudaStream_t stream = nullptr;
   int N = 0, NG = 0, off = 0, H = 0, period = 1, n_ind = 0, nblocks = 0;
   int mppi_grid = 0, mppi_block = 0, mppi_iters = 0, mppi_stash = 0, num_sms = 0;
+  // K1 for the ODE predictor (ctk_kernels_mppi_ode.cuh)
+  ctk_ode_params ode_p{};
+  ctk_cost_params cost_p{};
+  OdeHot ode_hot{};
+  bool ode_kernel = false;     // MPPI + ODE predictor + intermediate_steps == 1 + few inducing points
+  int ode_ilp = 2, ode_period_t = 0, ode_grid = 0, ode_block = 0;
+  size_t ode_smem = 0;
+  // fused tick finish / cross-GPU exchange (MppiFuse)
+  unsigned int* d_ticket = nullptr;
+  unsigned long long* d_mbox = nullptr;           // local mailbox [2][CTK_MAX_PEERS][2 + n_ind]
+  unsigned long long* mbox_peer[CTK_MAX_PEERS] = {nullptr};
+  bool mbox_ipc[CTK_MAX_PEERS] = {false};
+  int xworld = 1, xrank = 0;
+  unsigned int xseq = 0;
   // common
   float *d_s0 = nullptr, *d_u_prev = nullptr, *d_u_out = nullptr, *d_J = nullptr;
   float *h_pin = nullptr;  // pinned staging: s[8] | u[8]
@@ -109,7 +125,15 @@ static cudaError_t dalloc(T** p, size_t n) {
   return e;
 }
 
+static void mppi_ode_geometry(ctk_handle* h);
 static cudaError_t upload_consts(ctk_handle* h) {
+  if (h->cfg.optimizer == CTK_OPT_MPPI) {
+    const ctk_config& c = h->cfg;
+    MppiCorr mc{(double)c.mppi_cc_weight, (double)c.mppi_coef_du2, (double)c.mppi_R, (double)c.mppi_half_R,
+                (double)c.mppi_neg_inv_LBD, (double)c.mppi_stdev, (double)c.action_low, (double)c.action_high};
+    derive_ode_hot(h->ode_p, h->cost_p, h->H, mc, h->ode_hot);
+    mppi_ode_geometry(h);
+  }
   DevConsts kc;
   kc.fwd = h->fwd;
   kc.cost = h->cost;
@@ -166,6 +190,10 @@ extern "C" int ctk_destroy(ctk_handle* h) {
   if (h->d_elite_idx) cudaFree(h->d_elite_idx);
   if (h->d_best_idx) cudaFree(h->d_best_idx);
   mlp_tc_free(h->mlp_tc);
+  for (int r = 0; r < CTK_MAX_PEERS; ++r)
+    if (h->mbox_ipc[r] && h->mbox_peer[r]) cudaIpcCloseMemHandle(h->mbox_peer[r]);
+  if (h->d_ticket) cudaFree(h->d_ticket);
+  if (h->d_mbox) cudaFree(h->d_mbox);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->h_pin) cudaFreeHost(h->h_pin);
   delete h;
@@ -192,6 +220,7 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
   ctk_handle* h = new ctk_handle();
   h->cfg = *cfg;
   h->N = cfg->num_rollouts; h->NG = cfg->num_rollouts_global; h->off = cfg->rollout_offset; h->H = cfg->mpc_horizon;
+  h->ode_p = *ode; h->cost_p = *cost;
   derive_ode(*ode, h->ode);
   derive_fwd(*ode, h->fwd);
   derive_cost(*cost, h->H, h->cost);
@@ -241,8 +270,11 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
       h->mppi_stash = 0;
     }
     A(dalloc(&h->d_u_nom, (size_t)H), "u_nom");
-    A(dalloc(&h->d_partials, (size_t)h->mppi_grid * h->mppi_iters * (h->n_ind + 2)), "partials");
+    A(dalloc(&h->d_partials, (size_t)(h->num_sms > h->mppi_grid ? h->num_sms : h->mppi_grid) * (h->mppi_iters + 1) * (h->n_ind + 2)), "partials");
     A(dalloc(&h->d_record, (size_t)(h->n_ind + 2)), "record");
+    A(dalloc(&h->d_ticket, 1), "ticket");
+    A(dalloc(&h->d_mbox, (size_t)2 * CTK_MAX_PEERS * (h->n_ind + 2)), "mailbox");
+    h->mbox_peer[0] = h->d_mbox;
   } else if (cfg->optimizer == CTK_OPT_CEM) {
     if (!(cfg->cem_best_k >= 1 && cfg->cem_best_k <= 512 && cfg->cem_best_k <= cfg->num_rollouts_global && H <= 1024 && cfg->cem_outer_it >= 1)) {
       ctk_destroy(h);
@@ -280,6 +312,7 @@ extern "C" int ctk_set_stream(ctk_handle* h, void* s) { REQ(h, "null handle"); h
 extern "C" int ctk_set_cost_params(ctk_handle* h, const ctk_cost_params* c) {
   REQ(h && c, "null pointer");
   REQ(c->kind == CTK_COST_DEFAULT || c->kind == CTK_COST_QUADRATIC_BOUNDARY_GRAD, "unregistered cost function");
+  h->cost_p = *c;
   derive_cost(*c, h->H, h->cost);
   CU(cudaSetDevice(h->cfg.device));
   CU(upload_consts(h));
@@ -288,6 +321,7 @@ extern "C" int ctk_set_cost_params(ctk_handle* h, const ctk_cost_params* c) {
 extern "C" int ctk_set_ode_params(ctk_handle* h, const ctk_ode_params* o) {
   REQ(h && o, "null pointer");
   REQ(!(h->cfg.optimizer == CTK_OPT_RPGD && o->intermediate_steps > 1), "RPGD adjoint supports intermediate_steps == 1");
+  h->ode_p = *o;
   derive_ode(*o, h->ode);
   derive_fwd(*o, h->fwd);
   CU(cudaSetDevice(h->cfg.device));
@@ -399,12 +433,87 @@ extern "C" int ctk_reset(ctk_handle* h) {
 // ---------------------------------------------------------------------------------------------------------------
 static size_t pred_smem_floats(ctk_handle* h) { return mppi_pred_smem_floats(h->cfg.predictor == CTK_PRED_MLP ? 1 : 0, h->mlp); }
 
-static int mppi_local(ctk_handle* h, const float* s_dev, bool finalize, float* u_out_dev) {
+// Launch geometry of the ODE kernel: one CTA per SM, block sized so that every thread runs the same number of
+// rollout groups (no partially filled last wave); the iteration count with the least padding wins.
+static void mppi_ode_geometry(ctk_handle* h) {
+  const ctk_config& c = h->cfg;
+  h->ode_kernel = false;
+  if (c.predictor != CTK_PRED_ODE || h->ode_p.intermediate_steps > 1 || h->num_sms <= 0) return;
+  if (getenv("CTK_K1_GENERIC")) return;
+  const long long N = h->N, sms = h->num_sms;
+  int ilp = (c.logging || N <= sms * 64) ? 1 : 2;
+  if (const char* e = getenv("CTK_K1_ILP")) { const int v = atoi(e); if (!c.logging && (v == 1 || v == 2)) ilp = v; }
+  int maxb = mppi_ode_max_block(ilp);
+  if (const char* e = getenv("CTK_K1_BLOCK")) { const int v = atoi(e) / 32 * 32; if (v >= 32 && v <= maxb) maxb = v; }
+  // shared memory: draws stash [n_ind][ilp*T] + accumulators [n_ind][T] + small fixed part, <= 200 KB
+  const long long fixed = (long long)mppi_ode_smem_bytes(h->H, h->period, h->n_ind, ilp, 0);
+  const long long per_thread = 4ll * h->n_ind * (ilp + 1);
+  const long long tmax_smem = (200 * 1024 - fixed) / per_thread / 32 * 32;
+  if (tmax_smem < 32) return;  // too many inducing points: generic kernel (regenerates the draws)
+  if (maxb > tmax_smem) maxb = (int)tmax_smem;
+  const long long r0 = (N + sms * maxb * ilp - 1) / (sms * maxb * ilp);
+  long long best_cap = -1; int best_T = 32;
+  for (long long r = r0; r < r0 + 4; ++r) {
+    long long T = (N + r * sms * ilp - 1) / (r * sms * ilp);
+    T = (T + 31) / 32 * 32;
+    if (T < 32) T = 32;
+    if (T > maxb) continue;
+    const long long grid = std::min<long long>(sms, (N + T * ilp - 1) / (T * ilp));
+    const long long iters = (N + grid * T * ilp - 1) / (grid * T * ilp);
+    const long long cap = iters * T * ilp;  // per-SM time is proportional to iterations x (warps resident)
+    if (best_cap < 0 || cap < best_cap) { best_cap = cap; best_T = (int)T; }
+  }
+  h->ode_ilp = ilp;
+  h->ode_block = best_T;
+  h->ode_grid = (int)std::min<long long>(sms, (N + (long long)best_T * ilp - 1) / ((long long)best_T * ilp));
+  if (h->ode_grid < 1) h->ode_grid = 1;
+  h->ode_period_t = (h->period == 10 && !c.logging) ? 10 : 0;
+  if (getenv("CTK_K1_NO_UNROLL")) h->ode_period_t = 0;
+  h->ode_smem = mppi_ode_smem_bytes(h->H, h->period, h->n_ind, ilp, best_T);
+  h->ode_kernel = true;
+}
+
+static int make_fuse(ctk_handle* h, int mode, float* u_out_dev, MppiFuse* out) {
+  MppiFuse f{};
+  f.mode = mode;
+  f.world = 1; f.rank = 0; f.seq = 0;
+  f.ticket = h->d_ticket;
+  f.record_out = h->d_record;
+  f.mbox_local = h->d_mbox;
+  for (int r = 0; r < CTK_MAX_PEERS; ++r) f.mbox_peer[r] = h->mbox_peer[r];
+  f.u_nom = h->d_u_nom; f.u_prev = h->d_u_prev; f.u_out = u_out_dev; f.freeze_prev = h->cfg.freeze_previous_input;
+  if (mode == 2 && h->xworld > 1) {
+    f.world = h->xworld; f.rank = h->xrank;
+    h->xseq++;
+    if (h->xseq == 0) h->xseq = 1;
+    f.seq = h->xseq;
+  }
+  *out = f;
+  return CTK_OK;
+}
+
+// mode 1: rollouts + shard record (staged exchange follows)   mode 2: whole tick incl. cross-GPU exchange and u_nom update
+static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_dev) {
   NoiseSrc ns{};
   int rcn = make_noise(h, STREAM_MPPI, h->n_ind, 0, (size_t)h->NG, &ns);
   if (rcn != CTK_OK) return rcn;
   const ctk_config& c = h->cfg;
   const bool tc = (c.predictor == CTK_PRED_MLP && c.mlp_engine == CTK_MLP_TCGEN05);
+  const bool log = c.logging != 0;
+  MppiFuse fuse{};
+  make_fuse(h, tc ? 0 : mode, u_out_dev, &fuse);
+  if (h->ode_kernel) {
+    MppiOdeArgs a{};
+    a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
+    a.s0 = s_dev; a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = ns; a.k = h->ode_hot;
+    a.J = h->d_J; a.partials = h->d_partials; a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
+    a.fuse = fuse;
+    h->launches++;
+    KernelTimer kt(h);
+    cudaError_t e = launch_mppi_ode(h->cost.kind, log, h->ode_period_t, h->ode_ilp, h->ode_grid, h->ode_block, h->ode_smem, h->stream, a);
+    if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("mppi_ode_kernel: ") + cudaGetErrorString(e));
+    return CTK_OK;
+  }
   MppiArgs a{};
   a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
   a.s0 = s_dev; a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = ns;
@@ -423,29 +532,30 @@ static int mppi_local(ctk_handle* h, const float* s_dev, bool finalize, float* u
   a.kc = h->d_kc; a.kx = h->d_kx; a.mlp = h->mlp;
   a.J = h->d_J; a.partials = h->d_partials;
   a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
-  const bool log = c.logging != 0;
-  int nparts = h->mppi_grid;
+  a.fuse = fuse;
   if (tc) {
+    if (mode == 2 && h->xworld > 1) return fail(CTK_EINVAL, "the tcgen05 MLP engine uses the staged exchange (ctk_step_local / ctk_step_finish)");
+    int nparts = h->mppi_grid;
     std::string err;
     if (!mlp_tc_launch_mppi(h->mlp_tc, a, h->cost.kind, log, h->stream, &nparts, &h->launches, err))
       return fail(CTK_ECUDA, "mlp tcgen05 launch: " + err);
-  } else {
-    size_t smem = sizeof(float) * ((size_t)((h->H + 1) & ~1) + 2 * h->period + 32 + 32 * (h->n_ind + 1) +
-                                   (h->mppi_stash ? (size_t)h->n_ind * h->mppi_block : 0) + (size_t)h->n_ind * h->mppi_block +
-                                   pred_smem_floats(h));
+    MppiFinalize fin{};
+    fin.enable = (mode == 2) ? 1 : 0;
+    fin.H = h->H; fin.period = h->period; fin.n_ind = h->n_ind; fin.stdev = c.mppi_stdev; fin.lo = c.action_low; fin.hi = c.action_high;
+    fin.neg_inv_lbd = c.mppi_neg_inv_LBD; fin.u_nom = h->d_u_nom; fin.u_prev = h->d_u_prev; fin.u_out = u_out_dev;
+    fin.freeze_prev = c.freeze_previous_input;
     h->launches++;
-    KernelTimer kt(h);
-    cudaError_t e = launch_mppi_rollout(c.predictor == CTK_PRED_ODE ? 0 : 1, h->cost.kind, log, h->mppi_grid, h->mppi_block, smem,
-                                        h->stream, a);
-    if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("mppi_rollout_kernel: ") + cudaGetErrorString(e));
+    CU(launch_mppi_combine(h->d_partials, nparts, h->n_ind, c.mppi_neg_inv_LBD, h->d_record, fin, h->stream));
+    return CTK_OK;
   }
-  MppiFinalize fin{};
-  fin.enable = finalize ? 1 : 0;
-  fin.H = h->H; fin.period = h->period; fin.n_ind = h->n_ind; fin.stdev = c.mppi_stdev; fin.lo = c.action_low; fin.hi = c.action_high;
-  fin.neg_inv_lbd = c.mppi_neg_inv_LBD; fin.u_nom = h->d_u_nom; fin.u_prev = h->d_u_prev; fin.u_out = u_out_dev;
-  fin.freeze_prev = c.freeze_previous_input;
+  const size_t smem = sizeof(float) * ((size_t)((h->H + 1) & ~1) + 2 * h->period + 32 + 32 * (h->n_ind + 1) +
+                                       (h->mppi_stash ? (size_t)h->n_ind * h->mppi_block : 0) + (size_t)h->n_ind * h->mppi_block +
+                                       pred_smem_floats(h));
   h->launches++;
-  CU(launch_mppi_combine(h->d_partials, nparts, h->n_ind, c.mppi_neg_inv_LBD, h->d_record, fin, h->stream));
+  KernelTimer kt(h);
+  cudaError_t e = launch_mppi_rollout(c.predictor == CTK_PRED_ODE ? 0 : 1, h->cost.kind, log, h->mppi_grid, h->mppi_block, smem,
+                                      h->stream, a);
+  if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("mppi_rollout_kernel: ") + cudaGetErrorString(e));
   return CTK_OK;
 }
 
@@ -577,7 +687,7 @@ extern "C" int ctk_step_local(ctk_handle* h, const float* s_dev) {
   switch (h->cfg.optimizer) {
     case CTK_OPT_MPPI:
       h->tick++;
-      rc = mppi_local(h, s_dev, false, nullptr);
+      rc = mppi_local(h, s_dev, 1, nullptr);
       return rc;
     case CTK_OPT_CEM:
       if (h->cem_it == 0) h->tick++;
@@ -624,7 +734,7 @@ extern "C" int ctk_step(ctk_handle* h, const float* s_host, float* u_out_host) {
   int rc = CTK_OK;
   if (h->cfg.optimizer == CTK_OPT_MPPI) {
     h->tick++;
-    rc = mppi_local(h, h->d_s0, true, h->d_u_out);
+    rc = mppi_local(h, h->d_s0, 2, h->d_u_out);
   } else if (h->cfg.optimizer == CTK_OPT_CEM) {
     h->tick++;
     do {
@@ -638,9 +748,103 @@ extern "C" int ctk_step(ctk_handle* h, const float* s_host, float* u_out_host) {
     if (rc == CTK_OK) rc = rpgd_finish(h, h->d_u_out);
   }
   if (rc != CTK_OK) return rc;
-  CU(cudaMemcpyAsync(h->h_pin + 8, h->d_u_out, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(h->h_pin + 8, h->d_u_out, 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   u_out_host[0] = h->h_pin[8];
+  if (h->h_pin[9] != 0.0f) return fail(CTK_ECUDA, "cross-GPU exchange timed out: a peer shard did not deliver its record within 2 s");
+  return CTK_OK;
+}
+
+// Asynchronous, device-resident tick (no host copies, no synchronisation): with a connected exchange every shard
+// calls this once per tick and ends up with the same u_nom / u.
+extern "C" int ctk_step_device(ctk_handle* h, const float* s_dev, float* u_out_dev) {
+  REQ(h && s_dev, "null pointer");
+  if (!h->was_reset) return fail(CTK_ESTATE, "ctk_step before ctk_reset");
+  REQ(h->cfg.optimizer == CTK_OPT_MPPI || h->xworld == 1, "the fused cross-GPU exchange is implemented for MPPI; CEM shards use ctk_step_local / ctk_step_finish");
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->cfg.predictor == CTK_PRED_MLP && h->mlp.blob == nullptr) return fail(CTK_ESTATE, "MLP predictor without weights");
+  float* uo = u_out_dev ? u_out_dev : h->d_u_out;
+  int rc = CTK_OK;
+  h->tick++;
+  if (h->cfg.optimizer == CTK_OPT_MPPI) {
+    rc = mppi_local(h, s_dev, 2, uo);
+  } else if (h->cfg.optimizer == CTK_OPT_CEM) {
+    do {
+      rc = cem_local(h, s_dev, false);
+      if (rc != CTK_OK) break;
+      rc = cem_finish(h, h->cem_cand_ptr, h->cem_cand, uo);
+    } while (rc == CTK_OK && h->cem_it != 0);
+  } else {
+    rc = rpgd_local(h, s_dev);
+    if (rc == CTK_OK) rc = rpgd_finish(h, uo);
+  }
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused cross-GPU exchange: mailboxes in peer memory (one process per GPU -> CUDA IPC; one process -> peer access)
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int ctk_exchange_export(ctk_handle* h, void* ipc_handle_out64) {
+  REQ(h && ipc_handle_out64, "null pointer");
+  REQ(h->d_mbox != nullptr, "this optimizer has no exchange mailbox (MPPI only)");
+  CU(cudaSetDevice(h->cfg.device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t hd;
+  CU(cudaIpcGetMemHandle(&hd, h->d_mbox));
+  memcpy(ipc_handle_out64, &hd, sizeof(hd));
+  return CTK_OK;
+}
+static int exchange_reset(ctk_handle* h, int rank, int world) {
+  REQ(world >= 1 && world <= CTK_MAX_PEERS && rank >= 0 && rank < world, "need 0 <= rank < world <= 8");
+  CU(cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < CTK_MAX_PEERS; ++r) {
+    if (h->mbox_ipc[r] && h->mbox_peer[r]) cudaIpcCloseMemHandle(h->mbox_peer[r]);
+    h->mbox_peer[r] = nullptr; h->mbox_ipc[r] = false;
+  }
+  h->xworld = world; h->xrank = rank; h->xseq = 0;
+  CU(cudaMemset(h->d_mbox, 0, sizeof(unsigned long long) * 2 * CTK_MAX_PEERS * (h->n_ind + 2)));
+  return CTK_OK;
+}
+extern "C" int ctk_exchange_connect(ctk_handle* h, int rank, int world, const void* ipc_handles) {
+  REQ(h && ipc_handles, "null pointer");
+  REQ(h->d_mbox != nullptr, "this optimizer has no exchange mailbox (MPPI only)");
+  CU(cudaSetDevice(h->cfg.device));
+  int rc = exchange_reset(h, rank, world);
+  if (rc != CTK_OK) return rc;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { h->mbox_peer[r] = h->d_mbox; continue; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, (const char*)ipc_handles + (size_t)r * sizeof(hd), sizeof(hd));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      h->xworld = 1; h->xrank = 0;
+      return fail(CTK_ECUDA, std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+    }
+    h->mbox_peer[r] = (unsigned long long*)p;
+    h->mbox_ipc[r] = true;
+  }
+  return CTK_OK;
+}
+extern "C" int ctk_exchange_mailbox(ctk_handle* h, void** dev_ptr) {
+  REQ(h && dev_ptr, "null pointer");
+  *dev_ptr = h->d_mbox;
+  return CTK_OK;
+}
+extern "C" int ctk_exchange_connect_ptrs(ctk_handle* h, int rank, int world, void* const* mailboxes, const int* devices) {
+  REQ(h && mailboxes && devices, "null pointer");
+  REQ(h->d_mbox != nullptr, "this optimizer has no exchange mailbox (MPPI only)");
+  CU(cudaSetDevice(h->cfg.device));
+  int rc = exchange_reset(h, rank, world);
+  if (rc != CTK_OK) return rc;
+  for (int r = 0; r < world; ++r) {
+    if (r != rank && devices[r] != h->cfg.device) {
+      cudaError_t e = cudaDeviceEnablePeerAccess(devices[r], 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+      if (e != cudaSuccess) { h->xworld = 1; h->xrank = 0; return fail(CTK_ECUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); }
+    }
+    h->mbox_peer[r] = (r == rank) ? h->d_mbox : (unsigned long long*)mailboxes[r];
+  }
   return CTK_OK;
 }
 

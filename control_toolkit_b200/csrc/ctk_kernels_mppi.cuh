@@ -35,6 +35,103 @@ __device__ __forceinline__ void mppi_step(const MppiArgs& a, const CostC& cost, 
   u_last = u;
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Tick finish inside the rollout kernel (MppiFuse): combine softmin records, exchange across GPUs, update u_nom.
+// ----------------------------------------------------------------------------------------------------------------
+// records in[cnt][P] = [rho, a, b_z[n_ind]] -> out[P] (shared memory), rescaled exactly to the common minimum.
+// GLOBAL: `in` was written by other blocks of this launch -> read through L2 (ld.cg).  All threads participate.
+template <bool GLOBAL>
+__device__ __forceinline__ void combine_records(const float* in, int cnt, int P, float neg_inv_lbd, float* out, float* sh_red) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+  float mn = INFINITY;
+  for (int b = tid; b < cnt; b += blockDim.x) mn = fminf(mn, GLOBAL ? __ldcg(in + (size_t)b * P) : in[(size_t)b * P]);
+  const float rho = block_min(mn, sh_red);
+  for (int c = w; c < P - 1; c += nw) {
+    float acc = 0.0f;
+    for (int b = lane; b < cnt; b += 32) {
+      const float rb = GLOBAL ? __ldcg(in + (size_t)b * P) : in[(size_t)b * P];
+      const float v = GLOBAL ? __ldcg(in + (size_t)b * P + 1 + c) : in[(size_t)b * P + 1 + c];
+      const float sc = (rb < INFINITY) ? expf((rb - rho) * neg_inv_lbd) : 0.0f;
+      acc = fmaf(sc, v, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[1 + c] = acc;
+  }
+  if (tid == 0) out[0] = rho;
+  __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Called by ALL threads of EVERY block after the block stored its record partials[blockIdx.x][P].  The last block to
+// arrive finishes the tick.  scratch: >= 9 * P floats of shared memory; sh_unom: the shifted nominal (prologue copy).
+__device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float* partials, int n_ind, int H, int period,
+                                                 float stdev, float lo, float hi, float neg_inv_lbd, const float* sh_unom,
+                                                 float* scratch, float* sh_red) {
+  if (f.mode == 0) return;
+  const int tid = threadIdx.x, P = n_ind + 2;
+  __shared__ int sh_last;
+  __threadfence();  // this block's record is visible device-wide before the ticket
+  __syncthreads();
+  if (tid == 0) sh_last = (atomicAdd(f.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!sh_last) return;
+  if (tid == 0) *f.ticket = 0u;  // re-arm for the next launch (stream order makes this visible)
+  __threadfence();
+  float* sh_rec = scratch;      // [P]
+  float* sh_all = scratch + P;  // [world][P]
+  combine_records<true>(partials, (int)gridDim.x, P, neg_inv_lbd, sh_rec, sh_red);
+  if (f.record_out != nullptr)
+    for (int c = tid; c < P; c += blockDim.x) f.record_out[c] = sh_rec[c];
+  if (f.mode < 2) return;
+  int status = 0;
+  if (f.world > 1) {
+    // one 8-byte store per value: (float bits, seq).  The reader polls until the sequence number matches, so no
+    // fence / flag round trip is needed; double-buffered by seq parity (a rank can be at most one tick ahead).
+    const size_t base = (size_t)(f.seq & 1u) * f.world * P;
+    for (int i = tid; i < f.world * P; i += blockDim.x) {
+      const int r = i / P, c = i - r * P;
+      const unsigned long long v = ((unsigned long long)f.seq << 32) | (unsigned long long)__float_as_uint(sh_rec[c]);
+      unsigned long long* dst = f.mbox_peer[r] + base + (size_t)f.rank * P + c;
+      asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
+    }
+    const unsigned long long t0 = globaltimer_ns();
+    for (int i = tid; i < f.world * P; i += blockDim.x) {
+      const unsigned long long* src = f.mbox_local + base + i;
+      unsigned long long v;
+      int spins = 0;
+      while (true) {
+        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+        if ((unsigned int)(v >> 32) == f.seq) break;
+        if ((++spins & 1023) == 0 && globaltimer_ns() - t0 > 2000000000ull) { status = 1; break; }  // 2 s: peer lost
+      }
+      sh_all[i] = __uint_as_float((unsigned int)(v & 0xffffffffull));
+    }
+    status = __syncthreads_or(status);
+    combine_records<false>(sh_all, f.world, P, neg_inv_lbd, sh_rec, sh_red);
+  }
+  // optimizer_mppi.py:190-191: u_nom <- clip(shift(u_nom) + interp(sum_n w_n z_n) * stdev / sum_n w_n)
+  const float a = sh_rec[1];
+  for (int t = tid; t < H; t += blockDim.x) {
+    const int seg = t / period, j = t - seg * period;
+    float w0, w1;
+    interp_weights(j, period, &w0, &w1);
+    const float bz0 = sh_rec[2 + seg];
+    const float bz1 = (j > 0) ? sh_rec[2 + seg + 1] : 0.0f;
+    const float b = (fmaf(bz1, w1, bz0 * w0) * stdev) / a;
+    const float un = fminf(fmaxf(sh_unom[t] + b, lo), hi);
+    f.u_nom[t] = un;
+    if (t == 0) {
+      if (!f.freeze_prev) f.u_prev[0] = un;
+      if (f.u_out != nullptr) { f.u_out[0] = status ? __int_as_float(0x7fc00000) : un; f.u_out[1] = (float)status; }
+    }
+  }
+}
+
 // K1.  One CTA per SM slot, grid-stride over rollouts (host sizes grid x block so that every thread runs the same
 // number of rollouts: no tail wave).  Each thread keeps an online softmin over its rollouts; the block emits ONE record
 // [rho, a, b_z[n_ind]] at the end (a single block-wide reduction per launch).
@@ -183,6 +280,8 @@ __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const M
     out[1 + c] = s;
   }
   if (tid == 0) out[0] = rho_b;
+  // fused K2 (+ cross-GPU exchange): the last block to retire finishes the tick
+  mppi_tick_finish(a.fuse, a.partials, a.n_ind, a.H, a.period, a.stdev, a.lo, a.hi, a.neg_inv_lbd, sh_unom, sh_part, sh_red);
 }
 
 __global__ void __launch_bounds__(1024) mppi_combine_kernel(const float* __restrict__ in, int cnt, int n_ind,

@@ -1,0 +1,252 @@
+// ctk_kernels_mppi_ode.cuh -- K1 for the CartPole ODE predictor: fused sample -> rollout -> cost -> softmin record ->
+// (last block) tick finish.  Replaces reference optimizer_mppi.py:170-193 for one tick when the predictor is the Euler
+// ODE with intermediate_steps == 1 (the headline configuration); other cases run the generic kernel of
+// ctk_kernels_mppi.cuh.
+//
+// What is different from the generic kernel (all measured with ncu, profiles/):
+//  * scaled state variables (OdeHot): T = angle/sqrt(2), W = beta*angleD, V = (cF/g)*positionD remove 6 multiplies per
+//    step; every constant multiplier is a kernel parameter that ptxas keeps in a uniform register, so all but four FMAs
+//    per step read at most two vector registers (the sm_100 register file feeds 3-source FFMAs at ~2/3 rate);
+//  * the control terms of the stage cost and of the MPPI correction collapse to u*(kA u + kB u_prev + kC du); the
+//    du^2 term of the correction has a closed form per inducing-point segment and leaves the step loop entirely;
+//  * PERIOD is a template parameter: a segment is fully unrolled, the interpolation weight j/PERIOD is an immediate and
+//    du = fma(dy, w_j, y0) is one instruction;
+//  * ILP rollouts per thread are advanced in lock step (independent dependency chains): the last warps of an SM
+//    sub-partition still fill the FMA pipe, which removes the tail the hi-wid-first warp arbiter otherwise produces;
+//  * prologue global loads (s0, u_prev, u_nom) are issued together; no other global read precedes the rollout loop.
+#pragma once
+#include "ctk_device.cuh"
+#include "ctk_kernels_mppi.cuh"
+
+namespace ctk {
+
+constexpr float kInvSqrt2 = 0.70710678118654752f;
+constexpr float kSqrt2 = 1.41421356237309505f;
+// period of T = angle/sqrt(2):  2*pi/sqrt(2) = sqrt(2)*pi, split hi + lo
+constexpr float kTPerHi = 4.44288301467895508f;      // fp32(sqrt(2)*pi)
+constexpr float kTPerLo = -7.6520588976e-08f;         // sqrt(2)*pi - fp32(sqrt(2)*pi)
+constexpr float kInvTPer = 0.22507907903927651f;     // 1/(sqrt(2)*pi)
+
+struct Roll {  // one rollout's registers
+  float T, W, c, s, x, V, omc, ul, acc, y0, dy, y1;
+};
+
+// One rollout step.  wj = j/period (immediate when PERIOD is a template constant).
+template <int KIND, bool LOG>
+__device__ __forceinline__ void ode_mppi_step(const MppiOdeArgs& a, const OdeHot& k, Roll& r, float unom_t, float wj, bool first,
+                                              int t, int n, bool active) {
+  // Interpolator.py:97-106 (two non-zero weights): du = y0 (1 - wj) + y1 wj = y0 + (y1 - y0) wj
+  const float du = first ? r.y0 : fmaf(r.dy, wj, r.y0);
+  const float u = fminf(fmaxf(unom_t + du, k.lo), k.hi);  // optimizer_mppi.py:186-187
+  if (LOG && active) {
+    float* p = a.log_traj_soa + (size_t)t * 6 * a.N + n;
+    p[0] = r.T * kSqrt2; p[a.N] = r.W * k.inv_beta; p[2 * (size_t)a.N] = r.c; p[3 * (size_t)a.N] = r.s;
+    p[4 * (size_t)a.N] = r.x; p[5 * (size_t)a.N] = r.V * k.inv_cFg;
+    a.log_Q_soa[(size_t)t * a.N + n] = u;
+  }
+  // ---- stage cost / (H+1)  (spec: DESIGN.md section 3; Cost_Functions/__init__.py:49-64) ----
+  const float d = r.x - k.target;
+  const float e = fmaxf(fabsf(r.x) - k.thl_095, 0.0f);  // indicator(|x| > 0.95 THL) * (|x| - 0.95 THL)
+  float acc = r.acc;
+  acc = fmaf(d * d, k.k_dd, acc);
+  acc = fmaf(e * e, k.k_bar, acc);
+  acc = fmaf(r.omc * r.omc, k.k_ep, acc);
+  if (KIND == 1) {
+    acc = fmaf(r.W * r.W, k.k_ekp2, acc);
+    acc += (fabsf(r.x) > k.thl_09) ? k.k_border : 0.0f;
+  }
+  // cc u^2 + ccrc (u - u_prev)^2 + MPPI correction (0.5 R u^2 + R u du)  ==  u (kA u + kB u_prev + kC du) + ccrc u_prev^2;
+  // the u_prev^2 terms telescope into kA (boundary terms are added once per rollout by the caller)
+  float q = u * k.kA;
+  q = fmaf(r.ul, k.kB, q);
+  q = fmaf(du, k.kC, q);
+  r.acc = fmaf(u, q, acc);
+  r.ul = u;
+  // ---- Euler step with the old derivatives, scaled variables (see OdeHot) ----
+  float nn = fmaf(k.cUg, u, r.V);
+  const float ws = r.W * r.s;
+  nn = fmaf(-r.W, ws, nn);
+  const float t3 = fmaf(k.cTl2, r.W, r.s);
+  nn = fmaf(t3, r.c, nn);
+  const float Ap = fmaf(-r.c, r.c, k.K1p);
+  const float vd = nn * fast_rcp(Ap);
+  const float X = fmaf(vd, r.c, fmaf(k.kTm2, r.W, r.s));
+  float T = fmaf(r.W, k.h_T, r.T);
+  r.W = fmaf(X, k.h_W, r.W);
+  r.x = fmaf(r.V, k.h_x, r.x);
+  r.V = fmaf(vd, k.h_V, r.V);
+  // wrap: angle <- atan2(sin, cos)  ==  T - period * rint(T / period)
+  const float kk = rintf(T * kInvTPer);
+  T = fmaf(-kk, kTPerHi, T);
+  T = fmaf(-kk, kTPerLo, T);
+  r.T = T;
+  // half-angle sincos (ctk_math.cuh sincos_half with x = T)
+  const float tt = T * T;
+  float ps = fmaf(tt, kSinHalfLead, -2.4761327949818224e-05f);
+  ps = fmaf(tt, ps, 0.002083262661471963f);
+  ps = fmaf(tt, ps, -0.08333329111337662f);
+  const float sh = fmaf(T * tt, ps, T);
+  float pc = fmaf(tt, kCosHalfLead, 2.1885084606765304e-06f);
+  pc = fmaf(tt, pc, -0.0002455138601362705f);
+  pc = fmaf(tt, pc, 0.01473138015717268f);
+  pc = fmaf(tt, pc, -0.3535533845424652f);
+  const float ch = fmaf(tt, pc, 1.4142135381698608f);
+  r.omc = sh * sh;
+  r.c = fmaf(-sh, sh, 1.0f);
+  r.s = sh * ch;
+}
+
+template <int KIND, bool LOG, int PERIOD, int ILP, int MAXT>
+__global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
+  extern __shared__ float smem[];
+  const int T_ = blockDim.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = T_ >> 5;
+  const int period = PERIOD > 0 ? PERIOD : a.period;
+  const int P = a.n_ind + 1;
+  float* sh_unom = smem;                                   // [H] shifted nominal (+ pad)
+  float* sh_w = smem + ((a.H + 3) & ~3);                   // [period] j/period (runtime-period path)
+  float* sh_red = sh_w + ((period + 3) & ~3);              // [32]
+  float* sh_part = sh_red + 32;                            // [32][P]  (also the finish scratch)
+  float* sh_z = sh_part + 32 * P;                          // [n_ind][ILP*T] standard draws of the rollouts in flight
+  float* sh_acc = sh_z + (size_t)a.n_ind * ILP * T_;       // [n_ind][T] per-thread sum_n e_n z_n,i
+
+  // ---- prologue: the only global reads before the loop, issued together ----
+  const float s0v = (tid < 6) ? a.s0[tid] : 0.0f;
+  const float upv = a.u_prev[0];
+  for (int t = tid; t < a.H; t += T_) sh_unom[t] = a.u_nom[min(t + 1, a.H - 1)];  // optimizer_mppi.py:184
+  for (int j = tid; j < period; j += T_) sh_w[j] = (float)j / (float)period;      // Interpolator.py:63-74
+  if (tid < 6) sh_red[tid] = s0v;
+  const OdeHot& k = a.k;
+  for (int i = 0; i < a.n_ind; ++i) sh_acc[(size_t)i * T_ + tid] = 0.0f;
+  __syncthreads();
+  const float th0 = sh_red[0], om0 = sh_red[1], c0 = sh_red[2], sn0 = sh_red[3], x0 = sh_red[4], v0 = sh_red[5];
+  const float omc0 = 1.0f - cosf(th0);  // spec: E_pot uses cos(angle) of the measured state
+  const float T0 = th0 * kInvSqrt2, W0 = om0 * k.beta, V0 = v0 * k.cFg;
+  __syncthreads();  // sh_red is reused below
+
+  // closed form of sum_j du_j^2 over a full segment: cnt y0^2 + dy (2 W1 y0 + W2 dy)
+  const float pf = (float)period;
+  const float segW1x2_full = pf - 1.0f;                                             // 2 sum_j j/p
+  const float segW2_full = (pf - 1.0f) * (2.0f * pf - 1.0f) / (6.0f * pf);          // sum_j (j/p)^2
+  const int stride = gridDim.x * T_ * ILP;
+  const int nblk = (a.n_ind + 3) >> 2;
+  float rho_t = INFINITY, a_t = 0.0f;  // per-thread online softmin (optimizer_mppi.py:163-168, exact combine later)
+  float* sa = sh_acc + tid;
+
+  for (int base = blockIdx.x * T_ * ILP; base < a.N; base += stride) {
+    Roll r[ILP];
+    int n[ILP];
+    bool active[ILP];
+    // ---- K0: draws of the ILP rollouts -> shared-memory stash ----
+#pragma unroll
+    for (int q = 0; q < ILP; ++q) {
+      n[q] = base + q * T_ + tid;
+      active[q] = n[q] < a.N;
+      const uint32_t ng = (uint32_t)(a.off + (active[q] ? n[q] : 0));
+      float* sz = sh_z + q * T_ + tid;
+      for (int blk = 0; blk < nblk; ++blk) {
+        float zz[4];
+        noise4(a.noise, ng, (uint32_t)blk, zz);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (blk * 4 + e < a.n_ind) sz[(size_t)(blk * 4 + e) * ILP * T_] = zz[e];
+      }
+      r[q].T = T0; r[q].W = W0; r[q].c = c0; r[q].s = sn0; r[q].x = x0; r[q].V = V0; r[q].omc = omc0;
+      r[q].ul = upv;
+      r[q].acc = (k.k_ccrc * upv) * upv;  // telescoped ccrc term of u_{-1}
+      r[q].y0 = 0.0f; r[q].dy = 0.0f;
+      r[q].y1 = sz[0] * k.stdev;  // y0 of segment 0   (:173-175 normal * stdev before interpolation)
+    }
+    // ---- rollout: segments between inducing points ----
+    int t = 0;
+    for (int seg = 0; t < a.H; ++seg) {
+      const int cnt = min(period, a.H - t);
+      const bool full = (cnt == period);
+      const float cntf = (float)cnt;
+      const float w1x2 = full ? segW1x2_full : cntf * (cntf - 1.0f) / pf;
+      const float w2 = full ? segW2_full : (cntf - 1.0f) * cntf * (2.0f * cntf - 1.0f) / (6.0f * pf * pf);
+#pragma unroll
+      for (int q = 0; q < ILP; ++q) {
+        const float* sz = sh_z + q * T_ + tid;
+        const float y0 = r[q].y1;
+        const float y1 = (seg + 1 < a.n_ind) ? sz[(size_t)(seg + 1) * ILP * T_] * k.stdev : 0.0f;
+        r[q].y0 = y0;
+        r[q].y1 = y1;
+        r[q].dy = y1 - y0;
+        // optimizer_mppi.py:154-155, du^2 term: cc_weight 0.5 (1 - 1/NU) R sum_j du_j^2
+        const float sq = fmaf(r[q].dy, fmaf(w2, r[q].dy, w1x2 * y0), cntf * (y0 * y0));
+        r[q].acc = fmaf(sq, k.k_du2, r[q].acc);
+      }
+      if (PERIOD > 0 && full) {
+#pragma unroll
+        for (int j = 0; j < (PERIOD > 0 ? PERIOD : 1); ++j) {
+          const float un = sh_unom[t + j];
+#pragma unroll
+          for (int q = 0; q < ILP; ++q)
+            ode_mppi_step<KIND, LOG>(a, k, r[q], un, (float)j / (float)(PERIOD > 0 ? PERIOD : 1), j == 0, t + j, n[q], active[q]);
+        }
+      } else {
+#pragma unroll 2
+        for (int j = 0; j < cnt; ++j) {
+          const float un = sh_unom[t + j];
+          const float wj = sh_w[j];
+#pragma unroll
+          for (int q = 0; q < ILP; ++q) ode_mppi_step<KIND, LOG>(a, k, r[q], un, wj, false, t + j, n[q], active[q]);
+        }
+      }
+      t += cnt;
+    }
+
+    // ---- per-rollout total + per-thread online softmin ----
+#pragma unroll
+    for (int q = 0; q < ILP; ++q) {
+      const float th = r[q].T * kSqrt2;
+      if (LOG && active[q]) {
+        float* p = a.log_traj_soa + (size_t)a.H * 6 * a.N + n[q];
+        p[0] = th; p[a.N] = r[q].W * k.inv_beta; p[2 * (size_t)a.N] = r[q].c; p[3 * (size_t)a.N] = r[q].s;
+        p[4 * (size_t)a.N] = r[q].x; p[5 * (size_t)a.N] = r[q].V * k.inv_cFg;
+      }
+      const float term = (fabsf(th) > 0.2f || fabsf(r[q].x - k.target) > k.thl_01) ? k.k_term : 0.0f;
+      // Cost_Functions/__init__.py:90-92 (mean over H+1 incl. the terminal cost); the last step's telescoped
+      // ccrc u^2 term is removed again; optimizer_mppi.py:160
+      const float S = (fmaf(-k.k_ccrc * r[q].ul, r[q].ul, r[q].acc) + term) - k.shift;
+      if (active[q]) {
+        a.J[n[q]] = S;
+        if (S < INFINITY) {
+          const float rho_n = fminf(rho_t, S);
+          const float so = (rho_t < INFINITY) ? __expf((rho_t - rho_n) * k.neg_inv_lbd) : 0.0f;  // rescale the old sums
+          const float sn = __expf((S - rho_n) * k.neg_inv_lbd);
+          a_t = fmaf(a_t, so, sn);
+          rho_t = rho_n;
+          const float* sz = sh_z + q * T_ + tid;
+          for (int i = 0; i < a.n_ind; ++i) {
+            const size_t o = (size_t)i * T_;
+            sa[o] = fmaf(sa[o], so, sn * sz[(size_t)i * ILP * T_]);
+          }
+        }
+      }
+    }
+  }
+
+  // ---- one block softmin record [rho_b, a_b, b_z[n_ind]] ----
+  const float rho_b = block_min(rho_t, sh_red);
+  const float sc = (rho_t < INFINITY) ? expf((rho_t - rho_b) * k.neg_inv_lbd) : 0.0f;
+  {
+    const float ws = warp_sum(a_t * sc);
+    if (lane == 0) sh_part[w * P] = ws;
+  }
+  for (int i = 0; i < a.n_ind; ++i) {
+    const float ws = warp_sum(sa[(size_t)i * T_] * sc);
+    if (lane == 0) sh_part[w * P + 1 + i] = ws;
+  }
+  __syncthreads();
+  float* out = a.partials + (size_t)blockIdx.x * (P + 1);
+  for (int c = tid; c < P; c += T_) {
+    float s = 0.0f;
+    for (int ww = 0; ww < nw; ++ww) s += sh_part[ww * P + c];
+    out[1 + c] = s;
+  }
+  if (tid == 0) out[0] = rho_b;
+  mppi_tick_finish(a.fuse, a.partials, a.n_ind, a.H, period, k.stdev, k.lo, k.hi, k.neg_inv_lbd, sh_unom, sh_part, sh_red);
+}
+
+}  // namespace ctk

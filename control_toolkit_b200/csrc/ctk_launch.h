@@ -10,6 +10,10 @@ namespace ctk {
 // pred: 0 ODE, 1 MLP (SIMT engine); kind: cost class; log: write SoA trajectory logs
 cudaError_t launch_mppi_rollout(int pred, int kind, bool log, int nblocks, int block, size_t smem, cudaStream_t st, const MppiArgs& a);
 int mppi_max_block_threads(int pred);
+// K1 for the ODE predictor with intermediate_steps == 1 (scaled variables, ILP rollouts per thread)
+cudaError_t launch_mppi_ode(int kind, bool log, int period_t, int ilp, int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a);
+int mppi_ode_max_block(int ilp);
+size_t mppi_ode_smem_bytes(int H, int period, int n_ind, int ilp, int block);
 cudaError_t launch_mppi_combine(const float* in, int cnt, int n_ind, float neg_inv_lbd, float* record_out,
                                 const MppiFinalize& fin, cudaStream_t st);
 cudaError_t launch_transpose(const float* in, float* out, int R, int C, cudaStream_t st);

@@ -1,5 +1,6 @@
 // ctk_mppi.cu -- translation unit owning the MPPI kernels (K1, K2), the log transpose and the nominal rollout.
 #include "ctk_kernels_mppi.cuh"
+#include "ctk_kernels_mppi_ode.cuh"
 #include "ctk_launch.h"
 
 namespace ctk {
@@ -25,6 +26,31 @@ cudaError_t launch_mppi_rollout(int pred, int kind, bool log, int nblocks, int b
 }
 int mppi_max_block_threads(int pred) { return pred == 0 ? OdePred::kMaxThreads : MlpSimtPred::kMaxThreads; }
 size_t mppi_pred_smem_floats(int pred, const MlpDev& m) { return pred == 0 ? 0 : MlpSimtPred::smem_floats(m); }
+
+// K1 for the ODE predictor (ctk_kernels_mppi_ode.cuh).  period_t: 10 -> the segment-unrolled instantiation, else runtime period.
+template <int KIND, bool LOG, int PERIOD, int ILP>
+static cudaError_t launch_mppi_ode_t(int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a) {
+  auto k = mppi_ode_kernel<KIND, LOG, PERIOD, ILP, 1024>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  k<<<grid, block, smem, st>>>(a);
+  return cudaGetLastError();
+}
+template <int KIND>
+static cudaError_t launch_mppi_ode_k(bool log, int period_t, int ilp, int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a) {
+  if (log) return launch_mppi_ode_t<KIND, true, 0, 1>(grid, block, smem, st, a);
+  if (period_t == 10) return ilp == 2 ? launch_mppi_ode_t<KIND, false, 10, 2>(grid, block, smem, st, a) : launch_mppi_ode_t<KIND, false, 10, 1>(grid, block, smem, st, a);
+  return ilp == 2 ? launch_mppi_ode_t<KIND, false, 0, 2>(grid, block, smem, st, a) : launch_mppi_ode_t<KIND, false, 0, 1>(grid, block, smem, st, a);
+}
+cudaError_t launch_mppi_ode(int kind, bool log, int period_t, int ilp, int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a) {
+  return kind == 0 ? launch_mppi_ode_k<0>(log, period_t, ilp, grid, block, smem, st, a) : launch_mppi_ode_k<1>(log, period_t, ilp, grid, block, smem, st, a);
+}
+int mppi_ode_max_block(int ilp) { (void)ilp; return 1024; }
+size_t mppi_ode_smem_bytes(int H, int period, int n_ind, int ilp, int block) {
+  return sizeof(float) * ((size_t)((H + 3) & ~3) + ((period + 3) & ~3) + 32 + 32 * (size_t)(n_ind + 1) + (size_t)n_ind * ilp * block + (size_t)n_ind * block);
+}
 
 cudaError_t launch_mppi_combine(const float* in, int cnt, int n_ind, float neg_inv_lbd, float* record_out,
                                 const MppiFinalize& fin, cudaStream_t st) {

@@ -4,7 +4,10 @@ The path shards naturally by sample: rank r evaluates the
 [offset_r, offset_r + count_r).  Philox counters and the injected-noise buffer are indexed by GLOBAL id, so the
 sampled population is independent of the number of shards.  Per tick the only exchange is
 
-* MPPI : one all-gather of the per-shard softmin record [rho_r, a_r, b_z,r[n_ind]]   (n_ind + 2 floats),
+* MPPI : the per-shard softmin record [rho_r, a_r, b_z,r[n_ind]] (n_ind + 2 floats).  Default ("p2p"): every shard's
+         rollout kernel stores its record straight into the peers' mailboxes over NVLink (CUDA IPC mapped memory) and the
+         last block of each shard combines them -- the whole sharded tick is ONE kernel launch per GPU, no NCCL call.
+         Fallback ("nccl", or CTK_EXCHANGE=nccl): one all-gather of the record between two kernels (staged),
 * CEM  : per outer iteration one all-gather of k (ordered-cost, global-id) keys       (2k floats); the elite control
          rows are regenerated from the counter-based noise on every rank, never sent,
 * RPGD : none (replicas only).
@@ -73,15 +76,45 @@ class ShardPlan:
 
     # -- one sharded tick through the C ABI -----------------------------------------------------------------------
     def attach(self, opt, lib) -> None:
-        """Run the handle on torch's current stream so the NCCL all-gather is ordered with the kernels."""
+        """Run the handle on torch's current stream (ordering with NCCL / torch events) and, for MPPI on more than one
+        shard, connect the fused NVLink exchange: all-gather the 64-byte CUDA IPC handles of the mailboxes."""
+        import os
+
         import torch
+        import torch.distributed as dist
         torch.cuda.set_device(opt.device)
         L.check(lib.ctk_set_stream(opt._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         opt._shard_attached = True
+        opt._exchange = "none" if self.world_size == 1 else "nccl"
+        if self.world_size > 1 and opt._OPT == L.OPT_MPPI and os.environ.get("CTK_EXCHANGE", "p2p") != "nccl":
+            mine = (C.c_ubyte * 64)()
+            L.check(lib.ctk_exchange_export(opt._h, C.cast(mine, C.c_void_p)))
+            dev = f"cuda:{opt.device}"
+            t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=dev)
+            allh = torch.empty(64 * self.world_size, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, t, group=self.group)
+            blob = bytes(allh.cpu().numpy().tobytes())
+            buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+            rc = lib.ctk_exchange_connect(opt._h, self.rank, self.world_size, C.cast(buf, C.c_void_p))
+            ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)  # all shards or none
+            if int(ok.item()) == 1:
+                opt._exchange = "p2p"
+            else:
+                import warnings
+                warnings.warn("fused NVLink exchange unavailable (%s); using the staged NCCL all-gather"
+                              % (lib.ctk_last_error() or b"").decode())
+                if rc == 0:  # connected here but not everywhere: fall back consistently
+                    none = (C.c_ubyte * 64)()
+                    lib.ctk_exchange_connect(opt._h, 0, 1, C.cast(none, C.c_void_p))
+            dist.barrier(group=self.group)  # every mailbox is mapped before the first tick stores into it
 
     def run_tick_device(self, opt, lib, s_dev_ptr: int, u_dev_ptr: int) -> None:
         """Asynchronous sharded tick: s and u stay on the device (used by bench.py's device-resident timing)."""
         import torch
+        if getattr(opt, "_exchange", "nccl") in ("p2p", "none"):
+            L.check(lib.ctk_step_device(opt._h, C.c_void_p(s_dev_ptr), C.c_void_p(u_dev_ptr)))
+            return
         while True:
             more = L.check(lib.ctk_step_local(opt._h, C.c_void_p(s_dev_ptr)))
             ptr, n = C.c_void_p(), C.c_size_t()
@@ -109,4 +142,7 @@ class ShardPlan:
         opt._s_pin.copy_(torch.from_numpy(s32))
         opt._s_dev.copy_(opt._s_pin, non_blocking=True)
         self.run_tick_device(opt, lib, opt._s_dev.data_ptr(), opt._u_dev.data_ptr())
-        return opt._u_dev[:1].cpu().numpy()
+        out = opt._u_dev[:2].cpu().numpy()
+        if opt._exchange == "p2p" and out[1] != 0.0:
+            raise RuntimeError("cross-GPU exchange timed out: a peer shard did not deliver its record within 2 s")
+        return out[:1]

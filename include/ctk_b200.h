@@ -162,6 +162,23 @@ int ctk_step_local(ctk_handle *h, const float *s_dev);
 int ctk_partials(ctk_handle *h, float **dev_ptr, size_t *n_floats);
 int ctk_step_finish(ctk_handle *h, const float *gathered_dev, int num_shards, float *u_out_dev);
 
+/* Asynchronous device-resident tick: s_dev [ns] and u_out_dev [2] (u, exchange status) stay on the device, nothing is
+   synchronised.  With a connected exchange (below) every shard calls it once per tick; the whole tick -- rollouts,
+   softmin record, NVLink record exchange, u_nom update -- is ONE kernel launch.                                    */
+int ctk_step_device(ctk_handle *h, const float *s_dev, float *u_out_dev);
+
+/* ---- fused cross-GPU exchange (MPPI) --------------------------------------------------------------- */
+/* Each shard owns a mailbox in its HBM; peers store their softmin record (n_ind + 2 values, each packed with the tick's
+   sequence number in one 8-byte store) straight into it over NVLink from inside the rollout kernel, and the last block
+   of every shard combines the records -- no NCCL call, no extra launch.  One process per GPU: export the local
+   mailbox as a 64-byte CUDA IPC handle, all-gather the handles with any host transport, connect.  One process driving
+   several GPUs (tests): pass the mailbox pointers and device ordinals directly.  ctk_step / ctk_step_device then
+   exchange; every shard must tick in lock step.  A peer that never delivers makes ctk_step fail after 2 s.           */
+int ctk_exchange_export(ctk_handle *h, void *ipc_handle_out64);
+int ctk_exchange_connect(ctk_handle *h, int rank, int world, const void *ipc_handles /* world x 64 bytes */);
+int ctk_exchange_mailbox(ctk_handle *h, void **dev_ptr);
+int ctk_exchange_connect_ptrs(ctk_handle *h, int rank, int world, void *const *mailboxes, const int *devices);
+
 /* ---- state / logs ------------------------------------------------------------------------------------------- */
 int ctk_get_state(ctk_handle *h, int which, float *dst_host, size_t n);
 int ctk_set_state(ctk_handle *h, int which, const float *src_host, size_t n);
