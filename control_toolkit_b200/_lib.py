@@ -98,6 +98,7 @@ SYMBOLS = {
     "ctk_get_launch_count": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "ctk_enable_kernel_timing": (C.c_int, [_H, C.c_int]),
     "ctk_get_kernel_timing": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "ctk_debug_trace": (C.c_int, [_H, C.c_int, C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_int)]),
     "ctk_rollout_single": (C.c_int, [_H, _FP, _FP, _FP, _FP]),
     "ctk_last_error": (C.c_char_p, []),
     "ctk_abi_version": (C.c_int, []),

@@ -58,7 +58,8 @@ struct MppiFuse {
   int mode;                  // 0: block records only (legacy K2 launch follows)  1: + shard record  2: + finalize
   int world, rank;           // shards taking part in the exchange (1: no exchange)
   unsigned int seq;          // exchange sequence number of this tick (monotonic, never 0)
-  unsigned int* ticket;      // device counter (self-resetting): blocks retired
+  unsigned int lseq;         // sequence number of this launch (monotonic, never 0): tag of the block records
+  unsigned long long* tagged;  // [gridDim.x][2 + n_ind] block records as (value, lseq) pairs
   float* record_out;         // [2 + n_ind] shard record (mode >= 1)
   unsigned long long* mbox_local;                 // [2][world][2 + n_ind] (value, seq) pairs written by the peers
   unsigned long long* mbox_peer[CTK_MAX_PEERS];   // peers' mailboxes (mbox_peer[rank] == mbox_local)
@@ -126,6 +127,7 @@ struct MppiOdeArgs {
   float* partials;      // [gridDim.x][2 + n_ind]
   float* log_traj_soa;  // [(H+1)][6][N] or null
   float* log_Q_soa;     // [H][N] or null
+  unsigned long long* trace;  // [gridDim.x][8] globaltimer stamps per block (diagnostics) or null
   MppiFuse fuse;
 };
 

@@ -45,16 +45,22 @@ __device__ __forceinline__ void noise4(const NoiseSrc& ns, uint32_t n_global, ui
     out[2] = (float)(r.z >> 8) * 5.9604644775390625e-8f;
     out[3] = (float)(r.w >> 8) * 5.9604644775390625e-8f;
   } else {
-    // Box-Muller on (0,1] x [-0.5,0.5): statistical quality only (no parity requirement on this branch)
-    const float u1 = fmaf((float)(r.x >> 8), 5.9604644775390625e-8f, 5.9604644775390625e-8f);
-    const float u3 = fmaf((float)(r.z >> 8), 5.9604644775390625e-8f, 5.9604644775390625e-8f);
-    const float a2 = ((float)(int32_t)r.y) * 1.4629180792671596e-9f;  // 2*pi * y / 2^32 in [-pi, pi)
-    const float a4 = ((float)(int32_t)r.w) * 1.4629180792671596e-9f;
-    const float r1 = sqrtf(-2.0f * __logf(u1));
-    const float r3 = sqrtf(-2.0f * __logf(u3));
-    float s2, c2, s4, c4;
-    __sincosf(a2, &s2, &c2);
-    __sincosf(a4, &s4, &c4);
+    // Box-Muller on (0,1] x [-pi,pi): statistical quality only (no parity requirement on this branch).  Uniforms are built
+    // from the top 23 bits with the exponent trick (ALU pipe, no I2F), radius and angle use one MUFU each:
+    // r = sqrt(-2 ln2 * log2(u)).
+    const float u1 = 2.0f - __uint_as_float(0x3f800000u | (r.x >> 9));                    // (0, 1]
+    const float u3 = 2.0f - __uint_as_float(0x3f800000u | (r.z >> 9));
+    const float a2 = (__uint_as_float(0x3f800000u | (r.y >> 9)) - 1.5f) * 6.283185307f;   // [-pi, pi)
+    const float a4 = (__uint_as_float(0x3f800000u | (r.w >> 9)) - 1.5f) * 6.283185307f;
+    float l1, l3, r1, r3, s2, c2, s4, c4;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(u1));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l3) : "f"(u3));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(l1 * -1.3862943611198906f));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r3) : "f"(l3 * -1.3862943611198906f));
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s2) : "f"(a2));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c2) : "f"(a2));
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s4) : "f"(a4));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c4) : "f"(a4));
     out[0] = r1 * c2;
     out[1] = r1 * s2;
     out[2] = r3 * c4;

@@ -51,9 +51,11 @@ struct ctk_handle {
   OdeHot ode_hot{};
   bool ode_kernel = false;     // MPPI + ODE predictor + intermediate_steps == 1 + few inducing points
   int ode_ilp = 2, ode_period_t = 0, ode_grid = 0, ode_block = 0;
+  unsigned long long* d_trace = nullptr;  // optional per-block phase timeline of the last ODE-kernel launch
   size_t ode_smem = 0;
   // fused tick finish / cross-GPU exchange (MppiFuse)
-  unsigned int* d_ticket = nullptr;
+  unsigned long long* d_tagged = nullptr;         // [num_sms][2 + n_ind] tagged block records
+  unsigned int lseq = 0;
   unsigned long long* d_mbox = nullptr;           // local mailbox [2][CTK_MAX_PEERS][2 + n_ind]
   unsigned long long* mbox_peer[CTK_MAX_PEERS] = {nullptr};
   bool mbox_ipc[CTK_MAX_PEERS] = {false};
@@ -192,7 +194,8 @@ extern "C" int ctk_destroy(ctk_handle* h) {
   mlp_tc_free(h->mlp_tc);
   for (int r = 0; r < CTK_MAX_PEERS; ++r)
     if (h->mbox_ipc[r] && h->mbox_peer[r]) cudaIpcCloseMemHandle(h->mbox_peer[r]);
-  if (h->d_ticket) cudaFree(h->d_ticket);
+  if (h->d_tagged) cudaFree(h->d_tagged);
+  if (h->d_trace) cudaFree(h->d_trace);
   if (h->d_mbox) cudaFree(h->d_mbox);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -272,7 +275,7 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
     A(dalloc(&h->d_u_nom, (size_t)H), "u_nom");
     A(dalloc(&h->d_partials, (size_t)(h->num_sms > h->mppi_grid ? h->num_sms : h->mppi_grid) * (h->mppi_iters + 1) * (h->n_ind + 2)), "partials");
     A(dalloc(&h->d_record, (size_t)(h->n_ind + 2)), "record");
-    A(dalloc(&h->d_ticket, 1), "ticket");
+    A(dalloc(&h->d_tagged, (size_t)(h->num_sms > h->mppi_grid ? h->num_sms : h->mppi_grid) * (h->n_ind + 2)), "tagged");
     A(dalloc(&h->d_mbox, (size_t)2 * CTK_MAX_PEERS * (h->n_ind + 2)), "mailbox");
     h->mbox_peer[0] = h->d_mbox;
   } else if (cfg->optimizer == CTK_OPT_CEM) {
@@ -441,7 +444,9 @@ static void mppi_ode_geometry(ctk_handle* h) {
   if (c.predictor != CTK_PRED_ODE || h->ode_p.intermediate_steps > 1 || h->num_sms <= 0) return;
   if (getenv("CTK_K1_GENERIC")) return;
   const long long N = h->N, sms = h->num_sms;
-  int ilp = (c.logging || N <= sms * 64) ? 1 : 2;
+  // two rollouts per thread pay off once a thread runs several of them; below one full wave of single-rollout threads
+  // (<= 1024 per SM) more warps hide the step latency better than more chains per warp (measured, profiles/)
+  int ilp = (c.logging || N <= sms * 1024) ? 1 : 2;
   if (const char* e = getenv("CTK_K1_ILP")) { const int v = atoi(e); if (!c.logging && (v == 1 || v == 2)) ilp = v; }
   int maxb = mppi_ode_max_block(ilp);
   if (const char* e = getenv("CTK_K1_BLOCK")) { const int v = atoi(e) / 32 * 32; if (v >= 32 && v <= maxb) maxb = v; }
@@ -477,7 +482,9 @@ static int make_fuse(ctk_handle* h, int mode, float* u_out_dev, MppiFuse* out) {
   MppiFuse f{};
   f.mode = mode;
   f.world = 1; f.rank = 0; f.seq = 0;
-  f.ticket = h->d_ticket;
+  f.tagged = h->d_tagged;
+  if (mode != 0) { h->lseq++; if (h->lseq == 0) h->lseq = 1; }
+  f.lseq = h->lseq;
   f.record_out = h->d_record;
   f.mbox_local = h->d_mbox;
   for (int r = 0; r < CTK_MAX_PEERS; ++r) f.mbox_peer[r] = h->mbox_peer[r];
@@ -505,6 +512,7 @@ static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_
   if (h->ode_kernel) {
     MppiOdeArgs a{};
     a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
+    a.trace = h->d_trace;
     a.s0 = s_dev; a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = ns; a.k = h->ode_hot;
     a.J = h->d_J; a.partials = h->d_partials; a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
     a.fuse = fuse;
@@ -548,7 +556,7 @@ static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_
     CU(launch_mppi_combine(h->d_partials, nparts, h->n_ind, c.mppi_neg_inv_LBD, h->d_record, fin, h->stream));
     return CTK_OK;
   }
-  const size_t smem = sizeof(float) * ((size_t)((h->H + 1) & ~1) + 2 * h->period + 32 + 32 * (h->n_ind + 1) +
+  const size_t smem = sizeof(float) * ((size_t)((h->H + 1) & ~1) + 2 * h->period + 32 + 42 * (h->n_ind + 1) + 16 +
                                        (h->mppi_stash ? (size_t)h->n_ind * h->mppi_block : 0) + (size_t)h->n_ind * h->mppi_block +
                                        pred_smem_floats(h));
   h->launches++;
@@ -944,6 +952,14 @@ extern "C" int ctk_enable_kernel_timing(ctk_handle* h, int on) {
   REQ(h, "null handle");
   h->timing = on != 0;
   h->ev_used = 0;
+  if (on) {  // create the events up front: cudaEventCreate inside a timed multi-GPU loop would skew the ranks
+    CU(cudaSetDevice(h->cfg.device));
+    while (h->ev.size() < 512) {
+      cudaEvent_t e;
+      CU(cudaEventCreate(&e));
+      h->ev.push_back(e);
+    }
+  }
   return CTK_OK;
 }
 extern "C" int ctk_get_kernel_timing(ctk_handle* h, double* ms_sum, int64_t* n) {
@@ -959,6 +975,22 @@ extern "C" int ctk_get_kernel_timing(ctk_handle* h, double* ms_sum, int64_t* n) 
   *ms_sum = tot;
   *n = (int64_t)(h->ev_used / 2);
   h->ev_used = 0;
+  return CTK_OK;
+}
+// Diagnostics: per-block globaltimer stamps of the ODE rollout kernel's phases (kernel entry, prologue done, rollouts done,
+// block reduce done, record stored, tick finished).  enable allocates the buffer; get copies [grid][8] uint64 of the last launch.
+extern "C" int ctk_debug_trace(ctk_handle* h, int enable, uint64_t* out_host, size_t n_u64, int* grid_out) {
+  REQ(h, "null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->stream));
+  const size_t n = (size_t)(h->num_sms > 0 ? h->num_sms : 148) * 8;
+  if (out_host && h->d_trace) {
+    REQ(n_u64 >= n, "trace buffer too small");
+    CU(cudaMemcpy(out_host, h->d_trace, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  }
+  if (grid_out) *grid_out = h->ode_grid;
+  if (enable && !h->d_trace) { CU(cudaMalloc((void**)&h->d_trace, n * sizeof(uint64_t))); CU(cudaMemset(h->d_trace, 0, n * sizeof(uint64_t))); }
+  if (!enable && h->d_trace) { cudaFree(h->d_trace); h->d_trace = nullptr; }
   return CTK_OK;
 }
 extern "C" int ctk_get_launch_count(ctk_handle* h, int64_t* v) { REQ(h && v, "null pointer"); *v = h->launches; return CTK_OK; }

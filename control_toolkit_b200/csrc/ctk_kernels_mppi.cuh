@@ -39,18 +39,19 @@ __device__ __forceinline__ void mppi_step(const MppiArgs& a, const CostC& cost, 
 // Tick finish inside the rollout kernel (MppiFuse): combine softmin records, exchange across GPUs, update u_nom.
 // ----------------------------------------------------------------------------------------------------------------
 // records in[cnt][P] = [rho, a, b_z[n_ind]] -> out[P] (shared memory), rescaled exactly to the common minimum.
-// GLOBAL: `in` was written by other blocks of this launch -> read through L2 (ld.cg).  All threads participate.
+// GLOBAL: `in` is the tagged (value, seq) array written by other blocks of this launch: element i is the low word of the
+// i-th 8-byte slot, read through L2 (ld.cg).  All threads participate.
 template <bool GLOBAL>
 __device__ __forceinline__ void combine_records(const float* in, int cnt, int P, float neg_inv_lbd, float* out, float* sh_red) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
   float mn = INFINITY;
-  for (int b = tid; b < cnt; b += blockDim.x) mn = fminf(mn, GLOBAL ? __ldcg(in + (size_t)b * P) : in[(size_t)b * P]);
+  for (int b = tid; b < cnt; b += blockDim.x) mn = fminf(mn, GLOBAL ? __ldcg(in + 2 * ((size_t)b * P)) : in[(size_t)b * P]);
   const float rho = block_min(mn, sh_red);
   for (int c = w; c < P - 1; c += nw) {
     float acc = 0.0f;
     for (int b = lane; b < cnt; b += 32) {
-      const float rb = GLOBAL ? __ldcg(in + (size_t)b * P) : in[(size_t)b * P];
-      const float v = GLOBAL ? __ldcg(in + (size_t)b * P + 1 + c) : in[(size_t)b * P + 1 + c];
+      const float rb = GLOBAL ? __ldcg(in + 2 * ((size_t)b * P)) : in[(size_t)b * P];
+      const float v = GLOBAL ? __ldcg(in + 2 * ((size_t)b * P + 1 + c)) : in[(size_t)b * P + 1 + c];
       const float sc = (rb < INFINITY) ? expf((rb - rho) * neg_inv_lbd) : 0.0f;
       acc = fmaf(sc, v, acc);
     }
@@ -67,52 +68,74 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-// Called by ALL threads of EVERY block after the block stored its record partials[blockIdx.x][P].  The last block to
-// arrive finishes the tick.  scratch: >= 9 * P floats of shared memory; sh_unom: the shifted nominal (prologue copy).
-__device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float* partials, int n_ind, int H, int period,
-                                                 float stdev, float lo, float hi, float neg_inv_lbd, const float* sh_unom,
-                                                 float* scratch, float* sh_red) {
-  if (f.mode == 0) return;
-  const int tid = threadIdx.x, P = n_ind + 2;
-  __shared__ int sh_last;
-  __threadfence();  // this block's record is visible device-wide before the ticket
+__device__ __forceinline__ void st_tagged(unsigned long long* dst, float v, unsigned int seq) {
+  const unsigned long long x = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(x) : "memory");
+}
+// poll an 8-byte (value, seq) slot until the sequence number matches; returns false after ~2 s (writer lost)
+__device__ __forceinline__ bool ld_tagged(const unsigned long long* src, unsigned int seq, unsigned long long t0, float* v_out) {
+  unsigned long long v;
+  int spins = 0;
+  while (true) {
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+    if ((unsigned int)(v >> 32) == seq) break;
+    if ((++spins & 1023) == 0 && globaltimer_ns() - t0 > 2000000000ull) { *v_out = 0.0f; return false; }
+  }
+  *v_out = __uint_as_float((unsigned int)(v & 0xffffffffull));
+  return true;
+}
+
+// Called by ALL threads of EVERY block once the block's record brec[P] = [rho_b, a_b, b_z[n_ind]] is complete in SHARED
+// memory (the call starts with a barrier).  mode 0: the record is stored as plain floats to partials[blockIdx.x][P] (a
+// separate combine launch follows).  mode >= 1: every value is published as ONE 8-byte (value, launch sequence number)
+// store -- no fence, no atomic, no ticket -- and block 0, the finisher, polls the grid's slots until their tags match,
+// combines them, exchanges the shard record with the peer GPUs through the same tagged-store protocol and updates
+// u_nom.  scratch: >= 9 * P floats of shared memory; sh_unom: the shifted nominal (prologue copy); big / big_floats: larger
+// shared scratch -- when the grid's records fit they are staged there by the polling pass itself.
+__device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float* brec, float* partials, int n_ind, int H,
+                                                 int period, float stdev, float lo, float hi, float neg_inv_lbd,
+                                                 const float* sh_unom, float* scratch, float* sh_red, float* big = nullptr,
+                                                 int big_floats = 0) {
+  const int tid = threadIdx.x, P = n_ind + 2, G = (int)gridDim.x;
   __syncthreads();
-  if (tid == 0) sh_last = (atomicAdd(f.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
-  __syncthreads();
-  if (!sh_last) return;
-  if (tid == 0) *f.ticket = 0u;  // re-arm for the next launch (stream order makes this visible)
-  __threadfence();
+  if (f.mode == 0) {
+    for (int c = tid; c < P; c += blockDim.x) partials[(size_t)blockIdx.x * P + c] = brec[c];
+    return;
+  }
+  for (int c = tid; c < P; c += blockDim.x) st_tagged(f.tagged + (size_t)blockIdx.x * P + c, brec[c], f.lseq);
+  if (blockIdx.x != 0) return;
   float* sh_rec = scratch;      // [P]
   float* sh_all = scratch + P;  // [world][P]
-  combine_records<true>(partials, (int)gridDim.x, P, neg_inv_lbd, sh_rec, sh_red);
+  int status = 0;
+  const unsigned long long t0 = globaltimer_ns();
+  if (G * P <= big_floats) {
+    for (int i = tid; i < G * P; i += blockDim.x)
+      if (!ld_tagged(f.tagged + i, f.lseq, t0, big + i)) status = 2;
+    __syncthreads();
+    combine_records<false>(big, G, P, neg_inv_lbd, sh_rec, sh_red);
+  } else {  // records do not fit in shared memory: wait for all of them, then combine from global memory (low words)
+    float dummy;
+    for (int i = tid; i < G * P; i += blockDim.x)
+      if (!ld_tagged(f.tagged + i, f.lseq, t0, &dummy)) status = 2;
+    __syncthreads();
+    combine_records<true>(reinterpret_cast<const float*>(f.tagged), G, P, neg_inv_lbd, sh_rec, sh_red);
+  }
   if (f.record_out != nullptr)
     for (int c = tid; c < P; c += blockDim.x) f.record_out[c] = sh_rec[c];
   if (f.mode < 2) return;
-  int status = 0;
   if (f.world > 1) {
-    // one 8-byte store per value: (float bits, seq).  The reader polls until the sequence number matches, so no
-    // fence / flag round trip is needed; double-buffered by seq parity (a rank can be at most one tick ahead).
+    // double-buffered by seq parity: a rank can be at most one tick ahead of its slowest peer
     const size_t base = (size_t)(f.seq & 1u) * f.world * P;
     for (int i = tid; i < f.world * P; i += blockDim.x) {
       const int r = i / P, c = i - r * P;
-      const unsigned long long v = ((unsigned long long)f.seq << 32) | (unsigned long long)__float_as_uint(sh_rec[c]);
-      unsigned long long* dst = f.mbox_peer[r] + base + (size_t)f.rank * P + c;
-      asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
+      st_tagged(f.mbox_peer[r] + base + (size_t)f.rank * P + c, sh_rec[c], f.seq);
     }
-    const unsigned long long t0 = globaltimer_ns();
-    for (int i = tid; i < f.world * P; i += blockDim.x) {
-      const unsigned long long* src = f.mbox_local + base + i;
-      unsigned long long v;
-      int spins = 0;
-      while (true) {
-        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
-        if ((unsigned int)(v >> 32) == f.seq) break;
-        if ((++spins & 1023) == 0 && globaltimer_ns() - t0 > 2000000000ull) { status = 1; break; }  // 2 s: peer lost
-      }
-      sh_all[i] = __uint_as_float((unsigned int)(v & 0xffffffffull));
-    }
+    for (int i = tid; i < f.world * P; i += blockDim.x)
+      if (!ld_tagged(f.mbox_local + base + i, f.seq, t0, sh_all + i)) status = 1;
     status = __syncthreads_or(status);
     combine_records<false>(sh_all, f.world, P, neg_inv_lbd, sh_rec, sh_red);
+  } else {
+    status = __syncthreads_or(status);
   }
   // optimizer_mppi.py:190-191: u_nom <- clip(shift(u_nom) + interp(sum_n w_n z_n) * stdev / sum_n w_n)
   const float a = sh_rec[1];
@@ -141,8 +164,8 @@ __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const M
   float* sh_unom = smem;                 // [H] shifted nominal
   float2* sh_w = reinterpret_cast<float2*>(smem + ((a.H + 1) & ~1));  // [period] interpolation weights (w0, w1)
   float* sh_red = reinterpret_cast<float*>(sh_w + a.period);          // [32] reduction scratch
-  float* sh_part = sh_red + 32;          // [32][n_ind + 1]
-  float* sh_z = sh_part + 32 * (a.n_ind + 1);  // [n_ind][blockDim] stash of this rollout's standard draws (if a.stash)
+  float* sh_part = sh_red + 32;          // [32][n_ind + 1] per-warp partial sums | block record | finish scratch
+  float* sh_z = sh_part + 42 * (a.n_ind + 1) + 16;  // [n_ind][blockDim] stash of this rollout's standard draws (if a.stash)
   float* sh_acc = sh_z + (a.stash ? (size_t)a.n_ind * blockDim.x : 0);  // [n_ind][blockDim] per-thread sum_n e_n z_n,i
   float* sh_pred = sh_acc + (size_t)a.n_ind * blockDim.x;
 
@@ -273,15 +296,16 @@ __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const M
     if (lane == 0) sh_part[w * P + 1 + i] = ws;
   }
   __syncthreads();
-  float* out = a.partials + (size_t)blockIdx.x * (P + 1);
+  float* brec = sh_part + 32 * P;  // [P + 1] block record, behind the per-warp partial sums
   for (int c = tid; c < P; c += blockDim.x) {
     float s = 0.0f;
     for (int ww = 0; ww < nw; ++ww) s += sh_part[ww * P + c];
-    out[1 + c] = s;
+    brec[1 + c] = s;
   }
-  if (tid == 0) out[0] = rho_b;
-  // fused K2 (+ cross-GPU exchange): the last block to retire finishes the tick
-  mppi_tick_finish(a.fuse, a.partials, a.n_ind, a.H, a.period, a.stdev, a.lo, a.hi, a.neg_inv_lbd, sh_unom, sh_part, sh_red);
+  if (tid == 0) brec[0] = rho_b;
+  // fused K2 (+ cross-GPU exchange): block 0 finishes the tick
+  mppi_tick_finish(a.fuse, brec, a.partials, a.n_ind, a.H, a.period, a.stdev, a.lo, a.hi, a.neg_inv_lbd, sh_unom, brec + P + 1,
+                   sh_red, sh_z, (int)((a.stash ? (size_t)a.n_ind * blockDim.x : 0) + (size_t)a.n_ind * blockDim.x));
 }
 
 __global__ void __launch_bounds__(1024) mppi_combine_kernel(const float* __restrict__ in, int cnt, int n_ind,

@@ -105,10 +105,14 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
   float* sh_unom = smem;                                   // [H] shifted nominal (+ pad)
   float* sh_w = smem + ((a.H + 3) & ~3);                   // [period] j/period (runtime-period path)
   float* sh_red = sh_w + ((period + 3) & ~3);              // [32]
-  float* sh_part = sh_red + 32;                            // [32][P]  (also the finish scratch)
-  float* sh_z = sh_part + 32 * P;                          // [n_ind][ILP*T] standard draws of the rollouts in flight
-  float* sh_acc = sh_z + (size_t)a.n_ind * ILP * T_;       // [n_ind][T] per-thread sum_n e_n z_n,i
+  float* sh_part = sh_red + 32;                            // [12][P + 1]: block record + finish scratch
+  float* sh_z = sh_part + 12 * (P + 1);                          // [n_ind][ILP*T] standard draws of the rollouts in flight
+  float* sh_acc = sh_z + (size_t)max(a.n_ind * ILP, 2) * T_;  // [n_ind][T] per-thread sum_n e_n z_n,i
 
+  auto trace = [&](int slot) {  // optional per-block timeline (bench.py --trace): globaltimer at the phase boundaries
+    if (a.trace != nullptr && tid == 0) a.trace[(size_t)blockIdx.x * 8 + slot] = globaltimer_ns();
+  };
+  trace(0);
   // ---- prologue: the only global reads before the loop, issued together ----
   const float s0v = (tid < 6) ? a.s0[tid] : 0.0f;
   const float upv = a.u_prev[0];
@@ -122,6 +126,7 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
   const float omc0 = 1.0f - cosf(th0);  // spec: E_pot uses cos(angle) of the measured state
   const float T0 = th0 * kInvSqrt2, W0 = om0 * k.beta, V0 = v0 * k.cFg;
   __syncthreads();  // sh_red is reused below
+  trace(1);
 
   // closed form of sum_j du_j^2 over a full segment: cnt y0^2 + dy (2 W1 y0 + W2 dy)
   const float pf = (float)period;
@@ -227,26 +232,35 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
     }
   }
 
-  // ---- one block softmin record [rho_b, a_b, b_z[n_ind]] ----
+  // ---- one block softmin record [rho_b, a_b, b_z[n_ind]]: column c is summed by warp c straight from shared memory ----
+  trace(2);
   const float rho_b = block_min(rho_t, sh_red);
-  const float sc = (rho_t < INFINITY) ? expf((rho_t - rho_b) * k.neg_inv_lbd) : 0.0f;
+  trace(3);
+  float* sh_sc = sh_z;        // the draws stash is free now: [T] rescale factors, [T] rescaled a_t
+  float* sh_at = sh_z + T_;
   {
-    const float ws = warp_sum(a_t * sc);
-    if (lane == 0) sh_part[w * P] = ws;
-  }
-  for (int i = 0; i < a.n_ind; ++i) {
-    const float ws = warp_sum(sa[(size_t)i * T_] * sc);
-    if (lane == 0) sh_part[w * P + 1 + i] = ws;
+    const float sc = (rho_t < INFINITY) ? expf((rho_t - rho_b) * k.neg_inv_lbd) : 0.0f;
+    sh_sc[tid] = sc;
+    sh_at[tid] = a_t * sc;
   }
   __syncthreads();
-  float* out = a.partials + (size_t)blockIdx.x * (P + 1);
-  for (int c = tid; c < P; c += T_) {
-    float s = 0.0f;
-    for (int ww = 0; ww < nw; ++ww) s += sh_part[ww * P + c];
-    out[1 + c] = s;
+  float* brec = sh_part;  // [P + 1]
+  for (int c = w; c < P; c += nw) {
+    float acc = 0.0f;
+    if (c == 0) {
+      for (int t = lane; t < T_; t += 32) acc += sh_at[t];
+    } else {
+      const float* col = sh_acc + (size_t)(c - 1) * T_;
+      for (int t = lane; t < T_; t += 32) acc = fmaf(col[t], sh_sc[t], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) brec[1 + c] = acc;
   }
-  if (tid == 0) out[0] = rho_b;
-  mppi_tick_finish(a.fuse, a.partials, a.n_ind, a.H, period, k.stdev, k.lo, k.hi, k.neg_inv_lbd, sh_unom, sh_part, sh_red);
+  if (tid == 0) brec[0] = rho_b;
+  trace(4);
+  mppi_tick_finish(a.fuse, brec, a.partials, a.n_ind, a.H, period, k.stdev, k.lo, k.hi, k.neg_inv_lbd, sh_unom, brec + P + 1, sh_red, sh_z,
+                   (int)((size_t)max(a.n_ind * ILP, 2) * T_ + (size_t)a.n_ind * T_));
+  trace(5);
 }
 
 }  // namespace ctk

@@ -192,6 +192,8 @@ int ctk_get_launch_count(ctk_handle *h, int64_t *value);
    summed duration and the number of timed launches since enable().                                                */
 int ctk_enable_kernel_timing(ctk_handle *h, int on);
 int ctk_get_kernel_timing(ctk_handle *h, double *ms_sum, int64_t *n_launches);
+/* diagnostics: per-block phase timeline (globaltimer ns) of the last MPPI/ODE rollout-kernel launch, [grid][8] uint64   */
+int ctk_debug_trace(ctk_handle *h, int enable, uint64_t *out_host, size_t n_u64, int *grid_out);
 /* standalone nominal rollout of one control sequence (reference optimizer_mppi.py:199-202 predict_optimal_trajectory,
    optimizer_rpgd.py:382-386): s_host [ns], Q_host [H] -> traj_host [H+1, ns], summed stage cost (may be NULL).     */
 int ctk_rollout_single(ctk_handle *h, const float *s_host, const float *Q_host, float *traj_host, float *summed_stage_cost);
