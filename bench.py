@@ -110,7 +110,7 @@ class ClockSampler:
                 "samples": len(self.samples), "reasons": reasons}
 
 
-def build_controller(workload, shard=None, device=0, logging=False, n_override=None):
+def build_controller(workload, shard=None, device=0, logging=False, n_override=None, mlp_engine="simt"):
     import control_toolkit_b200 as ctk
     from control_toolkit_b200.Controllers.controller_mpc import controller_mpc
     opt_name, pred, cost, N, H = WORKLOADS[workload]
@@ -118,6 +118,8 @@ def build_controller(workload, shard=None, device=0, logging=False, n_override=N
     if pred.startswith("Dense"):
         ctk.register_mlp(pred, ctk.MLPSpec.random_init(2))
     cfg = dict(MPPI_CFG, mpc_horizon=H, num_rollouts=N, shard=shard, device_index=device)
+    if pred.startswith("Dense"):
+        cfg["mlp_engine"] = mlp_engine
     ctrl = controller_mpc("CartPole", (np.array([-1.0], np.float32), np.array([1.0], np.float32)),
                           {"target_position": 0.0, "target_equilibrium": 1.0},
                           config_controller=dict(optimizer=opt_name, predictor_specification=pred, cost_function_specification=cost,
@@ -192,7 +194,8 @@ def run_ours(args):
     dev = f"cuda:{local_rank}"
     lib = L.load()
     plan = ShardPlan(rank, world)
-    ctrl, N, H = build_controller(args.workload, shard=plan if world > 1 else None, device=local_rank, n_override=args.rollouts)
+    ctrl, N, H = build_controller(args.workload, shard=plan if world > 1 else None, device=local_rank, n_override=args.rollouts,
+                                  mlp_engine=args.mlp_engine)
     opt = ctrl.optimizer
     plan.attach(opt, lib)  # handle runs on torch's current stream (events + NCCL ordering)
     K, W = args.steps, args.warmup
@@ -265,19 +268,34 @@ def run_ours(args):
         # ---- roofline of the dominant kernel (K1 fused rollout), measured live above ----
         k1_ms = ms_sum.value / max(n_k.value, 1)
         n_local = opt._n_local
-        flop = FLOP_PER_ROLLOUT_STEP["mppi_ode"] * n_local * H
-        peak, clk = C.c_double(), C.c_double()
-        L.check(lib.ctk_fp32_peak(local_rank, C.byref(peak), C.byref(clk)))
-        achieved = flop / (k1_ms * 1e-3) / 1e12
-        roofline = {"bound": "fp32", "kernel": "mppi_ode_kernel (fused sample+rollout+cost+softmin+exchange+update, the whole tick)", "achieved": achieved, "peak": peak.value,
-                    "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None, "traffic": None,
-                    "peak_source": "measured live: FP32 FMA-chain microbenchmark (ctk_fp32_peak), implied FFMA clock %.0f MHz; "
-                                   "theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5" % clk.value,
-                    "flop_per_rollout_step": FLOP_PER_ROLLOUT_STEP["mppi_ode"], "kernel_ms": k1_ms,
-                    "kernel_share_of_tick": k1_ms / ms_per_step,
-                    "hbm": {"algorithmic_bytes_per_launch": 4.0 * n_local, "achieved_gbs": 4.0 * n_local / (k1_ms * 1e-3) / 1e9,
-                            "peak_gbs": json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"]
-                            if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else 6650.0}}
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(REPO, "MEASURED_PEAKS.json")) else {}
+        is_mlp = WORKLOADS[args.workload][1].startswith("Dense")
+        if is_mlp:
+            # dense contraction: 2*(6*128 + 128*128 + 128*5) FLOP per rollout-step; the 128x128 layer (92 %) runs on the
+            # tensor cores as six bf16 products (3-term split operands) when mlp_engine == tcgen05
+            fl_step = 35584.0
+            flop = fl_step * n_local * H
+            achieved = flop / (k1_ms * 1e-3) / 1e12
+            tpeak = float(peaks.get("bf16_tflops", 1648.0))
+            roofline = {"bound": "tensor", "kernel": f"mppi_rollout_kernel<{'MlpTcPred' if args.mlp_engine == 'tcgen05' else 'MlpSimtPred'}>",
+                        "achieved": achieved, "peak": tpeak, "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": None,
+                        "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, cuBLAS 8192^3)" if peaks else "fallback 1648",
+                        "flop_per_rollout_step": fl_step, "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms / ms_per_step,
+                        "tensor_flop_issued_per_algorithmic": 6.0 * 32768.0 / fl_step if args.mlp_engine == "tcgen05" else 0.0}
+        else:
+            flop = FLOP_PER_ROLLOUT_STEP["mppi_ode"] * n_local * H
+            peak, clk = C.c_double(), C.c_double()
+            L.check(lib.ctk_fp32_peak(local_rank, C.byref(peak), C.byref(clk)))
+            achieved = flop / (k1_ms * 1e-3) / 1e12
+            roofline = {"bound": "fp32", "kernel": "mppi_ode_kernel (fused sample+rollout+cost+softmin+exchange+update, the whole tick)",
+                        "achieved": achieved, "peak": peak.value,
+                        "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None, "traffic": None,
+                        "peak_source": "measured live: FP32 FMA-chain microbenchmark (ctk_fp32_peak), implied FFMA clock %.0f MHz; "
+                                       "theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5" % clk.value,
+                        "flop_per_rollout_step": FLOP_PER_ROLLOUT_STEP["mppi_ode"], "kernel_ms": k1_ms,
+                        "kernel_share_of_tick": k1_ms / ms_per_step,
+                        "hbm": {"algorithmic_bytes_per_launch": 4.0 * n_local, "achieved_gbs": 4.0 * n_local / (k1_ms * 1e-3) / 1e9,
+                                "peak_gbs": peaks.get("hbm_gbs", 6650.0)}}
         # ---- CPU baseline: oracle port on a bounded sample of the same workload ----
         n_sample = min(N, args.cpu_sample)
         rate, sec, threads = cpu_mppi_rate(args.workload, n_sample, 2, 1)
@@ -289,6 +307,7 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": args.workload, "optimizer": "mppi", "num_rollouts": N, "mpc_horizon": H,
                            "predictor": WORKLOADS[args.workload][1], "cost": "default", "noise": "in-kernel Philox4x32-10",
+                           **({"mlp_engine": args.mlp_engine} if WORKLOADS[args.workload][1].startswith("Dense") else {}),
                            "parallelism": f"rollouts sharded over {world} GPU(s); exchange per tick: {getattr(opt, '_exchange', 'none')} "
                                           f"({'in-kernel NVLink mailbox stores, ' if getattr(opt, '_exchange', '') == 'p2p' else ''}{H // 10 + 3} floats per shard)",
                            "l2": "flushed between timed ticks (256 MiB memset); inputs are 24 B per tick"},
@@ -310,6 +329,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mppi_ode_1m", choices=sorted(WORKLOADS))
     ap.add_argument("--rollouts", type=int, default=None, help="override the global rollout count")
+    ap.add_argument("--mlp-engine", default="tcgen05", choices=["simt", "tcgen05"], help="MLP predictor engine (mppi_mlp_c4 workload)")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="rollouts per CPU-baseline tick (bounded sample)")
     args = ap.parse_args()
     if args.impl == "reference":

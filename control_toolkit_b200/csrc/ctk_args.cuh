@@ -23,6 +23,7 @@ struct MlpDev {
   int hidden;              // <= 128, multiple of 16
   const float* blob;       // device: W1[6][hid] | b1[hid] | W2[hid][hid] | b2[hid] | W3T[5][hid] | b3[8]
   int blob_floats;
+  const void* tc_blob;     // device: tcgen05 engine blob (ctk_mlp_tc.cuh: W2 bf16 split tiles | W1 | b1 | b2 | W3T | b3) or null
 };
 
 CTK_HD int mlp_blob_floats(int hid) { return 6 * hid + hid + hid * hid + hid + 5 * hid + 8; }

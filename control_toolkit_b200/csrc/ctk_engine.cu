@@ -86,7 +86,7 @@ struct ctk_handle {
   size_t inj_cap = 0, inj_size = 0, inj_pos = 0;
   // mlp
   float* d_mlp = nullptr;
-  MlpTcDev mlp_tc{};
+  void* d_mlp_tc = nullptr;  // tcgen05 engine blob (ctk_mlp_tc.cuh)
   // counters
   int64_t count = 0, adam_step = 0, tick = 0, launches = 0;
   bool was_reset = false;
@@ -128,6 +128,7 @@ static cudaError_t dalloc(T** p, size_t n) {
 }
 
 static void mppi_ode_geometry(ctk_handle* h);
+static int pred_id(const ctk_handle* h);
 static cudaError_t upload_consts(ctk_handle* h) {
   if (h->cfg.optimizer == CTK_OPT_MPPI) {
     const ctk_config& c = h->cfg;
@@ -191,7 +192,7 @@ extern "C" int ctk_destroy(ctk_handle* h) {
   if (h->d_keys[1]) cudaFree(h->d_keys[1]);
   if (h->d_elite_idx) cudaFree(h->d_elite_idx);
   if (h->d_best_idx) cudaFree(h->d_best_idx);
-  mlp_tc_free(h->mlp_tc);
+  if (h->d_mlp_tc) cudaFree(h->d_mlp_tc);
   for (int r = 0; r < CTK_MAX_PEERS; ++r)
     if (h->mbox_ipc[r] && h->mbox_peer[r]) cudaIpcCloseMemHandle(h->mbox_peer[r]);
   if (h->d_tagged) cudaFree(h->d_tagged);
@@ -227,7 +228,7 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
   derive_ode(*ode, h->ode);
   derive_fwd(*ode, h->fwd);
   derive_cost(*cost, h->H, h->cost);
-  h->mlp = MlpDev{0, nullptr, 0};
+  h->mlp = MlpDev{0, nullptr, 0, nullptr};
   h->nblocks = (h->N + 127) / 128;
   const int N = h->N, H = h->H;
   int rc = CTK_OK;
@@ -254,7 +255,7 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
     cudaDeviceProp prop;
     A(cudaGetDeviceProperties(&prop, cfg->device), "props");
     h->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
-    const int maxb = mppi_max_block_threads(cfg->predictor == CTK_PRED_ODE ? 0 : 1);
+    const int maxb = mppi_max_block_threads(pred_id(h));
     const long long slots = (long long)h->num_sms * maxb;
     const int r = (int)((N + slots - 1) / slots);                                  // rollouts per thread
     int T = (int)(((((long long)N + (long long)r * h->num_sms - 1) / ((long long)r * h->num_sms)) + 31) / 32 * 32);
@@ -349,10 +350,39 @@ extern "C" int ctk_set_mlp_weights(ctk_handle* h, const ctk_mlp_weights* w) {
   if (h->d_mlp) { cudaFree(h->d_mlp); h->d_mlp = nullptr; }
   CU(dalloc(&h->d_mlp, (size_t)nf));
   CU(cudaMemcpy(h->d_mlp, blob.data(), sizeof(float) * nf, cudaMemcpyHostToDevice));
-  h->mlp = MlpDev{hid, h->d_mlp, nf};
+  h->mlp = MlpDev{hid, h->d_mlp, nf, nullptr};
   if (h->cfg.mlp_engine == CTK_MLP_TCGEN05) {
-    std::string err;
-    if (!mlp_tc_upload(h->mlp_tc, w, err)) return fail(CTK_ECUDA, "mlp_tc_upload: " + err);
+    REQ(hid == kTcHidden, "the tcgen05 MLP engine is built for hidden == 128 (use mlp_engine=simt otherwise)");
+    REQ(h->cfg.optimizer == CTK_OPT_MPPI, "the tcgen05 MLP engine is implemented for MPPI (use mlp_engine=simt for CEM)");
+    // W2 as three bf16 terms (w = w1 + w2 + w3, round-to-nearest-even each), B operand tiles: row n = output unit, k = input unit
+    std::vector<uint8_t> tc(kTcBlobBytes, 0);
+    auto bf16_rn = [](float f) -> uint16_t {
+      uint32_t x; memcpy(&x, &f, 4);
+      if ((x & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((x >> 16) | 0x40);  // NaN
+      x += 0x7fffu + ((x >> 16) & 1u);
+      return (uint16_t)(x >> 16);
+    };
+    auto bf16_f = [](uint16_t u) -> float { uint32_t x = (uint32_t)u << 16; float f; memcpy(&f, &x, 4); return f; };
+    for (int k = 0; k < 128; ++k)
+      for (int n = 0; n < 128; ++n) {
+        const float wv = w->W2[k * 128 + n];
+        const uint16_t t1 = bf16_rn(wv); const float r1 = wv - bf16_f(t1);
+        const uint16_t t2 = bf16_rn(r1); const float r2 = r1 - bf16_f(t2);
+        const uint16_t t3 = bf16_rn(r2);
+        const uint32_t off = tc_tile_offset(n, k);
+        memcpy(&tc[0 * kTcTileBytes + off], &t1, 2); memcpy(&tc[1 * kTcTileBytes + off], &t2, 2); memcpy(&tc[2 * kTcTileBytes + off], &t3, 2);
+      }
+    float* f = reinterpret_cast<float*>(tc.data() + 3 * kTcTileBytes);
+    memcpy(f, w->W1, sizeof(float) * 6 * 128); f += 6 * 128;
+    memcpy(f, w->b1, sizeof(float) * 128); f += 128;
+    memcpy(f, w->b2, sizeof(float) * 128); f += 128;
+    for (int k = 0; k < 5; ++k) for (int j = 0; j < 128; ++j) f[k * 128 + j] = w->W3[j * 5 + k];
+    f += 5 * 128;
+    memcpy(f, w->b3, sizeof(float) * 5);
+    if (h->d_mlp_tc) { cudaFree(h->d_mlp_tc); h->d_mlp_tc = nullptr; }
+    CU(cudaMalloc(&h->d_mlp_tc, kTcBlobBytes));
+    CU(cudaMemcpy(h->d_mlp_tc, tc.data(), kTcBlobBytes, cudaMemcpyHostToDevice));
+    h->mlp.tc_blob = h->d_mlp_tc;
   }
   return CTK_OK;
 }
@@ -434,7 +464,11 @@ extern "C" int ctk_reset(ctk_handle* h) {
 // ---------------------------------------------------------------------------------------------------------------
 // the tick
 // ---------------------------------------------------------------------------------------------------------------
-static size_t pred_smem_floats(ctk_handle* h) { return mppi_pred_smem_floats(h->cfg.predictor == CTK_PRED_MLP ? 1 : 0, h->mlp); }
+static int pred_id(const ctk_handle* h) {  // 0 ODE, 1 MLP on the FP32 pipe, 2 MLP with the dense layer on tcgen05
+  if (h->cfg.predictor != CTK_PRED_MLP) return 0;
+  return (h->cfg.mlp_engine == CTK_MLP_TCGEN05 && h->cfg.optimizer == CTK_OPT_MPPI) ? 2 : 1;
+}
+static size_t pred_smem_floats(ctk_handle* h) { return mppi_pred_smem_floats(pred_id(h), h->mlp); }
 
 // Launch geometry of the ODE kernel: one CTA per SM, block sized so that every thread runs the same number of
 // rollout groups (no partially filled last wave); the iteration count with the least padding wins.
@@ -505,10 +539,9 @@ static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_
   int rcn = make_noise(h, STREAM_MPPI, h->n_ind, 0, (size_t)h->NG, &ns);
   if (rcn != CTK_OK) return rcn;
   const ctk_config& c = h->cfg;
-  const bool tc = (c.predictor == CTK_PRED_MLP && c.mlp_engine == CTK_MLP_TCGEN05);
   const bool log = c.logging != 0;
   MppiFuse fuse{};
-  make_fuse(h, tc ? 0 : mode, u_out_dev, &fuse);
+  make_fuse(h, mode, u_out_dev, &fuse);
   if (h->ode_kernel) {
     MppiOdeArgs a{};
     a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
@@ -541,27 +574,13 @@ static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_
   a.J = h->d_J; a.partials = h->d_partials;
   a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
   a.fuse = fuse;
-  if (tc) {
-    if (mode == 2 && h->xworld > 1) return fail(CTK_EINVAL, "the tcgen05 MLP engine uses the staged exchange (ctk_step_local / ctk_step_finish)");
-    int nparts = h->mppi_grid;
-    std::string err;
-    if (!mlp_tc_launch_mppi(h->mlp_tc, a, h->cost.kind, log, h->stream, &nparts, &h->launches, err))
-      return fail(CTK_ECUDA, "mlp tcgen05 launch: " + err);
-    MppiFinalize fin{};
-    fin.enable = (mode == 2) ? 1 : 0;
-    fin.H = h->H; fin.period = h->period; fin.n_ind = h->n_ind; fin.stdev = c.mppi_stdev; fin.lo = c.action_low; fin.hi = c.action_high;
-    fin.neg_inv_lbd = c.mppi_neg_inv_LBD; fin.u_nom = h->d_u_nom; fin.u_prev = h->d_u_prev; fin.u_out = u_out_dev;
-    fin.freeze_prev = c.freeze_previous_input;
-    h->launches++;
-    CU(launch_mppi_combine(h->d_partials, nparts, h->n_ind, c.mppi_neg_inv_LBD, h->d_record, fin, h->stream));
-    return CTK_OK;
-  }
   const size_t smem = sizeof(float) * ((size_t)((h->H + 1) & ~1) + 2 * h->period + 32 + 42 * (h->n_ind + 1) + 16 +
                                        (h->mppi_stash ? (size_t)h->n_ind * h->mppi_block : 0) + (size_t)h->n_ind * h->mppi_block +
                                        pred_smem_floats(h));
   h->launches++;
   KernelTimer kt(h);
-  cudaError_t e = launch_mppi_rollout(c.predictor == CTK_PRED_ODE ? 0 : 1, h->cost.kind, log, h->mppi_grid, h->mppi_block, smem,
+  if (pred_id(h) == 2 && h->mlp.tc_blob == nullptr) return fail(CTK_ESTATE, "tcgen05 MLP engine without weights");
+  cudaError_t e = launch_mppi_rollout(pred_id(h), h->cost.kind, log, h->mppi_grid, h->mppi_block, smem,
                                       h->stream, a);
   if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("mppi_rollout_kernel: ") + cudaGetErrorString(e));
   return CTK_OK;

@@ -1,25 +1,202 @@
-// ctk_mlp_tc.cuh -- tcgen05 (UMMA + TMEM) engine for the MLP predictor.  Placeholder interface; the kernel lands in
-// a later commit.  Until then selecting CTK_MLP_TCGEN05 fails loudly (no silent fallback to the SIMT engine).
+// ctk_mlp_tc.cuh -- tcgen05 (UMMA + TMEM) engine of the MLP predictor (6 -> 128 tanh -> 128 tanh -> 5, config C4).
+// Replaces PredictorWrapper.predict_core for the neural predictor (reference call sites optimizer_mppi.py:188,
+// optimizer_cem_tf.py:57).  Drop-in `Pred` of the generic rollout kernels (ctk_kernels_mppi.cuh): one CTA = 128
+// rollouts = the M dimension of the MMA, thread r owns rollout (row) r for everything that is not the dense layer.
+//
+//   layer 1 (6 -> 128, 4 % of the FLOPs)  : FP32 FMAs per thread, weights broadcast from shared memory; tanh; the row of h1
+//                                            is split into THREE bf16 terms (h = a1 + a2 + a3, 24 mantissa bits) and stored
+//                                            as three K-major operand tiles in the canonical no-swizzle core-matrix layout;
+//   layer 2 (128 -> 128, 92 % of the FLOPs): D[128x128] (fp32, TMEM) = sum of the six significant products of the bf16
+//                                            splits of h1 and W2 (a3 w1, a2 w2, a1 w3, a2 w1, a1 w2, a1 w1; smallest first):
+//                                            48 tcgen05.mma.kind::f16 (M128 N128 K16) issued by one thread, completion by
+//                                            tcgen05.commit -> mbarrier;  error vs an exact product ~2e-7 (tools/lab/umma_lab.cu);
+//   layer 3 (128 -> 5)                     : each thread reads its accumulator row back with tcgen05.ld (32 columns at a
+//                                            time), applies bias + tanh and folds the 5 outputs with FP32 FMAs.
+// bf16 x 3 instead of TF32 x 3: same tensor time (6 products at twice the rate), but the operand tiles are half the size,
+// which is what lets A (96 KB) and W2 (96 KB) both live in shared memory.
 #pragma once
-#include <string>
+#include <cuda_bf16.h>
 
-#include "../../include/ctk_b200.h"
 #include "ctk_args.cuh"
+#include "ctk_device.cuh"
+#include "ctk_predictor.cuh"
 
 namespace ctk {
 
-struct MlpTcDev {
-  void* blob = nullptr;
-};
+constexpr int kTcHidden = 128;
+constexpr uint32_t kTcTileBytes = 128 * 128 * 2;  // one bf16 operand tile [128 rows][128 k]
+constexpr uint32_t kTcKStride = 2048;             // bytes between core matrices along K  (descriptor LBO)
+constexpr uint32_t kTcMnStride = 128;             // bytes between 8-row groups along M/N (descriptor SBO)
+// byte offset of element (row, k) inside an operand tile: 8x8 core matrices of 16-byte rows
+__host__ __device__ inline uint32_t tc_tile_offset(int row, int k) { return (uint32_t)(k >> 3) * kTcKStride + (uint32_t)row * 16u + (uint32_t)(k & 7) * 2u; }
+// device blob: W2 split tiles [3][32768 B] | W1 [6][128] | b1 [128] | b2 [128] | W3T [5][128] | b3 [8]   (floats after the tiles)
+constexpr uint32_t kTcBlobFloats = 6 * 128 + 128 + 128 + 5 * 128 + 8;
+constexpr uint32_t kTcBlobBytes = 3 * kTcTileBytes + kTcBlobFloats * 4;
 
-inline void mlp_tc_free(MlpTcDev&) {}
-inline bool mlp_tc_upload(MlpTcDev&, const ctk_mlp_weights*, std::string& err) {
-  err = "tcgen05 MLP engine not built";
-  return false;
+#ifdef __CUDACC__
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
+  // SmemDescriptor (sm_100): start address, leading / stride byte offsets in 16-byte units, version 1, no swizzle
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)(kTcKStride >> 4) << 16) | ((uint64_t)(kTcMnStride >> 4) << 32) | (1ull << 46);
 }
-inline bool mlp_tc_launch_mppi(MlpTcDev&, const MppiArgs&, int, bool, cudaStream_t, int*, int64_t*, std::string& err) {
-  err = "tcgen05 MLP engine not built";
-  return false;
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+struct MlpTcPred {
+  static constexpr bool kCooperative = true;  // every thread of the CTA must call step() the same number of times
+  static constexpr int kMaxThreads = 128;
+  uint8_t* sA;        // [3][32768] activation split tiles (written per step)
+  uint8_t* sB;        // [3][32768] W2 split tiles (resident)
+  const float *W1, *b1, *b2, *W3T, *b3;
+  uint64_t* mbar;
+  uint32_t* tmem_slot;
+  uint32_t phase;
+
+  static size_t smem_floats(const MlpDev&) { return (6 * (size_t)kTcTileBytes + kTcBlobFloats * 4 + 64 + 1024) / 4; }
+
+  __device__ __forceinline__ MlpTcPred(const DevConsts*, const MlpDev& m, float* sm) {
+    uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)sm + 1023) & ~(uintptr_t)1023);
+    sA = base;
+    sB = base + 3 * kTcTileBytes;
+    float* f = reinterpret_cast<float*>(sB + 3 * kTcTileBytes);
+    W1 = f; b1 = W1 + 6 * 128; b2 = b1 + 128; W3T = b2 + 128; b3 = W3T + 5 * 128;
+    mbar = reinterpret_cast<uint64_t*>(f + kTcBlobFloats);
+    tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    phase = 0;
+    const uint4* src = reinterpret_cast<const uint4*>(m.tc_blob);
+    uint4* dst = reinterpret_cast<uint4*>(sB);
+    for (int i = threadIdx.x; i < (int)(kTcBlobBytes / 16); i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if ((threadIdx.x >> 5) == 0) {  // one warp allocates 128 TMEM columns (the fp32 accumulator) for the CTA's lifetime
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // W2 tiles were written through the generic proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    // caller issues __syncthreads() after construction
+  }
+  __device__ __forceinline__ ~MlpTcPred() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(*tmem_slot) : "memory");
+    }
+  }
+  __device__ __forceinline__ void substep(State& z, float u, float& omc) { step(z, u, omc); }
+  __device__ __forceinline__ bool single_substep() const { return false; }
+  __device__ __forceinline__ void use_uniform(const HotUK&) {}
+
+  // net input [Q, angleD, cos, sin, position, positionD] -> next [angleD, cos, sin, position, positionD];
+  // angle = atan2(sin, cos)  (oracle/spec.py MLPPredictor.step); same FP32 op order as MlpSimtPred outside layer 2
+  __device__ __noinline__ void step(State& z, float u, float& omc) {
+    const int tid = threadIdx.x;
+    const float x[6] = {u, z.om, z.c, z.s, z.x, z.v};
+    // ---- layer 1 + tanh + 3-term bf16 split -> operand tiles ----
+    uint8_t* arow = sA + (size_t)tid * 16;
+#pragma unroll 2
+    for (int kg = 0; kg < 16; ++kg) {
+      float h[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = kg * 8 + jj;
+        float acc = 0.0f;  // torch: (x @ W1) + b1 -> accumulate the dot product first, then add the bias
+#pragma unroll
+        for (int i = 0; i < 6; ++i) acc = fmaf(x[i], W1[i * 128 + j], acc);
+        h[jj] = tanh_acc(acc + b1[j]);
+      }
+      uint32_t p1[4], p2[4], p3[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float a0 = h[2 * q], a1 = h[2 * q + 1];
+        const float a0_1 = __bfloat162float(__float2bfloat16_rn(a0)), a1_1 = __bfloat162float(__float2bfloat16_rn(a1));
+        const float r0 = a0 - a0_1, r1 = a1 - a1_1;  // exact
+        const float a0_2 = __bfloat162float(__float2bfloat16_rn(r0)), a1_2 = __bfloat162float(__float2bfloat16_rn(r1));
+        p1[q] = pack_bf16x2(a0_1, a1_1);
+        p2[q] = pack_bf16x2(a0_2, a1_2);
+        p3[q] = pack_bf16x2(r0 - a0_2, r1 - a1_2);
+      }
+      uint8_t* dst = arow + (size_t)kg * kTcKStride;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+      *reinterpret_cast<uint4*>(dst + kTcTileBytes) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+      *reinterpret_cast<uint4*>(dst + 2 * kTcTileBytes) = make_uint4(p3[0], p3[1], p3[2], p3[3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // operand tiles -> visible to the tensor core (async proxy)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    const uint32_t tmem = *tmem_slot;
+    // ---- layer 2 on the tensor core: one thread issues 6 x 8 MMAs (M128 N128 K16, bf16 -> fp32 in TMEM) ----
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // instruction descriptor: D fp32, A/B bf16, both K-major, N = 128, M = 128
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+      uint32_t acc = 0;
+#pragma unroll
+      for (int term = 0; term < 6; ++term) {  // smallest products first: (a3 w1) (a2 w2) (a1 w3) (a2 w1) (a1 w2) (a1 w1)
+        constexpr int ta[6] = {2, 1, 0, 1, 0, 0}, tb[6] = {0, 1, 2, 0, 1, 0};
+        const uint32_t ab = a0 + ta[term] * kTcTileBytes, bb = b0 + tb[term] * kTcTileBytes;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          umma_bf16(tmem, umma_smem_desc(ab + ks * 2 * kTcKStride), umma_smem_desc(bb + ks * 2 * kTcKStride), idesc, acc);
+          acc = 1;
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+    }
+    {
+      uint32_t done = 0;
+      const uint32_t bar = smem_u32(mbar);
+      while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+      }
+      phase ^= 1u;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- accumulator row -> bias + tanh -> layer 3 ----
+    float y[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    const uint32_t trow = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t v[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
+          "%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+            "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+            "=r"(v[30]), "=r"(v[31])
+          : "r"(trow + c0));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) {
+        const int j = c0 + jj;
+        const float h2 = tanh_acc(__uint_as_float(v[jj]) + b2[j]);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) y[k] = fmaf(h2, W3T[k * 128 + j], y[k]);
+      }
+    }
+    z.om = y[0] + b3[0];
+    z.c = y[1] + b3[1];
+    z.s = y[2] + b3[2];
+    z.x = y[3] + b3[3];
+    z.v = y[4] + b3[4];
+    z.th = atan2f(z.s, z.c);
+    // the network's (cos, sin) outputs are not normalised: cos(atan2(s, c)) = c / hypot(s, c)
+    omc = 1.0f - z.c * rsqrtf(fmaf(z.c, z.c, z.s * z.s));
+  }
+};
+#endif  // __CUDACC__
 
 }  // namespace ctk

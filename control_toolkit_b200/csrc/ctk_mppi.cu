@@ -1,6 +1,7 @@
 // ctk_mppi.cu -- translation unit owning the MPPI kernels (K1, K2), the log transpose and the nominal rollout.
 #include "ctk_kernels_mppi.cuh"
 #include "ctk_kernels_mppi_ode.cuh"
+#include "ctk_mlp_tc.cuh"
 #include "ctk_launch.h"
 
 namespace ctk {
@@ -21,11 +22,13 @@ static cudaError_t launch_mppi_p(int kind, bool log, int nblocks, int block, siz
   return log ? launch_mppi_t<Pred, 1, true>(nblocks, block, smem, st, a) : launch_mppi_t<Pred, 1, false>(nblocks, block, smem, st, a);
 }
 cudaError_t launch_mppi_rollout(int pred, int kind, bool log, int nblocks, int block, size_t smem, cudaStream_t st, const MppiArgs& a) {
+  if (pred == 2) return launch_mppi_p<MlpTcPred>(kind, log, nblocks, block, smem, st, a);
   return pred == 0 ? launch_mppi_p<OdePred>(kind, log, nblocks, block, smem, st, a)
                    : launch_mppi_p<MlpSimtPred>(kind, log, nblocks, block, smem, st, a);
 }
-int mppi_max_block_threads(int pred) { return pred == 0 ? OdePred::kMaxThreads : MlpSimtPred::kMaxThreads; }
-size_t mppi_pred_smem_floats(int pred, const MlpDev& m) { return pred == 0 ? 0 : MlpSimtPred::smem_floats(m); }
+// pred: 0 ODE, 1 MLP on the FP32 pipe, 2 MLP with layer 2 on the tensor cores (tcgen05)
+int mppi_max_block_threads(int pred) { return pred == 0 ? OdePred::kMaxThreads : (pred == 2 ? MlpTcPred::kMaxThreads : MlpSimtPred::kMaxThreads); }
+size_t mppi_pred_smem_floats(int pred, const MlpDev& m) { return pred == 0 ? 0 : (pred == 2 ? MlpTcPred::smem_floats(m) : MlpSimtPred::smem_floats(m)); }
 
 // K1 for the ODE predictor (ctk_kernels_mppi_ode.cuh).  period_t: 10 -> the segment-unrolled instantiation, else runtime period.
 template <int KIND, bool LOG, int PERIOD, int ILP>

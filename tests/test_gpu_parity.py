@@ -104,6 +104,31 @@ def test_mppi_matches_reference_golden(name):
     assert out["rollout_trajectories_logged"].shape == (meta["ticks"], opt.num_rollouts, opt.mpc_horizon + 1, 6)
 
 
+@pytest.mark.parametrize("name", [n for n in golden_names("mppi_") if "mlp" in n])
+def test_mppi_mlp_tcgen05_matches_reference_golden(name):
+    """The MLP predictor with its dense layer on the tensor cores (tcgen05.mma, bf16 x 3 split operands, fp32 accumulation in
+    TMEM: ctk_mlp_tc.cuh) against the same reference fixtures and tolerances as the FP32-pipe engine, and against that
+    engine directly (the two differ only in how the 128 x 128 layer is summed)."""
+    z, meta = load_golden(name)
+    ctrl = make_controller(meta, mlp_engine="tcgen05")
+    simt = make_controller(meta)
+    opt = ctrl.optimizer
+    floors = fp32_noise_floor(name)
+    for t in range(meta["ticks"]):
+        u = ctrl.step(z["states"][t], time=0.02 * t)
+        u_s = simt.step(z["states"][t], time=0.02 * t)
+        tol_s, tol_u, _ = _tols(floors[t])
+        e_u = _u_err(u, z[f"u_{t}"], z[f"u_nom_{t}"])
+        e_nom = max_rel(opt.u_nom, z[f"u_nom_{t}"])
+        e_simt = max_rel(opt.u_nom, simt.optimizer.u_nom)
+        e_J = max_elem_rel(opt.logging_values["J_logged"], z[f"J_{t}"])
+        _report(f"{name} [tcgen05] tick {t}: u {e_u:.2e} u_nom {e_nom:.2e} vs-simt {e_simt:.2e} J {e_J:.2e} | fp32 floor: state {floors[t]['state']:.2e}")
+        assert e_u < tol_u and e_nom < tol_s, (name, t, e_u, e_nom, floors[t])
+        assert e_simt < tol_s, (name, t, e_simt)
+        assert abs(float(u) - float(u_s)) < tol_u * max(float(np.abs(z[f"u_nom_{t}"]).max()), 1e-2)
+        _check_J(opt.logging_values["J_logged"], z[f"J_{t}"], floors[t], (name, "tcgen05", t))
+
+
 @pytest.mark.parametrize("name", golden_names("cem_"))
 def test_cem_matches_reference_golden(name):
     z, meta = load_golden(name)
