@@ -44,10 +44,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<const uint32_t*>(&v);
-}
 
 struct MlpTcPred {
   static constexpr bool kCooperative = true;  // every thread of the CTA must call step() the same number of times
@@ -97,39 +93,60 @@ struct MlpTcPred {
   __device__ __forceinline__ bool single_substep() const { return false; }
   __device__ __forceinline__ void use_uniform(const HotUK&) {}
 
+  // tanh(x) = 1 - 2 / (exp(2x) + 1) for either sign (x -> -inf: e -> 0, t -> -1; x -> +inf: e -> inf, r -> 0, t -> 1):
+  // FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA.  Absolute error <= ~3e-7 (the two MUFU approximations), the same bound the
+  // FP32-pipe engine's tanh_acc has outside its small-|x| series branch.
+  static __device__ __forceinline__ float tanh5(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));  // exp(2x) = 2^(2x log2 e)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+  }
+  static __device__ __forceinline__ float4 lds4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+  }
+  // three bf16 terms of two floats by TRUNCATION (x = t1 + t2 + t3 + O(2^-24 x), every residual exact): the high halves are
+  // picked by PRMT, the residuals by LOP3 + FADD -- ALU / FMA pipes only, the conversion unit stays free for the MUFU tanh
+  static __device__ __forceinline__ void split3(float a0, float a1, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+    const uint32_t u0 = __float_as_uint(a0), u1 = __float_as_uint(a1);
+    p1 = __byte_perm(u0, u1, 0x7632);
+    const float r0 = a0 - __uint_as_float(u0 & 0xffff0000u), r1 = a1 - __uint_as_float(u1 & 0xffff0000u);
+    const uint32_t v0 = __float_as_uint(r0), v1 = __float_as_uint(r1);
+    p2 = __byte_perm(v0, v1, 0x7632);
+    const float s0 = r0 - __uint_as_float(v0 & 0xffff0000u), s1 = r1 - __uint_as_float(v1 & 0xffff0000u);
+    p3 = __byte_perm(__float_as_uint(s0), __float_as_uint(s1), 0x7632);
+  }
+
   // net input [Q, angleD, cos, sin, position, positionD] -> next [angleD, cos, sin, position, positionD];
   // angle = atan2(sin, cos)  (oracle/spec.py MLPPredictor.step); same FP32 op order as MlpSimtPred outside layer 2
   __device__ __noinline__ void step(State& z, float u, float& omc) {
     const int tid = threadIdx.x;
     const float x[6] = {u, z.om, z.c, z.s, z.x, z.v};
+    const uint32_t aW1 = smem_u32(W1), ab1 = smem_u32(b1), ab2 = smem_u32(b2), aW3 = smem_u32(W3T);
     // ---- layer 1 + tanh + 3-term bf16 split -> operand tiles ----
-    uint8_t* arow = sA + (size_t)tid * 16;
-#pragma unroll 2
+    const uint32_t arow = smem_u32(sA) + (uint32_t)tid * 16u;
+#pragma unroll 4
     for (int kg = 0; kg < 16; ++kg) {
-      float h[8];
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int j = kg * 8 + jj;
-        float acc = 0.0f;  // torch: (x @ W1) + b1 -> accumulate the dot product first, then add the bias
-#pragma unroll
-        for (int i = 0; i < 6; ++i) acc = fmaf(x[i], W1[i * 128 + j], acc);
-        h[jj] = tanh_acc(acc + b1[j]);
-      }
       uint32_t p1[4], p2[4], p3[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float a0 = h[2 * q], a1 = h[2 * q + 1];
-        const float a0_1 = __bfloat162float(__float2bfloat16_rn(a0)), a1_1 = __bfloat162float(__float2bfloat16_rn(a1));
-        const float r0 = a0 - a0_1, r1 = a1 - a1_1;  // exact
-        const float a0_2 = __bfloat162float(__float2bfloat16_rn(r0)), a1_2 = __bfloat162float(__float2bfloat16_rn(r1));
-        p1[q] = pack_bf16x2(a0_1, a1_1);
-        p2[q] = pack_bf16x2(a0_2, a1_2);
-        p3[q] = pack_bf16x2(r0 - a0_2, r1 - a1_2);
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t jo = (uint32_t)(kg * 8 + half * 4) * 4u;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);  // torch: (x @ W1) + b1 -> accumulate the dot product first, then add the bias
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const float4 w = lds4(aW1 + (uint32_t)i * 512u + jo);
+          acc.x = fmaf(x[i], w.x, acc.x); acc.y = fmaf(x[i], w.y, acc.y); acc.z = fmaf(x[i], w.z, acc.z); acc.w = fmaf(x[i], w.w, acc.w);
+        }
+        const float4 bb = lds4(ab1 + jo);
+        split3(tanh5(acc.x + bb.x), tanh5(acc.y + bb.y), p1[2 * half], p2[2 * half], p3[2 * half]);
+        split3(tanh5(acc.z + bb.z), tanh5(acc.w + bb.w), p1[2 * half + 1], p2[2 * half + 1], p3[2 * half + 1]);
       }
-      uint8_t* dst = arow + (size_t)kg * kTcKStride;
-      *reinterpret_cast<uint4*>(dst) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-      *reinterpret_cast<uint4*>(dst + kTcTileBytes) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
-      *reinterpret_cast<uint4*>(dst + 2 * kTcTileBytes) = make_uint4(p3[0], p3[1], p3[2], p3[3]);
+      const uint32_t dst = arow + (uint32_t)kg * kTcKStride;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(p1[0]), "r"(p1[1]), "r"(p1[2]), "r"(p1[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kTcTileBytes), "r"(p2[0]), "r"(p2[1]), "r"(p2[2]), "r"(p2[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 2 * kTcTileBytes), "r"(p3[0]), "r"(p3[1]), "r"(p3[2]), "r"(p3[3]) : "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // operand tiles -> visible to the tensor core (async proxy)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -180,11 +197,16 @@ struct MlpTcPred {
           : "r"(trow + c0));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        const int j = c0 + jj;
-        const float h2 = tanh_acc(__uint_as_float(v[jj]) + b2[j]);
+      for (int g = 0; g < 8; ++g) {
+        const uint32_t jo = (uint32_t)(c0 + g * 4) * 4u;
+        const float4 bb = lds4(ab2 + jo);
+        const float h0 = tanh5(__uint_as_float(v[4 * g]) + bb.x), h1 = tanh5(__uint_as_float(v[4 * g + 1]) + bb.y);
+        const float h2 = tanh5(__uint_as_float(v[4 * g + 2]) + bb.z), h3 = tanh5(__uint_as_float(v[4 * g + 3]) + bb.w);
 #pragma unroll
-        for (int k = 0; k < 5; ++k) y[k] = fmaf(h2, W3T[k * 128 + j], y[k]);
+        for (int k = 0; k < 5; ++k) {  // same accumulation order over j as the FP32-pipe engine
+          const float4 w = lds4(aW3 + (uint32_t)k * 512u + jo);
+          y[k] = fmaf(h3, w.w, fmaf(h2, w.z, fmaf(h1, w.y, fmaf(h0, w.x, y[k]))));
+        }
       }
     }
     z.om = y[0] + b3[0];
