@@ -153,6 +153,7 @@ class template_optimizer:
             w = pred_spec.to_c()
             L.check(lib.ctk_set_mlp_weights(self._h, C.byref(w)))
         self._u_buf = np.zeros(1, np.float32)
+        self._state_buf = None
 
     def _require_backend(self):
         if self._h is None:
@@ -178,13 +179,19 @@ class template_optimizer:
             z = np.ascontiguousarray(self.rng.standard_draws(kind, shape), dtype=np.float32).ravel()
             L.check(lib.ctk_push_injected_noise(self._h, L.fptr(z), z.size))
 
-    def _tick(self, lib, s: np.ndarray) -> np.ndarray:
+    def _tick(self, lib, s: np.ndarray, state_which=None, state_n=0) -> np.ndarray:
         s32 = np.ascontiguousarray(np.asarray(s, dtype=np.float32).reshape(-1))
         if s32.size != 6:
             raise ValueError(f"state must have {6} entries, got {s32.size}")
         if self.shard is not None and self.shard.world_size > 1:
+            self._state_buf = None
             return self.shard.run_tick(self, lib, s32)
-        L.check(lib.ctk_step(self._h, L.fptr(s32), L.fptr(self._u_buf)))
+        if state_which is not None:  # u and one [H] state array with a single device->host window and synchronisation
+            if self._state_buf is None or self._state_buf.size != state_n:
+                self._state_buf = np.empty(state_n, np.float32)
+            L.check(lib.ctk_step_state(self._h, L.fptr(s32), L.fptr(self._u_buf), state_which, L.fptr(self._state_buf), state_n))
+        else:
+            L.check(lib.ctk_step(self._h, L.fptr(s32), L.fptr(self._u_buf)))
         return self._u_buf.copy()
 
     # -- state / logs ------------------------------------------------------------------------------------------

@@ -82,10 +82,13 @@ class optimizer_mppi(template_optimizer):
         self._refresh_live_cost(lib)
         self._feed_noise(lib, [("normal", (self.num_rollouts, self.number_of_interpolation_inducing_points,
                                            self.num_control_inputs))])
-        u = self._tick(lib, s)
-        self.u = np.squeeze(u)  # :212 0-d for nu == 1
         H, nu, ns, N = self.mpc_horizon, self.num_control_inputs, 6, self._n_local
-        self.u_nom = self._get_state(L.STATE_U_NOM, (1, H, nu))
+        u = self._tick(lib, s, L.STATE_U_NOM, H)
+        self.u = np.squeeze(u)  # :212 0-d for nu == 1
+        if self._state_buf is not None:
+            self.u_nom = self._state_buf.reshape(1, H, nu).copy()
+        else:
+            self.u_nom = self._get_state(L.STATE_U_NOM, (1, H, nu))
         if self.optimizer_logging:
             self.rollout_trajectories = self._get_log(L.LOG_ROLLOUTS, (N, H + 1, ns))
             self.logging_values["Q_logged"] = self._get_log(L.LOG_Q, (N, H, nu))

@@ -82,6 +82,7 @@ SYMBOLS = {
     "ctk_push_injected_noise": (C.c_int, [_H, _FP, C.c_size_t]),
     "ctk_clear_injected_noise": (C.c_int, [_H]),
     "ctk_step": (C.c_int, [_H, _FP, _FP]),
+    "ctk_step_state": (C.c_int, [_H, _FP, _FP, C.c_int, _FP, C.c_size_t]),
     "ctk_step_local": (C.c_int, [_H, C.c_void_p]),
     "ctk_partials": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "ctk_step_finish": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p]),

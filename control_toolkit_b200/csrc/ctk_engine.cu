@@ -63,7 +63,7 @@ struct ctk_handle {
   unsigned int xseq = 0;
   // common
   float *d_s0 = nullptr, *d_u_prev = nullptr, *d_u_out = nullptr, *d_J = nullptr;
-  float *h_pin = nullptr;  // pinned staging: s[8] | u[8]
+  float *h_pin = nullptr;  // pinned staging: s[8] | u[8] | one [H] state array (ctk_step_state)
   // mppi
   float *d_u_nom = nullptr, *d_partials = nullptr, *d_record = nullptr;
   // cem
@@ -239,7 +239,7 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
   A(dalloc(&h->d_J, (size_t)N), "J");
   A(cudaMalloc((void**)&h->d_kc, sizeof(DevConsts)), "consts");
   A(dalloc(&h->d_kx, 4), "kx");
-  A(cudaMallocHost((void**)&h->h_pin, 16 * sizeof(float)), "pinned");
+  A(cudaMallocHost((void**)&h->h_pin, (16 + (size_t)H) * sizeof(float)), "pinned");
   if (cfg->logging) {
     A(dalloc(&h->d_log_traj_soa, (size_t)(H + 1) * 6 * N), "log_traj");
     A(dalloc(&h->d_log_Q_soa, (size_t)H * N), "log_Q");
@@ -751,7 +751,20 @@ extern "C" int ctk_step_finish(ctk_handle* h, const float* gathered, int G, floa
   }
 }
 
-extern "C" int ctk_step(ctk_handle* h, const float* s_host, float* u_out_host) {
+static int state_ptr(ctk_handle* h, int which, float** p, size_t* n, bool* tmajor);
+static int step_host(ctk_handle* h, const float* s_host, float* u_out_host, const float* state_dev, float* state_out_host, size_t n_state);
+extern "C" int ctk_step(ctk_handle* h, const float* s_host, float* u_out_host) { return step_host(h, s_host, u_out_host, nullptr, nullptr, 0); }
+// ctk_step + read-back of one [H] state array (MPPI u_nom, CEM dist_mue / stdev) in the SAME device->host copy window and
+// synchronisation: the plugin's step() needs u and the warm-start sequence every tick (optimizer_mppi.py:220).
+extern "C" int ctk_step_state(ctk_handle* h, const float* s_host, float* u_out_host, int which, float* state_out_host, size_t n) {
+  REQ(h && state_out_host, "null pointer");
+  float* p; size_t cnt; bool tm;
+  int rc = state_ptr(h, which, &p, &cnt, &tm);
+  if (rc != CTK_OK) return rc;
+  REQ(!tm && n == cnt && cnt <= (size_t)h->H, "ctk_step_state reads the [H] state arrays only");
+  return step_host(h, s_host, u_out_host, p, state_out_host, n);
+}
+static int step_host(ctk_handle* h, const float* s_host, float* u_out_host, const float* state_dev, float* state_out_host, size_t n_state) {
   REQ(h && s_host && u_out_host, "null pointer");
   if (!h->was_reset) return fail(CTK_ESTATE, "ctk_step before ctk_reset");
   CU(cudaSetDevice(h->cfg.device));
@@ -776,8 +789,10 @@ extern "C" int ctk_step(ctk_handle* h, const float* s_host, float* u_out_host) {
   }
   if (rc != CTK_OK) return rc;
   CU(cudaMemcpyAsync(h->h_pin + 8, h->d_u_out, 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (state_dev) CU(cudaMemcpyAsync(h->h_pin + 16, state_dev, n_state * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   u_out_host[0] = h->h_pin[8];
+  if (state_dev) memcpy(state_out_host, h->h_pin + 16, n_state * sizeof(float));
   if (h->h_pin[9] != 0.0f) return fail(CTK_ECUDA, "cross-GPU exchange timed out: a peer shard did not deliver its record within 2 s");
   return CTK_OK;
 }

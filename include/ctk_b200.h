@@ -151,6 +151,10 @@ int ctk_clear_injected_noise(ctk_handle *h);
 /* replaces optimizer.step(s, time) (controller_mpc.py:104): one full tick, host in / host out.
    s_host [num_states]; u_out_host [num_control_inputs].                                                          */
 int ctk_step(ctk_handle *h, const float *s_host, float *u_out_host);
+/* ctk_step plus the read-back of one [H] state array (CTK_STATE_U_NOM / CEM_MU / CEM_STD) in the same copy window and
+   synchronisation: the plugin's step() returns u AND refreshes the warm-start sequence every tick
+   (optimizer_mppi.py:220 optimal_control_sequence = u_nom).                                                         */
+int ctk_step_state(ctk_handle *h, const float *s_host, float *u_out_host, int which, float *state_out_host, size_t n);
 /* The same tick split for sharded (multi-GPU) use and for device-resident timing:
    ctk_step_local   : sample + rollout + cost + local reduction; asynchronous on the handle's stream; s_dev [ns].
    ctk_partials     : device pointer / float count of this shard's exchange record
