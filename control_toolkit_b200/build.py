@@ -20,7 +20,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libctk_b200.so")
 UNITS = ["ctk_engine.cu", "ctk_mppi.cu", "ctk_cem.cu", "ctk_rpgd.cu", "ctk_mlp_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-I", INCLUDE, "-I", CSRC]
+              "-I", INCLUDE, "-I", CSRC] + os.environ.get("CTK_NVCC_EXTRA", "").split()  # e.g. -DCTK_TC_TRACE (diagnostics)
 
 
 def _nvcc() -> str:

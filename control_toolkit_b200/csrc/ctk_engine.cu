@@ -44,7 +44,7 @@ struct ctk_handle {
   float* d_kx = nullptr;      // device: {lo, hi, k_du2, k_udu}
   cudaStream_t stream = nullptr;
   int N = 0, NG = 0, off = 0, H = 0, period = 1, n_ind = 0, nblocks = 0;
-  int mppi_grid = 0, mppi_block = 0, mppi_iters = 0, mppi_stash = 0, num_sms = 0;
+  int mppi_grid = 0, mppi_block = 0, mppi_rpb = 0, mppi_iters = 0, mppi_stash = 0, num_sms = 0;  // rpb: rollouts per block
   // K1 for the ODE predictor (ctk_kernels_mppi_ode.cuh)
   ctk_ode_params ode_p{};
   ctk_cost_params cost_p{};
@@ -272,6 +272,15 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
       h->mppi_block = T;
       h->mppi_grid = (int)std::min<long long>(h->num_sms, ((long long)N + T - 1) / T);
       h->mppi_stash = 0;
+    }
+    h->mppi_rpb = h->mppi_block;
+    if (pred_id(h) == 2) {  // tcgen05 MLP engine: 512 threads work on the 128 rollouts of one MMA tile (ctk_mlp_tc.cuh)
+      h->mppi_block = 512; h->mppi_rpb = 128;
+      h->mppi_grid = (int)std::min<long long>(h->num_sms, ((long long)N + 127) / 128);
+      if (h->mppi_grid < 1) h->mppi_grid = 1;
+      h->mppi_iters = (int)((N + (long long)h->mppi_grid * 128 - 1) / ((long long)h->mppi_grid * 128));
+      h->mppi_stash = ((size_t)h->n_ind * 128 * sizeof(float) <= 8 * 1024) ? 1 : 0;
+      if ((size_t)h->n_ind * 128 * sizeof(float) > 8 * 1024) { ctk_destroy(h); return fail(CTK_EINVAL, "tcgen05 MLP engine: too many inducing points (shared memory is taken by the operand tiles)"); }
     }
     A(dalloc(&h->d_u_nom, (size_t)H), "u_nom");
     A(dalloc(&h->d_partials, (size_t)(h->num_sms > h->mppi_grid ? h->num_sms : h->mppi_grid) * (h->mppi_iters + 1) * (h->n_ind + 2)), "partials");
@@ -575,7 +584,7 @@ static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_
   a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
   a.fuse = fuse;
   const size_t smem = sizeof(float) * ((size_t)((h->H + 1) & ~1) + 2 * h->period + 32 + 42 * (h->n_ind + 1) + 16 +
-                                       (h->mppi_stash ? (size_t)h->n_ind * h->mppi_block : 0) + (size_t)h->n_ind * h->mppi_block +
+                                       (h->mppi_stash ? (size_t)h->n_ind * h->mppi_rpb : 0) + (size_t)h->n_ind * h->mppi_rpb +
                                        pred_smem_floats(h));
   h->launches++;
   KernelTimer kt(h);

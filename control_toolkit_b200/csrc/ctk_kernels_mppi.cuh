@@ -165,9 +165,11 @@ __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const M
   float2* sh_w = reinterpret_cast<float2*>(smem + ((a.H + 1) & ~1));  // [period] interpolation weights (w0, w1)
   float* sh_red = reinterpret_cast<float*>(sh_w + a.period);          // [32] reduction scratch
   float* sh_part = sh_red + 32;          // [32][n_ind + 1] per-warp partial sums | block record | finish scratch
-  float* sh_z = sh_part + 42 * (a.n_ind + 1) + 16;  // [n_ind][blockDim] stash of this rollout's standard draws (if a.stash)
-  float* sh_acc = sh_z + (a.stash ? (size_t)a.n_ind * blockDim.x : 0);  // [n_ind][blockDim] per-thread sum_n e_n z_n,i
-  float* sh_pred = sh_acc + (size_t)a.n_ind * blockDim.x;
+  float* sh_z = sh_part + 42 * (a.n_ind + 1) + 16;  // [n_ind][rpb] stash of this rollout's standard draws (if a.stash)
+  // rollouts per block: blockDim, unless the predictor brings helper threads that own no rollout (MlpTcPred)
+  const int rpb = Pred::kRolloutsPerBlock > 0 ? Pred::kRolloutsPerBlock : (int)blockDim.x;
+  float* sh_acc = sh_z + (a.stash ? (size_t)a.n_ind * rpb : 0);  // [n_ind][rpb] per-thread sum_n e_n z_n,i
+  float* sh_pred = sh_acc + (size_t)a.n_ind * rpb;
 
   for (int t = threadIdx.x; t < a.H; t += blockDim.x) sh_unom[t] = a.u_nom[min(t + 1, a.H - 1)];
   for (int j = threadIdx.x; j < a.period; j += blockDim.x) interp_weights(j, a.period, &sh_w[j].x, &sh_w[j].y);
@@ -185,21 +187,23 @@ __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const M
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
   const int P = a.n_ind + 1;
-  const int stride = gridDim.x * blockDim.x;
+  const int stride = gridDim.x * rpb;
+  const bool owner = tid < rpb;  // this thread carries a rollout
   const int nblk = (a.n_ind + 3) >> 2;
   const State z0 = {a.s0[0], a.s0[1], a.s0[2], a.s0[3], a.s0[4], a.s0[5]};
   const float omc0 = 1.0f - cosf(z0.th);  // spec: E_pot uses cos(angle); for t >= 1 the state carries 1 - cos
   const float u_prev0 = a.u_prev[0];
-  float* sz = sh_z + tid;
-  float* sa = sh_acc + tid;
-  for (int i = 0; i < a.n_ind; ++i) sa[(size_t)i * blockDim.x] = 0.0f;
+  float* sz = sh_z + min(tid, rpb - 1);
+  float* sa = sh_acc + min(tid, rpb - 1);
+  if (owner)
+    for (int i = 0; i < a.n_ind; ++i) sa[(size_t)i * rpb] = 0.0f;
   // per-thread online softmin over this thread's rollouts: rho_t = running min, a_t = sum e, sa[i] = sum e z_i
   float rho_t = INFINITY, a_t = 0.0f;
   const uint32_t a_unom = smem_u32(sh_unom), a_w = smem_u32(sh_w);
 
-  for (int base = blockIdx.x * blockDim.x; base < a.N; base += stride) {
+  for (int base = blockIdx.x * rpb; base < a.N; base += stride) {
     const int n = base + tid;
-    const bool active = n < a.N;
+    const bool active = owner && n < a.N;
     const uint32_t ng = (uint32_t)(a.off + (active ? n : 0));
     float S = INFINITY;
     if (active || Pred::kCooperative) {
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const M
       // inducing-point draws arrive four at a time (one Philox block); zq is a rotating window, zq[0] = next draw
       float zq[4];
       noise4(a.noise, ng, 0, zq);
-      if (a.stash) sz[0] = zq[0];
+      if (a.stash && owner) sz[0] = zq[0];
       float y_prev = __fmul_rn(zq[0], stdev);  // :173-175  normal * stdev (before interpolation)
       zq[0] = zq[1]; zq[1] = zq[2]; zq[2] = zq[3];
       int have = 3, nextblk = 1, i = 1;  // i = next inducing point to load
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const M
             ++nextblk;
             have = 4;
           }
-          if (a.stash) sz[(size_t)i * blockDim.x] = zq[0];
+          if (a.stash && owner) sz[(size_t)i * rpb] = zq[0];
           y_cur = __fmul_rn(zq[0], stdev);
           zq[0] = zq[1]; zq[1] = zq[2]; zq[2] = zq[3];
           --have; ++i;
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const M
       rho_t = rho_n;
       if (a.stash) {
         for (int i = 0; i < a.n_ind; ++i) {
-          const size_t o = (size_t)i * blockDim.x;
+          const size_t o = (size_t)i * rpb;
           sa[o] = fmaf(sa[o], so, sn * sz[o]);
         }
       } else {
@@ -275,7 +279,7 @@ __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const M
           for (int q = 0; q < 4; ++q) {
             const int i = blk * 4 + q;
             if (i < a.n_ind) {
-              const size_t o = (size_t)i * blockDim.x;
+              const size_t o = (size_t)i * rpb;
               sa[o] = fmaf(sa[o], so, sn * zz[q]);
             }
           }
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const M
     if (lane == 0) sh_part[w * P] = ws;
   }
   for (int i = 0; i < a.n_ind; ++i) {
-    const float ws = warp_sum(sa[(size_t)i * blockDim.x] * sc);
+    const float ws = warp_sum((owner ? sa[(size_t)i * rpb] : 0.0f) * sc);
     if (lane == 0) sh_part[w * P + 1 + i] = ws;
   }
   __syncthreads();
@@ -305,7 +309,7 @@ __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const M
   if (tid == 0) brec[0] = rho_b;
   // fused K2 (+ cross-GPU exchange): block 0 finishes the tick
   mppi_tick_finish(a.fuse, brec, a.partials, a.n_ind, a.H, a.period, a.stdev, a.lo, a.hi, a.neg_inv_lbd, sh_unom, brec + P + 1,
-                   sh_red, sh_z, (int)((a.stash ? (size_t)a.n_ind * blockDim.x : 0) + (size_t)a.n_ind * blockDim.x));
+                   sh_red, sh_z, (int)((a.stash ? (size_t)a.n_ind * rpb : 0) + (size_t)a.n_ind * rpb));
 }
 
 __global__ void __launch_bounds__(1024) mppi_combine_kernel(const float* __restrict__ in, int cnt, int n_ind,

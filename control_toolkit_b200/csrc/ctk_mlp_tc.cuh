@@ -1,7 +1,8 @@
 // ctk_mlp_tc.cuh -- tcgen05 (UMMA + TMEM) engine of the MLP predictor (6 -> 128 tanh -> 128 tanh -> 5, config C4).
 // Replaces PredictorWrapper.predict_core for the neural predictor (reference call sites optimizer_mppi.py:188,
 // optimizer_cem_tf.py:57).  Drop-in `Pred` of the generic rollout kernels (ctk_kernels_mppi.cuh): one CTA = 128
-// rollouts = the M dimension of the MMA, thread r owns rollout (row) r for everything that is not the dense layer.
+// rollouts = the M dimension of the MMA, 512 threads: thread (row r, quarter q) works on a quarter of row r's columns in the
+// FP32 stages (4 warps per scheduler hide the MUFU / shared-memory latency); threads with q = 0 own the rollouts.
 //
 //   layer 1 (6 -> 128, 4 % of the FLOPs)  : FP32 FMAs per thread, weights broadcast from shared memory; tanh; the row of h1
 //                                            is split into THREE bf16 terms (h = a1 + a2 + a3, 24 mantissa bits) and stored
@@ -16,6 +17,7 @@
 // which is what lets A (96 KB) and W2 (96 KB) both live in shared memory.
 #pragma once
 #include <cuda_bf16.h>
+#include <cstdio>
 
 #include "ctk_args.cuh"
 #include "ctk_device.cuh"
@@ -47,15 +49,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 
 struct MlpTcPred {
   static constexpr bool kCooperative = true;  // every thread of the CTA must call step() the same number of times
-  static constexpr int kMaxThreads = 128;
-  uint8_t* sA;        // [3][32768] activation split tiles (written per step)
+  static constexpr int kMaxThreads = 512;
+  static constexpr int kRolloutsPerBlock = 128;  // threads 128..511 are helpers: they own no rollout
+  uint8_t* sA;        // [3][32768] activation split tiles (written per step); reused for the layer-3 partial sums
+  float* sx;          // [128][8] network inputs of the rows (owners -> helpers)
   uint8_t* sB;        // [3][32768] W2 split tiles (resident)
   const float *W1, *b1, *b2, *W3T, *b3;
   uint64_t* mbar;
   uint32_t* tmem_slot;
   uint32_t phase;
+#ifdef CTK_TC_TRACE
+  long long tr[8];  // accumulated clock64 deltas of the step phases (diagnostics build)
+  long long tl;
+#endif
 
-  static size_t smem_floats(const MlpDev&) { return (6 * (size_t)kTcTileBytes + kTcBlobFloats * 4 + 64 + 1024) / 4; }
+  static size_t smem_floats(const MlpDev&) { return (6 * (size_t)kTcTileBytes + kTcBlobFloats * 4 + 64 + 128 * 8 * 4 + 1024) / 4; }
 
   __device__ __forceinline__ MlpTcPred(const DevConsts*, const MlpDev& m, float* sm) {
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)sm + 1023) & ~(uintptr_t)1023);
@@ -63,14 +71,20 @@ struct MlpTcPred {
     sB = base + 3 * kTcTileBytes;
     float* f = reinterpret_cast<float*>(sB + 3 * kTcTileBytes);
     W1 = f; b1 = W1 + 6 * 128; b2 = b1 + 128; W3T = b2 + 128; b3 = W3T + 5 * 128;
-    mbar = reinterpret_cast<uint64_t*>(f + kTcBlobFloats);
-    tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    mbar = reinterpret_cast<uint64_t*>(f + kTcBlobFloats);  // [2]: one per half of the accumulator columns
+    tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+    sx = f + kTcBlobFloats + 16;
     phase = 0;
+#ifdef CTK_TC_TRACE
+    for (int i = 0; i < 8; ++i) tr[i] = 0;
+    tl = 0;
+#endif
     const uint4* src = reinterpret_cast<const uint4*>(m.tc_blob);
     uint4* dst = reinterpret_cast<uint4*>(sB);
     for (int i = threadIdx.x; i < (int)(kTcBlobBytes / 16); i += blockDim.x) dst[i] = src[i];
     if (threadIdx.x == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar + 1)) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if ((threadIdx.x >> 5) == 0) {  // one warp allocates 128 TMEM columns (the fp32 accumulator) for the CTA's lifetime
@@ -82,6 +96,10 @@ struct MlpTcPred {
     // caller issues __syncthreads() after construction
   }
   __device__ __forceinline__ ~MlpTcPred() {
+#ifdef CTK_TC_TRACE
+    if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 200))
+      printf("tc trace tid %d: B1 %lld  L1 %lld  B2 %lld  issue %lld  mma-wait %lld  epilogue %lld  B3+update %lld  outside %lld (cycles, summed)\n", (int)threadIdx.x, tr[0], tr[1], tr[2], tr[3], tr[4], tr[5], tr[6], tr[7]);
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if ((threadIdx.x >> 5) == 0) {
@@ -120,15 +138,34 @@ struct MlpTcPred {
   }
 
   // net input [Q, angleD, cos, sin, position, positionD] -> next [angleD, cos, sin, position, positionD];
-  // angle = atan2(sin, cos)  (oracle/spec.py MLPPredictor.step); same FP32 op order as MlpSimtPred outside layer 2
-  __device__ __noinline__ void step(State& z, float u, float& omc) {
-    const int tid = threadIdx.x;
-    const float x[6] = {u, z.om, z.c, z.s, z.x, z.v};
+  // angle = atan2(sin, cos)  (oracle/spec.py MLPPredictor.step).  Called by all 512 threads; only q = 0 threads carry state.
+  __device__ __forceinline__ void step(State& z, float u, float& omc) {
+    const int tid = threadIdx.x, row = tid & 127, q = tid >> 7;
+#ifdef CTK_TC_TRACE
+    long long tc0 = clock64();
+    if (tl) tr[7] += tc0 - tl;
+#define TCT(i) { long long tc1 = clock64(); tr[i] += tc1 - tc0; tc0 = tc1; }
+#else
+#define TCT(i)
+#endif
     const uint32_t aW1 = smem_u32(W1), ab1 = smem_u32(b1), ab2 = smem_u32(b2), aW3 = smem_u32(W3T);
-    // ---- layer 1 + tanh + 3-term bf16 split -> operand tiles ----
-    const uint32_t arow = smem_u32(sA) + (uint32_t)tid * 16u;
-#pragma unroll 4
-    for (int kg = 0; kg < 16; ++kg) {
+    if (q == 0) {
+      float4* d = reinterpret_cast<float4*>(sx + row * 8);
+      d[0] = make_float4(u, z.om, z.c, z.s);
+      d[1] = make_float4(z.x, z.v, 0.f, 0.f);
+    }
+    __syncthreads();  // inputs visible; also: every thread is done with the previous step's partial sums (they alias sA)
+    TCT(0)
+    float x[6];
+    {
+      const float4 v0 = lds4(smem_u32(sx + row * 8)), v1 = lds4(smem_u32(sx + row * 8 + 4));
+      x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y;
+    }
+    // ---- layer 1 + tanh + 3-term bf16 split -> operand tiles: this thread's quarter of the row (k in [32 q, 32 q + 32)) ----
+    const uint32_t arow = smem_u32(sA) + (uint32_t)row * 16u;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int kg = q * 4 + kk;
       uint32_t p1[4], p2[4], p3[4];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -148,75 +185,105 @@ struct MlpTcPred {
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kTcTileBytes), "r"(p2[0]), "r"(p2[1]), "r"(p2[2]), "r"(p2[3]) : "memory");
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 2 * kTcTileBytes), "r"(p3[0]), "r"(p3[1]), "r"(p3[2]), "r"(p3[3]) : "memory");
     }
+    TCT(1)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // operand tiles -> visible to the tensor core (async proxy)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    TCT(2)
     const uint32_t tmem = *tmem_slot;
-    // ---- layer 2 on the tensor core: one thread issues 6 x 8 MMAs (M128 N128 K16, bf16 -> fp32 in TMEM) ----
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // instruction descriptor: D fp32, A/B bf16, both K-major, N = 128, M = 128
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-      uint32_t acc = 0;
+    // ---- layer 2 on the tensor core: one thread issues 6 x 8 MMAs (M128 N128 K16, bf16 -> fp32 in TMEM).  Both operands come
+    //      from shared memory: 8 KB per MMA, i.e. the full 128 B/clk of the SM's shared memory for the 64 cycles the tensor
+    //      core needs -- splitting N would re-read the A tiles and make the layer shared-memory bound (measured) ----
+    if ((tid >> 5) == 0) {
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // instruction descriptor: D fp32, A/B bf16, both K-major, N = 128, M = 128
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        uint32_t acc = 0;
 #pragma unroll
-      for (int term = 0; term < 6; ++term) {  // smallest products first: (a3 w1) (a2 w2) (a1 w3) (a2 w1) (a1 w2) (a1 w1)
-        constexpr int ta[6] = {2, 1, 0, 1, 0, 0}, tb[6] = {0, 1, 2, 0, 1, 0};
-        const uint32_t ab = a0 + ta[term] * kTcTileBytes, bb = b0 + tb[term] * kTcTileBytes;
+        for (int term = 0; term < 6; ++term) {  // smallest products first: (a3 w1) (a2 w2) (a1 w3) (a2 w1) (a1 w2) (a1 w1)
+          constexpr int ta[6] = {2, 1, 0, 1, 0, 0}, tb[6] = {0, 1, 2, 0, 1, 0};
+          const uint32_t ab = a0 + ta[term] * kTcTileBytes, bb = b0 + tb[term] * kTcTileBytes;
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          umma_bf16(tmem, umma_smem_desc(ab + ks * 2 * kTcKStride), umma_smem_desc(bb + ks * 2 * kTcKStride), idesc, acc);
-          acc = 1;
+          for (int ks = 0; ks < 8; ++ks) {
+            umma_bf16(tmem, umma_smem_desc(ab + ks * 2 * kTcKStride), umma_smem_desc(bb + ks * 2 * kTcKStride), idesc, acc);
+            acc = 1;
+          }
         }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
-    }
-    {
+      __syncwarp();  // lanes 1..31 must not spin on the barrier while lane 0 is still issuing (same warp: they would steal its issue slots)
+      TCT(3)
+      // ONE warp waits on the mbarrier; the other 15 sleep in the hardware barrier below instead of polling shared memory,
+      // whose full bandwidth the tensor core needs for its operands (an all-warp try_wait spin slowed the MMAs by 25 %)
       uint32_t done = 0;
       const uint32_t bar = smem_u32(mbar);
       while (!done) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(done) : "r"(bar), "r"(phase) : "memory");
       }
-      phase ^= 1u;
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // ---- accumulator row -> bias + tanh -> layer 3 ----
+    __syncthreads();
+    // ---- accumulator -> bias + tanh -> layer 3 partial sums: columns [32 q, 32 q + 32) ----
     float y[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    const uint32_t trow = tmem + ((uint32_t)((tid >> 5) * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    TCT(4)
 #pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 32) {
-      uint32_t v[32];
+    for (int hh = 0; hh < 2; ++hh) {
+      const int c0 = q * 32 + hh * 16;
+      uint32_t v[16];
       asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
-          "%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
           : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
-            "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
-            "=r"(v[30]), "=r"(v[31])
+            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
           : "r"(trow + c0));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
+      for (int g = 0; g < 4; ++g) {
         const uint32_t jo = (uint32_t)(c0 + g * 4) * 4u;
         const float4 bb = lds4(ab2 + jo);
         const float h0 = tanh5(__uint_as_float(v[4 * g]) + bb.x), h1 = tanh5(__uint_as_float(v[4 * g + 1]) + bb.y);
         const float h2 = tanh5(__uint_as_float(v[4 * g + 2]) + bb.z), h3 = tanh5(__uint_as_float(v[4 * g + 3]) + bb.w);
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {  // same accumulation order over j as the FP32-pipe engine
+        for (int k = 0; k < 5; ++k) {
           const float4 w = lds4(aW3 + (uint32_t)k * 512u + jo);
           y[k] = fmaf(h3, w.w, fmaf(h2, w.z, fmaf(h1, w.y, fmaf(h0, w.x, y[k]))));
         }
       }
     }
-    z.om = y[0] + b3[0];
-    z.c = y[1] + b3[1];
-    z.s = y[2] + b3[2];
-    z.x = y[3] + b3[3];
-    z.v = y[4] + b3[4];
-    z.th = atan2f(z.s, z.c);
-    // the network's (cos, sin) outputs are not normalised: cos(atan2(s, c)) = c / hypot(s, c)
-    omc = 1.0f - z.c * rsqrtf(fmaf(z.c, z.c, z.s * z.s));
+    TCT(5)
+    phase ^= 1u;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    // all MMAs of this step have completed (both barriers observed): the operand tiles are free and carry the partial sums
+    float* sy = reinterpret_cast<float*>(sA);  // [3][128][8]
+    if (q > 0) {
+      float4* d = reinterpret_cast<float4*>(sy + ((q - 1) * 128 + row) * 8);
+      d[0] = make_float4(y[0], y[1], y[2], y[3]);
+      d[1] = make_float4(y[4], 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    if (q == 0) {
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        const float4 v0 = lds4(smem_u32(sy + (p * 128 + row) * 8)), v1 = lds4(smem_u32(sy + (p * 128 + row) * 8 + 4));
+        y[0] += v0.x; y[1] += v0.y; y[2] += v0.z; y[3] += v0.w; y[4] += v1.x;
+      }
+      z.om = y[0] + b3[0];
+      z.c = y[1] + b3[1];
+      z.s = y[2] + b3[2];
+      z.x = y[3] + b3[3];
+      z.v = y[4] + b3[4];
+      z.th = atan2f(z.s, z.c);
+      // the network's (cos, sin) outputs are not normalised: cos(atan2(s, c)) = c / hypot(s, c)
+      omc = 1.0f - z.c * rsqrtf(fmaf(z.c, z.c, z.s * z.s));
+    }
+    TCT(6)
+#ifdef CTK_TC_TRACE
+    tl = clock64();
+#endif
   }
 };
 #endif  // __CUDACC__

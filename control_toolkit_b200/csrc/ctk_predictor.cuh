@@ -11,6 +11,7 @@ namespace ctk {
 
 struct OdePred {
   static constexpr bool kCooperative = false;
+  static constexpr int kRolloutsPerBlock = 0;  // 0: every thread of the block carries a rollout
 #ifndef CTK_ODE_MAX_THREADS
 #define CTK_ODE_MAX_THREADS 1024
 #endif
@@ -40,6 +41,7 @@ __device__ __forceinline__ float tanh_acc(float x) {
 
 struct MlpSimtPred {
   static constexpr bool kCooperative = false;
+  static constexpr int kRolloutsPerBlock = 0;
   static constexpr int kMaxThreads = 128;
   int hid;
   const float *W1, *b1, *W2, *b2, *W3T, *b3;  // shared memory

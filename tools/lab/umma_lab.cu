@@ -29,8 +29,8 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 }
 
 // variant 0: LBO = K-direction core-matrix stride, SBO = M/N-direction 8-row-group stride; variant 1: swapped
-__global__ void __launch_bounds__(128) umma_test(const __nv_bfloat16* __restrict__ A3, const __nv_bfloat16* __restrict__ B3, float* __restrict__ D,
-                                                 int variant, int nterms) {
+__global__ void __launch_bounds__(512) umma_test(const __nv_bfloat16* __restrict__ A3, const __nv_bfloat16* __restrict__ B3, float* __restrict__ D,
+                                                 int variant, int nterms, long long* cycles, int reps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;                 // 3 x 32768
   uint8_t* sB = smem + 3 * 32768;     // 3 x 32768
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(128) umma_test(const __nv_bfloat16* __restrict
   __shared__ uint32_t tmem_base_sh;
   const int tid = threadIdx.x, warp = tid >> 5;
   // operands arrive already in the canonical layout: plain copy
-  for (int i = tid; i < 3 * 32768 / 16; i += 128) {
+  for (int i = tid; i < 3 * 32768 / 16; i += blockDim.x) {
     reinterpret_cast<uint4*>(sA)[i] = reinterpret_cast<const uint4*>(A3)[i];
     reinterpret_cast<uint4*>(sB)[i] = reinterpret_cast<const uint4*>(B3)[i];
   }
@@ -57,6 +57,8 @@ __global__ void __launch_bounds__(128) umma_test(const __nv_bfloat16* __restrict
   const uint32_t tmem = tmem_base_sh;
   // instruction descriptor: c=F32 (1<<4), a=BF16 (1<<7), b=BF16 (1<<10), K-major both, N=128 (16<<17), M=128 (8<<24)
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+  long long t_start = clock64();
+  for (int rep = 0; rep < reps; ++rep) {
   if (tid == 0) {
     const uint32_t kstride = 2048, mstride = 128;  // layout: (k/8)*2048 + row*16 + (k%8)*2
     const uint32_t lbo = variant == 0 ? kstride : mstride, sbo = variant == 0 ? mstride : kstride;
@@ -77,11 +79,16 @@ __global__ void __launch_bounds__(128) umma_test(const __nv_bfloat16* __restrict
     uint32_t done = 0;
     while (!done) {
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
-                   : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0u) : "memory");
+                   : "=r"(done) : "r"(smem_u32(&mbar)), "r"((uint32_t)(rep & 1)) : "memory");
     }
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncthreads();
+  }
+  if (tid == 0 && cycles && blockIdx.x == 0) *cycles = (clock64() - t_start) / reps;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   // thread (row) r reads its 128 columns, 32 at a time
+  if (tid < 128)
   for (int c0 = 0; c0 < 128; c0 += 32) {
     uint32_t v[32];
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
@@ -94,7 +101,7 @@ __global__ void __launch_bounds__(128) umma_test(const __nv_bfloat16* __restrict
           "=r"(v[31])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    for (int j = 0; j < 32; ++j) D[(size_t)tid * 128 + c0 + j] = __uint_as_float(v[j]);
+    if (blockIdx.x == 0) for (int j = 0; j < 32; ++j) D[(size_t)tid * 128 + c0 + j] = __uint_as_float(v[j]);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -104,7 +111,8 @@ __global__ void __launch_bounds__(128) umma_test(const __nv_bfloat16* __restrict
 static uint16_t bf16_rn(float f) { __nv_bfloat16 b = __float2bfloat16_rn(f); uint16_t u; memcpy(&u, &b, 2); return u; }
 static float bf16_f(uint16_t u) { uint32_t x = (uint32_t)u << 16; float f; memcpy(&f, &x, 4); return f; }
 
-int main() {
+int main(int argc, char** argv) {
+  const int grid = argc > 1 ? atoi(argv[1]) : 1, block = argc > 2 ? atoi(argv[2]) : 128;
   const int M = 128, N = 128, K = 128;
   std::vector<float> A(M * K), B(N * K);  // B[n][k]
   srand(1);
@@ -131,16 +139,17 @@ int main() {
   const size_t smem = 6 * 32768 + 1024;
   cudaFuncSetAttribute(umma_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   std::vector<float> D(M * N);
-  for (int variant = 0; variant < 2; ++variant)
+  long long* dC; cudaMalloc(&dC, 8); long long hc = 0;
+  for (int variant = 0; variant < 1; ++variant)
     for (int nterms : {1, 3, 6}) {
       cudaMemset(dD, 0, M * N * 4);
-      umma_test<<<1, 128, smem>>>(dA, dB, dD, variant, nterms);
+      umma_test<<<grid, block, smem>>>(dA, dB, dD, variant, nterms, dC, 200);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("variant %d nterms %d: CUDA error %s\n", variant, nterms, cudaGetErrorString(e)); return 1; }
-      cudaMemcpy(D.data(), dD, M * N * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(D.data(), dD, M * N * 4, cudaMemcpyDeviceToHost); cudaMemcpy(&hc, dC, 8, cudaMemcpyDeviceToHost);
       double mx = 0, mref = 0;
       for (int i = 0; i < M * N; ++i) { mx = fmax(mx, fabs(D[i] - ref[i])); mref = fmax(mref, fabs(ref[i])); }
-      printf("variant %d (LBO=%s) terms %d: max abs err %.3e (max |ref| %.3f)  D[0]=%.6f ref %.6f  D[129]=%.6f ref %.6f\n", variant,
+      printf("[%lld cycles per %d-MMA series] variant %d (LBO=%s) terms %d: max abs err %.3e (max |ref| %.3f)  D[0]=%.6f ref %.6f  D[129]=%.6f ref %.6f\n", hc, nterms * 8, variant,
              variant == 0 ? "K-stride" : "MN-stride", nterms, mx, mref, D[0], ref[0], D[129], ref[129]);
     }
   return 0;
