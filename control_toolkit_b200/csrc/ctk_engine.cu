@@ -274,8 +274,8 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
       h->mppi_stash = 0;
     }
     h->mppi_rpb = h->mppi_block;
-    if (pred_id(h) == 2) {  // tcgen05 MLP engine: 512 threads work on the 128 rollouts of one MMA tile (ctk_mlp_tc.cuh)
-      h->mppi_block = 512; h->mppi_rpb = 128;
+    if (pred_id(h) == 2) {  // tcgen05 MLP engine: 16 worker warps + 1 MMA-issuer warp on the 128 rollouts of one MMA tile (ctk_mlp_tc.cuh)
+      h->mppi_block = mppi_max_block_threads(2); h->mppi_rpb = 128;
       h->mppi_grid = (int)std::min<long long>(h->num_sms, ((long long)N + 127) / 128);
       if (h->mppi_grid < 1) h->mppi_grid = 1;
       h->mppi_iters = (int)((N + (long long)h->mppi_grid * 128 - 1) / ((long long)h->mppi_grid * 128));

@@ -1,8 +1,10 @@
 // ctk_mlp_tc.cuh -- tcgen05 (UMMA + TMEM) engine of the MLP predictor (6 -> 128 tanh -> 128 tanh -> 5, config C4).
 // Replaces PredictorWrapper.predict_core for the neural predictor (reference call sites optimizer_mppi.py:188,
 // optimizer_cem_tf.py:57).  Drop-in `Pred` of the generic rollout kernels (ctk_kernels_mppi.cuh): one CTA = 128
-// rollouts = the M dimension of the MMA, 512 threads: thread (row r, quarter q) works on a quarter of row r's columns in the
-// FP32 stages (4 warps per scheduler hide the MUFU / shared-memory latency); threads with q = 0 own the rollouts.
+// rollouts = the M dimension of the MMA, 16 worker warps: thread (row r, quarter q) works on a quarter of row r's columns in the
+// FP32 stages (4 warps per scheduler hide the MUFU / shared-memory latency), threads with q = 0 own the rollouts; a 17th warp
+// only issues the MMAs, one K-quarter at a time, as soon as the workers have produced it (named barriers 1..4), so the
+// tensor core runs underneath the FP32 layer-1 stage.
 //
 //   layer 1 (6 -> 128, 4 % of the FLOPs)  : FP32 FMAs per thread, weights broadcast from shared memory; tanh; the row of h1
 //                                            is split into THREE bf16 terms (h = a1 + a2 + a3, 24 mantissa bits) and stored
@@ -49,8 +51,8 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 
 struct MlpTcPred {
   static constexpr bool kCooperative = true;  // every thread of the CTA must call step() the same number of times
-  static constexpr int kMaxThreads = 512;
-  static constexpr int kRolloutsPerBlock = 128;  // threads 128..511 are helpers: they own no rollout
+  static constexpr int kMaxThreads = 544;  // 16 worker warps + 1 MMA-issuer warp
+  static constexpr int kRolloutsPerBlock = 128;  // threads 128..543 are helpers: they own no rollout
   uint8_t* sA;        // [3][32768] activation split tiles (written per step); reused for the layer-3 partial sums
   float* sx;          // [128][8] network inputs of the rows (owners -> helpers)
   uint8_t* sB;        // [3][32768] W2 split tiles (resident)
@@ -149,23 +151,67 @@ struct MlpTcPred {
 #define TCT(i)
 #endif
     const uint32_t aW1 = smem_u32(W1), ab1 = smem_u32(b1), ab2 = smem_u32(b2), aW3 = smem_u32(W3T);
+    if (tid >= 512) {
+      // ===== MMA issuer warp: layer 2 on the tensor core, pipelined against the workers' layer-1 stage by quarters of K =====
+      __syncthreads();  // (S1)
+      const uint32_t tmem_i = *tmem_slot;
+      // instruction descriptor: D fp32, A/B bf16, both K-major, N = 128, M = 128
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+      uint32_t acc = 0;
+#pragma unroll 1
+      for (int p = 0; p < 4; ++p) {
+        asm volatile("bar.sync %0, 544;" ::"r"(1 + p) : "memory");  // quarter p of the operand tiles is complete (workers arrive)
+        if (tid == 512) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int term = 0; term < 6; ++term) {  // per quarter, smallest products first: (a3 w1) (a2 w2) (a1 w3) (a2 w1) (a1 w2) (a1 w1)
+            constexpr int ta[6] = {2, 1, 0, 1, 0, 0}, tb[6] = {0, 1, 2, 0, 1, 0};
+            const uint32_t ab = a0 + ta[term] * kTcTileBytes, bb = b0 + tb[term] * kTcTileBytes;
+#pragma unroll
+            for (int kq = 0; kq < 2; ++kq) {
+              const uint32_t ks = (uint32_t)(2 * p + kq);
+              umma_bf16(tmem_i, umma_smem_desc(ab + ks * 2 * kTcKStride), umma_smem_desc(bb + ks * 2 * kTcKStride), idesc, acc);
+              acc = 1;
+            }
+          }
+          if (p == 3)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+        }
+        __syncwarp();
+      }
+      {  // this warp alone waits for the MMAs; the workers sleep in the hardware barrier (S2) instead of polling shared memory
+        uint32_t done = 0;
+        const uint32_t bar = smem_u32(mbar);
+        while (!done) {
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                       : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+        }
+        phase ^= 1u;
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();  // (S2) accumulator complete
+      __syncthreads();  // (S3) partial sums exchanged
+      return;
+    }
     if (q == 0) {
       float4* d = reinterpret_cast<float4*>(sx + row * 8);
       d[0] = make_float4(u, z.om, z.c, z.s);
       d[1] = make_float4(z.x, z.v, 0.f, 0.f);
     }
-    __syncthreads();  // inputs visible; also: every thread is done with the previous step's partial sums (they alias sA)
+    __syncthreads();  // (S1) inputs visible; also: every thread is done with the previous step's partial sums (they alias sA)
     TCT(0)
     float x[6];
     {
       const float4 v0 = lds4(smem_u32(sx + row * 8)), v1 = lds4(smem_u32(sx + row * 8 + 4));
       x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y;
     }
-    // ---- layer 1 + tanh + 3-term bf16 split -> operand tiles: this thread's quarter of the row (k in [32 q, 32 q + 32)) ----
+    // ---- layer 1 + tanh + 3-term bf16 split -> operand tiles.  In phase p this thread produces k-group 4 p + q of its row, so
+    //      that after phase p the K-quarter [32 p, 32 p + 32) is complete for all rows and its MMAs can start ----
     const uint32_t arow = smem_u32(sA) + (uint32_t)row * 16u;
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const int kg = q * 4 + kk;
+    for (int p = 0; p < 4; ++p) {
+      const int kg = 4 * p + q;
       uint32_t p1[4], p2[4], p3[4];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -184,48 +230,15 @@ struct MlpTcPred {
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(p1[0]), "r"(p1[1]), "r"(p1[2]), "r"(p1[3]) : "memory");
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kTcTileBytes), "r"(p2[0]), "r"(p2[1]), "r"(p2[2]), "r"(p2[3]) : "memory");
       asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 2 * kTcTileBytes), "r"(p3[0]), "r"(p3[1]), "r"(p3[2]), "r"(p3[3]) : "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // operand tiles -> visible to the tensor core (async proxy)
+      asm volatile("bar.arrive %0, 544;" ::"r"(1 + p) : "memory");  // non-blocking: tell the issuer warp that quarter p is written
     }
     TCT(1)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // operand tiles -> visible to the tensor core (async proxy)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    __syncthreads();  // (S2) released when the issuer warp has seen the MMAs complete
     TCT(2)
     const uint32_t tmem = *tmem_slot;
-    // ---- layer 2 on the tensor core: one thread issues 6 x 8 MMAs (M128 N128 K16, bf16 -> fp32 in TMEM).  Both operands come
-    //      from shared memory: 8 KB per MMA, i.e. the full 128 B/clk of the SM's shared memory for the 64 cycles the tensor
-    //      core needs -- splitting N would re-read the A tiles and make the layer shared-memory bound (measured) ----
-    if ((tid >> 5) == 0) {
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // instruction descriptor: D fp32, A/B bf16, both K-major, N = 128, M = 128
-        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-        uint32_t acc = 0;
-#pragma unroll
-        for (int term = 0; term < 6; ++term) {  // smallest products first: (a3 w1) (a2 w2) (a1 w3) (a2 w1) (a1 w2) (a1 w1)
-          constexpr int ta[6] = {2, 1, 0, 1, 0, 0}, tb[6] = {0, 1, 2, 0, 1, 0};
-          const uint32_t ab = a0 + ta[term] * kTcTileBytes, bb = b0 + tb[term] * kTcTileBytes;
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            umma_bf16(tmem, umma_smem_desc(ab + ks * 2 * kTcKStride), umma_smem_desc(bb + ks * 2 * kTcKStride), idesc, acc);
-            acc = 1;
-          }
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
-      }
-      __syncwarp();  // lanes 1..31 must not spin on the barrier while lane 0 is still issuing (same warp: they would steal its issue slots)
-      TCT(3)
-      // ONE warp waits on the mbarrier; the other 15 sleep in the hardware barrier below instead of polling shared memory,
-      // whose full bandwidth the tensor core needs for its operands (an all-warp try_wait spin slowed the MMAs by 25 %)
-      uint32_t done = 0;
-      const uint32_t bar = smem_u32(mbar);
-      while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(done) : "r"(bar), "r"(phase) : "memory");
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    }
-    __syncthreads();
+    TCT(3)
     // ---- accumulator -> bias + tanh -> layer 3 partial sums: columns [32 q, 32 q + 32) ----
     float y[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     const uint32_t trow = tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
@@ -255,7 +268,6 @@ struct MlpTcPred {
       }
     }
     TCT(5)
-    phase ^= 1u;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     // all MMAs of this step have completed (both barriers observed): the operand tiles are free and carry the partial sums
     float* sy = reinterpret_cast<float*>(sA);  // [3][128][8]
@@ -264,7 +276,7 @@ struct MlpTcPred {
       d[0] = make_float4(y[0], y[1], y[2], y[3]);
       d[1] = make_float4(y[4], 0.f, 0.f, 0.f);
     }
-    __syncthreads();
+    __syncthreads();  // (S3)
     if (q == 0) {
 #pragma unroll
       for (int p = 0; p < 3; ++p) {
