@@ -67,17 +67,48 @@ __global__ void __launch_bounds__(TOPK_THREADS) cem_refit_kernel(const CemRefitA
   __shared__ uint64_t sh[TOPK_THREADS];
   __shared__ uint32_t sh_elite[TOPK_THREADS];
   uint64_t key = (threadIdx.x < a.cnt) ? a.cand[threadIdx.x] : KEY_MAX;
-  key = block_bitonic_sort(key, sh);
+  int n_sort = 32;
+  while (n_sort < a.cnt) n_sort <<= 1;
+  key = block_bitonic_sort(key, sh, n_sort);
   if (threadIdx.x < a.k) {
     sh_elite[threadIdx.x] = (uint32_t)(key & 0xffffffffu);
     if (a.elite_idx_out != nullptr) a.elite_idx_out[threadIdx.x] = (int32_t)(key & 0xffffffffu);
   }
   __syncthreads();
 
-  // column t: elite_Q[e, t] for e = 0..k-1 (rank order); mean then population std (tf.math.reduce_std)
+  // column t: elite_Q[e, t] for e = 0..k-1 (rank order); mean then population std (tf.math.reduce_std).  The elite rows are
+  // regenerated from the counter-based noise: one Philox block (4 consecutive steps of one elite) per thread into shared
+  // memory, then every column sums its k entries in rank order (same arithmetic as a per-column loop, 64x fewer Philox calls)
+  constexpr int kQCap = 8192;
+  __shared__ float sh_q[kQCap];
   float new_mu = 0.0f, new_sd = 0.0f, first_q = 0.0f;
   const int t = threadIdx.x;
-  if (t < a.H) {
+  const int H4 = (a.H + 3) >> 2, Hs = H4 * 4;
+  if (a.k * Hs <= kQCap) {
+    for (int item = threadIdx.x; item < a.k * H4; item += blockDim.x) {
+      const int e = item / H4, blk = item - e * H4;
+      float zz[4];
+      noise4(a.noise, sh_elite[e], (uint32_t)blk, zz);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int tt = blk * 4 + j;
+        if (tt < a.H) sh_q[e * Hs + tt] = cem_sample(a.mu[tt], a.sd[tt], zz[j], a.lo, a.hi);
+      }
+    }
+    __syncthreads();
+    if (t < a.H) {
+      float acc = 0.0f;
+      for (int e = 0; e < a.k; ++e) acc += sh_q[e * Hs + t];
+      first_q = sh_q[t];
+      new_mu = acc / (float)a.k;
+      float var = 0.0f;
+      for (int e = 0; e < a.k; ++e) {
+        const float d = sh_q[e * Hs + t] - new_mu;
+        var = fmaf(d, d, var);
+      }
+      new_sd = sqrtf(var / (float)a.k);
+    }
+  } else if (t < a.H) {  // k x H too large for the staging buffer: per-column regeneration
     const float mu = a.mu[t], sd = a.sd[t];
     float acc = 0.0f;
     for (int e = 0; e < a.k; ++e) {

@@ -8,11 +8,12 @@
 namespace ctk {
 
 
-// sort the 1024 keys of a block ascending; on return thread i holds the i-th smallest
-__device__ __forceinline__ uint64_t block_bitonic_sort(uint64_t key, uint64_t* sh /*[1024]*/) {
+// sort the 1024 keys of a block ascending; on return thread i holds the i-th smallest.  n_sort (power of two): only the first
+// n_sort threads hold real keys (the rest KEY_MAX), so the network can stop at subsequences of that size.
+__device__ __forceinline__ uint64_t block_bitonic_sort(uint64_t key, uint64_t* sh /*[1024]*/, int n_sort = TOPK_THREADS) {
   const int tid = threadIdx.x;
 #pragma unroll 1
-  for (int size = 2; size <= TOPK_THREADS; size <<= 1) {
+  for (int size = 2; size <= n_sort; size <<= 1) {
     const bool desc = (tid & size) != 0;  // direction of this thread's bitonic subsequence
 #pragma unroll 1
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
