@@ -17,18 +17,12 @@
 #pragma once
 #include "ctk_device.cuh"
 #include "ctk_kernels_mppi.cuh"
+#include "ctk_ode_scaled.cuh"
 
 namespace ctk {
 
-constexpr float kInvSqrt2 = 0.70710678118654752f;
-constexpr float kSqrt2 = 1.41421356237309505f;
-// period of T = angle/sqrt(2):  2*pi/sqrt(2) = sqrt(2)*pi, split hi + lo
-constexpr float kTPerHi = 4.44288301467895508f;      // fp32(sqrt(2)*pi)
-constexpr float kTPerLo = -7.6520588976e-08f;         // sqrt(2)*pi - fp32(sqrt(2)*pi)
-constexpr float kInvTPer = 0.22507907903927651f;     // 1/(sqrt(2)*pi)
-
-struct Roll {  // one rollout's registers
-  float T, W, c, s, x, V, omc, ul, acc, y0, dy, y1;
+struct Roll : ScaledState {  // one rollout's registers
+  float ul, acc, y0, dy, y1;
 };
 
 // One rollout step.  wj = j/period (immediate when PERIOD is a template constant).
@@ -44,56 +38,11 @@ __device__ __forceinline__ void ode_mppi_step(const MppiOdeArgs& a, const OdeHot
     p[4 * (size_t)a.N] = r.x; p[5 * (size_t)a.N] = r.V * k.inv_cFg;
     a.log_Q_soa[(size_t)t * a.N + n] = u;
   }
-  // ---- stage cost / (H+1)  (spec: DESIGN.md section 3; Cost_Functions/__init__.py:49-64) ----
-  const float d = r.x - k.target;
-  const float e = fmaxf(fabsf(r.x) - k.thl_095, 0.0f);  // indicator(|x| > 0.95 THL) * (|x| - 0.95 THL)
-  float acc = r.acc;
-  acc = fmaf(d * d, k.k_dd, acc);
-  acc = fmaf(e * e, k.k_bar, acc);
-  acc = fmaf(r.omc * r.omc, k.k_ep, acc);
-  if (KIND == 1) {
-    acc = fmaf(r.W * r.W, k.k_ekp2, acc);
-    acc += (fabsf(r.x) > k.thl_09) ? k.k_border : 0.0f;
-  }
-  // cc u^2 + ccrc (u - u_prev)^2 + MPPI correction (0.5 R u^2 + R u du)  ==  u (kA u + kB u_prev + kC du) + ccrc u_prev^2;
-  // the u_prev^2 terms telescope into kA (boundary terms are added once per rollout by the caller)
-  float q = u * k.kA;
-  q = fmaf(r.ul, k.kB, q);
-  q = fmaf(du, k.kC, q);
-  r.acc = fmaf(u, q, acc);
+  // stage cost / (H+1) (spec: DESIGN.md section 3; Cost_Functions/__init__.py:49-64) merged with the MPPI correction
+  // (optimizer_mppi.py:154-155), then the Euler step in scaled variables (ctk_ode_scaled.cuh)
+  r.acc = stage_cost_scaled<KIND>(r.acc, r, u, r.ul, du, k);
   r.ul = u;
-  // ---- Euler step with the old derivatives, scaled variables (see OdeHot) ----
-  float nn = fmaf(k.cUg, u, r.V);
-  const float ws = r.W * r.s;
-  nn = fmaf(-r.W, ws, nn);
-  const float t3 = fmaf(k.cTl2, r.W, r.s);
-  nn = fmaf(t3, r.c, nn);
-  const float Ap = fmaf(-r.c, r.c, k.K1p);
-  const float vd = nn * fast_rcp(Ap);
-  const float X = fmaf(vd, r.c, fmaf(k.kTm2, r.W, r.s));
-  float T = fmaf(r.W, k.h_T, r.T);
-  r.W = fmaf(X, k.h_W, r.W);
-  r.x = fmaf(r.V, k.h_x, r.x);
-  r.V = fmaf(vd, k.h_V, r.V);
-  // wrap: angle <- atan2(sin, cos)  ==  T - period * rint(T / period)
-  const float kk = rintf(T * kInvTPer);
-  T = fmaf(-kk, kTPerHi, T);
-  T = fmaf(-kk, kTPerLo, T);
-  r.T = T;
-  // half-angle sincos (ctk_math.cuh sincos_half with x = T)
-  const float tt = T * T;
-  float ps = fmaf(tt, kSinHalfLead, -2.4761327949818224e-05f);
-  ps = fmaf(tt, ps, 0.002083262661471963f);
-  ps = fmaf(tt, ps, -0.08333329111337662f);
-  const float sh = fmaf(T * tt, ps, T);
-  float pc = fmaf(tt, kCosHalfLead, 2.1885084606765304e-06f);
-  pc = fmaf(tt, pc, -0.0002455138601362705f);
-  pc = fmaf(tt, pc, 0.01473138015717268f);
-  pc = fmaf(tt, pc, -0.3535533845424652f);
-  const float ch = fmaf(tt, pc, 1.4142135381698608f);
-  r.omc = sh * sh;
-  r.c = fmaf(-sh, sh, 1.0f);
-  r.s = sh * ch;
+  ode_step_scaled(r, u, k);
 }
 
 template <int KIND, bool LOG, int PERIOD, int ILP, int MAXT>
@@ -210,10 +159,8 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
         p[0] = th; p[a.N] = r[q].W * k.inv_beta; p[2 * (size_t)a.N] = r[q].c; p[3 * (size_t)a.N] = r[q].s;
         p[4 * (size_t)a.N] = r[q].x; p[5 * (size_t)a.N] = r[q].V * k.inv_cFg;
       }
-      const float term = (fabsf(th) > 0.2f || fabsf(r[q].x - k.target) > k.thl_01) ? k.k_term : 0.0f;
-      // Cost_Functions/__init__.py:90-92 (mean over H+1 incl. the terminal cost); the last step's telescoped
-      // ccrc u^2 term is removed again; optimizer_mppi.py:160
-      const float S = (fmaf(-k.k_ccrc * r[q].ul, r[q].ul, r[q].acc) + term) - k.shift;
+      // Cost_Functions/__init__.py:90-92 (mean over H+1 incl. the terminal cost); optimizer_mppi.py:160
+      const float S = finish_cost_scaled(r[q].acc, r[q], r[q].ul, k);
       if (active[q]) {
         a.J[n[q]] = S;
         if (S < INFINITY) {

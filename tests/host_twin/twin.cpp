@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "../../control_toolkit_b200/csrc/ctk_derive.h"
+#include "../../control_toolkit_b200/csrc/ctk_ode_scaled.cuh"
 
 using namespace ctk;
 
@@ -59,5 +60,30 @@ void twin_grad(const float* s0, const float* Q, int N, int H, const ctk_ode_para
     }
   }
   delete[] tape;
+}
+
+// K1's scaled-variable arithmetic (ctk_ode_scaled.cuh + derive_ode_hot): S[n] = total MPPI cost of rollout n (trajectory cost +
+// control-cost correction, optimizer_mppi.py:154-161) for given clipped controls u and unclipped perturbations du [N][H];
+// traj (optional) [N][H+1][6] in the reference's unscaled variables.
+void twin_rollout_scaled(const float* s0, const float* U, const float* dU, int N, int H, const ctk_ode_params* op, const ctk_cost_params* cp,
+                         float u_prev, float cc_weight, float coef_du2, float R, float half_R, float* S, float* traj) {
+  OdeHot k;
+  MppiCorr mc{(double)cc_weight, (double)coef_du2, (double)R, (double)half_R, -0.01, 1.0, -1.0, 1.0};
+  derive_ode_hot(*op, *cp, H, mc, k);
+  for (int n = 0; n < N; ++n) {
+    ScaledState r;
+    scaled_from_state(s0, k, r);
+    float ul = u_prev, acc = (k.k_ccrc * u_prev) * u_prev;
+    for (int t = 0; t < H; ++t) {
+      if (traj) scaled_to_state(r, k, traj + ((size_t)n * (H + 1) + t) * 6);
+      const float u = U[(size_t)n * H + t], du = dU[(size_t)n * H + t];
+      acc = cp->kind == 0 ? stage_cost_scaled<0>(acc, r, u, ul, du, k) : stage_cost_scaled<1>(acc, r, u, ul, du, k);
+      acc = fmaf(du * du, k.k_du2, acc);  // the kernel uses the per-segment closed form of this sum
+      ul = u;
+      ode_step_scaled(r, u, k);
+    }
+    if (traj) scaled_to_state(r, k, traj + ((size_t)n * (H + 1) + H) * 6);
+    S[n] = finish_cost_scaled(acc, r, ul, k);
+  }
 }
 }

@@ -69,3 +69,31 @@ def test_adjoint_matches_autograd(twin, cost_name):
         for n in range(N):
             scale = np.abs(go[n]).max()
             assert np.abs(g[n] - go[n]).max() / scale < 2e-4, (n, np.abs(g[n] - go[n]).max(), scale)
+
+
+@pytest.mark.parametrize("cost_name", ["default", "quadratic_boundary_grad"])
+def test_scaled_variable_rollout_matches_spec(twin, cost_name):
+    """The MPPI/ODE kernel's arithmetic (ctk_ode_scaled.cuh: scaled state variables, merged control terms, telescoped
+    control-change cost) and derive_ode_hot against the oracle spec: trajectories and the total MPPI cost
+    S = trajectory cost + sum_t cc (0.5 (1 - 1/NU) R du^2 + R u du + 0.5 R u^2)   (optimizer_mppi.py:154-161)."""
+    N, H = 64, 100
+    rng = np.random.default_rng(9)
+    f = np.float32
+    cc, R, NU = f(1.0), f(1.0), f(1000.0)
+    coef_du2 = f(f(0.5) * (f(1) - f(1.0) / NU)) * R
+    for s0 in spec.synthetic_states(4, seed=11):
+        dU = (rng.standard_normal((N, H)) * 0.2).astype(np.float32)
+        U = np.clip(rng.uniform(-0.5, 0.5, (1, H)).astype(np.float32) + dU, -1, 1).astype(np.float32)
+        ode, cost = _params(cost_name)
+        S = np.zeros(N, np.float32)
+        traj = np.zeros((N, H + 1, 6), np.float32)
+        twin.twin_rollout_scaled(_fp(s0), _fp(U), _fp(dU), N, H, C.byref(ode), C.byref(cost), C.c_float(0.3), C.c_float(cc),
+                                 C.c_float(coef_du2), C.c_float(R), C.c_float(f(0.5) * R), _fp(S), _fp(traj))
+        ro = spec.ODEPredictor().predict_core(torch.from_numpy(np.tile(s0, (N, 1))), torch.from_numpy(U[..., None]))
+        Jo = spec.trajectory_cost(ro, torch.from_numpy(U[..., None]), 0.3, spec.CostParams(name=cost_name)).numpy().astype(np.float64)
+        corr = (cc * (0.5 * (1 - 1.0 / 1000.0) * R * dU.astype(np.float64) ** 2 + R * U.astype(np.float64) * dU + 0.5 * R * U.astype(np.float64) ** 2)).sum(1)
+        So = Jo + corr
+        for c in range(6):
+            scale = max(np.abs(ro[..., c].numpy()).max(), 1e-6)
+            assert np.abs(traj[..., c] - ro[..., c].numpy()).max() / scale < 4e-4, c
+        assert np.max(np.abs(S - So) / (np.abs(So) + 1e-3)) < 2e-4
