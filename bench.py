@@ -41,15 +41,30 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 
-FLOP_PER_ROLLOUT_STEP = {"mppi_ode": 80.0, "cem_ode": 65.0}  # SURVEY.md 8d convention, re-derived in DESIGN.md
+FLOP_PER_ROLLOUT_STEP = {"mppi_ode": 80.0, "cem_ode": 65.0, "rpgd_grad": 200.0, "rpgd_fwd": 66.0}  # SURVEY.md 8d convention
 MPPI_CFG = dict(seed=42, mpc_timestep=0.02, cc_weight=1.0, R=1.0, LBD=100.0, NU=1000.0, SQRTRHOINV=0.03,
                 period_interpolation_inducing_points=10)
+CEM_CFG = dict(seed=42, mpc_timestep=0.02, cem_outer_it=3, cem_initial_action_stdev=0.5, cem_stdev_min=0.01, cem_best_k=64,
+               warmup=False, warmup_iterations=250)
+RPGD_CFG = dict(seed=42, mpc_timestep=0.02, SAMPLING_DISTRIBUTION="uniform", period_interpolation_inducing_points=10,
+                learning_rate=0.05, adam_beta_1=0.9, adam_beta_2=0.999, adam_epsilon=1e-08, gradmax_clip=5, rtol=0.001,
+                opt_keep_k_ratio=0.25, outer_its=2, resamp_per=10, sample_stdev=0.5, sample_mean=0.0,
+                sample_whole_control_space=True, uniform_dist_min=-1.0, uniform_dist_max=1.0, shift_previous=1, warmup=False,
+                warmup_iterations=250)
 WORKLOADS = {
     # name: (optimizer, predictor, cost, N_global, H)
     "mppi_ode_1m": ("mppi", "ODE", "default", 1_000_000, 100),   # BASELINE configs[4] (the metric's config)
     "mppi_ode_c1": ("mppi", "ODE", "default", 2000, 50),         # configs[0]
+    "cem_ode_c2": ("cem-tf", "ODE", "default", 4096, 50),        # configs[1]
+    "rpgd_ode_c3": ("rpgd", "ODE", "quadratic_boundary_grad", 32, 50),  # configs[2]
     "mppi_mlp_c4": ("mppi", "Dense-6IN-128H1-128H2-5OUT-0", "default", 65536, 100),  # configs[3]
 }
+OPT_CFG = {"mppi": MPPI_CFG, "cem-tf": CEM_CFG, "rpgd": RPGD_CFG}
+
+
+def passes_per_tick(opt_name):
+    """rollout passes one optimizer.step() makes over the population (CEM cem_outer_it; RPGD fwd+bwd per Adam step + 1)."""
+    return {"mppi": 1, "cem-tf": CEM_CFG["cem_outer_it"], "rpgd": 2 * RPGD_CFG["outer_its"] + 1}[opt_name]
 
 
 def _emit(line: dict) -> None:
@@ -117,14 +132,14 @@ def build_controller(workload, shard=None, device=0, logging=False, n_override=N
     N = n_override or N
     if pred.startswith("Dense"):
         ctk.register_mlp(pred, ctk.MLPSpec.random_init(2))
-    cfg = dict(MPPI_CFG, mpc_horizon=H, num_rollouts=N, shard=shard, device_index=device)
+    cfg = dict(OPT_CFG[opt_name], mpc_horizon=H, num_rollouts=N, shard=shard, device_index=device)
     if pred.startswith("Dense"):
         cfg["mlp_engine"] = mlp_engine
     ctrl = controller_mpc("CartPole", (np.array([-1.0], np.float32), np.array([1.0], np.float32)),
                           {"target_position": 0.0, "target_equilibrium": 1.0},
                           config_controller=dict(optimizer=opt_name, predictor_specification=pred, cost_function_specification=cost,
                                                  controller_logging=logging, calculate_optimal_trajectory=False),
-                          config_optimizers={opt_name: cfg}, config_cost_function={"cost_function_name_default": "default"})
+                          config_optimizers={opt_name: cfg}, config_cost_function={"cost_function_name_default": cost})
     ctrl.configure(optimizer_name=opt_name, predictor_specification=pred)
     return ctrl, N, H
 
@@ -133,15 +148,18 @@ def build_controller(workload, shard=None, device=0, logging=False, n_override=N
 # CPU arm: the oracle port of the reference's MPPI on the host cores
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_mppi_rate(workload, n_sample, ticks, warm=1):
-    """rollout-steps/s of oracle.mppi.MPPIOracle (restatement of reference optimizer_mppi.py, torch-CPU fp32)."""
+    """rollout-steps/s of the oracle port of the reference optimizer (oracle/{mppi,cem,rpgd}.py, torch-CPU fp32)."""
     import torch
     from oracle import spec
+    from oracle.cem import CEMOracle
     from oracle.mppi import MPPIOracle
+    from oracle.rpgd import RPGDOracle
     torch.set_num_threads(os.cpu_count() or 1)
-    _, pred, cost, _, H = WORKLOADS[workload]
+    opt_name, pred, cost, _, H = WORKLOADS[workload]
     predictor = spec.ODEPredictor() if pred == "ODE" else spec.MLPPredictor(spec.MLPWeights.random_init(2))
-    o = MPPIOracle(predictor, spec.CostParams(name=cost), mpc_horizon=H, num_rollouts=n_sample,
-                   **{k: v for k, v in MPPI_CFG.items() if k != "seed"})
+    cls = {"mppi": MPPIOracle, "cem-tf": CEMOracle, "rpgd": RPGDOracle}[opt_name]
+    o = cls(predictor, spec.CostParams(name=cost), mpc_horizon=H, num_rollouts=n_sample,
+            **{k: v for k, v in OPT_CFG[opt_name].items() if k != "seed"})
     g = torch.Generator().manual_seed(42)
 
     class _Rng:  # the reference's torch rng duck type (others/globals_and_utils.py:61-82)
@@ -149,6 +167,12 @@ def cpu_mppi_rate(workload, n_sample, ticks, warm=1):
         def normal(shape, dtype=torch.float32, mean=0.0, stddev=1.0):
             return torch.normal(mean=mean, std=stddev, size=tuple(shape), generator=g, dtype=dtype)
 
+        @staticmethod
+        def uniform(shape, dtype=torch.float32, minval=0.0, maxval=1.0):
+            return torch.rand(tuple(shape), generator=g, dtype=dtype) * (maxval - minval) + minval
+
+    if opt_name == "rpgd":
+        o.reset(_Rng)
     states = synthetic_states(ticks + warm, 0)
     times = []
     for t in range(ticks + warm):
@@ -156,21 +180,21 @@ def cpu_mppi_rate(workload, n_sample, ticks, warm=1):
         o.step(states[t], _Rng)
         if t >= warm:
             times.append(time.perf_counter() - t0)
-    return n_sample * H / statistics.mean(times), statistics.mean(times), torch.get_num_threads()
+    return n_sample * H * passes_per_tick(opt_name) / statistics.mean(times), statistics.mean(times), torch.get_num_threads()
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    _, _, _, N, H = WORKLOADS[args.workload]
+    opt_name, _, _, N, H = WORKLOADS[args.workload]
     n_sample = min(N, args.cpu_sample)
     rate, sec, threads = cpu_mppi_rate(args.workload, n_sample, args.steps, args.warmup)
-    sample = f"{args.steps} ticks of {n_sample} rollouts x H={H} (of {N}) per step, oracle port of optimizer_mppi.py, torch-CPU fp32"
+    sample = f"{args.steps} ticks of {n_sample} rollouts x H={H} (of {N}) per step, oracle port of the reference's optimizer_{opt_name.replace('-', '_')}.py, torch-CPU fp32"
     line = {"impl": "reference", "metric": "rollout-steps/s", "value": rate, "unit": "rollout-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "optimizer": "mppi", "num_rollouts": N, "mpc_horizon": H, "predictor": WORKLOADS[args.workload][1]},
+            "config": {"workload": args.workload, "optimizer": opt_name, "num_rollouts": N, "mpc_horizon": H, "predictor": WORKLOADS[args.workload][1]},
             "cpu_baseline": {"value": rate, "unit": "rollout-steps/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "rollout-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -245,7 +269,9 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(total_ms.item()) / K
-    value = N * H / (ms_per_step * 1e-3)
+    opt_name = WORKLOADS[args.workload][0]
+    passes = passes_per_tick(opt_name)
+    value = N * H * passes / (ms_per_step * 1e-3)
 
     # ---- e2e through the public plugin API: host state in, host control out, every step ----
     host_states = synthetic_states(K + W, 1)
@@ -262,7 +288,7 @@ def run_ours(args):
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = N * H * K / float(e2e_s.item())
+    e2e_value = N * H * passes * K / float(e2e_s.item())
 
     if rank == 0:
         # ---- roofline of the dominant kernel (K1 fused rollout), measured live above ----
@@ -282,6 +308,27 @@ def run_ours(args):
                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, cuBLAS 8192^3)" if peaks else "fallback 1648",
                         "flop_per_rollout_step": fl_step, "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms / ms_per_step,
                         "tensor_flop_issued_per_algorithmic": 6.0 * 32768.0 / fl_step if args.mlp_engine == "tcgen05" else 0.0}
+        elif opt_name == "cem-tf":
+            fl_step = FLOP_PER_ROLLOUT_STEP["cem_ode"]
+            peak, clk = C.c_double(), C.c_double()
+            L.check(lib.ctk_fp32_peak(local_rank, C.byref(peak), C.byref(clk)))
+            achieved = fl_step * n_local * H / (k1_ms * 1e-3) / 1e12  # k1_ms: average over the cem_outer_it rollout launches of a tick
+            roofline = {"bound": "fp32", "kernel": "cem_rollout_kernel<OdePred> (one launch per outer iteration)", "achieved": achieved,
+                        "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": None,
+                        "peak_source": "measured live: FP32 FMA-chain microbenchmark (ctk_fp32_peak)", "flop_per_rollout_step": fl_step,
+                        "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms * passes / ms_per_step,
+                        "note": "4096 rollouts occupy 32 of 148 SMs with one warp per scheduler: the tick is launch- and latency-bound"}
+        elif opt_name == "rpgd":
+            its = RPGD_CFG["outer_its"]
+            fl_launch = (FLOP_PER_ROLLOUT_STEP["rpgd_grad"] * its + FLOP_PER_ROLLOUT_STEP["rpgd_fwd"]) * n_local * H
+            peak, clk = C.c_double(), C.c_double()
+            L.check(lib.ctk_fp32_peak(local_rank, C.byref(peak), C.byref(clk)))
+            achieved = fl_launch / (k1_ms * 1e-3) / 1e12
+            roofline = {"bound": "fp32", "kernel": "rpgd_grad_kernel (all Adam iterations + the final rollout of a tick in one launch)",
+                        "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": None,
+                        "peak_source": "measured live: FP32 FMA-chain microbenchmark (ctk_fp32_peak)",
+                        "flop_per_launch": fl_launch, "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms / ms_per_step,
+                        "note": "32 trajectories = one warp: a serial dependency chain of 5 x 50 steps, latency-bound by construction"}
         else:
             flop = FLOP_PER_ROLLOUT_STEP["mppi_ode"] * n_local * H
             peak, clk = C.c_double(), C.c_double()
@@ -300,18 +347,18 @@ def run_ours(args):
         n_sample = min(N, args.cpu_sample)
         rate, sec, threads = cpu_mppi_rate(args.workload, n_sample, 2, 1)
         cpu = {"value": rate, "unit": "rollout-steps/s", "cores": threads, "kind": "port",
-               "sample": f"2 ticks of {n_sample} rollouts x H={H} (of {N}); oracle port of reference optimizer_mppi.py, torch-CPU fp32; "
+               "sample": f"2 ticks of {n_sample} rollouts x H={H} (of {N}); oracle port of reference optimizer_{opt_name.replace('-', '_')}.py, torch-CPU fp32; "
                          f"{sec:.2f} s/tick"}
         line = {"metric": "rollout-steps/s", "value": value, "unit": "rollout-steps/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": args.workload, "optimizer": "mppi", "num_rollouts": N, "mpc_horizon": H,
-                           "predictor": WORKLOADS[args.workload][1], "cost": "default", "noise": "in-kernel Philox4x32-10",
+                "config": {"workload": args.workload, "optimizer": opt_name, "rollout_passes_per_tick": passes, "num_rollouts": N, "mpc_horizon": H,
+                           "predictor": WORKLOADS[args.workload][1], "cost": WORKLOADS[args.workload][2], "noise": "in-kernel Philox4x32-10",
                            **({"mlp_engine": args.mlp_engine} if WORKLOADS[args.workload][1].startswith("Dense") else {}),
                            "parallelism": f"rollouts sharded over {world} GPU(s); exchange per tick: {getattr(opt, '_exchange', 'none')} "
                                           f"({'in-kernel NVLink mailbox stores, ' if getattr(opt, '_exchange', '') == 'p2p' else ''}{H // 10 + 3} floats per shard)",
                            "l2": "flushed between timed ticks (256 MiB memset); inputs are 24 B per tick"},
-                "e2e": {"value": e2e_value, "unit": "rollout-steps/s", "h2d_bytes_per_step": 24, "d2h_bytes_per_step": 4 + 4 * H,
+                "e2e": {"value": e2e_value, "unit": "rollout-steps/s", "h2d_bytes_per_step": 24, "d2h_bytes_per_step": (8 + 4 * H) if opt_name == "mppi" else 8,
                         "p50_step_latency_ms": statistics.median(lat) * 1e3, "api": "controller_mpc.step(s_host) -> u_host"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "wall_s_timed_region": wall}
