@@ -615,8 +615,16 @@ static int cem_local(ctk_handle* h, const float* s_dev, bool to_k) {
     if (h->cem_iters < 1) return fail(CTK_EINVAL, "CEM iteration count < 1");
     h->elite_log_rows = 0;
   }
+  const int uni = c.cem_uniform_actions ? 1 : 0;
+  if (uni && h->cem_it == 0) {
+    // random shooting: Q = z (high - low) + low with z ~ U[0,1)  ==  the CEM sample clip(mu + z sd) with mu = low, sd = high - low
+    std::vector<float> mu((size_t)h->H, c.action_low), sd((size_t)h->H, c.action_high - c.action_low);
+    CU(cudaMemcpyAsync(h->d_mu, mu.data(), sizeof(float) * h->H, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_sd, sd.data(), sizeof(float) * h->H, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));  // mu / sd are stack-lifetime host vectors
+  }
   NoiseSrc ns{};
-  int rcn = make_noise(h, STREAM_CEM | ((uint32_t)h->cem_it << 8), h->H, 0, (size_t)h->NG, &ns);
+  int rcn = make_noise(h, STREAM_CEM | ((uint32_t)h->cem_it << 8), h->H, uni, (size_t)h->NG, &ns);
   if (rcn != CTK_OK) return rcn;
   h->cem_noise = ns;
   CemArgs a{};

@@ -119,7 +119,9 @@ typedef struct ctk_config {
   float rpgd_learning_rate, rpgd_gradmax_clip;
   double rpgd_beta_1, rpgd_beta_2, rpgd_epsilon;
   int32_t mlp_engine;             /* CTK_MLP_*                                                                   */
-  int32_t reserved[7];
+  int32_t cem_uniform_actions;    /* 1: random shooting (reference optimizer_random_action_tf.py:56-68): every tick samples
+                                     Q ~ U[action_low, action_high) instead of N(dist_mue, stdev); use cem_outer_it = cem_best_k = 1 */
+  int32_t reserved[6];
 } ctk_config;
 
 typedef struct ctk_handle ctk_handle;

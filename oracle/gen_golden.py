@@ -1,7 +1,7 @@
 """oracle.gen_golden -- TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz.
 
 Runs the reference's UNMODIFIED ``controller_mpc`` + ``optimizer_mppi`` / ``optimizer_rpgd`` /
-``optimizer_cem_tf`` files (imported from /root/reference through the shims in oracle/refharness) on
+``optimizer_cem_tf`` / ``optimizer_random_action_tf`` files (imported from /root/reference through the shims in oracle/refharness) on
 torch-CPU fp32 with the build's pinned predictor / cost spec and INJECTED noise, and stores inputs +
 outputs as small fixtures.  Must be run in the build container (needs /root/reference):
 
@@ -64,6 +64,11 @@ CASES = {
     "rpgd_warmup_n64": ("rpgd", "ODE", "quadratic_boundary_grad",
                         _c(RPGD_BASE, num_rollouts=64, warmup=True, warmup_iterations=6, resamp_per=2,
                            period_interpolation_inducing_points=5), 4, False),
+    # reference Optimizers/optimizer_random_action_tf.py (sibling optimizer on the same kernels)
+    "random_action_n512": ("random-action-tf", "ODE", "default",
+                           dict(seed=42, mpc_horizon=50, mpc_timestep=0.02, num_rollouts=512), 3, True),
+    "random_action_n4096_h30": ("random-action-tf", "ODE", "default",
+                                dict(seed=42, mpc_horizon=30, mpc_timestep=0.02, num_rollouts=4096), 2, False),
     "mppi_mlp_c4_n256": ("mppi", "Dense-6IN-128H1-128H2-5OUT-0", "default",
                          _c(MPPI_BASE, num_rollouts=256, mpc_horizon=100), 2, False),
     "mppi_mlp_h50_n64": ("mppi", "Dense-6IN-128H1-128H2-5OUT-0", "default",
@@ -87,7 +92,7 @@ def run_reference_case(name: str) -> dict:
 
     # controller config is read at controller construction time (reference Controllers/__init__.py:39)
     cc = dict(mpc=dict(optimizer=opt_name, predictor_specification=pred_spec, cost_function_specification=cost_name,
-                       computation_library="tensorflow" if opt_name == "cem-tf" else "pytorch", device="cpu",
+                       computation_library="tensorflow" if opt_name.endswith("-tf") else "pytorch", device="cpu",
                        controller_logging=True, calculate_optimal_trajectory=False))
     with open(os.path.join("Control_Toolkit_ASF", "config_controllers.yml"), "w") as f:
         yaml.safe_dump(cc, f)
@@ -113,7 +118,7 @@ def run_reference_case(name: str) -> dict:
         # tick (Optimizers/__init__.py:35) and has no .copy() (Controllers/__init__.py:177) -> give it a numpy 0.
         opt.u = np.float32(0.0)
 
-    if opt_name == "cem-tf":
+    if opt_name in ("cem-tf", "random-action-tf"):
         import tensorflow as tfshim
         argsort_log = []
         _orig = tfshim.argsort
@@ -149,6 +154,10 @@ def run_reference_case(name: str) -> dict:
             out[f"sorted_gap_{t}"] = np.array([float(np.sort(np.asarray(lv["J_logged"]))[k] -
                                                       np.sort(np.asarray(lv["J_logged"]))[k - 1])], np.float32)
             argsort_log.clear()
+        elif opt_name == "random-action-tf":
+            out[f"J_{t}"] = np.asarray(lv["J_logged"]).copy()
+            out[f"best_idx_{t}"] = np.array([int(argsort_log[-1][0])], np.int64)  # tf.argsort(traj_cost)[0]  (:66-67)
+            argsort_log.clear()
         elif opt_name == "rpgd":
             step, m, v = opt.opt.get_weights()
             out[f"Q_{t}"] = opt.Q_tf.numpy().copy()
@@ -170,7 +179,7 @@ def run_reference_case(name: str) -> dict:
         acc += float(np.sum(chk.standard_draws(kind, shape).astype(np.float64)))
     out["noise_checksum"] = np.array([acc], np.float64)
 
-    if opt_name == "cem-tf":
+    if opt_name in ("cem-tf", "random-action-tf"):
         tfshim.argsort = _orig
     return out
 

@@ -160,6 +160,28 @@ def test_cem_matches_reference_golden(name):
         np.testing.assert_array_equal(got_elite[-1], np.argsort(J, kind="stable")[:k])
 
 
+@pytest.mark.parametrize("name", golden_names("random_action_"))
+def test_random_action_matches_reference_golden(name):
+    """Random shooting (reference Optimizers/optimizer_random_action_tf.py) on the CEM kernels with a uniform
+    sampling distribution: the chosen rollout index must be IDENTICAL, u (one of the sampled controls) bit-exact."""
+    z, meta = load_golden(name)
+    ctrl = make_controller(meta)
+    opt = ctrl.optimizer
+    floors = fp32_noise_floor(name)
+    for t in range(meta["ticks"]):
+        u = ctrl.step(z["states"][t], time=0.02 * t)
+        e_J = max_elem_rel(opt.logging_values["J_logged"], z[f"J_{t}"])
+        _report(f"{name} tick {t}: best {opt.best_index} (ref {int(z[f'best_idx_{t}'][0])}) u {float(u):.7f} J {e_J:.2e}")
+        assert np.ndim(u) == 0
+        assert opt.best_index == int(z[f"best_idx_{t}"][0])
+        assert float(u) == float(z[f"u_{t}"][0])
+        _check_J(opt.logging_values["J_logged"], z[f"J_{t}"], floors[t], (name, t))
+        if t == 0 and "rollouts_0" in z:
+            assert max_rel(opt.logging_values["Q_logged"], z["Q_logged_0"]) == 0.0
+            e_tr = max(max_rel(opt.logging_values["rollout_trajectories_logged"][..., c], z["rollouts_0"][..., c]) for c in range(6))
+            assert e_tr < TOL_TRAJ
+
+
 @pytest.mark.parametrize("name", golden_names("rpgd_"))
 def test_rpgd_matches_reference_golden(name):
     """adam_form='torch' reproduces the reference's runnable (torch) branch, optimizer_rpgd.py:56-82."""

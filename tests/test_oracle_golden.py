@@ -84,3 +84,20 @@ def test_rpgd_keras_vs_torch_adam_form():
         u = o.step(z["states"][t], rng)
         assert rel_err(u, z[f"u_{t}"]) < 5e-2
         assert rel_err(o.Q.numpy(), z[f"Q_{t}"]) < 5e-2
+
+
+@pytest.mark.parametrize("name", golden_names("random_action_"))
+def test_random_action_oracle_matches_reference(name):
+    """oracle/random_action.py vs the unmodified reference Optimizers/optimizer_random_action_tf.py."""
+    z, meta = load_golden(name)
+    o = make_oracle(meta)
+    rng = replay(meta)
+    o.reset(rng)  # the reference draws (and discards) one population in optimizer_reset
+    for t in range(meta["ticks"]):
+        u = o.step(z["states"][t], rng)
+        assert o.last["best_idx"] == int(z[f"best_idx_{t}"][0])
+        assert rel_err(u, z[f"u_{t}"]) == 0.0  # u is one of the sampled controls: bit-exact
+        assert rel_err(o.last["J"], z[f"J_{t}"]) < TOL
+        if t == 0 and "rollouts_0" in z:
+            assert rel_err(o.last["rollouts"], z["rollouts_0"]) < TOL
+            assert rel_err(o.last["Q"], z["Q_logged_0"]) == 0.0
