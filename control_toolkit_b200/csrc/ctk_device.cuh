@@ -27,9 +27,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 
-// four consecutive standard draws (index 4*blk .. 4*blk+3) of global rollout n
+// four consecutive standard draws (index 4*blk .. 4*blk+3) of global rollout n.  INJ = false: the caller guarantees Philox
+// mode (ns.inj == nullptr), the injected-noise branch is compiled out (hot kernels)
+template <bool INJ = true>
 __device__ __forceinline__ void noise4(const NoiseSrc& ns, uint32_t n_global, uint32_t blk, float out[4]) {
-  if (ns.inj != nullptr) {
+  if (INJ && ns.inj != nullptr) {
     const float* row = ns.inj + (size_t)n_global * ns.per_rollout;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {

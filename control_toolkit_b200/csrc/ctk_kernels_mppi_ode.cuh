@@ -45,7 +45,8 @@ __device__ __forceinline__ void ode_mppi_step(const MppiOdeArgs& a, const OdeHot
   ode_step_scaled(r, u, k);
 }
 
-template <int KIND, bool LOG, int PERIOD, int ILP, int MAXT>
+// INJ: injected-noise mode possible (verification); the production instantiations compile that branch out.
+template <int KIND, bool LOG, int PERIOD, int ILP, int MAXT, bool INJ>
 __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
   extern __shared__ float smem[];
   const int T_ = blockDim.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = T_ >> 5;
@@ -62,13 +63,33 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
     if (a.trace != nullptr && tid == 0) a.trace[(size_t)blockIdx.x * 8 + slot] = globaltimer_ns();
   };
   trace(0);
-  // ---- prologue: the only global reads before the loop, issued together ----
+  // ---- prologue: the only global reads before the loop are issued first and consumed last -- the Philox draws of the first
+  //      rollout group are generated while they are in flight (after the L2 flush they come from DRAM) ----
   const float s0v = (tid < 6) ? a.s0[tid] : 0.0f;
   const float upv = a.u_prev[0];
-  for (int t = tid; t < a.H; t += T_) sh_unom[t] = a.u_nom[min(t + 1, a.H - 1)];  // optimizer_mppi.py:184
+  const float unom_first = (tid < a.H) ? a.u_nom[min(tid + 1, a.H - 1)] : 0.0f;  // optimizer_mppi.py:184 (shift on read)
+  const OdeHot& k = a.k;
+  const int nblk = (a.n_ind + 3) >> 2;
+  auto gen_noise = [&](int base) {  // K0: draws of the ILP rollouts of a group -> shared-memory stash
+#pragma unroll
+    for (int q = 0; q < ILP; ++q) {
+      const int nq = base + q * T_ + tid;
+      const uint32_t ng = (uint32_t)(a.off + (nq < a.N ? nq : 0));
+      float* sz = sh_z + q * T_ + tid;
+      for (int blk = 0; blk < nblk; ++blk) {
+        float zz[4];
+        noise4<INJ>(a.noise, ng, (uint32_t)blk, zz);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (blk * 4 + e < a.n_ind) sz[(size_t)(blk * 4 + e) * ILP * T_] = zz[e];
+      }
+    }
+  };
+  gen_noise(blockIdx.x * T_ * ILP);
+  if (tid < a.H) sh_unom[tid] = unom_first;
+  for (int t = tid + T_; t < a.H; t += T_) sh_unom[t] = a.u_nom[min(t + 1, a.H - 1)];
   for (int j = tid; j < period; j += T_) sh_w[j] = (float)j / (float)period;      // Interpolator.py:63-74
   if (tid < 6) sh_red[tid] = s0v;
-  const OdeHot& k = a.k;
   for (int i = 0; i < a.n_ind; ++i) sh_acc[(size_t)i * T_ + tid] = 0.0f;
   __syncthreads();
   const float th0 = sh_red[0], om0 = sh_red[1], c0 = sh_red[2], sn0 = sh_red[3], x0 = sh_red[4], v0 = sh_red[5];
@@ -82,7 +103,6 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
   const float segW1x2_full = pf - 1.0f;                                             // 2 sum_j j/p
   const float segW2_full = (pf - 1.0f) * (2.0f * pf - 1.0f) / (6.0f * pf);          // sum_j (j/p)^2
   const int stride = gridDim.x * T_ * ILP;
-  const int nblk = (a.n_ind + 3) >> 2;
   float rho_t = INFINITY, a_t = 0.0f;  // per-thread online softmin (optimizer_mppi.py:163-168, exact combine later)
   float* sa = sh_acc + tid;
 
@@ -90,20 +110,12 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
     Roll r[ILP];
     int n[ILP];
     bool active[ILP];
-    // ---- K0: draws of the ILP rollouts -> shared-memory stash ----
+    if (base != (int)(blockIdx.x * T_ * ILP)) gen_noise(base);  // the first group's draws were generated in the prologue
 #pragma unroll
     for (int q = 0; q < ILP; ++q) {
       n[q] = base + q * T_ + tid;
       active[q] = n[q] < a.N;
-      const uint32_t ng = (uint32_t)(a.off + (active[q] ? n[q] : 0));
-      float* sz = sh_z + q * T_ + tid;
-      for (int blk = 0; blk < nblk; ++blk) {
-        float zz[4];
-        noise4(a.noise, ng, (uint32_t)blk, zz);
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (blk * 4 + e < a.n_ind) sz[(size_t)(blk * 4 + e) * ILP * T_] = zz[e];
-      }
+      const float* sz = sh_z + q * T_ + tid;
       r[q].T = T0; r[q].W = W0; r[q].c = c0; r[q].s = sn0; r[q].x = x0; r[q].V = V0; r[q].omc = omc0;
       r[q].ul = upv;
       r[q].acc = (k.k_ccrc * upv) * upv;  // telescoped ccrc term of u_{-1}

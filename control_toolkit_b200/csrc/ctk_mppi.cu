@@ -31,9 +31,9 @@ int mppi_max_block_threads(int pred) { return pred == 0 ? OdePred::kMaxThreads :
 size_t mppi_pred_smem_floats(int pred, const MlpDev& m) { return pred == 0 ? 0 : (pred == 2 ? MlpTcPred::smem_floats(m) : MlpSimtPred::smem_floats(m)); }
 
 // K1 for the ODE predictor (ctk_kernels_mppi_ode.cuh).  period_t: 10 -> the segment-unrolled instantiation, else runtime period.
-template <int KIND, bool LOG, int PERIOD, int ILP>
+template <int KIND, bool LOG, int PERIOD, int ILP, bool INJ>
 static cudaError_t launch_mppi_ode_t(int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a) {
-  auto k = mppi_ode_kernel<KIND, LOG, PERIOD, ILP, 1024>;
+  auto k = mppi_ode_kernel<KIND, LOG, PERIOD, ILP, 1024, INJ>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -41,11 +41,14 @@ static cudaError_t launch_mppi_ode_t(int grid, int block, size_t smem, cudaStrea
   k<<<grid, block, smem, st>>>(a);
   return cudaGetLastError();
 }
+// production instantiations: no logging, Philox noise only; logging or injected noise (verification) run the generic-period,
+// one-rollout-per-thread instantiation
 template <int KIND>
 static cudaError_t launch_mppi_ode_k(bool log, int period_t, int ilp, int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a) {
-  if (log) return launch_mppi_ode_t<KIND, true, 0, 1>(grid, block, smem, st, a);
-  if (period_t == 10) return ilp == 2 ? launch_mppi_ode_t<KIND, false, 10, 2>(grid, block, smem, st, a) : launch_mppi_ode_t<KIND, false, 10, 1>(grid, block, smem, st, a);
-  return ilp == 2 ? launch_mppi_ode_t<KIND, false, 0, 2>(grid, block, smem, st, a) : launch_mppi_ode_t<KIND, false, 0, 1>(grid, block, smem, st, a);
+  if (log) return launch_mppi_ode_t<KIND, true, 0, 1, true>(grid, block, smem, st, a);
+  if (a.noise.inj != nullptr) return launch_mppi_ode_t<KIND, false, 0, 1, true>(grid, block, smem, st, a);
+  if (period_t == 10) return ilp == 2 ? launch_mppi_ode_t<KIND, false, 10, 2, false>(grid, block, smem, st, a) : launch_mppi_ode_t<KIND, false, 10, 1, false>(grid, block, smem, st, a);
+  return ilp == 2 ? launch_mppi_ode_t<KIND, false, 0, 2, false>(grid, block, smem, st, a) : launch_mppi_ode_t<KIND, false, 0, 1, false>(grid, block, smem, st, a);
 }
 cudaError_t launch_mppi_ode(int kind, bool log, int period_t, int ilp, int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a) {
   return kind == 0 ? launch_mppi_ode_k<0>(log, period_t, ilp, grid, block, smem, st, a) : launch_mppi_ode_k<1>(log, period_t, ilp, grid, block, smem, st, a);
