@@ -54,6 +54,7 @@ RPGD_CFG = dict(seed=42, mpc_timestep=0.02, SAMPLING_DISTRIBUTION="uniform", per
 WORKLOADS = {
     # name: (optimizer, predictor, cost, N_global, H)
     "mppi_ode_1m": ("mppi", "ODE", "default", 1_000_000, 100),   # BASELINE configs[4] (the metric's config)
+    "mppi_ode_1m_log": ("mppi", "ODE", "default", 1_000_000, 100),  # the same tick with optimizer_logging on: HBM-write bound
     "mppi_ode_c1": ("mppi", "ODE", "default", 2000, 50),         # configs[0]
     "cem_ode_c2": ("cem-tf", "ODE", "default", 4096, 50),        # configs[1]
     "rpgd_ode_c3": ("rpgd", "ODE", "quadratic_boundary_grad", 32, 50),  # configs[2]
@@ -218,8 +219,9 @@ def run_ours(args):
     dev = f"cuda:{local_rank}"
     lib = L.load()
     plan = ShardPlan(rank, world)
+    logging_on = args.workload.endswith("_log")
     ctrl, N, H = build_controller(args.workload, shard=plan if world > 1 else None, device=local_rank, n_override=args.rollouts,
-                                  mlp_engine=args.mlp_engine)
+                                  mlp_engine=args.mlp_engine, logging=logging_on)
     opt = ctrl.optimizer
     plan.attach(opt, lib)  # handle runs on torch's current stream (events + NCCL ordering)
     K, W = args.steps, args.warmup
@@ -275,20 +277,27 @@ def run_ours(args):
 
     # ---- e2e through the public plugin API: host state in, host control out, every step ----
     host_states = synthetic_states(K + W, 1)
-    for i in range(min(W, 3)):
+    for i in range(min(W, 3) if not logging_on else 1):
         ctrl.step(host_states[i])
+        if logging_on:
+            for v in ctrl.logs.values():
+                v.clear()
     barrier()
     lat = []
+    Ke = min(K, 3) if logging_on else K  # with logging every step hands 2.8 GB of trajectories to the host
     t0 = time.perf_counter()
-    for i in range(K):
+    for i in range(Ke):
         t1 = time.perf_counter()
         ctrl.step(host_states[W + i])
         lat.append(time.perf_counter() - t1)
+        if logging_on:
+            for v in ctrl.logs.values():
+                v.clear()
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = N * H * passes * K / float(e2e_s.item())
+    e2e_value = N * H * passes * Ke / float(e2e_s.item())
 
     if rank == 0:
         # ---- roofline of the dominant kernel (K1 fused rollout), measured live above ----
@@ -308,6 +317,15 @@ def run_ours(args):
                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, cuBLAS 8192^3)" if peaks else "fallback 1648",
                         "flop_per_rollout_step": fl_step, "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms / ms_per_step,
                         "tensor_flop_issued_per_algorithmic": 6.0 * 32768.0 / fl_step if args.mlp_engine == "tcgen05" else 0.0}
+        elif logging_on:
+            # optimizer_logging on: rollout_trajectories_logged [N,H+1,6] + Q_logged [N,H,1] + J [N] are written by the rollout kernel
+            byt = 4.0 * n_local * ((H + 1) * 6 + H + 1)
+            hpk = float(peaks.get("hbm_gbs", 6650.0))
+            ach = byt / (k1_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "mppi_ode_kernel<LOG> (fused tick + coalesced SoA trajectory log)", "achieved": ach, "peak": hpk,
+                        "unit": "GB/s", "frac": ach / hpk, "traffic": None, "algorithmic_bytes_per_launch": byt,
+                        "bytes_per_rollout_step": 28.0, "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)" if peaks else "fallback 6650",
+                        "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms / ms_per_step}
         elif opt_name == "cem-tf":
             fl_step = FLOP_PER_ROLLOUT_STEP["cem_ode"]
             peak, clk = C.c_double(), C.c_double()
@@ -357,8 +375,8 @@ def run_ours(args):
                            **({"mlp_engine": args.mlp_engine} if WORKLOADS[args.workload][1].startswith("Dense") else {}),
                            "parallelism": f"rollouts sharded over {world} GPU(s); exchange per tick: {getattr(opt, '_exchange', 'none')} "
                                           f"({'in-kernel NVLink mailbox stores, ' if getattr(opt, '_exchange', '') == 'p2p' else ''}{H // 10 + 3} floats per shard)",
-                           "l2": "flushed between timed ticks (256 MiB memset); inputs are 24 B per tick"},
-                "e2e": {"value": e2e_value, "unit": "rollout-steps/s", "h2d_bytes_per_step": 24, "d2h_bytes_per_step": (8 + 4 * H) if opt_name == "mppi" else 8,
+                           "l2": "flushed between timed ticks (256 MiB memset); inputs are 24 B per tick", "logging": logging_on},
+                "e2e": {"value": e2e_value, "unit": "rollout-steps/s", "h2d_bytes_per_step": 24, "d2h_bytes_per_step": (4 * N * ((H + 1) * 6 + H + 1) + 8 + 4 * H) if logging_on else ((8 + 4 * H) if opt_name == "mppi" else 8),
                         "p50_step_latency_ms": statistics.median(lat) * 1e3, "api": "controller_mpc.step(s_host) -> u_host"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "wall_s_timed_region": wall}

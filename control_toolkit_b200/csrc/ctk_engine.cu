@@ -489,8 +489,8 @@ static void mppi_ode_geometry(ctk_handle* h) {
   const long long N = h->N, sms = h->num_sms;
   // two rollouts per thread pay off once a thread runs several of them; below one full wave of single-rollout threads
   // (<= 1024 per SM) more warps hide the step latency better than more chains per warp (measured, profiles/)
-  int ilp = (c.logging || N <= sms * 1024) ? 1 : 2;
-  if (const char* e = getenv("CTK_K1_ILP")) { const int v = atoi(e); if (!c.logging && (v == 1 || v == 2)) ilp = v; }
+  int ilp = (N <= sms * 1024) ? 1 : 2;
+  if (const char* e = getenv("CTK_K1_ILP")) { const int v = atoi(e); if (v == 1 || v == 2) ilp = v; }
   int maxb = mppi_ode_max_block(ilp);
   if (const char* e = getenv("CTK_K1_BLOCK")) { const int v = atoi(e) / 32 * 32; if (v >= 32 && v <= maxb) maxb = v; }
   // shared memory: draws stash [n_ind][ilp*T] + accumulators [n_ind][T] + small fixed part, <= 200 KB
@@ -515,7 +515,7 @@ static void mppi_ode_geometry(ctk_handle* h) {
   h->ode_block = best_T;
   h->ode_grid = (int)std::min<long long>(sms, (N + (long long)best_T * ilp - 1) / ((long long)best_T * ilp));
   if (h->ode_grid < 1) h->ode_grid = 1;
-  h->ode_period_t = (h->period == 10 && !c.logging) ? 10 : 0;
+  h->ode_period_t = (h->period == 10) ? 10 : 0;
   if (getenv("CTK_K1_NO_UNROLL")) h->ode_period_t = 0;
   h->ode_smem = mppi_ode_smem_bytes(h->H, h->period, h->n_ind, ilp, best_T);
   h->ode_kernel = true;

@@ -41,12 +41,15 @@ static cudaError_t launch_mppi_ode_t(int grid, int block, size_t smem, cudaStrea
   k<<<grid, block, smem, st>>>(a);
   return cudaGetLastError();
 }
-// production instantiations: no logging, Philox noise only; logging or injected noise (verification) run the generic-period,
-// one-rollout-per-thread instantiation
+// production instantiations: Philox noise only; injected noise (verification) and odd periods with logging run the
+// generic-period, one-rollout-per-thread instantiation (any launch geometry is valid for it: grid-stride loop)
 template <int KIND>
 static cudaError_t launch_mppi_ode_k(bool log, int period_t, int ilp, int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a) {
-  if (log) return launch_mppi_ode_t<KIND, true, 0, 1, true>(grid, block, smem, st, a);
-  if (a.noise.inj != nullptr) return launch_mppi_ode_t<KIND, false, 0, 1, true>(grid, block, smem, st, a);
+  if (a.noise.inj != nullptr) return log ? launch_mppi_ode_t<KIND, true, 0, 1, true>(grid, block, smem, st, a) : launch_mppi_ode_t<KIND, false, 0, 1, true>(grid, block, smem, st, a);
+  if (log) {  // trajectory logging with in-kernel noise: HBM-write bound, the fast loop keeps the stores fed
+    if (period_t == 10) return ilp == 2 ? launch_mppi_ode_t<KIND, true, 10, 2, false>(grid, block, smem, st, a) : launch_mppi_ode_t<KIND, true, 10, 1, false>(grid, block, smem, st, a);
+    return launch_mppi_ode_t<KIND, true, 0, 1, true>(grid, block, smem, st, a);
+  }
   if (period_t == 10) return ilp == 2 ? launch_mppi_ode_t<KIND, false, 10, 2, false>(grid, block, smem, st, a) : launch_mppi_ode_t<KIND, false, 10, 1, false>(grid, block, smem, st, a);
   return ilp == 2 ? launch_mppi_ode_t<KIND, false, 0, 2, false>(grid, block, smem, st, a) : launch_mppi_ode_t<KIND, false, 0, 1, false>(grid, block, smem, st, a);
 }
