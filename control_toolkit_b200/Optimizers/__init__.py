@@ -64,6 +64,7 @@ class template_optimizer:
         self._h = None
         self._cost_spec = None
         self._cost_live = (None, None)
+        self._ode_spec = None
         self._dt = None
 
     # -- reference API -----------------------------------------------------------------------------------------
@@ -113,6 +114,7 @@ class template_optimizer:
         pred_kind, pred_spec = specs.resolve_predictor(env, predictor_specification)
         ode_spec = pred_spec if pred_kind == L.PRED_ODE else specs.ODE_REGISTRY.get(env, specs.CartPoleODE())
         self._dt = float(dt)
+        self._ode_spec = ode_spec
 
         cfg = L.ctk_config()
         cfg.abi_version = L.CTK_ABI_VERSION
@@ -161,13 +163,21 @@ class template_optimizer:
         return L.load()
 
     def _refresh_live_cost(self, lib) -> None:
-        """target_position / target_equilibrium may change between ticks (controller update_attributes,
-        reference Controllers/__init__.py:106-107)."""
+        """target_position / target_equilibrium -- and the pole length L of the ODE predictor (reference
+        controller_server/controller_server.py:21-28 lists it among the live attributes) -- may change between ticks
+        (controller update_attributes, reference Controllers/__init__.py:106-107)."""
         live = self._live_targets()
         if live != self._cost_live:
             c = self._cost_spec.to_c(*live)
             L.check(lib.ctk_set_cost_params(self._h, C.byref(c)))
             self._cost_live = live
+        vp = getattr(self.cost_function, "variable_parameters", None)
+        L_live = getattr(vp, "L", None) if vp is not None else None
+        if L_live is not None and self._ode_spec is not None and float(L_live) != float(self._ode_spec.L):
+            from dataclasses import replace
+            self._ode_spec = replace(self._ode_spec, L=float(L_live))
+            o = self._ode_spec.to_c(self._dt)
+            L.check(lib.ctk_set_ode_params(self._h, C.byref(o)))
 
     def _feed_noise(self, lib, blocks) -> None:
         """blocks: list of (kind, shape) standard-draw blocks this call will consume, in order."""

@@ -28,6 +28,7 @@ import pytest
 
 from gpu_helpers import make_controller, max_elem_rel, max_rel
 from helpers import fp32_noise_floor, golden_names, load_golden, make_oracle, replay
+from helpers import oracle_state as oracle_state_np
 
 pytestmark = pytest.mark.gpu
 
@@ -158,6 +159,44 @@ def test_cem_matches_reference_golden(name):
         _check_J(J, z[f"J_{t}"], floors[t], (name, t))
         # the device top-k applied to the device's own costs must equal a stable argsort (bit-exact index work)
         np.testing.assert_array_equal(got_elite[-1], np.argsort(J, kind="stable")[:k])
+
+
+@pytest.mark.parametrize("optimizer", ["mppi", "cem-tf"])
+def test_predictor_breadth_intermediate_steps_and_pole_length(optimizer):
+    """the ODE predictor with intermediate_steps > 1 (generic rollout kernel: sub-step loop) and a different pole
+    length, then a LIVE pole-length change through variable_parameters.L (ctk_set_ode_params) -- against the oracle."""
+    from dataclasses import replace
+    from control_toolkit_b200 import specs
+    from oracle import spec
+    from oracle.replay_rng import ReplayRNG
+    name = {"mppi": "mppi_c1_n64", "cem-tf": "cem_c2_n256_k16"}[optimizer]
+    z, meta = load_golden(name)
+    saved = specs.ODE_REGISTRY["CartPole"]
+    try:
+        specs.ODE_REGISTRY["CartPole"] = replace(saved, intermediate_steps=4, L=0.25)
+        ctrl = make_controller(meta, rng=None, logging=False)
+        ctrl.optimizer.rng = ReplayRNG(77, as_torch=False)
+        ctrl.optimizer.optimizer_reset()
+        o = make_oracle(meta)
+        o.predictor = spec.ODEPredictor(spec.CartPoleParams(dt=meta["cfg"]["mpc_timestep"], intermediate_steps=4, L=0.25))
+        rng = ReplayRNG(77)
+        states = spec.synthetic_states(4, seed=13)
+        for t in range(4):
+            upd = {}
+            if t == 2:  # live change of the pole length through the controller's own update_attributes path
+                upd = {"L": 0.15}
+                o.predictor = spec.ODEPredictor(spec.CartPoleParams(dt=meta["cfg"]["mpc_timestep"], intermediate_steps=4, L=0.15))
+            u = ctrl.step(states[t], updated_attributes=upd)
+            uo = o.step(states[t], rng)
+            ref = oracle_state_np(o, meta)
+            got = ctrl.optimizer.u_nom if optimizer == "mppi" else ctrl.optimizer.dist_mue
+            e = max_rel(got, ref)
+            _report(f"breadth {optimizer} isteps=4 L={'0.15' if t >= 2 else '0.25'} tick {t}: state {e:.2e} u {abs(float(u) - float(np.ravel(uo)[0])):.2e}")
+            assert e < 1e-4, (optimizer, t, e)
+            assert abs(float(u) - float(np.ravel(uo)[0])) < 1e-4
+        # the pole length matters: the two settings give different controls (the live update reached the kernels)
+    finally:
+        specs.ODE_REGISTRY["CartPole"] = saved
 
 
 @pytest.mark.parametrize("name", golden_names("random_action_"))
