@@ -176,5 +176,14 @@ __device__ __forceinline__ void interp_weights(int j, int period, float* w0, flo
   *w0 = (float)(period - j) / (float)period;
   *w1 = (float)j / (float)period;
 }
+// Reference quirk, reproduced (others/Interpolator.py:73-74): the weight of the LAST inducing point on the last matrix row is
+// set to 1 BEFORE the whole matrix is divided by the period.  When H - 1 is a multiple of the period that row survives the
+// truncation to H rows, and the final horizon step reads y_last / period instead of y_last.  Segment index n_ind - 1 is only
+// ever reached by that step (otherwise the horizon ends inside segment n_ind - 2).
+__device__ __forceinline__ float interp_last_point_weight(int period) { return 1.0f / (float)period; }
+__device__ __forceinline__ void interp_weights(int seg, int j, int period, int n_ind, float* w0, float* w1) {
+  *w0 = (seg == n_ind - 1) ? interp_last_point_weight(period) : (float)(period - j) / (float)period;
+  *w1 = (float)j / (float)period;
+}
 
 }  // namespace ctk

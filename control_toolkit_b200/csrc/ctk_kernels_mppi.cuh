@@ -142,7 +142,7 @@ __device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float*
   for (int t = tid; t < H; t += blockDim.x) {
     const int seg = t / period, j = t - seg * period;
     float w0, w1;
-    interp_weights(j, period, &w0, &w1);
+    interp_weights(seg, j, period, n_ind, &w0, &w1);
     const float bz0 = sh_rec[2 + seg];
     const float bz1 = (j > 0) ? sh_rec[2 + seg + 1] : 0.0f;
     const float b = (fmaf(bz1, w1, bz0 * w0) * stdev) / a;
@@ -232,6 +232,8 @@ __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const M
           y_cur = __fmul_rn(zq[0], stdev);
           zq[0] = zq[1]; zq[1] = zq[2]; zq[2] = zq[3];
           --have; ++i;
+        } else {
+          y_prev = __fmul_rn(y_prev, interp_last_point_weight(a.period));  // segment n_ind - 1: reference quirk (ctk_device.cuh)
         }
         const int cnt = min(a.period, a.H - t);
         uint32_t pw = a_w;
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(1024) mppi_combine_kernel(const float* __restr
   for (int t = threadIdx.x; t < fin.H; t += blockDim.x) {
     const int seg = t / fin.period, j = t - seg * fin.period;
     float w0, w1;
-    interp_weights(j, fin.period, &w0, &w1);
+    interp_weights(seg, j, fin.period, fin.n_ind, &w0, &w1);
     const float bz0 = sh_rec[2 + seg];
     const float bz1 = (j > 0) ? sh_rec[2 + seg + 1] : 0.0f;
     const float b = (fmaf(bz1, w1, bz0 * w0) * fin.stdev) / a;

@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
 #pragma unroll
       for (int q = 0; q < ILP; ++q) {
         const float* sz = sh_z + q * T_ + tid;
-        const float y0 = r[q].y1;
+        float y0 = r[q].y1;
+        if (seg == a.n_ind - 1) y0 *= interp_last_point_weight(period);  // reference quirk: last point weighs 1/period (ctk_device.cuh)
         const float y1 = (seg + 1 < a.n_ind) ? sz[(size_t)(seg + 1) * ILP * T_] * k.stdev : 0.0f;
         r[q].y0 = y0;
         r[q].y1 = y1;

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) rpgd_select_kernel(const RpgdSel
       // fresh sample (:451-453): interpolate clipped inducing points (Interpolator.py:97-106)
       const int seg = t / a.period, j = t - seg * a.period;
       float w0, w1;
-      interp_weights(j, a.period, &w0, &w1);
+      interp_weights(seg, j, a.period, a.n_ind, &w0, &w1);
       const float y0 = rpgd_sample_point(a, (uint32_t)n, seg);
       const float y1 = (j > 0) ? rpgd_sample_point(a, (uint32_t)n, seg + 1) : 0.0f;
       q = fmaf(y1, w1, __fmul_rn(y0, w0));
@@ -167,7 +167,7 @@ __global__ void rpgd_init_kernel(const RpgdSelectArgs a) {
     const int t = idx / a.N, n = idx - t * a.N;
     const int seg = t / a.period, j = t - seg * a.period;
     float w0, w1;
-    interp_weights(j, a.period, &w0, &w1);
+    interp_weights(seg, j, a.period, a.n_ind, &w0, &w1);
     const float y0 = rpgd_sample_point(a, (uint32_t)n, seg);
     const float y1 = (j > 0) ? rpgd_sample_point(a, (uint32_t)n, seg + 1) : 0.0f;
     a.Qn[idx] = fmaf(y1, w1, __fmul_rn(y0, w0));

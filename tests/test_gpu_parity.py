@@ -161,6 +161,58 @@ def test_cem_matches_reference_golden(name):
         np.testing.assert_array_equal(got_elite[-1], np.argsort(J, kind="stable")[:k])
 
 
+@pytest.mark.parametrize("N,H,period", [(1, 1, 10), (1, 7, 3), (33, 2, 10), (33, 11, 50), (257, 101, 10), (1000, 30, 7), (64, 10, 10),
+                                        (100, 21, 20), (2000, 50, 1)])
+def test_mppi_edge_geometries_match_oracle(N, H, period):
+    """Ragged / degenerate MPPI geometries against the oracle on injected noise: a single rollout, a horizon of one step, a
+    period longer than the horizon, N not a multiple of the warp size, a partial last inducing-point segment -- the cases the
+    segment-unrolled kernel and its closed-form du^2 term special-case."""
+    from oracle import spec
+    from oracle.replay_rng import ReplayRNG
+    z, meta = load_golden("mppi_c1_n64")
+    meta = dict(meta, cfg=dict(meta["cfg"], num_rollouts=N, mpc_horizon=H, period_interpolation_inducing_points=period))
+    ctrl = make_controller(meta, rng=None, logging=True)
+    ctrl.optimizer.rng = ReplayRNG(5, as_torch=False)
+    ctrl.optimizer.optimizer_reset()
+    o = make_oracle(meta)
+    rng = ReplayRNG(5)
+    for t, s0 in enumerate(spec.synthetic_states(3, seed=21)):
+        u = ctrl.step(s0)
+        uo = o.step(s0, rng)
+        ref = o.u_nom.numpy()
+        e = float(np.max(np.abs(ctrl.optimizer.u_nom - ref))) / max(float(np.max(np.abs(ref))), 1e-2)
+        eJ = max_elem_rel(ctrl.optimizer.logging_values["J_logged"], o.last["J"])
+        _report(f"edge N={N} H={H} p={period} tick {t}: u_nom {e:.2e} J {eJ:.2e}")
+        assert ctrl.optimizer.u_nom.shape == (1, H, 1) and np.ndim(u) == 0
+        assert e < 1e-4, (N, H, period, t, e)
+        assert abs(float(u) - float(np.ravel(uo)[0])) < 1e-4
+        assert eJ < 1e-2
+
+
+def test_rpgd_last_inducing_point_quirk():
+    """reference others/Interpolator.py:73-74 divides the '1' of the last inducing point by the period: with H - 1 a multiple of the
+    period the final horizon step of every sampled sequence is y_last / period.  RPGD's initial population must show it."""
+    from control_toolkit_b200 import _lib as L
+    from oracle.replay_rng import ReplayRNG
+    z, meta = load_golden("rpgd_c3")
+    meta = dict(meta, cfg=dict(meta["cfg"], mpc_horizon=41))
+    ctrl = make_controller(meta, rng=None, logging=False, adam_form="torch")
+    opt = ctrl.optimizer
+    opt.rng = ReplayRNG(9, as_torch=False)
+    opt.optimizer_reset()
+    o = make_oracle(meta)
+    rng = ReplayRNG(9)
+    o.reset(rng)
+    Q = opt._get_state(L.STATE_RPGD_Q, (opt.num_rollouts, 41))
+    Qo = o.Q.numpy()[..., 0]
+    assert np.abs(Q - Qo).max() < 1e-6
+    assert np.abs(Qo[:, 40]).max() <= 0.1 + 1e-6  # |y_last| <= 1, period 10
+    for t in range(2):
+        u = ctrl.step(z["states"][t])
+        uo = o.step(z["states"][t], rng)
+        assert max_rel(opt._get_state(L.STATE_RPGD_Q, (opt.num_rollouts, 41)), o.Q.numpy()[..., 0]) < 1e-4
+
+
 @pytest.mark.parametrize("optimizer", ["mppi", "cem-tf"])
 def test_predictor_breadth_intermediate_steps_and_pole_length(optimizer):
     """the ODE predictor with intermediate_steps > 1 (generic rollout kernel: sub-step loop) and a different pole
