@@ -185,6 +185,7 @@ struct RpgdSelectArgs {
   int N, H, k, period, n_ind;
   int shift_previous;
   int resample;            // count % resamp_per == 0
+  int tail_resample;       // gradient mode: no reordering, the LAST control of every row is redrawn (noise rows 0..N-1, one draw each)
   const float* J;          // [N]
   const float *Q, *m, *v;  // [H][N] current
   const float* ages;       // [N]

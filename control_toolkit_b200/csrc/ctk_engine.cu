@@ -698,14 +698,20 @@ static int rpgd_local(ctk_handle* h, const float* s_dev) {
 
 static int rpgd_finish(ctk_handle* h, float* u_out_dev) {
   const ctk_config& c = h->cfg;
-  const int resample = (h->count % c.rpgd_resamp_per == 0) ? 1 : 0;  // optimizer_rpgd.py:449
+  const int grad_mode = c.rpgd_gradient_mode ? 1 : 0;
+  const int resample = (!grad_mode && h->count % c.rpgd_resamp_per == 0) ? 1 : 0;  // optimizer_rpgd.py:449
   NoiseSrc ns{};
-  if (resample && h->N - c.rpgd_keep_k > 0) {
+  if (grad_mode) {  // one uniform draw per row for the vacated last step (optimizer_gradient_tf.py:142-147)
+    int rcn = make_noise(h, STREAM_RPGD_RESAMPLE, 1, 1, (size_t)h->N, &ns);
+    if (rcn != CTK_OK) return rcn;
+  } else if (resample && h->N - c.rpgd_keep_k > 0) {
     int rcn = make_noise(h, STREAM_RPGD_RESAMPLE, h->n_ind, c.rpgd_distribution == CTK_DIST_UNIFORM, (size_t)(h->N - c.rpgd_keep_k), &ns);
     if (rcn != CTK_OK) return rcn;
   }
   RpgdSelectArgs a = rpgd_sample_args(h, ns);
   a.resample = resample;
+  a.tail_resample = grad_mode;
+  if (grad_mode) { a.dist = CTK_DIST_UNIFORM; a.s_min = c.action_low; a.s_max = c.action_high; }
   a.J = h->d_J; a.Q = h->d_Q[h->cur]; a.m = h->d_m[h->cur]; a.v = h->d_v[h->cur]; a.ages = h->d_ages[h->cur];
   const int nx = h->cur ^ 1;
   a.Qn = h->d_Q[nx]; a.mn = h->d_m[nx]; a.vn = h->d_v[nx]; a.agesn = h->d_ages[nx];

@@ -147,6 +147,8 @@ __global__ void __launch_bounds__(TOPK_THREADS) rpgd_select_kernel(const RpgdSel
       const int src = a.resample ? sh_best[n - nnew] : n;  // gather in best order (:454) or identity
       const int ts = min(t + a.shift_previous, a.H - 1);   // :376-379 shift, repeat the last
       q = a.Q[(size_t)ts * a.N + src];
+      // optimizer_gradient_tf.py:142-149: the vacated last step gets a fresh uniform control instead of a repeat
+      if (a.tail_resample && t == a.H - 1) q = rpgd_sample_point(a, (uint32_t)n, 0);
       // Adam moments: always shifted by ONE with zero fill (:462-513)
       mm = (t + 1 < a.H) ? a.m[(size_t)(t + 1) * a.N + src] : 0.0f;
       vv = (t + 1 < a.H) ? a.v[(size_t)(t + 1) * a.N + src] : 0.0f;

@@ -121,7 +121,10 @@ typedef struct ctk_config {
   int32_t mlp_engine;             /* CTK_MLP_*                                                                   */
   int32_t cem_uniform_actions;    /* 1: random shooting (reference optimizer_random_action_tf.py:56-68): every tick samples
                                      Q ~ U[action_low, action_high) instead of N(dist_mue, stdev); use cem_outer_it = cem_best_k = 1 */
-  int32_t reserved[6];
+  int32_t rpgd_gradient_mode;     /* 1: population gradient descent (reference optimizer_gradient_tf.py:101-167): no ranking-based
+                                     resampling; every tick all rows shift by one step and their last control is redrawn from
+                                     U[action_low, action_high) (one draw per row); use period 1, keep_k = num_rollouts       */
+  int32_t reserved[5];
 } ctk_config;
 
 typedef struct ctk_handle ctk_handle;

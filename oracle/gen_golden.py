@@ -69,6 +69,33 @@ CASES = {
                            dict(seed=42, mpc_horizon=50, mpc_timestep=0.02, num_rollouts=512), 3, True),
     "random_action_n4096_h30": ("random-action-tf", "ODE", "default",
                                 dict(seed=42, mpc_horizon=30, mpc_timestep=0.02, num_rollouts=4096), 2, False),
+    # reference Optimizers/optimizer_gradient_tf.py (template block config_optimizers.yml:48-61): Adam on the whole population
+    "gradient_n40": ("gradient-tf", "ODE", "quadratic_boundary_grad",
+                     dict(seed=42, mpc_horizon=35, mpc_timestep=0.02, learning_rate=0.05, adam_beta_1=0.9, adam_beta_2=0.999,
+                          adam_epsilon=1.0e-07, rtol=1.0e-3, gradient_steps=5, num_rollouts=40, initial_action_stdev=0.5,
+                          gradmax_clip=5, warmup=False, warmup_iterations=250), 6, True),
+    "gradient_warmup_n33": ("gradient-tf", "ODE", "quadratic_boundary_grad",
+                            dict(seed=42, mpc_horizon=20, mpc_timestep=0.02, learning_rate=0.1, adam_beta_1=0.9, adam_beta_2=0.999,
+                                 adam_epsilon=1.0e-07, rtol=1.0e-3, gradient_steps=2, num_rollouts=33, initial_action_stdev=0.5,
+                                 gradmax_clip=2, warmup=True, warmup_iterations=7), 4, False),
+    # reference Optimizers/optimizer_cem_naive_grad_tf.py (template block config_optimizers.yml:23-32): CEM whose samples take one
+    # clipped gradient-descent step before they are ranked
+    "cem_naive_grad_n200": ("cem-naive-grad-tf", "ODE", "quadratic_boundary_grad",
+                            dict(seed=42, mpc_horizon=35, mpc_timestep=0.02, cem_outer_it=1, num_rollouts=200, cem_stdev_min=0.1,
+                                 cem_initial_action_stdev=0.5, cem_best_k=40, learning_rate=0.1, gradmax_clip=10), 5, True),
+    "cem_naive_grad_it3_n96": ("cem-naive-grad-tf", "ODE", "quadratic_boundary_grad",
+                               dict(seed=42, mpc_horizon=20, mpc_timestep=0.02, cem_outer_it=3, num_rollouts=96, cem_stdev_min=0.05,
+                                    cem_initial_action_stdev=0.7, cem_best_k=12, learning_rate=0.2, gradmax_clip=2), 4, False),
+    # reference Optimizers/optimizer_cem_grad_bharadhwaj_tf.py (template block config_optimizers.yml:33-47): elites carried between the
+    # outer iterations, one Adam step (persistent moments) on the whole population before ranking
+    "cem_bharadhwaj_n32": ("cem-grad-bharadhwaj-tf", "ODE", "quadratic_boundary_grad",
+                           dict(seed=42, mpc_horizon=50, mpc_timestep=0.02, learning_rate=0.05, adam_beta_1=0.9, adam_beta_2=0.999,
+                                adam_epsilon=1.0e-08, num_rollouts=32, cem_best_k=8, cem_outer_it=2, cem_initial_action_stdev=2,
+                                cem_stdev_min=1.e-6, gradmax_clip=5, warmup=False, warmup_iterations=250), 6, True),
+    "cem_bharadhwaj_warmup_n64": ("cem-grad-bharadhwaj-tf", "ODE", "quadratic_boundary_grad",
+                                  dict(seed=42, mpc_horizon=30, mpc_timestep=0.02, learning_rate=0.1, adam_beta_1=0.9, adam_beta_2=0.999,
+                                       adam_epsilon=1.0e-08, num_rollouts=64, cem_best_k=16, cem_outer_it=3, cem_initial_action_stdev=0.8,
+                                       cem_stdev_min=1.e-3, gradmax_clip=3, warmup=True, warmup_iterations=5), 3, False),
     "mppi_mlp_c4_n256": ("mppi", "Dense-6IN-128H1-128H2-5OUT-0", "default",
                          _c(MPPI_BASE, num_rollouts=256, mpc_horizon=100), 2, False),
     "mppi_mlp_h50_n64": ("mppi", "Dense-6IN-128H1-128H2-5OUT-0", "default",
@@ -118,7 +145,7 @@ def run_reference_case(name: str) -> dict:
         # tick (Optimizers/__init__.py:35) and has no .copy() (Controllers/__init__.py:177) -> give it a numpy 0.
         opt.u = np.float32(0.0)
 
-    if opt_name in ("cem-tf", "random-action-tf"):
+    if opt_name.endswith("-tf"):
         import tensorflow as tfshim
         argsort_log = []
         _orig = tfshim.argsort
@@ -135,7 +162,7 @@ def run_reference_case(name: str) -> dict:
                                               cfg=cfg, ticks=ticks, noise_seed=NOISE_SEED, state_seed=STATE_SEED,
                                               mlp_seed=MLP_SEED))),
            "states": states}
-    if opt_name == "rpgd":
+    if opt_name in ("rpgd", "gradient-tf"):
         out["Q_init"] = opt.Q_tf.numpy().copy()
 
     for t in range(ticks):
@@ -154,9 +181,31 @@ def run_reference_case(name: str) -> dict:
             out[f"sorted_gap_{t}"] = np.array([float(np.sort(np.asarray(lv["J_logged"]))[k] -
                                                       np.sort(np.asarray(lv["J_logged"]))[k - 1])], np.float32)
             argsort_log.clear()
+        elif opt_name in ("cem-naive-grad-tf", "cem-grad-bharadhwaj-tf"):
+            out[f"dist_mue_{t}"] = opt.dist_mue.numpy().copy()
+            out[f"stdev_{t}"] = opt.stdev.numpy().copy()
+            out[f"J_{t}"] = np.asarray(lv["J_logged"]).copy()  # costs of the LAST outer iteration (after the gradient step)
+            k = cfg["cem_best_k"]
+            out[f"elite_idx_{t}"] = np.stack([a[:k] for a in argsort_log]).astype(np.int64)  # [iters, k]
+            out[f"Qn_{t}"] = np.asarray(lv["Q_logged"]).copy()  # the population after the gradient step, last outer iteration
+            if opt_name == "cem-grad-bharadhwaj-tf":
+                step, m, v = opt.optim.get_weights()
+                out[f"adam_m_{t}"] = np.asarray(m).copy()
+                out[f"adam_v_{t}"] = np.asarray(v).copy()
+                out[f"adam_step_{t}"] = np.array([int(step)], np.int64)
+            argsort_log.clear()
         elif opt_name == "random-action-tf":
             out[f"J_{t}"] = np.asarray(lv["J_logged"]).copy()
             out[f"best_idx_{t}"] = np.array([int(argsort_log[-1][0])], np.int64)  # tf.argsort(traj_cost)[0]  (:66-67)
+            argsort_log.clear()
+        elif opt_name == "gradient-tf":
+            step, m, v = opt.optim.get_weights()
+            out[f"Q_{t}"] = opt.Q_tf.numpy().copy()  # AFTER the warm-start shift (:136-144)
+            out[f"adam_m_{t}"] = np.asarray(m).copy()
+            out[f"adam_v_{t}"] = np.asarray(v).copy()
+            out[f"adam_step_{t}"] = np.array([int(step)], np.int64)
+            out[f"J_{t}"] = np.asarray(lv["J_logged"]).copy()
+            out[f"best_idx_{t}"] = np.array([int(argsort_log[-1][0])], np.int64)
             argsort_log.clear()
         elif opt_name == "rpgd":
             step, m, v = opt.opt.get_weights()
@@ -179,7 +228,7 @@ def run_reference_case(name: str) -> dict:
         acc += float(np.sum(chk.standard_draws(kind, shape).astype(np.float64)))
     out["noise_checksum"] = np.array([acc], np.float64)
 
-    if opt_name in ("cem-tf", "random-action-tf"):
+    if opt_name.endswith("-tf"):
         tfshim.argsort = _orig
     return out
 

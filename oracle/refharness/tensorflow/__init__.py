@@ -70,7 +70,7 @@ def reduce_mean(x, axis=None, keepdims=False):
 
 
 def concat(xs, axis):
-    return _torch.cat(list(xs), dim=axis)
+    return _torch.cat([x if isinstance(x, _torch.Tensor) else _torch.as_tensor(_np.asarray(x)) for x in xs], dim=axis)
 
 
 def squeeze(x):
@@ -98,10 +98,10 @@ class _Generator:
     def from_seed(cls, seed):
         return cls(seed)
 
-    def normal(self, shape, dtype=float32, mean=0.0, stddev=1.0):
+    def normal(self, shape, mean=0.0, stddev=1.0, dtype=float32):
         return _torch.randn(tuple(shape), generator=self._g, dtype=dtype) * stddev + mean
 
-    def uniform(self, shape, dtype=float32, minval=0.0, maxval=1.0):
+    def uniform(self, shape, minval=0.0, maxval=1.0, dtype=float32):
         return _torch.rand(tuple(shape), generator=self._g, dtype=dtype) * (maxval - minval) + minval
 
 
@@ -110,3 +110,121 @@ class _Random:
 
 
 random = _Random()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Additions for the reference's UNMODIFIED ``Optimizers/optimizer_gradient_tf.py`` / ``optimizer_random_action_tf.py``:
+# tf.Variable, tf.GradientTape, tf.clip_by_norm, tf.zeros_like and the LEGACY Keras Adam (``get_weights()`` returns
+# ``[iterations, m, v]`` once slots exist, ``[]`` before the first apply_gradients), with TF's documented semantics:
+# * ``tf.clip_by_norm(t, c, axes)`` = t * c / max(||t||_2, c), norm over ``axes`` with keepdims;
+# * Keras Adam ``_resource_apply_dense``: t = iterations + 1; lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);
+#   m += (g - m)(1 - b1); v += (g^2 - v)(1 - b2); var -= lr_t * m / (sqrt(v) + eps); iterations += 1.
+# ----------------------------------------------------------------------------------------------------------------------
+class _Var(_torch.Tensor):
+    """tf.Variable stand-in: a leaf torch tensor with ``assign`` (in place) whose slices are new tensors."""
+
+    __torch_function__ = _torch._C._disabled_torch_function_impl
+
+    @staticmethod
+    def __new__(cls, value, dtype=float32):
+        return _torch.Tensor._make_subclass(cls, _torch.as_tensor(value, dtype=dtype).detach().clone(), False)
+
+    def __init__(self, value, dtype=float32):
+        pass
+
+    def assign(self, value):
+        with _torch.no_grad():
+            self.requires_grad_(False)
+            self.copy_(_torch.as_tensor(value, dtype=self.dtype).detach())
+        return self
+
+    def __getitem__(self, idx):
+        return _torch.Tensor.__getitem__(self.as_subclass(_torch.Tensor), idx).clone()
+
+    def numpy(self):
+        return self.as_subclass(_torch.Tensor).detach().numpy().copy()
+
+
+def _unwrap(x):
+    return x.as_subclass(_torch.Tensor) if isinstance(x, _Var) else x
+
+
+Variable = _Var
+_plain_clip_by_value = clip_by_value
+
+
+def clip_by_value(x, lo, hi):  # noqa: F811  (accepts tf.Variable)
+    return _plain_clip_by_value(_unwrap(x), lo, hi)
+
+
+def zeros_like(x):
+    return _torch.zeros_like(_unwrap(x) if not isinstance(x, (int, _np.integer)) else _torch.tensor(x))
+
+
+def clip_by_norm(t, clip_norm, axes=None):
+    t = _unwrap(t)
+    n = _torch.sqrt(_torch.sum(t * t, dim=tuple(axes) if axes is not None else None, keepdim=True))
+    c = _torch.as_tensor(clip_norm, dtype=t.dtype)
+    return t * c / _torch.maximum(n, c)
+
+
+class GradientTape:
+    def __init__(self, watch_accessed_variables=True, persistent=False):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def watch(self, var):
+        var.requires_grad_(True)  # leaf: the ops inside the tape build the autograd graph on it
+
+    def gradient(self, target, source):
+        (g,) = _torch.autograd.grad(_torch.sum(target), source)
+        source.requires_grad_(False)
+        return g.as_subclass(_torch.Tensor) if isinstance(g, _Var) else g
+
+
+class _KerasAdam:
+    def __init__(self, learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, **_):
+        self.lr, self.b1, self.b2, self.eps = float(learning_rate), float(beta_1), float(beta_2), float(epsilon)
+        self.iterations = 0
+        self._m = self._v = None
+
+    def apply_gradients(self, grads_and_vars):
+        for g, var in grads_and_vars:
+            g = g.detach()
+            if self._m is None:
+                self._m, self._v = _torch.zeros_like(g), _torch.zeros_like(g)
+            t = self.iterations + 1
+            f32 = _np.float32
+            lr_t = f32(f32(self.lr) * _np.sqrt(f32(1) - _np.power(f32(self.b2), f32(t))) / (f32(1) - _np.power(f32(self.b1), f32(t))))
+            self._m = self._m + (g - self._m) * f32(1 - self.b1)
+            self._v = self._v + (g * g - self._v) * f32(1 - self.b2)
+            var.assign(_unwrap(var).detach() - float(lr_t) * self._m / (_torch.sqrt(self._v) + f32(self.eps)))
+        self.iterations += 1
+
+    def get_weights(self):
+        if self._m is None:
+            return []
+        return [_np.int64(self.iterations), self._m.numpy().copy(), self._v.numpy().copy()]
+
+    def set_weights(self, weights):
+        if len(weights) == 0:
+            return
+        self.iterations = int(_np.asarray(weights[0]))
+        self._m = _torch.as_tensor(_np.asarray(weights[1]), dtype=float32).clone()
+        self._v = _torch.as_tensor(_np.asarray(weights[2]), dtype=float32).clone()
+
+
+class _KerasOptimizers:
+    Adam = _KerasAdam
+
+
+class _Keras:
+    optimizers = _KerasOptimizers()
+
+
+keras = _Keras()

@@ -47,11 +47,13 @@ class ReplayRNG:
             return x.detach()
         return np.float32(x) if not self.as_torch else float(np.float32(x))
 
-    def normal(self, shape, dtype=None, mean=0.0, stddev=1.0):
+    # positional order as in tf.random.Generator (shape, mean, stddev, dtype) / (shape, minval, maxval, dtype): the reference's
+    # optimizer_gradient_tf.py:173-178 passes minval / maxval positionally
+    def normal(self, shape, mean=0.0, stddev=1.0, dtype=None):
         z = self._wrap(self.standard_draws("normal", shape))
         return z * self._scalar(stddev) + self._scalar(mean)
 
-    def uniform(self, shape, dtype=None, minval=0.0, maxval=1.0):
+    def uniform(self, shape, minval=0.0, maxval=1.0, dtype=None):
         z = self._wrap(self.standard_draws("uniform", shape))
         lo, hi = self._scalar(minval), self._scalar(maxval)
         return z * (hi - lo) + lo

@@ -6,6 +6,7 @@ import numpy as np
 
 from oracle import spec
 from oracle.cem import CEMOracle
+from oracle.gradient import GradientOracle
 from oracle.mppi import MPPIOracle
 from oracle.random_action import RandomActionOracle
 from oracle.replay_rng import ReplayRNG
@@ -35,7 +36,8 @@ def make_oracle(meta, **over):
     cost = spec.CostParams(name=meta["cost"])
     cfg = dict(meta["cfg"])
     cfg.update(over)
-    cls = {"mppi": MPPIOracle, "cem-tf": CEMOracle, "rpgd": RPGDOracle, "random-action-tf": RandomActionOracle}[meta["optimizer"]]
+    cls = {"mppi": MPPIOracle, "cem-tf": CEMOracle, "rpgd": RPGDOracle, "random-action-tf": RandomActionOracle,
+           "gradient-tf": GradientOracle}[meta["optimizer"]]
     return cls(pred, cost, **cfg)
 
 
@@ -59,7 +61,7 @@ def oracle_state(o, meta):
     """The optimizer state array the parity contract names (u_nom / dist_mue / Q)."""
     if meta["optimizer"] == "random-action-tf":
         return np.atleast_1d(np.asarray(o.u, np.float32))
-    return {"mppi": lambda: o.u_nom, "cem-tf": lambda: o.dist_mue, "rpgd": lambda: o.Q}[meta["optimizer"]]().numpy()
+    return {"mppi": lambda: o.u_nom, "cem-tf": lambda: o.dist_mue, "rpgd": lambda: o.Q, "gradient-tf": lambda: o.Q}[meta["optimizer"]]().numpy()
 
 
 _FLOOR_CACHE = {}
@@ -82,7 +84,7 @@ def fp32_noise_floor(name, ticks=None, **over):
     if meta["predictor"].startswith("Dense"):
         o64.predictor = spec.MLPPredictor(spec.MLPWeights.random_init(meta["mlp_seed"]), dtype=torch.float64)
     r32, r64 = replay(meta), replay(meta)
-    if meta["optimizer"] in ("rpgd", "random-action-tf"):
+    if meta["optimizer"] in ("rpgd", "random-action-tf", "gradient-tf"):
         o32.reset(r32)
         o64.reset(r64)
     out = []

@@ -332,6 +332,34 @@ def test_random_action_matches_reference_golden(name):
             assert e_tr < TOL_TRAJ
 
 
+@pytest.mark.parametrize("name", golden_names("gradient_"))
+def test_gradient_matches_reference_golden(name):
+    """Population gradient descent (reference Optimizers/optimizer_gradient_tf.py) on the RPGD kernels in
+    gradient mode (Keras Adam, no ranking-based resampling, tail redraw): chosen sequence index identical, u / Q / Adam
+    state within the fp32 floor of the path on every fixture tick."""
+    z, meta = load_golden(name)
+    ctrl = make_controller(meta)
+    opt = ctrl.optimizer
+    assert max_rel(opt.Q_tf, z["Q_init"]) == 0.0
+    floors = fp32_noise_floor(name)
+    for t in range(meta["ticks"]):
+        u = ctrl.step(z["states"][t], time=0.02 * t)
+        tol_s, tol_u, tol_J = _tols(floors[t])
+        step, m, v = opt.adam_weights()
+        e_u = max_rel(u, z[f"u_{t}"], floor=1.0)
+        e_Q = max_rel(opt.Q_tf, z[f"Q_{t}"])
+        e_m = max_rel(m, z[f"adam_m_{t}"])
+        e_v = max_rel(v, z[f"adam_v_{t}"])
+        _report(f"{name} tick {t}: best {opt.best_index()} (ref {int(z[f'best_idx_{t}'][0])}) u {e_u:.2e} Q {e_Q:.2e} m {e_m:.2e} "
+                f"v {e_v:.2e} | fp32 floor: state {floors[t]['state']:.2e}")
+        assert np.ndim(u) == 0  # :132 squeeze
+        assert step == int(z[f"adam_step_{t}"][0])
+        assert opt.best_index() == int(z[f"best_idx_{t}"][0])
+        assert e_u < tol_u and e_Q < tol_s, (name, t, e_u, e_Q, floors[t])
+        assert e_m < 10 * tol_s and e_v < 10 * tol_s, (name, t, e_m, e_v)
+        _check_J(opt.logging_values["J_logged"], z[f"J_{t}"], floors[t], (name, t))
+
+
 @pytest.mark.parametrize("name", golden_names("rpgd_"))
 def test_rpgd_matches_reference_golden(name):
     """adam_form='torch' reproduces the reference's runnable (torch) branch, optimizer_rpgd.py:56-82."""

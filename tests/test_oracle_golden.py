@@ -101,3 +101,22 @@ def test_random_action_oracle_matches_reference(name):
         if t == 0 and "rollouts_0" in z:
             assert rel_err(o.last["rollouts"], z["rollouts_0"]) < TOL
             assert rel_err(o.last["Q"], z["Q_logged_0"]) == 0.0
+
+
+@pytest.mark.parametrize("name", golden_names("gradient_"))
+def test_gradient_oracle_matches_reference(name):
+    """oracle/gradient.py vs the unmodified reference Optimizers/optimizer_gradient_tf.py."""
+    z, meta = load_golden(name)
+    o = make_oracle(meta)
+    rng = replay(meta)
+    o.reset(rng)
+    assert rel_err(o.Q.numpy(), z["Q_init"]) == 0.0
+    for t in range(meta["ticks"]):
+        u = o.step(z["states"][t], rng)
+        assert o.last["best_idx"] == int(z[f"best_idx_{t}"][0])
+        assert rel_err(u, z[f"u_{t}"]) < 5e-6
+        assert rel_err(o.Q.numpy(), z[f"Q_{t}"]) < 5e-6
+        assert rel_err(o.m.numpy(), z[f"adam_m_{t}"]) < 2e-5
+        assert rel_err(o.v.numpy(), z[f"adam_v_{t}"]) < 2e-5
+        assert o.adam_step == int(z[f"adam_step_{t}"][0])
+        assert rel_err(o.last["J"], z[f"J_{t}"]) < 5e-6
