@@ -173,7 +173,7 @@ struct RpgdGradArgs {
   float lr, gradmax_clip;
   double beta1, beta2, eps;
   long long adam_step0;  // global step counter before this tick's first gradient step
-  int adam_form;         // 0 Keras, 1 torch
+  int adam_form;         // 0 Keras, 1 torch, 2 plain gradient descent q - lr * g (optimizer_cem_naive_grad_tf.py:74)
   OdeC ode;              // adjoint constants
   FwdK fwd;              // forward constants
   CostC cost;
@@ -199,6 +199,30 @@ struct RpgdSelectArgs {
   float* u_out;            // [1] or null
   int freeze_prev;
   int32_t* best_idx_out;   // [k]
+};
+
+// Gradient-assisted CEM (reference optimizer_cem_naive_grad_tf.py, optimizer_cem_grad_bharadhwaj_tf.py): population stored like RPGD
+struct GradCemSampleArgs {
+  int H, ld, col0, cnt;    // dst[t * ld + col0 + r] for r < cnt, t < H
+  const float *mu, *sd;    // [H]
+  NoiseSrc noise;          // rows 0..cnt-1, per_rollout = H
+  float lo, hi;
+  float* dst;
+};
+
+struct GradCemRefitArgs {
+  int N, H, k;
+  const float* J;          // [N] costs of the population AFTER its gradient step
+  const float* Q;          // [H][N] that population
+  float* Q_carry;          // [H][N] next buffer: the k elites are written to columns 0..k-1 (rank order), or null
+  float *mu, *sd;          // [H] out
+  int last;                // 1: post-loop clip / shift
+  int u_from_mean;         // 1: u = refit mean[0] (naive-grad :105), 0: u = best sample's first control (bharadhwaj :168)
+  float sd_min, sd_init, mid;
+  float* u_prev;
+  float* u_out;
+  int freeze_prev;
+  int32_t* elite_idx_out;  // [k] or null
 };
 
 constexpr int TOPK_THREADS = 1024;  // keys per top-k block

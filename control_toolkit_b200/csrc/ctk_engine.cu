@@ -77,6 +77,7 @@ struct ctk_handle {
   // rpgd
   float *d_Q[2] = {nullptr, nullptr}, *d_m[2] = {nullptr, nullptr}, *d_v[2] = {nullptr, nullptr}, *d_ages[2] = {nullptr, nullptr};
   int cur = 0;
+  const float* pending_s = nullptr;  // gradient-assisted CEM modes: state pointer of the tick in flight
   float *d_unom_log = nullptr, *d_ages_log = nullptr, *d_Q_log = nullptr;
   int32_t* d_best_idx = nullptr;
   // logs
@@ -314,6 +315,18 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
     A(dalloc(&h->d_unom_log, (size_t)H), "unom_log"); A(dalloc(&h->d_ages_log, (size_t)N), "ages_log");
     A(dalloc(&h->d_Q_log, (size_t)N * H), "Q_log");
     A(dalloc(&h->d_best_idx, (size_t)N), "best_idx");
+    if (cfg->rpgd_gradient_mode >= 2) {  // gradient-assisted CEM: distribution + per-iteration elite log on top of the population
+      int iters = cfg->cem_outer_it;
+      if (cfg->cem_warmup && cfg->cem_warmup_iterations > iters) iters = cfg->cem_warmup_iterations;
+      if (!(cfg->rpgd_gradient_mode <= 3 && cfg->cem_best_k >= 1 && cfg->cem_best_k <= N && cfg->cem_outer_it >= 1 && h->period == 1 &&
+            iters >= 1)) {
+        ctk_destroy(h);
+        return fail(CTK_EINVAL, "gradient-assisted CEM needs 1 <= cem_best_k <= num_rollouts, cem_outer_it >= 1 and inducing-point period 1");
+      }
+      A(dalloc(&h->d_mu, (size_t)H), "mu"); A(dalloc(&h->d_sd, (size_t)H), "sd");
+      h->elite_log_cap = iters;
+      A(dalloc(&h->d_elite_idx, (size_t)iters * cfg->cem_best_k), "elite_idx");
+    }
   }
   if (rc == CTK_OK) A(upload_consts(h), "upload_consts");
   if (rc != CTK_OK) { std::string keep = g_err; ctk_destroy(h); g_err = keep; return rc; }
@@ -453,6 +466,13 @@ extern "C" int ctk_reset(ctk_handle* h) {
     CU(cudaMemcpyAsync(h->d_sd, sd.data(), sizeof(float) * h->H, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->cem_it = 0;
+  } else if (h->cfg.rpgd_gradient_mode >= 2) {
+    // optimizer_cem_naive_grad_tf.py:116-119 / optimizer_cem_grad_bharadhwaj_tf.py:180-184: only the distribution (and count) is
+    // reset; the Keras Adam slots of the bharadhwaj variant survive optimizer_reset()
+    CU(cudaMemcpyAsync(h->d_mu, tmp.data(), sizeof(float) * h->H, cudaMemcpyHostToDevice, h->stream));
+    std::vector<float> sd((size_t)h->H, h->cfg.cem_initial_action_stdev);
+    CU(cudaMemcpyAsync(h->d_sd, sd.data(), sizeof(float) * h->H, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
   } else {
     NoiseSrc ns{};
     int rcn = make_noise(h, STREAM_RPGD_INIT, h->n_ind, h->cfg.rpgd_distribution == CTK_DIST_UNIFORM, (size_t)h->N, &ns);
@@ -674,8 +694,66 @@ static int cem_finish(ctk_handle* h, const uint64_t* cand, int cnt, float* u_out
   return CTK_OK;
 }
 
+// Gradient-assisted CEM tick (rpgd_gradient_mode 2: optimizer_cem_naive_grad_tf.py:90-114, 3: optimizer_cem_grad_bharadhwaj_tf.py:151-178)
+static int gradcem_tick(ctk_handle* h, const float* s_dev, float* u_out_dev) {
+  const ctk_config& c = h->cfg;
+  const bool carry = c.rpgd_gradient_mode == 3;
+  const int N = h->N, H = h->H, k = c.cem_best_k;
+  const int iters = (carry && c.cem_warmup && h->count == 0) ? c.cem_warmup_iterations : c.cem_outer_it;
+  const int kc = carry ? k : 0;
+  auto sample = [&](int col0, int cnt, uint32_t sub) -> int {
+    if (cnt <= 0) return CTK_OK;
+    GradCemSampleArgs a{};
+    int rcn = make_noise(h, STREAM_CEM | (sub << 8), H, 0, (size_t)cnt, &a.noise);
+    if (rcn != CTK_OK) return rcn;
+    a.H = H; a.ld = N; a.col0 = col0; a.cnt = cnt; a.mu = h->d_mu; a.sd = h->d_sd; a.lo = c.action_low; a.hi = c.action_high;
+    a.dst = h->d_Q[h->cur];
+    h->launches++;
+    CU(launch_gradcem_sample(a, h->stream));
+    return CTK_OK;
+  };
+  int rc = carry ? sample(0, k, 0) : CTK_OK;  // bharadhwaj :159 the first "elites" are plain samples
+  if (rc != CTK_OK) return rc;
+  h->elite_log_rows = 0;
+  for (int it = 0; it < iters; ++it) {
+    rc = sample(kc, N - kc, (uint32_t)it + 1);
+    if (rc != CTK_OK) return rc;
+    RpgdGradArgs a{};
+    a.N = N; a.H = H; a.iters = 1; a.s0 = s_dev; a.u_prev = h->d_u_prev;
+    a.Q = h->d_Q[h->cur]; a.m = h->d_m[0]; a.v = h->d_v[0];
+    a.lo = c.action_low; a.hi = c.action_high; a.lr = c.rpgd_learning_rate; a.gradmax_clip = c.rpgd_gradmax_clip;
+    a.beta1 = c.rpgd_beta_1; a.beta2 = c.rpgd_beta_2; a.eps = c.rpgd_epsilon; a.adam_step0 = h->adam_step;
+    a.adam_form = carry ? 0 : 2;
+    a.ode = h->ode; a.fwd = h->fwd; a.cost = h->cost; a.J = h->d_J; a.log_traj_soa = h->d_log_traj_soa;
+    const int B = 32;
+    const size_t smem = sizeof(float) * (size_t)H * B * 8;
+    if (smem > 227 * 1024) return fail(CTK_EINVAL, "mpc_horizon too large for the shared-memory tape (max 227)");
+    h->launches++;
+    {
+      KernelTimer kt(h);
+      CU(launch_rpgd_grad(h->cost.kind, c.logging != 0, (N + B - 1) / B, B, smem, h->stream, a));
+    }
+    if (carry) h->adam_step += 1;
+    const bool last = it == iters - 1;
+    if (last && c.logging) CU(cudaMemcpyAsync(h->d_Q_log, h->d_Q[h->cur], sizeof(float) * N * H, cudaMemcpyDeviceToDevice, h->stream));
+    GradCemRefitArgs r{};
+    r.N = N; r.H = H; r.k = k; r.J = h->d_J; r.Q = h->d_Q[h->cur]; r.Q_carry = carry ? h->d_Q[h->cur ^ 1] : nullptr;
+    r.mu = h->d_mu; r.sd = h->d_sd; r.last = last ? 1 : 0; r.u_from_mean = carry ? 0 : 1;
+    r.sd_min = c.cem_stdev_min; r.sd_init = c.cem_initial_action_stdev; r.mid = 0.5f * (c.action_low + c.action_high);
+    r.u_prev = h->d_u_prev; r.u_out = u_out_dev; r.freeze_prev = c.freeze_previous_input;
+    r.elite_idx_out = (it < h->elite_log_cap) ? h->d_elite_idx + (size_t)it * k : nullptr;
+    h->launches++;
+    CU(launch_gradcem_refit(r, h->stream));
+    if (r.elite_idx_out) h->elite_log_rows++;
+    if (carry) h->cur ^= 1;
+  }
+  h->count++;
+  return CTK_OK;
+}
+
 static int rpgd_local(ctk_handle* h, const float* s_dev) {
   const ctk_config& c = h->cfg;
+  if (c.rpgd_gradient_mode >= 2) { h->pending_s = s_dev; return CTK_OK; }  // the whole tick runs in rpgd_finish (needs u_out)
   const int iters = (h->count == 0) ? c.rpgd_first_iter_count : c.rpgd_outer_its;  // optimizer_rpgd.py:397-400
   RpgdGradArgs a{};
   a.N = h->N; a.H = h->H; a.iters = iters; a.s0 = s_dev; a.u_prev = h->d_u_prev;
@@ -698,7 +776,8 @@ static int rpgd_local(ctk_handle* h, const float* s_dev) {
 
 static int rpgd_finish(ctk_handle* h, float* u_out_dev) {
   const ctk_config& c = h->cfg;
-  const int grad_mode = c.rpgd_gradient_mode ? 1 : 0;
+  if (c.rpgd_gradient_mode >= 2) return gradcem_tick(h, h->pending_s, u_out_dev);
+  const int grad_mode = c.rpgd_gradient_mode == 1 ? 1 : 0;
   const int resample = (!grad_mode && h->count % c.rpgd_resamp_per == 0) ? 1 : 0;  // optimizer_rpgd.py:449
   NoiseSrc ns{};
   if (grad_mode) {  // one uniform draw per row for the vacated last step (optimizer_gradient_tf.py:142-147)
@@ -930,8 +1009,9 @@ static int state_ptr(ctk_handle* h, int which, float** p, size_t* n, bool* tmajo
     case CTK_STATE_CEM_MU: *p = h->d_mu; *n = H; break;
     case CTK_STATE_CEM_STD: *p = h->d_sd; *n = H; break;
     case CTK_STATE_RPGD_Q: *p = h->d_Q[h->cur]; *n = N * H; *tmajor = true; break;
-    case CTK_STATE_RPGD_M: *p = h->d_m[h->cur]; *n = N * H; *tmajor = true; break;
-    case CTK_STATE_RPGD_V: *p = h->d_v[h->cur]; *n = N * H; *tmajor = true; break;
+    // gradient-assisted CEM keeps its Adam moments attached to the population ROWS (never permuted): buffer 0
+    case CTK_STATE_RPGD_M: *p = h->d_m[h->cfg.rpgd_gradient_mode >= 2 ? 0 : h->cur]; *n = N * H; *tmajor = true; break;
+    case CTK_STATE_RPGD_V: *p = h->d_v[h->cfg.rpgd_gradient_mode >= 2 ? 0 : h->cur]; *n = N * H; *tmajor = true; break;
     case CTK_STATE_RPGD_AGES: *p = h->d_ages[h->cur]; *n = N; break;
     case CTK_STATE_U_PREV: *p = h->d_u_prev; *n = 1; break;
     default: return fail(CTK_EINVAL, "unknown state id");
@@ -1073,6 +1153,7 @@ extern "C" int ctk_get_log(ctk_handle* h, int which, void* dst, size_t nbytes) {
     }
     case CTK_LOG_ELITE_IDX:
       if (h->cfg.optimizer == CTK_OPT_CEM) { src = h->d_elite_idx; need = (size_t)h->elite_log_rows * h->cfg.cem_best_k * 4; }
+      else if (h->cfg.optimizer == CTK_OPT_RPGD && h->cfg.rpgd_gradient_mode >= 2) { src = h->d_elite_idx; need = (size_t)h->elite_log_rows * h->cfg.cem_best_k * 4; }
       else if (h->cfg.optimizer == CTK_OPT_RPGD) { src = h->d_best_idx; need = (size_t)h->cfg.rpgd_keep_k * 4; }
       else return fail(CTK_EINVAL, "no elite log for MPPI");
       break;

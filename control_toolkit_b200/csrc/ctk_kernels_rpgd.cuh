@@ -65,7 +65,10 @@ __global__ void __launch_bounds__(32) rpgd_grad_kernel(const RpgdGradArgs a) {
       const size_t gi = (size_t)t * a.N + n;
       float mm = a.m[gi], vv = a.v[gi];
       float q = sq[t * B + tid];
-      if (a.adam_form == 1) {
+      if (a.adam_form == 2) {
+        // plain gradient descent on the clipped gradient, reference optimizer_cem_naive_grad_tf.py:72-74
+        q = __fsub_rn(q, __fmul_rn(a.lr, g));
+      } else if (a.adam_form == 1) {
         // torch form, reference optimizer_rpgd.py:56-82
         mm = fmaf(g, omb1, mm * b1);
         vv = fmaf(g * g, omb2, vv * b2);
@@ -176,6 +179,68 @@ __global__ void rpgd_init_kernel(const RpgdSelectArgs a) {
     a.mn[idx] = 0.0f;
     a.vn[idx] = 0.0f;
     if (t == 0) a.agesn[n] = 0.0f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gradient-assisted CEM (reference optimizer_cem_naive_grad_tf.py:58-87, optimizer_cem_grad_bharadhwaj_tf.py:93-132)
+// ---------------------------------------------------------------------------------------------------------------
+// Q[t][col0 + r] = clip(mu_t + z_{r,t} * sd_t)  (multiply and add separately rounded, as the reference's tf ops)
+__global__ void gradcem_sample_kernel(const GradCemSampleArgs a) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < a.cnt * a.H; idx += gridDim.x * blockDim.x) {
+    const int t = idx / a.cnt, r = idx - t * a.cnt;
+    const float z = noise1(a.noise, (uint32_t)r, t);
+    a.dst[(size_t)t * a.ld + a.col0 + r] = fminf(fmaxf(__fadd_rn(a.mu[t], __fmul_rn(z, a.sd[t])), a.lo), a.hi);
+  }
+}
+
+// argsort of the N <= 1024 costs (ties to the lower index), elite gather in rank order, mean / population std per horizon step,
+// elites carried into the next population buffer, and on the last outer iteration the clip / shift / u of ``step``
+__global__ void __launch_bounds__(TOPK_THREADS) gradcem_refit_kernel(const GradCemRefitArgs a) {
+  __shared__ uint64_t sh[TOPK_THREADS];
+  __shared__ int sh_best[TOPK_THREADS];
+  const int tid = threadIdx.x;
+  uint64_t key = (tid < a.N) ? make_key(a.J[tid], (uint32_t)tid) : KEY_MAX;
+  key = block_bitonic_sort(key, sh);
+  if (tid < a.k) {
+    sh_best[tid] = (int)(key & 0xffffffffu);
+    if (a.elite_idx_out != nullptr) a.elite_idx_out[tid] = sh_best[tid];
+  }
+  __syncthreads();
+  for (int t = tid; t < a.H; t += blockDim.x) {
+    const float* row = a.Q + (size_t)t * a.N;
+    float acc = 0.0f;
+    for (int e = 0; e < a.k; ++e) acc += row[sh_best[e]];
+    const float new_mu = acc / (float)a.k;
+    float var = 0.0f;
+    for (int e = 0; e < a.k; ++e) {
+      const float q = row[sh_best[e]];
+      const float d = q - new_mu;
+      var = fmaf(d, d, var);
+      if (a.Q_carry != nullptr) a.Q_carry[(size_t)t * a.N + e] = q;
+    }
+    const float new_sd = sqrtf(var / (float)a.k);
+    if (!a.last) {
+      a.mu[t] = new_mu;
+      a.sd[t] = new_sd;
+    } else {
+      const float sdc = fminf(fmaxf(new_sd, a.sd_min), 10.0f);  // naive :103 / bharadhwaj :139
+      if (t > 0) {
+        a.mu[t - 1] = new_mu;
+        a.sd[t - 1] = sdc;
+      } else {
+        const float u = a.u_from_mean ? new_mu : row[sh_best[0]];
+        if (!a.freeze_prev) a.u_prev[0] = u;
+        if (a.u_out != nullptr) a.u_out[0] = u;
+      }
+    }
+  }
+  if (a.last) {
+    __syncthreads();  // column H-1 is written by the thread of column H (none) -> fill after every shifted store is issued
+    if (tid == 0) {
+      a.mu[a.H - 1] = a.mid;
+      a.sd[a.H - 1] = a.sd_init;
+    }
   }
 }
 

@@ -26,6 +26,8 @@ cudaError_t launch_cem_refit(const CemRefitArgs& a, cudaStream_t st);
 cudaError_t launch_rpgd_grad(int kind, bool log, int nblocks, int block, size_t smem, cudaStream_t st, const RpgdGradArgs& a);
 cudaError_t launch_rpgd_select(const RpgdSelectArgs& a, cudaStream_t st);
 cudaError_t launch_rpgd_init(const RpgdSelectArgs& a, cudaStream_t st);
+cudaError_t launch_gradcem_sample(const GradCemSampleArgs& a, cudaStream_t st);
+cudaError_t launch_gradcem_refit(const GradCemRefitArgs& a, cudaStream_t st);
 
 cudaError_t launch_single_rollout(int pred, const float* s0, const float* Q, int H, const DevConsts* kc, const MlpDev& mlp, const float* u_prev, float* traj, float* summed, cudaStream_t st);
 cudaError_t launch_fma_peak(float* out, int blocks, int threads, int iters, cudaStream_t st);

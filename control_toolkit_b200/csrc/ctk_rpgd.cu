@@ -24,6 +24,15 @@ cudaError_t launch_rpgd_init(const RpgdSelectArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+cudaError_t launch_gradcem_sample(const GradCemSampleArgs& a, cudaStream_t st) {
+  gradcem_sample_kernel<<<(a.cnt * a.H + 255) / 256, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_gradcem_refit(const GradCemRefitArgs& a, cudaStream_t st) {
+  gradcem_refit_kernel<<<1, TOPK_THREADS, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
 // FP32 FMA-chain microbenchmark: 8 independent chains per thread, 16x unrolled
 __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
   float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;

@@ -121,9 +121,15 @@ typedef struct ctk_config {
   int32_t mlp_engine;             /* CTK_MLP_*                                                                   */
   int32_t cem_uniform_actions;    /* 1: random shooting (reference optimizer_random_action_tf.py:56-68): every tick samples
                                      Q ~ U[action_low, action_high) instead of N(dist_mue, stdev); use cem_outer_it = cem_best_k = 1 */
-  int32_t rpgd_gradient_mode;     /* 1: population gradient descent (reference optimizer_gradient_tf.py:101-167): no ranking-based
+  int32_t rpgd_gradient_mode;     /* 0: RPGD.  1: population gradient descent (reference optimizer_gradient_tf.py:101-167): no ranking-based
                                      resampling; every tick all rows shift by one step and their last control is redrawn from
-                                     U[action_low, action_high) (one draw per row); use period 1, keep_k = num_rollouts       */
+                                     U[action_low, action_high) (one draw per row); use period 1, keep_k = num_rollouts.
+                                     2: CEM with one clipped gradient-descent step per sample before ranking (reference
+                                     optimizer_cem_naive_grad_tf.py:58-114; u = first element of the refit mean).
+                                     3: CEM with carried elites and one Keras-Adam step on the population per outer iteration
+                                     (reference optimizer_cem_grad_bharadhwaj_tf.py:93-178; moments persist per row).
+                                     Modes 2/3 read the cem_* fields (outer_it, best_k, initial_action_stdev, stdev_min, warmup*)
+                                     and rpgd_learning_rate / gradmax_clip / beta / epsilon; period must be 1                  */
   int32_t reserved[5];
 } ctk_config;
 

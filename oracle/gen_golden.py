@@ -80,19 +80,19 @@ CASES = {
                                  gradmax_clip=2, warmup=True, warmup_iterations=7), 4, False),
     # reference Optimizers/optimizer_cem_naive_grad_tf.py (template block config_optimizers.yml:23-32): CEM whose samples take one
     # clipped gradient-descent step before they are ranked
-    "cem_naive_grad_n200": ("cem-naive-grad-tf", "ODE", "quadratic_boundary_grad",
+    "gradcem_naive_n200": ("cem-naive-grad-tf", "ODE", "quadratic_boundary_grad",
                             dict(seed=42, mpc_horizon=35, mpc_timestep=0.02, cem_outer_it=1, num_rollouts=200, cem_stdev_min=0.1,
                                  cem_initial_action_stdev=0.5, cem_best_k=40, learning_rate=0.1, gradmax_clip=10), 5, True),
-    "cem_naive_grad_it3_n96": ("cem-naive-grad-tf", "ODE", "quadratic_boundary_grad",
+    "gradcem_naive_it3_n96": ("cem-naive-grad-tf", "ODE", "quadratic_boundary_grad",
                                dict(seed=42, mpc_horizon=20, mpc_timestep=0.02, cem_outer_it=3, num_rollouts=96, cem_stdev_min=0.05,
                                     cem_initial_action_stdev=0.7, cem_best_k=12, learning_rate=0.2, gradmax_clip=2), 4, False),
     # reference Optimizers/optimizer_cem_grad_bharadhwaj_tf.py (template block config_optimizers.yml:33-47): elites carried between the
     # outer iterations, one Adam step (persistent moments) on the whole population before ranking
-    "cem_bharadhwaj_n32": ("cem-grad-bharadhwaj-tf", "ODE", "quadratic_boundary_grad",
+    "gradcem_bharadhwaj_n32": ("cem-grad-bharadhwaj-tf", "ODE", "quadratic_boundary_grad",
                            dict(seed=42, mpc_horizon=50, mpc_timestep=0.02, learning_rate=0.05, adam_beta_1=0.9, adam_beta_2=0.999,
                                 adam_epsilon=1.0e-08, num_rollouts=32, cem_best_k=8, cem_outer_it=2, cem_initial_action_stdev=2,
                                 cem_stdev_min=1.e-6, gradmax_clip=5, warmup=False, warmup_iterations=250), 6, True),
-    "cem_bharadhwaj_warmup_n64": ("cem-grad-bharadhwaj-tf", "ODE", "quadratic_boundary_grad",
+    "gradcem_bharadhwaj_warmup_n64": ("cem-grad-bharadhwaj-tf", "ODE", "quadratic_boundary_grad",
                                   dict(seed=42, mpc_horizon=30, mpc_timestep=0.02, learning_rate=0.1, adam_beta_1=0.9, adam_beta_2=0.999,
                                        adam_epsilon=1.0e-08, num_rollouts=64, cem_best_k=16, cem_outer_it=3, cem_initial_action_stdev=0.8,
                                        cem_stdev_min=1.e-3, gradmax_clip=3, warmup=True, warmup_iterations=5), 3, False),

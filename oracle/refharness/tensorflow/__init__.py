@@ -23,8 +23,10 @@ def convert_to_tensor(x, dtype=float32):
     return _torch.as_tensor(_np.asarray(x), dtype=dtype)
 
 
-def constant(x, dtype=None):
+def constant(x, dtype=None, shape=None):
     a = _np.asarray(x)
+    if shape is not None:  # tf.constant(value, shape=...): a scalar fills, anything else is reshaped (optimizer_cem_naive_grad_tf.py:106)
+        a = _np.full(tuple(shape), a.reshape(-1)[0], a.dtype) if a.size == 1 else a.reshape(tuple(shape))
     if dtype is None and a.dtype.kind in "iu":
         return a  # python-side integer constants (np.tile reps at optimizer_cem_tf.py:86)
     return _torch.as_tensor(a, dtype=dtype or float32)
@@ -32,6 +34,10 @@ def constant(x, dtype=None):
 
 def zeros(shape, dtype=float32):
     return _torch.zeros(tuple(int(s) for s in (shape if hasattr(shape, "__iter__") else (shape,))), dtype=dtype)
+
+
+def reshape(x, shape):
+    return _torch.as_tensor(_np.asarray(x) if not isinstance(x, _torch.Tensor) else x).reshape(tuple(int(v) for v in shape))
 
 
 def ones(shape, dtype=float32):
@@ -78,6 +84,10 @@ def squeeze(x):
 
 
 class _Math:
+    @staticmethod
+    def reduce_mean(x, axis=None, keepdims=False):
+        return _torch.mean(x, dim=axis, keepdim=keepdims)
+
     @staticmethod
     def reduce_std(x, axis=None, keepdims=False):
         mu = _torch.mean(x, dim=axis, keepdim=True)
@@ -126,10 +136,10 @@ class _Var(_torch.Tensor):
     __torch_function__ = _torch._C._disabled_torch_function_impl
 
     @staticmethod
-    def __new__(cls, value, dtype=float32):
-        return _torch.Tensor._make_subclass(cls, _torch.as_tensor(value, dtype=dtype).detach().clone(), False)
+    def __new__(cls, initial_value=None, trainable=True, dtype=float32, **_):
+        return _torch.Tensor._make_subclass(cls, _torch.as_tensor(initial_value, dtype=dtype).detach().clone(), False)
 
-    def __init__(self, value, dtype=float32):
+    def __init__(self, initial_value=None, trainable=True, dtype=float32, **_):
         pass
 
     def assign(self, value):

@@ -6,6 +6,7 @@ import numpy as np
 
 from oracle import spec
 from oracle.cem import CEMOracle
+from oracle.cem_grad import CEMBharadhwajOracle, CEMNaiveGradOracle
 from oracle.gradient import GradientOracle
 from oracle.mppi import MPPIOracle
 from oracle.random_action import RandomActionOracle
@@ -37,7 +38,7 @@ def make_oracle(meta, **over):
     cfg = dict(meta["cfg"])
     cfg.update(over)
     cls = {"mppi": MPPIOracle, "cem-tf": CEMOracle, "rpgd": RPGDOracle, "random-action-tf": RandomActionOracle,
-           "gradient-tf": GradientOracle}[meta["optimizer"]]
+           "gradient-tf": GradientOracle, "cem-naive-grad-tf": CEMNaiveGradOracle, "cem-grad-bharadhwaj-tf": CEMBharadhwajOracle}[meta["optimizer"]]
     return cls(pred, cost, **cfg)
 
 
@@ -61,7 +62,8 @@ def oracle_state(o, meta):
     """The optimizer state array the parity contract names (u_nom / dist_mue / Q)."""
     if meta["optimizer"] == "random-action-tf":
         return np.atleast_1d(np.asarray(o.u, np.float32))
-    return {"mppi": lambda: o.u_nom, "cem-tf": lambda: o.dist_mue, "rpgd": lambda: o.Q, "gradient-tf": lambda: o.Q}[meta["optimizer"]]().numpy()
+    return {"mppi": lambda: o.u_nom, "cem-tf": lambda: o.dist_mue, "rpgd": lambda: o.Q, "gradient-tf": lambda: o.Q,
+            "cem-naive-grad-tf": lambda: o.dist_mue, "cem-grad-bharadhwaj-tf": lambda: o.dist_mue}[meta["optimizer"]]().numpy()
 
 
 _FLOOR_CACHE = {}

@@ -120,3 +120,25 @@ def test_gradient_oracle_matches_reference(name):
         assert rel_err(o.v.numpy(), z[f"adam_v_{t}"]) < 2e-5
         assert o.adam_step == int(z[f"adam_step_{t}"][0])
         assert rel_err(o.last["J"], z[f"J_{t}"]) < 5e-6
+
+
+@pytest.mark.parametrize("name", golden_names("gradcem_"))
+def test_cem_grad_oracles_match_reference(name):
+    """oracle/cem_grad.py vs the unmodified reference Optimizers/optimizer_cem_naive_grad_tf.py and
+    optimizer_cem_grad_bharadhwaj_tf.py: identical elite index lists in every outer iteration."""
+    z, meta = load_golden(name)
+    o = make_oracle(meta)
+    rng = replay(meta)
+    o.reset(rng)
+    for t in range(meta["ticks"]):
+        u = o.step(z["states"][t], rng)
+        np.testing.assert_array_equal(o.last["elite_idx"], z[f"elite_idx_{t}"])
+        assert rel_err(u, z[f"u_{t}"]) < 5e-6
+        assert rel_err(o.dist_mue.numpy(), z[f"dist_mue_{t}"]) < 5e-6
+        assert rel_err(o.stdev.numpy(), z[f"stdev_{t}"]) < 5e-6
+        assert rel_err(o.last["Q"], z[f"Qn_{t}"]) < 5e-6
+        assert rel_err(o.last["J"], z[f"J_{t}"]) < 5e-6
+        if f"adam_m_{t}" in z:
+            assert rel_err(o.m.numpy(), z[f"adam_m_{t}"]) < 2e-5
+            assert rel_err(o.v.numpy(), z[f"adam_v_{t}"]) < 2e-5
+            assert o.adam_step == int(z[f"adam_step_{t}"][0])
