@@ -132,9 +132,10 @@ class optimizer_rpgd(template_optimizer):
             self._feed_noise(lib, [(self._draw_kind(), (self.num_rollouts - self.opt_keep_k,
                                                         self.number_of_interpolation_inducing_points,
                                                         self.num_control_inputs))])
-        u = self._tick(lib, s)
         H, nu, N = self.mpc_horizon, self.num_control_inputs, self.num_rollouts
-        self.u_nom = self._get_log(L.LOG_U_NOM, (1, H, nu))  # :426
+        u = self._tick(lib, s, L.STATE_U_NOM, H)  # u and Q[best] (:426) come back through the same host mirror
+        self.u_nom = (self._state_buf.reshape(1, H, nu).copy() if self._state_buf is not None
+                      else self._get_log(L.LOG_U_NOM, (1, H, nu)))
         if self.optimizer_logging:
             self.rollout_trajectories = self._get_log(L.LOG_ROLLOUTS, (N, H + 1, 6))
             self.logging_values["Q_logged"] = self._get_log(L.LOG_Q, (N, H, nu))

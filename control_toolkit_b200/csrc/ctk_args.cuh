@@ -19,6 +19,25 @@ struct NoiseSrc {
   int uniform;          // 0: N(0,1)  1: U[0,1)
 };
 
+// Initial state of a tick: either a device pointer (device-resident callers, ctk_step_device / ctk_step_local) or the six
+// values themselves inside the kernel parameters (host callers: ctk_step needs no host->device copy at all).
+struct S0 {
+  const float* p;  // [6] device, or null -> v
+  float v[6];
+#if defined(__CUDACC__)
+  __device__ __forceinline__ float ld(int i) const { return p != nullptr ? p[i] : v[i]; }
+#endif
+};
+
+// Result mirror in MAPPED pinned host memory (device view).  The kernel that finishes a tick stores u, the status word and
+// (optionally) one [H] state array there, then a system-scope fence and the launch's sequence number: the host caller
+// polls that word instead of enqueueing device->host copies and synchronising the stream.
+// Layout (floats): [8] u  [9] status  [10] sequence flag (uint32 bits)  [16 .. 16+H) state array.
+struct HostMirror {
+  float* p;          // null: no mirror (device-resident callers)
+  unsigned int seq;  // never 0
+};
+
 struct MlpDev {
   int hidden;              // <= 128, multiple of 16
   const float* blob;       // device: W1[6][hid] | b1[hid] | W2[hid][hid] | b2[hid] | W3T[5][hid] | b3[8]
@@ -68,11 +87,12 @@ struct MppiFuse {
   float* u_prev;             // [1] out (unless frozen)
   float* u_out;              // [2] out: u, exchange status (0 ok, 1 timeout)
   int freeze_prev;
+  HostMirror host;           // mode 2: u / status / u_nom[H] mirrored to the host caller
 };
 
 struct MppiArgs {
   int N, off, H, period, n_ind;  // local rollouts, global id offset, horizon, inducing-point period / count
-  const float* s0;               // [6] device
+  S0 s0;                         // initial state
   const float* u_nom;            // [H] device, UNSHIFTED state of the previous tick (shift applied on read, :184)
   const float* u_prev;           // [1] device, previous_input of the cost (self.u, :211)
   NoiseSrc noise;                // per_rollout = n_ind
@@ -119,7 +139,7 @@ struct OdeHot {
 
 struct MppiOdeArgs {
   int N, off, H, period, n_ind;
-  const float* s0;      // [6]
+  S0 s0;                // initial state
   const float* u_nom;   // [H] unshifted
   const float* u_prev;  // [1]
   NoiseSrc noise;
@@ -134,7 +154,7 @@ struct MppiOdeArgs {
 
 struct CemArgs {
   int N, off, H;
-  const float* s0;      // [6]
+  S0 s0;                // initial state
   const float* mu;      // [H] dist_mue
   const float* sd;      // [H] stdev
   const float* u_prev;  // [1]
@@ -160,11 +180,12 @@ struct CemRefitArgs {
   float* u_out;              // [1] or null
   int freeze_prev;
   int32_t* elite_idx_out;    // [k] global ids, best first (log) or null
+  HostMirror host;           // last iteration: u mirrored to the host caller
 };
 
 struct RpgdGradArgs {
   int N, H, iters;
-  const float* s0;      // [6]
+  S0 s0;                // initial state
   const float* u_prev;  // [1] previous_input (self.u)
   float* Q;             // [H][N] in/out
   float* m;             // [H][N] in/out
@@ -199,6 +220,7 @@ struct RpgdSelectArgs {
   float* u_out;            // [1] or null
   int freeze_prev;
   int32_t* best_idx_out;   // [k]
+  HostMirror host;         // u and u_nom_out[H] mirrored to the host caller
 };
 
 // Gradient-assisted CEM (reference optimizer_cem_naive_grad_tf.py, optimizer_cem_grad_bharadhwaj_tf.py): population stored like RPGD
@@ -223,6 +245,7 @@ struct GradCemRefitArgs {
   float* u_out;
   int freeze_prev;
   int32_t* elite_idx_out;  // [k] or null
+  HostMirror host;         // last iteration: u mirrored to the host caller
 };
 
 constexpr int TOPK_THREADS = 1024;  // keys per top-k block

@@ -8,6 +8,14 @@
 
 namespace ctk {
 
+// Publish a tick's result mirror to the host caller (see HostMirror): every thread that stored into m.p must have passed a
+// block barrier before the ONE calling thread gets here.
+__device__ __forceinline__ void host_publish(const HostMirror& m) {
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned int*>(m.p + 10) = m.seq;
+}
+
+
 // ----------------------------------------------------------------------------------------------------------
 // K0: Philox4x32-10 (Salmon et al. 2011), the generator behind tf.random.Generator.from_seed
 // (reference others/globals_and_utils.py:95-97).  Counter words: (draw block, global rollout id, tick, stream).

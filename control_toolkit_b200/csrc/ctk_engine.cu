@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -63,7 +65,10 @@ struct ctk_handle {
   unsigned int xseq = 0;
   // common
   float *d_s0 = nullptr, *d_u_prev = nullptr, *d_u_out = nullptr, *d_J = nullptr;
-  float *h_pin = nullptr;  // pinned staging: s[8] | u[8] | one [H] state array (ctk_step_state)
+  float *h_pin = nullptr;  // MAPPED pinned memory: s[8] | u, status, sequence flag .. [16) | one [H] state array (HostMirror layout)
+  float *d_pin = nullptr;  // the device's view of h_pin
+  HostMirror mirror{nullptr, 0};  // non-null only while a host-facing tick (ctk_step / ctk_step_state) is being enqueued
+  unsigned int hseq = 0;
   // mppi
   float *d_u_nom = nullptr, *d_partials = nullptr, *d_record = nullptr;
   // cem
@@ -240,7 +245,8 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
   A(dalloc(&h->d_J, (size_t)N), "J");
   A(cudaMalloc((void**)&h->d_kc, sizeof(DevConsts)), "consts");
   A(dalloc(&h->d_kx, 4), "kx");
-  A(cudaMallocHost((void**)&h->h_pin, (16 + (size_t)H) * sizeof(float)), "pinned");
+  A(cudaHostAlloc((void**)&h->h_pin, (32 + (size_t)H) * sizeof(float), cudaHostAllocMapped), "pinned");
+  if (h->h_pin) { memset(h->h_pin, 0, (32 + (size_t)H) * sizeof(float)); A(cudaHostGetDevicePointer((void**)&h->d_pin, h->h_pin, 0), "pinned (device view)"); }
   if (cfg->logging) {
     A(dalloc(&h->d_log_traj_soa, (size_t)(H + 1) * 6 * N), "log_traj");
     A(dalloc(&h->d_log_Q_soa, (size_t)H * N), "log_Q");
@@ -541,6 +547,14 @@ static void mppi_ode_geometry(ctk_handle* h) {
   h->ode_kernel = true;
 }
 
+// s_dev == nullptr: the state sits in h_pin[0..5] (host caller) and travels inside the kernel parameters
+static S0 make_s0(const ctk_handle* h, const float* s_dev) {
+  S0 s{};
+  s.p = s_dev;
+  if (s_dev == nullptr) for (int i = 0; i < 6; ++i) s.v[i] = h->h_pin[i];
+  return s;
+}
+
 static int make_fuse(ctk_handle* h, int mode, float* u_out_dev, MppiFuse* out) {
   MppiFuse f{};
   f.mode = mode;
@@ -552,6 +566,7 @@ static int make_fuse(ctk_handle* h, int mode, float* u_out_dev, MppiFuse* out) {
   f.mbox_local = h->d_mbox;
   for (int r = 0; r < CTK_MAX_PEERS; ++r) f.mbox_peer[r] = h->mbox_peer[r];
   f.u_nom = h->d_u_nom; f.u_prev = h->d_u_prev; f.u_out = u_out_dev; f.freeze_prev = h->cfg.freeze_previous_input;
+  if (mode == 2) f.host = h->mirror;
   if (mode == 2 && h->xworld > 1) {
     f.world = h->xworld; f.rank = h->xrank;
     h->xseq++;
@@ -575,7 +590,7 @@ static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_
     MppiOdeArgs a{};
     a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
     a.trace = h->d_trace;
-    a.s0 = s_dev; a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = ns; a.k = h->ode_hot;
+    a.s0 = make_s0(h, s_dev); a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = ns; a.k = h->ode_hot;
     a.J = h->d_J; a.partials = h->d_partials; a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
     a.fuse = fuse;
     h->launches++;
@@ -586,7 +601,7 @@ static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_
   }
   MppiArgs a{};
   a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
-  a.s0 = s_dev; a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = ns;
+  a.s0 = make_s0(h, s_dev); a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = ns;
   a.stdev = c.mppi_stdev; a.lo = c.action_low; a.hi = c.action_high;
   // :154-155 constants pre-multiplied by cc_weight (k_du2, k_udu live in d_kx); the 0.5 R u^2 term shares u^2 with the
   // cost's own cc term (k_cc)
@@ -648,7 +663,7 @@ static int cem_local(ctk_handle* h, const float* s_dev, bool to_k) {
   if (rcn != CTK_OK) return rcn;
   h->cem_noise = ns;
   CemArgs a{};
-  a.N = h->N; a.off = h->off; a.H = h->H; a.s0 = s_dev; a.mu = h->d_mu; a.sd = h->d_sd; a.u_prev = h->d_u_prev; a.noise = ns;
+  a.N = h->N; a.off = h->off; a.H = h->H; a.s0 = make_s0(h, s_dev); a.mu = h->d_mu; a.sd = h->d_sd; a.u_prev = h->d_u_prev; a.noise = ns;
   a.lo = c.action_low; a.hi = c.action_high; a.kc = h->d_kc; a.mlp = h->mlp; a.J = h->d_J;
   a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
   const size_t smem = sizeof(float) * (2 * (size_t)h->H + pred_smem_floats(h));
@@ -686,6 +701,7 @@ static int cem_finish(ctk_handle* h, const uint64_t* cand, int cnt, float* u_out
   a.sd_min = c.cem_stdev_min; a.sd_init = c.cem_initial_action_stdev;
   a.u_prev = h->d_u_prev; a.u_out = u_out_dev; a.freeze_prev = c.freeze_previous_input;
   a.elite_idx_out = (h->elite_log_rows < h->elite_log_cap) ? h->d_elite_idx + (size_t)h->elite_log_rows * c.cem_best_k : nullptr;
+  if (a.last) a.host = h->mirror;
   h->launches++;
   CU(launch_cem_refit(a, h->stream));
   if (a.elite_idx_out) h->elite_log_rows++;
@@ -719,7 +735,7 @@ static int gradcem_tick(ctk_handle* h, const float* s_dev, float* u_out_dev) {
     rc = sample(kc, N - kc, (uint32_t)it + 1);
     if (rc != CTK_OK) return rc;
     RpgdGradArgs a{};
-    a.N = N; a.H = H; a.iters = 1; a.s0 = s_dev; a.u_prev = h->d_u_prev;
+    a.N = N; a.H = H; a.iters = 1; a.s0 = make_s0(h, s_dev); a.u_prev = h->d_u_prev;
     a.Q = h->d_Q[h->cur]; a.m = h->d_m[0]; a.v = h->d_v[0];
     a.lo = c.action_low; a.hi = c.action_high; a.lr = c.rpgd_learning_rate; a.gradmax_clip = c.rpgd_gradmax_clip;
     a.beta1 = c.rpgd_beta_1; a.beta2 = c.rpgd_beta_2; a.eps = c.rpgd_epsilon; a.adam_step0 = h->adam_step;
@@ -742,6 +758,7 @@ static int gradcem_tick(ctk_handle* h, const float* s_dev, float* u_out_dev) {
     r.sd_min = c.cem_stdev_min; r.sd_init = c.cem_initial_action_stdev; r.mid = 0.5f * (c.action_low + c.action_high);
     r.u_prev = h->d_u_prev; r.u_out = u_out_dev; r.freeze_prev = c.freeze_previous_input;
     r.elite_idx_out = (it < h->elite_log_cap) ? h->d_elite_idx + (size_t)it * k : nullptr;
+    if (last) r.host = h->mirror;
     h->launches++;
     CU(launch_gradcem_refit(r, h->stream));
     if (r.elite_idx_out) h->elite_log_rows++;
@@ -756,7 +773,7 @@ static int rpgd_local(ctk_handle* h, const float* s_dev) {
   if (c.rpgd_gradient_mode >= 2) { h->pending_s = s_dev; return CTK_OK; }  // the whole tick runs in rpgd_finish (needs u_out)
   const int iters = (h->count == 0) ? c.rpgd_first_iter_count : c.rpgd_outer_its;  // optimizer_rpgd.py:397-400
   RpgdGradArgs a{};
-  a.N = h->N; a.H = h->H; a.iters = iters; a.s0 = s_dev; a.u_prev = h->d_u_prev;
+  a.N = h->N; a.H = h->H; a.iters = iters; a.s0 = make_s0(h, s_dev); a.u_prev = h->d_u_prev;
   a.Q = h->d_Q[h->cur]; a.m = h->d_m[h->cur]; a.v = h->d_v[h->cur];
   a.lo = c.action_low; a.hi = c.action_high; a.lr = c.rpgd_learning_rate; a.gradmax_clip = c.rpgd_gradmax_clip;
   a.beta1 = c.rpgd_beta_1; a.beta2 = c.rpgd_beta_2; a.eps = c.rpgd_epsilon; a.adam_step0 = h->adam_step; a.adam_form = c.rpgd_adam_form;
@@ -796,6 +813,7 @@ static int rpgd_finish(ctk_handle* h, float* u_out_dev) {
   a.Qn = h->d_Q[nx]; a.mn = h->d_m[nx]; a.vn = h->d_v[nx]; a.agesn = h->d_ages[nx];
   a.u_nom_out = h->d_unom_log; a.u_prev = h->d_u_prev; a.u_out = u_out_dev; a.freeze_prev = c.freeze_previous_input;
   a.best_idx_out = h->d_best_idx;
+  a.host = h->mirror;
   if (c.logging) {  // Q_logged / trajectory_ages_logged are the values BEFORE the warm-start update (:413-415)
     CU(cudaMemcpyAsync(h->d_Q_log, h->d_Q[h->cur], sizeof(float) * h->N * h->H, cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_ages_log, h->d_ages[h->cur], sizeof(float) * h->N, cudaMemcpyDeviceToDevice, h->stream));
@@ -866,33 +884,70 @@ extern "C" int ctk_step_state(ctk_handle* h, const float* s_host, float* u_out_h
   REQ(!tm && n == cnt && cnt <= (size_t)h->H, "ctk_step_state reads the [H] state arrays only");
   return step_host(h, s_host, u_out_host, p, state_out_host, n);
 }
+// Wait until the kernel that finishes the tick has published sequence number `seq` in the mapped result mirror.  Polling a
+// cache line of pinned host memory replaces cudaStreamSynchronize + the device->host copies (measured: ~15 us per step).
+static int wait_host_mirror(ctk_handle* h, unsigned int seq) {
+  volatile unsigned int* flag = reinterpret_cast<volatile unsigned int*>(h->h_pin + 10);
+  const auto t0 = std::chrono::steady_clock::now();
+  unsigned int spins = 0;
+  while (*flag != seq) {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+    if ((++spins & 0x3fffu) != 0) continue;
+    const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (el < 0.05) continue;
+    const cudaError_t e = cudaStreamQuery(h->stream);  // a faulted or finished stream will never publish
+    if (e == cudaSuccess) {
+      if (*flag == seq) break;
+      return fail(CTK_ECUDA, "tick kernels finished without publishing their result to the host mirror");
+    }
+    if (e != cudaErrorNotReady) return fail(CTK_ECUDA, std::string("tick failed on the device: ") + cudaGetErrorString(e));
+    if (el > 60.0) return fail(CTK_ECUDA, "tick did not finish within 60 s");
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return CTK_OK;
+}
+
+// Host-facing tick.  The state travels inside the kernel parameters (S0), the result comes back through the mapped host mirror
+// written by the tick's last kernel: no cudaMemcpy and no stream synchronisation on this path.
 static int step_host(ctk_handle* h, const float* s_host, float* u_out_host, const float* state_dev, float* state_out_host, size_t n_state) {
   REQ(h && s_host && u_out_host, "null pointer");
   if (!h->was_reset) return fail(CTK_ESTATE, "ctk_step before ctk_reset");
   CU(cudaSetDevice(h->cfg.device));
   if (h->cfg.predictor == CTK_PRED_MLP && h->mlp.blob == nullptr) return fail(CTK_ESTATE, "MLP predictor without weights");
   memcpy(h->h_pin, s_host, sizeof(float) * 6);
-  CU(cudaMemcpyAsync(h->d_s0, h->h_pin, sizeof(float) * 6, cudaMemcpyHostToDevice, h->stream));
+  // the mirror carries one [H] array: MPPI's u_nom / RPGD's best sequence; any other state array takes the copy path below
+  const bool state_in_mirror = state_dev != nullptr && h->cfg.rpgd_gradient_mode < 2 &&
+                               ((h->cfg.optimizer == CTK_OPT_MPPI && state_dev == h->d_u_nom) ||
+                                (h->cfg.optimizer == CTK_OPT_RPGD && state_dev == h->d_unom_log));
+  h->hseq++;
+  if (h->hseq == 0) h->hseq = 1;
+  h->mirror = HostMirror{h->d_pin, h->hseq};
   int rc = CTK_OK;
   if (h->cfg.optimizer == CTK_OPT_MPPI) {
     h->tick++;
-    rc = mppi_local(h, h->d_s0, 2, h->d_u_out);
+    rc = mppi_local(h, nullptr, 2, h->d_u_out);
   } else if (h->cfg.optimizer == CTK_OPT_CEM) {
     h->tick++;
     do {
-      rc = cem_local(h, h->d_s0, false);
+      rc = cem_local(h, nullptr, false);
       if (rc != CTK_OK) break;
       rc = cem_finish(h, h->cem_cand_ptr, h->cem_cand, h->d_u_out);
     } while (rc == CTK_OK && h->cem_it != 0);
   } else {
     h->tick++;
-    rc = rpgd_local(h, h->d_s0);
+    rc = rpgd_local(h, nullptr);
     if (rc == CTK_OK) rc = rpgd_finish(h, h->d_u_out);
   }
+  h->mirror = HostMirror{nullptr, 0};
   if (rc != CTK_OK) return rc;
-  CU(cudaMemcpyAsync(h->h_pin + 8, h->d_u_out, 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-  if (state_dev) CU(cudaMemcpyAsync(h->h_pin + 16, state_dev, n_state * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+  if (state_dev && !state_in_mirror) {
+    CU(cudaMemcpyAsync(h->h_pin + 16, state_dev, n_state * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  rc = wait_host_mirror(h, h->hseq);
+  if (rc != CTK_OK) return rc;
   u_out_host[0] = h->h_pin[8];
   if (state_dev) memcpy(state_out_host, h->h_pin + 16, n_state * sizeof(float));
   if (h->h_pin[9] != 0.0f) return fail(CTK_ECUDA, "cross-GPU exchange timed out: a peer shard did not deliver its record within 2 s");
@@ -1005,7 +1060,7 @@ static int state_ptr(ctk_handle* h, int which, float** p, size_t* n, bool* tmajo
   *tmajor = false;
   const size_t H = h->H, N = h->N;
   switch (which) {
-    case CTK_STATE_U_NOM: *p = h->d_u_nom; *n = H; break;
+    case CTK_STATE_U_NOM: *p = (h->cfg.optimizer == CTK_OPT_RPGD) ? h->d_unom_log : h->d_u_nom; *n = H; break;  // RPGD: Q[best] before the shift (:426)
     case CTK_STATE_CEM_MU: *p = h->d_mu; *n = H; break;
     case CTK_STATE_CEM_STD: *p = h->d_sd; *n = H; break;
     case CTK_STATE_RPGD_Q: *p = h->d_Q[h->cur]; *n = N * H; *tmajor = true; break;

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(128) cem_rollout_kernel(const CemArgs a) {
   const uint32_t ng = (uint32_t)(a.off + (active ? n : 0));
 
   State z;
-  z.th = a.s0[0]; z.om = a.s0[1]; z.c = a.s0[2]; z.s = a.s0[3]; z.x = a.s0[4]; z.v = a.s0[5];
+  z.th = a.s0.ld(0); z.om = a.s0.ld(1); z.c = a.s0.ld(2); z.s = a.s0.ld(3); z.x = a.s0.ld(4); z.v = a.s0.ld(5);
   float omc = 1.0f - cosf(z.th);
   float u_last = a.u_prev[0];
   float jsum = 0.0f;
@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) cem_refit_kernel(const CemRefitA
       } else {
         if (!a.freeze_prev) a.u_prev[0] = first_q;
         if (a.u_out != nullptr) a.u_out[0] = first_q;
+        if (a.host.p != nullptr) { a.host.p[8] = first_q; a.host.p[9] = 0.0f; host_publish(a.host); }
       }
       if (t == a.H - 1) {
         a.mu[t] = (a.lo + a.hi) * 0.5f;

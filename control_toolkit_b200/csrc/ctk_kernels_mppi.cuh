@@ -148,10 +148,16 @@ __device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float*
     const float b = (fmaf(bz1, w1, bz0 * w0) * stdev) / a;
     const float un = fminf(fmaxf(sh_unom[t] + b, lo), hi);
     f.u_nom[t] = un;
+    if (f.host.p != nullptr) f.host.p[16 + t] = un;
     if (t == 0) {
       if (!f.freeze_prev) f.u_prev[0] = un;
       if (f.u_out != nullptr) { f.u_out[0] = status ? __int_as_float(0x7fc00000) : un; f.u_out[1] = (float)status; }
+      if (f.host.p != nullptr) { f.host.p[8] = status ? __int_as_float(0x7fc00000) : un; f.host.p[9] = (float)status; }
     }
+  }
+  if (f.host.p != nullptr) {  // block 0 only gets here; uniform
+    __syncthreads();
+    if (tid == 0) host_publish(f.host);
   }
 }
 
@@ -190,7 +196,7 @@ __global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const M
   const int stride = gridDim.x * rpb;
   const bool owner = tid < rpb;  // this thread carries a rollout
   const int nblk = (a.n_ind + 3) >> 2;
-  const State z0 = {a.s0[0], a.s0[1], a.s0[2], a.s0[3], a.s0[4], a.s0[5]};
+  const State z0 = {a.s0.ld(0), a.s0.ld(1), a.s0.ld(2), a.s0.ld(3), a.s0.ld(4), a.s0.ld(5)};
   const float omc0 = 1.0f - cosf(z0.th);  // spec: E_pot uses cos(angle); for t >= 1 the state carries 1 - cos
   const float u_prev0 = a.u_prev[0];
   float* sz = sh_z + min(tid, rpb - 1);

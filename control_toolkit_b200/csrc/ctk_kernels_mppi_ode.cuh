@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
   trace(0);
   // ---- prologue: the only global reads before the loop are issued first and consumed last -- the Philox draws of the first
   //      rollout group are generated while they are in flight (after the L2 flush they come from DRAM) ----
-  const float s0v = (tid < 6) ? a.s0[tid] : 0.0f;
+  const float s0v = (tid < 6) ? a.s0.ld(tid) : 0.0f;
   const float upv = a.u_prev[0];
   const float unom_first = (tid < a.H) ? a.u_nom[min(tid + 1, a.H - 1)] : 0.0f;  // optimizer_mppi.py:184 (shift on read)
   const OdeHot& k = a.k;

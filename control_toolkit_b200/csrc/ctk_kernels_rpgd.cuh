@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(32) rpgd_grad_kernel(const RpgdGradArgs a) {
   const float u_prev = a.u_prev[0];
   const float w = a.cost.inv_Hp1;
   State z0;
-  z0.th = a.s0[0]; z0.om = a.s0[1]; z0.c = a.s0[2]; z0.s = a.s0[3]; z0.x = a.s0[4]; z0.v = a.s0[5];
+  z0.th = a.s0.ld(0); z0.om = a.s0.ld(1); z0.c = a.s0.ld(2); z0.s = a.s0.ld(3); z0.x = a.s0.ld(4); z0.v = a.s0.ld(5);
   const float omc0 = 1.0f - cosf(z0.th);
 
   for (int t = 0; t < a.H; ++t) sq[t * B + tid] = a.Q[(size_t)t * a.N + n];
@@ -126,11 +126,20 @@ __global__ void __launch_bounds__(TOPK_THREADS) rpgd_select_kernel(const RpgdSel
   }
   __syncthreads();
   const int best = sh_best[0];
-  for (int t = tid; t < a.H; t += blockDim.x) a.u_nom_out[t] = a.Q[(size_t)t * a.N + best];  // :426
+  for (int t = tid; t < a.H; t += blockDim.x) {
+    const float q = a.Q[(size_t)t * a.N + best];
+    a.u_nom_out[t] = q;  // :426
+    if (a.host.p != nullptr) a.host.p[16 + t] = q;
+  }
   if (tid == 0) {
     const float u = a.Q[best];
     if (!a.freeze_prev) a.u_prev[0] = u;
     if (a.u_out != nullptr) a.u_out[0] = u;
+    if (a.host.p != nullptr) { a.host.p[8] = u; a.host.p[9] = 0.0f; }
+  }
+  if (a.host.p != nullptr) {
+    __syncthreads();
+    if (tid == 0) host_publish(a.host);
   }
   const int nnew = a.resample ? a.N - a.k : 0;
   for (int idx = tid; idx < a.N * a.H; idx += blockDim.x) {
@@ -232,6 +241,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) gradcem_refit_kernel(const GradC
         const float u = a.u_from_mean ? new_mu : row[sh_best[0]];
         if (!a.freeze_prev) a.u_prev[0] = u;
         if (a.u_out != nullptr) a.u_out[0] = u;
+        if (a.host.p != nullptr) { a.host.p[8] = u; a.host.p[9] = 0.0f; host_publish(a.host); }
       }
     }
   }
