@@ -54,6 +54,7 @@ CTK_HD int mlp_blob_floats(int hid) { return 6 * hid + hid + hid * hid + hid + 5
 struct DevConsts {
   FwdK fwd;
   CostC cost;
+  OdeC ode;  // adjoint constants (rpgd_grad_coef_kernel keeps them register-resident the same way)
 };
 
 // The 12 constants that appear as the multiplier / addend of an FMA whose other two sources are registers.  They are
@@ -195,6 +196,7 @@ struct RpgdGradArgs {
   double beta1, beta2, eps;
   long long adam_step0;  // global step counter before this tick's first gradient step
   int adam_form;         // 0 Keras, 1 torch, 2 plain gradient descent q - lr * g (optimizer_cem_naive_grad_tf.py:74)
+  const DevConsts* kc;   // device copy of {fwd, cost, ode}: register-resident constants of the coefficient-form kernel
   OdeC ode;              // adjoint constants
   FwdK fwd;              // forward constants
   CostC cost;

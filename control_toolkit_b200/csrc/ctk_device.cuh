@@ -113,6 +113,18 @@ __device__ __forceinline__ CostC load_cost(const DevConsts* kc) {
   return r;
 }
 
+// whole-struct volatile copy (all members are 32-bit): every value lands in a register and stays there
+template <class T>
+__device__ __forceinline__ T vload_struct(const T* src) {
+  static_assert(sizeof(T) % 4 == 0, "32-bit members only");
+  T r;
+  const volatile uint32_t* s = reinterpret_cast<const volatile uint32_t*>(src);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 4); ++i) d[i] = s[i];
+  return r;
+}
+
 // shared-memory loads through an explicit 32-bit shared address (one register, bumped by the caller): avoids the
 // per-iteration generic->shared base recomputation ptxas otherwise re-issues inside the rollout loop
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

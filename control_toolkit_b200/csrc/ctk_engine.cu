@@ -146,6 +146,7 @@ static cudaError_t upload_consts(ctk_handle* h) {
   DevConsts kc;
   kc.fwd = h->fwd;
   kc.cost = h->cost;
+  kc.ode = h->ode;
   const ctk_config& c = h->cfg;
   const float kx[4] = {c.action_low, c.action_high, (float)((double)c.mppi_cc_weight * (double)c.mppi_coef_du2),
                        (float)((double)c.mppi_cc_weight * (double)c.mppi_R)};
@@ -740,14 +741,15 @@ static int gradcem_tick(ctk_handle* h, const float* s_dev, float* u_out_dev) {
     a.lo = c.action_low; a.hi = c.action_high; a.lr = c.rpgd_learning_rate; a.gradmax_clip = c.rpgd_gradmax_clip;
     a.beta1 = c.rpgd_beta_1; a.beta2 = c.rpgd_beta_2; a.eps = c.rpgd_epsilon; a.adam_step0 = h->adam_step;
     a.adam_form = carry ? 0 : 2;
-    a.ode = h->ode; a.fwd = h->fwd; a.cost = h->cost; a.J = h->d_J; a.log_traj_soa = h->d_log_traj_soa;
+    a.kc = h->d_kc; a.ode = h->ode; a.fwd = h->fwd; a.cost = h->cost; a.J = h->d_J; a.log_traj_soa = h->d_log_traj_soa;
     const int B = 32;
-    const size_t smem = sizeof(float) * (size_t)H * B * 8;
+    const bool coef = sizeof(float) * (size_t)H * B * 12 <= 227 * 1024;  // coefficient tape: q, g, m, v and 8 coefficients per step
+    const size_t smem = sizeof(float) * (size_t)H * B * (coef ? 12 : 8);
     if (smem > 227 * 1024) return fail(CTK_EINVAL, "mpc_horizon too large for the shared-memory tape (max 227)");
     h->launches++;
     {
       KernelTimer kt(h);
-      CU(launch_rpgd_grad(h->cost.kind, c.logging != 0, (N + B - 1) / B, B, smem, h->stream, a));
+      CU(launch_rpgd_grad(h->cost.kind, c.logging != 0, coef, (N + B - 1) / B, B, smem, h->stream, a));
     }
     if (carry) h->adam_step += 1;
     const bool last = it == iters - 1;
@@ -777,15 +779,16 @@ static int rpgd_local(ctk_handle* h, const float* s_dev) {
   a.Q = h->d_Q[h->cur]; a.m = h->d_m[h->cur]; a.v = h->d_v[h->cur];
   a.lo = c.action_low; a.hi = c.action_high; a.lr = c.rpgd_learning_rate; a.gradmax_clip = c.rpgd_gradmax_clip;
   a.beta1 = c.rpgd_beta_1; a.beta2 = c.rpgd_beta_2; a.eps = c.rpgd_epsilon; a.adam_step0 = h->adam_step; a.adam_form = c.rpgd_adam_form;
-  a.ode = h->ode; a.fwd = h->fwd; a.cost = h->cost; a.J = h->d_J; a.log_traj_soa = h->d_log_traj_soa;
+  a.kc = h->d_kc; a.ode = h->ode; a.fwd = h->fwd; a.cost = h->cost; a.J = h->d_J; a.log_traj_soa = h->d_log_traj_soa;
   const int B = 32;
-  const size_t smem = sizeof(float) * (size_t)h->H * B * 8;
+  const bool coef = sizeof(float) * (size_t)h->H * B * 12 <= 227 * 1024 && getenv("CTK_RPGD_DIRECT_ADJOINT") == nullptr;
+  const size_t smem = sizeof(float) * (size_t)h->H * B * (coef ? 12 : 8);
   const bool log = c.logging != 0;
   if (smem > 227 * 1024) return fail(CTK_EINVAL, "RPGD: mpc_horizon too large for the shared-memory tape (max 227)");
   h->launches++;
   {
     KernelTimer kt(h);
-    CU(launch_rpgd_grad(h->cost.kind, log, (h->N + B - 1) / B, B, smem, h->stream, a));
+    CU(launch_rpgd_grad(h->cost.kind, log, coef, (h->N + B - 1) / B, B, smem, h->stream, a));
   }
   h->adam_step += iters;
   return CTK_OK;

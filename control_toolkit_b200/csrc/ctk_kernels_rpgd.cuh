@@ -107,6 +107,128 @@ __global__ void __launch_bounds__(32) rpgd_grad_kernel(const RpgdGradArgs a) {
   a.J[n] = (jsum + terminal_cost(z, a.cost)) - a.cost.shift;
 }
 
+// The same tick with the adjoint in COEFFICIENT form (ctk_math.cuh adjoint_coefficients / adjoint_apply): the forward pass folds
+// everything that depends on the pre-step state into 8 numbers per step, the reverse sweep is a 4-deep FMA chain per step, and
+// every constant is register-resident (volatile loads from the device copy) instead of being re-read from the parameter bank
+// inside the serial loops.  One warp walks 5 x H dependent steps per tick, so chain depth IS the run time.
+template <int KIND, bool LOG>
+__global__ void __launch_bounds__(32) rpgd_grad_coef_kernel(const RpgdGradArgs a) {
+  extern __shared__ float smem[];
+  constexpr int B = 32;
+  const int tid = threadIdx.x, H = a.H;
+  float* sq = smem + tid;                    // [H][B]
+  float* sg = sq + (size_t)H * B;            // [H][B]
+  float* sm = sg + (size_t)H * B;            // [H][B] Adam first moment  (global loads issued up front, latency hidden
+  float* sv = sm + (size_t)H * B;            // [H][B] Adam second moment  behind the first forward pass; written back once)
+  float* tp = sv + (size_t)H * B;            // [H][8][B]
+  const int n = blockIdx.x * B + tid;
+  if (n >= a.N) return;
+  const FwdK fwd = vload_struct(&a.kc->fwd);
+  const OdeC p = vload_struct(&a.kc->ode);
+  const CostC cost = vload_struct(&a.kc->cost);
+  const float u_prev = a.u_prev[0];
+  const float w = cost.inv_Hp1;
+  const float D2 = p.h * p.inv_mL_kp1L * p.neg_J_fric, KV = p.kp1 * p.neg_M_fric, KU = p.kp1 * p.u_max, hh = p.h;
+  const float gu_a = w * 2.0f * (cost.cc_weight * cost.R), gu_b = w * 2.0f * cost.ccrc_weight;
+  State z0;
+  z0.th = a.s0.ld(0); z0.om = a.s0.ld(1); z0.c = a.s0.ld(2); z0.s = a.s0.ld(3); z0.x = a.s0.ld(4); z0.v = a.s0.ld(5);
+  const float omc0 = 1.0f - cosf(z0.th);
+  const float lo = a.lo, hi = a.hi, clipc = a.gradmax_clip, lr = a.lr;
+
+  const bool moments = a.adam_form != 2;
+#pragma unroll 4
+  for (int t = 0; t < H; ++t) sq[t * B] = a.Q[(size_t)t * a.N + n];
+  if (moments) {
+#pragma unroll 4
+    for (int t = 0; t < H; ++t) { sm[t * B] = a.m[(size_t)t * a.N + n]; sv[t * B] = a.v[(size_t)t * a.N + n]; }
+  }
+
+  for (int it = 0; it < a.iters; ++it) {
+    // ---- forward: the next state (serial chain) and, off the chain, the adjoint coefficients of this step ----
+    State z = z0;
+#pragma unroll 2
+    for (int t = 0; t < H; ++t) {
+      const float q = sq[t * B];
+      const AdjCoef c = adjoint_coefficients<KIND>(z, q, p, cost, w);
+      float* o = tp + (size_t)t * 8 * B;
+      o[0] = c.E1; o[B] = c.E2; o[2 * B] = c.C1; o[3 * B] = c.C2; o[4 * B] = c.D1; o[5 * B] = c.cx; o[6 * B] = c.cth; o[7 * B] = c.com;
+      float omc_unused;
+      ode_substep(z, q, fwd, omc_unused);
+    }
+    // ---- reverse sweep ----
+    Adj lam = {0.f, 0.f, 0.f, 0.f};
+    float nrm2 = 0.0f;
+#pragma unroll 4
+    for (int t = H - 1; t >= 0; --t) {
+      const float* o = tp + (size_t)t * 8 * B;
+      AdjCoef c;
+      c.E1 = o[0]; c.E2 = o[B]; c.C1 = o[2 * B]; c.C2 = o[3 * B]; c.D1 = o[4 * B]; c.cx = o[5 * B]; c.cth = o[6 * B]; c.com = o[7 * B];
+      const float u = sq[t * B];
+      const float up = (t > 0) ? sq[(t - 1) * B] : u_prev;
+      // d(l_t)/d(u_t) + d(l_{t+1})/d(u_t)  (stage_cost_adjoint_u)
+      float gu = fmaf(gu_b, u - up, gu_a * u);
+      if (t < H - 1) gu = fmaf(-gu_b, sq[(t + 1) * B] - u, gu);
+      const float g = adjoint_apply(c, hh, D2, KV, KU, t > 0, lam) + gu;
+      sg[t * B] = g;
+      nrm2 = fmaf(g, g, nrm2);
+    }
+    // ---- clip_by_norm over the trajectory, optimizer update, box clip ----
+    const float den = fmaxf(sqrtf(nrm2), clipc);
+    const double step = (double)(a.adam_step0 + it + 1);
+    const double bc1d = 1.0 - pow(a.beta1, step), bc2d = 1.0 - pow(a.beta2, step);
+    const float b1 = (float)a.beta1, b2 = (float)a.beta2;
+    const float omb1 = (float)(1.0 - a.beta1), omb2 = (float)(1.0 - a.beta2);
+    const float bc1 = (float)bc1d, bc2 = (float)bc2d, eps = (float)a.eps;
+    const float alpha = (float)((double)a.lr * sqrt(bc2d) / bc1d);
+#pragma unroll 4
+    for (int t = 0; t < H; ++t) {
+      const float g = sg[t * B] * clipc / den;
+      float q = sq[t * B];
+      if (!moments) {
+        q = __fsub_rn(q, __fmul_rn(lr, g));
+      } else {
+        float mm = sm[t * B], vv = sv[t * B];
+        if (a.adam_form == 1) {
+          mm = fmaf(g, omb1, mm * b1);
+          vv = fmaf(g * g, omb2, vv * b2);
+          q = q - (lr * (mm / bc1)) / (sqrtf(vv / bc2) + eps);
+        } else {
+          mm = fmaf(g - mm, omb1, mm);
+          vv = fmaf(g * g - vv, omb2, vv);
+          q = q - (alpha * mm) / (sqrtf(vv) + eps);
+        }
+        sm[t * B] = mm;
+        sv[t * B] = vv;
+      }
+      sq[t * B] = fminf(fmaxf(q, lo), hi);
+    }
+  }
+  if (moments && a.iters > 0) {
+#pragma unroll 4
+    for (int t = 0; t < H; ++t) { a.m[(size_t)t * a.N + n] = sm[t * B]; a.v[(size_t)t * a.N + n] = sv[t * B]; }
+  }
+
+  // ---- cost of the updated population ----
+  State z = z0;
+  float omc = omc0, u_last = u_prev, jsum = 0.0f;
+  for (int t = 0; t < H; ++t) {
+    const float u = sq[t * B];
+    a.Q[(size_t)t * a.N + n] = u;
+    if (LOG) {
+      float* o = a.log_traj_soa + (size_t)t * 6 * a.N + n;
+      o[0] = z.th; o[a.N] = z.om; o[2 * a.N] = z.c; o[3 * a.N] = z.s; o[4 * (size_t)a.N] = z.x; o[5 * (size_t)a.N] = z.v;
+    }
+    jsum += stage_cost<KIND>(z, omc, u, u_last, cost);
+    ode_substep(z, u, fwd, omc);
+    u_last = u;
+  }
+  if (LOG) {
+    float* o = a.log_traj_soa + (size_t)H * 6 * a.N + n;
+    o[0] = z.th; o[a.N] = z.om; o[2 * a.N] = z.c; o[3 * a.N] = z.s; o[4 * (size_t)a.N] = z.x; o[5 * (size_t)a.N] = z.v;
+  }
+  a.J[n] = (jsum + terminal_cost(z, cost)) - cost.shift;
+}
+
 // sample_actions (:275-296) for one new row at horizon step t: clip(z*scale+offset) on inducing points, interpolate
 __device__ __forceinline__ float rpgd_sample_point(const RpgdSelectArgs& a, uint32_t row, int i) {
   const float z = noise1(a.noise, row, i);
@@ -119,7 +241,9 @@ __global__ void __launch_bounds__(TOPK_THREADS) rpgd_select_kernel(const RpgdSel
   __shared__ int sh_best[TOPK_THREADS];
   const int tid = threadIdx.x;
   uint64_t key = (tid < a.N) ? make_key(a.J[tid], (uint32_t)tid) : KEY_MAX;
-  key = block_bitonic_sort(key, sh);  // argsort (:345), stable by index
+  int n_sort = 32;
+  while (n_sort < a.N) n_sort <<= 1;
+  key = block_bitonic_sort(key, sh, n_sort);  // argsort (:345), stable by index; C3's 32 costs stay inside one warp's shuffles
   if (tid < a.k) {
     sh_best[tid] = (int)(key & 0xffffffffu);
     a.best_idx_out[tid] = sh_best[tid];
@@ -210,7 +334,9 @@ __global__ void __launch_bounds__(TOPK_THREADS) gradcem_refit_kernel(const GradC
   __shared__ int sh_best[TOPK_THREADS];
   const int tid = threadIdx.x;
   uint64_t key = (tid < a.N) ? make_key(a.J[tid], (uint32_t)tid) : KEY_MAX;
-  key = block_bitonic_sort(key, sh);
+  int n_sort = 32;
+  while (n_sort < a.N) n_sort <<= 1;
+  key = block_bitonic_sort(key, sh, n_sort);
   if (tid < a.k) {
     sh_best[tid] = (int)(key & 0xffffffffu);
     if (a.elite_idx_out != nullptr) a.elite_idx_out[tid] = sh_best[tid];

@@ -23,7 +23,8 @@ cudaError_t launch_cem_rollout(int pred, int kind, bool log, int nblocks, size_t
 cudaError_t launch_topk_level(const float* cost, const uint64_t* keys_in, int n, int off, int k, uint64_t* out, cudaStream_t st);
 cudaError_t launch_cem_refit(const CemRefitArgs& a, cudaStream_t st);
 
-cudaError_t launch_rpgd_grad(int kind, bool log, int nblocks, int block, size_t smem, cudaStream_t st, const RpgdGradArgs& a);
+// coef: coefficient-form adjoint (rpgd_grad_coef_kernel, tape of 12 floats per step) instead of the direct form (8 floats per step)
+cudaError_t launch_rpgd_grad(int kind, bool log, bool coef, int nblocks, int block, size_t smem, cudaStream_t st, const RpgdGradArgs& a);
 cudaError_t launch_rpgd_select(const RpgdSelectArgs& a, cudaStream_t st);
 cudaError_t launch_rpgd_init(const RpgdSelectArgs& a, cudaStream_t st);
 cudaError_t launch_gradcem_sample(const GradCemSampleArgs& a, cudaStream_t st);

@@ -213,6 +213,67 @@ CTK_HD void stage_cost_adjoint_state(const State& z, float cos_angle, float sin_
   if (KIND == 1) lam.om = fmaf(w * k.ekp_weight, 2.0f * z.om, lam.om);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same adjoint step in COEFFICIENT form.  ode_step_adjoint is linear in lam and everything else in it depends only on
+// the pre-step state, so the forward pass can fold the state-dependent part into five coefficients (+ the three
+// state-gradient terms of the stage cost).  The reverse sweep is then a 4-deep FMA chain per step instead of ~40 dependent
+// instructions -- the RPGD tick is ONE warp walking a serial chain, so chain depth is all that matters.
+//   gnum = E1 lam.v + E2 lam.om
+//   th' = lam.th + C1 gnum + C2 lam.om (+ cth)      om' = lam.om + h lam.th + D1 gnum + D2 lam.om (+ com)
+//   x'  = lam.x (+ cx)                              v'  = lam.v + h lam.x + KV gnum          dJ/dQ = KU gnum
+// ---------------------------------------------------------------------------------------------------------------
+struct AdjCoef {
+  float E1, E2, C1, C2, D1;  // dynamics
+  float cx, cth, com;        // d(stage cost)/d(x, angle, angleD) of the pre-step state, scaled by w
+};
+
+template <int KIND>
+CTK_HD AdjCoef adjoint_coefficients(const State& z, float Q, const OdeC& p, const CostC& k, float w) {
+  // forward intermediates exactly as in ode_step_adjoint
+  const float u = p.u_max * Q;
+  const float A = fmaf(-p.m, z.c * z.c, p.kp1_Mm);
+  const float T = p.neg_J_fric * z.om;
+  const float F = p.neg_M_fric * z.v;
+  const float om2 = z.om * z.om;
+  const float inner = (F + u) - (p.mL * om2) * z.s;
+  const float num = fmaf(p.kp1, inner, fmaf(p.mg * z.s, z.c, (T * z.c) * p.inv_L));
+  const float invA = fast_rcp(A);
+  const float vd = num * invA;
+  AdjCoef r;
+  r.E1 = invA * p.h;
+  r.E2 = r.E1 * (z.c * p.inv_kp1L);
+  const float Ps = fmaf(p.mg, z.c, -(p.kp1 * p.mL) * om2);
+  const float Pc = fmaf(p.two_m * z.c, vd, fmaf(p.mg, z.s, T * p.inv_L));
+  r.C1 = fmaf(Ps, z.c, -Pc * z.s);
+  r.C2 = p.h * fmaf(p.g_inv_kp1L, z.c, -(vd * p.inv_kp1L) * z.s);
+  r.D1 = fmaf(z.c * p.inv_L, p.neg_J_fric, -p.two_kp1_mL * (z.om * z.s));
+  // stage_cost_adjoint_state
+  const float d = (z.x - k.target_position) * k.inv_two_thl;
+  const float ax = fabsf(z.x);
+  const float e = (ax - k.thl_095) * k.inv_thl_005;
+  float ddx = 2.0f * d * k.inv_two_thl;
+  if (ax > k.thl_095) ddx += copysignf(2.0e9f * e * k.inv_thl_005, z.x);
+  r.cx = (w * k.dd_weight) * ddx;
+  const float omc = 1.0f - z.c;
+  r.cth = (w * k.ep_weight) * ((k.target_equilibrium * 0.25f) * (2.0f * omc * z.s));
+  r.com = (KIND == 1) ? (w * k.ekp_weight) * (2.0f * z.om) : 0.0f;
+  return r;
+}
+
+// lam (w.r.t. the state after the step) -> lam w.r.t. the state before it, including that state's stage-cost gradient if
+// add_cost; returns dJ/dQ through the dynamics.  D2 = h * inv_mL_kp1L * neg_J_fric, KV = kp1 * neg_M_fric, KU = kp1 * u_max.
+CTK_HD float adjoint_apply(const AdjCoef& c, float h, float D2, float KV, float KU, bool add_cost, Adj& lam) {
+  const float gnum = fmaf(c.E1, lam.v, c.E2 * lam.om);
+  Adj o;
+  o.th = fmaf(c.C1, gnum, fmaf(c.C2, lam.om, lam.th));
+  o.om = fmaf(c.D1, gnum, fmaf(D2, lam.om, fmaf(h, lam.th, lam.om)));
+  o.x = lam.x;
+  o.v = fmaf(KV, gnum, fmaf(h, lam.x, lam.v));
+  if (add_cost) { o.th += c.cth; o.om += c.com; o.x += c.cx; }
+  lam = o;
+  return KU * gnum;
+}
+
 // d(l_t)/d(u_t) + d(l_{t+1})/d(u_t), scaled by w.  has_next = (t < H-1).
 CTK_HD float stage_cost_adjoint_u(float u, float u_prev, float u_next, bool has_next, const CostC& k, float w) {
   float g = 2.0f * (k.cc_weight * k.R) * u + 2.0f * k.ccrc_weight * (u - u_prev);

@@ -4,9 +4,12 @@
 
 namespace ctk {
 
-cudaError_t launch_rpgd_grad(int kind, bool log, int nblocks, int block, size_t smem, cudaStream_t st, const RpgdGradArgs& a) {
+cudaError_t launch_rpgd_grad(int kind, bool log, bool coef, int nblocks, int block, size_t smem, cudaStream_t st, const RpgdGradArgs& a) {
   void (*k)(const RpgdGradArgs) = nullptr;
-  if (kind == 0) k = log ? rpgd_grad_kernel<0, true> : rpgd_grad_kernel<0, false>;
+  if (coef) {
+    if (kind == 0) k = log ? rpgd_grad_coef_kernel<0, true> : rpgd_grad_coef_kernel<0, false>;
+    else k = log ? rpgd_grad_coef_kernel<1, true> : rpgd_grad_coef_kernel<1, false>;
+  } else if (kind == 0) k = log ? rpgd_grad_kernel<0, true> : rpgd_grad_kernel<0, false>;
   else k = log ? rpgd_grad_kernel<1, true> : rpgd_grad_kernel<1, false>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -62,6 +62,35 @@ void twin_grad(const float* s0, const float* Q, int N, int H, const ctk_ode_para
   delete[] tape;
 }
 
+// the same gradient through the COEFFICIENT form of the adjoint (adjoint_coefficients in the forward pass, adjoint_apply in the
+// reverse sweep), as rpgd_grad_kernel does on the device
+void twin_grad_coef(const float* s0, const float* Q, int N, int H, const ctk_ode_params* op, const ctk_cost_params* cp,
+                    float u_prev, float* grad) {
+  OdeC ode; FwdK fwd; CostC cost;
+  derive_ode(*op, ode);
+  derive_fwd(*op, fwd);
+  derive_cost(*cp, H, cost);
+  const float w = cost.inv_Hp1;
+  const float D2 = ode.h * ode.inv_mL_kp1L * ode.neg_J_fric, KV = ode.kp1 * ode.neg_M_fric, KU = ode.kp1 * ode.u_max;
+  AdjCoef* tape = new AdjCoef[H];
+  for (int n = 0; n < N; ++n) {
+    const float* q = Q + (size_t)n * H;
+    State z{s0[0], s0[1], s0[2], s0[3], s0[4], s0[5]};
+    float omc_unused;
+    for (int t = 0; t < H; ++t) {
+      tape[t] = cost.kind == 0 ? adjoint_coefficients<0>(z, q[t], ode, cost, w) : adjoint_coefficients<1>(z, q[t], ode, cost, w);
+      ode_step(z, q[t], fwd, omc_unused);
+    }
+    Adj lam{0.f, 0.f, 0.f, 0.f};
+    for (int t = H - 1; t >= 0; --t) {
+      float g = adjoint_apply(tape[t], ode.h, D2, KV, KU, t > 0, lam);
+      g += stage_cost_adjoint_u(q[t], t > 0 ? q[t - 1] : u_prev, t < H - 1 ? q[t + 1] : 0.f, t < H - 1, cost, w);
+      grad[(size_t)n * H + t] = g;
+    }
+  }
+  delete[] tape;
+}
+
 // K1's scaled-variable arithmetic (ctk_ode_scaled.cuh + derive_ode_hot): S[n] = total MPPI cost of rollout n (trajectory cost +
 // control-cost correction, optimizer_mppi.py:154-161) for given clipped controls u and unclipped perturbations du [N][H];
 // traj (optional) [N][H+1][6] in the reference's unscaled variables.
