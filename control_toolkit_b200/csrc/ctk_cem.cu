@@ -11,8 +11,7 @@ static cudaError_t launch_cem_t(int nblocks, size_t smem, cudaStream_t st, const
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  k<<<nblocks, 128, smem, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(k, dim3(nblocks), dim3(128), smem, st, a);
 }
 template <class Pred>
 static cudaError_t launch_cem_p(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemArgs& a) {
@@ -29,6 +28,8 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_level_kernel(const float* _
   __shared__ uint64_t sh[TOPK_THREADS];
   const int i = blockIdx.x * TOPK_THREADS + threadIdx.x;
   uint64_t key = KEY_MAX;
+  pdl_wait();
+  pdl_trigger();
   if (i < n) key = (cost != nullptr) ? make_key(cost[i], (uint32_t)(off + i)) : keys_in[i];
   key = block_bitonic_sort(key, sh);
   if (threadIdx.x < k) out[(size_t)blockIdx.x * k + threadIdx.x] = key;
@@ -36,12 +37,10 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_level_kernel(const float* _
 
 cudaError_t launch_topk_level(const float* cost, const uint64_t* keys_in, int n, int off, int k, uint64_t* out, cudaStream_t st) {
   const int nb = (n + TOPK_THREADS - 1) / TOPK_THREADS;
-  topk_level_kernel<<<nb, TOPK_THREADS, 0, st>>>(cost, keys_in, n, off, k, out);
-  return cudaGetLastError();
+  return launch_pdl(topk_level_kernel, dim3(nb), dim3(TOPK_THREADS), 0, st, cost, keys_in, n, off, k, out);
 }
 cudaError_t launch_cem_refit(const CemRefitArgs& a, cudaStream_t st) {
-  cem_refit_kernel<<<1, TOPK_THREADS, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(cem_refit_kernel, dim3(1), dim3(TOPK_THREADS), 0, st, a);
 }
 
 }  // namespace ctk

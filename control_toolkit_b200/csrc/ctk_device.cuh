@@ -8,6 +8,12 @@
 
 namespace ctk {
 
+// Programmatic dependent launch (sm_90+): kernels of one tick are launched with programmaticStreamSerializationAllowed, so a
+// kernel's blocks are scheduled (and run their independent prologue) while the previous kernel of the stream drains; pdl_wait()
+// returns once that kernel has completed and its writes are visible.  Both are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Publish a tick's result mirror to the host caller (see HostMirror): every thread that stored into m.p must have passed a
 // block barrier before the ONE calling thread gets here.
 __device__ __forceinline__ void host_publish(const HostMirror& m) {

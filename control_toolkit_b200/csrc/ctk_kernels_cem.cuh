@@ -17,12 +17,14 @@ __global__ void __launch_bounds__(128) cem_rollout_kernel(const CemArgs a) {
   extern __shared__ float smem[];
   float* sh_mu = smem;         // [H]
   float* sh_sd = smem + a.H;   // [H]
+  Pred pred(a.kc, a.mlp, smem + 2 * a.H);  // constants: independent of the previous kernel, loaded while it drains
+  const CostC cost = load_cost(a.kc);
+  pdl_wait();
+  pdl_trigger();
   for (int t = threadIdx.x; t < a.H; t += blockDim.x) {
     sh_mu[t] = a.mu[t];
     sh_sd[t] = a.sd[t];
   }
-  Pred pred(a.kc, a.mlp, smem + 2 * a.H);
-  const CostC cost = load_cost(a.kc);
   __syncthreads();
 
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,6 +68,8 @@ __global__ void __launch_bounds__(128) cem_rollout_kernel(const CemArgs a) {
 __global__ void __launch_bounds__(TOPK_THREADS) cem_refit_kernel(const CemRefitArgs a) {
   __shared__ uint64_t sh[TOPK_THREADS];
   __shared__ uint32_t sh_elite[TOPK_THREADS];
+  pdl_wait();
+  pdl_trigger();
   uint64_t key = (threadIdx.x < a.cnt) ? a.cand[threadIdx.x] : KEY_MAX;
   int n_sort = 32;
   while (n_sort < a.cnt) n_sort <<= 1;

@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(32) rpgd_grad_kernel(const RpgdGradArgs a) {
   float* sg = sq + (size_t)a.H * B;    // [H][B]
   float* tp = sg + (size_t)a.H * B;    // [H][6][B]
   const int n = blockIdx.x * B + tid;
+  pdl_wait();
+  pdl_trigger();
   if (n >= a.N) return;
   const float u_prev = a.u_prev[0];
   const float w = a.cost.inv_Hp1;
@@ -123,9 +125,11 @@ __global__ void __launch_bounds__(32) rpgd_grad_coef_kernel(const RpgdGradArgs a
   float* tp = sv + (size_t)H * B;            // [H][8][B]
   const int n = blockIdx.x * B + tid;
   if (n >= a.N) return;
-  const FwdK fwd = vload_struct(&a.kc->fwd);
+  const FwdK fwd = vload_struct(&a.kc->fwd);  // constants: independent of the previous kernel, loaded while it drains
   const OdeC p = vload_struct(&a.kc->ode);
   const CostC cost = vload_struct(&a.kc->cost);
+  pdl_wait();
+  pdl_trigger();
   const float u_prev = a.u_prev[0];
   const float w = cost.inv_Hp1;
   const float D2 = p.h * p.inv_mL_kp1L * p.neg_J_fric, KV = p.kp1 * p.neg_M_fric, KU = p.kp1 * p.u_max, hh = p.h;
@@ -240,6 +244,8 @@ __global__ void __launch_bounds__(TOPK_THREADS) rpgd_select_kernel(const RpgdSel
   __shared__ uint64_t sh[TOPK_THREADS];
   __shared__ int sh_best[TOPK_THREADS];
   const int tid = threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
   uint64_t key = (tid < a.N) ? make_key(a.J[tid], (uint32_t)tid) : KEY_MAX;
   int n_sort = 32;
   while (n_sort < a.N) n_sort <<= 1;
@@ -320,6 +326,8 @@ __global__ void rpgd_init_kernel(const RpgdSelectArgs a) {
 // ---------------------------------------------------------------------------------------------------------------
 // Q[t][col0 + r] = clip(mu_t + z_{r,t} * sd_t)  (multiply and add separately rounded, as the reference's tf ops)
 __global__ void gradcem_sample_kernel(const GradCemSampleArgs a) {
+  pdl_wait();
+  pdl_trigger();
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < a.cnt * a.H; idx += gridDim.x * blockDim.x) {
     const int t = idx / a.cnt, r = idx - t * a.cnt;
     const float z = noise1(a.noise, (uint32_t)r, t);
@@ -333,6 +341,8 @@ __global__ void __launch_bounds__(TOPK_THREADS) gradcem_refit_kernel(const GradC
   __shared__ uint64_t sh[TOPK_THREADS];
   __shared__ int sh_best[TOPK_THREADS];
   const int tid = threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
   uint64_t key = (tid < a.N) ? make_key(a.J[tid], (uint32_t)tid) : KEY_MAX;
   int n_sort = 32;
   while (n_sort < a.N) n_sort <<= 1;

@@ -5,7 +5,27 @@
 
 #include "ctk_args.cuh"
 
+#include <cstdlib>
+#include <utility>
+
 namespace ctk {
+
+// Launch with programmatic stream serialization (see pdl_wait in ctk_device.cuh).  CTK_NO_PDL=1 falls back to plain launches.
+inline bool pdl_enabled() {
+  static const bool on = std::getenv("CTK_NO_PDL") == nullptr;
+  return on;
+}
+template <typename... P, typename... A>
+inline cudaError_t launch_pdl(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
+}
 
 // pred: 0 ODE, 1 MLP (SIMT engine); kind: cost class; log: write SoA trajectory logs
 cudaError_t launch_mppi_rollout(int pred, int kind, bool log, int nblocks, int block, size_t smem, cudaStream_t st, const MppiArgs& a);

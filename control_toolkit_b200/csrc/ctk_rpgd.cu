@@ -15,12 +15,10 @@ cudaError_t launch_rpgd_grad(int kind, bool log, bool coef, int nblocks, int blo
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  k<<<nblocks, block, smem, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(k, dim3(nblocks), dim3(block), smem, st, a);
 }
 cudaError_t launch_rpgd_select(const RpgdSelectArgs& a, cudaStream_t st) {
-  rpgd_select_kernel<<<1, TOPK_THREADS, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(rpgd_select_kernel, dim3(1), dim3(TOPK_THREADS), 0, st, a);
 }
 cudaError_t launch_rpgd_init(const RpgdSelectArgs& a, cudaStream_t st) {
   rpgd_init_kernel<<<(a.N * a.H + 255) / 256, 256, 0, st>>>(a);
@@ -28,12 +26,10 @@ cudaError_t launch_rpgd_init(const RpgdSelectArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_gradcem_sample(const GradCemSampleArgs& a, cudaStream_t st) {
-  gradcem_sample_kernel<<<(a.cnt * a.H + 255) / 256, 256, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(gradcem_sample_kernel, dim3((a.cnt * a.H + 255) / 256), dim3(256), 0, st, a);
 }
 cudaError_t launch_gradcem_refit(const GradCemRefitArgs& a, cudaStream_t st) {
-  gradcem_refit_kernel<<<1, TOPK_THREADS, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(gradcem_refit_kernel, dim3(1), dim3(TOPK_THREADS), 0, st, a);
 }
 
 // FP32 FMA-chain microbenchmark: 8 independent chains per thread, 16x unrolled
