@@ -260,10 +260,14 @@ def run_ours(args):
     # ---- second pass, same ticks: CUDA events around the rollout kernel only (roofline.achieved); kept out of the pass
     #      above so that the extra event records do not sit inside the timed ticks ----
     L.check(lib.ctk_enable_kernel_timing(opt._h, 1))
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     for i in range(K):
         flush.zero_()
+        ev2[i][0].record()
         tick(W + i)
+        ev2[i][1].record()
     barrier()
+    tick2_ms = sum(a.elapsed_time(b) for a, b in ev2) / K  # this rank's tick in the SAME pass the kernel events were taken in
     ms_sum, n_k = C.c_double(), C.c_int64()
     L.check(lib.ctk_get_kernel_timing(opt._h, C.byref(ms_sum), C.byref(n_k)))
     L.check(lib.ctk_enable_kernel_timing(opt._h, 0))
@@ -315,7 +319,7 @@ def run_ours(args):
             roofline = {"bound": "tensor", "kernel": f"mppi_rollout_kernel<{'MlpTcPred' if args.mlp_engine == 'tcgen05' else 'MlpSimtPred'}>",
                         "achieved": achieved, "peak": tpeak, "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": None,
                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, cuBLAS 8192^3)" if peaks else "fallback 1648",
-                        "flop_per_rollout_step": fl_step, "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms / ms_per_step,
+                        "flop_per_rollout_step": fl_step, "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms / tick2_ms,
                         "tensor_flop_issued_per_algorithmic": 6.0 * 32768.0 / fl_step if args.mlp_engine == "tcgen05" else 0.0}
         elif logging_on:
             # optimizer_logging on: rollout_trajectories_logged [N,H+1,6] + Q_logged [N,H,1] + J [N] are written by the rollout kernel
@@ -325,7 +329,7 @@ def run_ours(args):
             roofline = {"bound": "hbm", "kernel": "mppi_ode_kernel<LOG> (fused tick + coalesced SoA trajectory log)", "achieved": ach, "peak": hpk,
                         "unit": "GB/s", "frac": ach / hpk, "traffic": None, "algorithmic_bytes_per_launch": byt,
                         "bytes_per_rollout_step": 28.0, "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)" if peaks else "fallback 6650",
-                        "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms / ms_per_step}
+                        "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms / tick2_ms}
         elif opt_name == "cem-tf":
             fl_step = FLOP_PER_ROLLOUT_STEP["cem_ode"]
             peak, clk = C.c_double(), C.c_double()
@@ -334,7 +338,7 @@ def run_ours(args):
             roofline = {"bound": "fp32", "kernel": "cem_rollout_kernel<OdePred> (one launch per outer iteration)", "achieved": achieved,
                         "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": None,
                         "peak_source": "measured live: FP32 FMA-chain microbenchmark (ctk_fp32_peak)", "flop_per_rollout_step": fl_step,
-                        "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms * passes / ms_per_step,
+                        "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms * passes / tick2_ms,
                         "note": "4096 rollouts occupy 32 of 148 SMs with one warp per scheduler: the tick is launch- and latency-bound"}
         elif opt_name == "rpgd":
             its = RPGD_CFG["outer_its"]
@@ -342,10 +346,10 @@ def run_ours(args):
             peak, clk = C.c_double(), C.c_double()
             L.check(lib.ctk_fp32_peak(local_rank, C.byref(peak), C.byref(clk)))
             achieved = fl_launch / (k1_ms * 1e-3) / 1e12
-            roofline = {"bound": "fp32", "kernel": "rpgd_grad_kernel (all Adam iterations + the final rollout of a tick in one launch)",
+            roofline = {"bound": "fp32", "kernel": "rpgd_grad_coef_kernel (all Adam iterations + the final rollout of a tick in one launch)",
                         "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": None,
                         "peak_source": "measured live: FP32 FMA-chain microbenchmark (ctk_fp32_peak)",
-                        "flop_per_launch": fl_launch, "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms / ms_per_step,
+                        "flop_per_launch": fl_launch, "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms / tick2_ms,
                         "note": "32 trajectories = one warp: a serial dependency chain of 5 x 50 steps, latency-bound by construction"}
         else:
             flop = FLOP_PER_ROLLOUT_STEP["mppi_ode"] * n_local * H
@@ -358,9 +362,16 @@ def run_ours(args):
                         "peak_source": "measured live: FP32 FMA-chain microbenchmark (ctk_fp32_peak), implied FFMA clock %.0f MHz; "
                                        "theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5" % clk.value,
                         "flop_per_rollout_step": FLOP_PER_ROLLOUT_STEP["mppi_ode"], "kernel_ms": k1_ms,
-                        "kernel_share_of_tick": k1_ms / ms_per_step,
+                        "kernel_share_of_tick": k1_ms / tick2_ms,
                         "hbm": {"algorithmic_bytes_per_launch": 4.0 * n_local, "achieved_gbs": 4.0 * n_local / (k1_ms * 1e-3) / 1e9,
                                 "peak_gbs": peaks.get("hbm_gbs", 6650.0)}}
+        # measured DRAM traffic of that kernel (ncu --set full capture, per launch), when a capture of this workload is on file
+        tpath = os.path.join(REPO, "profiles", "ncu_traffic_r01.json")
+        tr = (json.load(open(tpath)) if os.path.exists(tpath) else {}).get(args.workload if args.rollouts is None else "", None)
+        if tr and world == 1 and not (is_mlp and args.mlp_engine != "tcgen05"):
+            roofline["traffic"] = tr["bytes"]
+            roofline["traffic_source"] = tr["source"]
+        roofline["tick_ms_same_pass"] = tick2_ms
         # ---- CPU baseline: oracle port on a bounded sample of the same workload ----
         n_sample = min(N, args.cpu_sample)
         rate, sec, threads = cpu_mppi_rate(args.workload, n_sample, 2, 1)

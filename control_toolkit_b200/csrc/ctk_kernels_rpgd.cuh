@@ -112,19 +112,25 @@ __global__ void __launch_bounds__(32) rpgd_grad_kernel(const RpgdGradArgs a) {
 // The same tick with the adjoint in COEFFICIENT form (ctk_math.cuh adjoint_coefficients / adjoint_apply): the forward pass folds
 // everything that depends on the pre-step state into 8 numbers per step, the reverse sweep is a 4-deep FMA chain per step, and
 // every constant is register-resident (volatile loads from the device copy) instead of being re-read from the parameter bank
-// inside the serial loops.  One warp walks 5 x H dependent steps per tick, so chain depth IS the run time.
+// inside the serial loops.  Block = 32 trajectories x kRpgdWarps warps: warp 0 walks the serial chains (5 x H dependent steps
+// per tick -- chain depth IS the run time), ALL warps share the phases that are parallel over the horizon (staging Q / Adam
+// moments from global memory, the Adam update with its IEEE divisions and square roots, the write-back), warp w taking the
+// steps t = w (mod kRpgdWarps).
+constexpr int kRpgdWarps = 8;
 template <int KIND, bool LOG>
-__global__ void __launch_bounds__(32) rpgd_grad_coef_kernel(const RpgdGradArgs a) {
+__global__ void __launch_bounds__(32 * kRpgdWarps) rpgd_grad_coef_kernel(const RpgdGradArgs a) {
   extern __shared__ float smem[];
-  constexpr int B = 32;
-  const int tid = threadIdx.x, H = a.H;
-  float* sq = smem + tid;                    // [H][B]
+  constexpr int B = 32, W = kRpgdWarps;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, H = a.H;
+  float* sq = smem + lane;                   // [H][B]
   float* sg = sq + (size_t)H * B;            // [H][B]
-  float* sm = sg + (size_t)H * B;            // [H][B] Adam first moment  (global loads issued up front, latency hidden
-  float* sv = sm + (size_t)H * B;            // [H][B] Adam second moment  behind the first forward pass; written back once)
+  float* sm = sg + (size_t)H * B;            // [H][B] Adam first moment  (global loads issued up front by all warps;
+  float* sv = sm + (size_t)H * B;            // [H][B] Adam second moment  written back once)
   float* tp = sv + (size_t)H * B;            // [H][8][B]
-  const int n = blockIdx.x * B + tid;
-  if (n >= a.N) return;
+  __shared__ float sh_den[B];
+  const int n_raw = blockIdx.x * B + lane;
+  const bool active = n_raw < a.N;
+  const int n = active ? n_raw : a.N - 1;    // inactive lanes shadow the last trajectory and never store to global memory
   const FwdK fwd = vload_struct(&a.kc->fwd);  // constants: independent of the previous kernel, loaded while it drains
   const OdeC p = vload_struct(&a.kc->ode);
   const CostC cost = vload_struct(&a.kc->cost);
@@ -141,51 +147,55 @@ __global__ void __launch_bounds__(32) rpgd_grad_coef_kernel(const RpgdGradArgs a
 
   const bool moments = a.adam_form != 2;
 #pragma unroll 4
-  for (int t = 0; t < H; ++t) sq[t * B] = a.Q[(size_t)t * a.N + n];
-  if (moments) {
-#pragma unroll 4
-    for (int t = 0; t < H; ++t) { sm[t * B] = a.m[(size_t)t * a.N + n]; sv[t * B] = a.v[(size_t)t * a.N + n]; }
+  for (int t = wid; t < H; t += W) {
+    sq[t * B] = a.Q[(size_t)t * a.N + n];
+    if (moments) { sm[t * B] = a.m[(size_t)t * a.N + n]; sv[t * B] = a.v[(size_t)t * a.N + n]; }
   }
+  __syncthreads();
 
   for (int it = 0; it < a.iters; ++it) {
-    // ---- forward: the next state (serial chain) and, off the chain, the adjoint coefficients of this step ----
-    State z = z0;
+    if (wid == 0) {
+      // ---- forward: the next state (serial chain) and, off the chain, the adjoint coefficients of this step ----
+      State z = z0;
 #pragma unroll 2
-    for (int t = 0; t < H; ++t) {
-      const float q = sq[t * B];
-      const AdjCoef c = adjoint_coefficients<KIND>(z, q, p, cost, w);
-      float* o = tp + (size_t)t * 8 * B;
-      o[0] = c.E1; o[B] = c.E2; o[2 * B] = c.C1; o[3 * B] = c.C2; o[4 * B] = c.D1; o[5 * B] = c.cx; o[6 * B] = c.cth; o[7 * B] = c.com;
-      float omc_unused;
-      ode_substep(z, q, fwd, omc_unused);
-    }
-    // ---- reverse sweep ----
-    Adj lam = {0.f, 0.f, 0.f, 0.f};
-    float nrm2 = 0.0f;
+      for (int t = 0; t < H; ++t) {
+        const float q = sq[t * B];
+        const AdjCoef c = adjoint_coefficients<KIND>(z, q, p, cost, w);
+        float* o = tp + (size_t)t * 8 * B;
+        o[0] = c.E1; o[B] = c.E2; o[2 * B] = c.C1; o[3 * B] = c.C2; o[4 * B] = c.D1; o[5 * B] = c.cx; o[6 * B] = c.cth; o[7 * B] = c.com;
+        float omc_unused;
+        ode_substep(z, q, fwd, omc_unused);
+      }
+      // ---- reverse sweep ----
+      Adj lam = {0.f, 0.f, 0.f, 0.f};
+      float nrm2 = 0.0f;
 #pragma unroll 4
-    for (int t = H - 1; t >= 0; --t) {
-      const float* o = tp + (size_t)t * 8 * B;
-      AdjCoef c;
-      c.E1 = o[0]; c.E2 = o[B]; c.C1 = o[2 * B]; c.C2 = o[3 * B]; c.D1 = o[4 * B]; c.cx = o[5 * B]; c.cth = o[6 * B]; c.com = o[7 * B];
-      const float u = sq[t * B];
-      const float up = (t > 0) ? sq[(t - 1) * B] : u_prev;
-      // d(l_t)/d(u_t) + d(l_{t+1})/d(u_t)  (stage_cost_adjoint_u)
-      float gu = fmaf(gu_b, u - up, gu_a * u);
-      if (t < H - 1) gu = fmaf(-gu_b, sq[(t + 1) * B] - u, gu);
-      const float g = adjoint_apply(c, hh, D2, KV, KU, t > 0, lam) + gu;
-      sg[t * B] = g;
-      nrm2 = fmaf(g, g, nrm2);
+      for (int t = H - 1; t >= 0; --t) {
+        const float* o = tp + (size_t)t * 8 * B;
+        AdjCoef c;
+        c.E1 = o[0]; c.E2 = o[B]; c.C1 = o[2 * B]; c.C2 = o[3 * B]; c.D1 = o[4 * B]; c.cx = o[5 * B]; c.cth = o[6 * B]; c.com = o[7 * B];
+        const float u = sq[t * B];
+        const float up = (t > 0) ? sq[(t - 1) * B] : u_prev;
+        // d(l_t)/d(u_t) + d(l_{t+1})/d(u_t)  (stage_cost_adjoint_u)
+        float gu = fmaf(gu_b, u - up, gu_a * u);
+        if (t < H - 1) gu = fmaf(-gu_b, sq[(t + 1) * B] - u, gu);
+        const float g = adjoint_apply(c, hh, D2, KV, KU, t > 0, lam) + gu;
+        sg[t * B] = g;
+        nrm2 = fmaf(g, g, nrm2);
+      }
+      sh_den[lane] = fmaxf(sqrtf(nrm2), clipc);  // clip_by_norm over the trajectory
     }
-    // ---- clip_by_norm over the trajectory, optimizer update, box clip ----
-    const float den = fmaxf(sqrtf(nrm2), clipc);
+    __syncthreads();
+    // ---- optimizer update, box clip: parallel over the horizon ----
+    const float den = sh_den[lane];
     const double step = (double)(a.adam_step0 + it + 1);
     const double bc1d = 1.0 - pow(a.beta1, step), bc2d = 1.0 - pow(a.beta2, step);
     const float b1 = (float)a.beta1, b2 = (float)a.beta2;
     const float omb1 = (float)(1.0 - a.beta1), omb2 = (float)(1.0 - a.beta2);
     const float bc1 = (float)bc1d, bc2 = (float)bc2d, eps = (float)a.eps;
     const float alpha = (float)((double)a.lr * sqrt(bc2d) / bc1d);
-#pragma unroll 4
-    for (int t = 0; t < H; ++t) {
+#pragma unroll 2
+    for (int t = wid; t < H; t += W) {
       const float g = sg[t * B] * clipc / den;
       float q = sq[t * B];
       if (!moments) {
@@ -206,18 +216,22 @@ __global__ void __launch_bounds__(32) rpgd_grad_coef_kernel(const RpgdGradArgs a
       }
       sq[t * B] = fminf(fmaxf(q, lo), hi);
     }
+    __syncthreads();
   }
-  if (moments && a.iters > 0) {
+  if (active) {
 #pragma unroll 4
-    for (int t = 0; t < H; ++t) { a.m[(size_t)t * a.N + n] = sm[t * B]; a.v[(size_t)t * a.N + n] = sv[t * B]; }
+    for (int t = wid; t < H; t += W) {
+      a.Q[(size_t)t * a.N + n] = sq[t * B];
+      if (moments && a.iters > 0) { a.m[(size_t)t * a.N + n] = sm[t * B]; a.v[(size_t)t * a.N + n] = sv[t * B]; }
+    }
   }
+  if (wid != 0 || !active) return;
 
   // ---- cost of the updated population ----
   State z = z0;
   float omc = omc0, u_last = u_prev, jsum = 0.0f;
   for (int t = 0; t < H; ++t) {
     const float u = sq[t * B];
-    a.Q[(size_t)t * a.N + n] = u;
     if (LOG) {
       float* o = a.log_traj_soa + (size_t)t * 6 * a.N + n;
       o[0] = z.th; o[a.N] = z.om; o[2 * a.N] = z.c; o[3 * a.N] = z.s; o[4 * (size_t)a.N] = z.x; o[5 * (size_t)a.N] = z.v;

@@ -15,7 +15,7 @@ cudaError_t launch_rpgd_grad(int kind, bool log, bool coef, int nblocks, int blo
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  return launch_pdl(k, dim3(nblocks), dim3(block), smem, st, a);
+  return launch_pdl(k, dim3(nblocks), dim3(coef ? 32 * kRpgdWarps : block), smem, st, a);
 }
 cudaError_t launch_rpgd_select(const RpgdSelectArgs& a, cudaStream_t st) {
   return launch_pdl(rpgd_select_kernel, dim3(1), dim3(TOPK_THREADS), 0, st, a);

@@ -248,6 +248,55 @@ def test_rpgd_edge_geometries_match_oracle(N, H, over):
     assert t >= 1  # at least the first tick ranked identically
 
 
+@pytest.mark.parametrize("fixture,N,H,over", [
+    ("gradient_n40", 1, 7, {}), ("gradient_n40", 33, 2, {"gradient_steps": 1}), ("gradient_n40", 257, 50, {"gradmax_clip": 0.5}),
+    ("gradcem_naive_n200", 1, 5, {"cem_best_k": 1}), ("gradcem_naive_n200", 33, 2, {"cem_best_k": 33, "cem_outer_it": 2}),
+    ("gradcem_naive_n200", 1000, 24, {"cem_best_k": 7}),
+    ("gradcem_bharadhwaj_n32", 2, 9, {"cem_best_k": 1}), ("gradcem_bharadhwaj_n32", 65, 3, {"cem_best_k": 65}),
+    ("gradcem_bharadhwaj_n32", 300, 40, {"cem_best_k": 32, "cem_outer_it": 1})])
+def test_sibling_gradient_optimizers_edge_geometries_match_oracle(fixture, N, H, over):
+    """gradient-tf, cem-naive-grad-tf and cem-grad-bharadhwaj-tf at ragged geometries against their oracles: a single sequence,
+    two / three-step horizons, k = 1 and k = N (no fresh samples in the carried-elite variant), populations that are not a
+    multiple of the warp or block size, an active and an inactive norm clip."""
+    from oracle import spec
+    from oracle.replay_rng import ReplayRNG
+    z, meta = load_golden(fixture)
+    meta = dict(meta, cfg=dict(meta["cfg"], num_rollouts=N, mpc_horizon=H, **over))
+    ctrl = make_controller(meta, rng=None, logging=True)
+    opt = ctrl.optimizer
+    opt.rng = ReplayRNG(11, as_torch=False)
+    opt.optimizer_reset()
+    o = make_oracle(meta)
+    rng = ReplayRNG(11)
+    o.reset(rng)
+    ok_ticks = 0
+    for t, s0 in enumerate(spec.synthetic_states(4, seed=29)):
+        u = ctrl.step(s0)
+        uo = o.step(s0, rng)
+        if meta["optimizer"] == "gradient-tf":
+            same = opt.best_index() == o.last["best_idx"]
+            e_state = max_rel(opt.Q_tf, o.Q.numpy(), floor=1e-2)
+        else:
+            got, ref = opt.elite_indices(), o.last["elite_idx"]
+            same = got.shape == ref.shape and all(set(a.tolist()) == set(b.tolist()) for a, b in zip(got, ref))
+            e_state = max(max_rel(opt.dist_mue, o.dist_mue.numpy(), floor=1e-2), max_rel(opt.stdev, o.stdev.numpy(), floor=1e-2))
+        e_u = abs(float(np.ravel(u)[0]) - float(np.ravel(uo)[0]))
+        dQ = np.abs(np.asarray(opt.logging_values["Q_logged"], np.float64) - o.last["Q"]).ravel()
+        e_Q, e_Q99 = float(dQ.max()), float(np.quantile(dQ, 0.99))  # controls live in [-1, 1]: absolute == relative to the range
+        _report(f"{meta['optimizer']} edge N={N} H={H} {over} tick {t}: state {e_state:.2e} Qn max {e_Q:.2e} q99 {e_Q99:.2e} u {e_u:.2e} "
+                f"same_ranking {same}")
+        if not same:
+            break  # a noise-level swap in the cost ranking changes the refit / the chosen sequence from here on
+        # Adam divides by sqrt(v): where |g| ~ 1e-6 a rounding-level gradient difference moves a control by O(lr) (DESIGN.md, Adam
+        # quirk), and 50 unstable steps x several ticks amplify it -> 99 % of the controls within 2e-4, the worst within 5e-3;
+        # the first tick (no accumulated history) and the distribution / chosen control are held to 2e-4 throughout
+        assert e_Q99 < 2e-4 and e_Q < (2e-4 if t == 0 else 5e-3) and e_u < 2e-4, (fixture, N, H, over, t, e_Q, e_Q99, e_u)
+        if meta["optimizer"] != "gradient-tf":
+            assert e_state < 2e-4, (fixture, N, H, over, t, e_state)
+        ok_ticks += 1
+    assert ok_ticks >= 1
+
+
 def test_rpgd_last_inducing_point_quirk():
     """reference others/Interpolator.py:73-74 divides the '1' of the last inducing point by the period: with H - 1 a multiple of the
     period the final horizon step of every sampled sequence is y_last / period.  RPGD's initial population must show it."""
