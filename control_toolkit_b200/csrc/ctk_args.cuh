@@ -168,6 +168,22 @@ struct CemArgs {
   float* log_Q_soa;     // [H][N] or null
 };
 
+// K3 for the ODE predictor with intermediate_steps == 1: the scaled-variable step of K1 (ctk_ode_scaled.cuh)
+struct CemOdeArgs {
+  int N, off, H;
+  S0 s0;                // initial state
+  const float* mu;      // [H] dist_mue
+  const float* sd;      // [H] stdev
+  const float* u_prev;  // [1]
+  NoiseSrc noise;       // per_rollout = H
+  OdeHot k;             // uniform-register constants (derive_ode_hot with a zero MPPI correction; lo / hi = control limits)
+  float* J;             // [N]
+  float* log_traj_soa;  // [(H+1)][6][N] or null
+  float* log_Q_soa;     // [H][N] or null
+  uint64_t* cand_out;   // != null: every block (256 rollouts) also sorts its (cost, global id) keys and emits its kk smallest
+  int kk;               //          to cand_out[blockIdx.x * kk ..] -- level 0 of the hierarchical top-k without its own launch
+};
+
 struct CemRefitArgs {
   int H, k, cnt;             // cnt candidate keys (num_shards * k, each shard's list sorted or not)
   const uint64_t* cand;      // [cnt] (ordered cost, global id)

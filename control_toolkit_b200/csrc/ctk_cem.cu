@@ -21,6 +21,16 @@ static cudaError_t launch_cem_p(int kind, bool log, int nblocks, size_t smem, cu
 cudaError_t launch_cem_rollout(int pred, int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemArgs& a) {
   return pred == 0 ? launch_cem_p<OdePred>(kind, log, nblocks, smem, st, a) : launch_cem_p<MlpSimtPred>(kind, log, nblocks, smem, st, a);
 }
+cudaError_t launch_cem_ode(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemOdeArgs& a) {
+  void (*k)(const CemOdeArgs) = nullptr;
+  if (kind == 0) k = log ? cem_ode_kernel<0, true> : cem_ode_kernel<0, false>;
+  else k = log ? cem_ode_kernel<1, true> : cem_ode_kernel<1, false>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  return launch_pdl(k, dim3(nblocks), dim3(a.cand_out != nullptr ? kCemOdeTopkThreads : 128), smem, st, a);
+}
 // Level 0: keys from costs (global index = off + i).  Each block sorts 1024 keys and emits its k smallest.
 // Level >0: same on candidate keys.  out has gridDim.x * k keys.
 __global__ void __launch_bounds__(TOPK_THREADS) topk_level_kernel(const float* __restrict__ cost, const uint64_t* __restrict__ keys_in,

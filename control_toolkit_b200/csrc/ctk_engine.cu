@@ -142,6 +142,12 @@ static cudaError_t upload_consts(ctk_handle* h) {
                 (double)c.mppi_neg_inv_LBD, (double)c.mppi_stdev, (double)c.action_low, (double)c.action_high};
     derive_ode_hot(h->ode_p, h->cost_p, h->H, mc, h->ode_hot);
     mppi_ode_geometry(h);
+  } else if (h->cfg.optimizer == CTK_OPT_CEM) {
+    // K3s (scaled-variable CEM rollout): the same constants with a zero MPPI correction
+    const ctk_config& c = h->cfg;
+    MppiCorr mc{0.0, 0.0, 0.0, 0.0, 0.0, 0.0, (double)c.action_low, (double)c.action_high};
+    derive_ode_hot(h->ode_p, h->cost_p, h->H, mc, h->ode_hot);
+    h->ode_kernel = c.predictor == CTK_PRED_ODE && h->ode_p.intermediate_steps <= 1 && getenv("CTK_CEM_GENERIC") == nullptr;
   }
   DevConsts kc;
   kc.fwd = h->fwd;
@@ -302,7 +308,7 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
       return fail(CTK_EINVAL, "CEM needs 1 <= cem_best_k <= min(512, num_rollouts), mpc_horizon <= 1024, cem_outer_it >= 1");
     }
     A(dalloc(&h->d_mu, (size_t)H), "mu"); A(dalloc(&h->d_sd, (size_t)H), "sd");
-    const size_t nk = (size_t)((N + 1023) / 1024) * cfg->cem_best_k + 1024;
+    const size_t nk = (size_t)((N + 255) / 256) * cfg->cem_best_k + 1024;  // level-0 candidates of 256-rollout blocks (fused top-k) or 1024-key blocks
     A(dalloc(&h->d_keys[0], nk), "keys0"); A(dalloc(&h->d_keys[1], nk), "keys1");
     int iters = cfg->cem_outer_it;
     if (cfg->cem_warmup && cfg->cem_warmup_iterations > iters) iters = cfg->cem_warmup_iterations;
@@ -670,14 +676,27 @@ static int cem_local(ctk_handle* h, const float* s_dev, bool to_k) {
   int rcn = make_noise(h, STREAM_CEM | ((uint32_t)h->cem_it << 8), h->H, uni, (size_t)h->NG, &ns);
   if (rcn != CTK_OK) return rcn;
   h->cem_noise = ns;
-  CemArgs a{};
-  a.N = h->N; a.off = h->off; a.H = h->H; a.s0 = make_s0(h, s_dev); a.mu = h->d_mu; a.sd = h->d_sd; a.u_prev = h->d_u_prev; a.noise = ns;
-  a.lo = c.action_low; a.hi = c.action_high; a.kc = h->d_kc; a.mlp = h->mlp; a.J = h->d_J;
-  a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
-  const size_t smem = sizeof(float) * (2 * (size_t)h->H + pred_smem_floats(h));
   h->launches++;
   cudaError_t e;
-  {
+  int fused_cand = 0;  // > 0: the rollout kernel already left that many level-0 candidate keys in d_keys[0]
+  if (h->ode_kernel) {
+    CemOdeArgs a{};
+    a.N = h->N; a.off = h->off; a.H = h->H; a.s0 = make_s0(h, s_dev); a.mu = h->d_mu; a.sd = h->d_sd; a.u_prev = h->d_u_prev; a.noise = ns;
+    a.k = h->ode_hot; a.J = h->d_J; a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
+    int nb = h->nblocks;
+    if (c.cem_best_k <= 128 && getenv("CTK_CEM_NO_FUSED_TOPK") == nullptr) {  // level 0 of the top-k inside the rollout kernel
+      nb = (h->N + 255) / 256;
+      a.cand_out = h->d_keys[0]; a.kk = c.cem_best_k;
+      fused_cand = nb * c.cem_best_k;
+    }
+    KernelTimer kt(h);
+    e = launch_cem_ode(h->cost.kind, c.logging != 0, nb, sizeof(float) * 2 * (size_t)h->H, h->stream, a);
+  } else {
+    CemArgs a{};
+    a.N = h->N; a.off = h->off; a.H = h->H; a.s0 = make_s0(h, s_dev); a.mu = h->d_mu; a.sd = h->d_sd; a.u_prev = h->d_u_prev; a.noise = ns;
+    a.lo = c.action_low; a.hi = c.action_high; a.kc = h->d_kc; a.mlp = h->mlp; a.J = h->d_J;
+    a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
+    const size_t smem = sizeof(float) * (2 * (size_t)h->H + pred_smem_floats(h));
     KernelTimer kt(h);
     e = launch_cem_rollout(c.predictor == CTK_PRED_ODE ? 0 : 1, h->cost.kind, c.logging != 0, h->nblocks, smem, h->stream, a);
   }
@@ -687,7 +706,12 @@ static int cem_local(ctk_handle* h, const float* s_dev, bool to_k) {
   int n = h->N, lvl = 0;
   const float* cost = h->d_J;
   const uint64_t* kin = nullptr;
-  while (true) {
+  bool done = false;
+  if (fused_cand > 0) {
+    n = fused_cand; cost = nullptr; kin = h->d_keys[0]; lvl = 1;
+    done = n <= TOPK_THREADS && (!to_k || n == k);
+  }
+  while (!done) {
     const int nb = (n + TOPK_THREADS - 1) / TOPK_THREADS;
     uint64_t* outk = h->d_keys[lvl & 1];
     h->launches++;

@@ -4,6 +4,7 @@
 #include "ctk_device.cuh"
 #include "ctk_predictor.cuh"
 #include "ctk_topk.cuh"
+#include "ctk_ode_scaled.cuh"
 
 namespace ctk {
 
@@ -65,6 +66,77 @@ __global__ void __launch_bounds__(128) cem_rollout_kernel(const CemArgs a) {
 }
 
 // One block of 1024 threads: merge candidates -> global top-k (bitonic), regenerate elite Q, refit mu / sd.
+// K3s: the same sample -> rollout -> cost pass for the ODE predictor in the scaled state variables of K1 (12-instruction Euler
+// step, cost with the control terms merged into u (kA u + kB u_prev) and the u_prev^2 terms telescoped; constants are kernel
+// parameters -> uniform registers).  The Philox block of the NEXT four steps is generated next to the current four steps'
+// dependent chain, so the draw latency never sits on it.
+constexpr int kCemOdeTopkThreads = 256;  // block size when the block-level top-k is fused in (CemOdeArgs::cand_out)
+template <int KIND, bool LOG>
+__global__ void __launch_bounds__(kCemOdeTopkThreads) cem_ode_kernel(const CemOdeArgs a) {
+  extern __shared__ float smem[];
+  float* sh_mu = smem;         // [H]
+  float* sh_sd = smem + a.H;   // [H]
+  __shared__ uint64_t sh_keys[kCemOdeTopkThreads];
+  const OdeHot& k = a.k;
+  pdl_wait();
+  pdl_trigger();
+  for (int t = threadIdx.x; t < a.H; t += blockDim.x) {
+    sh_mu[t] = a.mu[t];
+    sh_sd[t] = a.sd[t];
+  }
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = n < a.N;
+  if (!active && a.cand_out == nullptr) return;
+  uint64_t key = KEY_MAX;
+  if (active) {
+  const uint32_t ng = (uint32_t)(a.off + n);
+  const float s0v[6] = {a.s0.ld(0), a.s0.ld(1), a.s0.ld(2), a.s0.ld(3), a.s0.ld(4), a.s0.ld(5)};
+  ScaledState r;
+  scaled_from_state(s0v, k, r);
+  const float u_prev = a.u_prev[0];
+  float ul = u_prev;
+  float acc = (k.k_ccrc * u_prev) * u_prev;  // telescoped control-change cost: + k_ccrc u_{-1}^2 here, - k_ccrc u_{H-1}^2 at the end
+  float zn[4];
+  noise4(a.noise, ng, 0u, zn);
+  for (int t0 = 0; t0 < a.H; t0 += 4) {
+    const float z0 = zn[0], z1 = zn[1], z2 = zn[2], z3 = zn[3];
+    if (t0 + 4 < a.H) noise4(a.noise, ng, (uint32_t)((t0 >> 2) + 1), zn);
+    const float zz[4] = {z0, z1, z2, z3};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = t0 + q;
+      if (t < a.H) {
+        const float u = cem_sample(sh_mu[t], sh_sd[t], zz[q], k.lo, k.hi);
+        if (LOG) {
+          float st[6];
+          scaled_to_state(r, k, st);
+          float* p = a.log_traj_soa + (size_t)t * 6 * a.N + n;
+          p[0] = st[0]; p[a.N] = st[1]; p[2 * a.N] = st[2]; p[3 * a.N] = st[3]; p[4 * (size_t)a.N] = st[4]; p[5 * (size_t)a.N] = st[5];
+          a.log_Q_soa[(size_t)t * a.N + n] = u;
+        }
+        acc = stage_cost_scaled<KIND>(acc, r, u, ul, 0.0f, k);  // kC == 0 for CEM (no MPPI correction)
+        ode_step_scaled(r, u, k);
+        ul = u;
+      }
+    }
+  }
+  if (LOG) {
+    float st[6];
+    scaled_to_state(r, k, st);
+    float* p = a.log_traj_soa + (size_t)a.H * 6 * a.N + n;
+    p[0] = st[0]; p[a.N] = st[1]; p[2 * a.N] = st[2]; p[3 * a.N] = st[3]; p[4 * (size_t)a.N] = st[4]; p[5 * (size_t)a.N] = st[5];
+  }
+  const float J = finish_cost_scaled(acc, r, ul, k);
+  a.J[n] = J;
+  key = make_key(J, ng);
+  }
+  if (a.cand_out != nullptr) {  // block-level top-k (K4 level 0): blockDim.x == kCemOdeTopkThreads
+    key = block_bitonic_sort(key, sh_keys, kCemOdeTopkThreads);
+    if ((int)threadIdx.x < a.kk) a.cand_out[(size_t)blockIdx.x * a.kk + threadIdx.x] = key;
+  }
+}
+
 __global__ void __launch_bounds__(TOPK_THREADS) cem_refit_kernel(const CemRefitArgs a) {
   __shared__ uint64_t sh[TOPK_THREADS];
   __shared__ uint32_t sh_elite[TOPK_THREADS];
