@@ -61,6 +61,10 @@ class template_optimizer:
         self.mlp_engine = str(kwargs.pop("mlp_engine", "simt"))
         self.shard = kwargs.pop("shard", None)  # control_toolkit_b200.distributed.ShardPlan or None
         self.environment_name = kwargs.pop("environment_name", None)
+        # logs of at least this many bytes are handed out as read-only VIEWS of a pinned host buffer owned by the C handle (valid
+        # until the next step(); controller_mpc.update_logs copies them like the reference, Controllers/__init__.py:159-178);
+        # smaller logs are fresh copies.  None: always copy.
+        self.log_view_min_bytes = kwargs.pop("log_view_min_bytes", 16 << 20)
         self._h = None
         self._cost_spec = None
         self._cost_live = (None, None)
@@ -228,7 +232,16 @@ class template_optimizer:
 
     def _get_log(self, which: int, shape, dtype=np.float32) -> np.ndarray:
         lib = self._require_backend()
-        out = np.empty(int(np.prod(shape)), dtype)
+        count = int(np.prod(shape))
+        if self.log_view_min_bytes is not None and count * np.dtype(dtype).itemsize >= self.log_view_min_bytes:
+            ptr, n = C.c_void_p(), C.c_size_t()
+            L.check(lib.ctk_get_log_view(self._h, which, C.byref(ptr), C.byref(n)))
+            if n.value != count * np.dtype(dtype).itemsize:
+                raise RuntimeError(f"log {which}: {n.value} bytes on the device, {count * np.dtype(dtype).itemsize} expected")
+            view = np.frombuffer((C.c_char * n.value).from_address(ptr.value), dtype=dtype, count=count).reshape(shape)
+            view.flags.writeable = False
+            return view
+        out = np.empty(count, dtype)
         L.check(lib.ctk_get_log(self._h, which, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out.reshape(shape)
 

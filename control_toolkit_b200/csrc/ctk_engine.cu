@@ -67,6 +67,8 @@ struct ctk_handle {
   float *d_s0 = nullptr, *d_u_prev = nullptr, *d_u_out = nullptr, *d_J = nullptr;
   float *h_pin = nullptr;  // MAPPED pinned memory: s[8] | u, status, sequence flag .. [16) | one [H] state array (HostMirror layout)
   float *d_pin = nullptr;  // the device's view of h_pin
+  void* h_log[8] = {nullptr};      // pinned host buffers of ctk_get_log_view, by log id
+  size_t h_log_cap[8] = {0};
   HostMirror mirror{nullptr, 0};  // non-null only while a host-facing tick (ctk_step / ctk_step_state) is being enqueued
   unsigned int hseq = 0;
   // mppi
@@ -213,6 +215,7 @@ extern "C" int ctk_destroy(ctk_handle* h) {
   if (h->d_mbox) cudaFree(h->d_mbox);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->h_pin) cudaFreeHost(h->h_pin);
+  for (void* p : h->h_log) if (p) cudaFreeHost(p);
   delete h;
   return CTK_OK;
 }
@@ -1221,9 +1224,8 @@ extern "C" int ctk_debug_trace(ctk_handle* h, int enable, uint64_t* out_host, si
 }
 extern "C" int ctk_get_launch_count(ctk_handle* h, int64_t* v) { REQ(h && v, "null pointer"); *v = h->launches; return CTK_OK; }
 
-extern "C" int ctk_get_log(ctk_handle* h, int which, void* dst, size_t nbytes) {
-  REQ(h && dst, "null pointer");
-  CU(cudaSetDevice(h->cfg.device));
+// device source (after the layout transpose, if any) and size of one log
+static int log_source(ctk_handle* h, int which, const void** src_out, size_t* need_out) {
   const size_t N = h->N, H = h->H;
   const void* src = nullptr;
   size_t need = 0;
@@ -1254,9 +1256,41 @@ extern "C" int ctk_get_log(ctk_handle* h, int which, void* dst, size_t nbytes) {
       src = h->d_ages_log; need = N * 4; break;
     default: return fail(CTK_EINVAL, "unknown log id");
   }
+  *src_out = src;
+  *need_out = need;
+  return CTK_OK;
+}
+
+extern "C" int ctk_get_log(ctk_handle* h, int which, void* dst, size_t nbytes) {
+  REQ(h && dst, "null pointer");
+  CU(cudaSetDevice(h->cfg.device));
+  const void* src = nullptr;
+  size_t need = 0;
+  int rc = log_source(h, which, &src, &need);
+  if (rc != CTK_OK) return rc;
   REQ(nbytes == need, "size mismatch (expected " + std::to_string(need) + " bytes)");
   CU(cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
+  return CTK_OK;
+}
+
+extern "C" int ctk_get_log_view(ctk_handle* h, int which, const void** host_ptr, size_t* n_bytes) {
+  REQ(h && host_ptr && n_bytes, "null pointer");
+  REQ(which >= 0 && which < 8, "unknown log id");
+  CU(cudaSetDevice(h->cfg.device));
+  const void* src = nullptr;
+  size_t need = 0;
+  int rc = log_source(h, which, &src, &need);
+  if (rc != CTK_OK) return rc;
+  if (h->h_log_cap[which] < need) {
+    if (h->h_log[which]) { CU(cudaStreamSynchronize(h->stream)); cudaFreeHost(h->h_log[which]); h->h_log[which] = nullptr; h->h_log_cap[which] = 0; }
+    CU(cudaHostAlloc(&h->h_log[which], need ? need : 4, cudaHostAllocDefault));
+    h->h_log_cap[which] = need;
+  }
+  CU(cudaMemcpyAsync(h->h_log[which], src, need, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *host_ptr = h->h_log[which];
+  *n_bytes = need;
   return CTK_OK;
 }
 

@@ -200,6 +200,11 @@ int ctk_set_state(ctk_handle *h, int which, const float *src_host, size_t n);
 int ctk_get_counter(ctk_handle *h, int which, int64_t *value);
 int ctk_set_counter(ctk_handle *h, int which, int64_t value);
 int ctk_get_log(ctk_handle *h, int which, void *dst_host, size_t n_bytes);
+/* The same log, handed out as a VIEW of a handle-owned pinned host buffer (one device->host DMA at PCIe rate, no pageable
+   staging, no first-touch page faults on a fresh destination): *host_ptr stays valid until the next ctk_get_log_view of the
+   same log id, ctk_step or ctk_destroy.  Replaces the `.numpy()` hand-over of the logged tensors (reference
+   optimizer_mppi.py:214-218, Controllers/__init__.py:159-178 copies them into the controller's own history).           */
+int ctk_get_log_view(ctk_handle *h, int which, const void **host_ptr, size_t *n_bytes);
 /* number of CUDA kernels this handle has launched since create (bench.py "gpu_launches")                         */
 int ctk_get_launch_count(ctk_handle *h, int64_t *value);
 /* CUDA-event timing of the dominant kernel of a tick (the fused rollout kernel: K1 MPPI, K3 CEM, K6/K7 RPGD), used by

@@ -297,6 +297,30 @@ def test_sibling_gradient_optimizers_edge_geometries_match_oracle(fixture, N, H,
     assert ok_ticks >= 1
 
 
+def test_log_views_equal_copies():
+    """Logging export: logs handed out as views of the handle's pinned host buffer (ctk_get_log_view) hold exactly
+    what the copying path (ctk_get_log) returns, are read-only, and follow the next tick."""
+    z, meta = load_golden("mppi_c1_n64")
+    a = make_controller(meta, log_view_min_bytes=0)
+    b = make_controller(meta, log_view_min_bytes=None)
+    keep = None
+    for t in range(3):
+        a.step(z["states"][t])
+        b.step(z["states"][t])
+        la, lb = a.optimizer.logging_values, b.optimizer.logging_values
+        for key in ("Q_logged", "J_logged", "rollout_trajectories_logged"):
+            np.testing.assert_array_equal(la[key], lb[key])
+        assert not la["rollout_trajectories_logged"].flags.writeable and lb["rollout_trajectories_logged"].flags.writeable
+        if t == 0:
+            keep = la["rollout_trajectories_logged"]  # a view: it shows the NEXT tick's log after the next step()
+            first = lb["rollout_trajectories_logged"].copy()
+    assert not np.array_equal(keep, first)
+    np.testing.assert_array_equal(keep, b.optimizer.logging_values["rollout_trajectories_logged"])
+    # the controller's own history copies the views (reference Controllers/__init__.py:159-178)
+    hist = a.get_outputs()["rollout_trajectories_logged"]
+    np.testing.assert_array_equal(hist[0], first)
+
+
 def test_rpgd_last_inducing_point_quirk():
     """reference others/Interpolator.py:73-74 divides the '1' of the last inducing point by the period: with H - 1 a multiple of the
     period the final horizon step of every sampled sequence is y_last / period.  RPGD's initial population must show it."""
