@@ -344,12 +344,15 @@ def run_ours(args):
             fl_step = FLOP_PER_ROLLOUT_STEP["cem_ode"]
             peak, clk = C.c_double(), C.c_double()
             L.check(lib.ctk_fp32_peak(local_rank, C.byref(peak), C.byref(clk)))
-            achieved = fl_step * n_local * H / (k1_ms * 1e-3) / 1e12  # k1_ms: average over the cem_outer_it rollout launches of a tick
-            roofline = {"bound": "fp32", "kernel": "cem_rollout_kernel<OdePred> (one launch per outer iteration)", "achieved": achieved,
+            one_launch = launches == K  # persistent tick: all outer iterations (rollouts, top-k, refit) in ONE launch
+            per_launch = passes if one_launch else 1
+            achieved = fl_step * n_local * H * per_launch / (k1_ms * 1e-3) / 1e12
+            roofline = {"bound": "fp32", "kernel": ("cem_tick_kernel (persistent: the whole tick -- rollouts, top-k and refit of all outer iterations)" if one_launch
+                                                    else "cem_ode_kernel (one launch per outer iteration)"), "achieved": achieved,
                         "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": None,
                         "peak_source": "measured live: FP32 FMA-chain microbenchmark (ctk_fp32_peak)", "flop_per_rollout_step": fl_step,
-                        "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms * passes / tick2_ms,
-                        "note": "4096 rollouts occupy 32 of 148 SMs with one warp per scheduler: the tick is launch- and latency-bound"}
+                        "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms * (1 if one_launch else passes) / tick2_ms,
+                        "note": "4096 rollouts occupy 8 of 148 SMs: the tick is a chain of dependent phases, latency-bound by construction"}
         elif opt_name == "rpgd":
             its = RPGD_CFG["outer_its"]
             fl_launch = (FLOP_PER_ROLLOUT_STEP["rpgd_grad"] * its + FLOP_PER_ROLLOUT_STEP["rpgd_fwd"]) * n_local * H

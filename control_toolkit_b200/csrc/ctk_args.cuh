@@ -184,6 +184,33 @@ struct CemOdeArgs {
   int kk;               //          to cand_out[blockIdx.x * kk ..] -- level 0 of the hierarchical top-k without its own launch
 };
 
+// The whole CEM tick (all outer iterations) as ONE persistent launch for populations that fit one resident grid
+// (ctk_kernels_cem.cuh cem_tick_kernel): blocks exchange their candidate keys and block 0 publishes the refit distribution
+// through tagged 8-byte slots, so the iterations need no kernel boundary.
+struct CemTickArgs {
+  int N, off, H, k, iters;
+  S0 s0;
+  float *mu, *sd;              // [H] dist_mue / stdev, in/out
+  float* u_prev;               // [1] in (cost) / out (unless frozen)
+  float* u_out;                // [1] or null
+  int freeze_prev;
+  NoiseSrc noise;              // iteration 0; iteration it: stream | it << 8, inj + it * inj_stride
+  size_t inj_stride;           // draws per iteration (N_global * H)
+  OdeHot hot;                  // uniform-register constants (zero MPPI correction; lo / hi = control limits)
+  float* J;                    // [N] costs of the LAST iteration
+  float* log_traj_soa;         // [(H+1)][6][N] or null
+  float* log_Q_soa;            // [H][N] or null
+  unsigned long long* cand;    // [gridDim.x][k] tagged candidate keys: ordered cost (32) | id (16) | sequence tag (16)
+  int k2, runs_pad, q_cap;     // pow2 >= max(k, 32); pow2 >= gridDim.x; floats of the big shared buffer (>= runs_pad * k2 * 2)
+  unsigned long long* dist;    // [2][H] tagged mu / sd published by block 0 for the next iteration
+  unsigned int seq0;           // sequence number of iteration 0 (monotonic across ticks, never 0)
+  float sd_min, sd_init;
+  int32_t* elite_idx_out;      // [elite_cap][k] global ids, best first, or null
+  int elite_cap;
+  HostMirror host;
+  unsigned long long* trace;   // diagnostics (ctk_debug_trace): block 0's globaltimer stamps [iteration][8], or null
+};
+
 struct CemRefitArgs {
   int H, k, cnt;             // cnt candidate keys (num_shards * k, each shard's list sorted or not)
   const uint64_t* cand;      // [cnt] (ordered cost, global id)

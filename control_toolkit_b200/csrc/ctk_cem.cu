@@ -31,6 +31,27 @@ cudaError_t launch_cem_ode(int kind, bool log, int nblocks, size_t smem, cudaStr
   }
   return launch_pdl(k, dim3(nblocks), dim3(a.cand_out != nullptr ? kCemOdeTopkThreads : 128), smem, st, a);
 }
+cudaError_t launch_cem_tick(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemTickArgs& a) {
+  void (*k)(const CemTickArgs) = nullptr;
+  if (kind == 0) k = log ? cem_tick_kernel<0, true> : cem_tick_kernel<0, false>;
+  else k = log ? cem_tick_kernel<1, true> : cem_tick_kernel<1, false>;
+  if (smem > 11 * 1024) {  // 37 KB of static shared memory come on top
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  return launch_pdl(k, dim3(nblocks), dim3(kCemTickThreads), smem, st, a);
+}
+int cem_tick_rollouts_per_block() { return kCemTickRollouts; }
+// resident blocks per SM of the persistent tick kernel (its blocks wait for each other: the whole grid must be resident)
+int cem_tick_blocks_per_sm(int kind, bool log, size_t smem) {
+  void (*k)(const CemTickArgs) = nullptr;
+  if (kind == 0) k = log ? cem_tick_kernel<0, true> : cem_tick_kernel<0, false>;
+  else k = log ? cem_tick_kernel<1, true> : cem_tick_kernel<1, false>;
+  if (smem > 11 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, kCemTickThreads, smem) != cudaSuccess) return 0;
+  return nb;
+}
 // Level 0: keys from costs (global index = off + i).  Each block sorts 1024 keys and emits its k smallest.
 // Level >0: same on candidate keys.  out has gridDim.x * k keys.
 __global__ void __launch_bounds__(TOPK_THREADS) topk_level_kernel(const float* __restrict__ cost, const uint64_t* __restrict__ keys_in,

@@ -14,6 +14,32 @@ namespace ctk {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- tagged 8-byte slots: a 32-bit value and the sequence number of its producer in ONE store; consumers poll until the tag
+//      matches (no fence, no atomic, no flag round trip).  Used for the block records of K1/K2, the cross-GPU mailboxes and the
+//      in-kernel grid synchronisation of the persistent CEM tick ----
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ void st_tagged(unsigned long long* dst, float v, unsigned int seq) {
+  const unsigned long long x = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(x) : "memory");
+}
+// poll an 8-byte (value, seq) slot until the sequence number matches; returns false after ~2 s (writer lost)
+__device__ __forceinline__ bool ld_tagged(const unsigned long long* src, unsigned int seq, unsigned long long t0, float* v_out) {
+  unsigned long long v;
+  int spins = 0;
+  while (true) {
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+    if ((unsigned int)(v >> 32) == seq) break;
+    if ((++spins & 1023) == 0 && globaltimer_ns() - t0 > 2000000000ull) { *v_out = 0.0f; return false; }
+  }
+  *v_out = __uint_as_float((unsigned int)(v & 0xffffffffull));
+  return true;
+}
+
 // Publish a tick's result mirror to the host caller (see HostMirror): every thread that stored into m.p must have passed a
 // block barrier before the ONE calling thread gets here.
 __device__ __forceinline__ void host_publish(const HostMirror& m) {

@@ -81,6 +81,9 @@ struct ctk_handle {
   int cem_it = 0, cem_iters = 0, cem_cand = 0;
   uint64_t* cem_cand_ptr = nullptr;
   NoiseSrc cem_noise{};
+  unsigned long long *d_cem_cand = nullptr, *d_cem_dist = nullptr;  // persistent CEM tick: tagged candidate / distribution slots
+  unsigned int cem_seq = 0;
+  int cem_tick_per_sm = -1;  // resident blocks per SM of the persistent tick kernel (queried once)
   // rpgd
   float *d_Q[2] = {nullptr, nullptr}, *d_m[2] = {nullptr, nullptr}, *d_v[2] = {nullptr, nullptr}, *d_ages[2] = {nullptr, nullptr};
   int cur = 0;
@@ -206,6 +209,8 @@ extern "C" int ctk_destroy(ctk_handle* h) {
   if (h->d_keys[0]) cudaFree(h->d_keys[0]);
   if (h->d_keys[1]) cudaFree(h->d_keys[1]);
   if (h->d_elite_idx) cudaFree(h->d_elite_idx);
+  if (h->d_cem_cand) cudaFree(h->d_cem_cand);
+  if (h->d_cem_dist) cudaFree(h->d_cem_dist);
   if (h->d_best_idx) cudaFree(h->d_best_idx);
   if (h->d_mlp_tc) cudaFree(h->d_mlp_tc);
   for (int r = 0; r < CTK_MAX_PEERS; ++r)
@@ -317,6 +322,13 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
     if (cfg->cem_warmup && cfg->cem_warmup_iterations > iters) iters = cfg->cem_warmup_iterations;
     h->elite_log_cap = iters;
     A(dalloc(&h->d_elite_idx, (size_t)iters * cfg->cem_best_k), "elite_idx");
+    {  // persistent single-launch tick (cem_tick_kernel): tagged slots for one resident grid
+      cudaDeviceProp prop;
+      A(cudaGetDeviceProperties(&prop, cfg->device), "props");
+      h->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
+      A(dalloc(&h->d_cem_cand, (size_t)2 * h->num_sms * 128), "cem_cand");  // [blocks <= 2 x SMs][k <= 128]
+      A(dalloc(&h->d_cem_dist, (size_t)2 * 512), "cem_dist");
+    }
   } else {
     if (!(N <= 1024 && cfg->rpgd_keep_k >= 1 && cfg->rpgd_keep_k <= N && N == h->NG && cfg->predictor == CTK_PRED_ODE &&
           ode->intermediate_steps <= 1 && cfg->rpgd_shift_previous >= 0)) {
@@ -659,6 +671,80 @@ static int mppi_finish(ctk_handle* h, const float* gathered, int G, float* u_out
   return CTK_OK;
 }
 
+// The whole CEM tick in one persistent launch, when the population fits one resident grid and is not sharded
+struct CemTickGeom { int G, k2, runs_pad, big_floats; size_t smem; };
+static bool cem_tick_geometry(const ctk_handle* h, CemTickGeom* g) {
+  const ctk_config& c = h->cfg;
+  const int RB = cem_tick_rollouts_per_block();
+  g->G = (h->N + RB - 1) / RB;
+  g->k2 = 32;
+  while (g->k2 < c.cem_best_k) g->k2 <<= 1;
+  g->runs_pad = 1;
+  while (g->runs_pad < g->G) g->runs_pad <<= 1;
+  const long long run_floats = 2ll * g->runs_pad * g->k2;  // uint64 keys
+  g->big_floats = (int)std::max<long long>(8192, run_floats);
+  g->smem = sizeof(float) * ((size_t)((2 * h->H + 3) & ~3) + (size_t)g->big_floats);
+  return run_floats <= 40 * 1024;  // <= 160 KB of candidate runs
+}
+static bool cem_persistent_ok(ctk_handle* h) {
+  const ctk_config& c = h->cfg;
+  if (!(c.optimizer == CTK_OPT_CEM && h->ode_kernel && h->N == h->NG && h->off == 0 && h->xworld == 1 && c.cem_best_k <= 128 &&
+        h->H <= 512 && h->num_sms > 0 && h->N <= 65535 && getenv("CTK_CEM_MULTI_LAUNCH") == nullptr))
+    return false;
+  CemTickGeom g;
+  if (!cem_tick_geometry(h, &g)) return false;
+  if (h->cem_tick_per_sm < 0) h->cem_tick_per_sm = cem_tick_blocks_per_sm(h->cost.kind, c.logging != 0, g.smem);
+  return h->cem_tick_per_sm >= 1 && g.G <= h->cem_tick_per_sm * h->num_sms;  // every block must be resident: blocks wait for each other
+}
+static int cem_tick_persistent(ctk_handle* h, const float* s_dev, float* u_out_dev) {
+  const ctk_config& c = h->cfg;
+  const int iters = (c.cem_warmup && h->count == 0) ? c.cem_warmup_iterations : c.cem_outer_it;  // optimizer_cem_tf.py:92
+  if (iters < 1) return fail(CTK_EINVAL, "CEM iteration count < 1");
+  const int uni = c.cem_uniform_actions ? 1 : 0;
+  if (uni) {  // random shooting: Q = z (high - low) + low  ==  the CEM sample clip(mu + z sd) with mu = low, sd = high - low
+    std::vector<float> mu((size_t)h->H, c.action_low), sd((size_t)h->H, c.action_high - c.action_low);
+    CU(cudaMemcpyAsync(h->d_mu, mu.data(), sizeof(float) * h->H, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_sd, sd.data(), sizeof(float) * h->H, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  CemTickArgs a{};
+  for (int it = 0; it < iters; ++it) {  // one noise block per outer iteration: consecutive in the injected queue
+    NoiseSrc ns{};
+    int rcn = make_noise(h, STREAM_CEM | ((uint32_t)it << 8), h->H, uni, (size_t)h->NG, &ns);
+    if (rcn != CTK_OK) return rcn;
+    if (it == 0) a.noise = ns;
+    h->cem_noise = ns;
+  }
+  a.inj_stride = (size_t)h->NG * h->H;
+  a.N = h->N; a.off = h->off; a.H = h->H; a.k = c.cem_best_k; a.iters = iters;
+  a.s0 = make_s0(h, s_dev); a.mu = h->d_mu; a.sd = h->d_sd; a.u_prev = h->d_u_prev; a.u_out = u_out_dev;
+  a.freeze_prev = c.freeze_previous_input; a.hot = h->ode_hot; a.J = h->d_J;
+  a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
+  a.cand = h->d_cem_cand; a.dist = h->d_cem_dist;
+  if (h->cem_seq > 0xffff0000u) h->cem_seq = 0;
+  a.seq0 = h->cem_seq + 1;
+  h->cem_seq += (unsigned int)iters;
+  a.sd_min = c.cem_stdev_min; a.sd_init = c.cem_initial_action_stdev;
+  a.elite_idx_out = h->d_elite_idx; a.elite_cap = h->elite_log_cap;
+  a.host = h->mirror;
+  a.trace = h->d_trace;
+  h->elite_log_rows = iters < h->elite_log_cap ? iters : h->elite_log_cap;
+  h->cem_iters = iters;
+  CemTickGeom g;
+  cem_tick_geometry(h, &g);
+  a.k2 = g.k2; a.runs_pad = g.runs_pad; a.q_cap = g.big_floats;
+  h->launches++;
+  cudaError_t e;
+  {
+    KernelTimer kt(h);
+    e = launch_cem_tick(h->cost.kind, c.logging != 0, g.G, g.smem, h->stream, a);
+  }
+  if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("cem_tick_kernel: ") + cudaGetErrorString(e));
+  h->cem_it = 0;
+  h->count++;
+  return CTK_OK;
+}
+
 // CEM: rollouts + local top-k candidates.  to_k: reduce to exactly k keys (sharded exchange record).
 static int cem_local(ctk_handle* h, const float* s_dev, bool to_k) {
   const ctk_config& c = h->cfg;
@@ -967,7 +1053,8 @@ static int step_host(ctk_handle* h, const float* s_host, float* u_out_host, cons
     rc = mppi_local(h, nullptr, 2, h->d_u_out);
   } else if (h->cfg.optimizer == CTK_OPT_CEM) {
     h->tick++;
-    do {
+    if (cem_persistent_ok(h)) rc = cem_tick_persistent(h, nullptr, h->d_u_out);
+    else do {
       rc = cem_local(h, nullptr, false);
       if (rc != CTK_OK) break;
       rc = cem_finish(h, h->cem_cand_ptr, h->cem_cand, h->d_u_out);
@@ -1005,7 +1092,8 @@ extern "C" int ctk_step_device(ctk_handle* h, const float* s_dev, float* u_out_d
   if (h->cfg.optimizer == CTK_OPT_MPPI) {
     rc = mppi_local(h, s_dev, 2, uo);
   } else if (h->cfg.optimizer == CTK_OPT_CEM) {
-    do {
+    if (cem_persistent_ok(h)) rc = cem_tick_persistent(h, s_dev, uo);
+    else do {
       rc = cem_local(h, s_dev, false);
       if (rc != CTK_OK) break;
       rc = cem_finish(h, h->cem_cand_ptr, h->cem_cand, uo);

@@ -62,29 +62,6 @@ __device__ __forceinline__ void combine_records(const float* in, int cnt, int P,
   __syncthreads();
 }
 
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-__device__ __forceinline__ void st_tagged(unsigned long long* dst, float v, unsigned int seq) {
-  const unsigned long long x = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(v);
-  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(x) : "memory");
-}
-// poll an 8-byte (value, seq) slot until the sequence number matches; returns false after ~2 s (writer lost)
-__device__ __forceinline__ bool ld_tagged(const unsigned long long* src, unsigned int seq, unsigned long long t0, float* v_out) {
-  unsigned long long v;
-  int spins = 0;
-  while (true) {
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
-    if ((unsigned int)(v >> 32) == seq) break;
-    if ((++spins & 1023) == 0 && globaltimer_ns() - t0 > 2000000000ull) { *v_out = 0.0f; return false; }
-  }
-  *v_out = __uint_as_float((unsigned int)(v & 0xffffffffull));
-  return true;
-}
-
 // Called by ALL threads of EVERY block once the block's record brec[P] = [rho_b, a_b, b_z[n_ind]] is complete in SHARED
 // memory (the call starts with a barrier).  mode 0: the record is stored as plain floats to partials[blockIdx.x][P] (a
 // separate combine launch follows).  mode >= 1: every value is published as ONE 8-byte (value, launch sequence number)

@@ -41,6 +41,9 @@ size_t mppi_pred_smem_floats(int pred, const MlpDev& m);
 
 cudaError_t launch_cem_rollout(int pred, int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemArgs& a);
 cudaError_t launch_cem_ode(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemOdeArgs& a);
+cudaError_t launch_cem_tick(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemTickArgs& a);
+int cem_tick_rollouts_per_block();
+int cem_tick_blocks_per_sm(int kind, bool log, size_t smem);
 cudaError_t launch_topk_level(const float* cost, const uint64_t* keys_in, int n, int off, int k, uint64_t* out, cudaStream_t st);
 cudaError_t launch_cem_refit(const CemRefitArgs& a, cudaStream_t st);
 
