@@ -352,7 +352,7 @@ def run_ours(args):
                         "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": None,
                         "peak_source": "measured live: FP32 FMA-chain microbenchmark (ctk_fp32_peak)", "flop_per_rollout_step": fl_step,
                         "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms * (1 if one_launch else passes) / tick2_ms,
-                        "note": "4096 rollouts occupy 8 of 148 SMs: the tick is a chain of dependent phases, latency-bound by construction"}
+                        "note": "4096 rollouts = 32 blocks of 4 rollout warps: the tick is a chain of dependent phases (rollouts, block sort, grid merge, refit per outer iteration), latency-bound by construction"}
         elif opt_name == "rpgd":
             its = RPGD_CFG["outer_its"]
             fl_launch = (FLOP_PER_ROLLOUT_STEP["rpgd_grad"] * its + FLOP_PER_ROLLOUT_STEP["rpgd_fwd"]) * n_local * H

@@ -321,6 +321,35 @@ def test_log_views_equal_copies():
     np.testing.assert_array_equal(hist[0], first)
 
 
+@pytest.mark.parametrize("N,H,k,iters", [(4096, 50, 64, 3), (16000, 30, 64, 2), (300, 21, 100, 4), (65, 7, 1, 1), (9000, 12, 128, 2)])
+def test_cem_persistent_tick_equals_multi_launch(N, H, k, iters):
+    """The one-launch CEM tick (cem_tick_kernel: in-kernel grid synchronisation, merge tree) against the multi-launch path
+    (cem_ode_kernel -> top-k levels -> cem_refit_kernel) on in-kernel Philox noise: same arithmetic, so u, dist_mue, stdev, the
+    elite lists of every outer iteration and the per-rollout costs must be BIT-identical, tick after tick."""
+    z, meta = load_golden("cem_c2_n256_k16")
+    meta = dict(meta, cfg=dict(meta["cfg"], num_rollouts=N, mpc_horizon=H, cem_best_k=k, cem_outer_it=iters))
+    from oracle import spec
+    a = make_controller(meta, rng=None, logging=False)
+    b = make_controller(meta, rng=None, logging=False)
+    try:
+        for t, s0 in enumerate(spec.synthetic_states(4, seed=31)):
+            os.environ.pop("CTK_CEM_MULTI_LAUNCH", None)
+            la0 = a.optimizer.gpu_launches
+            ua = a.step(s0)
+            assert a.optimizer.gpu_launches - la0 == 1  # the whole tick was one launch
+            os.environ["CTK_CEM_MULTI_LAUNCH"] = "1"
+            lb0 = b.optimizer.gpu_launches
+            ub = b.step(s0)
+            assert b.optimizer.gpu_launches - lb0 >= 2 * iters
+            assert float(ua) == float(ub), (N, H, k, t)
+            np.testing.assert_array_equal(a.optimizer.dist_mue, b.optimizer.dist_mue)
+            np.testing.assert_array_equal(a.optimizer.stdev, b.optimizer.stdev)
+            np.testing.assert_array_equal(a.optimizer.last_elite_indices(iters), b.optimizer.last_elite_indices(iters))
+            np.testing.assert_array_equal(a.optimizer.last_costs(), b.optimizer.last_costs())
+    finally:
+        os.environ.pop("CTK_CEM_MULTI_LAUNCH", None)
+
+
 def test_rpgd_last_inducing_point_quirk():
     """reference others/Interpolator.py:73-74 divides the '1' of the last inducing point by the period: with H - 1 a multiple of the
     period the final horizon step of every sampled sequence is y_last / period.  RPGD's initial population must show it."""
