@@ -890,7 +890,7 @@ static int gradcem_tick(ctk_handle* h, const float* s_dev, float* u_out_dev) {
   return CTK_OK;
 }
 
-static int rpgd_local(ctk_handle* h, const float* s_dev) {
+static int rpgd_local(ctk_handle* h, const float* s_dev, const RpgdSelectArgs* fused_select = nullptr) {
   const ctk_config& c = h->cfg;
   if (c.rpgd_gradient_mode >= 2) { h->pending_s = s_dev; return CTK_OK; }  // the whole tick runs in rpgd_finish (needs u_out)
   const int iters = (h->count == 0) ? c.rpgd_first_iter_count : c.rpgd_outer_its;  // optimizer_rpgd.py:397-400
@@ -908,15 +908,15 @@ static int rpgd_local(ctk_handle* h, const float* s_dev) {
   h->launches++;
   {
     KernelTimer kt(h);
-    CU(launch_rpgd_grad(h->cost.kind, log, coef, (h->N + B - 1) / B, B, smem, h->stream, a));
+    CU(launch_rpgd_grad(h->cost.kind, log, coef, (h->N + B - 1) / B, B, smem, h->stream, a, coef ? fused_select : nullptr));
   }
   h->adam_step += iters;
   return CTK_OK;
 }
 
-static int rpgd_finish(ctk_handle* h, float* u_out_dev) {
+// K8 arguments of this tick (draws the resampling noise); the caller launches K8 -- on its own or fused into K6/K7 -- and commits
+static int rpgd_select_prepare(ctk_handle* h, float* u_out_dev, RpgdSelectArgs* out) {
   const ctk_config& c = h->cfg;
-  if (c.rpgd_gradient_mode >= 2) return gradcem_tick(h, h->pending_s, u_out_dev);
   const int grad_mode = c.rpgd_gradient_mode == 1 ? 1 : 0;
   const int resample = (!grad_mode && h->count % c.rpgd_resamp_per == 0) ? 1 : 0;  // optimizer_rpgd.py:449
   NoiseSrc ns{};
@@ -937,14 +937,46 @@ static int rpgd_finish(ctk_handle* h, float* u_out_dev) {
   a.u_nom_out = h->d_unom_log; a.u_prev = h->d_u_prev; a.u_out = u_out_dev; a.freeze_prev = c.freeze_previous_input;
   a.best_idx_out = h->d_best_idx;
   a.host = h->mirror;
+  *out = a;
+  return CTK_OK;
+}
+static void rpgd_select_commit(ctk_handle* h) {
+  h->cur ^= 1;
+  h->count++;
+}
+
+static int rpgd_finish(ctk_handle* h, float* u_out_dev) {
+  const ctk_config& c = h->cfg;
+  if (c.rpgd_gradient_mode >= 2) return gradcem_tick(h, h->pending_s, u_out_dev);
+  RpgdSelectArgs a{};
+  int rc = rpgd_select_prepare(h, u_out_dev, &a);
+  if (rc != CTK_OK) return rc;
   if (c.logging) {  // Q_logged / trajectory_ages_logged are the values BEFORE the warm-start update (:413-415)
     CU(cudaMemcpyAsync(h->d_Q_log, h->d_Q[h->cur], sizeof(float) * h->N * h->H, cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_ages_log, h->d_ages[h->cur], sizeof(float) * h->N, cudaMemcpyDeviceToDevice, h->stream));
   }
   h->launches++;
   CU(launch_rpgd_select(a, h->stream));
-  h->cur = nx;
-  h->count++;
+  rpgd_select_commit(h);
+  return CTK_OK;
+}
+
+// One RPGD tick for the host-facing / device-resident callers: a population of one block (N <= 32, C3) runs K6/K7 and K8 as ONE
+// launch; larger populations, logging and the gradient-assisted CEM modes take the two-launch path
+static int rpgd_tick(ctk_handle* h, const float* s_dev, float* u_out_dev) {
+  const ctk_config& c = h->cfg;
+  const bool fuse = c.rpgd_gradient_mode < 2 && h->N <= 32 && !c.logging && sizeof(float) * (size_t)h->H * 32 * 12 <= 220 * 1024 &&
+                    getenv("CTK_RPGD_DIRECT_ADJOINT") == nullptr && getenv("CTK_RPGD_TWO_LAUNCHES") == nullptr;
+  if (!fuse) {
+    int rc = rpgd_local(h, s_dev);
+    return rc == CTK_OK ? rpgd_finish(h, u_out_dev) : rc;
+  }
+  RpgdSelectArgs sel{};
+  int rc = rpgd_select_prepare(h, u_out_dev, &sel);
+  if (rc != CTK_OK) return rc;
+  rc = rpgd_local(h, s_dev, &sel);
+  if (rc != CTK_OK) return rc;
+  rpgd_select_commit(h);
   return CTK_OK;
 }
 
@@ -1061,8 +1093,7 @@ static int step_host(ctk_handle* h, const float* s_host, float* u_out_host, cons
     } while (rc == CTK_OK && h->cem_it != 0);
   } else {
     h->tick++;
-    rc = rpgd_local(h, nullptr);
-    if (rc == CTK_OK) rc = rpgd_finish(h, h->d_u_out);
+    rc = rpgd_tick(h, nullptr, h->d_u_out);
   }
   h->mirror = HostMirror{nullptr, 0};
   if (rc != CTK_OK) return rc;
@@ -1099,8 +1130,7 @@ extern "C" int ctk_step_device(ctk_handle* h, const float* s_dev, float* u_out_d
       rc = cem_finish(h, h->cem_cand_ptr, h->cem_cand, uo);
     } while (rc == CTK_OK && h->cem_it != 0);
   } else {
-    rc = rpgd_local(h, s_dev);
-    if (rc == CTK_OK) rc = rpgd_finish(h, uo);
+    rc = rpgd_tick(h, s_dev, uo);
   }
   return rc;
 }

@@ -109,6 +109,84 @@ __global__ void __launch_bounds__(32) rpgd_grad_kernel(const RpgdGradArgs a) {
   a.J[n] = (jsum + terminal_cost(z, a.cost)) - a.cost.shift;
 }
 
+// sample_actions (:275-296) for one new row at horizon step t: clip(z*scale+offset) on inducing points, interpolate
+__device__ __forceinline__ float rpgd_sample_point(const RpgdSelectArgs& a, uint32_t row, int i) {
+  const float z = noise1(a.noise, row, i);
+  const float y = a.dist == 0 ? __fadd_rn(__fmul_rn(z, a.s_std), a.s_mean) : __fadd_rn(__fmul_rn(z, a.s_max - a.s_min), a.s_min);
+  return fminf(fmaxf(y, a.lo), a.hi);
+}
+
+// K8 body: any block size >= the padded population (callers: rpgd_select_kernel, and rpgd_grad_coef_kernel when the whole
+// population is one block -- then the tick is ONE launch)
+__device__ __forceinline__ void rpgd_select_body(const RpgdSelectArgs& a, uint64_t* sh, int* sh_best) {
+  const int tid = threadIdx.x;
+  uint64_t key = (tid < a.N) ? make_key(a.J[tid], (uint32_t)tid) : KEY_MAX;
+  int n_sort = 32;
+  while (n_sort < a.N) n_sort <<= 1;
+  key = block_bitonic_sort(key, sh, n_sort);  // argsort (:345), stable by index; C3's 32 costs stay inside one warp's shuffles
+  if (tid < a.k) {
+    sh_best[tid] = (int)(key & 0xffffffffu);
+    a.best_idx_out[tid] = sh_best[tid];
+  }
+  __syncthreads();
+  const int best = sh_best[0];
+  for (int t = tid; t < a.H; t += blockDim.x) {
+    const float q = a.Q[(size_t)t * a.N + best];
+    a.u_nom_out[t] = q;  // :426
+    if (a.host.p != nullptr) a.host.p[16 + t] = q;
+  }
+  if (tid == 0) {
+    const float u = a.Q[best];
+    if (!a.freeze_prev) a.u_prev[0] = u;
+    if (a.u_out != nullptr) a.u_out[0] = u;
+    if (a.host.p != nullptr) { a.host.p[8] = u; a.host.p[9] = 0.0f; }
+  }
+  if (a.host.p != nullptr) {
+    __syncthreads();
+    if (tid == 0) host_publish(a.host);
+  }
+  const int nnew = a.resample ? a.N - a.k : 0;
+  for (int idx = tid; idx < a.N * a.H; idx += blockDim.x) {
+    const int t = idx / a.N, n = idx - t * a.N;
+    float q, mm, vv;
+    if (n < nnew) {
+      // fresh sample (:451-453): interpolate clipped inducing points (Interpolator.py:97-106)
+      const int seg = t / a.period, j = t - seg * a.period;
+      float w0, w1;
+      interp_weights(seg, j, a.period, a.n_ind, &w0, &w1);
+      const float y0 = rpgd_sample_point(a, (uint32_t)n, seg);
+      const float y1 = (j > 0) ? rpgd_sample_point(a, (uint32_t)n, seg + 1) : 0.0f;
+      q = fmaf(y1, w1, __fmul_rn(y0, w0));
+      mm = 0.0f;
+      vv = 0.0f;
+    } else {
+      const int src = a.resample ? sh_best[n - nnew] : n;  // gather in best order (:454) or identity
+      const int ts = min(t + a.shift_previous, a.H - 1);   // :376-379 shift, repeat the last
+      q = a.Q[(size_t)ts * a.N + src];
+      // optimizer_gradient_tf.py:142-149: the vacated last step gets a fresh uniform control instead of a repeat
+      if (a.tail_resample && t == a.H - 1) q = rpgd_sample_point(a, (uint32_t)n, 0);
+      // Adam moments: always shifted by ONE with zero fill (:462-513)
+      mm = (t + 1 < a.H) ? a.m[(size_t)(t + 1) * a.N + src] : 0.0f;
+      vv = (t + 1 < a.H) ? a.v[(size_t)(t + 1) * a.N + src] : 0.0f;
+    }
+    a.Qn[idx] = q;
+    a.mn[idx] = mm;
+    a.vn[idx] = vv;
+  }
+  for (int n = tid; n < a.N; n += blockDim.x) {
+    const float age = (n < nnew) ? 0.0f : a.ages[a.resample ? sh_best[n - nnew] : n];
+    a.agesn[n] = age + 1.0f;  // :514
+  }
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS) rpgd_select_kernel(const RpgdSelectArgs a) {
+  __shared__ uint64_t sh[TOPK_THREADS];
+  __shared__ int sh_best[TOPK_THREADS];
+  pdl_wait();
+  pdl_trigger();
+  rpgd_select_body(a, sh, sh_best);
+}
+
 // The same tick with the adjoint in COEFFICIENT form (ctk_math.cuh adjoint_coefficients / adjoint_apply): the forward pass folds
 // everything that depends on the pre-step state into 8 numbers per step, the reverse sweep is a 4-deep FMA chain per step, and
 // every constant is register-resident (volatile loads from the device copy) instead of being re-read from the parameter bank
@@ -118,7 +196,7 @@ __global__ void __launch_bounds__(32) rpgd_grad_kernel(const RpgdGradArgs a) {
 // steps t = w (mod kRpgdWarps).
 constexpr int kRpgdWarps = 8;
 template <int KIND, bool LOG>
-__global__ void __launch_bounds__(32 * kRpgdWarps) rpgd_grad_coef_kernel(const RpgdGradArgs a) {
+__global__ void __launch_bounds__(32 * kRpgdWarps) rpgd_grad_coef_kernel(const RpgdGradArgs a, const RpgdSelectArgs sel, const int fuse_select) {
   extern __shared__ float smem[];
   constexpr int B = 32, W = kRpgdWarps;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, H = a.H;
@@ -225,97 +303,31 @@ __global__ void __launch_bounds__(32 * kRpgdWarps) rpgd_grad_coef_kernel(const R
       if (moments && a.iters > 0) { a.m[(size_t)t * a.N + n] = sm[t * B]; a.v[(size_t)t * a.N + n] = sv[t * B]; }
     }
   }
-  if (wid != 0 || !active) return;
-
-  // ---- cost of the updated population ----
-  State z = z0;
-  float omc = omc0, u_last = u_prev, jsum = 0.0f;
-  for (int t = 0; t < H; ++t) {
-    const float u = sq[t * B];
+  if (wid == 0 && active) {
+    // ---- cost of the updated population ----
+    State z = z0;
+    float omc = omc0, u_last = u_prev, jsum = 0.0f;
+    for (int t = 0; t < H; ++t) {
+      const float u = sq[t * B];
+      if (LOG) {
+        float* o = a.log_traj_soa + (size_t)t * 6 * a.N + n;
+        o[0] = z.th; o[a.N] = z.om; o[2 * a.N] = z.c; o[3 * a.N] = z.s; o[4 * (size_t)a.N] = z.x; o[5 * (size_t)a.N] = z.v;
+      }
+      jsum += stage_cost<KIND>(z, omc, u, u_last, cost);
+      ode_substep(z, u, fwd, omc);
+      u_last = u;
+    }
     if (LOG) {
-      float* o = a.log_traj_soa + (size_t)t * 6 * a.N + n;
+      float* o = a.log_traj_soa + (size_t)H * 6 * a.N + n;
       o[0] = z.th; o[a.N] = z.om; o[2 * a.N] = z.c; o[3 * a.N] = z.s; o[4 * (size_t)a.N] = z.x; o[5 * (size_t)a.N] = z.v;
     }
-    jsum += stage_cost<KIND>(z, omc, u, u_last, cost);
-    ode_substep(z, u, fwd, omc);
-    u_last = u;
+    a.J[n] = (jsum + terminal_cost(z, cost)) - cost.shift;
   }
-  if (LOG) {
-    float* o = a.log_traj_soa + (size_t)H * 6 * a.N + n;
-    o[0] = z.th; o[a.N] = z.om; o[2 * a.N] = z.c; o[3 * a.N] = z.s; o[4 * (size_t)a.N] = z.x; o[5 * (size_t)a.N] = z.v;
-  }
-  a.J[n] = (jsum + terminal_cost(z, cost)) - cost.shift;
-}
-
-// sample_actions (:275-296) for one new row at horizon step t: clip(z*scale+offset) on inducing points, interpolate
-__device__ __forceinline__ float rpgd_sample_point(const RpgdSelectArgs& a, uint32_t row, int i) {
-  const float z = noise1(a.noise, row, i);
-  const float y = a.dist == 0 ? __fadd_rn(__fmul_rn(z, a.s_std), a.s_mean) : __fadd_rn(__fmul_rn(z, a.s_max - a.s_min), a.s_min);
-  return fminf(fmaxf(y, a.lo), a.hi);
-}
-
-__global__ void __launch_bounds__(TOPK_THREADS) rpgd_select_kernel(const RpgdSelectArgs a) {
-  __shared__ uint64_t sh[TOPK_THREADS];
-  __shared__ int sh_best[TOPK_THREADS];
-  const int tid = threadIdx.x;
-  pdl_wait();
-  pdl_trigger();
-  uint64_t key = (tid < a.N) ? make_key(a.J[tid], (uint32_t)tid) : KEY_MAX;
-  int n_sort = 32;
-  while (n_sort < a.N) n_sort <<= 1;
-  key = block_bitonic_sort(key, sh, n_sort);  // argsort (:345), stable by index; C3's 32 costs stay inside one warp's shuffles
-  if (tid < a.k) {
-    sh_best[tid] = (int)(key & 0xffffffffu);
-    a.best_idx_out[tid] = sh_best[tid];
-  }
-  __syncthreads();
-  const int best = sh_best[0];
-  for (int t = tid; t < a.H; t += blockDim.x) {
-    const float q = a.Q[(size_t)t * a.N + best];
-    a.u_nom_out[t] = q;  // :426
-    if (a.host.p != nullptr) a.host.p[16 + t] = q;
-  }
-  if (tid == 0) {
-    const float u = a.Q[best];
-    if (!a.freeze_prev) a.u_prev[0] = u;
-    if (a.u_out != nullptr) a.u_out[0] = u;
-    if (a.host.p != nullptr) { a.host.p[8] = u; a.host.p[9] = 0.0f; }
-  }
-  if (a.host.p != nullptr) {
-    __syncthreads();
-    if (tid == 0) host_publish(a.host);
-  }
-  const int nnew = a.resample ? a.N - a.k : 0;
-  for (int idx = tid; idx < a.N * a.H; idx += blockDim.x) {
-    const int t = idx / a.N, n = idx - t * a.N;
-    float q, mm, vv;
-    if (n < nnew) {
-      // fresh sample (:451-453): interpolate clipped inducing points (Interpolator.py:97-106)
-      const int seg = t / a.period, j = t - seg * a.period;
-      float w0, w1;
-      interp_weights(seg, j, a.period, a.n_ind, &w0, &w1);
-      const float y0 = rpgd_sample_point(a, (uint32_t)n, seg);
-      const float y1 = (j > 0) ? rpgd_sample_point(a, (uint32_t)n, seg + 1) : 0.0f;
-      q = fmaf(y1, w1, __fmul_rn(y0, w0));
-      mm = 0.0f;
-      vv = 0.0f;
-    } else {
-      const int src = a.resample ? sh_best[n - nnew] : n;  // gather in best order (:454) or identity
-      const int ts = min(t + a.shift_previous, a.H - 1);   // :376-379 shift, repeat the last
-      q = a.Q[(size_t)ts * a.N + src];
-      // optimizer_gradient_tf.py:142-149: the vacated last step gets a fresh uniform control instead of a repeat
-      if (a.tail_resample && t == a.H - 1) q = rpgd_sample_point(a, (uint32_t)n, 0);
-      // Adam moments: always shifted by ONE with zero fill (:462-513)
-      mm = (t + 1 < a.H) ? a.m[(size_t)(t + 1) * a.N + src] : 0.0f;
-      vv = (t + 1 < a.H) ? a.v[(size_t)(t + 1) * a.N + src] : 0.0f;
-    }
-    a.Qn[idx] = q;
-    a.mn[idx] = mm;
-    a.vn[idx] = vv;
-  }
-  for (int n = tid; n < a.N; n += blockDim.x) {
-    const float age = (n < nnew) ? 0.0f : a.ages[a.resample ? sh_best[n - nnew] : n];
-    a.agesn[n] = age + 1.0f;  // :514
+  if (fuse_select) {  // the population is this one block: argsort / shift / resample (K8) without a second launch
+    __shared__ uint64_t sh_sel[32 * kRpgdWarps];
+    __shared__ int sh_best[32 * kRpgdWarps];
+    __syncthreads();  // J, Q, m, v of every trajectory are written (same block: visible after the barrier)
+    rpgd_select_body(sel, sh_sel, sh_best);
   }
 }
 

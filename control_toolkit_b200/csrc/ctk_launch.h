@@ -48,7 +48,9 @@ cudaError_t launch_topk_level(const float* cost, const uint64_t* keys_in, int n,
 cudaError_t launch_cem_refit(const CemRefitArgs& a, cudaStream_t st);
 
 // coef: coefficient-form adjoint (rpgd_grad_coef_kernel, tape of 12 floats per step) instead of the direct form (8 floats per step)
-cudaError_t launch_rpgd_grad(int kind, bool log, bool coef, int nblocks, int block, size_t smem, cudaStream_t st, const RpgdGradArgs& a);
+// fused_select != null (coef only, one block): the select / resample step (K8) runs at the end of the same launch
+cudaError_t launch_rpgd_grad(int kind, bool log, bool coef, int nblocks, int block, size_t smem, cudaStream_t st, const RpgdGradArgs& a,
+                             const RpgdSelectArgs* fused_select = nullptr);
 cudaError_t launch_rpgd_select(const RpgdSelectArgs& a, cudaStream_t st);
 cudaError_t launch_rpgd_init(const RpgdSelectArgs& a, cudaStream_t st);
 cudaError_t launch_gradcem_sample(const GradCemSampleArgs& a, cudaStream_t st);

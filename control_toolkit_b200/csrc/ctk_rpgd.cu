@@ -4,18 +4,27 @@
 
 namespace ctk {
 
-cudaError_t launch_rpgd_grad(int kind, bool log, bool coef, int nblocks, int block, size_t smem, cudaStream_t st, const RpgdGradArgs& a) {
-  void (*k)(const RpgdGradArgs) = nullptr;
+cudaError_t launch_rpgd_grad(int kind, bool log, bool coef, int nblocks, int block, size_t smem, cudaStream_t st, const RpgdGradArgs& a,
+                             const RpgdSelectArgs* fused_select) {
   if (coef) {
+    void (*k)(const RpgdGradArgs, const RpgdSelectArgs, const int) = nullptr;
     if (kind == 0) k = log ? rpgd_grad_coef_kernel<0, true> : rpgd_grad_coef_kernel<0, false>;
     else k = log ? rpgd_grad_coef_kernel<1, true> : rpgd_grad_coef_kernel<1, false>;
-  } else if (kind == 0) k = log ? rpgd_grad_kernel<0, true> : rpgd_grad_kernel<0, false>;
+    if (smem > 32 * 1024) {  // 6 KB of static shared memory (fused select) come on top
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    const RpgdSelectArgs none{};
+    return launch_pdl(k, dim3(nblocks), dim3(32 * kRpgdWarps), smem, st, a, fused_select ? *fused_select : none, fused_select ? 1 : 0);
+  }
+  void (*k)(const RpgdGradArgs) = nullptr;
+  if (kind == 0) k = log ? rpgd_grad_kernel<0, true> : rpgd_grad_kernel<0, false>;
   else k = log ? rpgd_grad_kernel<1, true> : rpgd_grad_kernel<1, false>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  return launch_pdl(k, dim3(nblocks), dim3(coef ? 32 * kRpgdWarps : block), smem, st, a);
+  return launch_pdl(k, dim3(nblocks), dim3(block), smem, st, a);
 }
 cudaError_t launch_rpgd_select(const RpgdSelectArgs& a, cudaStream_t st) {
   return launch_pdl(rpgd_select_kernel, dim3(1), dim3(TOPK_THREADS), 0, st, a);
