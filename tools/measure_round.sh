@@ -19,6 +19,6 @@ python tools/step_breakdown.py 300 > $O/step_breakdown.txt 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_r01c.csv python bench.py --steps 3 --warmup 3 > $O/ncu_launch.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_cem_c2_r01c.csv python bench.py --workload cem_ode_c2 --steps 3 --warmup 3 > $O/ncu_launch_cem.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_rpgd_c3_r01c.csv python bench.py --workload rpgd_ode_c3 --steps 3 --warmup 3 > $O/ncu_launch_rpgd.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:cem_ode_kernel -s 6 -c 1 -o $O/prof_cem_ode_r01 -f python bench.py --workload cem_ode_c2 --steps 3 --warmup 3 > $O/ncu_cem.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:cem_tick_kernel -s 4 -c 1 -o $O/prof_cem_tick_r01 -f python bench.py --workload cem_ode_c2 --steps 3 --warmup 3 > $O/ncu_cem.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rpgd_grad -s 4 -c 1 -o $O/prof_rpgd_coef_r01 -f python bench.py --workload rpgd_ode_c3 --steps 3 --warmup 3 > $O/ncu_rpgd.log 2>&1
 echo done
