@@ -35,10 +35,12 @@ def test_registry_fails_loudly_for_unregistered_names():
 def test_optimizer_discovery_by_name():
     """reference others/globals_and_utils.py:103-133: 'cem-tf' -> file optimizer_cem_tf.py, class optimizer_cem_tf."""
     import control_toolkit_b200 as ctk
-    for key, cls in (("mppi", "optimizer_mppi"), ("cem-tf", "optimizer_cem_tf"), ("rpgd", "optimizer_rpgd")):
+    for key, cls in (("mppi", "optimizer_mppi"), ("cem-tf", "optimizer_cem_tf"), ("rpgd", "optimizer_rpgd"),
+                     ("random-action-tf", "optimizer_random_action_tf"), ("gradient-tf", "optimizer_gradient_tf"),
+                     ("cem-naive-grad-tf", "optimizer_cem_naive_grad_tf"), ("cem-grad-bharadhwaj-tf", "optimizer_cem_grad_bharadhwaj_tf")):
         C = ctk.import_optimizer_by_name(key)
         assert C.__name__ == cls
-        assert C.__mro__[1].__name__ == "template_optimizer"
+        assert "template_optimizer" in [b.__name__ for b in C.__mro__[1:]]
     with pytest.raises(ValueError, match="not found"):
         ctk.import_optimizer_by_name("rpgd-tf")  # the stale template key (SURVEY.md section 2 row 11)
 
@@ -63,6 +65,28 @@ def test_optimizer_constructor_contract():
     assert r.opt_keep_k == 8 and r.first_iter_count == 7 and r.optimizer_name == "rpgd"
     with pytest.raises(ValueError, match="dt and predictor_specification"):
         r.configure(num_states=6, num_control_inputs=1)
+    # the sibling optimizers: the reference's ctor kwargs (template blocks of config_optimizers.yml:23-61) and warm-up rules
+    G = ctk.import_optimizer_by_name("gradient-tf")
+    g = G(predictor=ctk.PredictorWrapper(), cost_function=ctk.CostFunctionWrapper(), control_limits=lim, computation_library=None, seed=1,
+          mpc_horizon=35, gradient_steps=5, num_rollouts=40, initial_action_stdev=0.5, learning_rate=0.05, adam_beta_1=0.9,
+          adam_beta_2=0.999, adam_epsilon=1.0e-07, gradmax_clip=5, rtol=1.0e-3, warmup=True, warmup_iterations=250,
+          optimizer_logging=False, calculate_optimal_trajectory=False, mpc_timestep=0.02)
+    assert g.first_iter_count == 250 and g.optimizer_name == "gradient-tf"  # optimizer_gradient_tf.py:66-68
+    B = ctk.import_optimizer_by_name("cem-grad-bharadhwaj-tf")
+    b = B(predictor=ctk.PredictorWrapper(), cost_function=ctk.CostFunctionWrapper(), control_limits=lim, computation_library=None, seed=1,
+          mpc_horizon=50, learning_rate=0.05, adam_beta_1=0.9, adam_beta_2=0.999, adam_epsilon=1.0e-08, num_rollouts=32, cem_best_k=8,
+          cem_outer_it=2, cem_initial_action_stdev=2, cem_stdev_min=1.e-6, gradmax_clip=5, warmup=True, warmup_iterations=9,
+          optimizer_logging=False, calculate_optimal_trajectory=False, mpc_timestep=0.02)
+    assert b._iterations() == 9 and b.optimizer_name == "cem-grad-bharadhwaj-tf"  # optimizer_cem_grad_bharadhwaj_tf.py:162
+    assert [blk[1][0] for blk in b._noise_blocks(2)] == [8, 24, 24]  # :159 k "elites", then N - k fresh samples per iteration (:95)
+    Nv = ctk.import_optimizer_by_name("cem-naive-grad-tf")
+    nv = Nv(predictor=ctk.PredictorWrapper(), cost_function=ctk.CostFunctionWrapper(), control_limits=lim, computation_library=None, seed=1,
+            mpc_horizon=35, cem_outer_it=1, num_rollouts=200, cem_stdev_min=0.1, cem_initial_action_stdev=0.5, cem_best_k=40,
+            learning_rate=0.1, gradmax_clip=10, optimizer_logging=False, calculate_optimal_trajectory=False, mpc_timestep=0.02)
+    assert nv._iterations() == 1 and nv.optimizer_name == "cem-naive-grad-tf"
+    for o2 in (g, b, nv):
+        with pytest.raises(RuntimeError, match="configure"):
+            o2.step(np.zeros(6))
 
 
 def test_mppi_host_constants_follow_reference_evaluation_order():
