@@ -177,7 +177,8 @@ class template_optimizer:
             self._cost_live = live
         vp = getattr(self.cost_function, "variable_parameters", None)
         L_live = getattr(vp, "L", None) if vp is not None else None
-        if L_live is not None and self._ode_spec is not None and float(L_live) != float(self._ode_spec.L):
+        # (the reference's server initialises L to 0.0 until a client sends the real value, controller_server.py:19-26: ignored)
+        if L_live is not None and float(L_live) > 0.0 and self._ode_spec is not None and float(L_live) != float(self._ode_spec.L):
             from dataclasses import replace
             self._ode_spec = replace(self._ode_spec, L=float(L_live))
             o = self._ode_spec.to_c(self._dt)
