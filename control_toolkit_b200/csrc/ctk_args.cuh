@@ -245,6 +245,11 @@ struct RpgdGradArgs {
   CostC cost;
   float* J;              // [N] cost of the final (get_action) rollout
   float* log_traj_soa;   // [(H+1)][6][N] or null
+  unsigned long long* trace;  // diagnostics (ctk_debug_trace): globaltimer stamps of block 0's phases, or null
+  // Adam bias corrections of the first kAdamHostIters gradient steps of this launch, evaluated on the host in float64 and rounded
+  // once (1 - beta1^t, 1 - beta2^t, lr sqrt(1 - beta2^t) / (1 - beta1^t)); later steps (warm-up ticks) use the in-kernel pow
+  int n_host_adam;
+  float bc1_h[8], bc2_h[8], alpha_h[8];
 };
 
 struct RpgdSelectArgs {

@@ -831,6 +831,17 @@ static int cem_finish(ctk_handle* h, const uint64_t* cand, int cnt, float* u_out
   return CTK_OK;
 }
 
+// Adam bias corrections of the first gradient steps of a launch (RpgdGradArgs::bc1_h ...), float64 on the host, rounded once
+static void fill_host_adam(RpgdGradArgs& a) {
+  a.n_host_adam = a.iters < 8 ? a.iters : 8;
+  for (int i = 0; i < a.n_host_adam; ++i) {
+    const double step = (double)(a.adam_step0 + i + 1);
+    const double bc1d = 1.0 - std::pow(a.beta1, step), bc2d = 1.0 - std::pow(a.beta2, step);
+    a.bc1_h[i] = (float)bc1d; a.bc2_h[i] = (float)bc2d;
+    a.alpha_h[i] = (float)((double)a.lr * std::sqrt(bc2d) / bc1d);
+  }
+}
+
 // Gradient-assisted CEM tick (rpgd_gradient_mode 2: optimizer_cem_naive_grad_tf.py:90-114, 3: optimizer_cem_grad_bharadhwaj_tf.py:151-178)
 static int gradcem_tick(ctk_handle* h, const float* s_dev, float* u_out_dev) {
   const ctk_config& c = h->cfg;
@@ -861,6 +872,7 @@ static int gradcem_tick(ctk_handle* h, const float* s_dev, float* u_out_dev) {
     a.lo = c.action_low; a.hi = c.action_high; a.lr = c.rpgd_learning_rate; a.gradmax_clip = c.rpgd_gradmax_clip;
     a.beta1 = c.rpgd_beta_1; a.beta2 = c.rpgd_beta_2; a.eps = c.rpgd_epsilon; a.adam_step0 = h->adam_step;
     a.adam_form = carry ? 0 : 2;
+    fill_host_adam(a);
     a.kc = h->d_kc; a.ode = h->ode; a.fwd = h->fwd; a.cost = h->cost; a.J = h->d_J; a.log_traj_soa = h->d_log_traj_soa;
     const int B = 32;
     const bool coef = sizeof(float) * (size_t)H * B * 12 <= 227 * 1024;  // coefficient tape: q, g, m, v and 8 coefficients per step
@@ -900,6 +912,8 @@ static int rpgd_local(ctk_handle* h, const float* s_dev, const RpgdSelectArgs* f
   a.lo = c.action_low; a.hi = c.action_high; a.lr = c.rpgd_learning_rate; a.gradmax_clip = c.rpgd_gradmax_clip;
   a.beta1 = c.rpgd_beta_1; a.beta2 = c.rpgd_beta_2; a.eps = c.rpgd_epsilon; a.adam_step0 = h->adam_step; a.adam_form = c.rpgd_adam_form;
   a.kc = h->d_kc; a.ode = h->ode; a.fwd = h->fwd; a.cost = h->cost; a.J = h->d_J; a.log_traj_soa = h->d_log_traj_soa;
+  a.trace = h->d_trace;
+  fill_host_adam(a);
   const int B = 32;
   const bool coef = sizeof(float) * (size_t)h->H * B * 12 <= 227 * 1024 && getenv("CTK_RPGD_DIRECT_ADJOINT") == nullptr;
   const size_t smem = sizeof(float) * (size_t)h->H * B * (coef ? 12 : 8);

@@ -146,6 +146,7 @@ __device__ __forceinline__ void rpgd_select_body(const RpgdSelectArgs& a, uint64
     if (tid == 0) host_publish(a.host);
   }
   const int nnew = a.resample ? a.N - a.k : 0;
+#pragma unroll 4
   for (int idx = tid; idx < a.N * a.H; idx += blockDim.x) {
     const int t = idx / a.N, n = idx - t * a.N;
     float q, mm, vv;
@@ -191,9 +192,10 @@ __global__ void __launch_bounds__(TOPK_THREADS) rpgd_select_kernel(const RpgdSel
 // everything that depends on the pre-step state into 8 numbers per step, the reverse sweep is a 4-deep FMA chain per step, and
 // every constant is register-resident (volatile loads from the device copy) instead of being re-read from the parameter bank
 // inside the serial loops.  Block = 32 trajectories x kRpgdWarps warps: warp 0 walks the serial chains (5 x H dependent steps
-// per tick -- chain depth IS the run time), ALL warps share the phases that are parallel over the horizon (staging Q / Adam
-// moments from global memory, the Adam update with its IEEE divisions and square roots, the write-back), warp w taking the
-// steps t = w (mod kRpgdWarps).
+// per tick -- chain depth IS the run time: the forward pass is the bare state recursion, the reverse sweep the 4-deep FMA
+// chain), ALL warps share the phases that are parallel over the horizon (staging Q / Adam moments from global memory, the
+// adjoint coefficients from the taped states, the Adam update with its IEEE divisions and square roots, the write-back),
+// warp w taking the steps t = w (mod kRpgdWarps).
 constexpr int kRpgdWarps = 8;
 template <int KIND, bool LOG>
 __global__ void __launch_bounds__(32 * kRpgdWarps) rpgd_grad_coef_kernel(const RpgdGradArgs a, const RpgdSelectArgs sel, const int fuse_select) {
@@ -223,6 +225,12 @@ __global__ void __launch_bounds__(32 * kRpgdWarps) rpgd_grad_coef_kernel(const R
   const float omc0 = 1.0f - cosf(z0.th);
   const float lo = a.lo, hi = a.hi, clipc = a.gradmax_clip, lr = a.lr;
 
+  int tslot = 0;
+  auto trace = [&]() {  // optional phase timeline (tools/rpgd_trace.py)
+    if (a.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && tslot < 32) a.trace[tslot] = globaltimer_ns();
+    ++tslot;
+  };
+  trace();
   const bool moments = a.adam_form != 2;
 #pragma unroll 4
   for (int t = wid; t < H; t += W) {
@@ -230,20 +238,35 @@ __global__ void __launch_bounds__(32 * kRpgdWarps) rpgd_grad_coef_kernel(const R
     if (moments) { sm[t * B] = a.m[(size_t)t * a.N + n]; sv[t * B] = a.v[(size_t)t * a.N + n]; }
   }
   __syncthreads();
+  trace();
 
   for (int it = 0; it < a.iters; ++it) {
     if (wid == 0) {
-      // ---- forward: the next state (serial chain) and, off the chain, the adjoint coefficients of this step ----
+      // ---- forward (warp 0): the bare state chain, pre-step states to the tape ----
       State z = z0;
 #pragma unroll 2
       for (int t = 0; t < H; ++t) {
-        const float q = sq[t * B];
-        const AdjCoef c = adjoint_coefficients<KIND>(z, q, p, cost, w);
         float* o = tp + (size_t)t * 8 * B;
-        o[0] = c.E1; o[B] = c.E2; o[2 * B] = c.C1; o[3 * B] = c.C2; o[4 * B] = c.D1; o[5 * B] = c.cx; o[6 * B] = c.cth; o[7 * B] = c.com;
+        o[0] = z.th; o[B] = z.om; o[2 * B] = z.c; o[3 * B] = z.s; o[4 * B] = z.x; o[5 * B] = z.v;
         float omc_unused;
-        ode_substep(z, q, fwd, omc_unused);
+        ode_substep(z, sq[t * B], fwd, omc_unused);
       }
+    }
+    __syncthreads();
+    trace();
+    // ---- adjoint coefficients (all warps, step t by warp t mod W): each (step, trajectory) slot of the tape is read and then
+    //      overwritten by the same thread, so the 8 coefficients replace the 6 state values in place ----
+#pragma unroll 2
+    for (int t = wid; t < H; t += W) {
+      float* o = tp + (size_t)t * 8 * B;
+      State z;
+      z.th = o[0]; z.om = o[B]; z.c = o[2 * B]; z.s = o[3 * B]; z.x = o[4 * B]; z.v = o[5 * B];
+      const AdjCoef c = adjoint_coefficients<KIND>(z, sq[t * B], p, cost, w);
+      o[0] = c.E1; o[B] = c.E2; o[2 * B] = c.C1; o[3 * B] = c.C2; o[4 * B] = c.D1; o[5 * B] = c.cx; o[6 * B] = c.cth; o[7 * B] = c.com;
+    }
+    __syncthreads();
+    trace();
+    if (wid == 0) {
       // ---- reverse sweep ----
       Adj lam = {0.f, 0.f, 0.f, 0.f};
       float nrm2 = 0.0f;
@@ -264,14 +287,20 @@ __global__ void __launch_bounds__(32 * kRpgdWarps) rpgd_grad_coef_kernel(const R
       sh_den[lane] = fmaxf(sqrtf(nrm2), clipc);  // clip_by_norm over the trajectory
     }
     __syncthreads();
+    trace();
     // ---- optimizer update, box clip: parallel over the horizon ----
     const float den = sh_den[lane];
-    const double step = (double)(a.adam_step0 + it + 1);
-    const double bc1d = 1.0 - pow(a.beta1, step), bc2d = 1.0 - pow(a.beta2, step);
     const float b1 = (float)a.beta1, b2 = (float)a.beta2;
-    const float omb1 = (float)(1.0 - a.beta1), omb2 = (float)(1.0 - a.beta2);
-    const float bc1 = (float)bc1d, bc2 = (float)bc2d, eps = (float)a.eps;
-    const float alpha = (float)((double)a.lr * sqrt(bc2d) / bc1d);
+    const float omb1 = (float)(1.0 - a.beta1), omb2 = (float)(1.0 - a.beta2), eps = (float)a.eps;
+    float bc1, bc2, alpha;
+    if (it < a.n_host_adam) {  // the double-precision pow / sqrt per thread cost ~1.5 us per gradient step (tools/rpgd_trace.py)
+      bc1 = a.bc1_h[it]; bc2 = a.bc2_h[it]; alpha = a.alpha_h[it];
+    } else {
+      const double step = (double)(a.adam_step0 + it + 1);
+      const double bc1d = 1.0 - pow(a.beta1, step), bc2d = 1.0 - pow(a.beta2, step);
+      bc1 = (float)bc1d; bc2 = (float)bc2d;
+      alpha = (float)((double)a.lr * sqrt(bc2d) / bc1d);
+    }
 #pragma unroll 2
     for (int t = wid; t < H; t += W) {
       const float g = sg[t * B] * clipc / den;
@@ -295,6 +324,7 @@ __global__ void __launch_bounds__(32 * kRpgdWarps) rpgd_grad_coef_kernel(const R
       sq[t * B] = fminf(fmaxf(q, lo), hi);
     }
     __syncthreads();
+    trace();
   }
   if (active) {
 #pragma unroll 4
@@ -303,6 +333,7 @@ __global__ void __launch_bounds__(32 * kRpgdWarps) rpgd_grad_coef_kernel(const R
       if (moments && a.iters > 0) { a.m[(size_t)t * a.N + n] = sm[t * B]; a.v[(size_t)t * a.N + n] = sv[t * B]; }
     }
   }
+  trace();
   if (wid == 0 && active) {
     // ---- cost of the updated population ----
     State z = z0;
@@ -323,12 +354,14 @@ __global__ void __launch_bounds__(32 * kRpgdWarps) rpgd_grad_coef_kernel(const R
     }
     a.J[n] = (jsum + terminal_cost(z, cost)) - cost.shift;
   }
+  trace();
   if (fuse_select) {  // the population is this one block: argsort / shift / resample (K8) without a second launch
     __shared__ uint64_t sh_sel[32 * kRpgdWarps];
     __shared__ int sh_best[32 * kRpgdWarps];
     __syncthreads();  // J, Q, m, v of every trajectory are written (same block: visible after the barrier)
     rpgd_select_body(sel, sh_sel, sh_best);
   }
+  trace();
 }
 
 // initial population (optimizer_reset :540): all N rows sampled; Adam state zeroed
