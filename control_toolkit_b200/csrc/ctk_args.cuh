@@ -30,9 +30,9 @@ struct S0 {
 };
 
 // Result mirror in MAPPED pinned host memory (device view).  The kernel that finishes a tick stores u, the status word and
-// (optionally) one [H] state array there, then a system-scope fence and the launch's sequence number: the host caller
-// polls that word instead of enqueueing device->host copies and synchronising the stream.
-// Layout (floats): [8] u  [9] status  [10] sequence flag (uint32 bits)  [16 .. 16+H) state array.
+// (optionally) one [H] state array there as tagged 8-byte slots (value | launch sequence number, ctk_device.cuh host_put): the
+// host caller polls the tags instead of enqueueing device->host copies and synchronising the stream.
+// Layout (uint64 slots): [4] u  [5] status  [8 .. 8+H) state array;  floats [0..6) carry the state in the other direction.
 struct HostMirror {
   float* p;          // null: no mirror (device-resident callers)
   unsigned int seq;  // never 0

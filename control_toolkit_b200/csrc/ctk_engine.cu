@@ -260,8 +260,8 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
   A(dalloc(&h->d_J, (size_t)N), "J");
   A(cudaMalloc((void**)&h->d_kc, sizeof(DevConsts)), "consts");
   A(dalloc(&h->d_kx, 4), "kx");
-  A(cudaHostAlloc((void**)&h->h_pin, (32 + (size_t)H) * sizeof(float), cudaHostAllocMapped), "pinned");
-  if (h->h_pin) { memset(h->h_pin, 0, (32 + (size_t)H) * sizeof(float)); A(cudaHostGetDevicePointer((void**)&h->d_pin, h->h_pin, 0), "pinned (device view)"); }
+  A(cudaHostAlloc((void**)&h->h_pin, (32 + 2 * (size_t)H) * sizeof(float), cudaHostAllocMapped), "pinned");
+  if (h->h_pin) { memset(h->h_pin, 0, (32 + 2 * (size_t)H) * sizeof(float)); A(cudaHostGetDevicePointer((void**)&h->d_pin, h->h_pin, 0), "pinned (device view)"); }
   if (cfg->logging) {
     A(dalloc(&h->d_log_traj_soa, (size_t)(H + 1) * 6 * N), "log_traj");
     A(dalloc(&h->d_log_Q_soa, (size_t)H * N), "log_Q");
@@ -1053,28 +1053,33 @@ extern "C" int ctk_step_state(ctk_handle* h, const float* s_host, float* u_out_h
   REQ(!tm && n == cnt && cnt <= (size_t)h->H, "ctk_step_state reads the [H] state arrays only");
   return step_host(h, s_host, u_out_host, p, state_out_host, n);
 }
-// Wait until the kernel that finishes the tick has published sequence number `seq` in the mapped result mirror.  Polling a
-// cache line of pinned host memory replaces cudaStreamSynchronize + the device->host copies (measured: ~15 us per step).
-static int wait_host_mirror(ctk_handle* h, unsigned int seq) {
-  volatile unsigned int* flag = reinterpret_cast<volatile unsigned int*>(h->h_pin + 10);
+// Wait until the kernel that finishes the tick has delivered the tagged slots [first, first + count) of the mapped result
+// mirror (value | sequence number, one 8-byte store each: host_put in ctk_device.cuh).  Polling pinned host memory replaces
+// cudaStreamSynchronize + the device->host copies (measured: ~15 us per step).
+static int wait_host_slots(ctk_handle* h, unsigned int seq, int first, int count, float* out) {
+  volatile unsigned long long* slots = reinterpret_cast<volatile unsigned long long*>(h->h_pin);
   const auto t0 = std::chrono::steady_clock::now();
   unsigned int spins = 0;
-  while (*flag != seq) {
+  for (int i = 0; i < count; ++i) {
+    unsigned long long v;
+    while ((unsigned int)((v = slots[first + i]) >> 32) != seq) {
 #if defined(__x86_64__) || defined(__i386__)
-    __builtin_ia32_pause();
+      __builtin_ia32_pause();
 #endif
-    if ((++spins & 0x3fffu) != 0) continue;
-    const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (el < 0.05) continue;
-    const cudaError_t e = cudaStreamQuery(h->stream);  // a faulted or finished stream will never publish
-    if (e == cudaSuccess) {
-      if (*flag == seq) break;
-      return fail(CTK_ECUDA, "tick kernels finished without publishing their result to the host mirror");
+      if ((++spins & 0x3fffu) != 0) continue;
+      const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (el < 0.05) continue;
+      const cudaError_t e = cudaStreamQuery(h->stream);  // a faulted or finished stream will never publish
+      if (e == cudaSuccess) {
+        if ((unsigned int)(slots[first + i] >> 32) == seq) continue;
+        return fail(CTK_ECUDA, "tick kernels finished without publishing their result to the host mirror");
+      }
+      if (e != cudaErrorNotReady) return fail(CTK_ECUDA, std::string("tick failed on the device: ") + cudaGetErrorString(e));
+      if (el > 60.0) return fail(CTK_ECUDA, "tick did not finish within 60 s");
     }
-    if (e != cudaErrorNotReady) return fail(CTK_ECUDA, std::string("tick failed on the device: ") + cudaGetErrorString(e));
-    if (el > 60.0) return fail(CTK_ECUDA, "tick did not finish within 60 s");
+    const unsigned int bits = (unsigned int)(v & 0xffffffffull);
+    memcpy(out + i, &bits, sizeof(float));
   }
-  std::atomic_thread_fence(std::memory_order_acquire);
   return CTK_OK;
 }
 
@@ -1111,15 +1116,20 @@ static int step_host(ctk_handle* h, const float* s_host, float* u_out_host, cons
   }
   h->mirror = HostMirror{nullptr, 0};
   if (rc != CTK_OK) return rc;
-  if (state_dev && !state_in_mirror) {
-    CU(cudaMemcpyAsync(h->h_pin + 16, state_dev, n_state * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-  }
-  rc = wait_host_mirror(h, h->hseq);
+  float us[2];  // u, status
+  rc = wait_host_slots(h, h->hseq, 4, 2, us);
   if (rc != CTK_OK) return rc;
-  u_out_host[0] = h->h_pin[8];
-  if (state_dev) memcpy(state_out_host, h->h_pin + 16, n_state * sizeof(float));
-  if (h->h_pin[9] != 0.0f) return fail(CTK_ECUDA, "cross-GPU exchange timed out: a peer shard did not deliver its record within 2 s");
+  u_out_host[0] = us[0];
+  if (state_dev) {
+    if (state_in_mirror) {
+      rc = wait_host_slots(h, h->hseq, 8, (int)n_state, state_out_host);
+      if (rc != CTK_OK) return rc;
+    } else {
+      CU(cudaMemcpyAsync(state_out_host, state_dev, n_state * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+    }
+  }
+  if (us[1] != 0.0f) return fail(CTK_ECUDA, "cross-GPU exchange timed out: a peer shard did not deliver its record within 2 s");
   return CTK_OK;
 }
 

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) cem_refit_kernel(const CemRefitA
       } else {
         if (!a.freeze_prev) a.u_prev[0] = first_q;
         if (a.u_out != nullptr) a.u_out[0] = first_q;
-        if (a.host.p != nullptr) { a.host.p[8] = first_q; a.host.p[9] = 0.0f; host_publish(a.host); }
+        if (a.host.p != nullptr) { host_put(a.host, 5, 0.0f); host_put(a.host, 4, first_q); }
       }
       if (t == a.H - 1) {
         a.mu[t] = (a.lo + a.hi) * 0.5f;
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(kCemTickThreads) cem_tick_kernel(const CemTick
           const float u = status ? __int_as_float(0x7fc00000) : first_q;
           if (!a.freeze_prev) a.u_prev[0] = u;
           if (a.u_out != nullptr) a.u_out[0] = u;
-          if (a.host.p != nullptr) { a.host.p[8] = u; a.host.p[9] = (float)status; host_publish(a.host); }
+          if (a.host.p != nullptr) { host_put(a.host, 5, (float)status); host_put(a.host, 4, u); }
         }
         if (tid == H - 1) {
           a.mu[tid] = (k.lo + k.hi) * 0.5f;

@@ -125,16 +125,12 @@ __device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float*
     const float b = (fmaf(bz1, w1, bz0 * w0) * stdev) / a;
     const float un = fminf(fmaxf(sh_unom[t] + b, lo), hi);
     f.u_nom[t] = un;
-    if (f.host.p != nullptr) f.host.p[16 + t] = un;
+    if (f.host.p != nullptr) host_put(f.host, 8 + t, un);
     if (t == 0) {
       if (!f.freeze_prev) f.u_prev[0] = un;
       if (f.u_out != nullptr) { f.u_out[0] = status ? __int_as_float(0x7fc00000) : un; f.u_out[1] = (float)status; }
-      if (f.host.p != nullptr) { f.host.p[8] = status ? __int_as_float(0x7fc00000) : un; f.host.p[9] = (float)status; }
+      if (f.host.p != nullptr) { host_put(f.host, 5, (float)status); host_put(f.host, 4, status ? __int_as_float(0x7fc00000) : un); }
     }
-  }
-  if (f.host.p != nullptr) {  // block 0 only gets here; uniform
-    __syncthreads();
-    if (tid == 0) host_publish(f.host);
   }
 }
 

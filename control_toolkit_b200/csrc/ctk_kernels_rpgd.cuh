@@ -133,17 +133,13 @@ __device__ __forceinline__ void rpgd_select_body(const RpgdSelectArgs& a, uint64
   for (int t = tid; t < a.H; t += blockDim.x) {
     const float q = a.Q[(size_t)t * a.N + best];
     a.u_nom_out[t] = q;  // :426
-    if (a.host.p != nullptr) a.host.p[16 + t] = q;
+    if (a.host.p != nullptr) host_put(a.host, 8 + t, q);
   }
   if (tid == 0) {
     const float u = a.Q[best];
     if (!a.freeze_prev) a.u_prev[0] = u;
     if (a.u_out != nullptr) a.u_out[0] = u;
-    if (a.host.p != nullptr) { a.host.p[8] = u; a.host.p[9] = 0.0f; }
-  }
-  if (a.host.p != nullptr) {
-    __syncthreads();
-    if (tid == 0) host_publish(a.host);
+    if (a.host.p != nullptr) { host_put(a.host, 5, 0.0f); host_put(a.host, 4, u); }
   }
   const int nnew = a.resample ? a.N - a.k : 0;
 #pragma unroll 4
@@ -436,7 +432,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) gradcem_refit_kernel(const GradC
         const float u = a.u_from_mean ? new_mu : row[sh_best[0]];
         if (!a.freeze_prev) a.u_prev[0] = u;
         if (a.u_out != nullptr) a.u_out[0] = u;
-        if (a.host.p != nullptr) { a.host.p[8] = u; a.host.p[9] = 0.0f; host_publish(a.host); }
+        if (a.host.p != nullptr) { host_put(a.host, 5, 0.0f); host_put(a.host, 4, u); }
       }
     }
   }
