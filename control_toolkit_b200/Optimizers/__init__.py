@@ -199,8 +199,7 @@ class template_optimizer:
         if s32.size != 6:
             raise ValueError(f"state must have {6} entries, got {s32.size}")
         if self.shard is not None and self.shard.world_size > 1:
-            self._state_buf = None
-            return self.shard.run_tick(self, lib, s32)
+            return self.shard.run_tick(self, lib, s32, state_which, state_n)
         if state_which is not None:  # u and one [H] state array with a single device->host window and synchronisation
             if self._state_buf is None or self._state_buf.size != state_n:
                 self._state_buf = np.empty(state_n, np.float32)

@@ -129,14 +129,22 @@ class ShardPlan:
             if not more:
                 break
 
-    def run_tick(self, opt, lib, s32: np.ndarray) -> np.ndarray:
-        """Sharded tick with host in / host out (the optimizer plugin's step())."""
+    def run_tick(self, opt, lib, s32: np.ndarray, state_which=None, state_n: int = 0) -> np.ndarray:
+        """Sharded tick with host in / host out (the optimizer plugin's step()).  With the fused exchange the [H] warm-start
+        sequence comes back through the same host mirror as u (opt._state_buf), as in the unsharded call."""
         import torch
         if not getattr(opt, "_shard_attached", False):
             self.attach(opt, lib)
         if opt._exchange in ("p2p", "none"):  # the C call does the staging, the fused tick and the read-back
-            L.check(lib.ctk_step(opt._h, L.fptr(s32), L.fptr(opt._u_buf)))
+            if state_which is not None:
+                if opt._state_buf is None or opt._state_buf.size != state_n:
+                    opt._state_buf = np.empty(state_n, np.float32)
+                L.check(lib.ctk_step_state(opt._h, L.fptr(s32), L.fptr(opt._u_buf), state_which, L.fptr(opt._state_buf), state_n))
+            else:
+                opt._state_buf = None
+                L.check(lib.ctk_step(opt._h, L.fptr(s32), L.fptr(opt._u_buf)))
             return opt._u_buf.copy()
+        opt._state_buf = None
         dev = f"cuda:{opt.device}"
         if not hasattr(opt, "_s_pin"):
             opt._s_pin = torch.empty(6, dtype=torch.float32).pin_memory()
