@@ -160,10 +160,15 @@ int ctk_clear_injected_noise(ctk_handle *h);
 
 /* ---- the hot path ------------------------------------------------------------------------------------------- */
 /* replaces optimizer.step(s, time) (controller_mpc.py:104): one full tick, host in / host out.
-   s_host [num_states]; u_out_host [num_control_inputs].                                                          */
+   s_host [num_states]; u_out_host [num_control_inputs].  The call issues no cudaMemcpy and no stream synchronisation:
+   the state travels inside the kernel parameters, the tick's last kernel stores u and a status word as tagged 8-byte
+   slots (value | launch sequence number) into mapped pinned host memory, and the call polls the tags (a faulted or
+   lost stream is detected through cudaStreamQuery after 50 ms; 60 s hard limit).  MPPI, CEM (unsharded populations up
+   to one resident grid) and RPGD with num_rollouts <= 32 run the whole tick as ONE kernel launch.                  */
 int ctk_step(ctk_handle *h, const float *s_host, float *u_out_host);
-/* ctk_step plus the read-back of one [H] state array (CTK_STATE_U_NOM / CEM_MU / CEM_STD) in the same copy window and
-   synchronisation: the plugin's step() returns u AND refreshes the warm-start sequence every tick
+/* ctk_step plus the read-back of one [H] state array: CTK_STATE_U_NOM (MPPI u_nom; RPGD Q[best] before the shift,
+   optimizer_rpgd.py:426) comes back through the same host mirror, CTK_STATE_CEM_MU / CEM_STD through one device->host copy.
+   The plugin's step() returns u AND refreshes the warm-start sequence every tick
    (optimizer_mppi.py:220 optimal_control_sequence = u_nom).                                                         */
 int ctk_step_state(ctk_handle *h, const float *s_host, float *u_out_host, int which, float *state_out_host, size_t n);
 /* The same tick split for sharded (multi-GPU) use and for device-resident timing:
