@@ -350,6 +350,65 @@ def test_cem_persistent_tick_equals_multi_launch(N, H, k, iters):
         os.environ.pop("CTK_CEM_MULTI_LAUNCH", None)
 
 
+# states at the edges of the domain: on / beyond the 0.95 THL barrier (THL = 0.198) and the 0.9 THL border of the RPGD cost, at the
+# terminal-cost thresholds (|angle| = 0.2, |x - target| = 0.1 THL), hanging, fast spinning, at rest
+_EXTREME = np.array([[3.1, 9.0, 0, 0, 0.19, 1.5], [-3.1, -9.0, 0, 0, -0.197, -1.5], [0.2, 0.0, 0, 0, 0.0198, 0.0],
+                     [0.0, 0.0, 0, 0, 0.0, 0.0], [1.5707964, 25.0, 0, 0, 0.1881, 3.0], [-0.19999, 0.5, 0, 0, -0.1782, -0.2]], np.float32)
+_EXTREME[:, 2], _EXTREME[:, 3] = np.cos(_EXTREME[:, 0]), np.sin(_EXTREME[:, 0])
+
+
+@pytest.mark.parametrize("fixture", ["mppi_c1_n64", "cem_c2_n256_k16", "rpgd_c3", "gradcem_naive_n200"])
+def test_extreme_states_match_oracle(fixture):
+    """Initial states at the edges of the domain (track barrier and border indicators, terminal-cost thresholds, hanging / spinning
+    pole, rest): every tick starts from the optimizer's reset state so that one chaotic tick cannot contaminate the next; finite
+    outputs, per-rollout costs and the chosen control against the oracle (costs there span 1e0 .. 1e12)."""
+    from oracle.replay_rng import ReplayRNG
+    z, meta = load_golden(fixture)
+    ctrl = make_controller(meta, rng=None, logging=True)
+    opt = ctrl.optimizer
+    for i, s0 in enumerate(_EXTREME):
+        opt.rng = ReplayRNG(40 + i, as_torch=False)
+        opt.optimizer_reset()
+        o = make_oracle(meta)
+        rng = ReplayRNG(40 + i)
+        if hasattr(o, "reset"):
+            o.reset(*([rng] if meta["optimizer"] in ("rpgd", "gradient-tf") else []))
+        u = ctrl.step(s0)
+        uo = o.step(s0, rng)
+        J, Jo = np.asarray(opt.logging_values["J_logged"], np.float64), np.asarray(o.last["J"], np.float64)
+        assert np.all(np.isfinite(J)) and np.all(np.isfinite(np.ravel(u)))
+        eJ = np.abs(J - Jo) / (np.abs(Jo) + 1e-3)
+        e_u = abs(float(np.ravel(u)[0]) - float(np.ravel(uo)[0]))
+        _report(f"extreme {fixture} state {i}: J q90 {np.quantile(eJ, 0.9):.2e} max {eJ.max():.2e} (J range {Jo.min():.3g} .. {Jo.max():.3g}) u {e_u:.2e}")
+        # the 1e9 barrier turns an ulp of position into 1e-4 of cost right at the edge: 90 % of the rollouts within 1e-3, all within 5e-2
+        assert np.quantile(eJ, 0.9) < 1e-3 and eJ.max() < 5e-2, (fixture, i, float(np.quantile(eJ, 0.9)), float(eJ.max()))
+        assert e_u < 2e-3, (fixture, i, e_u)
+
+
+def test_rpgd_long_horizon_takes_the_direct_form_kernel():
+    """H = 160 does not fit the coefficient tape (12 floats per step and trajectory): the tick falls back to the direct-form adjoint
+    kernel (8 floats per step) + the separate select launch and must still follow the oracle."""
+    from oracle.replay_rng import ReplayRNG
+    z, meta = load_golden("rpgd_c3")
+    meta = dict(meta, cfg=dict(meta["cfg"], num_rollouts=8, mpc_horizon=160, outer_its=1))
+    ctrl = make_controller(meta, rng=None, logging=True, adam_form="torch")
+    opt = ctrl.optimizer
+    opt.rng = ReplayRNG(12, as_torch=False)
+    opt.optimizer_reset()
+    o = make_oracle(meta)
+    rng = ReplayRNG(12)
+    o.reset(rng)
+    s0 = np.array([0.05, 0.1, np.cos(0.05), np.sin(0.05), 0.01, 0.0], np.float32)  # near upright: a well-conditioned 160-step rollout
+    l0 = opt.gpu_launches
+    u = ctrl.step(s0)
+    uo = o.step(s0, rng)
+    assert opt.gpu_launches - l0 >= 2
+    eJ = np.abs(np.asarray(opt.logging_values["J_logged"], np.float64) - o.last["J"]) / (np.abs(o.last["J"]) + 1e-3)
+    _report(f"rpgd H=160 direct form: J max {eJ.max():.2e} u {abs(float(u[0]) - float(np.ravel(uo)[0])):.2e}")
+    assert eJ.max() < 5e-2 and np.median(eJ) < 1e-3
+    np.testing.assert_array_equal(opt.best_indices()[:1], o.last["best_idx"][:1])
+
+
 def test_rpgd_last_inducing_point_quirk():
     """reference others/Interpolator.py:73-74 divides the '1' of the last inducing point by the period: with H - 1 a multiple of the
     period the final horizon step of every sampled sequence is y_last / period.  RPGD's initial population must show it."""
