@@ -66,10 +66,51 @@ __global__ void __launch_bounds__(128) cem_rollout_kernel(const CemArgs a) {
 }
 
 // One block of 1024 threads: merge candidates -> global top-k (bitonic), regenerate elite Q, refit mu / sd.
+// One CEM rollout in the scaled state variables of K1 (ctk_ode_scaled.cuh): sample -> step -> cost over the horizon, returns the
+// trajectory cost.  Full groups of four steps form ONE basic block together with the (independent) Philox block of the next
+// four steps, so the scheduler interleaves the draw latency with the state chain.  Shared by K3s and the persistent tick.
+template <int KIND, bool LOG>
+__device__ __forceinline__ float cem_rollout_scaled(const NoiseSrc& ns, uint32_t ng, int n, int N, int H, const float* sh_mu,
+                                                    const float* sh_sd, const ScaledState& r0, float u_prev, const OdeHot& k,
+                                                    float* log_traj_soa, float* log_Q_soa) {
+  ScaledState r = r0;
+  float ul = u_prev;
+  float acc = (k.k_ccrc * u_prev) * u_prev;  // telescoped control-change cost: + k_ccrc u_{-1}^2 here, - k_ccrc u_{H-1}^2 at the end
+  float zn[4];
+  noise4(ns, ng, 0u, zn);
+  auto log_state = [&](int t) {
+    float st[6];
+    scaled_to_state(r, k, st);
+    float* p = log_traj_soa + (size_t)t * 6 * N + n;
+    p[0] = st[0]; p[N] = st[1]; p[2 * N] = st[2]; p[3 * N] = st[3]; p[4 * (size_t)N] = st[4]; p[5 * (size_t)N] = st[5];
+  };
+  auto one_step = [&](int t, float zt) {
+    const float u = cem_sample(sh_mu[t], sh_sd[t], zt, k.lo, k.hi);
+    if (LOG) {
+      log_state(t);
+      log_Q_soa[(size_t)t * N + n] = u;
+    }
+    acc = stage_cost_scaled<KIND>(acc, r, u, ul, 0.0f, k);  // kC == 0 for CEM (no MPPI correction)
+    ode_step_scaled(r, u, k);
+    ul = u;
+  };
+  int t0 = 0;
+  for (; t0 + 4 <= H; t0 += 4) {
+    const float z0 = zn[0], z1 = zn[1], z2 = zn[2], z3 = zn[3];
+    noise4(ns, ng, (uint32_t)((t0 >> 2) + 1), zn);
+    one_step(t0, z0);
+    one_step(t0 + 1, z1);
+    one_step(t0 + 2, z2);
+    one_step(t0 + 3, z3);
+  }
+  for (int q = 0; t0 + q < H; ++q) one_step(t0 + q, zn[q]);
+  if (LOG) log_state(H);
+  return finish_cost_scaled(acc, r, ul, k);
+}
+
 // K3s: the same sample -> rollout -> cost pass for the ODE predictor in the scaled state variables of K1 (12-instruction Euler
 // step, cost with the control terms merged into u (kA u + kB u_prev) and the u_prev^2 terms telescoped; constants are kernel
-// parameters -> uniform registers).  The Philox block of the NEXT four steps is generated next to the current four steps'
-// dependent chain, so the draw latency never sits on it.
+// parameters -> uniform registers); the block can also emit its own top-k candidates (level 0 of K4).
 constexpr int kCemOdeTopkThreads = 256;  // block size when the block-level top-k is fused in (CemOdeArgs::cand_out)
 template <int KIND, bool LOG>
 __global__ void __launch_bounds__(kCemOdeTopkThreads) cem_ode_kernel(const CemOdeArgs a) {
@@ -90,46 +131,13 @@ __global__ void __launch_bounds__(kCemOdeTopkThreads) cem_ode_kernel(const CemOd
   if (!active && a.cand_out == nullptr) return;
   uint64_t key = KEY_MAX;
   if (active) {
-  const uint32_t ng = (uint32_t)(a.off + n);
-  const float s0v[6] = {a.s0.ld(0), a.s0.ld(1), a.s0.ld(2), a.s0.ld(3), a.s0.ld(4), a.s0.ld(5)};
-  ScaledState r;
-  scaled_from_state(s0v, k, r);
-  const float u_prev = a.u_prev[0];
-  float ul = u_prev;
-  float acc = (k.k_ccrc * u_prev) * u_prev;  // telescoped control-change cost: + k_ccrc u_{-1}^2 here, - k_ccrc u_{H-1}^2 at the end
-  float zn[4];
-  noise4(a.noise, ng, 0u, zn);
-  for (int t0 = 0; t0 < a.H; t0 += 4) {
-    const float z0 = zn[0], z1 = zn[1], z2 = zn[2], z3 = zn[3];
-    if (t0 + 4 < a.H) noise4(a.noise, ng, (uint32_t)((t0 >> 2) + 1), zn);
-    const float zz[4] = {z0, z1, z2, z3};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int t = t0 + q;
-      if (t < a.H) {
-        const float u = cem_sample(sh_mu[t], sh_sd[t], zz[q], k.lo, k.hi);
-        if (LOG) {
-          float st[6];
-          scaled_to_state(r, k, st);
-          float* p = a.log_traj_soa + (size_t)t * 6 * a.N + n;
-          p[0] = st[0]; p[a.N] = st[1]; p[2 * a.N] = st[2]; p[3 * a.N] = st[3]; p[4 * (size_t)a.N] = st[4]; p[5 * (size_t)a.N] = st[5];
-          a.log_Q_soa[(size_t)t * a.N + n] = u;
-        }
-        acc = stage_cost_scaled<KIND>(acc, r, u, ul, 0.0f, k);  // kC == 0 for CEM (no MPPI correction)
-        ode_step_scaled(r, u, k);
-        ul = u;
-      }
-    }
-  }
-  if (LOG) {
-    float st[6];
-    scaled_to_state(r, k, st);
-    float* p = a.log_traj_soa + (size_t)a.H * 6 * a.N + n;
-    p[0] = st[0]; p[a.N] = st[1]; p[2 * a.N] = st[2]; p[3 * a.N] = st[3]; p[4 * (size_t)a.N] = st[4]; p[5 * (size_t)a.N] = st[5];
-  }
-  const float J = finish_cost_scaled(acc, r, ul, k);
-  a.J[n] = J;
-  key = make_key(J, ng);
+    const uint32_t ng = (uint32_t)(a.off + n);
+    const float s0v[6] = {a.s0.ld(0), a.s0.ld(1), a.s0.ld(2), a.s0.ld(3), a.s0.ld(4), a.s0.ld(5)};
+    ScaledState r0;
+    scaled_from_state(s0v, k, r0);
+    const float J = cem_rollout_scaled<KIND, LOG>(a.noise, ng, n, a.N, a.H, sh_mu, sh_sd, r0, a.u_prev[0], k, a.log_traj_soa, a.log_Q_soa);
+    a.J[n] = J;
+    key = make_key(J, ng);
   }
   if (a.cand_out != nullptr) {  // block-level top-k (K4 level 0): blockDim.x == kCemOdeTopkThreads
     key = block_bitonic_sort(key, sh_keys, kCemOdeTopkThreads);
@@ -355,43 +363,7 @@ __global__ void __launch_bounds__(kCemTickThreads) cem_tick_kernel(const CemTick
     // ---- (B) sample -> rollout -> cost (K3s) ----
     uint64_t key = KEY_MAX;
     if (active) {
-      ScaledState r = r0;
-      float ul = u_prev;
-      float acc = (k.k_ccrc * u_prev) * u_prev;
-      float zn[4];
-      noise4(ns, ng, 0u, zn);
-      auto one_step = [&](int t, float zt) {
-        const float u = cem_sample(sh_mu[t], sh_sd[t], zt, k.lo, k.hi);
-        if (LOG) {
-          float st[6];
-          scaled_to_state(r, k, st);
-          float* p = a.log_traj_soa + (size_t)t * 6 * a.N + n;
-          p[0] = st[0]; p[a.N] = st[1]; p[2 * a.N] = st[2]; p[3 * a.N] = st[3]; p[4 * (size_t)a.N] = st[4]; p[5 * (size_t)a.N] = st[5];
-          a.log_Q_soa[(size_t)t * a.N + n] = u;
-        }
-        acc = stage_cost_scaled<KIND>(acc, r, u, ul, 0.0f, k);
-        ode_step_scaled(r, u, k);
-        ul = u;
-      };
-      int t0s = 0;
-      // full groups of four steps: ONE basic block holding the four dependent steps and the (independent) Philox block of the
-      // next four, so the scheduler interleaves the draw latency with the state chain
-      for (; t0s + 4 <= H; t0s += 4) {
-        const float z0 = zn[0], z1 = zn[1], z2 = zn[2], z3 = zn[3];
-        noise4(ns, ng, (uint32_t)((t0s >> 2) + 1), zn);
-        one_step(t0s, z0);
-        one_step(t0s + 1, z1);
-        one_step(t0s + 2, z2);
-        one_step(t0s + 3, z3);
-      }
-      for (int q = 0; t0s + q < H; ++q) one_step(t0s + q, zn[q]);
-      if (LOG) {
-        float st[6];
-        scaled_to_state(r, k, st);
-        float* p = a.log_traj_soa + (size_t)H * 6 * a.N + n;
-        p[0] = st[0]; p[a.N] = st[1]; p[2 * a.N] = st[2]; p[3 * a.N] = st[3]; p[4 * (size_t)a.N] = st[4]; p[5 * (size_t)a.N] = st[5];
-      }
-      const float J = finish_cost_scaled(acc, r, ul, k);
+      const float J = cem_rollout_scaled<KIND, LOG>(ns, ng, n, a.N, H, sh_mu, sh_sd, r0, u_prev, k, a.log_traj_soa, a.log_Q_soa);
       if (last) a.J[n] = J;
       key = make_key(J, ng);
     }
