@@ -202,6 +202,7 @@ struct CemTickArgs {
   float* log_Q_soa;            // [H][N] or null
   unsigned long long* cand;    // [gridDim.x][k] tagged candidate keys: ordered cost (32) | id (16) | sequence tag (16)
   int k2, runs_pad, q_cap;     // pow2 >= max(k, 32); pow2 >= gridDim.x; floats of the big shared buffer (>= runs_pad * k2 * 2)
+  int rb;                      // rollouts per block (power of two, 32 .. 512; the block has 512 threads)
   unsigned long long* dist;    // [2][H] tagged mu / sd published by block 0 for the next iteration
   unsigned int seq0;           // sequence number of iteration 0 (monotonic across ticks, never 0)
   float sd_min, sd_init;

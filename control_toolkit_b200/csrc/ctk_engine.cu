@@ -672,10 +672,12 @@ static int mppi_finish(ctk_handle* h, const float* gathered, int G, float* u_out
 }
 
 // The whole CEM tick in one persistent launch, when the population fits one resident grid and is not sharded
-struct CemTickGeom { int G, k2, runs_pad, big_floats; size_t smem; };
+struct CemTickGeom { int G, k2, runs_pad, big_floats, rb; size_t smem; };
 static bool cem_tick_geometry(const ctk_handle* h, CemTickGeom* g) {
   const ctk_config& c = h->cfg;
-  const int RB = cem_tick_rollouts_per_block();
+  int RB = cem_tick_rollouts_per_block();
+  if (const char* e = getenv("CTK_CEM_RB")) { const int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256 || v == 512) RB = v; }
+  g->rb = RB;
   g->G = (h->N + RB - 1) / RB;
   g->k2 = 32;
   while (g->k2 < c.cem_best_k) g->k2 <<= 1;
@@ -732,7 +734,7 @@ static int cem_tick_persistent(ctk_handle* h, const float* s_dev, float* u_out_d
   h->cem_iters = iters;
   CemTickGeom g;
   cem_tick_geometry(h, &g);
-  a.k2 = g.k2; a.runs_pad = g.runs_pad; a.q_cap = g.big_floats;
+  a.k2 = g.k2; a.runs_pad = g.runs_pad; a.q_cap = g.big_floats; a.rb = g.rb;
   h->launches++;
   cudaError_t e;
   {

@@ -325,7 +325,8 @@ __global__ void __launch_bounds__(kCemTickThreads) cem_tick_kernel(const CemTick
   __shared__ uint64_t sh_sort[kCemTickThreads];
   __shared__ uint32_t sh_elite[kCemTickMaxK];
   const OdeHot& k = a.hot;
-  constexpr int T = kCemTickThreads, RB = kCemTickRollouts;
+  constexpr int T = kCemTickThreads;
+  const int RB = a.rb;
   const int tid = threadIdx.x, b = blockIdx.x, H = a.H, G = (int)gridDim.x;
   const int n = b * RB + tid;
   const bool active = tid < RB && n < a.N;
