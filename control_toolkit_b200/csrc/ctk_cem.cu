@@ -31,11 +31,19 @@ cudaError_t launch_cem_ode(int kind, bool log, int nblocks, size_t smem, cudaStr
   }
   return launch_pdl(k, dim3(nblocks), dim3(a.cand_out != nullptr ? kCemOdeTopkThreads : 128), smem, st, a);
 }
+// FAST instantiations: Philox normal draws (no injected queue, no uniform mode) -> straight-line noise generation
+static void (*cem_tick_fn(int kind, bool log, bool fast))(const CemTickArgs) {
+  if (kind == 0) {
+    if (log) return fast ? cem_tick_kernel<0, true, true> : cem_tick_kernel<0, true, false>;
+    return fast ? cem_tick_kernel<0, false, true> : cem_tick_kernel<0, false, false>;
+  }
+  if (log) return fast ? cem_tick_kernel<1, true, true> : cem_tick_kernel<1, true, false>;
+  return fast ? cem_tick_kernel<1, false, true> : cem_tick_kernel<1, false, false>;
+}
 cudaError_t launch_cem_tick(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemTickArgs& a) {
-  void (*k)(const CemTickArgs) = nullptr;
-  if (kind == 0) k = log ? cem_tick_kernel<0, true> : cem_tick_kernel<0, false>;
-  else k = log ? cem_tick_kernel<1, true> : cem_tick_kernel<1, false>;
-  if (smem > 11 * 1024) {  // 37 KB of static shared memory come on top
+  const bool fast = a.noise.inj == nullptr && !a.noise.uniform;
+  void (*k)(const CemTickArgs) = cem_tick_fn(kind, log, fast);
+  if (smem > 11 * 1024) {  // static shared memory comes on top
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
@@ -44,9 +52,7 @@ cudaError_t launch_cem_tick(int kind, bool log, int nblocks, size_t smem, cudaSt
 int cem_tick_rollouts_per_block() { return kCemTickRollouts; }
 // resident blocks per SM of the persistent tick kernel (its blocks wait for each other: the whole grid must be resident)
 int cem_tick_blocks_per_sm(int kind, bool log, size_t smem) {
-  void (*k)(const CemTickArgs) = nullptr;
-  if (kind == 0) k = log ? cem_tick_kernel<0, true> : cem_tick_kernel<0, false>;
-  else k = log ? cem_tick_kernel<1, true> : cem_tick_kernel<1, false>;
+  void (*k)(const CemTickArgs) = cem_tick_fn(kind, log, false);  // the generic instantiation needs at least as many registers
   if (smem > 11 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, kCemTickThreads, smem) != cudaSuccess) return 0;

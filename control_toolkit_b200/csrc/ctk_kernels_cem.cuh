@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(128) cem_rollout_kernel(const CemArgs a) {
 // One CEM rollout in the scaled state variables of K1 (ctk_ode_scaled.cuh): sample -> step -> cost over the horizon, returns the
 // trajectory cost.  Full groups of four steps form ONE basic block together with the (independent) Philox block of the next
 // four steps, so the scheduler interleaves the draw latency with the state chain.  Shared by K3s and the persistent tick.
-template <int KIND, bool LOG>
+// FAST: Philox N(0,1) draws without the run-time noise-mode branches (production CEM ticks).
+template <int KIND, bool LOG, bool FAST = false>
 __device__ __forceinline__ float cem_rollout_scaled(const NoiseSrc& ns, uint32_t ng, int n, int N, int H, const float* sh_mu,
                                                     const float* sh_sd, const ScaledState& r0, float u_prev, const OdeHot& k,
                                                     float* log_traj_soa, float* log_Q_soa) {
@@ -77,7 +78,7 @@ __device__ __forceinline__ float cem_rollout_scaled(const NoiseSrc& ns, uint32_t
   float ul = u_prev;
   float acc = (k.k_ccrc * u_prev) * u_prev;  // telescoped control-change cost: + k_ccrc u_{-1}^2 here, - k_ccrc u_{H-1}^2 at the end
   float zn[4];
-  noise4(ns, ng, 0u, zn);
+  if (FAST) noise4_normal(ns, ng, 0u, zn); else noise4(ns, ng, 0u, zn);
   auto log_state = [&](int t) {
     float st[6];
     scaled_to_state(r, k, st);
@@ -97,7 +98,7 @@ __device__ __forceinline__ float cem_rollout_scaled(const NoiseSrc& ns, uint32_t
   int t0 = 0;
   for (; t0 + 4 <= H; t0 += 4) {
     const float z0 = zn[0], z1 = zn[1], z2 = zn[2], z3 = zn[3];
-    noise4(ns, ng, (uint32_t)((t0 >> 2) + 1), zn);
+    if (FAST) noise4_normal(ns, ng, (uint32_t)((t0 >> 2) + 1), zn); else noise4(ns, ng, (uint32_t)((t0 >> 2) + 1), zn);
     one_step(t0, z0);
     one_step(t0 + 1, z1);
     one_step(t0 + 2, z2);
@@ -314,7 +315,7 @@ __device__ __forceinline__ void merge_runs_tree(uint64_t* sh_runs, int runs, int
   }
 }
 
-template <int KIND, bool LOG>
+template <int KIND, bool LOG, bool FAST>
 __global__ void __launch_bounds__(kCemTickThreads) cem_tick_kernel(const CemTickArgs a) {
   extern __shared__ float smem[];
   float* sh_mu = smem;         // [H]
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(kCemTickThreads) cem_tick_kernel(const CemTick
     // ---- (B) sample -> rollout -> cost (K3s) ----
     uint64_t key = KEY_MAX;
     if (active) {
-      const float J = cem_rollout_scaled<KIND, LOG>(ns, ng, n, a.N, H, sh_mu, sh_sd, r0, u_prev, k, a.log_traj_soa, a.log_Q_soa);
+      const float J = cem_rollout_scaled<KIND, LOG, FAST>(ns, ng, n, a.N, H, sh_mu, sh_sd, r0, u_prev, k, a.log_traj_soa, a.log_Q_soa);
       if (last) a.J[n] = J;
       key = make_key(J, ng);
     }
