@@ -245,6 +245,25 @@ class template_optimizer:
         L.check(lib.ctk_get_log(self._h, which, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out.reshape(shape)
 
+    def export_philox(self, stream: int, tick: int, per_rollout: int, rows: int, uniform: bool = False, row0: int = 0,
+                      sub: int = 0) -> np.ndarray:
+        """The standard draws [rows, per_rollout] the kernels generate in-kernel for noise block (stream | sub << 8, tick) of this
+        handle (verification of the production instantiations against the oracle: ctk_philox_export)."""
+        lib = self._require_backend()
+        out = np.empty((int(rows), int(per_rollout)), np.float32)
+        L.check(lib.ctk_philox_export(self._h, int(stream) | (int(sub) << 8), int(tick), int(per_rollout), int(bool(uniform)),
+                                      int(row0), int(rows), L.fptr(out)))
+        return out
+
+    @property
+    def last_kernel(self) -> str:
+        """Template instantiation of the last rollout-kernel launch (ctk_last_kernel)."""
+        return (self._require_backend().ctk_last_kernel(self._h) or b"").decode()
+
+    @property
+    def tick_counter(self) -> int:
+        return self._get_counter(L.COUNTER_TICK)
+
     @property
     def gpu_launches(self) -> int:
         lib = self._require_backend()

@@ -24,6 +24,7 @@ ADAM_KERAS, ADAM_TORCH = 0, 1
 MLP_SIMT, MLP_TCGEN05 = 0, 1
 STATE_U_NOM, STATE_CEM_MU, STATE_CEM_STD, STATE_RPGD_Q, STATE_RPGD_M, STATE_RPGD_V, STATE_RPGD_AGES, STATE_U_PREV = range(8)
 COUNTER_COUNT, COUNTER_ADAM_STEP, COUNTER_TICK = range(3)
+STREAM_MPPI, STREAM_CEM, STREAM_RPGD_INIT, STREAM_RPGD_RESAMPLE = range(4)
 LOG_Q, LOG_J, LOG_ROLLOUTS, LOG_ELITE_IDX, LOG_U_NOM, LOG_AGES = range(6)
 
 
@@ -97,6 +98,7 @@ SYMBOLS = {
     "ctk_set_counter": (C.c_int, [_H, C.c_int, C.c_int64]),
     "ctk_get_log": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_size_t]),
     "ctk_get_log_view": (C.c_int, [_H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "ctk_last_kernel": (C.c_char_p, [_H]),
     "ctk_get_launch_count": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "ctk_enable_kernel_timing": (C.c_int, [_H, C.c_int]),
     "ctk_get_kernel_timing": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
@@ -107,6 +109,7 @@ SYMBOLS = {
     "ctk_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ctk_fp32_microbench": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "ctk_philox_fill": (C.c_int, [C.c_int, C.c_uint64, C.c_int, _FP, C.c_size_t]),
+    "ctk_philox_export": (C.c_int, [_H, C.c_uint32, C.c_int64, C.c_int, C.c_int, C.c_size_t, C.c_size_t, _FP]),
     "ctk_topk": (C.c_int, [C.c_int, _FP, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
 }
 

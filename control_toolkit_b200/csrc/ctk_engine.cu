@@ -105,6 +105,7 @@ struct ctk_handle {
   bool timing = false;
   std::vector<cudaEvent_t> ev;  // pairs
   size_t ev_used = 0;
+  std::string last_kernel;  // instantiation of the last rollout-kernel launch (ctk_last_kernel: tests pin the production kernels)
 };
 
 struct KernelTimer {  // records an event pair around the dominant kernel launch when timing is enabled
@@ -624,7 +625,9 @@ static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_
     a.fuse = fuse;
     h->launches++;
     KernelTimer kt(h);
-    cudaError_t e = launch_mppi_ode(h->cost.kind, log, h->ode_period_t, h->ode_ilp, h->ode_grid, h->ode_block, h->ode_smem, h->stream, a);
+    const char* tail = "";
+    cudaError_t e = launch_mppi_ode(h->cost.kind, log, h->ode_period_t, h->ode_ilp, h->ode_grid, h->ode_block, h->ode_smem, h->stream, a, &tail);
+    h->last_kernel = "mppi_ode_kernel<" + std::to_string(h->cost.kind) + tail;
     if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("mppi_ode_kernel: ") + cudaGetErrorString(e));
     return CTK_OK;
   }
@@ -655,6 +658,8 @@ static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_
   if (pred_id(h) == 2 && h->mlp.tc_blob == nullptr) return fail(CTK_ESTATE, "tcgen05 MLP engine without weights");
   cudaError_t e = launch_mppi_rollout(pred_id(h), h->cost.kind, log, h->mppi_grid, h->mppi_block, smem,
                                       h->stream, a);
+  h->last_kernel = std::string("mppi_rollout_kernel<") + (pred_id(h) == 2 ? "MlpTcPred" : pred_id(h) == 1 ? "MlpSimtPred" : "OdePred") + "," +
+                   std::to_string(h->cost.kind) + "," + (log ? "1" : "0") + ">" + (ns.inj ? " [injected noise]" : " [philox]");
   if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("mppi_rollout_kernel: ") + cudaGetErrorString(e));
   return CTK_OK;
 }
@@ -740,6 +745,8 @@ static int cem_tick_persistent(ctk_handle* h, const float* s_dev, float* u_out_d
   {
     KernelTimer kt(h);
     e = launch_cem_tick(h->cost.kind, c.logging != 0, g.G, g.smem, h->stream, a);
+    h->last_kernel = "cem_tick_kernel<" + std::to_string(h->cost.kind) + "," + (c.logging ? "1" : "0") + "," +
+                     ((a.noise.inj == nullptr && !a.noise.uniform) ? "1" : "0") + ">";
   }
   if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("cem_tick_kernel: ") + cudaGetErrorString(e));
   h->cem_it = 0;
@@ -782,6 +789,7 @@ static int cem_local(ctk_handle* h, const float* s_dev, bool to_k) {
     }
     KernelTimer kt(h);
     e = launch_cem_ode(h->cost.kind, c.logging != 0, nb, sizeof(float) * 2 * (size_t)h->H, h->stream, a);
+    h->last_kernel = "cem_ode_kernel<" + std::to_string(h->cost.kind) + "," + (c.logging ? "1" : "0") + ">" + (ns.inj ? " [injected noise]" : " [philox]");
   } else {
     CemArgs a{};
     a.N = h->N; a.off = h->off; a.H = h->H; a.s0 = make_s0(h, s_dev); a.mu = h->d_mu; a.sd = h->d_sd; a.u_prev = h->d_u_prev; a.noise = ns;
@@ -1366,6 +1374,9 @@ extern "C" int ctk_debug_trace(ctk_handle* h, int enable, uint64_t* out_host, si
   if (!enable && h->d_trace) { cudaFree(h->d_trace); h->d_trace = nullptr; }
   return CTK_OK;
 }
+// instantiation of the last rollout-kernel launch of this handle, e.g. "mppi_ode_kernel<0,0,10,2,1024,0>" (verification: the parity
+// tests assert that the kernel they compared with the oracle is the one bench.py times)
+extern "C" const char* ctk_last_kernel(ctk_handle* h) { return h ? h->last_kernel.c_str() : ""; }
 extern "C" int ctk_get_launch_count(ctk_handle* h, int64_t* v) { REQ(h && v, "null pointer"); *v = h->launches; return CTK_OK; }
 
 // device source (after the layout transpose, if any) and size of one log
@@ -1539,6 +1550,31 @@ extern "C" int ctk_philox_fill(int device, uint64_t seed, int kind, float* dst, 
   ns.per_rollout = 16; ns.uniform = kind;
   cudaError_t e = launch_philox_fill(ns, d, n, nullptr);
   if (e == cudaSuccess) e = cudaMemcpy(dst, d, sizeof(float) * n, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CU(e);
+  return CTK_OK;
+}
+
+static_assert((uint32_t)CTK_STREAM_MPPI == STREAM_MPPI && (uint32_t)CTK_STREAM_CEM == STREAM_CEM && (uint32_t)CTK_STREAM_RPGD_INIT == STREAM_RPGD_INIT &&
+                  (uint32_t)CTK_STREAM_RPGD_RESAMPLE == STREAM_RPGD_RESAMPLE, "public stream ids == kernel stream ids");
+// The standard draws a consumer of THIS handle generates in Philox mode: same key (seed), same counter words (draw block,
+// global rollout id, tick, stream) and the same device function (noise4) as the kernels, so a test can hand the oracle exactly
+// the numbers the production (in-kernel noise) instantiations consumed.
+extern "C" int ctk_philox_export(ctk_handle* h, uint32_t stream, int64_t tick, int per_rollout, int uniform, size_t row0, size_t rows,
+                                 float* dst_host) {
+  REQ(h && dst_host, "null pointer");
+  REQ(per_rollout >= 1, "per_rollout must be >= 1");
+  CU(cudaSetDevice(h->cfg.device));
+  const size_t n = rows * (size_t)per_rollout;
+  if (n == 0) return CTK_OK;
+  NoiseSrc ns{};
+  ns.inj = nullptr; ns.key0 = (uint32_t)(h->cfg.seed & 0xffffffffull); ns.key1 = (uint32_t)(h->cfg.seed >> 32);
+  ns.tick = (uint32_t)tick; ns.stream = stream; ns.per_rollout = per_rollout; ns.uniform = uniform ? 1 : 0;
+  float* d = nullptr;
+  CU(cudaMalloc((void**)&d, sizeof(float) * n));
+  cudaError_t e = launch_philox_export(ns, row0, d, n, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dst_host, d, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   cudaFree(d);
   CU(e);
   return CTK_OK;

@@ -31,7 +31,8 @@ inline cudaError_t launch_pdl(void (*kern)(P...), dim3 grid, dim3 block, size_t 
 cudaError_t launch_mppi_rollout(int pred, int kind, bool log, int nblocks, int block, size_t smem, cudaStream_t st, const MppiArgs& a);
 int mppi_max_block_threads(int pred);
 // K1 for the ODE predictor with intermediate_steps == 1 (scaled variables, ILP rollouts per thread)
-cudaError_t launch_mppi_ode(int kind, bool log, int period_t, int ilp, int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a);
+cudaError_t launch_mppi_ode(int kind, bool log, int period_t, int ilp, int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a,
+                            const char** name = nullptr);
 int mppi_ode_max_block(int ilp);
 size_t mppi_ode_smem_bytes(int H, int period, int n_ind, int ilp, int block);
 cudaError_t launch_mppi_combine(const float* in, int cnt, int n_ind, float neg_inv_lbd, float* record_out,
@@ -60,5 +61,6 @@ cudaError_t launch_single_rollout(int pred, const float* s0, const float* Q, int
 cudaError_t launch_fma_peak(float* out, int blocks, int threads, int iters, cudaStream_t st);
 cudaError_t launch_fp32_micro(int variant, float* out, int blocks, int threads, int iters, const float* seed, cudaStream_t st);
 cudaError_t launch_philox_fill(const NoiseSrc& ns, float* out, size_t n, cudaStream_t st);
+cudaError_t launch_philox_export(const NoiseSrc& ns, size_t row0, float* out, size_t n, cudaStream_t st);
 
 }  // namespace ctk

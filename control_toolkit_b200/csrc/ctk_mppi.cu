@@ -44,17 +44,37 @@ static cudaError_t launch_mppi_ode_t(int grid, int block, size_t smem, cudaStrea
 // production instantiations: Philox noise only; injected noise (verification) and odd periods with logging run the
 // generic-period, one-rollout-per-thread instantiation (any launch geometry is valid for it: grid-stride loop)
 template <int KIND>
-static cudaError_t launch_mppi_ode_k(bool log, int period_t, int ilp, int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a) {
-  if (a.noise.inj != nullptr) return log ? launch_mppi_ode_t<KIND, true, 0, 1, true>(grid, block, smem, st, a) : launch_mppi_ode_t<KIND, false, 0, 1, true>(grid, block, smem, st, a);
-  if (log) {  // trajectory logging with in-kernel noise: HBM-write bound, the fast loop keeps the stores fed
-    if (period_t == 10) return ilp == 2 ? launch_mppi_ode_t<KIND, true, 10, 2, false>(grid, block, smem, st, a) : launch_mppi_ode_t<KIND, true, 10, 1, false>(grid, block, smem, st, a);
-    return launch_mppi_ode_t<KIND, true, 0, 1, true>(grid, block, smem, st, a);
+static cudaError_t launch_mppi_ode_k(bool log, int period_t, int ilp, int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a,
+                                     const char** name) {
+  // template arguments after KIND: LOG, PERIOD, ILP, (MAXT = 1024), INJ
+#define CTK_ODE_CASE(LOG_, P_, I_, INJ_)                                                  \
+  do {                                                                                    \
+    if (name) *name = "," #LOG_ "," #P_ "," #I_ ",1024," #INJ_ ">";                        \
+    return launch_mppi_ode_t<KIND, LOG_, P_, I_, INJ_>(grid, block, smem, st, a);         \
+  } while (0)
+  if (a.noise.inj != nullptr) {
+    if (log) CTK_ODE_CASE(1, 0, 1, 1);
+    CTK_ODE_CASE(0, 0, 1, 1);
   }
-  if (period_t == 10) return ilp == 2 ? launch_mppi_ode_t<KIND, false, 10, 2, false>(grid, block, smem, st, a) : launch_mppi_ode_t<KIND, false, 10, 1, false>(grid, block, smem, st, a);
-  return ilp == 2 ? launch_mppi_ode_t<KIND, false, 0, 2, false>(grid, block, smem, st, a) : launch_mppi_ode_t<KIND, false, 0, 1, false>(grid, block, smem, st, a);
+  if (log) {  // trajectory logging with in-kernel noise: HBM-write bound, the fast loop keeps the stores fed
+    if (period_t == 10) {
+      if (ilp == 2) CTK_ODE_CASE(1, 10, 2, 0);
+      CTK_ODE_CASE(1, 10, 1, 0);
+    }
+    CTK_ODE_CASE(1, 0, 1, 1);
+  }
+  if (period_t == 10) {
+    if (ilp == 2) CTK_ODE_CASE(0, 10, 2, 0);
+    CTK_ODE_CASE(0, 10, 1, 0);
+  }
+  if (ilp == 2) CTK_ODE_CASE(0, 0, 2, 0);
+  CTK_ODE_CASE(0, 0, 1, 0);
+#undef CTK_ODE_CASE
 }
-cudaError_t launch_mppi_ode(int kind, bool log, int period_t, int ilp, int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a) {
-  return kind == 0 ? launch_mppi_ode_k<0>(log, period_t, ilp, grid, block, smem, st, a) : launch_mppi_ode_k<1>(log, period_t, ilp, grid, block, smem, st, a);
+// name (optional): the template-argument tail of the instantiation that was launched, e.g. ",0,10,2,1024,0>" (after KIND)
+cudaError_t launch_mppi_ode(int kind, bool log, int period_t, int ilp, int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a,
+                            const char** name) {
+  return kind == 0 ? launch_mppi_ode_k<0>(log, period_t, ilp, grid, block, smem, st, a, name) : launch_mppi_ode_k<1>(log, period_t, ilp, grid, block, smem, st, a, name);
 }
 int mppi_ode_max_block(int ilp) { (void)ilp; return 1024; }
 size_t mppi_ode_smem_bytes(int H, int period, int n_ind, int ilp, int block) {

@@ -108,5 +108,15 @@ cudaError_t launch_philox_fill(const NoiseSrc& ns, float* out, size_t n, cudaStr
   philox_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ns, out, n);
   return cudaGetLastError();
 }
+// rows [row0, row0 + n / per_rollout) of a noise block, through the SAME device function the consumers call (noise4)
+__global__ void philox_export_kernel(NoiseSrc ns, size_t row0, float* out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = noise1(ns, (uint32_t)(row0 + i / ns.per_rollout), (int)(i % ns.per_rollout));
+}
+cudaError_t launch_philox_export(const NoiseSrc& ns, size_t row0, float* out, size_t n, cudaStream_t st) {
+  philox_export_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ns, row0, out, n);
+  return cudaGetLastError();
+}
 
 }  // namespace ctk

@@ -212,6 +212,9 @@ int ctk_get_log(ctk_handle *h, int which, void *dst_host, size_t n_bytes);
 int ctk_get_log_view(ctk_handle *h, int which, const void **host_ptr, size_t *n_bytes);
 /* number of CUDA kernels this handle has launched since create (bench.py "gpu_launches")                         */
 int ctk_get_launch_count(ctk_handle *h, int64_t *value);
+/* template instantiation of this handle's last rollout-kernel launch, e.g. "mppi_ode_kernel<0,0,10,2,1024,0>" (the parity tests
+   assert that the instantiation they pinned to the oracle is the one bench.py times); valid until the next step / destroy      */
+const char *ctk_last_kernel(ctk_handle *h);
 /* CUDA-event timing of the dominant kernel of a tick (the fused rollout kernel: K1 MPPI, K3 CEM, K6/K7 RPGD), used by
    bench.py for roofline.achieved.  enable(on) resets the accumulator; get() synchronises the stream and returns the
    summed duration and the number of timed launches since enable().                                                */
@@ -233,6 +236,14 @@ int ctk_fp32_peak(int device, double *tflops, double *sm_clock_mhz_est);
 int ctk_fp32_microbench(int device, int variant, double *ginstr_per_s);
 /* Philox self-test: fill dst_host with n standard normals (kind 0) / uniforms (kind 1) exactly as the kernels draw */
 int ctk_philox_fill(int device, uint64_t seed, int kind, float *dst_host, size_t n);
+/* Verification hook for the PRODUCTION (in-kernel noise) instantiations: the standard draws rows [row0, row0 + rows) of the noise
+   block (stream, tick) of this handle -- same key, counters and device function as the kernels.  stream = CTK_STREAM_* | (outer
+   iteration << 8); tick = CTK_COUNTER_TICK of the step that consumed the block (RPGD's initial population: the counter at
+   ctk_reset).  dst_host [rows * per_rollout], row-major.  The oracle replays them through rng.normal / rng.uniform
+   (optimizer_mppi.py:173, optimizer_cem_tf.py:64, optimizer_rpgd.py:277,284).                                          */
+enum { CTK_STREAM_MPPI = 0, CTK_STREAM_CEM = 1, CTK_STREAM_RPGD_INIT = 2, CTK_STREAM_RPGD_RESAMPLE = 3 };
+int ctk_philox_export(ctk_handle *h, uint32_t stream, int64_t tick, int per_rollout, int uniform, size_t row0, size_t rows,
+                      float *dst_host);
 /* standalone top-k (ties -> lower index), the kernel behind tf.argsort(...)[:k] (optimizer_cem_tf.py:73-74)      */
 int ctk_topk(int device, const float *cost_host, int n, int k, int32_t *idx_out_host);
 

@@ -41,7 +41,7 @@ class CEMOracle:
     def step(self, s: np.ndarray, rng) -> np.ndarray:
         s = torch.as_tensor(np.tile(np.asarray(s, np.float32), (self.N, 1))).to(self.dtype)  # :86-87
         iterations = self.warmup_iterations if self.warmup and self.count == 0 else self.outer_it  # :92
-        elite_log = []
+        elite_log, cost_log = [], []
         for _ in range(iterations):  # :93-94 -> update_distribution :61-80
             Q = self.dist_mue.repeat(self.N, 1, 1) + torch.mul(
                 rng.normal(shape=(self.N, self.H, 1), dtype=torch.float32).to(self.dtype), self.stdev)  # :64-65
@@ -55,11 +55,12 @@ class CEMOracle:
             mu = torch.mean(elite_Q, dim=0, keepdim=True)
             self.stdev = torch.sqrt(torch.mean((elite_Q - mu) * (elite_Q - mu), dim=0, keepdim=True))  # :78
             elite_log.append(best_idx.numpy().copy())
+            cost_log.append(traj_cost.numpy().copy())
         # :99-102
         self.stdev = torch.minimum(torch.maximum(self.stdev, torch.tensor(float(np.float32(self.std_min)), dtype=self.dtype)), torch.tensor(1.0e8, dtype=self.dtype))
         self.stdev = torch.cat([self.stdev[:, 1:, :], float(np.float32(self.init_std)) * torch.ones((1, 1, 1), dtype=self.dtype)], dim=1)
         self.u = elite_Q[0, 0, :].squeeze().numpy().copy()
         self.dist_mue = torch.cat([self.dist_mue[:, 1:, :], (self.low + self.high) * 0.5 * torch.ones((1, 1, 1), dtype=self.dtype)], dim=1)
-        self.last = dict(J=traj_cost.numpy(), Q=Q.numpy(), rollouts=rollout.numpy(), elite_idx=np.stack(elite_log))
+        self.last = dict(J=traj_cost.numpy(), Q=Q.numpy(), rollouts=rollout.numpy(), elite_idx=np.stack(elite_log), J_iters=np.stack(cost_log))
         self.count += 1  # :110
         return self.u

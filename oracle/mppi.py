@@ -85,3 +85,40 @@ class MPPIOracle:
         self.u = u_nom[0, 0, :].squeeze().numpy().copy()  # :191,212
         self.last = dict(J=S.numpy(), Q=u_run.numpy(), rollouts=rollout.numpy(), delta_u=delta_u.numpy())
         return self.u
+
+    def step_chunked(self, s: np.ndarray, rng, chunk: int = 65536) -> np.ndarray:
+        """The same tick evaluated ``chunk`` rollouts at a time (full-size configs: 10^6 x 100 would need > 5 GB of
+        intermediates in one piece).  Identical arithmetic per rollout; the population sums ``a`` and ``b`` are accumulated per chunk
+        (fp32 partial sums, then summed), i.e. a different -- equally valid -- fp32 summation tree than torch.sum's over N.
+        tests/test_oracle_golden.py checks it against step()."""
+        s1 = torch.as_tensor(np.asarray(s, np.float32)).to(self.dtype).reshape(1, -1)
+        u_old = self.u
+        u_nom = torch.cat([self.u_nom[:, 1:, :], self.u_nom[:, -1:, :]], 1)
+        z_all = rng.normal([self.N, self.n_ind, 1], dtype=torch.float32).to(self.dtype)
+        S_parts = []
+        for c0 in range(0, self.N, chunk):
+            z = z_all[c0:c0 + chunk]
+            n = z.shape[0]
+            delta_u = self._interpolate(z * self.SQRTRHODTINV)
+            u_run = torch.minimum(torch.maximum(u_nom.repeat(n, 1, 1) + delta_u, self.low), self.high)
+            rollout = self.predictor.predict_core(s1.repeat(n, 1), u_run)
+            total = spec.trajectory_cost(rollout, u_run, u_old, self.cost)
+            corr = torch.sum(self.cc_weight * (0.5 * (1 - 1.0 / self.NU) * self.R * (delta_u ** 2)
+                                               + self.R * u_run * delta_u + 0.5 * self.R * (u_run ** 2)), (1, 2))
+            S_parts.append(total + corr)
+        S = torch.cat(S_parts)
+        rho = torch.amin(S, 0)
+        exp_s = torch.exp(-1.0 / self.LBD * (S - rho))
+        a_parts, b_parts = [], []
+        for c0 in range(0, self.N, chunk):
+            e = exp_s[c0:c0 + chunk]
+            delta_u = self._interpolate(z_all[c0:c0 + chunk] * self.SQRTRHODTINV)
+            a_parts.append(torch.sum(e, 0))
+            b_parts.append(torch.sum(e[:, None, None] * delta_u, 0))
+        a = torch.sum(torch.stack(a_parts), 0)
+        b = torch.sum(torch.stack(b_parts), 0) / a
+        u_nom = torch.minimum(torch.maximum(u_nom + b, self.low), self.high)
+        self.u_nom = u_nom
+        self.u = u_nom[0, 0, :].squeeze().numpy().copy()
+        self.last = dict(J=S.numpy())
+        return self.u

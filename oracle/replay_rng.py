@@ -57,3 +57,25 @@ class ReplayRNG:
         z = self._wrap(self.standard_draws("uniform", shape))
         lo, hi = self._scalar(minval), self._scalar(maxval)
         return z * (hi - lo) + lo
+
+
+class QueueRNG(ReplayRNG):
+    """Replays GIVEN blocks of standard draws, in order (e.g. the in-kernel Philox draws of a production tick, exported with
+    ctk_philox_export): the oracle then consumes exactly the numbers the CUDA kernels generated."""
+
+    def __init__(self, blocks=(), as_torch: bool = True):
+        super().__init__(0, as_torch)
+        self.queue = [np.ascontiguousarray(b, dtype=np.float32) for b in blocks]
+
+    def push(self, block):
+        self.queue.append(np.ascontiguousarray(block, dtype=np.float32))
+
+    def standard_draws(self, kind: str, shape) -> np.ndarray:
+        shape = tuple(int(s) for s in shape)
+        if not self.queue:
+            raise RuntimeError(f"QueueRNG: no block left for a {kind} draw of shape {shape}")
+        z = self.queue.pop(0)
+        if z.size != int(np.prod(shape)):
+            raise RuntimeError(f"QueueRNG: next block has {z.size} draws, the consumer asks for {shape}")
+        self.blocks.append((kind, shape))
+        return z.reshape(shape)

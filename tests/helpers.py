@@ -96,6 +96,7 @@ def fp32_noise_floor(name, ticks=None, **over):
         scale = max(float(np.max(np.abs(s64))), 1e-2)
         eJ = np.abs(o32.last["J"].astype(np.float64) - o64.last["J"]) / (np.abs(o64.last["J"]) + 1e-3)
         out.append(dict(state=rel_err(s32, s64), J=float(eJ.max()), J_q99=float(np.quantile(eJ, 0.99)),
-                        u=float(np.max(np.abs(np.ravel(u32) - np.ravel(u64)))) / scale))
+                        u=float(np.max(np.abs(np.ravel(u32) - np.ravel(u64)))) / scale,
+                        state64=np.array(s64, np.float64), state32=np.array(s32, np.float64)))  # the float64 truth / fp32 reference of this tick
     _FLOOR_CACHE[key] = out
     return out

@@ -10,12 +10,14 @@ DESIGN.md "fp32 noise floor"), relative to the state array's max magnitude:
     |cuda - reference fp32|           : median 4e-6 .. 8e-6, max 1.7e-5 .. 4.0e-5, 68-97 % of ticks < 1e-5
     (an exact-arithmetic CUDA build -- no FMA contraction, IEEE division, accurate sincosf -- shows the same numbers)
 so 1e-5 is met in the median but is below what ANY independent fp32 implementation can guarantee per tick.  Asserted:
-  * every golden tick: state (u, u_nom / dist_mue, stdev / Q) within  max(2e-5, 6 x floor_t)  capped at 1e-4, where
-    floor_t is the reference's OWN |fp32 - float64| deviation on that very tick (tests/helpers.fp32_noise_floor): ticks
-    whose rollouts are well conditioned must agree to 2e-5, the chaotic ones (H = 100, 256 samples: floor 1.6e-5) are
-    held to a multiple of the reference's own rounding noise.  Over 60 random states both CUDA rollout kernels reach
-    7e-5..8e-5 on that configuration while their distance to the float64 truth (4.5e-5 max) is within 2 x the
-    reference's (2.7e-5 max); CEM elite index SETS identical;
+  * the north-star bound itself -- state (u, u_nom / dist_mue, stdev / Q) within 1e-5, HARD -- on every tick of the fixtures
+    whose path is well conditioned (HARD_1E5 below: C1 at N = 2000, every CEM fixture incl. C2, the MLP fixtures incl. the C4
+    geometry, ...; measured <= 4e-6) and, in test_gpu_production_pinning.py, at the full BASELINE sizes C1 / C2 / C4 / C5;
+  * on the chaotic fixtures (N = 64, H = 100 with 256 samples, RPGD's 50-step gradients: the reference's OWN
+    |fp32 - float64| deviation on that very tick, floor_t from tests/helpers.fp32_noise_floor, is 0.5e-5 .. 1.8e-5) the
+    exception is explicit and symmetric: |cuda - float64 truth| <= max(1e-5, 2 x floor_t) -- the CUDA path is as close to exact
+    arithmetic as the reference's own fp32 evaluation is, up to a factor 2 -- and |cuda - reference fp32| <= max(2e-5,
+    6 x floor_t) capped at 1e-4; CEM elite index SETS identical;
   * statistically (test_mppi_error_distribution): median < 1e-5, >= 60 % of ticks < 1e-5, max < 6e-5;
   * per-rollout cost J (a logged diagnostic), element-wise relative: 99 % of the rollouts within 1e-4 + 3 x the
     reference's own q99 fp32 floor, the worst within 1e-3 + 10 x its max floor.
@@ -40,9 +42,25 @@ TOL_TRAJ = 1e-4  # logged trajectories, relative to the component scale
 TOL_STATE_HARD = 5e-5
 
 
-def _tols(floor):
+# fixtures on which the north-star tolerance (1e-5 relative on u and the optimizer state) is asserted as is, on every tick
+HARD_1E5 = {"mppi_c1_n2000", "mppi_lbd1_n512", "mppi_h43_p10_n64", "mppi_h20_p1_n96", "mppi_mlp_c4_n256", "mppi_mlp_h50_n64",
+            "cem_c2_n256_k16", "cem_c2_n4096_k64", "cem_warmup_n128", "rpgd_normal_shift2"}
+
+
+def _tols(floor, name=None):
+    if name in HARD_1E5:
+        return TOL_STATE, TOL_STATE, TOL_COST + 2 * floor["J"]
     tol = min(max(2e-5, 6.0 * floor["state"]), 1e-4)
     return tol, tol, TOL_COST + 2 * floor["J"]
+
+
+def _assert_symmetric(state_cuda, floor, tag):
+    """|cuda - float64 truth| <= max(1e-5, 2 x |reference fp32 - float64 truth|) on this tick (same scale as the floor)."""
+    truth = floor["state64"].ravel()
+    scale = max(float(np.max(np.abs(truth))), 1e-30)
+    e64 = float(np.max(np.abs(np.asarray(state_cuda, np.float64).ravel() - truth))) / scale
+    _report(f"{tag}: |cuda - float64 truth| {e64:.2e} vs reference's own {floor['state']:.2e}")
+    assert e64 <= max(TOL_STATE, 2.0 * floor["state"]), (tag, e64, floor["state"])
 
 
 def _check_J(J, J_ref, floor, tag):
@@ -84,7 +102,7 @@ def test_mppi_matches_reference_golden(name):
     floors = fp32_noise_floor(name)
     for t in range(meta["ticks"]):
         u = ctrl.step(z["states"][t], time=0.02 * t)
-        tol_s, tol_u, tol_J = _tols(floors[t])
+        tol_s, tol_u, tol_J = _tols(floors[t], name)
         e_u = _u_err(u, z[f"u_{t}"], z[f"u_nom_{t}"])
         e_nom = max_rel(opt.u_nom, z[f"u_nom_{t}"])
         e_J = max_elem_rel(opt.logging_values["J_logged"], z[f"J_{t}"])
@@ -92,6 +110,7 @@ def test_mppi_matches_reference_golden(name):
                 f"state {floors[t]['state']:.2e} J {floors[t]['J']:.2e}")
         assert np.ndim(u) == 0  # reference optimizer_mppi.py:212 squeezes to 0-d
         assert e_u < tol_u and e_nom < tol_s, (name, t, e_u, e_nom, floors[t])
+        _assert_symmetric(opt.u_nom, floors[t], f"{name} tick {t}")
         _check_J(opt.logging_values["J_logged"], z[f"J_{t}"], floors[t], (name, t))
         if t == 0 and "rollouts_0" in z:
             # injected noise -> sampled controls are bit-exact up to the interpolation matmul's rounding
@@ -118,7 +137,7 @@ def test_mppi_mlp_tcgen05_matches_reference_golden(name):
     for t in range(meta["ticks"]):
         u = ctrl.step(z["states"][t], time=0.02 * t)
         u_s = simt.step(z["states"][t], time=0.02 * t)
-        tol_s, tol_u, _ = _tols(floors[t])
+        tol_s, tol_u, _ = _tols(floors[t], name)
         e_u = _u_err(u, z[f"u_{t}"], z[f"u_nom_{t}"])
         e_nom = max_rel(opt.u_nom, z[f"u_nom_{t}"])
         e_simt = max_rel(opt.u_nom, simt.optimizer.u_nom)
@@ -139,7 +158,7 @@ def test_cem_matches_reference_golden(name):
     floors = fp32_noise_floor(name)
     for t in range(meta["ticks"]):
         u = ctrl.step(z["states"][t], time=0.02 * t)
-        tol_s, tol_u, tol_J = _tols(floors[t])
+        tol_s, tol_u, tol_J = _tols(floors[t], name)
         ref_elite = z[f"elite_idx_{t}"]
         got_elite = opt.elite_indices
         assert got_elite.shape == ref_elite.shape
@@ -156,6 +175,7 @@ def test_cem_matches_reference_golden(name):
         _report(f"{name} tick {t}: u {e_u:.2e} mu {e_mu:.2e} sd {e_sd:.2e} J {e_J:.2e} | fp32 floor: state "
                 f"{floors[t]['state']:.2e} J {floors[t]['J']:.2e}")
         assert e_u < tol_u and e_mu < tol_s and e_sd < tol_s, (name, t, e_u, e_mu, e_sd)
+        _assert_symmetric(opt.dist_mue, floors[t], f"{name} tick {t}")
         _check_J(J, z[f"J_{t}"], floors[t], (name, t))
         # the device top-k applied to the device's own costs must equal a stable argsort (bit-exact index work)
         np.testing.assert_array_equal(got_elite[-1], np.argsort(J, kind="stable")[:k])
@@ -205,17 +225,36 @@ def test_cem_edge_geometries_match_oracle(N, H, k, iters):
     for t, s0 in enumerate(spec.synthetic_states(3, seed=22)):
         u = ctrl.step(s0)
         uo = o.step(s0, rng)
-        gap = np.sort(o.last["J"])[min(k, N - 1)] - np.sort(o.last["J"])[k - 1] if N > k else np.inf
-        same_set = set(ctrl.optimizer.elite_indices[-1].tolist()) == set(np.asarray(o.last["elite_idx"][-1]).tolist())
+        Jd = np.asarray(ctrl.optimizer.logging_values["J_logged"], np.float32)
+        dev_all, orc_all = ctrl.optimizer.elite_indices, np.asarray(o.last["elite_idx"])
+        differ = [it for it in range(iters) if set(dev_all[it].tolist()) != set(orc_all[it].tolist())]
+        same_set = not differ
         e_mu = max_rel(ctrl.optimizer.dist_mue, o.dist_mue.numpy(), floor=1e-2)
         e_sd = max_rel(ctrl.optimizer.stdev, o.stdev.numpy(), floor=1e-2)
-        _report(f"cem edge N={N} H={H} k={k} it={iters} tick {t}: mu {e_mu:.2e} sd {e_sd:.2e} same_set {same_set} gap {gap:.2e}")
-        assert same_set or gap < 1e-4 * abs(np.sort(o.last["J"])[k - 1])  # identical unless the k / k+1 costs are within fp32 noise
+        _report(f"cem edge N={N} H={H} k={k} it={iters} tick {t}: mu {e_mu:.2e} sd {e_sd:.2e} same_set {same_set}")
+        # index work is bit-exact on the device's OWN costs: ties broken by index (tf.argsort == top_k(-x) semantics)
+        np.testing.assert_array_equal(dev_all[-1], np.argsort(Jd, kind="stable")[:k])
         if same_set:
             assert e_mu < 1e-4 and e_sd < 1e-4, (N, H, k, t, e_mu, e_sd)
             assert abs(float(u) - float(np.ravel(uo)[0])) < 1e-5
         else:
-            break  # the distributions legitimately diverge after a noise-level elite swap
+            # The ONLY admissible difference: in the FIRST outer iteration whose elite sets differ, the members in question tie with
+            # the k-th cost in the ORACLE's own fp32 costs to within a few ulp.  It happens at H = 1: the cost is dominated by the
+            # state terms of s0 (~1e4), several samples differ only in their control terms (~1), whose contribution is below the
+            # ulp of the sum -- the oracle's left-to-right fp32 sum rounds them to EXACTLY equal costs (index decides), while the
+            # device's merged-FMA form u (kA u + kB u_prev) keeps them an ulp apart (cost decides).  No fp32 implementation with
+            # another summation order can reproduce such a tie.
+            it = differ[0]
+            Jo = np.asarray(o.last["J_iters"][it], np.float32)
+            order = np.argsort(Jo, kind="stable")
+            Jk = float(Jo[order[k - 1]])
+            ulp = float(np.spacing(np.float32(abs(Jk))))
+            lo, hi = max(k - 3, 0), min(k + 3, N)
+            _report(f"  first differing iteration {it}: oracle ranks {lo}..{hi - 1}: idx {order[lo:hi].tolist()} J {[float(x) for x in Jo[order[lo:hi]]]} "
+                    f"(ulp at J_k = {ulp:.3e}); device elite {sorted(dev_all[it].tolist())} oracle elite {sorted(orc_all[it].tolist())}")
+            for i in set(dev_all[it].tolist()) ^ set(orc_all[it].tolist()):
+                assert abs(float(Jo[i]) - Jk) <= 4 * ulp, (N, H, k, t, it, i, float(Jo[i]), Jk, ulp)
+            break  # the distributions legitimately diverge after an ulp-level elite swap
 
 
 @pytest.mark.parametrize("N,H,over", [(1, 9, {}), (33, 2, {"resamp_per": 1}), (40, 31, {"shift_previous": 0, "outer_its": 1}),
@@ -505,7 +544,7 @@ def test_gradient_matches_reference_golden(name):
     floors = fp32_noise_floor(name)
     for t in range(meta["ticks"]):
         u = ctrl.step(z["states"][t], time=0.02 * t)
-        tol_s, tol_u, tol_J = _tols(floors[t])
+        tol_s, tol_u, tol_J = _tols(floors[t], name)
         step, m, v = opt.adam_weights()
         e_u = max_rel(u, z[f"u_{t}"], floor=1.0)
         e_Q = max_rel(opt.Q_tf, z[f"Q_{t}"])
@@ -565,7 +604,7 @@ def test_rpgd_matches_reference_golden(name):
     floors = fp32_noise_floor(name)
     for t in range(meta["ticks"]):
         u = ctrl.step(z["states"][t], time=0.02 * t)
-        tol_s, tol_u, tol_J = _tols(floors[t])
+        tol_s, tol_u, tol_J = _tols(floors[t], name)
         step, m, v = opt.adam_weights()
         e_u = _u_err(u, z[f"u_{t}"], z[f"Q_{t}"])
         e_Q = max_rel(opt.Q_tf, z[f"Q_{t}"])
@@ -579,6 +618,7 @@ def test_rpgd_matches_reference_golden(name):
         assert step == int(z[f"adam_step_{t}"][0])
         np.testing.assert_array_equal(opt.trajectory_ages, z[f"ages_{t}"])
         assert e_u < tol_u and e_Q < tol_s and e_un < tol_s, (name, t, e_u, e_Q, e_un, floors[t])
+        _assert_symmetric(opt.Q_tf, floors[t], f"{name} tick {t}")
         # Adam moments are raw gradient statistics (no normalisation): gradients through 50 unstable steps carry
         # ~10x the relative rounding noise of the states
         assert e_m < 10 * tol_s and e_v < 10 * tol_s, (name, t, e_m, e_v)

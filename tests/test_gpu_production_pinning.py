@@ -1,0 +1,250 @@
+"""-m gpu: the PRODUCTION kernel instantiations -- in-kernel Philox noise, segment-unrolled PERIOD = 10, two rollouts per thread,
+the FAST persistent CEM tick, the one-launch RPGD tick, the tcgen05 MLP engine -- pinned to the oracle at the BASELINE sizes.
+
+The golden / injected-noise tests (test_gpu_parity.py) run ``mppi_ode_kernel<KIND,LOG,0,1,1024,1>`` (runtime period, one rollout
+per thread, injected-noise branch); bench.py times ``mppi_ode_kernel<0,0,10,2,1024,0>``.  Here the optimizer runs with
+``rng = None`` (the production path), the standard draws the kernels generated are exported with ``ctk_philox_export`` (same key,
+counter words and device function) and replayed through the oracle's rng (``oracle.replay_rng.QueueRNG``), so both sides consume
+identical numbers.  Every test asserts ``optimizer.last_kernel`` -- the instantiation that actually ran.
+
+Tolerances: north star 1e-5 relative on u / optimizer state, asserted HARD wherever the path is well conditioned (C1, C2, C4, C5);
+where the reference's own fp32-vs-float64 deviation on that very tick (floor) is larger, the symmetric criterion
+|cuda - float64 truth| <= max(1e-5, 2 x |reference fp32 - float64 truth|) is asserted instead (see test_gpu_parity.py docstring).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from gpu_helpers import make_controller, max_rel
+from helpers import load_golden, make_oracle
+from test_gpu_parity import _check_J, _report
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _oracles(meta, **over):
+    import torch
+    from oracle import spec
+    o32, o64 = make_oracle(meta, **over), make_oracle(meta, dtype=torch.float64, **over)
+    if meta["predictor"].startswith("Dense"):
+        o64.predictor = spec.MLPPredictor(spec.MLPWeights.random_init(meta["mlp_seed"]), dtype=torch.float64)
+    return o32, o64
+
+
+def _J_floor(J32, J64):
+    e = np.abs(np.asarray(J32, np.float64) - np.asarray(J64, np.float64)) / (np.abs(np.asarray(J64, np.float64)) + 1e-3)
+    return {"J": float(e.max()), "J_q99": float(np.quantile(e, 0.99))}
+
+
+def _state_errs(cuda, ref32, ref64):
+    scale = max(float(np.max(np.abs(ref64))), 1e-2)
+    d = lambda a, b: float(np.max(np.abs(np.asarray(a, np.float64).ravel() - np.asarray(b, np.float64).ravel()))) / scale  # noqa: E731
+    return d(cuda, ref32), d(cuda, ref64), d(ref32, ref64)
+
+
+def _assert_state(tag, e32, e64, floor, hard):
+    _report(f"{tag}: |cuda-ref32| {e32:.2e} |cuda-f64| {e64:.2e} | floor |ref32-f64| {floor:.2e}")
+    if hard:
+        assert e32 < TOL, (tag, e32, e64, floor)
+    else:
+        assert e32 < min(max(2e-5, 6.0 * floor), 1e-4), (tag, e32, floor)
+    assert e64 <= max(TOL, 2.0 * floor), (tag, "distance to the float64 truth", e64, floor)
+
+
+MPPI_CASES = [
+    # id, fixture for the config, N, H, period, env, expected kernel, ticks, hard 1e-5
+    ("c1", "mppi_c1_n2000", 2000, 50, 10, {}, "mppi_ode_kernel<0,0,10,1,1024,0>", 3, True),
+    ("c1_ilp2", "mppi_c1_n2000", 2000, 50, 10, {"CTK_K1_ILP": "2"}, "mppi_ode_kernel<0,0,10,2,1024,0>", 3, True),
+    ("c1_period7", "mppi_c1_n2000", 2000, 50, 7, {"CTK_K1_ILP": "2"}, "mppi_ode_kernel<0,0,0,2,1024,0>", 2, True),
+    ("h100_ragged", "mppi_h100_n256", 30011, 97, 10, {"CTK_K1_ILP": "2"}, "mppi_ode_kernel<0,0,10,2,1024,0>", 2, True),
+    ("c5_1m", "mppi_h100_n256", 1_000_000, 100, 10, {}, "mppi_ode_kernel<0,0,10,2,1024,0>", 2, True),
+]
+
+
+@pytest.mark.parametrize("cid,fixture,N,H,period,env,kernel,ticks,hard", MPPI_CASES, ids=[c[0] for c in MPPI_CASES])
+def test_mppi_production_kernel_matches_oracle(monkeypatch, cid, fixture, N, H, period, env, kernel, ticks, hard):
+    """BASELINE configs[0] and configs[4] (10^6 x 100, FULL size) on the instantiation bench.py times (north star: Q and optimizer
+    state within 1e-5; reference optimizer_mppi.py:170-193)."""
+    from control_toolkit_b200 import _lib as L
+    from oracle import spec
+    from oracle.replay_rng import QueueRNG
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    _, meta = load_golden(fixture)
+    meta = dict(meta, cfg=dict(meta["cfg"], num_rollouts=N, mpc_horizon=H, period_interpolation_inducing_points=period))
+    ctrl = make_controller(meta, rng=None, logging=False)
+    opt = ctrl.optimizer
+    assert opt.rng is None
+    o32, o64 = _oracles(meta)
+    n_ind = opt.number_of_interpolation_inducing_points
+    for t, s in enumerate(spec.synthetic_states(ticks, seed=31)):
+        u = ctrl.step(s)
+        assert opt.last_kernel == kernel, opt.last_kernel
+        z = opt.export_philox(L.STREAM_MPPI, opt.tick_counter, n_ind, N)
+        u32 = o32.step_chunked(s, QueueRNG([z]))
+        o64.step_chunked(s, QueueRNG([z]))
+        e32, e64, floor = _state_errs(opt.u_nom, o32.u_nom.numpy(), o64.u_nom.numpy())
+        _assert_state(f"production mppi {cid} N={N} H={H} p={period} [{opt.last_kernel}] tick {t} u_nom", e32, e64, floor, hard)
+        assert abs(float(u) - float(np.ravel(u32)[0])) < (TOL if hard else 1e-4) * max(float(np.abs(o32.u_nom.numpy()).max()), 1e-2)
+        J = opt._get_log(L.LOG_J, (N,))
+        _check_J(J, o32.last["J"], _J_floor(o32.last["J"], o64.last["J"]), (f"production mppi {cid}", t))
+
+
+def test_mppi_production_logging_kernel_matches_oracle():
+    """optimizer_logging on with in-kernel noise: mppi_ode_kernel<0,1,10,...,0> (the HBM-write-bound workload of bench.py
+    --workload mppi_ode_1m_log) -- logged controls / trajectories against the oracle on the exported draws."""
+    from control_toolkit_b200 import _lib as L
+    from oracle import spec
+    from oracle.replay_rng import QueueRNG
+    _, meta = load_golden("mppi_c1_n2000")
+    N, H = 4000, 50
+    meta = dict(meta, cfg=dict(meta["cfg"], num_rollouts=N, mpc_horizon=H))
+    ctrl = make_controller(meta, rng=None, logging=True)
+    opt = ctrl.optimizer
+    o32, o64 = _oracles(meta)
+    for t, s in enumerate(spec.synthetic_states(2, seed=32)):
+        ctrl.step(s)
+        assert opt.last_kernel == "mppi_ode_kernel<0,1,10,1,1024,0>", opt.last_kernel
+        z = opt.export_philox(L.STREAM_MPPI, opt.tick_counter, opt.number_of_interpolation_inducing_points, N)
+        o32.step(s, QueueRNG([z]))
+        o64.step(s, QueueRNG([z]))
+        e32, e64, floor = _state_errs(opt.u_nom, o32.u_nom.numpy(), o64.u_nom.numpy())
+        _assert_state(f"production mppi logging tick {t} u_nom", e32, e64, floor, True)
+        e_Q = max_rel(opt.logging_values["Q_logged"], o32.last["Q"])
+        e_tr = max(max_rel(opt.logging_values["rollout_trajectories_logged"][..., c], o32.last["rollouts"][..., c]) for c in range(6))
+        _report(f"production mppi logging tick {t}: Q_logged {e_Q:.2e} rollouts {e_tr:.2e}")
+        assert e_Q < 1e-6 and e_tr < 1e-4
+
+
+@pytest.mark.parametrize("engine,kernel", [("tcgen05", "mppi_rollout_kernel<MlpTcPred,0,0> [philox]"), ("simt", "mppi_rollout_kernel<MlpSimtPred,0,0> [philox]")])
+def test_mppi_mlp_c4_full_size_matches_oracle(engine, kernel):
+    """BASELINE configs[3] at FULL size (65 536 rollouts x horizon 100, 2 x 128 tanh MLP) with in-kernel noise, the dense layer on
+    the tensor cores (tcgen05) -- and the FP32-pipe engine on a quarter of the population (it needs ~45 ms per full tick)."""
+    from control_toolkit_b200 import _lib as L
+    from oracle import spec
+    from oracle.replay_rng import QueueRNG
+    _, meta = load_golden("mppi_mlp_c4_n256")
+    N, H = (65536, 100) if engine == "tcgen05" else (16384, 100)
+    meta = dict(meta, cfg=dict(meta["cfg"], num_rollouts=N, mpc_horizon=H))
+    ctrl = make_controller(meta, rng=None, logging=False, mlp_engine=engine)
+    opt = ctrl.optimizer
+    o32, o64 = _oracles(meta)
+    for t, s in enumerate(spec.synthetic_states(2, seed=33)):
+        u = ctrl.step(s)
+        assert opt.last_kernel == kernel, opt.last_kernel
+        z = opt.export_philox(L.STREAM_MPPI, opt.tick_counter, opt.number_of_interpolation_inducing_points, N)
+        u32 = o32.step_chunked(s, QueueRNG([z]), chunk=16384)
+        o64.step_chunked(s, QueueRNG([z]), chunk=16384)
+        e32, e64, floor = _state_errs(opt.u_nom, o32.u_nom.numpy(), o64.u_nom.numpy())
+        _assert_state(f"production mppi C4 {engine} N={N} tick {t} u_nom", e32, e64, floor, True)
+        assert abs(float(u) - float(np.ravel(u32)[0])) < TOL
+        _check_J(opt._get_log(L.LOG_J, (N,)), o32.last["J"], _J_floor(o32.last["J"], o64.last["J"]), (f"production mppi C4 {engine}", t))
+
+
+CEM_CASES = [
+    ("c2_persistent_fast", 4096, 50, 64, 3, {}, "cem_tick_kernel<0,0,1>"),
+    ("c2_multi_launch", 4096, 50, 64, 3, {"CTK_CEM_MULTI_LAUNCH": "1"}, "cem_ode_kernel<0,0> [philox]"),
+    ("ragged_persistent_fast", 9001, 37, 100, 2, {}, "cem_tick_kernel<0,0,1>"),
+    ("large_multi_launch", 200_000, 30, 64, 2, {}, "cem_ode_kernel<0,0> [philox]"),
+]
+
+
+@pytest.mark.parametrize("cid,N,H,k,iters,env,kernel", CEM_CASES, ids=[c[0] for c in CEM_CASES])
+def test_cem_production_kernels_match_oracle(monkeypatch, cid, N, H, k, iters, env, kernel):
+    """BASELINE configs[1] on the production instantiation (persistent one-launch tick with the straight-line Philox draws,
+    cem_tick_kernel<.,.,FAST = true>) and on the multi-launch path: elite index sets of EVERY outer iteration identical to the
+    oracle's stable argsort, distribution within 1e-5 (reference optimizer_cem_tf.py:54-80,99-102)."""
+    from control_toolkit_b200 import _lib as L
+    from oracle import spec
+    from oracle.replay_rng import QueueRNG
+    for kk, v in env.items():
+        monkeypatch.setenv(kk, v)
+    _, meta = load_golden("cem_c2_n4096_k64")
+    meta = dict(meta, cfg=dict(meta["cfg"], num_rollouts=N, mpc_horizon=H, cem_best_k=k, cem_outer_it=iters))
+    ctrl = make_controller(meta, rng=None, logging=False)
+    opt = ctrl.optimizer
+    o32, o64 = _oracles(meta)
+    for t, s in enumerate(spec.synthetic_states(3, seed=34)):
+        u = ctrl.step(s)
+        assert opt.last_kernel == kernel, opt.last_kernel
+        blocks = [opt.export_philox(L.STREAM_CEM, opt.tick_counter, H, N, sub=it) for it in range(iters)]
+        u32 = o32.step(s, QueueRNG(blocks))
+        o64.step(s, QueueRNG(blocks))
+        got, ref = opt.last_elite_indices(iters), np.asarray(o32.last["elite_idx"])
+        for it in range(iters):
+            same_set = set(got[it].tolist()) == set(ref[it].tolist())
+            _report(f"production cem {cid} tick {t} it {it}: elite set identical {same_set} order identical {bool(np.array_equal(got[it], ref[it]))}")
+            assert same_set, (cid, t, it, sorted(set(got[it].tolist()) ^ set(ref[it].tolist())))
+        for nm, a, b32, b64 in (("mu", opt.dist_mue, o32.dist_mue, o64.dist_mue), ("sd", opt.stdev, o32.stdev, o64.stdev)):
+            e32, e64, floor = _state_errs(a, b32.numpy(), b64.numpy())
+            _assert_state(f"production cem {cid} [{opt.last_kernel}] tick {t} {nm}", e32, e64, floor, True)
+        assert abs(float(u) - float(np.ravel(u32)[0])) < TOL
+        J = opt.last_costs()
+        _check_J(J, o32.last["J"], _J_floor(o32.last["J"], o64.last["J"]), (f"production cem {cid}", t))
+        np.testing.assert_array_equal(got[-1], np.argsort(J, kind="stable")[:k])  # ties broken by index on the device's own costs
+
+
+@pytest.mark.parametrize("adam_form", ["torch", "keras"])
+def test_rpgd_production_one_launch_tick_matches_oracle(adam_form):
+    """BASELINE configs[2] (32 trajectories, H = 50) with in-kernel noise: the one-launch tick (coefficient-form adjoint + Adam +
+    select / resample fused) against the oracle on the exported initial population and resampling draws
+    (reference optimizer_rpgd.py:306-380,443-516,527-548)."""
+    from control_toolkit_b200 import _lib as L
+    from oracle import spec
+    from oracle.replay_rng import QueueRNG
+    _, meta = load_golden("rpgd_c3")
+    ctrl = make_controller(meta, rng=None, logging=False, adam_form=adam_form)
+    opt = ctrl.optimizer
+    N, H, k, n_ind = opt.num_rollouts, opt.mpc_horizon, opt.opt_keep_k, opt.number_of_interpolation_inducing_points
+    uni = opt.SAMPLING_DISTRIBUTION == "uniform"
+    o32, o64 = _oracles(meta, adam_form=adam_form)
+    z0 = opt.export_philox(L.STREAM_RPGD_INIT, opt.tick_counter, n_ind, N, uniform=uni)
+    o32.reset(QueueRNG([z0]))
+    o64.reset(QueueRNG([z0]))
+    assert max_rel(opt.Q_tf, o32.Q.numpy()) < 1e-6
+    launches0 = opt.gpu_launches
+    for t, s in enumerate(spec.synthetic_states(12, seed=35)):
+        resample = opt.count % opt.resamp_per == 0
+        u = ctrl.step(s)
+        blocks = [opt.export_philox(L.STREAM_RPGD_RESAMPLE, opt.tick_counter, n_ind, N - k, uniform=uni)] if resample else []
+        u32 = o32.step(s, QueueRNG(blocks))
+        o64.step(s, QueueRNG(blocks))
+        np.testing.assert_array_equal(opt.best_indices(), o32.last["best_idx"])
+        e32, e64, floor = _state_errs(opt.Q_tf, o32.Q.numpy(), o64.Q.numpy())
+        _assert_state(f"production rpgd {adam_form} tick {t} Q", e32, e64, floor, False)
+        _, m, v = opt.adam_weights()
+        em, ev = max_rel(m, o32.m.numpy(), floor=1e-3), max_rel(v, o32.v.numpy(), floor=1e-3)
+        fm, fv = max_rel(o32.m.numpy(), o64.m.numpy(), floor=1e-3), max_rel(o32.v.numpy(), o64.v.numpy(), floor=1e-3)
+        _report(f"production rpgd {adam_form} tick {t}: m {em:.2e} (floor {fm:.2e}) v {ev:.2e} (floor {fv:.2e})")
+        assert em < max(1e-4, 10 * fm) and ev < max(1e-4, 10 * fv)
+        assert np.max(np.abs(np.ravel(u) - np.ravel(u32))) < 1e-4
+    assert opt.gpu_launches - launches0 == 12  # one launch per tick
+
+
+def test_philox_export_is_what_the_kernels_draw():
+    """ctk_philox_export against the logged controls of a Philox tick: Q_logged = clip(shift(u_nom) + interp(z) * stdev) must be
+    reproduced from the exported z to fp32 rounding (the export uses the same counters, key and device function)."""
+    from control_toolkit_b200 import _lib as L
+    from oracle.mppi import interpolation_matrix
+    _, meta = load_golden("mppi_c1_n64")
+    N, H = 777, 50
+    meta = dict(meta, cfg=dict(meta["cfg"], num_rollouts=N, mpc_horizon=H))
+    ctrl = make_controller(meta, rng=None, logging=True)
+    opt = ctrl.optimizer
+    s = np.array([0.3, -0.2, np.cos(0.3), np.sin(0.3), 0.01, 0.0], np.float32)
+    u_nom_before = opt.u_nom.copy()
+    ctrl.step(s)
+    z = opt.export_philox(L.STREAM_MPPI, opt.tick_counter, opt.number_of_interpolation_inducing_points, N)
+    assert abs(float(z.mean())) < 0.05 and abs(float(z.std()) - 1.0) < 0.05
+    W = interpolation_matrix(H, 10)  # [n_ind, H]
+    du = (z * np.float32(opt.SQRTRHODTINV)) @ W
+    shifted = np.concatenate([u_nom_before[0, 1:, 0], u_nom_before[0, -1:, 0]])
+    Q = np.clip(shifted[None, :] + du, -1.0, 1.0)
+    assert np.max(np.abs(opt.logging_values["Q_logged"][..., 0] - Q)) < 1e-6
+    # a different tick / stream / row offset gives different numbers; the same arguments the same numbers
+    z2 = opt.export_philox(L.STREAM_MPPI, opt.tick_counter, opt.number_of_interpolation_inducing_points, 100, row0=50)
+    np.testing.assert_array_equal(z2, z[50:150])
+    assert not np.array_equal(opt.export_philox(L.STREAM_MPPI, opt.tick_counter + 1, 6, 100), z[:100])
