@@ -113,7 +113,7 @@ class optimizer_cem_naive_grad_tf(template_optimizer):
         lib = self._require_backend()
         L.check(lib.ctk_reset(self._h))
         self.count = 0
-        self.u = 0.0
+        # self.u (the cost's previous_input) survives optimizer_reset() in the reference: only optimizer_cem_tf.py:117 resets it
 
     # reference attributes, read from the device on demand
     @property

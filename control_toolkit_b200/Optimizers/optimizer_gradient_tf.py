@@ -104,7 +104,7 @@ class optimizer_gradient_tf(template_optimizer):
         self._feed_noise(lib, [("uniform", (self.num_rollouts, self.mpc_horizon, self.num_control_inputs))])  # :171-176
         L.check(lib.ctk_reset(self._h))
         self.count = 0
-        self.u = 0.0
+        # self.u (the cost's previous_input) survives optimizer_reset() in the reference: only optimizer_cem_tf.py:117 resets it
 
     # reference attributes, read from the device on demand
     @property

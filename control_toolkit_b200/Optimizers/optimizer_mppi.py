@@ -103,7 +103,7 @@ class optimizer_mppi(template_optimizer):
     def optimizer_reset(self):
         lib = self._require_backend()
         L.check(lib.ctk_reset(self._h))
-        self.u = 0.0
+        # self.u (the cost's previous_input) survives optimizer_reset() in the reference: only optimizer_cem_tf.py:117 resets it
         self.u_nom = self._get_state(L.STATE_U_NOM, (1, self.mpc_horizon, self.num_control_inputs))
 
     # state access (part of the parity contract: "optimizer state within 1e-5")

@@ -78,7 +78,7 @@ class optimizer_random_action_tf(template_optimizer):
     def optimizer_reset(self):
         lib = self._require_backend()
         L.check(lib.ctk_reset(self._h))
-        self.u = 0.0
+        # self.u (the cost's previous_input) survives optimizer_reset() in the reference: only optimizer_cem_tf.py:117 resets it
         if self.rng is not None:  # the reference draws (and discards) one population here (:78-87): keep a replay rng in step
             self.rng.standard_draws(*self._population_block())
 

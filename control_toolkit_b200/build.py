@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libctk_b200.so")
-UNITS = ["ctk_engine.cu", "ctk_mppi.cu", "ctk_cem.cu", "ctk_rpgd.cu", "ctk_mlp_tc.cu"]
+UNITS = ["ctk_engine.cu", "ctk_mppi.cu", "ctk_cem.cu", "ctk_rpgd.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-I", INCLUDE, "-I", CSRC] + os.environ.get("CTK_NVCC_EXTRA", "").split()  # e.g. -DCTK_TC_TRACE (diagnostics)
 
@@ -57,7 +57,10 @@ def _compile(unit: str, verbose: bool) -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    units = [u for u in UNITS if os.path.exists(os.path.join(CSRC, u))]
+    units = list(UNITS)
+    missing = [u for u in units if not os.path.exists(os.path.join(CSRC, u))]
+    if missing:
+        raise RuntimeError(f"translation units listed in build.py but not in csrc/: {missing}")
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "digest.txt")
     digest = _sources_digest()

@@ -53,7 +53,8 @@ __device__ __forceinline__ void host_put(const HostMirror& m, int slot, float v)
 // K0: Philox4x32-10 (Salmon et al. 2011), the generator behind tf.random.Generator.from_seed
 // (reference others/globals_and_utils.py:95-97).  Counter words: (draw block, global rollout id, tick, stream).
 // TF's exact stream cannot be reproduced offline, so parity is defined under injected noise only; this
-// generator is validated statistically (tests/test_philox.py) and against a numpy Philox restatement.
+// generator is validated statistically (tests/test_gpu_parity.py::test_philox_statistics_and_determinism); the production kernels are
+// pinned to the oracle on the EXPORTED draws (ctk_philox_export, tests/test_gpu_production_pinning.py).
 // ----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -142,6 +143,7 @@ static cudaError_t dalloc(T** p, size_t n) {
 static void mppi_ode_geometry(ctk_handle* h);
 static int pred_id(const ctk_handle* h);
 static cudaError_t upload_consts(ctk_handle* h) {
+  h->cem_tick_per_sm = -1;  // the cost kind selects the persistent tick's instantiation (register count): re-query its occupancy
   if (h->cfg.optimizer == CTK_OPT_MPPI) {
     const ctk_config& c = h->cfg;
     MppiCorr mc{(double)c.mppi_cc_weight, (double)c.mppi_coef_du2, (double)c.mppi_R, (double)c.mppi_half_R,
@@ -238,6 +240,10 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
           cfg->rollout_offset + cfg->num_rollouts <= cfg->num_rollouts_global, "bad shard geometry");
   REQ(cost->kind == CTK_COST_DEFAULT || cost->kind == CTK_COST_QUADRATIC_BOUNDARY_GRAD, "unregistered cost function");
   REQ(cfg->action_low <= cfg->action_high, "action_low > action_high");
+  if (cfg->optimizer == CTK_OPT_RPGD) {
+    REQ(cfg->rpgd_resamp_per >= 1 || cfg->rpgd_gradient_mode != 0, "rpgd_resamp_per must be >= 1");
+    REQ(cfg->rpgd_outer_its >= 0 && cfg->rpgd_first_iter_count >= 0, "RPGD iteration counts must be >= 0");
+  }
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
   REQ(cfg->device >= 0 && cfg->device < ndev, "no such CUDA device");
@@ -486,7 +492,9 @@ extern "C" int ctk_reset(ctk_handle* h) {
   CU(cudaSetDevice(h->cfg.device));
   const float mid = 0.5f * (h->cfg.action_low + h->cfg.action_high);
   std::vector<float> tmp((size_t)h->H, mid);
-  CU(cudaMemsetAsync(h->d_u_prev, 0, sizeof(float), h->stream));  // self.u = 0.0 (Optimizers/__init__.py:35)
+  // self.u, the previous_input of the cost, is reset ONLY by optimizer_cem_tf.optimizer_reset (optimizer_cem_tf.py:117); MPPI (:227-231),
+  // RPGD (:527-548), random-action, gradient-tf and the gradient-assisted CEM variants keep the last applied control
+  if (h->cfg.optimizer == CTK_OPT_CEM && !h->cfg.cem_uniform_actions) CU(cudaMemsetAsync(h->d_u_prev, 0, sizeof(float), h->stream));
   if (h->cfg.optimizer == CTK_OPT_MPPI) {
     CU(cudaMemcpyAsync(h->d_u_nom, tmp.data(), sizeof(float) * h->H, cudaMemcpyHostToDevice, h->stream));
   } else if (h->cfg.optimizer == CTK_OPT_CEM) {
@@ -720,6 +728,8 @@ static int cem_tick_persistent(ctk_handle* h, const float* s_dev, float* u_out_d
     int rcn = make_noise(h, STREAM_CEM | ((uint32_t)it << 8), h->H, uni, (size_t)h->NG, &ns);
     if (rcn != CTK_OK) return rcn;
     if (it == 0) a.noise = ns;
+    else if ((ns.inj != nullptr) != (a.noise.inj != nullptr))  // the kernel reads iteration it at inj + it * inj_stride
+      return fail(CTK_EINVAL, "injected-noise queue ran out between the outer iterations of a CEM tick: queue all iterations or none");
     h->cem_noise = ns;
   }
   a.inj_stride = (size_t)h->NG * h->H;
@@ -1076,8 +1086,10 @@ static int wait_host_slots(ctk_handle* h, unsigned int seq, int first, int count
 #if defined(__x86_64__) || defined(__i386__)
       __builtin_ia32_pause();
 #endif
-      if ((++spins & 0x3fffu) != 0) continue;
+      if ((++spins & 0xffu) != 0) continue;
       const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      // short ticks (C1-C3: 15-50 us) are caught by the pause loop; a long one (logging: tens of ms) gives the core away between polls
+      if (el > 100e-6) { struct timespec ts = {0, el > 2e-3 ? 50000 : 5000}; nanosleep(&ts, nullptr); }
       if (el < 0.05) continue;
       const cudaError_t e = cudaStreamQuery(h->stream);  // a faulted or finished stream will never publish
       if (e == cudaSuccess) {
@@ -1139,7 +1151,13 @@ static int step_host(ctk_handle* h, const float* s_host, float* u_out_host, cons
       CU(cudaStreamSynchronize(h->stream));
     }
   }
-  if (us[1] != 0.0f) return fail(CTK_ECUDA, "cross-GPU exchange timed out: a peer shard did not deliver its record within 2 s");
+  if (us[1] != 0.0f) {
+    if (h->cfg.optimizer == CTK_OPT_CEM)
+      return fail(CTK_ECUDA, "persistent CEM tick: a block of the grid did not publish its candidates / the distribution within 2 s "
+                             "(grid not co-resident? another kernel holding SM slots); set CTK_CEM_MULTI_LAUNCH=1 to use the multi-launch path");
+    if (us[1] == 2.0f) return fail(CTK_ECUDA, "tick finish timed out: a block of this GPU's grid did not publish its softmin record within 2 s");
+    return fail(CTK_ECUDA, "cross-GPU exchange timed out: a peer shard did not deliver its record within 2 s");
+  }
   return CTK_OK;
 }
 

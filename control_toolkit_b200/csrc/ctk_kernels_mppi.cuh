@@ -83,18 +83,19 @@ __device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float*
   if (blockIdx.x != 0) return;
   float* sh_rec = scratch;      // [P]
   float* sh_all = scratch + P;  // [world][P]
-  int status = 0;
+  int status = 0;  // 0 ok, 1 a peer shard's record did not arrive, 2 a block record of this grid did not arrive
   const unsigned long long t0 = globaltimer_ns();
+  int lost = 0;
   if (G * P <= big_floats) {
     for (int i = tid; i < G * P; i += blockDim.x)
-      if (!ld_tagged(f.tagged + i, f.lseq, t0, big + i)) status = 2;
-    __syncthreads();
+      if (!ld_tagged(f.tagged + i, f.lseq, t0, big + i)) lost = 1;
+    if (__syncthreads_or(lost)) status = 2;
     combine_records<false>(big, G, P, neg_inv_lbd, sh_rec, sh_red);
   } else {  // records do not fit in shared memory: wait for all of them, then combine from global memory (low words)
     float dummy;
     for (int i = tid; i < G * P; i += blockDim.x)
-      if (!ld_tagged(f.tagged + i, f.lseq, t0, &dummy)) status = 2;
-    __syncthreads();
+      if (!ld_tagged(f.tagged + i, f.lseq, t0, &dummy)) lost = 1;
+    if (__syncthreads_or(lost)) status = 2;
     combine_records<true>(reinterpret_cast<const float*>(f.tagged), G, P, neg_inv_lbd, sh_rec, sh_red);
   }
   if (f.record_out != nullptr)
@@ -107,12 +108,11 @@ __device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float*
       const int r = i / P, c = i - r * P;
       st_tagged(f.mbox_peer[r] + base + (size_t)f.rank * P + c, sh_rec[c], f.seq);
     }
+    lost = 0;
     for (int i = tid; i < f.world * P; i += blockDim.x)
-      if (!ld_tagged(f.mbox_local + base + i, f.seq, t0, sh_all + i)) status = 1;
-    status = __syncthreads_or(status);
+      if (!ld_tagged(f.mbox_local + base + i, f.seq, t0, sh_all + i)) lost = 1;
+    if (__syncthreads_or(lost) && status == 0) status = 1;
     combine_records<false>(sh_all, f.world, P, neg_inv_lbd, sh_rec, sh_red);
-  } else {
-    status = __syncthreads_or(status);
   }
   // optimizer_mppi.py:190-191: u_nom <- clip(shift(u_nom) + interp(sum_n w_n z_n) * stdev / sum_n w_n)
   const float a = sh_rec[1];

@@ -96,11 +96,17 @@ CASES = {
                                   dict(seed=42, mpc_horizon=30, mpc_timestep=0.02, learning_rate=0.1, adam_beta_1=0.9, adam_beta_2=0.999,
                                        adam_epsilon=1.0e-08, num_rollouts=64, cem_best_k=16, cem_outer_it=3, cem_initial_action_stdev=0.8,
                                        cem_stdev_min=1.e-3, gradmax_clip=3, warmup=True, warmup_iterations=5), 3, False),
+    # controller_reset() in the middle of an episode: only optimizer_cem_tf.optimizer_reset zeroes self.u (optimizer_cem_tf.py:117);
+    # MPPI (:227-231) and RPGD (:527-548) keep the last applied control as the cost's previous_input
+    "mppi_reset_mid_n64": ("mppi", "ODE", "default", _c(MPPI_BASE, num_rollouts=64), 4, False),
+    "rpgd_reset_mid_n32": ("rpgd", "ODE", "quadratic_boundary_grad", _c(RPGD_BASE, resamp_per=2), 5, False),
+    "cem_reset_mid_n128": ("cem-tf", "ODE", "default", _c(CEM_BASE, num_rollouts=128, cem_best_k=8, mpc_horizon=30), 4, False),
     "mppi_mlp_c4_n256": ("mppi", "Dense-6IN-128H1-128H2-5OUT-0", "default",
                          _c(MPPI_BASE, num_rollouts=256, mpc_horizon=100), 2, False),
     "mppi_mlp_h50_n64": ("mppi", "Dense-6IN-128H1-128H2-5OUT-0", "default",
                          _c(MPPI_BASE, num_rollouts=64, mpc_horizon=50), 2, True),
 }
+RESET_BEFORE_TICK = {"mppi_reset_mid_n64": 2, "rpgd_reset_mid_n32": 3, "cem_reset_mid_n128": 2}  # controller_reset() before that tick
 NOISE_SEED = 1
 STATE_SEED = 0
 MLP_SEED = 2
@@ -160,12 +166,14 @@ def run_reference_case(name: str) -> dict:
     states = spec.synthetic_states(ticks, STATE_SEED)
     out = {"config": np.array(json.dumps(dict(case=name, optimizer=opt_name, predictor=pred_spec, cost=cost_name,
                                               cfg=cfg, ticks=ticks, noise_seed=NOISE_SEED, state_seed=STATE_SEED,
-                                              mlp_seed=MLP_SEED))),
+                                              mlp_seed=MLP_SEED, reset_before_tick=RESET_BEFORE_TICK.get(name, -1)))),
            "states": states}
     if opt_name in ("rpgd", "gradient-tf"):
         out["Q_init"] = opt.Q_tf.numpy().copy()
 
     for t in range(ticks):
+        if t == RESET_BEFORE_TICK.get(name, -1):
+            ctrl.controller_reset()  # reference Controllers/controller_mpc.py:108-109
         u = ctrl.step(states[t], time=0.02 * t)
         out[f"u_{t}"] = np.asarray(u, np.float32).reshape(-1)
         lv = opt.logging_values

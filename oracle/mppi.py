@@ -50,12 +50,12 @@ class MPPIOracle:
         self.SQRTRHODTINV = torch.tensor(np.float32(np.array(SQRTRHOINV) * (1 / np.sqrt(mpc_timestep))), dtype=dtype)
         self.low = torch.tensor([action_low], dtype=dtype)
         self.high = torch.tensor([action_high], dtype=dtype)
+        self.u = 0.0  # Optimizers/__init__.py:35 (constructor only)
         self.reset()
 
     def reset(self):
-        # optimizer_mppi.py:227-231
+        # optimizer_mppi.py:227-231: ONLY u_nom is reset; self.u (the previous_input of the cost) keeps the last applied control
         self.u_nom = 0.5 * (self.low + self.high) * torch.ones([1, self.H, 1], dtype=self.dtype)
-        self.u = 0.0
         self.last = {}
 
     def _interpolate(self, y):  # y [N, n_ind, 1] -> [N, H, 1]; Interpolator.py:97-106 (batched matmul per control)

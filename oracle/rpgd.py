@@ -46,6 +46,7 @@ class RPGDOracle:
         self.W = torch.from_numpy(interpolation_matrix(self.H, int(period_interpolation_inducing_points))).to(dtype)
         self.n_ind = self.W.shape[0]
         self.Q = None
+        self.u = np.float32(0.0)  # Optimizers/__init__.py:35 (constructor only; optimizer_reset :527-548 keeps the last applied control)
 
     # -- :275-296 -----------------------------------------------------------------------------------
     def sample_actions(self, rng, batch):
@@ -63,7 +64,6 @@ class RPGDOracle:
         self.count = 0
         self.adam_step, self.m, self.v = 0, None, None
         self.ages = torch.zeros((self.N,), dtype=self.dtype)
-        self.u = np.float32(0.0)
         self.last = {}
 
     def _cost(self, s, Q):  # :298-304

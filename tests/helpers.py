@@ -46,6 +46,15 @@ def replay(meta):
     return ReplayRNG(meta["noise_seed"])
 
 
+def maybe_reset_oracle(o, meta, t, rng):
+    """controller_reset() before tick t of the reset-mid-episode fixtures (oracle side)."""
+    if t == meta.get("reset_before_tick", -1):
+        if meta["optimizer"] in ("mppi", "cem-tf"):
+            o.reset()
+        else:
+            o.reset(rng)
+
+
 def rel_err(a, b):
     a = np.asarray(a, np.float64).ravel()
     b = np.asarray(b, np.float64).ravel()
@@ -91,6 +100,8 @@ def fp32_noise_floor(name, ticks=None, **over):
         o64.reset(r64)
     out = []
     for t in range(ticks):
+        maybe_reset_oracle(o32, meta, t, r32)
+        maybe_reset_oracle(o64, meta, t, r64)
         u32, u64 = o32.step(z["states"][t], r32), o64.step(z["states"][t], r64)
         s32, s64 = oracle_state(o32, meta), oracle_state(o64, meta)
         scale = max(float(np.max(np.abs(s64))), 1e-2)

@@ -43,7 +43,7 @@ TOL_STATE_HARD = 5e-5
 
 
 # fixtures on which the north-star tolerance (1e-5 relative on u and the optimizer state) is asserted as is, on every tick
-HARD_1E5 = {"mppi_c1_n2000", "mppi_lbd1_n512", "mppi_h43_p10_n64", "mppi_h20_p1_n96", "mppi_mlp_c4_n256", "mppi_mlp_h50_n64",
+HARD_1E5 = {"cem_reset_mid_n128", "mppi_c1_n2000", "mppi_lbd1_n512", "mppi_h43_p10_n64", "mppi_h20_p1_n96", "mppi_mlp_c4_n256", "mppi_mlp_h50_n64",
             "cem_c2_n256_k16", "cem_c2_n4096_k64", "cem_warmup_n128", "rpgd_normal_shift2"}
 
 
@@ -101,6 +101,8 @@ def test_mppi_matches_reference_golden(name):
     opt = ctrl.optimizer
     floors = fp32_noise_floor(name)
     for t in range(meta["ticks"]):
+        if t == meta.get("reset_before_tick", -1):
+            ctrl.controller_reset()  # mid-episode: the cost's previous_input keeps the last applied control (optimizer_mppi.py:227-231)
         u = ctrl.step(z["states"][t], time=0.02 * t)
         tol_s, tol_u, tol_J = _tols(floors[t], name)
         e_u = _u_err(u, z[f"u_{t}"], z[f"u_nom_{t}"])
@@ -157,6 +159,8 @@ def test_cem_matches_reference_golden(name):
     k = meta["cfg"]["cem_best_k"]
     floors = fp32_noise_floor(name)
     for t in range(meta["ticks"]):
+        if t == meta.get("reset_before_tick", -1):
+            ctrl.controller_reset()  # optimizer_cem_tf.py:113-117: the one optimizer whose reset zeroes self.u
         u = ctrl.step(z["states"][t], time=0.02 * t)
         tol_s, tol_u, tol_J = _tols(floors[t], name)
         ref_elite = z[f"elite_idx_{t}"]
@@ -543,6 +547,8 @@ def test_gradient_matches_reference_golden(name):
     assert max_rel(opt.Q_tf, z["Q_init"]) == 0.0
     floors = fp32_noise_floor(name)
     for t in range(meta["ticks"]):
+        if t == meta.get("reset_before_tick", -1):
+            ctrl.controller_reset()  # optimizer_rpgd.py:527-548: new population, Adam reset, self.u kept
         u = ctrl.step(z["states"][t], time=0.02 * t)
         tol_s, tol_u, tol_J = _tols(floors[t], name)
         step, m, v = opt.adam_weights()
@@ -603,6 +609,8 @@ def test_rpgd_matches_reference_golden(name):
     assert max_rel(opt.Q_tf, z["Q_init"]) < 1e-6
     floors = fp32_noise_floor(name)
     for t in range(meta["ticks"]):
+        if t == meta.get("reset_before_tick", -1):
+            ctrl.controller_reset()  # optimizer_rpgd.py:527-548: new population, Adam reset, self.u kept
         u = ctrl.step(z["states"][t], time=0.02 * t)
         tol_s, tol_u, tol_J = _tols(floors[t], name)
         step, m, v = opt.adam_weights()

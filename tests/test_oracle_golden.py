@@ -5,7 +5,7 @@ single-threaded, the test may run with several threads -> different reduction or
 import numpy as np
 import pytest
 
-from helpers import golden_names, load_golden, make_oracle, rel_err, replay
+from helpers import golden_names, load_golden, make_oracle, maybe_reset_oracle, rel_err, replay
 
 TOL = 2e-6
 
@@ -28,6 +28,7 @@ def test_mppi_oracle_matches_reference(name):
     o = make_oracle(meta)
     rng = replay(meta)
     for t in range(meta["ticks"]):
+        maybe_reset_oracle(o, meta, t, rng)
         u = o.step(z["states"][t], rng)
         assert rel_err(u, z[f"u_{t}"]) < TOL
         assert rel_err(o.u_nom.numpy(), z[f"u_nom_{t}"]) < TOL
@@ -43,6 +44,7 @@ def test_cem_oracle_matches_reference(name):
     o = make_oracle(meta)
     rng = replay(meta)
     for t in range(meta["ticks"]):
+        maybe_reset_oracle(o, meta, t, rng)
         u = o.step(z["states"][t], rng)
         np.testing.assert_array_equal(o.last["elite_idx"], z[f"elite_idx_{t}"])
         assert rel_err(u, z[f"u_{t}"]) < TOL
@@ -59,6 +61,7 @@ def test_rpgd_oracle_matches_reference(name):
     o.reset(rng)
     assert rel_err(o.Q.numpy(), z["Q_init"]) == 0.0
     for t in range(meta["ticks"]):
+        maybe_reset_oracle(o, meta, t, rng)
         u = o.step(z["states"][t], rng)
         assert rel_err(u, z[f"u_{t}"]) < TOL, (t, u, z[f"u_{t}"])
         assert rel_err(o.Q.numpy(), z[f"Q_{t}"]) < TOL
@@ -131,6 +134,7 @@ def test_cem_grad_oracles_match_reference(name):
     rng = replay(meta)
     o.reset(rng)
     for t in range(meta["ticks"]):
+        maybe_reset_oracle(o, meta, t, rng)
         u = o.step(z["states"][t], rng)
         np.testing.assert_array_equal(o.last["elite_idx"], z[f"elite_idx_{t}"])
         assert rel_err(u, z[f"u_{t}"]) < 5e-6
