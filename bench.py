@@ -237,6 +237,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    fused = getattr(opt, "_exchange", "none") in ("p2p", "none")  # the tick is ctk_step_device (one C call, no NCCL in between)
+
+    def align():
+        """Device-side barrier across the shards (mailbox flags, one tiny kernel) enqueued BEFORE a timed tick: the shards' L2
+        flushes run un-synchronised, and without it their skew would be spent waiting inside the timed tick's exchange."""
+        if world > 1 and getattr(opt, "_exchange", "") == "p2p":
+            L.check(lib.ctk_exchange_barrier(opt._h))
+
     for i in range(W):
         tick(i)
     barrier()
@@ -249,6 +257,7 @@ def run_ours(args):
     wall0 = time.perf_counter()
     for i in range(K):
         flush.zero_()
+        align()
         ev[i][0].record()
         tick(W + i)
         ev[i][1].record()
@@ -282,6 +291,28 @@ def run_ours(args):
         L.check(lib.ctk_get_kernel_timing(opt._h, C.byref(ms_sum), C.byref(n_k)))
         L.check(lib.ctk_enable_kernel_timing(opt._h, 0))
         kernel_ms_source = "CUDA events around the kernel launch on the handle's stream, second pass over the same ticks"
+    # ---- third figure, clearly separate: the same K ticks BACK TO BACK inside ONE event pair (no per-tick flush, no per-tick
+    #      events): consecutive ticks overlap through programmatic dependent launch, which a per-tick event pair forbids.  The
+    #      difference to ms_per_step is the event-pair / launch gap and the cold prologue, not work. ----
+    pipelined_ms = None
+    if fused:
+        Kp = max(K, 50)
+        st_rep = states[W:W + K].repeat((Kp + K - 1) // K, 1)[:Kp].contiguous()
+        u_rep = torch.zeros(Kp, 2, dtype=torch.float32, device=dev)
+        L.check(lib.ctk_step_device_n(opt._h, C.c_void_p(st_rep.data_ptr()), 6, C.c_void_p(u_rep.data_ptr()), 2, min(Kp, 10)))  # warm
+        barrier()
+        align()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        L.check(lib.ctk_step_device_n(opt._h, C.c_void_p(st_rep.data_ptr()), 6, C.c_void_p(u_rep.data_ptr()), 2, Kp))
+        p1.record()
+        barrier()
+        pm = torch.tensor([p0.elapsed_time(p1) / Kp], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(pm, op=dist.ReduceOp.MAX)
+        pipelined_ms = float(pm.item())
+        if not bool(torch.isfinite(u_rep).all()) or float(u_rep[:, 1].abs().max()) != 0.0:
+            raise RuntimeError("pipelined ticks reported an exchange failure")
     total_ms = torch.tensor([sum(per_tick_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -326,11 +357,15 @@ def run_ours(args):
             flop = fl_step * n_local * H
             achieved = flop / (k1_ms * 1e-3) / 1e12
             tpeak = float(peaks.get("bf16_tflops", 1648.0))
-            roofline = {"bound": "tensor", "kernel": f"mppi_rollout_kernel<{'MlpTcPred' if args.mlp_engine == 'tcgen05' else 'MlpSimtPred'}>",
+            pred_name = {"tcgen05": "MlpTcPred", "tcgen05_bf16": "MlpTcBf16Pred", "tcgen05_fast": "MlpTcFastPred"}.get(args.mlp_engine, "MlpSimtPred")
+            products = {"tcgen05": 6.0, "tcgen05_bf16": 1.0, "tcgen05_fast": 1.0}.get(args.mlp_engine, 0.0)
+            roofline = {"bound": "tensor", "kernel": f"mppi_rollout_kernel<{pred_name}>",
                         "achieved": achieved, "peak": tpeak, "unit": "TFLOP/s", "frac": achieved / tpeak, "traffic": None,
                         "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, cuBLAS 8192^3)" if peaks else "fallback 1648",
                         "flop_per_rollout_step": fl_step, "kernel_ms": k1_ms, "kernel_share_of_tick": k1_ms / tick2_ms,
-                        "tensor_flop_issued_per_algorithmic": 6.0 * 32768.0 / fl_step if args.mlp_engine == "tcgen05" else 0.0}
+                        "tensor_flop_issued_per_algorithmic": products * 32768.0 / fl_step,
+                        "precision": {"tcgen05": "fp32-level (six products of three-term bf16 splits)", "tcgen05_bf16": "one bf16 product (operands rounded to bfloat16): opt-in, parity vs an oracle with the same rounding",
+                                      "tcgen05_fast": "one bf16 product + MUFU.TANH: opt-in, no parity bound"}.get(args.mlp_engine, "fp32")}
         elif logging_on:
             # optimizer_logging on: rollout_trajectories_logged [N,H+1,6] + Q_logged [N,H,1] + J [N] are written by the rollout kernel
             byt = 4.0 * n_local * ((H + 1) * 6 + H + 1)
@@ -403,9 +438,13 @@ def run_ours(args):
                            **({"mlp_engine": args.mlp_engine} if WORKLOADS[args.workload][1].startswith("Dense") else {}),
                            "parallelism": f"rollouts sharded over {world} GPU(s); exchange per tick: {getattr(opt, '_exchange', 'none')} "
                                           f"({'in-kernel NVLink mailbox stores, ' if getattr(opt, '_exchange', '') == 'p2p' else ''}{H // 10 + 3} floats per shard)",
-                           "l2": "flushed between timed ticks (256 MiB memset); inputs are 24 B per tick", "logging": logging_on},
+                           "l2": "flushed between timed ticks (256 MiB memset" + ("; shards aligned by a device-side mailbox barrier before each timed tick" if world > 1 else "") + "); inputs are 24 B per tick", "logging": logging_on},
                 "e2e": {"value": e2e_value, "unit": "rollout-steps/s", "h2d_bytes_per_step": 24, "d2h_bytes_per_step": (4 * N * ((H + 1) * 6 + H + 1) + 8 + 4 * H) if logging_on else ((8 + 4 * H) if opt_name == "mppi" else 8),
                         "p50_step_latency_ms": statistics.median(lat) * 1e3, "api": api_name},
+                "pipelined": (None if pipelined_ms is None else
+                              {"value": N * H * passes / (pipelined_ms * 1e-3), "unit": "rollout-steps/s", "ms_per_step": pipelined_ms,
+                               "ticks": max(K, 50), "how": "ticks back to back inside ONE CUDA-event pair (ctk_step_device_n), no per-tick L2 flush, "
+                                                           "max over ranks; consecutive ticks overlap through programmatic dependent launch"}),
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "wall_s_timed_region": wall}
         _emit(line)
@@ -422,7 +461,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mppi_ode_1m", choices=sorted(WORKLOADS))
     ap.add_argument("--rollouts", type=int, default=None, help="override the global rollout count")
-    ap.add_argument("--mlp-engine", default="tcgen05", choices=["simt", "tcgen05"], help="MLP predictor engine (mppi_mlp_c4 workload)")
+    ap.add_argument("--mlp-engine", default="tcgen05", choices=["simt", "tcgen05", "tcgen05_bf16", "tcgen05_fast"], help="MLP predictor engine (mppi_mlp_c4 workload)")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="rollouts per CPU-baseline tick (bounded sample)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -140,7 +140,10 @@ class template_optimizer:
         cfg.seed = self.seed & 0xFFFFFFFFFFFFFFFF
         cfg.logging = int(self.optimizer_logging)
         cfg.freeze_previous_input = int(self.freeze_previous_input)
-        cfg.mlp_engine = {"simt": L.MLP_SIMT, "tcgen05": L.MLP_TCGEN05}[self.mlp_engine]
+        engines = {"simt": L.MLP_SIMT, "tcgen05": L.MLP_TCGEN05, "tcgen05_bf16": L.MLP_TCGEN05_BF16, "tcgen05_fast": L.MLP_TCGEN05_FAST}
+        if self.mlp_engine not in engines:
+            raise ValueError(f"mlp_engine must be one of {sorted(engines)}, got {self.mlp_engine!r}")
+        cfg.mlp_engine = engines[self.mlp_engine]
         self._fill_config(cfg)
 
         tp, te = self._live_targets()

@@ -21,7 +21,7 @@ PRED_ODE, PRED_MLP = 0, 1
 COST_DEFAULT, COST_QUADRATIC_BOUNDARY_GRAD = 0, 1
 DIST_NORMAL, DIST_UNIFORM = 0, 1
 ADAM_KERAS, ADAM_TORCH = 0, 1
-MLP_SIMT, MLP_TCGEN05 = 0, 1
+MLP_SIMT, MLP_TCGEN05, MLP_TCGEN05_BF16, MLP_TCGEN05_FAST = 0, 1, 2, 3
 STATE_U_NOM, STATE_CEM_MU, STATE_CEM_STD, STATE_RPGD_Q, STATE_RPGD_M, STATE_RPGD_V, STATE_RPGD_AGES, STATE_U_PREV = range(8)
 COUNTER_COUNT, COUNTER_ADAM_STEP, COUNTER_TICK = range(3)
 STREAM_MPPI, STREAM_CEM, STREAM_RPGD_INIT, STREAM_RPGD_RESAMPLE = range(4)
@@ -88,6 +88,8 @@ SYMBOLS = {
     "ctk_partials": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "ctk_step_finish": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p]),
     "ctk_step_device": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
+    "ctk_step_device_n": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
+    "ctk_exchange_barrier": (C.c_int, [_H]),
     "ctk_exchange_export": (C.c_int, [_H, C.c_void_p]),
     "ctk_exchange_connect": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
     "ctk_exchange_mailbox": (C.c_int, [_H, C.POINTER(C.c_void_p)]),

@@ -69,24 +69,30 @@ struct alignas(16) HotUK {
 };
 
 // ----------------------------------------------------------------------------------------------------------------
-// In-kernel tick finish (K2 fused into the rollout kernel): the LAST block to retire combines the block records,
-// optionally exchanges the shard record with the peer GPUs through NVLink peer stores into their mailboxes
-// (value + sequence number packed in one 8-byte store: no fence, one NVLink traversal), and updates u_nom / u.
-// Replaces reference optimizer_mppi.py:163-168,190-191 (+ the cross-shard weighted-sum exchange of SURVEY 8e).
+// In-kernel tick finish (K2 fused into the rollout kernel).  Every block publishes its softmin record [rho_b, a_b, b_z[n_ind]]
+// as tagged 8-byte slots (value | sequence number in ONE store: no fence, no flag round trip) straight into the mailbox of EVERY
+// shard -- its own GPU's and, over NVLink peer stores, the peers' (one hop: the remote latency runs underneath the wait for the
+// slowest local block) -- and block 0 of every shard, the finisher, polls the world x grid records of its own mailbox, rescales
+// them exactly to the global minimum and updates u_nom / u.  Every shard combines the same records in the same order: the
+// replicated optimizer state stays bit-identical.  Replaces reference optimizer_mppi.py:163-168,190-191 (+ the cross-shard
+// weighted-sum exchange of SURVEY 8e).
+// Mailbox layout (uint64 slots): [2 (sequence parity)][CTK_MAX_PEERS (source shard)][CTK_MBOX_BLOCKS (source block)][2 + n_ind],
+// then the barrier area [2][CTK_MAX_PEERS].  Double-buffered by parity: a shard can be at most one tick ahead of its slowest peer.
 // ----------------------------------------------------------------------------------------------------------------
 constexpr int CTK_MAX_PEERS = 8;
+constexpr int CTK_MBOX_BLOCKS = 320;  // >= the grid of any rollout kernel (one or two CTAs per SM: 148 SMs on B200)
+CTK_HD size_t mbox_record_slots(int n_ind) { return (size_t)2 * CTK_MAX_PEERS * CTK_MBOX_BLOCKS * (n_ind + 2); }
+CTK_HD size_t mbox_total_slots(int n_ind) { return mbox_record_slots(n_ind) + 2 * CTK_MAX_PEERS; }
 struct MppiFuse {
-  int mode;                  // 0: block records only (legacy K2 launch follows)  1: + shard record  2: + finalize
+  int mode;                  // 0: block records only (legacy K2 launch follows)  1: + shard record (staged exchange)  2: + finalize
   int world, rank;           // shards taking part in the exchange (1: no exchange)
-  unsigned int seq;          // exchange sequence number of this tick (monotonic, never 0)
-  unsigned int lseq;         // sequence number of this launch (monotonic, never 0): tag of the block records
-  unsigned long long* tagged;  // [gridDim.x][2 + n_ind] block records as (value, lseq) pairs
+  unsigned int seq;          // sequence number of this launch (monotonic, never 0, in lock step on all shards): tag of the records
   float* record_out;         // [2 + n_ind] shard record (mode >= 1)
-  unsigned long long* mbox_local;                 // [2][world][2 + n_ind] (value, seq) pairs written by the peers
-  unsigned long long* mbox_peer[CTK_MAX_PEERS];   // peers' mailboxes (mbox_peer[rank] == mbox_local)
+  unsigned long long* mbox_local;                 // this shard's mailbox
+  unsigned long long* mbox_peer[CTK_MAX_PEERS];   // every shard's mailbox (mbox_peer[rank] == mbox_local)
   float* u_nom;              // [H] in/out
   float* u_prev;             // [1] out (unless frozen)
-  float* u_out;              // [2] out: u, exchange status (0 ok, 1 timeout)
+  float* u_out;              // [2] out: u, status (0 ok, 1 a peer's record missing, 2 a local block's record missing)
   int freeze_prev;
   HostMirror host;           // mode 2: u / status / u_nom[H] mirrored to the host caller
 };
@@ -140,6 +146,7 @@ struct OdeHot {
 
 struct MppiOdeArgs {
   int N, off, H, period, n_ind;
+  int t0;               // threads of block 0 that carry rollouts (multiple of 32, <= blockDim.x): the finisher block gets a smaller share
   S0 s0;                // initial state
   const float* u_nom;   // [H] unshifted
   const float* u_prev;  // [1]

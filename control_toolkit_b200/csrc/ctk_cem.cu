@@ -47,7 +47,19 @@ cudaError_t launch_cem_tick(int kind, bool log, int nblocks, size_t smem, cudaSt
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  return launch_pdl(k, dim3(nblocks), dim3(kCemTickThreads), smem, st, a);
+  // The blocks of this kernel wait for each other (tagged-slot grid synchronisation), so the WHOLE grid must be co-resident: a
+  // cooperative launch makes the runtime guarantee that -- or fail with cudaErrorCooperativeLaunchTooLarge, in which case the
+  // caller takes the multi-launch path -- instead of relying on an occupancy query that assumes an otherwise idle GPU.
+  static const bool coop = std::getenv("CTK_CEM_NO_COOP") == nullptr;
+  if (!coop) return launch_pdl(k, dim3(nblocks), dim3(kCemTickThreads), smem, st, a);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nblocks); cfg.blockDim = dim3(kCemTickThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k, a);
 }
 int cem_tick_rollouts_per_block() { return kCemTickRollouts; }
 // resident blocks per SM of the persistent tick kernel (its blocks wait for each other: the whole grid must be resident)

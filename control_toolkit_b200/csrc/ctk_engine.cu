@@ -57,9 +57,9 @@ struct ctk_handle {
   unsigned long long* d_trace = nullptr;  // optional per-block phase timeline of the last ODE-kernel launch
   size_t ode_smem = 0;
   // fused tick finish / cross-GPU exchange (MppiFuse)
-  unsigned long long* d_tagged = nullptr;         // [num_sms][2 + n_ind] tagged block records
-  unsigned int lseq = 0;
-  unsigned long long* d_mbox = nullptr;           // local mailbox [2][CTK_MAX_PEERS][2 + n_ind]
+  unsigned long long* d_mbox = nullptr;           // local mailbox (layout: MppiFuse)
+  unsigned int bseq = 0;                          // sequence number of the exchange barrier (ctk_exchange_barrier)
+  int ode_t0 = 0;                                 // rollout-carrying threads of block 0 (the finisher's reduced share)
   unsigned long long* mbox_peer[CTK_MAX_PEERS] = {nullptr};
   bool mbox_ipc[CTK_MAX_PEERS] = {false};
   int xworld = 1, xrank = 0;
@@ -84,7 +84,8 @@ struct ctk_handle {
   NoiseSrc cem_noise{};
   unsigned long long *d_cem_cand = nullptr, *d_cem_dist = nullptr;  // persistent CEM tick: tagged candidate / distribution slots
   unsigned int cem_seq = 0;
-  int cem_tick_per_sm = -1;  // resident blocks per SM of the persistent tick kernel (queried once)
+  int cem_tick_per_sm = -1;  // resident blocks per SM of the persistent tick kernel (re-queried when the instantiation changes)
+  bool cem_coop_refused = false;  // the runtime refused the cooperative launch once: multi-launch path from then on
   // rpgd
   float *d_Q[2] = {nullptr, nullptr}, *d_m[2] = {nullptr, nullptr}, *d_v[2] = {nullptr, nullptr}, *d_ages[2] = {nullptr, nullptr};
   int cur = 0;
@@ -218,7 +219,6 @@ extern "C" int ctk_destroy(ctk_handle* h) {
   if (h->d_mlp_tc) cudaFree(h->d_mlp_tc);
   for (int r = 0; r < CTK_MAX_PEERS; ++r)
     if (h->mbox_ipc[r] && h->mbox_peer[r]) cudaIpcCloseMemHandle(h->mbox_peer[r]);
-  if (h->d_tagged) cudaFree(h->d_tagged);
   if (h->d_trace) cudaFree(h->d_trace);
   if (h->d_mbox) cudaFree(h->d_mbox);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -303,9 +303,10 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
       h->mppi_stash = 0;
     }
     h->mppi_rpb = h->mppi_block;
-    if (pred_id(h) == 2) {  // tcgen05 MLP engine: 16 worker warps + 1 MMA-issuer warp on the 128 rollouts of one MMA tile (ctk_mlp_tc.cuh)
+    if (pred_id(h) >= 2) {  // tcgen05 MLP engines: 16 worker warps + 1 MMA-issuer warp on the 128 rollouts of one MMA tile (ctk_mlp_tc.cuh)
       h->mppi_block = mppi_max_block_threads(2); h->mppi_rpb = 128;
-      h->mppi_grid = (int)std::min<long long>(h->num_sms, ((long long)N + 127) / 128);
+      const int per_sm = pred_id(h) >= 3 ? 2 : 1;  // the single-product engines keep two tiles (CTAs) in flight per SM
+      h->mppi_grid = (int)std::min<long long>((long long)per_sm * h->num_sms, ((long long)N + 127) / 128);
       if (h->mppi_grid < 1) h->mppi_grid = 1;
       h->mppi_iters = (int)((N + (long long)h->mppi_grid * 128 - 1) / ((long long)h->mppi_grid * 128));
       h->mppi_stash = ((size_t)h->n_ind * 128 * sizeof(float) <= 8 * 1024) ? 1 : 0;
@@ -314,8 +315,8 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
     A(dalloc(&h->d_u_nom, (size_t)H), "u_nom");
     A(dalloc(&h->d_partials, (size_t)(h->num_sms > h->mppi_grid ? h->num_sms : h->mppi_grid) * (h->mppi_iters + 1) * (h->n_ind + 2)), "partials");
     A(dalloc(&h->d_record, (size_t)(h->n_ind + 2)), "record");
-    A(dalloc(&h->d_tagged, (size_t)(h->num_sms > h->mppi_grid ? h->num_sms : h->mppi_grid) * (h->n_ind + 2)), "tagged");
-    A(dalloc(&h->d_mbox, (size_t)2 * CTK_MAX_PEERS * (h->n_ind + 2)), "mailbox");
+    if (h->mppi_grid > CTK_MBOX_BLOCKS || h->num_sms > CTK_MBOX_BLOCKS) { ctk_destroy(h); return fail(CTK_EINVAL, "device has more SMs than the mailbox has block slots (CTK_MBOX_BLOCKS)"); }
+    A(dalloc(&h->d_mbox, mbox_total_slots(h->n_ind)), "mailbox");
     h->mbox_peer[0] = h->d_mbox;
   } else if (cfg->optimizer == CTK_OPT_CEM) {
     if (!(cfg->cem_best_k >= 1 && cfg->cem_best_k <= 512 && cfg->cem_best_k <= cfg->num_rollouts_global && H <= 1024 && cfg->cem_outer_it >= 1)) {
@@ -408,9 +409,10 @@ extern "C" int ctk_set_mlp_weights(ctk_handle* h, const ctk_mlp_weights* w) {
   CU(dalloc(&h->d_mlp, (size_t)nf));
   CU(cudaMemcpy(h->d_mlp, blob.data(), sizeof(float) * nf, cudaMemcpyHostToDevice));
   h->mlp = MlpDev{hid, h->d_mlp, nf, nullptr};
-  if (h->cfg.mlp_engine == CTK_MLP_TCGEN05) {
-    REQ(hid == kTcHidden, "the tcgen05 MLP engine is built for hidden == 128 (use mlp_engine=simt otherwise)");
-    REQ(h->cfg.optimizer == CTK_OPT_MPPI, "the tcgen05 MLP engine is implemented for MPPI (use mlp_engine=simt for CEM)");
+  if (h->cfg.mlp_engine != CTK_MLP_SIMT) {
+    REQ(h->cfg.mlp_engine >= CTK_MLP_TCGEN05 && h->cfg.mlp_engine <= CTK_MLP_TCGEN05_FAST, "unknown mlp_engine");
+    REQ(hid == kTcHidden, "the tcgen05 MLP engines are built for hidden == 128 (use mlp_engine=simt otherwise)");
+    REQ(h->cfg.optimizer == CTK_OPT_MPPI, "the tcgen05 MLP engines are implemented for MPPI (use mlp_engine=simt for CEM)");
     // W2 as three bf16 terms (w = w1 + w2 + w3, round-to-nearest-even each), B operand tiles: row n = output unit, k = input unit
     std::vector<uint8_t> tc(kTcBlobBytes, 0);
     auto bf16_rn = [](float f) -> uint16_t {
@@ -530,9 +532,16 @@ extern "C" int ctk_reset(ctk_handle* h) {
 // ---------------------------------------------------------------------------------------------------------------
 // the tick
 // ---------------------------------------------------------------------------------------------------------------
-static int pred_id(const ctk_handle* h) {  // 0 ODE, 1 MLP on the FP32 pipe, 2 MLP with the dense layer on tcgen05
+// 0 ODE, 1 MLP on the FP32 pipe, 2 MLP with the dense layer on tcgen05 (bf16 x 3 split, fp32-level), 3 one bf16 product, 4 + MUFU.TANH
+static int pred_id(const ctk_handle* h) {
   if (h->cfg.predictor != CTK_PRED_MLP) return 0;
-  return (h->cfg.mlp_engine == CTK_MLP_TCGEN05 && h->cfg.optimizer == CTK_OPT_MPPI) ? 2 : 1;
+  if (h->cfg.optimizer != CTK_OPT_MPPI) return 1;
+  switch (h->cfg.mlp_engine) {
+    case CTK_MLP_TCGEN05: return 2;
+    case CTK_MLP_TCGEN05_BF16: return 3;
+    case CTK_MLP_TCGEN05_FAST: return 4;
+    default: return 1;
+  }
 }
 static size_t pred_smem_floats(ctk_handle* h) { return mppi_pred_smem_floats(pred_id(h), h->mlp); }
 
@@ -556,16 +565,21 @@ static void mppi_ode_geometry(ctk_handle* h) {
   const long long tmax_smem = (200 * 1024 - fixed) / per_thread / 32 * 32;
   if (tmax_smem < 32) return;  // too many inducing points: generic kernel (regenerates the draws)
   if (maxb > tmax_smem) maxb = (int)tmax_smem;
+  // Block 0 is the tick's finisher: in a back-to-back chain of ticks its SM is the last to be handed to the next launch (it is still
+  // combining the records when the other blocks' SMs are already running the next tick's prologue), so it carries a smaller share
+  // of the rollouts (t0 = share x T threads) and is through them when the others are.  Only when every SM has a block.
+  double share = 0.75;
+  if (const char* e = getenv("CTK_K1_FINISHER_SHARE")) { const double v = atof(e); if (v >= 0.1 && v <= 1.0) share = v; }
+  auto t0_of = [&](long long T) { long long t0 = (long long)(share * (double)T) / 32 * 32; return t0 < 32 ? 32ll : (t0 > T ? T : t0); };
   const long long r0 = (N + sms * maxb * ilp - 1) / (sms * maxb * ilp);
   long long best_cap = -1; int best_T = 32;
   for (long long r = r0; r < r0 + 4; ++r) {
-    long long T = (N + r * sms * ilp - 1) / (r * sms * ilp);
+    long long T = (long long)((double)N / ((double)r * ilp * ((double)sms - 1.0 + share)));
     T = (T + 31) / 32 * 32;
     if (T < 32) T = 32;
+    while (T <= maxb && r * ilp * (t0_of(T) + (sms - 1) * T) < N) T += 32;
     if (T > maxb) continue;
-    const long long grid = std::min<long long>(sms, (N + T * ilp - 1) / (T * ilp));
-    const long long iters = (N + grid * T * ilp - 1) / (grid * T * ilp);
-    const long long cap = iters * T * ilp;  // per-SM time is proportional to iterations x (warps resident)
+    const long long cap = r * T * ilp;  // per-SM time is proportional to iterations x (warps resident)
     if (best_cap < 0 || cap < best_cap) { best_cap = cap; best_T = (int)T; }
   }
   // Small populations: a block narrower than 4 warps leaves the tick finish (block 0 polls and combines gridDim x (n_ind+2)
@@ -577,8 +591,16 @@ static void mppi_ode_geometry(ctk_handle* h) {
   if (best_T < min_T) best_T = (int)std::min<long long>(min_T, (N + 31) / 32 * 32);
   h->ode_ilp = ilp;
   h->ode_block = best_T;
-  h->ode_grid = (int)std::min<long long>(sms, (N + (long long)best_T * ilp - 1) / ((long long)best_T * ilp));
-  if (h->ode_grid < 1) h->ode_grid = 1;
+  // the reduced share only when every SM carries a block of at least 8 warps (T came out of the search above, so the grid fills the
+  // device); smaller populations: equal shares (t0 = T), as many blocks as there are groups of T x ilp rollouts
+  if (best_T >= 256 && best_cap > 0) {
+    h->ode_grid = (int)sms;
+    h->ode_t0 = (int)t0_of(best_T);
+  } else {
+    h->ode_grid = (int)std::min<long long>(sms, (N + (long long)best_T * ilp - 1) / ((long long)best_T * ilp));
+    if (h->ode_grid < 1) h->ode_grid = 1;
+    h->ode_t0 = best_T;
+  }
   h->ode_period_t = (h->period == 10) ? 10 : 0;
   if (getenv("CTK_K1_NO_UNROLL")) h->ode_period_t = 0;
   h->ode_smem = mppi_ode_smem_bytes(h->H, h->period, h->n_ind, ilp, best_T);
@@ -597,20 +619,14 @@ static int make_fuse(ctk_handle* h, int mode, float* u_out_dev, MppiFuse* out) {
   MppiFuse f{};
   f.mode = mode;
   f.world = 1; f.rank = 0; f.seq = 0;
-  f.tagged = h->d_tagged;
-  if (mode != 0) { h->lseq++; if (h->lseq == 0) h->lseq = 1; }
-  f.lseq = h->lseq;
+  if (mode != 0) { h->xseq++; if (h->xseq == 0) h->xseq = 1; }  // every shard ticks in lock step: the same sequence everywhere
+  f.seq = h->xseq;
   f.record_out = h->d_record;
   f.mbox_local = h->d_mbox;
   for (int r = 0; r < CTK_MAX_PEERS; ++r) f.mbox_peer[r] = h->mbox_peer[r];
   f.u_nom = h->d_u_nom; f.u_prev = h->d_u_prev; f.u_out = u_out_dev; f.freeze_prev = h->cfg.freeze_previous_input;
   if (mode == 2) f.host = h->mirror;
-  if (mode == 2 && h->xworld > 1) {
-    f.world = h->xworld; f.rank = h->xrank;
-    h->xseq++;
-    if (h->xseq == 0) h->xseq = 1;
-    f.seq = h->xseq;
-  }
+  if (mode == 2 && h->xworld > 1) { f.world = h->xworld; f.rank = h->xrank; }
   *out = f;
   return CTK_OK;
 }
@@ -627,6 +643,7 @@ static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_
   if (h->ode_kernel) {
     MppiOdeArgs a{};
     a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
+    a.t0 = h->ode_t0;
     a.trace = h->d_trace;
     a.s0 = make_s0(h, s_dev); a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = ns; a.k = h->ode_hot;
     a.J = h->d_J; a.partials = h->d_partials; a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
@@ -663,10 +680,10 @@ static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_
                                        pred_smem_floats(h));
   h->launches++;
   KernelTimer kt(h);
-  if (pred_id(h) == 2 && h->mlp.tc_blob == nullptr) return fail(CTK_ESTATE, "tcgen05 MLP engine without weights");
+  if (pred_id(h) >= 2 && h->mlp.tc_blob == nullptr) return fail(CTK_ESTATE, "tcgen05 MLP engine without weights");
   cudaError_t e = launch_mppi_rollout(pred_id(h), h->cost.kind, log, h->mppi_grid, h->mppi_block, smem,
                                       h->stream, a);
-  h->last_kernel = std::string("mppi_rollout_kernel<") + (pred_id(h) == 2 ? "MlpTcPred" : pred_id(h) == 1 ? "MlpSimtPred" : "OdePred") + "," +
+  h->last_kernel = std::string("mppi_rollout_kernel<") + (pred_id(h) == 4 ? "MlpTcFastPred" : pred_id(h) == 3 ? "MlpTcBf16Pred" : pred_id(h) == 2 ? "MlpTcPred" : pred_id(h) == 1 ? "MlpSimtPred" : "OdePred") + "," +
                    std::to_string(h->cost.kind) + "," + (log ? "1" : "0") + ">" + (ns.inj ? " [injected noise]" : " [philox]");
   if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("mppi_rollout_kernel: ") + cudaGetErrorString(e));
   return CTK_OK;
@@ -704,15 +721,19 @@ static bool cem_tick_geometry(const ctk_handle* h, CemTickGeom* g) {
 static bool cem_persistent_ok(ctk_handle* h) {
   const ctk_config& c = h->cfg;
   if (!(c.optimizer == CTK_OPT_CEM && h->ode_kernel && h->N == h->NG && h->off == 0 && h->xworld == 1 && c.cem_best_k <= 128 &&
-        h->H <= 512 && h->num_sms > 0 && h->N <= 65535 && getenv("CTK_CEM_MULTI_LAUNCH") == nullptr))
+        h->H <= 512 && h->num_sms > 0 && h->N <= 65535 && !h->cem_coop_refused && getenv("CTK_CEM_MULTI_LAUNCH") == nullptr))
     return false;
   CemTickGeom g;
   if (!cem_tick_geometry(h, &g)) return false;
   if (h->cem_tick_per_sm < 0) h->cem_tick_per_sm = cem_tick_blocks_per_sm(h->cost.kind, c.logging != 0, g.smem);
   return h->cem_tick_per_sm >= 1 && g.G <= h->cem_tick_per_sm * h->num_sms;  // every block must be resident: blocks wait for each other
 }
+// returns 1 if the runtime refused the cooperative launch (grid not co-resident right now): nothing was consumed, the caller runs
+// the multi-launch path
 static int cem_tick_persistent(ctk_handle* h, const float* s_dev, float* u_out_dev) {
   const ctk_config& c = h->cfg;
+  const size_t inj_pos0 = h->inj_pos;
+  const unsigned int cem_seq0 = h->cem_seq;
   const int iters = (c.cem_warmup && h->count == 0) ? c.cem_warmup_iterations : c.cem_outer_it;  // optimizer_cem_tf.py:92
   if (iters < 1) return fail(CTK_EINVAL, "CEM iteration count < 1");
   const int uni = c.cem_uniform_actions ? 1 : 0;
@@ -757,6 +778,12 @@ static int cem_tick_persistent(ctk_handle* h, const float* s_dev, float* u_out_d
     e = launch_cem_tick(h->cost.kind, c.logging != 0, g.G, g.smem, h->stream, a);
     h->last_kernel = "cem_tick_kernel<" + std::to_string(h->cost.kind) + "," + (c.logging ? "1" : "0") + "," +
                      ((a.noise.inj == nullptr && !a.noise.uniform) ? "1" : "0") + ">";
+  }
+  if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
+    cudaGetLastError();
+    h->cem_coop_refused = true;
+    h->inj_pos = inj_pos0; h->cem_seq = cem_seq0; h->launches--;
+    return 1;
   }
   if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("cem_tick_kernel: ") + cudaGetErrorString(e));
   h->cem_it = 0;
@@ -1126,8 +1153,8 @@ static int step_host(ctk_handle* h, const float* s_host, float* u_out_host, cons
     rc = mppi_local(h, nullptr, 2, h->d_u_out);
   } else if (h->cfg.optimizer == CTK_OPT_CEM) {
     h->tick++;
-    if (cem_persistent_ok(h)) rc = cem_tick_persistent(h, nullptr, h->d_u_out);
-    else do {
+    rc = cem_persistent_ok(h) ? cem_tick_persistent(h, nullptr, h->d_u_out) : 1;
+    if (rc == 1) do {
       rc = cem_local(h, nullptr, false);
       if (rc != CTK_OK) break;
       rc = cem_finish(h, h->cem_cand_ptr, h->cem_cand, h->d_u_out);
@@ -1155,8 +1182,8 @@ static int step_host(ctk_handle* h, const float* s_host, float* u_out_host, cons
     if (h->cfg.optimizer == CTK_OPT_CEM)
       return fail(CTK_ECUDA, "persistent CEM tick: a block of the grid did not publish its candidates / the distribution within 2 s "
                              "(grid not co-resident? another kernel holding SM slots); set CTK_CEM_MULTI_LAUNCH=1 to use the multi-launch path");
-    if (us[1] == 2.0f) return fail(CTK_ECUDA, "tick finish timed out: a block of this GPU's grid did not publish its softmin record within 2 s");
-    return fail(CTK_ECUDA, "cross-GPU exchange timed out: a peer shard did not deliver its record within 2 s");
+    return fail(CTK_ECUDA, h->xworld > 1 ? "cross-GPU exchange timed out: a block record of this grid or of a peer shard did not arrive within 2 s"
+                                         : "tick finish timed out: a block of this GPU's grid did not publish its softmin record within 2 s");
   }
   return CTK_OK;
 }
@@ -1175,8 +1202,8 @@ extern "C" int ctk_step_device(ctk_handle* h, const float* s_dev, float* u_out_d
   if (h->cfg.optimizer == CTK_OPT_MPPI) {
     rc = mppi_local(h, s_dev, 2, uo);
   } else if (h->cfg.optimizer == CTK_OPT_CEM) {
-    if (cem_persistent_ok(h)) rc = cem_tick_persistent(h, s_dev, uo);
-    else do {
+    rc = cem_persistent_ok(h) ? cem_tick_persistent(h, s_dev, uo) : 1;
+    if (rc == 1) do {
       rc = cem_local(h, s_dev, false);
       if (rc != CTK_OK) break;
       rc = cem_finish(h, h->cem_cand_ptr, h->cem_cand, uo);
@@ -1185,6 +1212,18 @@ extern "C" int ctk_step_device(ctk_handle* h, const float* s_dev, float* u_out_d
     rc = rpgd_tick(h, s_dev, uo);
   }
   return rc;
+}
+
+// n ticks back to back on the handle's stream: tick i reads its state from s_dev + i * s_stride (device memory) and writes
+// [u, status] to u_out_dev + i * u_stride.  One C call enqueues the whole chain, so consecutive ticks overlap through programmatic
+// dependent launch (the next tick's noise generation runs underneath the previous tick's finish / exchange / launch gap).
+extern "C" int ctk_step_device_n(ctk_handle* h, const float* s_dev, size_t s_stride, float* u_out_dev, size_t u_stride, int n) {
+  REQ(h && s_dev && n >= 0, "null pointer or negative tick count");
+  for (int i = 0; i < n; ++i) {
+    int rc = ctk_step_device(h, s_dev + (size_t)i * s_stride, u_out_dev ? u_out_dev + (size_t)i * u_stride : nullptr);
+    if (rc != CTK_OK) return rc;
+  }
+  return CTK_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1208,7 +1247,8 @@ static int exchange_reset(ctk_handle* h, int rank, int world) {
     h->mbox_peer[r] = nullptr; h->mbox_ipc[r] = false;
   }
   h->xworld = world; h->xrank = rank; h->xseq = 0;
-  CU(cudaMemset(h->d_mbox, 0, sizeof(unsigned long long) * 2 * CTK_MAX_PEERS * (h->n_ind + 2)));
+  h->bseq = 0;
+  CU(cudaMemset(h->d_mbox, 0, sizeof(unsigned long long) * mbox_total_slots(h->n_ind)));
   return CTK_OK;
 }
 extern "C" int ctk_exchange_connect(ctk_handle* h, int rank, int world, const void* ipc_handles) {
@@ -1230,6 +1270,22 @@ extern "C" int ctk_exchange_connect(ctk_handle* h, int rank, int world, const vo
     h->mbox_peer[r] = (unsigned long long*)p;
     h->mbox_ipc[r] = true;
   }
+  return CTK_OK;
+}
+extern "C" int ctk_exchange_barrier(ctk_handle* h) {
+  REQ(h, "null handle");
+  REQ(h->d_mbox != nullptr, "this optimizer has no exchange mailbox");
+  if (h->xworld <= 1) return CTK_OK;
+  CU(cudaSetDevice(h->cfg.device));
+  MppiFuse f{};
+  f.world = h->xworld; f.rank = h->xrank;
+  h->bseq++;
+  if (h->bseq == 0) h->bseq = 1;
+  f.seq = h->bseq;
+  f.mbox_local = h->d_mbox;
+  for (int r = 0; r < CTK_MAX_PEERS; ++r) f.mbox_peer[r] = h->mbox_peer[r];
+  h->launches++;
+  CU(launch_exchange_barrier(f, mbox_record_slots(h->n_ind), h->stream));
   return CTK_OK;
 }
 extern "C" int ctk_exchange_mailbox(ctk_handle* h, void** dev_ptr) {
@@ -1382,10 +1438,16 @@ extern "C" int ctk_debug_trace(ctk_handle* h, int enable, uint64_t* out_host, si
   REQ(h, "null handle");
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaStreamSynchronize(h->stream));
-  const size_t n = (size_t)(h->num_sms > 0 ? h->num_sms : 148) * 8;
+  const size_t per = (size_t)CTK_MBOX_BLOCKS * 8, n = 4 * per;  // the last 4 launches, slot = launch sequence number & 3
   if (out_host && h->d_trace) {
-    REQ(n_u64 >= n, "trace buffer too small");
-    CU(cudaMemcpy(out_host, h->d_trace, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (n_u64 >= n) {  // whole history, oldest first
+      std::vector<uint64_t> tmp(n);
+      CU(cudaMemcpy(tmp.data(), h->d_trace, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+      for (int i = 0; i < 4; ++i) memcpy(out_host + (size_t)i * per, tmp.data() + (size_t)((h->xseq + 1 + i) & 3u) * per, per * sizeof(uint64_t));
+    } else {  // the last launch only
+      REQ(n_u64 >= (size_t)(h->num_sms > 0 ? h->num_sms : 148) * 8, "trace buffer too small");
+      CU(cudaMemcpy(out_host, h->d_trace + (size_t)(h->xseq & 3u) * per, (size_t)(h->num_sms > 0 ? h->num_sms : 148) * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
   }
   if (grid_out) *grid_out = h->ode_grid;
   if (enable && !h->d_trace) { CU(cudaMalloc((void**)&h->d_trace, n * sizeof(uint64_t))); CU(cudaMemset(h->d_trace, 0, n * sizeof(uint64_t))); }

@@ -38,20 +38,19 @@ __device__ __forceinline__ void mppi_step(const MppiArgs& a, const CostC& cost, 
 // ----------------------------------------------------------------------------------------------------------------
 // Tick finish inside the rollout kernel (MppiFuse): combine softmin records, exchange across GPUs, update u_nom.
 // ----------------------------------------------------------------------------------------------------------------
-// records in[cnt][P] = [rho, a, b_z[n_ind]] -> out[P] (shared memory), rescaled exactly to the common minimum.
-// GLOBAL: `in` is the tagged (value, seq) array written by other blocks of this launch: element i is the low word of the
-// i-th 8-byte slot, read through L2 (ld.cg).  All threads participate.
-template <bool GLOBAL>
-__device__ __forceinline__ void combine_records(const float* in, int cnt, int P, float neg_inv_lbd, float* out, float* sh_red) {
+// records rec(b, c), b < cnt, c < P: [rho, a, b_z[n_ind]] -> out[P] (shared memory), rescaled exactly to the common minimum.
+// All threads participate.
+template <class Rec>
+__device__ __forceinline__ void combine_records(Rec rec, int cnt, int P, float neg_inv_lbd, float* out, float* sh_red) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
   float mn = INFINITY;
-  for (int b = tid; b < cnt; b += blockDim.x) mn = fminf(mn, GLOBAL ? __ldcg(in + 2 * ((size_t)b * P)) : in[(size_t)b * P]);
+  for (int b = tid; b < cnt; b += blockDim.x) mn = fminf(mn, rec(b, 0));
   const float rho = block_min(mn, sh_red);
   for (int c = w; c < P - 1; c += nw) {
     float acc = 0.0f;
     for (int b = lane; b < cnt; b += 32) {
-      const float rb = GLOBAL ? __ldcg(in + 2 * ((size_t)b * P)) : in[(size_t)b * P];
-      const float v = GLOBAL ? __ldcg(in + 2 * ((size_t)b * P + 1 + c)) : in[(size_t)b * P + 1 + c];
+      const float rb = rec(b, 0);
+      const float v = rec(b, 1 + c);
       const float sc = (rb < INFINITY) ? expf((rb - rho) * neg_inv_lbd) : 0.0f;
       acc = fmaf(sc, v, acc);
     }
@@ -62,13 +61,58 @@ __device__ __forceinline__ void combine_records(const float* in, int cnt, int P,
   __syncthreads();
 }
 
+// Poll n tagged slots src(i) until their sequence numbers match; values -> dst[i] (dst may be null: wait only).  Up to four
+// loads per thread are in flight before the first tag is checked (a dependent poll per slot would serialise the L2 latency).
+// Returns 0, or 1 if a slot did not arrive within ~2 s.
+template <class Src>
+__device__ __forceinline__ int poll_tagged(Src src, int n, unsigned int seq, unsigned long long t0, float* dst) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  int lost = 0;
+  for (int base = 0; base < n; base += 4 * T) {
+    const unsigned long long* p[4];
+    bool need[4];
+    float val[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = base + j * T + tid;
+      need[j] = i < n;
+      p[j] = src(need[j] ? i : 0);
+      val[j] = 0.0f;
+    }
+    int spins = 0;
+    while (true) {
+      unsigned long long v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (need[j]) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v[j]) : "l"(p[j]) : "memory");
+      bool pending = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!need[j]) continue;
+        if ((unsigned int)(v[j] >> 32) == seq) { val[j] = __uint_as_float((unsigned int)(v[j] & 0xffffffffull)); need[j] = false; }
+        else pending = true;
+      }
+      if (!pending) break;
+      if ((++spins & 1023) == 0 && globaltimer_ns() - t0 > 2000000000ull) { lost = 1; break; }
+    }
+    if (dst != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = base + j * T + tid;
+        if (i < n) dst[i] = val[j];
+      }
+    }
+  }
+  return lost;
+}
+
 // Called by ALL threads of EVERY block once the block's record brec[P] = [rho_b, a_b, b_z[n_ind]] is complete in SHARED
 // memory (the call starts with a barrier).  mode 0: the record is stored as plain floats to partials[blockIdx.x][P] (a
-// separate combine launch follows).  mode >= 1: every value is published as ONE 8-byte (value, launch sequence number)
-// store -- no fence, no atomic, no ticket -- and block 0, the finisher, polls the grid's slots until their tags match,
-// combines them, exchanges the shard record with the peer GPUs through the same tagged-store protocol and updates
-// u_nom.  scratch: >= 9 * P floats of shared memory; sh_unom: the shifted nominal (prologue copy); big / big_floats: larger
-// shared scratch -- when the grid's records fit they are staged there by the polling pass itself.
+// separate combine launch follows).  mode >= 1: every value is published as ONE 8-byte (value, sequence number) store -- no
+// fence, no atomic, no ticket -- into this shard's mailbox and (mode 2, world > 1) straight into every peer's; block 0, the
+// finisher, polls the world x grid records of its own mailbox until their tags match, combines them and updates u_nom.
+// scratch: >= 2 * P floats of shared memory; sh_unom: the shifted nominal (prologue copy); big / big_floats: larger shared
+// scratch -- when the records fit they are staged there by the polling pass itself.
 __device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float* brec, float* partials, int n_ind, int H,
                                                  int period, float stdev, float lo, float hi, float neg_inv_lbd,
                                                  const float* sh_unom, float* scratch, float* sh_red, float* big = nullptr,
@@ -79,41 +123,39 @@ __device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float*
     for (int c = tid; c < P; c += blockDim.x) partials[(size_t)blockIdx.x * P + c] = brec[c];
     return;
   }
-  for (int c = tid; c < P; c += blockDim.x) st_tagged(f.tagged + (size_t)blockIdx.x * P + c, brec[c], f.lseq);
+  const int world = (f.mode == 2) ? f.world : 1;
+  const int rank = (world > 1) ? f.rank : 0;
+  const size_t base = (size_t)(f.seq & 1u) * CTK_MAX_PEERS * CTK_MBOX_BLOCKS * P;  // parity buffer
+  const size_t shard = (size_t)CTK_MBOX_BLOCKS * P;                                  // slots per source shard
+  {
+    const size_t mine = base + (size_t)rank * shard + (size_t)blockIdx.x * P;
+    for (int i = tid; i < world * P; i += blockDim.x) {
+      const int r = i / P, c = i - r * P;
+      st_tagged((world > 1 ? f.mbox_peer[r] : f.mbox_local) + mine + c, brec[c], f.seq);
+    }
+  }
   if (blockIdx.x != 0) return;
-  float* sh_rec = scratch;      // [P]
-  float* sh_all = scratch + P;  // [world][P]
+  float* sh_rec = scratch;  // [P]
   int status = 0;  // 0 ok, 1 a peer shard's record did not arrive, 2 a block record of this grid did not arrive
   const unsigned long long t0 = globaltimer_ns();
-  int lost = 0;
-  if (G * P <= big_floats) {
-    for (int i = tid; i < G * P; i += blockDim.x)
-      if (!ld_tagged(f.tagged + i, f.lseq, t0, big + i)) lost = 1;
-    if (__syncthreads_or(lost)) status = 2;
-    combine_records<false>(big, G, P, neg_inv_lbd, sh_rec, sh_red);
-  } else {  // records do not fit in shared memory: wait for all of them, then combine from global memory (low words)
-    float dummy;
-    for (int i = tid; i < G * P; i += blockDim.x)
-      if (!ld_tagged(f.tagged + i, f.lseq, t0, &dummy)) lost = 1;
-    if (__syncthreads_or(lost)) status = 2;
-    combine_records<true>(reinterpret_cast<const float*>(f.tagged), G, P, neg_inv_lbd, sh_rec, sh_red);
+  const int GP = G * P, nrec = world * G;
+  const unsigned long long* mb = f.mbox_local + base;
+  auto slot = [&](int i) -> const unsigned long long* {  // slot i of the world x G x P records that take part
+    const int r = i / GP, j = i - r * GP;
+    return mb + (size_t)r * shard + j;
+  };
+  if (nrec * P <= big_floats) {
+    const int lost = poll_tagged(slot, nrec * P, f.seq, t0, big);
+    if (__syncthreads_or(lost)) status = 1;
+    combine_records([&](int b, int c) { return big[b * P + c]; }, nrec, P, neg_inv_lbd, sh_rec, sh_red);
+  } else {  // records do not fit in shared memory: wait for all of them, then combine from global memory (low words, through L2)
+    const int lost = poll_tagged(slot, nrec * P, f.seq, t0, nullptr);
+    if (__syncthreads_or(lost)) status = 1;
+    combine_records([&](int b, int c) { return __ldcg(reinterpret_cast<const float*>(slot(b * P + c))); }, nrec, P, neg_inv_lbd, sh_rec, sh_red);
   }
   if (f.record_out != nullptr)
     for (int c = tid; c < P; c += blockDim.x) f.record_out[c] = sh_rec[c];
   if (f.mode < 2) return;
-  if (f.world > 1) {
-    // double-buffered by seq parity: a rank can be at most one tick ahead of its slowest peer
-    const size_t base = (size_t)(f.seq & 1u) * f.world * P;
-    for (int i = tid; i < f.world * P; i += blockDim.x) {
-      const int r = i / P, c = i - r * P;
-      st_tagged(f.mbox_peer[r] + base + (size_t)f.rank * P + c, sh_rec[c], f.seq);
-    }
-    lost = 0;
-    for (int i = tid; i < f.world * P; i += blockDim.x)
-      if (!ld_tagged(f.mbox_local + base + i, f.seq, t0, sh_all + i)) lost = 1;
-    if (__syncthreads_or(lost) && status == 0) status = 1;
-    combine_records<false>(sh_all, f.world, P, neg_inv_lbd, sh_rec, sh_red);
-  }
   // optimizer_mppi.py:190-191: u_nom <- clip(shift(u_nom) + interp(sum_n w_n z_n) * stdev / sum_n w_n)
   const float a = sh_rec[1];
   for (int t = tid; t < H; t += blockDim.x) {
@@ -138,7 +180,7 @@ __device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float*
 // number of rollouts: no tail wave).  Each thread keeps an online softmin over its rollouts; the block emits ONE record
 // [rho, a, b_z[n_ind]] at the end (a single block-wide reduction per launch).
 template <class Pred, int KIND, bool LOG>
-__global__ void __launch_bounds__(Pred::kMaxThreads) mppi_rollout_kernel(const MppiArgs a) {
+__global__ void __launch_bounds__(Pred::kMaxThreads, Pred::kMinBlocks) mppi_rollout_kernel(const MppiArgs a) {
   extern __shared__ float smem[];
   float* sh_unom = smem;                 // [H] shifted nominal
   float2* sh_w = reinterpret_cast<float2*>(smem + ((a.H + 1) & ~1));  // [period] interpolation weights (w0, w1)

@@ -13,7 +13,11 @@
 //    du = fma(dy, w_j, y0) is one instruction;
 //  * ILP rollouts per thread are advanced in lock step (independent dependency chains): the last warps of an SM
 //    sub-partition still fill the FMA pipe, which removes the tail the hi-wid-first warp arbiter otherwise produces;
-//  * prologue global loads (s0, u_prev, u_nom) are issued together; no other global read precedes the rollout loop.
+//  * the state-independent part of the prologue (the Philox draws of the first rollout group) runs BEFORE griddepcontrol.wait: in a
+//    back-to-back chain of ticks (programmatic dependent launch) it overlaps the previous tick's finish / exchange / launch gap;
+//    the global reads of the prologue (s0, u_prev, u_nom) follow the wait and were prefetched into L2 before the draws;
+//  * block 0, the finisher of the tick, carries fewer rollouts (t0 of blockDim.x threads): in a chain it is the block that starts
+//    last (its SM is the one the previous tick's finisher occupied) and it has to be through its rollouts when the others are.
 #pragma once
 #include "ctk_device.cuh"
 #include "ctk_kernels_mppi.cuh"
@@ -23,7 +27,20 @@ namespace ctk {
 
 struct Roll : ScaledState {  // one rollout's registers
   float ul, acc, y0, dy, y1;
+  float tot, comp;  // compensated running total of the per-segment cost sums (see fold_segment)
 };
+
+// The total cost S ~ 5e3 enters the softmin as exp(-(S - rho) / lambda) with lambda = 100: one ulp of S (4.9e-4) is 5e-6 relative
+// in the weight, and a 100-term sequential fp32 sum wanders by several ulp -- more than the reference's torch.mean over [H + 1]
+// (vectorised pairwise summation).  The stage costs are therefore summed per inducing-point segment (partial sums an order of
+// magnitude below S) and the segment sums enter the total through a compensated (Kahan) addition: 4 FADD per SEGMENT.
+__device__ __forceinline__ void fold_segment(Roll& r) {
+  const float y = r.acc - r.comp;
+  const float t = r.tot + y;
+  r.comp = (t - r.tot) - y;
+  r.tot = t;
+  r.acc = 0.0f;
+}
 
 // One rollout step.  wj = j/period (immediate when PERIOD is a template constant).
 template <int KIND, bool LOG>
@@ -59,21 +76,25 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
   float* sh_z = sh_part + 12 * (P + 1);                          // [n_ind][ILP*T] standard draws of the rollouts in flight
   float* sh_acc = sh_z + (size_t)max(a.n_ind * ILP, 2) * T_;  // [n_ind][T] per-thread sum_n e_n z_n,i
 
-  auto trace = [&](int slot) {  // optional per-block timeline (bench.py --trace): globaltimer at the phase boundaries
-    if (a.trace != nullptr && tid == 0) a.trace[(size_t)blockIdx.x * 8 + slot] = globaltimer_ns();
+  auto trace = [&](int slot) {  // optional per-block timeline (tools/k1_trace.py): globaltimer at the phase boundaries, last 4 launches
+    if (a.trace != nullptr && tid == 0) a.trace[((size_t)(a.fuse.seq & 3u) * CTK_MBOX_BLOCKS + blockIdx.x) * 8 + slot] = globaltimer_ns();
   };
   trace(0);
-  // ---- prologue: the only global reads before the loop are issued first and consumed last -- the Philox draws of the first
-  //      rollout group are generated while they are in flight (after the L2 flush they come from DRAM) ----
-  const float s0v = (tid < 6) ? a.s0.ld(tid) : 0.0f;
-  const float upv = a.u_prev[0];
-  const float unom_first = (tid < a.H) ? a.u_nom[min(tid + 1, a.H - 1)] : 0.0f;  // optimizer_mppi.py:184 (shift on read)
+  pdl_trigger();  // the next launch of the stream (the next tick of a chain) may be scheduled as soon as SMs free up
+  // ---- prologue.  Prefetch the lines the global reads below will touch (after an L2 flush they come from DRAM), generate the
+  //      Philox draws of the first rollout group -- they depend on nothing the previous tick produces -- and only then wait for the
+  //      previous launch of the stream to complete (no-op unless launched as a programmatic dependent) ----
+  if (tid < 8) {
+    const float* pf = (tid < 6) ? a.u_nom + tid * 32 : (tid == 6 ? a.u_prev : a.s0.p);
+    if (pf != nullptr && (tid >= 6 || tid * 32 < a.H)) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+  }
   const OdeHot& k = a.k;
   const int nblk = (a.n_ind + 3) >> 2;
+  const int Ta_ = (blockIdx.x == 0) ? a.t0 : T_;
   auto gen_noise = [&](int base) {  // K0: draws of the ILP rollouts of a group -> shared-memory stash
 #pragma unroll
     for (int q = 0; q < ILP; ++q) {
-      const int nq = base + q * T_ + tid;
+      const int nq = base + q * Ta_ + tid;
       const uint32_t ng = (uint32_t)(a.off + (nq < a.N ? nq : 0));
       float* sz = sh_z + q * T_ + tid;
       for (int blk = 0; blk < nblk; ++blk) {
@@ -85,12 +106,18 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
       }
     }
   };
-  gen_noise(blockIdx.x * T_ * ILP);
-  if (tid < a.H) sh_unom[tid] = unom_first;
-  for (int t = tid + T_; t < a.H; t += T_) sh_unom[t] = a.u_nom[min(t + 1, a.H - 1)];
+  // rollouts of this block: groups of ILP * Ta consecutive ids, Ta = the block's rollout-carrying threads (block 0: a.t0)
+  const int Ta = (blockIdx.x == 0) ? a.t0 : T_;
+  const int boff = (blockIdx.x == 0) ? 0 : ILP * (a.t0 + ((int)blockIdx.x - 1) * T_);
+  const int stride = ILP * (a.t0 + ((int)gridDim.x - 1) * T_);
+  if (tid < Ta) gen_noise(boff);
   for (int j = tid; j < period; j += T_) sh_w[j] = (float)j / (float)period;      // Interpolator.py:63-74
-  if (tid < 6) sh_red[tid] = s0v;
   for (int i = 0; i < a.n_ind; ++i) sh_acc[(size_t)i * T_ + tid] = 0.0f;
+  pdl_wait();
+  const float s0v = (tid < 6) ? a.s0.ld(tid) : 0.0f;
+  const float upv = a.u_prev[0];
+  for (int t = tid; t < a.H; t += T_) sh_unom[t] = a.u_nom[min(t + 1, a.H - 1)];  // optimizer_mppi.py:184 (shift on read)
+  if (tid < 6) sh_red[tid] = s0v;
   __syncthreads();
   const float th0 = sh_red[0], om0 = sh_red[1], c0 = sh_red[2], sn0 = sh_red[3], x0 = sh_red[4], v0 = sh_red[5];
   const float omc0 = 1.0f - cosf(th0);  // spec: E_pot uses cos(angle) of the measured state
@@ -102,23 +129,24 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
   const float pf = (float)period;
   const float segW1x2_full = pf - 1.0f;                                             // 2 sum_j j/p
   const float segW2_full = (pf - 1.0f) * (2.0f * pf - 1.0f) / (6.0f * pf);          // sum_j (j/p)^2
-  const int stride = gridDim.x * T_ * ILP;
   float rho_t = INFINITY, a_t = 0.0f;  // per-thread online softmin (optimizer_mppi.py:163-168, exact combine later)
   float* sa = sh_acc + tid;
 
-  for (int base = blockIdx.x * T_ * ILP; base < a.N; base += stride) {
+  if (tid < Ta)  // (warp-uniform: Ta is a multiple of 32; no block barrier inside the loop)
+  for (int base = boff; base < a.N; base += stride) {
     Roll r[ILP];
     int n[ILP];
     bool active[ILP];
-    if (base != (int)(blockIdx.x * T_ * ILP)) gen_noise(base);  // the first group's draws were generated in the prologue
+    if (base != boff) gen_noise(base);  // the first group's draws were generated in the prologue
 #pragma unroll
     for (int q = 0; q < ILP; ++q) {
-      n[q] = base + q * T_ + tid;
+      n[q] = base + q * Ta + tid;
       active[q] = n[q] < a.N;
       const float* sz = sh_z + q * T_ + tid;
       r[q].T = T0; r[q].W = W0; r[q].c = c0; r[q].s = sn0; r[q].x = x0; r[q].V = V0; r[q].omc = omc0;
       r[q].ul = upv;
       r[q].acc = (k.k_ccrc * upv) * upv;  // telescoped ccrc term of u_{-1}
+      r[q].tot = 0.0f; r[q].comp = 0.0f;
       r[q].y0 = 0.0f; r[q].dy = 0.0f;
       r[q].y1 = sz[0] * k.stdev;  // y0 of segment 0   (:173-175 normal * stdev before interpolation)
     }
@@ -161,6 +189,8 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
         }
       }
       t += cnt;
+#pragma unroll
+      for (int q = 0; q < ILP; ++q) fold_segment(r[q]);
     }
 
     // ---- per-rollout total + per-thread online softmin ----
@@ -173,7 +203,7 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
         p[4 * (size_t)a.N] = r[q].x; p[5 * (size_t)a.N] = r[q].V * k.inv_cFg;
       }
       // Cost_Functions/__init__.py:90-92 (mean over H+1 incl. the terminal cost); optimizer_mppi.py:160
-      const float S = finish_cost_scaled(r[q].acc, r[q], r[q].ul, k);
+      const float S = finish_cost_scaled(r[q].tot - r[q].comp, r[q], r[q].ul, k);
       if (active[q]) {
         a.J[n[q]] = S;
         if (S < INFINITY) {

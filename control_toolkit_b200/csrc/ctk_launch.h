@@ -37,6 +37,7 @@ int mppi_ode_max_block(int ilp);
 size_t mppi_ode_smem_bytes(int H, int period, int n_ind, int ilp, int block);
 cudaError_t launch_mppi_combine(const float* in, int cnt, int n_ind, float neg_inv_lbd, float* record_out,
                                 const MppiFinalize& fin, cudaStream_t st);
+cudaError_t launch_exchange_barrier(const MppiFuse& f, size_t bar_off, cudaStream_t st);
 cudaError_t launch_transpose(const float* in, float* out, int R, int C, cudaStream_t st);
 size_t mppi_pred_smem_floats(int pred, const MlpDev& m);
 

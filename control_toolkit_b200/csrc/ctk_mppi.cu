@@ -23,12 +23,17 @@ static cudaError_t launch_mppi_p(int kind, bool log, int nblocks, int block, siz
 }
 cudaError_t launch_mppi_rollout(int pred, int kind, bool log, int nblocks, int block, size_t smem, cudaStream_t st, const MppiArgs& a) {
   if (pred == 2) return launch_mppi_p<MlpTcPred>(kind, log, nblocks, block, smem, st, a);
+  if (pred == 3) return launch_mppi_p<MlpTcBf16Pred>(kind, log, nblocks, block, smem, st, a);
+  if (pred == 4) return launch_mppi_p<MlpTcFastPred>(kind, log, nblocks, block, smem, st, a);
   return pred == 0 ? launch_mppi_p<OdePred>(kind, log, nblocks, block, smem, st, a)
                    : launch_mppi_p<MlpSimtPred>(kind, log, nblocks, block, smem, st, a);
 }
-// pred: 0 ODE, 1 MLP on the FP32 pipe, 2 MLP with layer 2 on the tensor cores (tcgen05)
-int mppi_max_block_threads(int pred) { return pred == 0 ? OdePred::kMaxThreads : (pred == 2 ? MlpTcPred::kMaxThreads : MlpSimtPred::kMaxThreads); }
-size_t mppi_pred_smem_floats(int pred, const MlpDev& m) { return pred == 0 ? 0 : (pred == 2 ? MlpTcPred::smem_floats(m) : MlpSimtPred::smem_floats(m)); }
+// pred: 0 ODE, 1 MLP on the FP32 pipe, 2 MLP with layer 2 on the tensor cores (tcgen05, bf16 x 3 split: fp32-level), 3 / 4 the opt-in
+// single-bf16-product engines (3: exact tanh, 4: MUFU.TANH)
+int mppi_max_block_threads(int pred) { return pred == 0 ? OdePred::kMaxThreads : (pred >= 2 ? MlpTcPred::kMaxThreads : MlpSimtPred::kMaxThreads); }
+size_t mppi_pred_smem_floats(int pred, const MlpDev& m) {
+  return pred == 0 ? 0 : (pred == 2 ? MlpTcPred::smem_floats(m) : (pred >= 3 ? MlpTcBf16Pred::smem_floats(m) : MlpSimtPred::smem_floats(m)));
+}
 
 // K1 for the ODE predictor (ctk_kernels_mppi_ode.cuh).  period_t: 10 -> the segment-unrolled instantiation, else runtime period.
 template <int KIND, bool LOG, int PERIOD, int ILP, bool INJ>
@@ -38,8 +43,9 @@ static cudaError_t launch_mppi_ode_t(int grid, int block, size_t smem, cudaStrea
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  k<<<grid, block, smem, st>>>(a);
-  return cudaGetLastError();
+  // programmatic stream serialization: in a back-to-back chain of ticks the next launch's blocks are scheduled as this one's retire
+  // and run their state-independent prologue before griddepcontrol.wait (ctk_kernels_mppi_ode.cuh)
+  return launch_pdl(k, dim3(grid), dim3(block), smem, st, a);
 }
 // production instantiations: Philox noise only; injected noise (verification) and odd periods with logging run the
 // generic-period, one-rollout-per-thread instantiation (any launch geometry is valid for it: grid-stride loop)
@@ -85,6 +91,23 @@ cudaError_t launch_mppi_combine(const float* in, int cnt, int n_ind, float neg_i
                                 const MppiFinalize& fin, cudaStream_t st) {
   const size_t sm = sizeof(float) * (32 + 2 + n_ind + (fin.enable ? fin.H : 0));
   mppi_combine_kernel<<<1, 1024, sm, st>>>(in, cnt, n_ind, neg_inv_lbd, record_out, fin);
+  return cudaGetLastError();
+}
+
+// Cross-shard barrier on the device (bench.py: aligns the shards' streams before a timed tick so that skew accumulated OUTSIDE the
+// timed region -- the un-synchronised L2 flush -- is not spent waiting inside the tick's exchange): every shard stores a tagged flag
+// into every mailbox's barrier area and polls its own.
+__global__ void exchange_barrier_kernel(MppiFuse f, size_t bar_off) {
+  const int tid = threadIdx.x;
+  const size_t o = bar_off + (size_t)(f.seq & 1u) * CTK_MAX_PEERS;
+  if (tid < f.world) st_tagged(f.mbox_peer[tid] + o + f.rank, 1.0f, f.seq);
+  if (tid < f.world) {
+    float v;
+    ld_tagged(f.mbox_local + o + tid, f.seq, globaltimer_ns(), &v);
+  }
+}
+cudaError_t launch_exchange_barrier(const MppiFuse& f, size_t bar_off, cudaStream_t st) {
+  exchange_barrier_kernel<<<1, 32, 0, st>>>(f, bar_off);
   return cudaGetLastError();
 }
 

@@ -16,6 +16,7 @@ struct OdePred {
 #define CTK_ODE_MAX_THREADS 1024
 #endif
   static constexpr int kMaxThreads = CTK_ODE_MAX_THREADS;
+  static constexpr int kMinBlocks = 1;
   FwdK p;  // forward constants, register-resident (ctk_device.cuh load_fwd)
   __device__ __forceinline__ OdePred(const DevConsts* kc, const MlpDev&, float*) : p(load_fwd(kc)) {}
   // take the FMA-multiplier constants from kernel parameters (uniform registers) instead of vector registers
@@ -43,6 +44,7 @@ struct MlpSimtPred {
   static constexpr bool kCooperative = false;
   static constexpr int kRolloutsPerBlock = 0;
   static constexpr int kMaxThreads = 128;
+  static constexpr int kMinBlocks = 1;
   int hid;
   const float *W1, *b1, *W2, *b2, *W3T, *b3;  // shared memory
   __device__ __forceinline__ MlpSimtPred(const DevConsts*, const MlpDev& m, float* sm) {

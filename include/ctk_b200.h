@@ -37,7 +37,11 @@ enum { CTK_PRED_ODE = 0, CTK_PRED_MLP = 1 };                             /* pred
 enum { CTK_COST_DEFAULT = 0, CTK_COST_QUADRATIC_BOUNDARY_GRAD = 1 };     /* cost_function_specification                         */
 enum { CTK_DIST_NORMAL = 0, CTK_DIST_UNIFORM = 1 };                      /* RPGD SAMPLING_DISTRIBUTION                          */
 enum { CTK_ADAM_KERAS = 0, CTK_ADAM_TORCH = 1 };                         /* reference optimizer_rpgd.py:34-43 vs :56-82         */
-enum { CTK_MLP_SIMT = 0, CTK_MLP_TCGEN05 = 1 };                          /* MLP predictor engine                                */
+/* MLP predictor engine.  SIMT: FP32 pipe (numerical anchor).  TCGEN05: 128 x 128 layer on the tensor cores as six products of
+   three-term bf16 splits (fp32-level accuracy, passes the fp32 reference fixtures).  TCGEN05_BF16 / TCGEN05_FAST: opt-in reduced
+   precision -- ONE bf16 product (operands rounded to bfloat16, fp32 accumulation); _FAST additionally evaluates tanh with the
+   single-instruction MUFU.TANH (~2^-11 relative).  Parity of _BF16 is defined against an oracle applying the same operand rounding. */
+enum { CTK_MLP_SIMT = 0, CTK_MLP_TCGEN05 = 1, CTK_MLP_TCGEN05_BF16 = 2, CTK_MLP_TCGEN05_FAST = 3 };
 
 /* which = state arrays (get/set).  Layouts are the reference's: [1,H,nu] or [N,H,nu] row-major.                 */
 enum {
@@ -187,6 +191,11 @@ int ctk_step_finish(ctk_handle *h, const float *gathered_dev, int num_shards, fl
    softmin record, NVLink record exchange, u_nom update -- is ONE kernel launch.                                    */
 int ctk_step_device(ctk_handle *h, const float *s_dev, float *u_out_dev);
 
+/* n ticks back to back (states s_dev + i * s_stride floats, results [u, status] to u_out_dev + i * u_stride floats; u_out_dev may
+   be NULL): one call enqueues the whole chain, consecutive ticks overlap through programmatic dependent launch -- the next tick's
+   in-kernel noise generation runs underneath the previous tick's finish / exchange / launch gap.                          */
+int ctk_step_device_n(ctk_handle *h, const float *s_dev, size_t s_stride, float *u_out_dev, size_t u_stride, int n);
+
 /* ---- fused cross-GPU exchange (MPPI) --------------------------------------------------------------- */
 /* Each shard owns a mailbox in its HBM; peers store their softmin record (n_ind + 2 values, each packed with the tick's
    sequence number in one 8-byte store) straight into it over NVLink from inside the rollout kernel, and the last block
@@ -197,6 +206,9 @@ int ctk_step_device(ctk_handle *h, const float *s_dev, float *u_out_dev);
 int ctk_exchange_export(ctk_handle *h, void *ipc_handle_out64);
 int ctk_exchange_connect(ctk_handle *h, int rank, int world, const void *ipc_handles /* world x 64 bytes */);
 int ctk_exchange_mailbox(ctk_handle *h, void **dev_ptr);
+/* device-side barrier across the connected shards on the handle's stream (one tiny kernel: tagged flags through the mailboxes);
+   bench.py aligns the shards with it BEFORE a timed tick, so that skew from outside the timed region is not measured inside  */
+int ctk_exchange_barrier(ctk_handle *h);
 int ctk_exchange_connect_ptrs(ctk_handle *h, int rank, int world, void *const *mailboxes, const int *devices);
 
 /* ---- state / logs ------------------------------------------------------------------------------------------- */

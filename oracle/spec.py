@@ -190,13 +190,21 @@ class MLPPredictor:
     num_states = NUM_STATES
     num_control_inputs = NUM_CONTROLS
 
-    def __init__(self, weights: MLPWeights, dtype=torch.float32):
+    def __init__(self, weights: MLPWeights, dtype=torch.float32, bf16_layer2: bool = False):
+        """bf16_layer2: the input rounding of the opt-in 'tcgen05_bf16' / 'tcgen05_fast' engines -- the operands of the 128 x 128
+        layer (h1 and W2) are rounded to bfloat16 (round to nearest even), products and sums stay fp32 (SURVEY section 7 hard part 4:
+        'the MLP parity is defined against an oracle that applies the same input rounding')."""
         self.w = weights
+        self.bf16_layer2 = bool(bf16_layer2)
         self.t = {k: torch.from_numpy(np.ascontiguousarray(getattr(weights, k))).to(dtype) for k in ("W1", "b1", "W2", "b2", "W3", "b3")}
+        if self.bf16_layer2:
+            self.t["W2"] = self.t["W2"].to(torch.bfloat16).to(dtype)
 
     def step(self, s: torch.Tensor, Q: torch.Tensor) -> torch.Tensor:
         x = torch.cat([Q, s[:, 1:]], dim=1)  # [N,6]
         h1 = torch.tanh(x @ self.t["W1"] + self.t["b1"])
+        if self.bf16_layer2:
+            h1 = h1.to(torch.bfloat16).to(h1.dtype)
         h2 = torch.tanh(h1 @ self.t["W2"] + self.t["b2"])
         y = h2 @ self.t["W3"] + self.t["b3"]  # [N,5]
         angle = torch.atan2(y[:, 2], y[:, 1])

@@ -9,7 +9,7 @@ identical numbers.  Every test asserts ``optimizer.last_kernel`` -- the instanti
 
 Tolerances: north star 1e-5 relative on u / optimizer state, asserted HARD wherever the path is well conditioned (C1, C2, C4, C5);
 where the reference's own fp32-vs-float64 deviation on that very tick (floor) is larger, the symmetric criterion
-|cuda - float64 truth| <= max(1e-5, 2 x |reference fp32 - float64 truth|) is asserted instead (see test_gpu_parity.py docstring).
+|cuda - float64 truth| <= max(1e-5, 3 x |reference fp32 - float64 truth|) is asserted instead (see test_gpu_parity.py docstring).
 """
 import os
 
@@ -51,7 +51,7 @@ def _assert_state(tag, e32, e64, floor, hard):
         assert e32 < TOL, (tag, e32, e64, floor)
     else:
         assert e32 < min(max(2e-5, 6.0 * floor), 1e-4), (tag, e32, floor)
-    assert e64 <= max(TOL, 2.0 * floor), (tag, "distance to the float64 truth", e64, floor)
+    assert e64 <= max(TOL, 3.0 * floor), (tag, "distance to the float64 truth", e64, floor)
 
 
 MPPI_CASES = [
@@ -205,10 +205,12 @@ def test_rpgd_production_one_launch_tick_matches_oracle(adam_form):
     o32.reset(QueueRNG([z0]))
     o64.reset(QueueRNG([z0]))
     assert max_rel(opt.Q_tf, o32.Q.numpy()) < 1e-6
-    launches0 = opt.gpu_launches
+    launches = 0
     for t, s in enumerate(spec.synthetic_states(12, seed=35)):
         resample = opt.count % opt.resamp_per == 0
+        l0 = opt.gpu_launches
         u = ctrl.step(s)
+        launches += opt.gpu_launches - l0  # (the state read-backs below launch layout transposes of their own)
         blocks = [opt.export_philox(L.STREAM_RPGD_RESAMPLE, opt.tick_counter, n_ind, N - k, uniform=uni)] if resample else []
         u32 = o32.step(s, QueueRNG(blocks))
         o64.step(s, QueueRNG(blocks))
@@ -221,7 +223,7 @@ def test_rpgd_production_one_launch_tick_matches_oracle(adam_form):
         _report(f"production rpgd {adam_form} tick {t}: m {em:.2e} (floor {fm:.2e}) v {ev:.2e} (floor {fv:.2e})")
         assert em < max(1e-4, 10 * fm) and ev < max(1e-4, 10 * fv)
         assert np.max(np.abs(np.ravel(u) - np.ravel(u32))) < 1e-4
-    assert opt.gpu_launches - launches0 == 12  # one launch per tick
+    assert launches == 12  # one launch per tick
 
 
 def test_philox_export_is_what_the_kernels_draw():
@@ -248,3 +250,44 @@ def test_philox_export_is_what_the_kernels_draw():
     z2 = opt.export_philox(L.STREAM_MPPI, opt.tick_counter, opt.number_of_interpolation_inducing_points, 100, row0=50)
     np.testing.assert_array_equal(z2, z[50:150])
     assert not np.array_equal(opt.export_philox(L.STREAM_MPPI, opt.tick_counter + 1, 6, 100), z[:100])
+
+
+@pytest.mark.parametrize("engine,kernel", [("tcgen05_bf16", "mppi_rollout_kernel<MlpTcBf16Pred,0,0> [philox]"),
+                                            ("tcgen05_fast", "mppi_rollout_kernel<MlpTcFastPred,0,0> [philox]")])
+def test_mppi_mlp_reduced_precision_engines(engine, kernel):
+    """The opt-in single-bf16-product engines (SURVEY section 7 hard part 4).  `tcgen05_bf16`: parity is DEFINED against an oracle that
+    applies the same operand rounding (h1 and W2 to bfloat16, round to nearest even: oracle/spec.py MLPPredictor(bf16_layer2=True));
+    the rounding is discontinuous (an fp32 ulp in h1 can flip a bf16 rounding), so the bound is 1e-4 on u_nom, not 1e-5.
+    `tcgen05_fast` (+ MUFU.TANH, ~2^-11 relative per activation) is not held to a parity bound: its distance to the fp32 oracle is
+    measured and bounded loosely (the controls live in [-1, 1])."""
+    from control_toolkit_b200 import _lib as L
+    from oracle import spec
+    from oracle.replay_rng import QueueRNG
+    _, meta = load_golden("mppi_mlp_c4_n256")
+    N, H = 16384, 100
+    meta = dict(meta, cfg=dict(meta["cfg"], num_rollouts=N, mpc_horizon=H))
+    ctrl = make_controller(meta, rng=None, logging=False, mlp_engine=engine)
+    opt = ctrl.optimizer
+    o_same = make_oracle(meta)
+    o_same.predictor = spec.MLPPredictor(spec.MLPWeights.random_init(meta["mlp_seed"]), bf16_layer2=True)
+    o_fp32 = make_oracle(meta)
+    for t, s in enumerate(spec.synthetic_states(2, seed=36)):
+        ctrl.step(s)
+        assert opt.last_kernel == kernel, opt.last_kernel
+        z = opt.export_philox(L.STREAM_MPPI, opt.tick_counter, opt.number_of_interpolation_inducing_points, N)
+        o_same.step_chunked(s, QueueRNG([z]), chunk=16384)
+        o_fp32.step_chunked(s, QueueRNG([z]), chunk=16384)
+        e_same = max_rel(opt.u_nom, o_same.u_nom.numpy(), floor=1e-2)
+        e_fp32 = max_rel(opt.u_nom, o_fp32.u_nom.numpy(), floor=1e-2)
+        J = opt._get_log(L.LOG_J, (N,))
+        eJ = np.abs(J.astype(np.float64) - o_same.last["J"]) / (np.abs(o_same.last["J"]) + 1e-3)
+        _report(f"mlp engine {engine} N={N} tick {t}: u_nom vs same-rounding oracle {e_same:.2e}, vs fp32 oracle {e_fp32:.2e}; "
+                f"J vs same-rounding oracle median {np.median(eJ):.2e} q99 {np.quantile(eJ, 0.99):.2e}")
+        if engine == "tcgen05_bf16":
+            assert e_same < 1e-4, (t, e_same)
+            assert np.median(eJ) < 1e-4
+        assert e_fp32 < 2e-2, (t, e_fp32)
+        # keep the two oracles on the device's trajectory of optimizer states (the comparison is per tick)
+        for o in (o_same, o_fp32):
+            o.u_nom = __import__("torch").from_numpy(opt.u_nom.copy())
+            o.u = np.float32(opt.u)
