@@ -76,13 +76,21 @@ struct alignas(16) HotUK {
 // them exactly to the global minimum and updates u_nom / u.  Every shard combines the same records in the same order: the
 // replicated optimizer state stays bit-identical.  Replaces reference optimizer_mppi.py:163-168,190-191 (+ the cross-shard
 // weighted-sum exchange of SURVEY 8e).
-// Mailbox layout (uint64 slots): [2 (sequence parity)][CTK_MAX_PEERS (source shard)][CTK_MBOX_BLOCKS (source block)][2 + n_ind],
-// then the barrier area [2][CTK_MAX_PEERS].  Double-buffered by parity: a shard can be at most one tick ahead of its slowest peer.
+// Mailbox layout (uint64 slots): [2 (sequence parity)][CTK_MAX_PEERS (source shard)][CTK_MBOX_BLOCKS (source block)][record stride],
+// then the barrier area [2][CTK_MAX_PEERS] and the hand-over slots.  Double-buffered by parity: a shard can be at most one tick
+// ahead of its slowest peer.
+// Chained ticks (ctk_step_device_n): the finisher also publishes u_prev and u_nom[H] as tagged slots (handover); the next tick of the
+// chain polls them instead of waiting for the previous launch to complete (griddepcontrol.wait), which takes the kernel-completion /
+// dependent-release latency off the tick-to-tick critical path.
 // ----------------------------------------------------------------------------------------------------------------
 constexpr int CTK_MAX_PEERS = 8;
 constexpr int CTK_MBOX_BLOCKS = 320;  // >= the grid of any rollout kernel (one or two CTAs per SM: 148 SMs on B200)
-CTK_HD size_t mbox_record_slots(int n_ind) { return (size_t)2 * CTK_MAX_PEERS * CTK_MBOX_BLOCKS * (n_ind + 2); }
-CTK_HD size_t mbox_total_slots(int n_ind) { return mbox_record_slots(n_ind) + 2 * CTK_MAX_PEERS; }
+CTK_HD int mbox_record_stride(int n_ind) { return (n_ind + 3) & ~1; }  // slots per record: 2 + n_ind padded to even (16-byte polls)
+CTK_HD size_t mbox_record_slots(int n_ind) { return (size_t)2 * CTK_MAX_PEERS * CTK_MBOX_BLOCKS * mbox_record_stride(n_ind); }
+// + barrier area [2][CTK_MAX_PEERS] + tagged hand-over of the tick's result to the next tick of a chain: u_prev, u_nom[H] (H <= 4096 slots)
+CTK_HD size_t mbox_barrier_offset(int n_ind) { return mbox_record_slots(n_ind); }
+CTK_HD size_t mbox_handover_offset(int n_ind) { return mbox_record_slots(n_ind) + 2 * CTK_MAX_PEERS; }
+CTK_HD size_t mbox_total_slots(int n_ind, int H) { return mbox_handover_offset(n_ind) + 1 + (size_t)H; }
 struct MppiFuse {
   int mode;                  // 0: block records only (legacy K2 launch follows)  1: + shard record (staged exchange)  2: + finalize
   int world, rank;           // shards taking part in the exchange (1: no exchange)
@@ -90,6 +98,9 @@ struct MppiFuse {
   float* record_out;         // [2 + n_ind] shard record (mode >= 1)
   unsigned long long* mbox_local;                 // this shard's mailbox
   unsigned long long* mbox_peer[CTK_MAX_PEERS];   // every shard's mailbox (mbox_peer[rank] == mbox_local)
+  unsigned long long* handover;                   // [1 + H] tagged u_prev, u_nom[H] of the tick (local)
+  unsigned long long* trace; // diagnostics: block 0's row of the phase timeline (slots 6, 7: records polled, records combined) or null
+  int chained;               // 1: the previous launch of the stream is the previous tick of this handle's chain: poll its hand-over
   float* u_nom;              // [H] in/out
   float* u_prev;             // [1] out (unless frozen)
   float* u_out;              // [2] out: u, status (0 ok, 1 a peer's record missing, 2 a local block's record missing)

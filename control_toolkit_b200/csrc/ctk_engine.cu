@@ -59,6 +59,7 @@ struct ctk_handle {
   // fused tick finish / cross-GPU exchange (MppiFuse)
   unsigned long long* d_mbox = nullptr;           // local mailbox (layout: MppiFuse)
   unsigned int bseq = 0;                          // sequence number of the exchange barrier (ctk_exchange_barrier)
+  bool chain_hint = false;                        // set by ctk_step_device_n for ticks 1.. of a chain: the tick may poll the hand-over
   int ode_t0 = 0;                                 // rollout-carrying threads of block 0 (the finisher's reduced share)
   unsigned long long* mbox_peer[CTK_MAX_PEERS] = {nullptr};
   bool mbox_ipc[CTK_MAX_PEERS] = {false};
@@ -316,7 +317,7 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
     A(dalloc(&h->d_partials, (size_t)(h->num_sms > h->mppi_grid ? h->num_sms : h->mppi_grid) * (h->mppi_iters + 1) * (h->n_ind + 2)), "partials");
     A(dalloc(&h->d_record, (size_t)(h->n_ind + 2)), "record");
     if (h->mppi_grid > CTK_MBOX_BLOCKS || h->num_sms > CTK_MBOX_BLOCKS) { ctk_destroy(h); return fail(CTK_EINVAL, "device has more SMs than the mailbox has block slots (CTK_MBOX_BLOCKS)"); }
-    A(dalloc(&h->d_mbox, mbox_total_slots(h->n_ind)), "mailbox");
+    A(dalloc(&h->d_mbox, mbox_total_slots(h->n_ind, H)), "mailbox");
     h->mbox_peer[0] = h->d_mbox;
   } else if (cfg->optimizer == CTK_OPT_CEM) {
     if (!(cfg->cem_best_k >= 1 && cfg->cem_best_k <= 512 && cfg->cem_best_k <= cfg->num_rollouts_global && H <= 1024 && cfg->cem_outer_it >= 1)) {
@@ -623,6 +624,10 @@ static int make_fuse(ctk_handle* h, int mode, float* u_out_dev, MppiFuse* out) {
   f.seq = h->xseq;
   f.record_out = h->d_record;
   f.mbox_local = h->d_mbox;
+  f.handover = h->d_mbox + mbox_handover_offset(h->n_ind);
+  f.trace = h->d_trace ? h->d_trace + (size_t)(h->xseq & 3u) * CTK_MBOX_BLOCKS * 8 : nullptr;
+  f.chained = (mode == 2 && h->chain_hint && h->ode_kernel && h->xseq > 1) ? 1 : 0;
+  h->chain_hint = false;
   for (int r = 0; r < CTK_MAX_PEERS; ++r) f.mbox_peer[r] = h->mbox_peer[r];
   f.u_nom = h->d_u_nom; f.u_prev = h->d_u_prev; f.u_out = u_out_dev; f.freeze_prev = h->cfg.freeze_previous_input;
   if (mode == 2) f.host = h->mirror;
@@ -1219,8 +1224,13 @@ extern "C" int ctk_step_device(ctk_handle* h, const float* s_dev, float* u_out_d
 // dependent launch (the next tick's noise generation runs underneath the previous tick's finish / exchange / launch gap).
 extern "C" int ctk_step_device_n(ctk_handle* h, const float* s_dev, size_t s_stride, float* u_out_dev, size_t u_stride, int n) {
   REQ(h && s_dev && n >= 0, "null pointer or negative tick count");
+  static const bool handover = getenv("CTK_NO_HANDOVER") == nullptr;
   for (int i = 0; i < n; ++i) {
+    // ticks 1.. of the chain: nothing but this handle's previous tick precedes them on the stream, and the caller's states were
+    // complete before tick 0 was launched, so they may take u_nom from the previous finisher's tagged hand-over
+    h->chain_hint = i > 0 && handover && h->cfg.optimizer == CTK_OPT_MPPI;
     int rc = ctk_step_device(h, s_dev + (size_t)i * s_stride, u_out_dev ? u_out_dev + (size_t)i * u_stride : nullptr);
+    h->chain_hint = false;
     if (rc != CTK_OK) return rc;
   }
   return CTK_OK;
@@ -1248,7 +1258,7 @@ static int exchange_reset(ctk_handle* h, int rank, int world) {
   }
   h->xworld = world; h->xrank = rank; h->xseq = 0;
   h->bseq = 0;
-  CU(cudaMemset(h->d_mbox, 0, sizeof(unsigned long long) * mbox_total_slots(h->n_ind)));
+  CU(cudaMemset(h->d_mbox, 0, sizeof(unsigned long long) * mbox_total_slots(h->n_ind, h->H)));
   return CTK_OK;
 }
 extern "C" int ctk_exchange_connect(ctk_handle* h, int rank, int world, const void* ipc_handles) {
@@ -1285,7 +1295,7 @@ extern "C" int ctk_exchange_barrier(ctk_handle* h) {
   f.mbox_local = h->d_mbox;
   for (int r = 0; r < CTK_MAX_PEERS; ++r) f.mbox_peer[r] = h->mbox_peer[r];
   h->launches++;
-  CU(launch_exchange_barrier(f, mbox_record_slots(h->n_ind), h->stream));
+  CU(launch_exchange_barrier(f, mbox_barrier_offset(h->n_ind), h->stream));
   return CTK_OK;
 }
 extern "C" int ctk_exchange_mailbox(ctk_handle* h, void** dev_ptr) {

@@ -38,72 +38,80 @@ __device__ __forceinline__ void mppi_step(const MppiArgs& a, const CostC& cost, 
 // ----------------------------------------------------------------------------------------------------------------
 // Tick finish inside the rollout kernel (MppiFuse): combine softmin records, exchange across GPUs, update u_nom.
 // ----------------------------------------------------------------------------------------------------------------
-// records rec(b, c), b < cnt, c < P: [rho, a, b_z[n_ind]] -> out[P] (shared memory), rescaled exactly to the common minimum.
-// All threads participate.
-template <class Rec>
-__device__ __forceinline__ void combine_records(Rec rec, int cnt, int P, float neg_inv_lbd, float* out, float* sh_red) {
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
-  float mn = INFINITY;
-  for (int b = tid; b < cnt; b += blockDim.x) mn = fminf(mn, rec(b, 0));
-  const float rho = block_min(mn, sh_red);
-  for (int c = w; c < P - 1; c += nw) {
-    float acc = 0.0f;
-    for (int b = lane; b < cnt; b += 32) {
-      const float rb = rec(b, 0);
-      const float v = rec(b, 1 + c);
-      const float sc = (rb < INFINITY) ? expf((rb - rho) * neg_inv_lbd) : 0.0f;
-      acc = fmaf(sc, v, acc);
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) out[1 + c] = acc;
-  }
-  if (tid == 0) out[0] = rho;
-  __syncthreads();
-}
-
-// Poll n tagged slots src(i) until their sequence numbers match; values -> dst[i] (dst may be null: wait only).  Up to four
-// loads per thread are in flight before the first tag is checked (a dependent poll per slot would serialise the L2 latency).
-// Returns 0, or 1 if a slot did not arrive within ~2 s.
-template <class Src>
-__device__ __forceinline__ int poll_tagged(Src src, int n, unsigned int seq, unsigned long long t0, float* dst) {
+// Poll the nrec records rec_ptr(m) (P tagged slots each, stride even: 16-byte loads) until all their sequence numbers match;
+// values -> dst[m * P + c] (dst may be null: wait only).  Thread t owns records t, t + blockDim, ...: all loads of a record are in
+// flight before the first tag is checked, and a thread's records are polled in turn, so after the LAST record of the tick has
+// landed the poll completes within one or two L2 round trips.  Returns 0, or 1 if a record did not arrive within ~2 s.
+template <class RecPtr>
+__device__ __forceinline__ int poll_records(RecPtr rec_ptr, int nrec, int P, unsigned int seq, unsigned long long t0, float* dst) {
+  constexpr int MAXP2 = 8;  // up to 16 slots (n_ind <= 14) per record take the fast path
   const int tid = threadIdx.x, T = blockDim.x;
+  const int P2 = (P + 1) >> 1;
   int lost = 0;
-  for (int base = 0; base < n; base += 4 * T) {
-    const unsigned long long* p[4];
-    bool need[4];
-    float val[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = base + j * T + tid;
-      need[j] = i < n;
-      p[j] = src(need[j] ? i : 0);
-      val[j] = 0.0f;
-    }
+  if (P2 <= MAXP2) {
+    unsigned int pending = 0;  // bit j: record tid + j * T still missing
+    const int mine = (nrec - tid + T - 1) / T;  // records owned by this thread
+    for (int j = 0; j < mine && j < 32; ++j) pending |= 1u << j;
     int spins = 0;
-    while (true) {
-      unsigned long long v[4];
+    while (pending) {
+      for (int j = 0; j < mine && j < 32; ++j) {
+        if (!(pending & (1u << j))) continue;
+        const int m = tid + j * T;
+        const unsigned long long* p = rec_ptr(m);
+        unsigned long long v[2 * MAXP2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (need[j]) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v[j]) : "l"(p[j]) : "memory");
-      bool pending = false;
+        for (int q = 0; q < MAXP2; ++q)
+          if (q < P2) asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v[2 * q]), "=l"(v[2 * q + 1]) : "l"(p + 2 * q) : "memory");
+        bool ok = true;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (!need[j]) continue;
-        if ((unsigned int)(v[j] >> 32) == seq) { val[j] = __uint_as_float((unsigned int)(v[j] & 0xffffffffull)); need[j] = false; }
-        else pending = true;
+        for (int c = 0; c < 2 * MAXP2; ++c)
+          if (c < P) ok = ok && ((unsigned int)(v[c] >> 32) == seq);
+        if (ok) {
+          if (dst != nullptr) {
+#pragma unroll
+            for (int c = 0; c < 2 * MAXP2; ++c)
+              if (c < P) dst[m * P + c] = __uint_as_float((unsigned int)(v[c] & 0xffffffffull));
+          }
+          pending &= ~(1u << j);
+        }
       }
-      if (!pending) break;
-      if ((++spins & 1023) == 0 && globaltimer_ns() - t0 > 2000000000ull) { lost = 1; break; }
+      if (pending && (++spins & 255) == 0 && globaltimer_ns() - t0 > 2000000000ull) { lost = 1; break; }
     }
-    if (dst != nullptr) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int i = base + j * T + tid;
-        if (i < n) dst[i] = val[j];
-      }
+    if (mine > 32) lost = 1;  // (cannot happen: nrec <= 8 x 320 records over >= 128 threads)
+  } else {  // many inducing points: slot by slot
+    for (int i = tid; i < nrec * P; i += T) {
+      const int m = i / P, c = i - m * P;
+      float v;
+      if (!ld_tagged(rec_ptr(m) + c, seq, t0, &v)) lost = 1;
+      if (dst != nullptr) dst[i] = v;
     }
   }
   return lost;
+}
+
+// records rec(b, c), b < cnt, c < P: [rho, a, b_z[n_ind]] -> out[P] (shared memory), rescaled exactly to the common minimum.
+// Fallback for record sets that do not fit in shared memory (read through L2); every warp derives the common minimum itself.
+template <class Rec>
+__device__ __forceinline__ void combine_records(Rec rec, int cnt, int P, float neg_inv_lbd, float* out) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+  if (w < P - 1) {
+    float mn = INFINITY;
+    for (int b = lane; b < cnt; b += 32) mn = fminf(mn, rec(b, 0));
+    const float rho = warp_min(mn);
+    for (int c = w; c < P - 1; c += nw) {
+      float acc = 0.0f;
+      for (int b = lane; b < cnt; b += 32) {
+        const float rb = rec(b, 0);
+        const float v = rec(b, 1 + c);
+        const float sc = (rb < INFINITY) ? expf((rb - rho) * neg_inv_lbd) : 0.0f;
+        acc = fmaf(sc, v, acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) out[1 + c] = acc;
+    }
+    if (w == 0 && lane == 0) out[0] = rho;
+  }
+  __syncthreads();
 }
 
 // Called by ALL threads of EVERY block once the block's record brec[P] = [rho_b, a_b, b_z[n_ind]] is complete in SHARED
@@ -111,13 +119,17 @@ __device__ __forceinline__ int poll_tagged(Src src, int n, unsigned int seq, uns
 // separate combine launch follows).  mode >= 1: every value is published as ONE 8-byte (value, sequence number) store -- no
 // fence, no atomic, no ticket -- into this shard's mailbox and (mode 2, world > 1) straight into every peer's; block 0, the
 // finisher, polls the world x grid records of its own mailbox until their tags match, combines them and updates u_nom.
-// scratch: >= 2 * P floats of shared memory; sh_unom: the shifted nominal (prologue copy); big / big_floats: larger shared
-// scratch -- when the records fit they are staged there by the polling pass itself.
+// scratch: >= 3 * P + 2 floats of shared memory; sh_unom: the shifted nominal (prologue copy); wtab: [period] interpolation weights;
+// big / big_floats: larger shared scratch -- when the records fit they are staged there by the polling pass itself.
+// The summation order depends only on (world, grid, P) -- never on the block size -- so every shard, whatever its launch geometry,
+// computes bit-identical results from the same records.
 __device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float* brec, float* partials, int n_ind, int H,
                                                  int period, float stdev, float lo, float hi, float neg_inv_lbd,
-                                                 const float* sh_unom, float* scratch, float* sh_red, float* big = nullptr,
-                                                 int big_floats = 0) {
-  const int tid = threadIdx.x, P = n_ind + 2, G = (int)gridDim.x;
+                                                 const float* sh_unom, const float2* wtab, float* scratch, float* sh_red,
+                                                 float* big = nullptr, int big_floats = 0) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5, P = n_ind + 2, G = (int)gridDim.x;
+  unsigned int* sh_min = reinterpret_cast<unsigned int*>(sh_red);
+  if (tid == 0) sh_min[0] = 0xffffffffu;
   __syncthreads();
   if (f.mode == 0) {
     for (int c = tid; c < P; c += blockDim.x) partials[(size_t)blockIdx.x * P + c] = brec[c];
@@ -125,33 +137,62 @@ __device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float*
   }
   const int world = (f.mode == 2) ? f.world : 1;
   const int rank = (world > 1) ? f.rank : 0;
-  const size_t base = (size_t)(f.seq & 1u) * CTK_MAX_PEERS * CTK_MBOX_BLOCKS * P;  // parity buffer
-  const size_t shard = (size_t)CTK_MBOX_BLOCKS * P;                                  // slots per source shard
+  const int RS = mbox_record_stride(n_ind);
+  const size_t base = (size_t)(f.seq & 1u) * CTK_MAX_PEERS * CTK_MBOX_BLOCKS * RS;  // parity buffer
+  const size_t shard = (size_t)CTK_MBOX_BLOCKS * RS;                                  // slots per source shard
   {
-    const size_t mine = base + (size_t)rank * shard + (size_t)blockIdx.x * P;
+    const size_t mine = base + (size_t)rank * shard + (size_t)blockIdx.x * RS;
     for (int i = tid; i < world * P; i += blockDim.x) {
       const int r = i / P, c = i - r * P;
       st_tagged((world > 1 ? f.mbox_peer[r] : f.mbox_local) + mine + c, brec[c], f.seq);
     }
   }
   if (blockIdx.x != 0) return;
-  float* sh_rec = scratch;  // [P]
-  int status = 0;  // 0 ok, 1 a peer shard's record did not arrive, 2 a block record of this grid did not arrive
+  float* sh_rec = scratch;          // [P]
+  float* sh_half = scratch + P;     // [2][P] partial column sums of the two halves of a large record set
+  int status = 0;  // 0 ok, 1 a block record of this grid or of a peer shard did not arrive
   const unsigned long long t0 = globaltimer_ns();
-  const int GP = G * P, nrec = world * G;
+  const int nrec = world * G;
   const unsigned long long* mb = f.mbox_local + base;
-  auto slot = [&](int i) -> const unsigned long long* {  // slot i of the world x G x P records that take part
-    const int r = i / GP, j = i - r * GP;
-    return mb + (size_t)r * shard + j;
+  auto rec_ptr = [&](int m) -> const unsigned long long* {  // record m of the world x G records that take part
+    const int r = m / G, b = m - r * G;
+    return mb + (size_t)r * shard + (size_t)b * RS;
   };
   if (nrec * P <= big_floats) {
-    const int lost = poll_tagged(slot, nrec * P, f.seq, t0, big);
+    const int lost = poll_records(rec_ptr, nrec, P, f.seq, t0, big);
+    // common minimum: the thread's own records (it has just written them) -> warp (redux) -> block (one shared atomic per warp)
+    float mn = INFINITY;
+    for (int m = tid; m < nrec; m += blockDim.x) mn = fminf(mn, big[m * P]);
+    const unsigned int omin = __reduce_min_sync(0xffffffffu, float_to_ordered(mn));
+    if (lane == 0) atomicMin(sh_min, omin);
     if (__syncthreads_or(lost)) status = 1;
-    combine_records([&](int b, int c) { return big[b * P + c]; }, nrec, P, neg_inv_lbd, sh_rec, sh_red);
+    if (f.trace != nullptr && tid == 0) f.trace[6] = globaltimer_ns();
+    const float rho = ordered_to_float(sh_min[0]);
+    // rescale factors exp(-(rho_b - rho) / lambda), one per record, in place of rho_b
+    for (int m = tid; m < nrec; m += blockDim.x) {
+      const float rb = big[m * P];
+      big[m * P] = (rb < INFINITY) ? expf((rb - rho) * neg_inv_lbd) : 0.0f;
+    }
+    __syncthreads();
+    // column sums: (column, half) pairs over the warps; the two halves split the record range at a fixed point
+    const int halves = nrec > 256 ? 2 : 1, split = halves == 2 ? (nrec + 1) / 2 : nrec;
+    for (int idx = w; idx < (P - 1) * halves; idx += nw) {
+      const int c = idx % (P - 1), hf = idx / (P - 1);
+      const int b0 = hf == 0 ? 0 : split, b1 = hf == 0 ? split : nrec;
+      float acc = 0.0f;
+      for (int b = b0 + lane; b < b1; b += 32) acc = fmaf(big[b * P], big[b * P + 1 + c], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) sh_half[hf * P + 1 + c] = acc;
+    }
+    __syncthreads();
+    if (tid < P - 1) sh_rec[1 + tid] = halves == 2 ? sh_half[1 + tid] + sh_half[P + 1 + tid] : sh_half[1 + tid];
+    if (tid == 0) sh_rec[0] = rho;
+    __syncthreads();
+    if (f.trace != nullptr && tid == 0) f.trace[7] = globaltimer_ns();
   } else {  // records do not fit in shared memory: wait for all of them, then combine from global memory (low words, through L2)
-    const int lost = poll_tagged(slot, nrec * P, f.seq, t0, nullptr);
+    const int lost = poll_records(rec_ptr, nrec, P, f.seq, t0, nullptr);
     if (__syncthreads_or(lost)) status = 1;
-    combine_records([&](int b, int c) { return __ldcg(reinterpret_cast<const float*>(slot(b * P + c))); }, nrec, P, neg_inv_lbd, sh_rec, sh_red);
+    combine_records([&](int b, int c) { return __ldcg(reinterpret_cast<const float*>(rec_ptr(b) + c)); }, nrec, P, neg_inv_lbd, sh_rec);
   }
   if (f.record_out != nullptr)
     for (int c = tid; c < P; c += blockDim.x) f.record_out[c] = sh_rec[c];
@@ -160,12 +201,16 @@ __device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float*
   const float a = sh_rec[1];
   for (int t = tid; t < H; t += blockDim.x) {
     const int seg = t / period, j = t - seg * period;
-    float w0, w1;
-    interp_weights(seg, j, period, n_ind, &w0, &w1);
+    const float2 wt = wtab[j];  // ((period - j)/period, j/period), Interpolator.py:63-74
+    const float w0 = (seg == n_ind - 1) ? interp_last_point_weight(period) : wt.x;
     const float bz0 = sh_rec[2 + seg];
     const float bz1 = (j > 0) ? sh_rec[2 + seg + 1] : 0.0f;
-    const float b = (fmaf(bz1, w1, bz0 * w0) * stdev) / a;
+    const float b = (fmaf(bz1, wt.y, bz0 * w0) * stdev) / a;
     const float un = fminf(fmaxf(sh_unom[t] + b, lo), hi);
+    if (f.handover != nullptr) {  // first: the next tick of a chain is polling these
+      st_tagged(f.handover + 1 + t, un, f.seq);
+      if (t == 0) st_tagged(f.handover, f.freeze_prev ? f.u_prev[0] : un, f.seq);
+    }
     f.u_nom[t] = un;
     if (f.host.p != nullptr) host_put(f.host, 8 + t, un);
     if (t == 0) {
@@ -331,7 +376,7 @@ __global__ void __launch_bounds__(Pred::kMaxThreads, Pred::kMinBlocks) mppi_roll
   }
   if (tid == 0) brec[0] = rho_b;
   // fused K2 (+ cross-GPU exchange): block 0 finishes the tick
-  mppi_tick_finish(a.fuse, brec, a.partials, a.n_ind, a.H, a.period, a.stdev, a.lo, a.hi, a.neg_inv_lbd, sh_unom, brec + P + 1,
+  mppi_tick_finish(a.fuse, brec, a.partials, a.n_ind, a.H, a.period, a.stdev, a.lo, a.hi, a.neg_inv_lbd, sh_unom, sh_w, brec + P + 1,
                    sh_red, sh_z, (int)((a.stash ? (size_t)a.n_ind * rpb : 0) + (size_t)a.n_ind * rpb));
 }
 

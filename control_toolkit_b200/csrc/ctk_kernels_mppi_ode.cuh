@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
   const int period = PERIOD > 0 ? PERIOD : a.period;
   const int P = a.n_ind + 1;
   float* sh_unom = smem;                                   // [H] shifted nominal (+ pad)
-  float* sh_w = smem + ((a.H + 3) & ~3);                   // [period] j/period (runtime-period path)
-  float* sh_red = sh_w + ((period + 3) & ~3);              // [32]
+  float2* sh_w = reinterpret_cast<float2*>(smem + ((a.H + 3) & ~3));  // [period] interpolation weights ((period - j)/period, j/period)
+  float* sh_red = reinterpret_cast<float*>(sh_w) + 2 * ((period + 3) & ~3);  // [32]
   float* sh_part = sh_red + 32;                            // [12][P + 1]: block record + finish scratch
   float* sh_z = sh_part + 12 * (P + 1);                          // [n_ind][ILP*T] standard draws of the rollouts in flight
   float* sh_acc = sh_z + (size_t)max(a.n_ind * ILP, 2) * T_;  // [n_ind][T] per-thread sum_n e_n z_n,i
@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
   // ---- prologue.  Prefetch the lines the global reads below will touch (after an L2 flush they come from DRAM), generate the
   //      Philox draws of the first rollout group -- they depend on nothing the previous tick produces -- and only then wait for the
   //      previous launch of the stream to complete (no-op unless launched as a programmatic dependent) ----
-  if (tid < 8) {
+  const bool chained = a.fuse.chained != 0;  // the previous launch is the previous tick of this handle's chain (ctk_step_device_n)
+  if (tid < 8 && !chained) {
     const float* pf = (tid < 6) ? a.u_nom + tid * 32 : (tid == 6 ? a.u_prev : a.s0.p);
     if (pf != nullptr && (tid >= 6 || tid * 32 < a.H)) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
   }
@@ -111,14 +112,24 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
   const int boff = (blockIdx.x == 0) ? 0 : ILP * (a.t0 + ((int)blockIdx.x - 1) * T_);
   const int stride = ILP * (a.t0 + ((int)gridDim.x - 1) * T_);
   if (tid < Ta) gen_noise(boff);
-  for (int j = tid; j < period; j += T_) sh_w[j] = (float)j / (float)period;      // Interpolator.py:63-74
+  for (int j = tid; j < period; j += T_) interp_weights(j, period, &sh_w[j].x, &sh_w[j].y);  // Interpolator.py:63-74
   for (int i = 0; i < a.n_ind; ++i) sh_acc[(size_t)i * T_ + tid] = 0.0f;
-  pdl_wait();
-  const float s0v = (tid < 6) ? a.s0.ld(tid) : 0.0f;
-  const float upv = a.u_prev[0];
-  for (int t = tid; t < a.H; t += T_) sh_unom[t] = a.u_nom[min(t + 1, a.H - 1)];  // optimizer_mppi.py:184 (shift on read)
+  const float s0v = (tid < 6) ? a.s0.ld(tid) : 0.0f;  // (a chain's states were complete before its first tick was launched)
+  if (chained) {
+    // the previous tick's finisher publishes u_prev and u_nom[H] as tagged slots: poll them instead of waiting for that launch
+    // to complete (its kernel-completion / dependent-release latency leaves the tick-to-tick critical path)
+    const unsigned long long t0p = globaltimer_ns();
+    const unsigned int pseq = a.fuse.seq - 1u;
+    for (int t = tid; t < a.H; t += T_) ld_tagged(a.fuse.handover + 1 + min(t + 1, a.H - 1), pseq, t0p, &sh_unom[t]);
+    if (tid == 31) ld_tagged(a.fuse.handover, pseq, t0p, &sh_red[6]);
+  } else {
+    pdl_wait();
+    for (int t = tid; t < a.H; t += T_) sh_unom[t] = a.u_nom[min(t + 1, a.H - 1)];  // optimizer_mppi.py:184 (shift on read)
+    if (tid == 31) sh_red[6] = a.u_prev[0];
+  }
   if (tid < 6) sh_red[tid] = s0v;
   __syncthreads();
+  const float upv = sh_red[6];
   const float th0 = sh_red[0], om0 = sh_red[1], c0 = sh_red[2], sn0 = sh_red[3], x0 = sh_red[4], v0 = sh_red[5];
   const float omc0 = 1.0f - cosf(th0);  // spec: E_pot uses cos(angle) of the measured state
   const float T0 = th0 * kInvSqrt2, W0 = om0 * k.beta, V0 = v0 * k.cFg;
@@ -183,7 +194,7 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
 #pragma unroll 2
         for (int j = 0; j < cnt; ++j) {
           const float un = sh_unom[t + j];
-          const float wj = sh_w[j];
+          const float wj = sh_w[j].y;
 #pragma unroll
           for (int q = 0; q < ILP; ++q) ode_mppi_step<KIND, LOG>(a, k, r[q], un, wj, false, t + j, n[q], active[q]);
         }
@@ -248,7 +259,7 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
   }
   if (tid == 0) brec[0] = rho_b;
   trace(4);
-  mppi_tick_finish(a.fuse, brec, a.partials, a.n_ind, a.H, period, k.stdev, k.lo, k.hi, k.neg_inv_lbd, sh_unom, brec + P + 1, sh_red, sh_z,
+  mppi_tick_finish(a.fuse, brec, a.partials, a.n_ind, a.H, period, k.stdev, k.lo, k.hi, k.neg_inv_lbd, sh_unom, sh_w, brec + P + 1, sh_red, sh_z,
                    (int)((size_t)max(a.n_ind * ILP, 2) * T_ + (size_t)a.n_ind * T_));
   trace(5);
 }

@@ -84,7 +84,7 @@ cudaError_t launch_mppi_ode(int kind, bool log, int period_t, int ilp, int grid,
 }
 int mppi_ode_max_block(int ilp) { (void)ilp; return 1024; }
 size_t mppi_ode_smem_bytes(int H, int period, int n_ind, int ilp, int block) {
-  return sizeof(float) * ((size_t)((H + 3) & ~3) + ((period + 3) & ~3) + 32 + 12 * (size_t)(n_ind + 2) + (size_t)(n_ind * ilp > 2 ? n_ind * ilp : 2) * block + (size_t)n_ind * block);
+  return sizeof(float) * ((size_t)((H + 3) & ~3) + 2 * ((period + 3) & ~3) + 32 + 12 * (size_t)(n_ind + 2) + (size_t)(n_ind * ilp > 2 ? n_ind * ilp : 2) * block + (size_t)n_ind * block);
 }
 
 cudaError_t launch_mppi_combine(const float* in, int cnt, int n_ind, float neg_inv_lbd, float* record_out,

@@ -39,7 +39,7 @@ def main():
         torch.cuda.synchronize()
     L.check(lib.ctk_debug_trace(opt._h, 1, buf.ctypes.data_as(C.POINTER(C.c_uint64)), buf.size, C.byref(grid)))
     g = grid.value
-    t = buf.reshape(4, 320, 8)[:, :g, :6].astype(np.int64)
+    t = buf.reshape(4, 320, 8)[:, :g, :].astype(np.int64)
     t0 = t[1, :, 0].min()
     t = (t - t0) / 1e3
     print(f"N={n} grid={g} chain of {ticks} ticks: {e0.elapsed_time(e1) * 1e3 / ticks:.2f} us per tick (one event pair around the chain)")
@@ -50,7 +50,8 @@ def main():
         prev_fin = t[i - 1, 0, 5]
         print(f"  {i}: start {a[:, 0].min():8.2f} {np.median(a[:, 0]):8.2f} {a[:, 0].max():8.2f} ({a[0, 0]:8.2f}) | prologue {np.median(a[:, 1]):8.2f} ({a[0, 1]:8.2f}) | "
               f"rollouts {np.median(a[:, 2]):8.2f} {a[:, 2].max():8.2f} ({a[0, 2]:8.2f}) | records {a[:, 4].max():8.2f} | finished {a[0, 5]:8.2f} | "
-              f"period {a[0, 5] - prev_fin:6.2f}  (previous finish -> median prologue done {np.median(a[:, 1]) - prev_fin:5.2f})")
+              f"period {a[0, 5] - prev_fin:6.2f}  (previous finish -> median prologue done {np.median(a[:, 1]) - prev_fin:5.2f}; "
+              f"finisher: last record stamp -> polled {a[0, 6] - a[:, 4].max():5.2f} -> combined {a[0, 7] - a[0, 6]:5.2f} -> finished {a[0, 5] - a[0, 7]:5.2f})")
 
 
 if __name__ == "__main__":
