@@ -57,6 +57,7 @@ WORKLOADS = {
     "mppi_ode_1m_log": ("mppi", "ODE", "default", 1_000_000, 100),  # the same tick with optimizer_logging on: HBM-write bound
     "mppi_ode_c1": ("mppi", "ODE", "default", 2000, 50),         # configs[0]
     "cem_ode_c2": ("cem-tf", "ODE", "default", 4096, 50),        # configs[1]
+    "cem_ode_large": ("cem-tf", "ODE", "default", 1_000_000, 50),  # sharded CEM: candidate keys exchanged through the NVLink mailboxes
     "rpgd_ode_c3": ("rpgd", "ODE", "quadratic_boundary_grad", 32, 50),  # configs[2]
     "mppi_mlp_c4": ("mppi", "Dense-6IN-128H1-128H2-5OUT-0", "default", 65536, 100),  # configs[3]
 }
@@ -269,12 +270,12 @@ def run_ours(args):
     # ---- second pass, same ticks: CUDA events around the rollout kernel only (roofline.achieved); kept out of the pass
     #      above so that the extra event records do not sit inside the timed ticks ----
     single_launch_tick = launches == K
-    if world > 1 and single_launch_tick:
+    if world > 1 and (single_launch_tick or fused):
         # sharded MPPI: the tick IS one launch, already bracketed by an event pair in the pass above.  A second pass with extra
         # event records inside the handle skews the ranks against each other and the skew is then spent waiting inside the fused
         # exchange (measured: 0.18 ms "kernel" at 8 GPUs for a 0.042 ms tick), so the kernel time is this rank's tick time of
         # the timed pass (an upper bound: it includes the ~6 us event-pair overhead)
-        ms_sum, n_k = C.c_double(sum(per_tick_ms)), C.c_int64(K)
+        ms_sum, n_k = C.c_double(sum(per_tick_ms)), C.c_int64(K if single_launch_tick else 0)
         tick2_ms = sum(per_tick_ms) / K
         kernel_ms_source = "event pair around the one-launch tick in the timed pass (rank 0)"
     else:
@@ -381,6 +382,8 @@ def run_ours(args):
             L.check(lib.ctk_fp32_peak(local_rank, C.byref(peak), C.byref(clk)))
             one_launch = launches == K  # persistent tick: all outer iterations (rollouts, top-k, refit) in ONE launch
             per_launch = passes if one_launch else 1
+            if not n_k.value:  # sharded run: no kernel-event pass (it would skew the shards): the tick's own event pair, an upper bound
+                k1_ms = tick2_ms / (1 if one_launch else passes)
             achieved = fl_step * n_local * H * per_launch / (k1_ms * 1e-3) / 1e12
             roofline = {"bound": "fp32", "kernel": ("cem_tick_kernel (persistent: the whole tick -- rollouts, top-k and refit of all outer iterations)" if one_launch
                                                     else "cem_ode_kernel (one launch per outer iteration)"), "achieved": achieved,
@@ -437,7 +440,8 @@ def run_ours(args):
                            "predictor": WORKLOADS[args.workload][1], "cost": WORKLOADS[args.workload][2], "noise": "in-kernel Philox4x32-10",
                            **({"mlp_engine": args.mlp_engine} if WORKLOADS[args.workload][1].startswith("Dense") else {}),
                            "parallelism": f"rollouts sharded over {world} GPU(s); exchange per tick: {getattr(opt, '_exchange', 'none')} "
-                                          f"({'in-kernel NVLink mailbox stores, ' if getattr(opt, '_exchange', '') == 'p2p' else ''}{H // 10 + 3} floats per shard)",
+                                          f"({'in-kernel NVLink mailbox stores, ' if getattr(opt, '_exchange', '') == 'p2p' else ''}"
+                                          + (f"{H // 10 + 3} floats per shard)" if opt_name == "mppi" else f"{CEM_CFG['cem_best_k']} (cost, id) keys per shard and outer iteration)" if opt_name == "cem-tf" else "none)"),
                            "l2": "flushed between timed ticks (256 MiB memset" + ("; shards aligned by a device-side mailbox barrier before each timed tick" if world > 1 else "") + "); inputs are 24 B per tick", "logging": logging_on},
                 "e2e": {"value": e2e_value, "unit": "rollout-steps/s", "h2d_bytes_per_step": 24, "d2h_bytes_per_step": (4 * N * ((H + 1) * 6 + H + 1) + 8 + 4 * H) if logging_on else ((8 + 4 * H) if opt_name == "mppi" else 8),
                         "p50_step_latency_ms": statistics.median(lat) * 1e3, "api": api_name},

@@ -70,11 +70,13 @@ struct alignas(16) HotUK {
 
 // ----------------------------------------------------------------------------------------------------------------
 // In-kernel tick finish (K2 fused into the rollout kernel).  Every block publishes its softmin record [rho_b, a_b, b_z[n_ind]]
-// as tagged 8-byte slots (value | sequence number in ONE store: no fence, no flag round trip) straight into the mailbox of EVERY
-// shard -- its own GPU's and, over NVLink peer stores, the peers' (one hop: the remote latency runs underneath the wait for the
-// slowest local block) -- and block 0 of every shard, the finisher, polls the world x grid records of its own mailbox, rescales
-// them exactly to the global minimum and updates u_nom / u.  Every shard combines the same records in the same order: the
-// replicated optimizer state stays bit-identical.  Replaces reference optimizer_mppi.py:163-168,190-191 (+ the cross-shard
+// as tagged 8-byte slots (value | sequence number in ONE store: no fence, no flag round trip) into its shard's mailbox; block 0
+// of every shard, the finisher, polls the grid's records, rescales them exactly to their minimum, forwards the shard's combined
+// record over NVLink peer stores into every shard's mailbox (hops == 2, default), polls the world's shard records and updates
+// u_nom / u.  hops == 1 instead stores every BLOCK record straight into every shard's mailbox and lets each finisher combine
+// world x grid records: one global hop less on paper, measured slower at 8 GPUs (13 k small NVLink writes per GPU and tick take
+// ~6 us to land, a single forwarded record ~2.8 us).  Every shard combines the same records in the same order: the replicated
+// optimizer state stays bit-identical.  Replaces reference optimizer_mppi.py:163-168,190-191 (+ the cross-shard
 // weighted-sum exchange of SURVEY 8e).
 // Mailbox layout (uint64 slots): [2 (sequence parity)][CTK_MAX_PEERS (source shard)][CTK_MBOX_BLOCKS (source block)][record stride],
 // then the barrier area [2][CTK_MAX_PEERS] and the hand-over slots.  Double-buffered by parity: a shard can be at most one tick
@@ -100,6 +102,7 @@ struct MppiFuse {
   unsigned long long* mbox_peer[CTK_MAX_PEERS];   // every shard's mailbox (mbox_peer[rank] == mbox_local)
   unsigned long long* handover;                   // [1 + H] tagged u_prev, u_nom[H] of the tick (local)
   unsigned long long* trace; // diagnostics: block 0's row of the phase timeline (slots 6, 7: records polled, records combined) or null
+  int hops;                  // cross-GPU exchange: 1 every block stores its record into every shard's mailbox; 2 the finisher forwards the shard record
   int chained;               // 1: the previous launch of the stream is the previous tick of this handle's chain: poll its hand-over
   float* u_nom;              // [H] in/out
   float* u_prev;             // [1] out (unless frozen)
@@ -244,7 +247,17 @@ struct CemRefitArgs {
   int freeze_prev;
   int32_t* elite_idx_out;    // [k] global ids, best first (log) or null
   HostMirror host;           // last iteration: u mirrored to the host caller
+  // Fused cross-GPU candidate exchange (CEM row): world > 1 -> `cand` holds THIS shard's k best keys; the kernel stores
+  // them into every shard's mailbox over NVLink (two tagged 8-byte slots per key: high / low word | sequence number), polls the
+  // world x k keys of its own mailbox and merges them -- every shard refits the same distribution, no NCCL call, no host round trip.
+  // Mailbox layout (uint64 slots): [2 (sequence parity)][CTK_MAX_PEERS][kCemMboxKeys][2], then the barrier area.
+  int world, rank;
+  unsigned int seq;          // exchange sequence number of this outer iteration (monotonic, never 0, lock step on all shards)
+  unsigned long long* mbox_local;
+  unsigned long long* mbox_peer[CTK_MAX_PEERS];
 };
+constexpr int kCemMboxKeys = 512;  // = the largest cem_best_k
+CTK_HD size_t cem_mbox_slots() { return (size_t)2 * CTK_MAX_PEERS * kCemMboxKeys * 2 + 2 * CTK_MAX_PEERS; }
 
 struct RpgdGradArgs {
   int N, H, iters;

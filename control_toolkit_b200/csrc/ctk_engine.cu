@@ -336,6 +336,8 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
       A(cudaGetDeviceProperties(&prop, cfg->device), "props");
       h->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
       A(dalloc(&h->d_cem_cand, (size_t)2 * h->num_sms * 128), "cem_cand");  // [blocks <= 2 x SMs][k <= 128]
+      A(dalloc(&h->d_mbox, cem_mbox_slots()), "mailbox");  // fused cross-GPU candidate exchange (CemRefitArgs)
+      h->mbox_peer[0] = h->d_mbox;
       A(dalloc(&h->d_cem_dist, (size_t)2 * 512), "cem_dist");
     }
   } else {
@@ -625,6 +627,10 @@ static int make_fuse(ctk_handle* h, int mode, float* u_out_dev, MppiFuse* out) {
   f.record_out = h->d_record;
   f.mbox_local = h->d_mbox;
   f.handover = h->d_mbox + mbox_handover_offset(h->n_ind);
+  {
+    static const int hops_env = getenv("CTK_EXCHANGE_HOPS") ? atoi(getenv("CTK_EXCHANGE_HOPS")) : 0;
+    f.hops = (hops_env == 1 || hops_env == 2) ? hops_env : 2;  // measured at 8 GPUs (profiles/): two hops 32.0 us per chained tick, one hop 33.4
+  }
   f.trace = h->d_trace ? h->d_trace + (size_t)(h->xseq & 3u) * CTK_MBOX_BLOCKS * 8 : nullptr;
   f.chained = (mode == 2 && h->chain_hint && h->ode_kernel && h->xseq > 1) ? 1 : 0;
   h->chain_hint = false;
@@ -865,10 +871,21 @@ static int cem_local(ctk_handle* h, const float* s_dev, bool to_k) {
   return CTK_OK;
 }
 
-static int cem_finish(ctk_handle* h, const uint64_t* cand, int cnt, float* u_out_dev) {
+// fused == true: `cand` holds this shard's k keys, the refit kernel exchanges them with the connected shards through the mailboxes
+static int cem_finish(ctk_handle* h, const uint64_t* cand, int cnt, float* u_out_dev, bool fused = false) {
   const ctk_config& c = h->cfg;
   REQ(cnt >= c.cem_best_k && cnt <= TOPK_THREADS, "CEM candidate count must be in [k, 1024]");
   CemRefitArgs a{};
+  a.world = 1; a.rank = 0;
+  if (fused && h->xworld > 1) {
+    REQ(cnt == c.cem_best_k, "fused CEM exchange needs exactly k local candidates");
+    a.world = h->xworld; a.rank = h->xrank;
+    h->xseq++;
+    if (h->xseq == 0) h->xseq = 1;
+    a.seq = h->xseq;
+    a.mbox_local = h->d_mbox;
+    for (int r = 0; r < CTK_MAX_PEERS; ++r) a.mbox_peer[r] = h->mbox_peer[r];
+  }
   a.H = h->H; a.k = c.cem_best_k; a.cnt = cnt; a.cand = cand; a.noise = h->cem_noise; a.lo = c.action_low; a.hi = c.action_high;
   a.mu = h->d_mu; a.sd = h->d_sd; a.last = (h->cem_it == h->cem_iters - 1) ? 1 : 0;
   a.sd_min = c.cem_stdev_min; a.sd_init = c.cem_initial_action_stdev;
@@ -1160,9 +1177,9 @@ static int step_host(ctk_handle* h, const float* s_host, float* u_out_host, cons
     h->tick++;
     rc = cem_persistent_ok(h) ? cem_tick_persistent(h, nullptr, h->d_u_out) : 1;
     if (rc == 1) do {
-      rc = cem_local(h, nullptr, false);
+      rc = cem_local(h, nullptr, h->xworld > 1);
       if (rc != CTK_OK) break;
-      rc = cem_finish(h, h->cem_cand_ptr, h->cem_cand, h->d_u_out);
+      rc = cem_finish(h, h->cem_cand_ptr, h->cem_cand, h->d_u_out, h->xworld > 1);
     } while (rc == CTK_OK && h->cem_it != 0);
   } else {
     h->tick++;
@@ -1198,7 +1215,7 @@ static int step_host(ctk_handle* h, const float* s_host, float* u_out_host, cons
 extern "C" int ctk_step_device(ctk_handle* h, const float* s_dev, float* u_out_dev) {
   REQ(h && s_dev, "null pointer");
   if (!h->was_reset) return fail(CTK_ESTATE, "ctk_step before ctk_reset");
-  REQ(h->cfg.optimizer == CTK_OPT_MPPI || h->xworld == 1, "the fused cross-GPU exchange is implemented for MPPI; CEM shards use ctk_step_local / ctk_step_finish");
+  REQ(h->cfg.optimizer != CTK_OPT_RPGD || h->xworld == 1, "RPGD is replicas-only (no cross-GPU exchange)");
   CU(cudaSetDevice(h->cfg.device));
   if (h->cfg.predictor == CTK_PRED_MLP && h->mlp.blob == nullptr) return fail(CTK_ESTATE, "MLP predictor without weights");
   float* uo = u_out_dev ? u_out_dev : h->d_u_out;
@@ -1209,9 +1226,9 @@ extern "C" int ctk_step_device(ctk_handle* h, const float* s_dev, float* u_out_d
   } else if (h->cfg.optimizer == CTK_OPT_CEM) {
     rc = cem_persistent_ok(h) ? cem_tick_persistent(h, s_dev, uo) : 1;
     if (rc == 1) do {
-      rc = cem_local(h, s_dev, false);
+      rc = cem_local(h, s_dev, h->xworld > 1);
       if (rc != CTK_OK) break;
-      rc = cem_finish(h, h->cem_cand_ptr, h->cem_cand, uo);
+      rc = cem_finish(h, h->cem_cand_ptr, h->cem_cand, uo, h->xworld > 1);
     } while (rc == CTK_OK && h->cem_it != 0);
   } else {
     rc = rpgd_tick(h, s_dev, uo);
@@ -1241,7 +1258,7 @@ extern "C" int ctk_step_device_n(ctk_handle* h, const float* s_dev, size_t s_str
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int ctk_exchange_export(ctk_handle* h, void* ipc_handle_out64) {
   REQ(h && ipc_handle_out64, "null pointer");
-  REQ(h->d_mbox != nullptr, "this optimizer has no exchange mailbox (MPPI only)");
+  REQ(h->d_mbox != nullptr, "this optimizer has no exchange mailbox (RPGD is replicas-only)");
   CU(cudaSetDevice(h->cfg.device));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   cudaIpcMemHandle_t hd;
@@ -1251,6 +1268,7 @@ extern "C" int ctk_exchange_export(ctk_handle* h, void* ipc_handle_out64) {
 }
 static int exchange_reset(ctk_handle* h, int rank, int world) {
   REQ(world >= 1 && world <= CTK_MAX_PEERS && rank >= 0 && rank < world, "need 0 <= rank < world <= 8");
+  REQ(h->cfg.optimizer != CTK_OPT_CEM || (long long)world * h->cfg.cem_best_k <= TOPK_THREADS, "sharded CEM: world x cem_best_k must be <= 1024");
   CU(cudaStreamSynchronize(h->stream));
   for (int r = 0; r < CTK_MAX_PEERS; ++r) {
     if (h->mbox_ipc[r] && h->mbox_peer[r]) cudaIpcCloseMemHandle(h->mbox_peer[r]);
@@ -1258,12 +1276,12 @@ static int exchange_reset(ctk_handle* h, int rank, int world) {
   }
   h->xworld = world; h->xrank = rank; h->xseq = 0;
   h->bseq = 0;
-  CU(cudaMemset(h->d_mbox, 0, sizeof(unsigned long long) * mbox_total_slots(h->n_ind, h->H)));
+  CU(cudaMemset(h->d_mbox, 0, sizeof(unsigned long long) * (h->cfg.optimizer == CTK_OPT_CEM ? cem_mbox_slots() : mbox_total_slots(h->n_ind, h->H))));
   return CTK_OK;
 }
 extern "C" int ctk_exchange_connect(ctk_handle* h, int rank, int world, const void* ipc_handles) {
   REQ(h && ipc_handles, "null pointer");
-  REQ(h->d_mbox != nullptr, "this optimizer has no exchange mailbox (MPPI only)");
+  REQ(h->d_mbox != nullptr, "this optimizer has no exchange mailbox (RPGD is replicas-only)");
   CU(cudaSetDevice(h->cfg.device));
   int rc = exchange_reset(h, rank, world);
   if (rc != CTK_OK) return rc;
@@ -1295,7 +1313,7 @@ extern "C" int ctk_exchange_barrier(ctk_handle* h) {
   f.mbox_local = h->d_mbox;
   for (int r = 0; r < CTK_MAX_PEERS; ++r) f.mbox_peer[r] = h->mbox_peer[r];
   h->launches++;
-  CU(launch_exchange_barrier(f, mbox_barrier_offset(h->n_ind), h->stream));
+  CU(launch_exchange_barrier(f, h->cfg.optimizer == CTK_OPT_CEM ? cem_mbox_slots() - 2 * CTK_MAX_PEERS : mbox_barrier_offset(h->n_ind), h->stream));
   return CTK_OK;
 }
 extern "C" int ctk_exchange_mailbox(ctk_handle* h, void** dev_ptr) {
@@ -1305,7 +1323,7 @@ extern "C" int ctk_exchange_mailbox(ctk_handle* h, void** dev_ptr) {
 }
 extern "C" int ctk_exchange_connect_ptrs(ctk_handle* h, int rank, int world, void* const* mailboxes, const int* devices) {
   REQ(h && mailboxes && devices, "null pointer");
-  REQ(h->d_mbox != nullptr, "this optimizer has no exchange mailbox (MPPI only)");
+  REQ(h->d_mbox != nullptr, "this optimizer has no exchange mailbox (RPGD is replicas-only)");
   CU(cudaSetDevice(h->cfg.device));
   int rc = exchange_reset(h, rank, world);
   if (rc != CTK_OK) return rc;

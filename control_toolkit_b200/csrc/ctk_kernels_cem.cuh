@@ -151,9 +151,38 @@ __global__ void __launch_bounds__(TOPK_THREADS) cem_refit_kernel(const CemRefitA
   __shared__ uint32_t sh_elite[TOPK_THREADS];
   pdl_wait();
   pdl_trigger();
-  uint64_t key = (threadIdx.x < a.cnt) ? a.cand[threadIdx.x] : KEY_MAX;
+  uint64_t key = KEY_MAX;
+  int cnt = a.cnt;
+  if (a.world > 1) {
+    // fused candidate exchange: this shard's k keys -> every shard's mailbox; then the world x k keys of the own mailbox
+    const int tid = threadIdx.x;
+    const size_t base = (size_t)(a.seq & 1u) * CTK_MAX_PEERS * kCemMboxKeys * 2;
+    for (int i = tid; i < a.world * a.k; i += blockDim.x) {
+      const int r = i / a.k, e = i - r * a.k;
+      const uint64_t kv = a.cand[e];
+      unsigned long long* dst = a.mbox_peer[r] + base + ((size_t)a.rank * kCemMboxKeys + e) * 2;
+      const unsigned long long x0 = ((unsigned long long)a.seq << 32) | (kv >> 32), x1 = ((unsigned long long)a.seq << 32) | (kv & 0xffffffffull);
+      asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(x0), "l"(x1) : "memory");
+    }
+    cnt = a.world * a.k;
+    const unsigned long long t0 = globaltimer_ns();
+    if (tid < cnt) {
+      const int r = tid / a.k, e = tid - r * a.k;
+      const unsigned long long* src = a.mbox_local + base + ((size_t)r * kCemMboxKeys + e) * 2;
+      unsigned long long v0, v1;
+      int spins = 0;
+      while (true) {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v0), "=l"(v1) : "l"(src) : "memory");
+        if ((unsigned int)(v0 >> 32) == a.seq && (unsigned int)(v1 >> 32) == a.seq) break;
+        if ((++spins & 1023) == 0 && globaltimer_ns() - t0 > 2000000000ull) { v0 = v1 = 0xffffffffull; break; }  // lost peer: sorts last
+      }
+      key = ((v0 & 0xffffffffull) << 32) | (v1 & 0xffffffffull);
+    }
+  } else if (threadIdx.x < a.cnt) {
+    key = a.cand[threadIdx.x];
+  }
   int n_sort = 32;
-  while (n_sort < a.cnt) n_sort <<= 1;
+  while (n_sort < cnt) n_sort <<= 1;
   key = block_bitonic_sort(key, sh, n_sort);
   if (threadIdx.x < a.k) {
     sh_elite[threadIdx.x] = (uint32_t)(key & 0xffffffffu);

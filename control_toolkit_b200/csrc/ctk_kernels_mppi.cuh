@@ -114,6 +114,40 @@ __device__ __forceinline__ void combine_records(Rec rec, int cnt, int P, float n
   __syncthreads();
 }
 
+// Combine nrec records staged in shared memory (big[m * P + c]) into out[P], rescaled exactly to their common minimum.  The
+// summation order depends only on (nrec, P) -- never on the block size -- so every shard computes bit-identical results.
+__device__ __forceinline__ void staged_combine(float* big, int nrec, int P, float neg_inv_lbd, int lost, unsigned int* sh_min,
+                                               float* out, float* sh_half, int* status) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = blockDim.x >> 5;
+  // common minimum: the thread's own records (it has just written them) -> warp (redux) -> block (one shared atomic per warp)
+  float mn = INFINITY;
+  for (int m = tid; m < nrec; m += blockDim.x) mn = fminf(mn, big[m * P]);
+  const unsigned int omin = __reduce_min_sync(0xffffffffu, float_to_ordered(mn));
+  if (lane == 0) atomicMin(sh_min, omin);
+  if (__syncthreads_or(lost)) *status = 1;
+  const float rho = ordered_to_float(sh_min[0]);
+  // rescale factors exp(-(rho_b - rho) / lambda), one per record, in place of rho_b
+  for (int m = tid; m < nrec; m += blockDim.x) {
+    const float rb = big[m * P];
+    big[m * P] = (rb < INFINITY) ? expf((rb - rho) * neg_inv_lbd) : 0.0f;
+  }
+  __syncthreads();
+  // column sums: (column, half) pairs over the warps; the two halves split the record range at a fixed point
+  const int halves = nrec > 256 ? 2 : 1, split = halves == 2 ? (nrec + 1) / 2 : nrec;
+  for (int idx = w; idx < (P - 1) * halves; idx += nw) {
+    const int c = idx % (P - 1), hf = idx / (P - 1);
+    const int b0 = hf == 0 ? 0 : split, b1 = hf == 0 ? split : nrec;
+    float acc = 0.0f;
+    for (int b = b0 + lane; b < b1; b += 32) acc = fmaf(big[b * P], big[b * P + 1 + c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) sh_half[hf * P + 1 + c] = acc;
+  }
+  __syncthreads();
+  if (tid < P - 1) out[1 + tid] = halves == 2 ? sh_half[1 + tid] + sh_half[P + 1 + tid] : sh_half[1 + tid];
+  if (tid == 0) out[0] = rho;
+  __syncthreads();
+}
+
 // Called by ALL threads of EVERY block once the block's record brec[P] = [rho_b, a_b, b_z[n_ind]] is complete in SHARED
 // memory (the call starts with a barrier).  mode 0: the record is stored as plain floats to partials[blockIdx.x][P] (a
 // separate combine launch follows).  mode >= 1: every value is published as ONE 8-byte (value, sequence number) store -- no
@@ -141,10 +175,17 @@ __device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float*
   const size_t base = (size_t)(f.seq & 1u) * CTK_MAX_PEERS * CTK_MBOX_BLOCKS * RS;  // parity buffer
   const size_t shard = (size_t)CTK_MBOX_BLOCKS * RS;                                  // slots per source shard
   {
+    // hops == 1: the record goes straight to every shard (16-byte stores: two tagged slots per NVLink write); hops == 2: only to
+    // this shard's own mailbox, the finisher forwards the shard's combined record
     const size_t mine = base + (size_t)rank * shard + (size_t)blockIdx.x * RS;
-    for (int i = tid; i < world * P; i += blockDim.x) {
-      const int r = i / P, c = i - r * P;
-      st_tagged((world > 1 ? f.mbox_peer[r] : f.mbox_local) + mine + c, brec[c], f.seq);
+    const int dests = (world > 1 && f.hops != 2) ? world : 1;
+    const int P2 = (P + 1) >> 1;
+    for (int i = tid; i < dests * P2; i += blockDim.x) {
+      const int r = i / P2, q = i - r * P2;
+      unsigned long long* dst = (dests > 1 ? f.mbox_peer[r] : f.mbox_local) + mine + 2 * q;
+      const unsigned long long x0 = ((unsigned long long)f.seq << 32) | (unsigned long long)__float_as_uint(brec[2 * q]);
+      const unsigned long long x1 = ((unsigned long long)f.seq << 32) | (unsigned long long)__float_as_uint(2 * q + 1 < P ? brec[2 * q + 1] : 0.0f);
+      asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(x0), "l"(x1) : "memory");
     }
   }
   if (blockIdx.x != 0) return;
@@ -159,35 +200,26 @@ __device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float*
     return mb + (size_t)r * shard + (size_t)b * RS;
   };
   if (nrec * P <= big_floats) {
-    const int lost = poll_records(rec_ptr, nrec, P, f.seq, t0, big);
-    // common minimum: the thread's own records (it has just written them) -> warp (redux) -> block (one shared atomic per warp)
-    float mn = INFINITY;
-    for (int m = tid; m < nrec; m += blockDim.x) mn = fminf(mn, big[m * P]);
-    const unsigned int omin = __reduce_min_sync(0xffffffffu, float_to_ordered(mn));
-    if (lane == 0) atomicMin(sh_min, omin);
-    if (__syncthreads_or(lost)) status = 1;
+    // records staged in shared memory by the poll; hops == 2: only this grid's records now, the shard records of the peers after
+    const int hops2 = (world > 1 && f.hops == 2) ? 1 : 0;
+    const int n1 = hops2 ? G : nrec;
+    auto rec1 = [&](int m) -> const unsigned long long* { return hops2 ? mb + (size_t)rank * shard + (size_t)m * RS : rec_ptr(m); };
+    const int lost = poll_records(rec1, n1, P, f.seq, t0, big);
+    staged_combine(big, n1, P, neg_inv_lbd, lost, sh_min, sh_rec, sh_half, &status);
     if (f.trace != nullptr && tid == 0) f.trace[6] = globaltimer_ns();
-    const float rho = ordered_to_float(sh_min[0]);
-    // rescale factors exp(-(rho_b - rho) / lambda), one per record, in place of rho_b
-    for (int m = tid; m < nrec; m += blockDim.x) {
-      const float rb = big[m * P];
-      big[m * P] = (rb < INFINITY) ? expf((rb - rho) * neg_inv_lbd) : 0.0f;
+    if (hops2) {
+      // second hop: this shard's combined record -> every shard's mailbox (slot of block CTK_MBOX_BLOCKS - 1), then the world's
+      const size_t mine2 = base + (size_t)rank * shard + (size_t)(CTK_MBOX_BLOCKS - 1) * RS;
+      for (int i = tid; i < world * P; i += blockDim.x) {
+        const int r = i / P, c = i - r * P;
+        st_tagged(f.mbox_peer[r] + mine2 + c, sh_rec[c], f.seq);
+      }
+      if (tid == 0) sh_min[0] = 0xffffffffu;
+      __syncthreads();
+      auto rec2 = [&](int m) -> const unsigned long long* { return mb + (size_t)m * shard + (size_t)(CTK_MBOX_BLOCKS - 1) * RS; };
+      const int lost2 = poll_records(rec2, world, P, f.seq, t0, big);
+      staged_combine(big, world, P, neg_inv_lbd, lost2, sh_min, sh_rec, sh_half, &status);
     }
-    __syncthreads();
-    // column sums: (column, half) pairs over the warps; the two halves split the record range at a fixed point
-    const int halves = nrec > 256 ? 2 : 1, split = halves == 2 ? (nrec + 1) / 2 : nrec;
-    for (int idx = w; idx < (P - 1) * halves; idx += nw) {
-      const int c = idx % (P - 1), hf = idx / (P - 1);
-      const int b0 = hf == 0 ? 0 : split, b1 = hf == 0 ? split : nrec;
-      float acc = 0.0f;
-      for (int b = b0 + lane; b < b1; b += 32) acc = fmaf(big[b * P], big[b * P + 1 + c], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) sh_half[hf * P + 1 + c] = acc;
-    }
-    __syncthreads();
-    if (tid < P - 1) sh_rec[1 + tid] = halves == 2 ? sh_half[1 + tid] + sh_half[P + 1 + tid] : sh_half[1 + tid];
-    if (tid == 0) sh_rec[0] = rho;
-    __syncthreads();
     if (f.trace != nullptr && tid == 0) f.trace[7] = globaltimer_ns();
   } else {  // records do not fit in shared memory: wait for all of them, then combine from global memory (low words, through L2)
     const int lost = poll_records(rec_ptr, nrec, P, f.seq, t0, nullptr);

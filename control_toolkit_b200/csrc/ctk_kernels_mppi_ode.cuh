@@ -85,9 +85,14 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
   //      Philox draws of the first rollout group -- they depend on nothing the previous tick produces -- and only then wait for the
   //      previous launch of the stream to complete (no-op unless launched as a programmatic dependent) ----
   const bool chained = a.fuse.chained != 0;  // the previous launch is the previous tick of this handle's chain (ctk_step_device_n)
-  if (tid < 8 && !chained) {
-    const float* pf = (tid < 6) ? a.u_nom + tid * 32 : (tid == 6 ? a.u_prev : a.s0.p);
-    if (pf != nullptr && (tid >= 6 || tid * 32 < a.H)) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+  // Not chained: wait for the previous launch of the stream (no-op unless launched as a programmatic dependent) and ISSUE the
+  // prologue's global reads now -- after an L2 flush they come from DRAM -- so that they are in flight underneath the Philox draws.
+  float s0v = 0.0f, upv_ld = 0.0f, unom_first = 0.0f;
+  if (!chained) {
+    pdl_wait();
+    s0v = (tid < 6) ? a.s0.ld(tid) : 0.0f;
+    upv_ld = a.u_prev[0];
+    unom_first = (tid < a.H) ? a.u_nom[min(tid + 1, a.H - 1)] : 0.0f;  // optimizer_mppi.py:184 (shift on read)
   }
   const OdeHot& k = a.k;
   const int nblk = (a.n_ind + 3) >> 2;
@@ -114,18 +119,19 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
   if (tid < Ta) gen_noise(boff);
   for (int j = tid; j < period; j += T_) interp_weights(j, period, &sh_w[j].x, &sh_w[j].y);  // Interpolator.py:63-74
   for (int i = 0; i < a.n_ind; ++i) sh_acc[(size_t)i * T_ + tid] = 0.0f;
-  const float s0v = (tid < 6) ? a.s0.ld(tid) : 0.0f;  // (a chain's states were complete before its first tick was launched)
   if (chained) {
-    // the previous tick's finisher publishes u_prev and u_nom[H] as tagged slots: poll them instead of waiting for that launch
-    // to complete (its kernel-completion / dependent-release latency leaves the tick-to-tick critical path)
+    // Chained: the Philox draws above ran underneath the previous tick's finish; its finisher publishes u_prev and u_nom[H] as
+    // tagged slots: poll them instead of waiting for that launch to complete (the kernel-completion / dependent-release latency
+    // leaves the tick-to-tick critical path).  A chain's states were complete before its first tick was launched.
+    s0v = (tid < 6) ? a.s0.ld(tid) : 0.0f;
     const unsigned long long t0p = globaltimer_ns();
     const unsigned int pseq = a.fuse.seq - 1u;
     for (int t = tid; t < a.H; t += T_) ld_tagged(a.fuse.handover + 1 + min(t + 1, a.H - 1), pseq, t0p, &sh_unom[t]);
     if (tid == 31) ld_tagged(a.fuse.handover, pseq, t0p, &sh_red[6]);
   } else {
-    pdl_wait();
-    for (int t = tid; t < a.H; t += T_) sh_unom[t] = a.u_nom[min(t + 1, a.H - 1)];  // optimizer_mppi.py:184 (shift on read)
-    if (tid == 31) sh_red[6] = a.u_prev[0];
+    if (tid < a.H) sh_unom[tid] = unom_first;
+    for (int t = tid + T_; t < a.H; t += T_) sh_unom[t] = a.u_nom[min(t + 1, a.H - 1)];
+    if (tid == 31) sh_red[6] = upv_ld;
   }
   if (tid < 6) sh_red[tid] = s0v;
   __syncthreads();

@@ -6,10 +6,13 @@ sampled population is independent of the number of shards.  Per tick the only ex
 
 * MPPI : the per-shard softmin record [rho_r, a_r, b_z,r[n_ind]] (n_ind + 2 floats).  Default ("p2p"): every shard's
          rollout kernel stores its record straight into the peers' mailboxes over NVLink (CUDA IPC mapped memory) and the
-         last block of each shard combines them -- the whole sharded tick is ONE kernel launch per GPU, no NCCL call.
+         finisher block of each shard combines them -- the whole sharded tick is ONE kernel launch per GPU, no NCCL call.
          Fallback ("nccl", or CTK_EXCHANGE=nccl): one all-gather of the record between two kernels (staged),
-* CEM  : per outer iteration one all-gather of k (ordered-cost, global-id) keys       (2k floats); the elite control
-         rows are regenerated from the counter-based noise on every rank, never sent,
+* CEM  : per outer iteration k (ordered-cost, global-id) keys per shard.  Default ("p2p"): the refit kernel of every shard stores
+         its k keys into the peers' mailboxes over NVLink and merges the world x k keys it finds in its own -- the sharded tick
+         is a chain of asynchronous launches per GPU, no NCCL call, no host round trip.  Fallback ("nccl"): one all-gather of the
+         keys per outer iteration (staged).  The elite control rows are regenerated from the counter-based noise on every rank,
+         never sent,
 * RPGD : none (replicas only).
 
 Every rank then runs the same combine/update kernel on the gathered records, so the optimizer state stays replicated.
@@ -86,7 +89,7 @@ class ShardPlan:
         L.check(lib.ctk_set_stream(opt._h, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         opt._shard_attached = True
         opt._exchange = "none" if self.world_size == 1 else "nccl"
-        if self.world_size > 1 and opt._OPT == L.OPT_MPPI and os.environ.get("CTK_EXCHANGE", "p2p") != "nccl":
+        if self.world_size > 1 and opt._OPT in (L.OPT_MPPI, L.OPT_CEM) and os.environ.get("CTK_EXCHANGE", "p2p") != "nccl":
             mine = (C.c_ubyte * 64)()
             L.check(lib.ctk_exchange_export(opt._h, C.cast(mine, C.c_void_p)))
             dev = f"cuda:{opt.device}"

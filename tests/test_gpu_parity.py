@@ -830,6 +830,52 @@ def test_fused_exchange_two_shards_one_launch_each():
         assert np.abs(a - c).max() < 2e-6
 
 
+@pytest.mark.parametrize("N,k,iters", [(4096, 64, 3), (20011, 100, 2)])
+def test_fused_cem_exchange_two_shards(N, k, iters):
+    """Sharded CEM over the NVLink mailboxes (SURVEY 8e CEM row; reference optimizer_cem_tf.py:73-78 is the per-iteration top-k + refit
+    that is merged across shards): each shard's refit kernel stores its k candidate keys into the peers' mailboxes, polls the
+    world x k keys of its own and merges them -- asynchronous launches only (ctk_step_device), no NCCL, no host round trip.  Elite
+    index lists, distribution and u identical to the unsharded tick and across shards.  GPU 0 / GPU 1 when two devices are visible,
+    else both shards on GPU 0 on separate streams."""
+    import ctypes as C
+    import torch
+    from control_toolkit_b200 import _lib as L
+    lib = L.load()
+    z, meta = load_golden("cem_c2_n4096_k64")
+    meta = dict(meta, cfg=dict(meta["cfg"], num_rollouts=N, cem_best_k=k, cem_outer_it=iters))
+    full = make_controller(meta, rng=None, logging=False)
+    devs = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
+    shards = [make_controller(meta, rng=None, logging=False, shard=_FixedShard(r, 2), device_index=devs[r]).optimizer for r in range(2)]
+    streams = [torch.cuda.Stream(device=d) for d in devs]
+    boxes = (C.c_void_p * 2)()
+    for r, o in enumerate(shards):
+        L.check(lib.ctk_set_stream(o._h, C.c_void_p(streams[r].cuda_stream)))
+        p = C.c_void_p()
+        L.check(lib.ctk_exchange_mailbox(o._h, C.byref(p)))
+        boxes[r] = p.value
+    dv = (C.c_int * 2)(*devs)
+    for r, o in enumerate(shards):
+        L.check(lib.ctk_exchange_connect_ptrs(o._h, r, 2, boxes, dv))
+    s_dev = [torch.zeros(6, device=f"cuda:{d}") for d in devs]
+    u_dev = [torch.zeros(4, device=f"cuda:{d}") for d in devs]
+    from oracle import spec
+    for t, s0 in enumerate(spec.synthetic_states(3, seed=41)):
+        u_full = full.step(s0)
+        for r in range(2):
+            s_dev[r].copy_(torch.from_numpy(np.asarray(s0, np.float32)))
+        torch.cuda.synchronize()
+        for r, o in enumerate(shards):
+            L.check(lib.ctk_step_device(o._h, C.c_void_p(s_dev[r].data_ptr()), C.c_void_p(u_dev[r].data_ptr())))
+        for d in set(devs):
+            torch.cuda.synchronize(d)
+        us = [float(u.cpu().numpy()[0]) for u in u_dev]
+        assert us[0] == us[1] == float(u_full), (t, us, u_full)  # same elites -> same regenerated rows -> bit-identical
+        for o in shards:
+            np.testing.assert_array_equal(o.last_elite_indices(iters), full.optimizer.last_elite_indices(iters))
+            np.testing.assert_array_equal(o.dist_mue, full.optimizer.dist_mue)
+            np.testing.assert_array_equal(o.stdev, full.optimizer.stdev)
+
+
 def test_philox_statistics_and_determinism():
     """In-kernel Philox4x32-10 (parity is defined under injected noise only; this validates the generator statistically):
     moments and a KS test of the normals / uniforms, identical streams for identical seeds, different for different."""
