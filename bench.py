@@ -185,19 +185,78 @@ def cpu_mppi_rate(workload, n_sample, ticks, warm=1):
     return n_sample * H * passes_per_tick(opt_name) / statistics.mean(times), statistics.mean(times), torch.get_num_threads()
 
 
+def cpu_reference_rate(workload, n_sample, ticks, warm=1):
+    """rollout-steps/s of the reference's UNMODIFIED optimizer file (imported from /root/reference through the test-only shims of
+    oracle/refharness: SI_Toolkit stand-in with the pinned spec predictor / cost, torch-CPU fp32).  Only where the reference checkout
+    exists (the build container); the GPU box has no /root/reference and times the oracle port instead."""
+    import copy
+    import logging
+    import torch
+    import yaml
+    from oracle.refharness.workspace import enter_workspace
+    torch.set_num_threads(os.cpu_count() or 1)
+    opt_name, pred, cost, _, H = WORKLOADS[workload]
+    cwd = os.getcwd()
+    enter_workspace()
+    try:
+        logging.disable(logging.INFO)
+        from oracle import spec
+        from SI_Toolkit.Predictors import predictor_wrapper as pw
+        cc = dict(mpc=dict(optimizer=opt_name, predictor_specification=pred, cost_function_specification=cost,
+                           computation_library="tensorflow" if opt_name.endswith("-tf") else "pytorch", device="cpu",
+                           controller_logging=False, calculate_optimal_trajectory=False))
+        with open(os.path.join("Control_Toolkit_ASF", "config_controllers.yml"), "w") as f:
+            yaml.safe_dump(cc, f)
+        if pred.startswith("Dense"):
+            pw.MLP_REGISTRY[pred] = spec.MLPWeights.random_init(2)
+        from Control_Toolkit.Controllers import controller_mpc as cm  # the reference module, unmodified
+        cm.config_optimizers[opt_name] = dict(copy.deepcopy(OPT_CFG[opt_name]), mpc_horizon=H, num_rollouts=n_sample)
+        ctrl = cm.controller_mpc(environment_name="CartPole", control_limits=(np.array([-1.0], np.float32), np.array([1.0], np.float32)),
+                                 initial_environment_attributes={"target_position": 0.0, "target_equilibrium": 1.0})
+        ctrl.configure(optimizer_name=opt_name, predictor_specification=pred)
+        if opt_name == "rpgd":
+            ctrl.optimizer.u = np.float32(0.0)
+        states = synthetic_states(ticks + warm, 0)
+        times = []
+        for t in range(ticks + warm):
+            t0 = time.perf_counter()
+            ctrl.step(states[t], time=0.02 * t)
+            if t >= warm:
+                times.append(time.perf_counter() - t0)
+    finally:
+        os.chdir(cwd)
+    return n_sample * H * passes_per_tick(opt_name) / statistics.mean(times), statistics.mean(times), torch.get_num_threads()
+
+
+def reference_checkout_available():
+    try:
+        from oracle.refharness.workspace import reference_available
+        return reference_available()
+    except Exception:
+        return False
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     opt_name, _, _, N, H = WORKLOADS[args.workload]
     n_sample = min(N, args.cpu_sample)
-    rate, sec, threads = cpu_mppi_rate(args.workload, n_sample, args.steps, args.warmup)
-    sample = f"{args.steps} ticks of {n_sample} rollouts x H={H} (of {N}) per step, oracle port of the reference's optimizer_{opt_name.replace('-', '_')}.py, torch-CPU fp32"
+    kind = "reference" if reference_checkout_available() else "port"
+    if kind == "reference":
+        rate, sec, threads = cpu_reference_rate(args.workload, n_sample, args.steps, args.warmup)
+        what = f"the reference's UNMODIFIED optimizer_{opt_name.replace('-', '_')}.py through controller_mpc (oracle/refharness shims), torch-CPU fp32"
+    else:
+        rate, sec, threads = cpu_mppi_rate(args.workload, n_sample, args.steps, args.warmup)
+        what = (f"oracle PORT of the reference's optimizer_{opt_name.replace('-', '_')}.py (torch-CPU fp32, eager); the reference checkout is not on this box -- "
+                "profiles/reference_vs_port_r02.json shows the port and the unmodified file within a few percent of each other on the same host")
+    sample = f"{args.steps} ticks of {n_sample} rollouts x H={H} (of {N}) per step, {what}"
     line = {"impl": "reference", "metric": "rollout-steps/s", "value": rate, "unit": "rollout-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "optimizer": opt_name, "num_rollouts": N, "mpc_horizon": H, "predictor": WORKLOADS[args.workload][1]},
-            "cpu_baseline": {"value": rate, "unit": "rollout-steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": "rollout-steps/s", "cores": threads, "kind": kind, "sample": sample,
+                             "same_config": n_sample == N},
             "e2e": {"value": rate, "unit": "rollout-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _emit(line)
@@ -428,9 +487,12 @@ def run_ours(args):
         if world == 1:  # the CPU baseline is timed at N = 1 only (the multi-GPU lines would just repeat it)
             n_sample = min(N, args.cpu_sample)
             rate, sec, threads = cpu_mppi_rate(args.workload, n_sample, 2, 1)
-            cpu = {"value": rate, "unit": "rollout-steps/s", "cores": threads, "kind": "port",
-                   "sample": f"2 ticks of {n_sample} rollouts x H={H} (of {N}); oracle port of reference optimizer_{opt_name.replace('-', '_')}.py, torch-CPU fp32; "
+            cpu = {"value": rate, "unit": "rollout-steps/s", "cores": threads, "kind": "port", "same_config": n_sample == N,
+                   "sample": f"2 ticks of {n_sample} rollouts x H={H} (of {N}); oracle PORT (torch-CPU fp32, eager) of reference optimizer_{opt_name.replace('-', '_')}.py; "
                              f"{sec:.2f} s/tick"}
+            if n_sample < N:  # throughput is flat in N once the population is large: a second, smaller sample next to it
+                rate2, sec2, _ = cpu_mppi_rate(args.workload, max(n_sample // 4, 1), 2, 1)
+                cpu["flat_in_N"] = {"rollouts": max(n_sample // 4, 1), "value": rate2, "s_per_tick": sec2}
         else:
             cpu = None
         line = {"metric": "rollout-steps/s", "value": value, "unit": "rollout-steps/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -466,7 +528,7 @@ def main():
     ap.add_argument("--workload", default="mppi_ode_1m", choices=sorted(WORKLOADS))
     ap.add_argument("--rollouts", type=int, default=None, help="override the global rollout count")
     ap.add_argument("--mlp-engine", default="tcgen05", choices=["simt", "tcgen05", "tcgen05_bf16", "tcgen05_fast"], help="MLP predictor engine (mppi_mlp_c4 workload)")
-    ap.add_argument("--cpu-sample", type=int, default=100_000, help="rollouts per CPU-baseline tick (bounded sample)")
+    ap.add_argument("--cpu-sample", type=int, default=250_000, help="rollouts per CPU-baseline tick (bounded sample; C1-C4 run at their full size)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

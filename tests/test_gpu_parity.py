@@ -785,18 +785,21 @@ def test_two_shards_equal_one(name):
             assert np.abs(shards[0].dist_mue - full.optimizer.dist_mue).max() < 1e-6
 
 
-def test_fused_exchange_two_shards_one_launch_each():
+@pytest.mark.parametrize("fixture,over", [("mppi_c1_n2000", {}), ("mppi_mlp_c4_n256", {"mlp_engine": "tcgen05"}), ("mppi_mlp_c4_n256", {"mlp_engine": "simt"})],
+                         ids=["ode_c1", "mlp_c4_tcgen05", "mlp_c4_simt"])
+def test_fused_exchange_two_shards_one_launch_each(fixture, over):
     """The fused cross-GPU exchange (MppiFuse: peer-memory mailboxes, ctk_exchange_connect_ptrs + ctk_step_device), driven
-    by two handles that own the two halves of the population.  Uses GPU 0 and GPU 1 when two devices are visible, else
+    by two handles that own the two halves of the population -- for the ODE predictor (K1) and for the MLP predictor on both
+    engines (SURVEY 8e row "MLP MPPI (C4): as MPPI, weights replicated").  Uses GPU 0 and GPU 1 when two devices are visible, else
     both shards run on GPU 0 on separate streams (the mailbox protocol is the same; only the stores are local)."""
     import ctypes as C
     import torch
     from control_toolkit_b200 import _lib as L
     lib = L.load()
-    z, meta = load_golden("mppi_c1_n2000")
-    full = make_controller(meta, rng=None, logging=False)
+    z, meta = load_golden(fixture)
+    full = make_controller(meta, rng=None, logging=False, **over)
     devs = [0, 1] if torch.cuda.device_count() >= 2 else [0, 0]
-    shards = [make_controller(meta, rng=None, logging=False, shard=_FixedShard(r, 2), device_index=devs[r]).optimizer for r in range(2)]
+    shards = [make_controller(meta, rng=None, logging=False, shard=_FixedShard(r, 2), device_index=devs[r], **over).optimizer for r in range(2)]
     streams = [torch.cuda.Stream(device=d) for d in devs]
     boxes = (C.c_void_p * 2)()
     for r, o in enumerate(shards):
@@ -809,7 +812,7 @@ def test_fused_exchange_two_shards_one_launch_each():
         L.check(lib.ctk_exchange_connect_ptrs(o._h, r, 2, boxes, dv))
     s_dev = [torch.zeros(6, device=f"cuda:{d}") for d in devs]
     u_dev = [torch.zeros(4, device=f"cuda:{d}") for d in devs]
-    for t in range(3):
+    for t in range(min(3, meta["ticks"])):
         u_full = full.step(z["states"][t])
         for r, o in enumerate(shards):
             s_dev[r].copy_(torch.from_numpy(np.asarray(z["states"][t], np.float32)))
