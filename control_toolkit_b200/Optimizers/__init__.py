@@ -65,6 +65,9 @@ class template_optimizer:
         # until the next step(); controller_mpc.update_logs copies them like the reference, Controllers/__init__.py:159-178);
         # smaller logs are fresh copies.  None: always copy.
         self.log_view_min_bytes = kwargs.pop("log_view_min_bytes", 16 << 20)
+        # > 1: the handle carries that many independent clients whose ticks run in ONE launch (optimizer_mppi.step_batch; the
+        # serving edge of SURVEY 8f.4).  1: the reference's single controller.
+        self.num_clients = int(kwargs.pop("num_clients", 1))
         self._h = None
         self._cost_spec = None
         self._cost_live = (None, None)
@@ -144,6 +147,7 @@ class template_optimizer:
         if self.mlp_engine not in engines:
             raise ValueError(f"mlp_engine must be one of {sorted(engines)}, got {self.mlp_engine!r}")
         cfg.mlp_engine = engines[self.mlp_engine]
+        cfg.num_clients = self.num_clients
         self._fill_config(cfg)
 
         tp, te = self._live_targets()
@@ -161,6 +165,10 @@ class template_optimizer:
             self._mlp_keepalive = pred_spec
             w = pred_spec.to_c()
             L.check(lib.ctk_set_mlp_weights(self._h, C.byref(w)))
+        elif pred_kind == L.PRED_GRU:
+            self._mlp_keepalive = pred_spec
+            w = pred_spec.to_c()
+            L.check(lib.ctk_set_gru_weights(self._h, C.byref(w)))
         self._u_buf = np.zeros(1, np.float32)
         self._state_buf = None
 

@@ -100,11 +100,33 @@ class optimizer_mppi(template_optimizer):
             self.optimal_trajectory, _ = self.rollout_single(s, self.u_nom)
         return self.u
 
+    def step_batch(self, states: np.ndarray, active=None) -> np.ndarray:
+        """Ticks of several clients in ONE kernel launch (``num_clients`` > 1; SURVEY 8f.4 -- what the reference's server does with one
+        ``ctrl.step`` per request, controller_server/controller_server.py:55-86): ``states`` [num_clients, num_states], ``active``
+        [num_clients] bools (None: all).  Returns u [num_clients] (NaN for inactive slots).  Every client keeps its own warm-start
+        sequence, previous input and Philox tick counter, so its controls equal those of a controller of its own."""
+        import ctypes as C
+        lib = self._require_backend()
+        self._refresh_live_cost(lib)
+        B = self.num_clients
+        s32 = np.ascontiguousarray(np.asarray(states, dtype=np.float32).reshape(B, -1))
+        if s32.shape[1] != 6:
+            raise ValueError(f"states must be [{B}, 6], got {s32.shape}")
+        act = np.ones(B, np.int32) if active is None else np.ascontiguousarray(np.asarray(active).astype(np.int32).reshape(B))
+        u = np.full(B, np.nan, np.float32)
+        L.check(lib.ctk_step_batch(self._h, L.fptr(s32), act.ctypes.data_as(C.POINTER(C.c_int32)), L.fptr(u)))
+        return u
+
+    def reset_client(self, client: int) -> None:
+        """A new client takes over slot ``client``: fresh warm-start sequence, previous input and tick counter."""
+        lib = self._require_backend()
+        L.check(lib.ctk_reset_client(self._h, int(client)))
+
     def optimizer_reset(self):
         lib = self._require_backend()
         L.check(lib.ctk_reset(self._h))
         # self.u (the cost's previous_input) survives optimizer_reset() in the reference: only optimizer_cem_tf.py:117 resets it
-        self.u_nom = self._get_state(L.STATE_U_NOM, (1, self.mpc_horizon, self.num_control_inputs))
+        self.u_nom = self._get_state(L.STATE_U_NOM, (self.num_clients, self.mpc_horizon, self.num_control_inputs))
 
     # state access (part of the parity contract: "optimizer state within 1e-5")
     def get_state(self) -> dict:

@@ -5,7 +5,7 @@ Drop-in optimizer plugins (``optimizer_mppi``, ``optimizer_cem_tf``, ``optimizer
 C ABI of ``libctk_b200.so`` (include/ctk_b200.h).  No TensorFlow, no Triton, no CPU fallback.
 """
 from ._lib import BackendUnavailable, LIB_PATH  # noqa: F401
-from .specs import MLPSpec, register_mlp  # noqa: F401
+from .specs import GRUSpec, MLPSpec, register_gru, register_mlp  # noqa: F401
 from .wrappers import CostFunctionWrapper, PredictorWrapper, VariableParameters  # noqa: F401
 
 __version__ = "0.1.0"

@@ -17,12 +17,12 @@ LIB_PATH = os.path.join(HERE, "libctk_b200.so")
 CTK_ABI_VERSION = 1
 CTK_OK, CTK_EINVAL, CTK_ECUDA, CTK_ESTATE = 0, -1, -2, -3
 OPT_MPPI, OPT_CEM, OPT_RPGD = 0, 1, 2
-PRED_ODE, PRED_MLP = 0, 1
+PRED_ODE, PRED_MLP, PRED_GRU = 0, 1, 2
 COST_DEFAULT, COST_QUADRATIC_BOUNDARY_GRAD = 0, 1
 DIST_NORMAL, DIST_UNIFORM = 0, 1
 ADAM_KERAS, ADAM_TORCH = 0, 1
 MLP_SIMT, MLP_TCGEN05, MLP_TCGEN05_BF16, MLP_TCGEN05_FAST = 0, 1, 2, 3
-STATE_U_NOM, STATE_CEM_MU, STATE_CEM_STD, STATE_RPGD_Q, STATE_RPGD_M, STATE_RPGD_V, STATE_RPGD_AGES, STATE_U_PREV = range(8)
+STATE_U_NOM, STATE_CEM_MU, STATE_CEM_STD, STATE_RPGD_Q, STATE_RPGD_M, STATE_RPGD_V, STATE_RPGD_AGES, STATE_U_PREV, STATE_RNN_H = range(9)
 COUNTER_COUNT, COUNTER_ADAM_STEP, COUNTER_TICK = range(3)
 STREAM_MPPI, STREAM_CEM, STREAM_RPGD_INIT, STREAM_RPGD_RESAMPLE = range(4)
 LOG_Q, LOG_J, LOG_ROLLOUTS, LOG_ELITE_IDX, LOG_U_NOM, LOG_AGES = range(6)
@@ -47,6 +47,10 @@ class ctk_mlp_weights(C.Structure):
     _fields_ = [("hidden", C.c_int32)] + [(n, C.POINTER(C.c_float)) for n in ("W1", "b1", "W2", "b2", "W3", "b3")]
 
 
+class ctk_gru_weights(C.Structure):
+    _fields_ = [("hidden", C.c_int32)] + [(n, C.POINTER(C.c_float)) for n in ("Wi1", "Wh1", "bi1", "bh1", "Wi2", "Wh2", "bi2", "bh2", "W3", "b3")]
+
+
 class ctk_config(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32), ("optimizer", C.c_int32), ("predictor", C.c_int32), ("device", C.c_int32),
@@ -65,7 +69,7 @@ class ctk_config(C.Structure):
         ("rpgd_sample_mean", C.c_float), ("rpgd_sample_stdev", C.c_float), ("rpgd_sample_min", C.c_float),
         ("rpgd_sample_max", C.c_float), ("rpgd_learning_rate", C.c_float), ("rpgd_gradmax_clip", C.c_float),
         ("rpgd_beta_1", C.c_double), ("rpgd_beta_2", C.c_double), ("rpgd_epsilon", C.c_double),
-        ("mlp_engine", C.c_int32), ("cem_uniform_actions", C.c_int32), ("rpgd_gradient_mode", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("mlp_engine", C.c_int32), ("cem_uniform_actions", C.c_int32), ("rpgd_gradient_mode", C.c_int32), ("num_clients", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -79,6 +83,7 @@ SYMBOLS = {
     "ctk_set_cost_params": (C.c_int, [_H, C.POINTER(ctk_cost_params)]),
     "ctk_set_ode_params": (C.c_int, [_H, C.POINTER(ctk_ode_params)]),
     "ctk_set_mlp_weights": (C.c_int, [_H, C.POINTER(ctk_mlp_weights)]),
+    "ctk_set_gru_weights": (C.c_int, [_H, C.POINTER(ctk_gru_weights)]),
     "ctk_set_stream": (C.c_int, [_H, C.c_void_p]),
     "ctk_push_injected_noise": (C.c_int, [_H, _FP, C.c_size_t]),
     "ctk_clear_injected_noise": (C.c_int, [_H]),
@@ -87,6 +92,8 @@ SYMBOLS = {
     "ctk_step_local": (C.c_int, [_H, C.c_void_p]),
     "ctk_partials": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "ctk_step_finish": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p]),
+    "ctk_step_batch": (C.c_int, [_H, _FP, C.POINTER(C.c_int32), _FP]),
+    "ctk_reset_client": (C.c_int, [_H, C.c_int]),
     "ctk_step_device": (C.c_int, [_H, C.c_void_p, C.c_void_p]),
     "ctk_step_device_n": (C.c_int, [_H, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
     "ctk_exchange_barrier": (C.c_int, [_H]),

@@ -12,13 +12,14 @@ import os
 import shutil
 import subprocess
 import sys
+import time
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libctk_b200.so")
-UNITS = ["ctk_engine.cu", "ctk_mppi.cu", "ctk_cem.cu", "ctk_rpgd.cu"]
+UNITS = ["ctk_engine.cu", "ctk_mppi.cu", "ctk_cem.cu", "ctk_rpgd.cu", "ctk_batch.cu", "ctk_gru.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-I", INCLUDE, "-I", CSRC] + os.environ.get("CTK_NVCC_EXTRA", "").split()  # e.g. -DCTK_TC_TRACE (diagnostics)
 
@@ -48,9 +49,12 @@ def _compile(unit: str, verbose: bool) -> str:
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
+    t0 = time.perf_counter()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {unit}:\n{r.stdout}\n{r.stderr}")
+    if os.environ.get("CTK_BUILD_TIMES"):
+        sys.stderr.write(f"{unit}: {time.perf_counter() - t0:.1f} s\n")
     if verbose:
         sys.stderr.write(r.stderr)
     return obj

@@ -43,9 +43,14 @@ struct MlpDev {
   const float* blob;       // device: W1[6][hid] | b1[hid] | W2[hid][hid] | b2[hid] | W3T[5][hid] | b3[8]
   int blob_floats;
   const void* tc_blob;     // device: tcgen05 engine blob (ctk_mlp_tc.cuh: W2 bf16 split tiles | W1 | b1 | b2 | W3T | b3) or null
+  // recurrent predictor (GruSimtPred): blob = Wi1[6][3h] | Wh1[h][3h] | bi1[3h] | bh1[3h] | Wi2[h][3h] | Wh2[h][3h] | bi2[3h] | bh2[3h] |
+  // W3T[5][h] | b3[8], gate order [r, z, n]; rnn_h = the SAVED hidden state [2][2h]: row 0 current (every rollout starts from it),
+  // row 1 the state before the last predictor.update (nominal rollout of the tick, reference optimizer_mppi.py:199-202)
+  const float* rnn_h;
 };
 
 CTK_HD int mlp_blob_floats(int hid) { return 6 * hid + hid + hid * hid + hid + 5 * hid + 8; }
+CTK_HD int gru_blob_floats(int hid) { return 3 * hid * (6 + hid + 2) + 3 * hid * (2 * hid + 2) + 5 * hid + 8; }
 
 // Loop-invariant constants of the rollout kernels live in DEVICE memory (handle-owned) and are read once per thread
 // with volatile loads: sm_100 FP instructions take no constant-bank operands and ptxas re-issues LDC/LDCU inside the
@@ -172,6 +177,16 @@ struct MppiOdeArgs {
   float* log_Q_soa;     // [H][N] or null
   unsigned long long* trace;  // [gridDim.x][8] globaltimer stamps per block (diagnostics) or null
   MppiFuse fuse;
+};
+
+// Several clients' MPPI ticks in one launch (mppi_ode_batch_kernel, ctk_kernels_mppi_ode.cuh): per-client inputs inside the kernel
+// parameters, per-client state behind the pointers of client 0 at fixed strides
+constexpr int kMaxBatchClients = 16;
+struct MppiBatch {
+  int active[kMaxBatchClients];
+  uint32_t tick[kMaxBatchClients];   // Philox counter word of the client's tick
+  float s0[kMaxBatchClients][8];     // measured states
+  size_t stride_unom, stride_J, stride_partials, stride_record, stride_mbox;  // elements between consecutive clients
 };
 
 struct CemArgs {

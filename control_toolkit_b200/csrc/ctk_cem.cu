@@ -19,6 +19,7 @@ static cudaError_t launch_cem_p(int kind, bool log, int nblocks, size_t smem, cu
   return log ? launch_cem_t<Pred, 1, true>(nblocks, smem, st, a) : launch_cem_t<Pred, 1, false>(nblocks, smem, st, a);
 }
 cudaError_t launch_cem_rollout(int pred, int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemArgs& a) {
+  if (pred == 5) return launch_cem_rollout_gru(kind, log, nblocks, smem, st, a);  // ctk_gru.cu
   return pred == 0 ? launch_cem_p<OdePred>(kind, log, nblocks, smem, st, a) : launch_cem_p<MlpSimtPred>(kind, log, nblocks, smem, st, a);
 }
 cudaError_t launch_cem_ode(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemOdeArgs& a) {

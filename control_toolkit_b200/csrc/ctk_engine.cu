@@ -101,6 +101,13 @@ struct ctk_handle {
   // mlp
   float* d_mlp = nullptr;
   void* d_mlp_tc = nullptr;  // tcgen05 engine blob (ctk_mlp_tc.cuh)
+  float* d_rnn_h = nullptr;  // recurrent predictor: saved hidden state [2][2 hid] (row 0 current, row 1 before the last update)
+  const float* step_s = nullptr;  // state pointer of the tick in flight (staged MPPI ticks: predictor.update runs in ctk_step_finish)
+  // multi-client batching (ctk_step_batch): per-client state sits behind the pointers of client 0 at fixed strides
+  int nclients = 1;
+  uint32_t client_tick[kMaxBatchClients] = {0};
+  float* h_batch = nullptr;  // pinned: [nclients][2] u, status
+  size_t mbox_stride = 0, partials_stride = 0;
   // counters
   int64_t count = 0, adam_step = 0, tick = 0, launches = 0;
   bool was_reset = false;
@@ -218,12 +225,14 @@ extern "C" int ctk_destroy(ctk_handle* h) {
   if (h->d_cem_dist) cudaFree(h->d_cem_dist);
   if (h->d_best_idx) cudaFree(h->d_best_idx);
   if (h->d_mlp_tc) cudaFree(h->d_mlp_tc);
+  if (h->d_rnn_h) cudaFree(h->d_rnn_h);
   for (int r = 0; r < CTK_MAX_PEERS; ++r)
     if (h->mbox_ipc[r] && h->mbox_peer[r]) cudaIpcCloseMemHandle(h->mbox_peer[r]);
   if (h->d_trace) cudaFree(h->d_trace);
   if (h->d_mbox) cudaFree(h->d_mbox);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->h_pin) cudaFreeHost(h->h_pin);
+  if (h->h_batch) cudaFreeHost(h->h_batch);
   for (void* p : h->h_log) if (p) cudaFreeHost(p);
   delete h;
   return CTK_OK;
@@ -233,7 +242,7 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
   REQ(cfg && ode && cost && out, "null pointer");
   REQ(cfg->abi_version == CTK_ABI_VERSION, "abi_version mismatch");
   REQ(cfg->optimizer >= CTK_OPT_MPPI && cfg->optimizer <= CTK_OPT_RPGD, "unknown optimizer");
-  REQ(cfg->predictor == CTK_PRED_ODE || cfg->predictor == CTK_PRED_MLP, "unknown predictor");
+  REQ(cfg->predictor == CTK_PRED_ODE || cfg->predictor == CTK_PRED_MLP || cfg->predictor == CTK_PRED_GRU, "unknown predictor");
   REQ(cfg->num_states == 6 && cfg->num_control_inputs == 1,
       "only the registered CartPole environment (6 states, 1 control) has device functors");
   REQ(cfg->num_rollouts >= 1 && cfg->mpc_horizon >= 1, "num_rollouts and mpc_horizon must be >= 1");
@@ -245,6 +254,10 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
     REQ(cfg->rpgd_resamp_per >= 1 || cfg->rpgd_gradient_mode != 0, "rpgd_resamp_per must be >= 1");
     REQ(cfg->rpgd_outer_its >= 0 && cfg->rpgd_first_iter_count >= 0, "RPGD iteration counts must be >= 0");
   }
+  const int B = cfg->num_clients > 1 ? cfg->num_clients : 1;
+  REQ(B <= kMaxBatchClients, "num_clients must be <= 16");
+  REQ(B == 1 || (cfg->optimizer == CTK_OPT_MPPI && cfg->predictor == CTK_PRED_ODE && !cfg->logging && cfg->num_rollouts == cfg->num_rollouts_global),
+      "multi-client handles are implemented for MPPI with the ODE predictor, logging off, unsharded");
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
   REQ(cfg->device >= 0 && cfg->device < ndev, "no such CUDA device");
@@ -254,18 +267,20 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
   h->cfg = *cfg;
   h->N = cfg->num_rollouts; h->NG = cfg->num_rollouts_global; h->off = cfg->rollout_offset; h->H = cfg->mpc_horizon;
   h->ode_p = *ode; h->cost_p = *cost;
+  h->nclients = B;
   derive_ode(*ode, h->ode);
   derive_fwd(*ode, h->fwd);
   derive_cost(*cost, h->H, h->cost);
-  h->mlp = MlpDev{0, nullptr, 0, nullptr};
+  h->mlp = MlpDev{0, nullptr, 0, nullptr, nullptr};
   h->nblocks = (h->N + 127) / 128;
   const int N = h->N, H = h->H;
   int rc = CTK_OK;
   auto A = [&](cudaError_t e, const char* what) {
     if (e != cudaSuccess && rc == CTK_OK) rc = fail(CTK_ECUDA, std::string("cudaMalloc ") + what + ": " + cudaGetErrorString(e));
   };
-  A(dalloc(&h->d_s0, 8), "s0"); A(dalloc(&h->d_u_prev, 1), "u_prev"); A(dalloc(&h->d_u_out, 4), "u_out");
-  A(dalloc(&h->d_J, (size_t)N), "J");
+  A(dalloc(&h->d_s0, 8), "s0"); A(dalloc(&h->d_u_prev, (size_t)B), "u_prev"); A(dalloc(&h->d_u_out, 4 + 2 * (size_t)B), "u_out");
+  A(dalloc(&h->d_J, (size_t)N * B), "J");
+  if (B > 1) A(cudaHostAlloc((void**)&h->h_batch, 2 * (size_t)B * sizeof(float), cudaHostAllocDefault), "pinned (batch results)");
   A(cudaMalloc((void**)&h->d_kc, sizeof(DevConsts)), "consts");
   A(dalloc(&h->d_kx, 4), "kx");
   A(cudaHostAlloc((void**)&h->h_pin, (32 + 2 * (size_t)H) * sizeof(float), cudaHostAllocMapped), "pinned");
@@ -304,7 +319,7 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
       h->mppi_stash = 0;
     }
     h->mppi_rpb = h->mppi_block;
-    if (pred_id(h) >= 2) {  // tcgen05 MLP engines: 16 worker warps + 1 MMA-issuer warp on the 128 rollouts of one MMA tile (ctk_mlp_tc.cuh)
+    if (pred_id(h) >= 2 && pred_id(h) <= 4) {  // tcgen05 MLP engines: 16 worker warps + 1 MMA-issuer warp on the 128 rollouts of one MMA tile (ctk_mlp_tc.cuh)
       h->mppi_block = mppi_max_block_threads(2); h->mppi_rpb = 128;
       const int per_sm = pred_id(h) >= 3 ? 2 : 1;  // the single-product engines keep two tiles (CTAs) in flight per SM
       h->mppi_grid = (int)std::min<long long>((long long)per_sm * h->num_sms, ((long long)N + 127) / 128);
@@ -313,11 +328,13 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
       h->mppi_stash = ((size_t)h->n_ind * 128 * sizeof(float) <= 8 * 1024) ? 1 : 0;
       if ((size_t)h->n_ind * 128 * sizeof(float) > 8 * 1024) { ctk_destroy(h); return fail(CTK_EINVAL, "tcgen05 MLP engine: too many inducing points (shared memory is taken by the operand tiles)"); }
     }
-    A(dalloc(&h->d_u_nom, (size_t)H), "u_nom");
-    A(dalloc(&h->d_partials, (size_t)(h->num_sms > h->mppi_grid ? h->num_sms : h->mppi_grid) * (h->mppi_iters + 1) * (h->n_ind + 2)), "partials");
-    A(dalloc(&h->d_record, (size_t)(h->n_ind + 2)), "record");
+    A(dalloc(&h->d_u_nom, (size_t)H * B), "u_nom");
+    h->partials_stride = (size_t)(h->num_sms > h->mppi_grid ? h->num_sms : h->mppi_grid) * (h->mppi_iters + 1) * (h->n_ind + 2);
+    A(dalloc(&h->d_partials, h->partials_stride * B), "partials");
+    A(dalloc(&h->d_record, (size_t)(h->n_ind + 2) * B), "record");
     if (h->mppi_grid > CTK_MBOX_BLOCKS || h->num_sms > CTK_MBOX_BLOCKS) { ctk_destroy(h); return fail(CTK_EINVAL, "device has more SMs than the mailbox has block slots (CTK_MBOX_BLOCKS)"); }
-    A(dalloc(&h->d_mbox, mbox_total_slots(h->n_ind, H)), "mailbox");
+    h->mbox_stride = (mbox_total_slots(h->n_ind, H) + 1) & ~(size_t)1;  // even: the records are polled with 16-byte loads
+    A(dalloc(&h->d_mbox, h->mbox_stride * B), "mailbox");
     h->mbox_peer[0] = h->d_mbox;
   } else if (cfg->optimizer == CTK_OPT_CEM) {
     if (!(cfg->cem_best_k >= 1 && cfg->cem_best_k <= 512 && cfg->cem_best_k <= cfg->num_rollouts_global && H <= 1024 && cfg->cem_outer_it >= 1)) {
@@ -368,6 +385,9 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
     }
   }
   if (rc == CTK_OK) A(upload_consts(h), "upload_consts");
+  if (rc == CTK_OK && B > 1 && !(h->ode_kernel && h->ode_ilp == 1))
+    rc = fail(CTK_EINVAL, "multi-client handles run the one-rollout-per-thread ODE kernel: intermediate_steps == 1, few inducing points, "
+                          "num_rollouts <= 1024 x SMs per client");
   if (rc != CTK_OK) { std::string keep = g_err; ctk_destroy(h); g_err = keep; return rc; }
   *out = h;
   return CTK_OK;
@@ -411,7 +431,8 @@ extern "C" int ctk_set_mlp_weights(ctk_handle* h, const ctk_mlp_weights* w) {
   if (h->d_mlp) { cudaFree(h->d_mlp); h->d_mlp = nullptr; }
   CU(dalloc(&h->d_mlp, (size_t)nf));
   CU(cudaMemcpy(h->d_mlp, blob.data(), sizeof(float) * nf, cudaMemcpyHostToDevice));
-  h->mlp = MlpDev{hid, h->d_mlp, nf, nullptr};
+  REQ(h->cfg.predictor == CTK_PRED_MLP, "ctk_set_mlp_weights on a handle whose predictor is not CTK_PRED_MLP");
+  h->mlp = MlpDev{hid, h->d_mlp, nf, nullptr, nullptr};
   if (h->cfg.mlp_engine != CTK_MLP_SIMT) {
     REQ(h->cfg.mlp_engine >= CTK_MLP_TCGEN05 && h->cfg.mlp_engine <= CTK_MLP_TCGEN05_FAST, "unknown mlp_engine");
     REQ(hid == kTcHidden, "the tcgen05 MLP engines are built for hidden == 128 (use mlp_engine=simt otherwise)");
@@ -446,6 +467,30 @@ extern "C" int ctk_set_mlp_weights(ctk_handle* h, const ctk_mlp_weights* w) {
     CU(cudaMemcpy(h->d_mlp_tc, tc.data(), kTcBlobBytes, cudaMemcpyHostToDevice));
     h->mlp.tc_blob = h->d_mlp_tc;
   }
+  return CTK_OK;
+}
+
+extern "C" int ctk_set_gru_weights(ctk_handle* h, const ctk_gru_weights* w) {
+  REQ(h && w && w->Wi1 && w->Wh1 && w->bi1 && w->bh1 && w->Wi2 && w->Wh2 && w->bi2 && w->bh2 && w->W3 && w->b3, "null pointer");
+  REQ(h->cfg.predictor == CTK_PRED_GRU, "ctk_set_gru_weights on a handle whose predictor is not CTK_PRED_GRU");
+  REQ(w->hidden >= 8 && w->hidden <= 32 && w->hidden % 8 == 0, "GRU hidden width must be a multiple of 8 in [8,32]");
+  CU(cudaSetDevice(h->cfg.device));
+  const int hid = w->hidden, g = 3 * hid, nf = gru_blob_floats(hid);
+  std::vector<float> blob((size_t)nf, 0.0f);
+  float* p = blob.data();
+  auto put = [&](const float* src, size_t n) { memcpy(p, src, sizeof(float) * n); p += n; };
+  put(w->Wi1, (size_t)6 * g); put(w->Wh1, (size_t)hid * g); put(w->bi1, g); put(w->bh1, g);
+  put(w->Wi2, (size_t)hid * g); put(w->Wh2, (size_t)hid * g); put(w->bi2, g); put(w->bh2, g);
+  for (int k = 0; k < 5; ++k) for (int j = 0; j < hid; ++j) p[k * hid + j] = w->W3[j * 5 + k];  // W3T[5][hid]
+  p += 5 * hid;
+  memcpy(p, w->b3, sizeof(float) * 5);
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->d_mlp) { cudaFree(h->d_mlp); h->d_mlp = nullptr; }
+  if (h->d_rnn_h) { cudaFree(h->d_rnn_h); h->d_rnn_h = nullptr; }
+  CU(dalloc(&h->d_mlp, (size_t)nf));
+  CU(cudaMemcpy(h->d_mlp, blob.data(), sizeof(float) * nf, cudaMemcpyHostToDevice));
+  CU(dalloc(&h->d_rnn_h, (size_t)4 * hid));  // zero state (SI_Toolkit resets the RNN when the predictor is configured)
+  h->mlp = MlpDev{hid, h->d_mlp, nf, nullptr, h->d_rnn_h};
   return CTK_OK;
 }
 
@@ -496,12 +541,12 @@ extern "C" int ctk_reset(ctk_handle* h) {
   REQ(h, "null handle");
   CU(cudaSetDevice(h->cfg.device));
   const float mid = 0.5f * (h->cfg.action_low + h->cfg.action_high);
-  std::vector<float> tmp((size_t)h->H, mid);
+  std::vector<float> tmp((size_t)h->H * h->nclients, mid);
   // self.u, the previous_input of the cost, is reset ONLY by optimizer_cem_tf.optimizer_reset (optimizer_cem_tf.py:117); MPPI (:227-231),
   // RPGD (:527-548), random-action, gradient-tf and the gradient-assisted CEM variants keep the last applied control
   if (h->cfg.optimizer == CTK_OPT_CEM && !h->cfg.cem_uniform_actions) CU(cudaMemsetAsync(h->d_u_prev, 0, sizeof(float), h->stream));
   if (h->cfg.optimizer == CTK_OPT_MPPI) {
-    CU(cudaMemcpyAsync(h->d_u_nom, tmp.data(), sizeof(float) * h->H, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_u_nom, tmp.data(), sizeof(float) * h->H * h->nclients, cudaMemcpyHostToDevice, h->stream));
   } else if (h->cfg.optimizer == CTK_OPT_CEM) {
     CU(cudaMemcpyAsync(h->d_mu, tmp.data(), sizeof(float) * h->H, cudaMemcpyHostToDevice, h->stream));
     std::vector<float> sd((size_t)h->H, h->cfg.cem_initial_action_stdev);
@@ -537,6 +582,7 @@ extern "C" int ctk_reset(ctk_handle* h) {
 // ---------------------------------------------------------------------------------------------------------------
 // 0 ODE, 1 MLP on the FP32 pipe, 2 MLP with the dense layer on tcgen05 (bf16 x 3 split, fp32-level), 3 one bf16 product, 4 + MUFU.TANH
 static int pred_id(const ctk_handle* h) {
+  if (h->cfg.predictor == CTK_PRED_GRU) return 5;  // recurrent predictor on the FP32 pipe (GruSimtPred)
   if (h->cfg.predictor != CTK_PRED_MLP) return 0;
   if (h->cfg.optimizer != CTK_OPT_MPPI) return 1;
   switch (h->cfg.mlp_engine) {
@@ -642,6 +688,14 @@ static int make_fuse(ctk_handle* h, int mode, float* u_out_dev, MppiFuse* out) {
   return CTK_OK;
 }
 
+// predictor.update(s, Q0 = new u_nom[0]) of a recurrent predictor (reference optimizer_mppi.py:192,195-197), after the tick's u_nom update
+static int rnn_update(ctk_handle* h, const float* s_dev) {
+  if (h->cfg.predictor != CTK_PRED_GRU) return CTK_OK;
+  h->launches++;
+  CU(launch_gru_update(make_s0(h, s_dev), h->d_u_nom, h->mlp, h->d_rnn_h, h->stream));
+  return CTK_OK;
+}
+
 // mode 1: rollouts + shard record (staged exchange follows)   mode 2: whole tick incl. cross-GPU exchange and u_nom update
 static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_dev) {
   NoiseSrc ns{};
@@ -691,12 +745,14 @@ static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_
                                        pred_smem_floats(h));
   h->launches++;
   KernelTimer kt(h);
-  if (pred_id(h) >= 2 && h->mlp.tc_blob == nullptr) return fail(CTK_ESTATE, "tcgen05 MLP engine without weights");
+  if (pred_id(h) >= 2 && pred_id(h) <= 4 && h->mlp.tc_blob == nullptr) return fail(CTK_ESTATE, "tcgen05 MLP engine without weights");
   cudaError_t e = launch_mppi_rollout(pred_id(h), h->cost.kind, log, h->mppi_grid, h->mppi_block, smem,
                                       h->stream, a);
-  h->last_kernel = std::string("mppi_rollout_kernel<") + (pred_id(h) == 4 ? "MlpTcFastPred" : pred_id(h) == 3 ? "MlpTcBf16Pred" : pred_id(h) == 2 ? "MlpTcPred" : pred_id(h) == 1 ? "MlpSimtPred" : "OdePred") + "," +
+  h->last_kernel = std::string("mppi_rollout_kernel<") + (pred_id(h) == 5 ? "GruSimtPred" : pred_id(h) == 4 ? "MlpTcFastPred" : pred_id(h) == 3 ? "MlpTcBf16Pred" : pred_id(h) == 2 ? "MlpTcPred" : pred_id(h) == 1 ? "MlpSimtPred" : "OdePred") + "," +
                    std::to_string(h->cost.kind) + "," + (log ? "1" : "0") + ">" + (ns.inj ? " [injected noise]" : " [philox]");
   if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("mppi_rollout_kernel: ") + cudaGetErrorString(e));
+  h->step_s = s_dev;
+  if (mode == 2) return rnn_update(h, s_dev);
   return CTK_OK;
 }
 
@@ -709,7 +765,7 @@ static int mppi_finish(ctk_handle* h, const float* gathered, int G, float* u_out
   fin.freeze_prev = c.freeze_previous_input;
   h->launches++;
   CU(launch_mppi_combine(gathered, G, h->n_ind, c.mppi_neg_inv_LBD, nullptr, fin, h->stream));
-  return CTK_OK;
+  return rnn_update(h, h->step_s);
 }
 
 // The whole CEM tick in one persistent launch, when the population fits one resident grid and is not sharded
@@ -845,7 +901,7 @@ static int cem_local(ctk_handle* h, const float* s_dev, bool to_k) {
     a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
     const size_t smem = sizeof(float) * (2 * (size_t)h->H + pred_smem_floats(h));
     KernelTimer kt(h);
-    e = launch_cem_rollout(c.predictor == CTK_PRED_ODE ? 0 : 1, h->cost.kind, c.logging != 0, h->nblocks, smem, h->stream, a);
+    e = launch_cem_rollout(pred_id(h), h->cost.kind, c.logging != 0, h->nblocks, smem, h->stream, a);
   }
   if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("cem_rollout_kernel: ") + cudaGetErrorString(e));
   // K4: hierarchical bitonic top-k
@@ -1067,7 +1123,7 @@ extern "C" int ctk_step_local(ctk_handle* h, const float* s_dev) {
   REQ(h && s_dev, "null pointer");
   if (!h->was_reset) return fail(CTK_ESTATE, "ctk_step before ctk_reset");
   CU(cudaSetDevice(h->cfg.device));
-  if (h->cfg.predictor == CTK_PRED_MLP && h->mlp.blob == nullptr) return fail(CTK_ESTATE, "MLP predictor without weights");
+  if (h->cfg.predictor != CTK_PRED_ODE && h->mlp.blob == nullptr) return fail(CTK_ESTATE, "network predictor without weights (ctk_set_mlp_weights / ctk_set_gru_weights)");
   int rc;
   switch (h->cfg.optimizer) {
     case CTK_OPT_MPPI:
@@ -1160,7 +1216,7 @@ static int step_host(ctk_handle* h, const float* s_host, float* u_out_host, cons
   REQ(h && s_host && u_out_host, "null pointer");
   if (!h->was_reset) return fail(CTK_ESTATE, "ctk_step before ctk_reset");
   CU(cudaSetDevice(h->cfg.device));
-  if (h->cfg.predictor == CTK_PRED_MLP && h->mlp.blob == nullptr) return fail(CTK_ESTATE, "MLP predictor without weights");
+  if (h->cfg.predictor != CTK_PRED_ODE && h->mlp.blob == nullptr) return fail(CTK_ESTATE, "network predictor without weights (ctk_set_mlp_weights / ctk_set_gru_weights)");
   memcpy(h->h_pin, s_host, sizeof(float) * 6);
   // the mirror carries one [H] array: MPPI's u_nom / RPGD's best sequence; any other state array takes the copy path below
   const bool state_in_mirror = state_dev != nullptr && h->cfg.rpgd_gradient_mode < 2 &&
@@ -1217,7 +1273,7 @@ extern "C" int ctk_step_device(ctk_handle* h, const float* s_dev, float* u_out_d
   if (!h->was_reset) return fail(CTK_ESTATE, "ctk_step before ctk_reset");
   REQ(h->cfg.optimizer != CTK_OPT_RPGD || h->xworld == 1, "RPGD is replicas-only (no cross-GPU exchange)");
   CU(cudaSetDevice(h->cfg.device));
-  if (h->cfg.predictor == CTK_PRED_MLP && h->mlp.blob == nullptr) return fail(CTK_ESTATE, "MLP predictor without weights");
+  if (h->cfg.predictor != CTK_PRED_ODE && h->mlp.blob == nullptr) return fail(CTK_ESTATE, "network predictor without weights (ctk_set_mlp_weights / ctk_set_gru_weights)");
   float* uo = u_out_dev ? u_out_dev : h->d_u_out;
   int rc = CTK_OK;
   h->tick++;
@@ -1250,6 +1306,76 @@ extern "C" int ctk_step_device_n(ctk_handle* h, const float* s_dev, size_t s_str
     h->chain_hint = false;
     if (rc != CTK_OK) return rc;
   }
+  return CTK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// several clients' ticks in one launch
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int ctk_step_batch(ctk_handle* h, const float* s_host, const int32_t* active, float* u_out_host) {
+  REQ(h && s_host && u_out_host, "null pointer");
+  REQ(h->cfg.optimizer == CTK_OPT_MPPI && h->ode_kernel && h->ode_ilp == 1 && !h->cfg.logging && h->xworld == 1,
+      "ctk_step_batch needs an unsharded MPPI handle on the one-rollout-per-thread ODE kernel, logging off");
+  if (!h->was_reset) return fail(CTK_ESTATE, "ctk_step_batch before ctk_reset");
+  CU(cudaSetDevice(h->cfg.device));
+  const int B = h->nclients, ns = h->cfg.num_states;
+  MppiBatch b{};
+  int n_active = 0;
+  for (int c = 0; c < B; ++c) {
+    b.active[c] = (active == nullptr || active[c] != 0) ? 1 : 0;
+    if (!b.active[c]) continue;
+    ++n_active;
+    b.tick[c] = ++h->client_tick[c];
+    for (int i = 0; i < ns && i < 8; ++i) b.s0[c][i] = s_host[(size_t)c * ns + i];
+  }
+  if (n_active == 0) return CTK_OK;
+  h->tick++;
+  NoiseSrc nsrc{};
+  int rcn = make_noise(h, STREAM_MPPI, h->n_ind, 0, (size_t)h->NG, &nsrc);
+  if (rcn != CTK_OK) return rcn;
+  REQ(nsrc.inj == nullptr, "ctk_step_batch draws its noise in-kernel (clear the injected-noise queue)");
+  MppiFuse fuse{};
+  make_fuse(h, 2, h->d_u_out, &fuse);
+  fuse.host = HostMirror{nullptr, 0};
+  fuse.handover = h->d_mbox + mbox_handover_offset(h->n_ind);
+  MppiOdeArgs a{};
+  a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
+  a.t0 = h->ode_t0;
+  a.trace = nullptr;
+  a.s0 = S0{}; a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = nsrc; a.k = h->ode_hot;
+  a.J = h->d_J; a.partials = h->d_partials; a.log_traj_soa = nullptr; a.log_Q_soa = nullptr;
+  a.fuse = fuse;
+  b.stride_unom = (size_t)h->H; b.stride_J = (size_t)h->N; b.stride_partials = h->partials_stride;
+  b.stride_record = (size_t)h->n_ind + 2; b.stride_mbox = h->mbox_stride;
+  h->launches++;
+  cudaError_t e;
+  {
+    KernelTimer kt(h);
+    e = launch_mppi_ode_batch(h->cost.kind, h->ode_period_t, h->ode_grid, B, h->ode_block, h->ode_smem, h->stream, a, b);
+  }
+  h->last_kernel = "mppi_ode_batch_kernel<" + std::to_string(h->cost.kind) + "," + std::to_string(h->ode_period_t) + ",1024> x " + std::to_string(n_active) + " clients";
+  if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("mppi_ode_batch_kernel: ") + cudaGetErrorString(e));
+  CU(cudaMemcpyAsync(h->h_batch ? h->h_batch : h->h_pin + 8, h->d_u_out, 2 * (size_t)B * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  const float* res = h->h_batch ? h->h_batch : h->h_pin + 8;
+  for (int c = 0; c < B; ++c) {
+    if (!b.active[c]) continue;
+    if (res[2 * c + 1] != 0.0f) return fail(CTK_ECUDA, "tick finish timed out: a block of client " + std::to_string(c) + "'s grid did not publish its softmin record within 2 s");
+    u_out_host[c] = res[2 * c];
+  }
+  return CTK_OK;
+}
+
+extern "C" int ctk_reset_client(ctk_handle* h, int client) {
+  REQ(h && client >= 0 && client < h->nclients, "no such client slot");
+  REQ(h->cfg.optimizer == CTK_OPT_MPPI, "multi-client handles are MPPI handles");
+  CU(cudaSetDevice(h->cfg.device));
+  const float mid = 0.5f * (h->cfg.action_low + h->cfg.action_high);
+  std::vector<float> tmp((size_t)h->H, mid);
+  CU(cudaMemcpyAsync(h->d_u_nom + (size_t)client * h->H, tmp.data(), sizeof(float) * h->H, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemsetAsync(h->d_u_prev + client, 0, sizeof(float), h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->client_tick[client] = 0;
   return CTK_OK;
 }
 
@@ -1351,7 +1477,7 @@ static int state_ptr(ctk_handle* h, int which, float** p, size_t* n, bool* tmajo
   *tmajor = false;
   const size_t H = h->H, N = h->N;
   switch (which) {
-    case CTK_STATE_U_NOM: *p = (h->cfg.optimizer == CTK_OPT_RPGD) ? h->d_unom_log : h->d_u_nom; *n = H; break;  // RPGD: Q[best] before the shift (:426)
+    case CTK_STATE_U_NOM: *p = (h->cfg.optimizer == CTK_OPT_RPGD) ? h->d_unom_log : h->d_u_nom; *n = H * (size_t)h->nclients; break;  // RPGD: Q[best] before the shift (:426)
     case CTK_STATE_CEM_MU: *p = h->d_mu; *n = H; break;
     case CTK_STATE_CEM_STD: *p = h->d_sd; *n = H; break;
     case CTK_STATE_RPGD_Q: *p = h->d_Q[h->cur]; *n = N * H; *tmajor = true; break;
@@ -1359,7 +1485,8 @@ static int state_ptr(ctk_handle* h, int which, float** p, size_t* n, bool* tmajo
     case CTK_STATE_RPGD_M: *p = h->d_m[h->cfg.rpgd_gradient_mode >= 2 ? 0 : h->cur]; *n = N * H; *tmajor = true; break;
     case CTK_STATE_RPGD_V: *p = h->d_v[h->cfg.rpgd_gradient_mode >= 2 ? 0 : h->cur]; *n = N * H; *tmajor = true; break;
     case CTK_STATE_RPGD_AGES: *p = h->d_ages[h->cur]; *n = N; break;
-    case CTK_STATE_U_PREV: *p = h->d_u_prev; *n = 1; break;
+    case CTK_STATE_U_PREV: *p = h->d_u_prev; *n = (size_t)h->nclients; break;
+    case CTK_STATE_RNN_H: *p = h->d_rnn_h; *n = 2 * (size_t)h->mlp.hidden; break;
     default: return fail(CTK_EINVAL, "unknown state id");
   }
   if (*p == nullptr) return fail(CTK_EINVAL, "state not present for this optimizer");
@@ -1572,7 +1699,7 @@ extern "C" int ctk_rollout_single(ctk_handle* h, const float* s_host, const floa
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_Q, Q_host, H * sizeof(float), cudaMemcpyHostToDevice, h->stream);
   if (e == cudaSuccess) {
     h->launches++;
-    e = launch_single_rollout(h->cfg.predictor == CTK_PRED_ODE ? 0 : 1, d_s, d_Q, H, h->d_kc, h->mlp, h->d_u_prev, d_traj,
+    e = launch_single_rollout(h->cfg.predictor == CTK_PRED_ODE ? 0 : (h->cfg.predictor == CTK_PRED_GRU ? 5 : 1), d_s, d_Q, H, h->d_kc, h->mlp, h->d_u_prev, d_traj,
                               d_sum, h->stream);
   }
   std::vector<float> tmp((size_t)(H + 1) * 6 + 1);

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(128) cem_rollout_kernel(const CemArgs a) {
   float omc = 1.0f - cosf(z.th);
   float u_last = a.u_prev[0];
   float jsum = 0.0f;
+  pred.begin_rollout();  // recurrent predictors: restore the saved hidden state
   for (int t0 = 0; t0 < a.H; t0 += 4) {
     float zz[4];
     noise4(a.noise, ng, (uint32_t)(t0 >> 2), zz);
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(kCemOdeTopkThreads) cem_ode_kernel(const CemOd
   }
 }
 
-__global__ void __launch_bounds__(TOPK_THREADS) cem_refit_kernel(const CemRefitArgs a) {
+static __global__ void __launch_bounds__(TOPK_THREADS) cem_refit_kernel(const CemRefitArgs a) {
   __shared__ uint64_t sh[TOPK_THREADS];
   __shared__ uint32_t sh_elite[TOPK_THREADS];
   pdl_wait();

@@ -307,6 +307,7 @@ __global__ void __launch_bounds__(Pred::kMaxThreads, Pred::kMinBlocks) mppi_roll
     if (active || Pred::kCooperative) {
       State z = z0;
       float omc = omc0, u_last = u_prev0, acc = 0.0f;
+      pred.begin_rollout();  // recurrent predictors: restore the saved hidden state
       const int nlog = active ? n : 0;
       // inducing-point draws arrive four at a time (one Philox block); zq is a rotating window, zq[0] = next draw
       float zq[4];
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(Pred::kMaxThreads, Pred::kMinBlocks) mppi_roll
                    sh_red, sh_z, (int)((a.stash ? (size_t)a.n_ind * rpb : 0) + (size_t)a.n_ind * rpb));
 }
 
-__global__ void __launch_bounds__(1024) mppi_combine_kernel(const float* __restrict__ in, int cnt, int n_ind,
+static __global__ void __launch_bounds__(1024) mppi_combine_kernel(const float* __restrict__ in, int cnt, int n_ind,
                                                            float neg_inv_lbd, float* __restrict__ record_out,
                                                            const MppiFinalize fin) {
   extern __shared__ float smem[];
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(1024) mppi_combine_kernel(const float* __restr
 
 // [R][C] -> [C][R] tiled transpose (logs are produced SoA/coalesced by the rollout kernels and handed out in the
 // reference's [N, H+1, ns] / [N, H, nu] layout)
-__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
+static __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {

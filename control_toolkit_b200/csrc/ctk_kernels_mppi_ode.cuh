@@ -63,8 +63,8 @@ __device__ __forceinline__ void ode_mppi_step(const MppiOdeArgs& a, const OdeHot
 }
 
 // INJ: injected-noise mode possible (verification); the production instantiations compile that branch out.
-template <int KIND, bool LOG, int PERIOD, int ILP, int MAXT, bool INJ>
-__global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
+template <int KIND, bool LOG, int PERIOD, int ILP, bool INJ>
+__device__ __forceinline__ void mppi_ode_body(const MppiOdeArgs& a) {
   extern __shared__ float smem[];
   const int T_ = blockDim.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = T_ >> 5;
   const int period = PERIOD > 0 ? PERIOD : a.period;
@@ -268,6 +268,45 @@ __global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
   mppi_tick_finish(a.fuse, brec, a.partials, a.n_ind, a.H, period, k.stdev, k.lo, k.hi, k.neg_inv_lbd, sh_unom, sh_w, brec + P + 1, sh_red, sh_z,
                    (int)((size_t)max(a.n_ind * ILP, 2) * T_ + (size_t)a.n_ind * T_));
   trace(5);
+}
+
+template <int KIND, bool LOG, int PERIOD, int ILP, int MAXT, bool INJ>
+__global__ void __launch_bounds__(MAXT) mppi_ode_kernel(const MppiOdeArgs a) {
+  mppi_ode_body<KIND, LOG, PERIOD, ILP, INJ>(a);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Several clients' ticks in ONE launch (the serving edge batches the states of several remote clients; reference
+// controller_server/controller_server.py:55-86 serves one ctrl.step per request).  gridDim.y = client slot; every client has its
+// own warm-start state (u_nom, u_prev), cost buffer, mailbox and Philox tick counter, laid out with fixed strides behind the
+// pointers of client 0; the x-dimension of the grid is one client's ordinary K1 geometry, so a client's tick is bit-identical to
+// the tick a handle of its own would run.  The state of client c travels inside the kernel parameters.  Inactive slots return at once.
+// ----------------------------------------------------------------------------------------------------------------
+template <int KIND, int PERIOD, int MAXT>
+__global__ void __launch_bounds__(MAXT) mppi_ode_batch_kernel(const MppiOdeArgs a0, const MppiBatch b) {
+  const int c = blockIdx.y;
+  if (!b.active[c]) return;
+  MppiOdeArgs a = a0;
+  a.s0.p = nullptr;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) a.s0.v[i] = b.s0[c][i];
+  a.noise.tick = b.tick[c];
+  a.u_nom += (size_t)c * b.stride_unom;
+  a.u_prev += c;
+  a.J += (size_t)c * b.stride_J;
+  a.partials += (size_t)c * b.stride_partials;
+  a.trace = nullptr;
+  a.fuse.record_out += (size_t)c * b.stride_record;
+  a.fuse.mbox_local += (size_t)c * b.stride_mbox;
+  a.fuse.mbox_peer[0] = a.fuse.mbox_local;
+  a.fuse.handover += (size_t)c * b.stride_mbox;
+  a.fuse.trace = nullptr;
+  a.fuse.chained = 0;
+  a.fuse.u_nom += (size_t)c * b.stride_unom;
+  a.fuse.u_prev += c;
+  a.fuse.u_out += 2 * c;
+  a.fuse.host.p = nullptr;
+  mppi_ode_body<KIND, false, PERIOD, 1, false>(a);
 }
 
 }  // namespace ctk

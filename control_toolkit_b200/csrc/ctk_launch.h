@@ -34,12 +34,21 @@ int mppi_max_block_threads(int pred);
 cudaError_t launch_mppi_ode(int kind, bool log, int period_t, int ilp, int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a,
                             const char** name = nullptr);
 int mppi_ode_max_block(int ilp);
+// several clients' ticks in one launch: grid (grid, nclients); Philox noise, logging off, ILP 1 (ctk_batch.cu)
+cudaError_t launch_mppi_ode_batch(int kind, int period_t, int grid, int nclients, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a,
+                                  const MppiBatch& b);
 size_t mppi_ode_smem_bytes(int H, int period, int n_ind, int ilp, int block);
 cudaError_t launch_mppi_combine(const float* in, int cnt, int n_ind, float neg_inv_lbd, float* record_out,
                                 const MppiFinalize& fin, cudaStream_t st);
 cudaError_t launch_exchange_barrier(const MppiFuse& f, size_t bar_off, cudaStream_t st);
 cudaError_t launch_transpose(const float* in, float* out, int R, int C, cudaStream_t st);
 size_t mppi_pred_smem_floats(int pred, const MlpDev& m);
+// recurrent predictor (ctk_gru.cu)
+cudaError_t launch_mppi_rollout_gru(int kind, bool log, int nblocks, int block, size_t smem, cudaStream_t st, const MppiArgs& a);
+cudaError_t launch_cem_rollout_gru(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemArgs& a);
+cudaError_t launch_single_rollout_gru(const float* s0, const float* Q, int H, const DevConsts* kc, const MlpDev& mlp, const float* u_prev,
+                                      float* traj, float* summed, cudaStream_t st);
+cudaError_t launch_gru_update(const S0& s0, const float* u_nom, const MlpDev& mlp, float* rnn_h, cudaStream_t st);
 
 cudaError_t launch_cem_rollout(int pred, int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemArgs& a);
 cudaError_t launch_cem_ode(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemOdeArgs& a);

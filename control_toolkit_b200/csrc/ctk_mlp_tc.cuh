@@ -113,6 +113,7 @@ struct MlpTcPred {
   __device__ __forceinline__ void substep(State& z, float u, float& omc) { step(z, u, omc); }
   __device__ __forceinline__ bool single_substep() const { return false; }
   __device__ __forceinline__ void use_uniform(const HotUK&) {}
+  __device__ __forceinline__ void begin_rollout() {}
 
   // tanh(x) = 1 - 2 / (exp(2x) + 1) for either sign (x -> -inf: e -> 0, t -> -1; x -> +inf: e -> inf, r -> 0, t -> 1):
   // FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA.  Absolute error <= ~3e-7 (the two MUFU approximations), the same bound the
@@ -364,6 +365,7 @@ struct MlpTcFastPredT {
   __device__ __forceinline__ void substep(State& z, float u, float& omc) { step(z, u, omc); }
   __device__ __forceinline__ bool single_substep() const { return false; }
   __device__ __forceinline__ void use_uniform(const HotUK&) {}
+  __device__ __forceinline__ void begin_rollout() {}
 
   static __device__ __forceinline__ float act(float x) {
     if (APPROX) {

@@ -25,13 +25,19 @@ cudaError_t launch_mppi_rollout(int pred, int kind, bool log, int nblocks, int b
   if (pred == 2) return launch_mppi_p<MlpTcPred>(kind, log, nblocks, block, smem, st, a);
   if (pred == 3) return launch_mppi_p<MlpTcBf16Pred>(kind, log, nblocks, block, smem, st, a);
   if (pred == 4) return launch_mppi_p<MlpTcFastPred>(kind, log, nblocks, block, smem, st, a);
+  if (pred == 5) return launch_mppi_rollout_gru(kind, log, nblocks, block, smem, st, a);  // ctk_gru.cu
   return pred == 0 ? launch_mppi_p<OdePred>(kind, log, nblocks, block, smem, st, a)
                    : launch_mppi_p<MlpSimtPred>(kind, log, nblocks, block, smem, st, a);
 }
 // pred: 0 ODE, 1 MLP on the FP32 pipe, 2 MLP with layer 2 on the tensor cores (tcgen05, bf16 x 3 split: fp32-level), 3 / 4 the opt-in
 // single-bf16-product engines (3: exact tanh, 4: MUFU.TANH)
-int mppi_max_block_threads(int pred) { return pred == 0 ? OdePred::kMaxThreads : (pred >= 2 ? MlpTcPred::kMaxThreads : MlpSimtPred::kMaxThreads); }
+// 5: the recurrent (GRU) predictor on the FP32 pipe
+int mppi_max_block_threads(int pred) {
+  if (pred == 5) return GruSimtPred::kMaxThreads;
+  return pred == 0 ? OdePred::kMaxThreads : (pred >= 2 ? MlpTcPred::kMaxThreads : MlpSimtPred::kMaxThreads);
+}
 size_t mppi_pred_smem_floats(int pred, const MlpDev& m) {
+  if (pred == 5) return GruSimtPred::smem_floats(m);
   return pred == 0 ? 0 : (pred == 2 ? MlpTcPred::smem_floats(m) : (pred >= 3 ? MlpTcBf16Pred::smem_floats(m) : MlpSimtPred::smem_floats(m)));
 }
 
@@ -129,6 +135,7 @@ __global__ void single_rollout_kernel(const float* s0, const float* Q, int H, co
   State z;
   z.th = s0[0]; z.om = s0[1]; z.c = s0[2]; z.s = s0[3]; z.x = s0[4]; z.v = s0[5];
   float omc = 1.0f - cosf(z.th), ul = u_prev[0], sum = 0.0f;
+  pred.begin_rollout();
   for (int t = 0; t <= H; ++t) {
     float* p = traj + t * 6;
     p[0] = z.th; p[1] = z.om; p[2] = z.c; p[3] = z.s; p[4] = z.x; p[5] = z.v;
@@ -146,6 +153,7 @@ cudaError_t launch_single_rollout(int pred, const float* s0, const float* Q, int
     single_rollout_kernel<OdePred><<<1, 32, 0, st>>>(s0, Q, H, kc, mlp, u_prev, traj, summed);
     return cudaGetLastError();
   }
+  if (pred == 5) return launch_single_rollout_gru(s0, Q, H, kc, mlp, u_prev, traj, summed, st);  // ctk_gru.cu
   const size_t smem = sizeof(float) * MlpSimtPred::smem_floats(mlp);
   auto k = single_rollout_kernel<MlpSimtPred>;
   if (smem > 48 * 1024) {

@@ -165,8 +165,78 @@ def register_mlp(predictor_specification: str, spec: MLPSpec) -> None:
     MLP_REGISTRY[str(predictor_specification)] = spec
 
 
+@dataclass
+class GRUSpec:
+    """Recurrent autoregressive predictor 6 -> GRU(hidden) -> GRU(hidden) -> Dense 5 ('GRU-6IN-32H1-32H2-5OUT-0').  Row-major
+    [in, 3*hidden] matrices, gate order [r, z, n] (include/ctk_b200.h ctk_gru_weights).  The hidden state is SAVED on the device:
+    every rollout starts from it and each MPPI tick advances it with (measured state, applied control) -- the reference's
+    predictor.update hook (reference Optimizers/optimizer_mppi.py:192,195-197) -- inside the tick's kernel sequence."""
+    Wi1: np.ndarray
+    Wh1: np.ndarray
+    bi1: np.ndarray
+    bh1: np.ndarray
+    Wi2: np.ndarray
+    Wh2: np.ndarray
+    bi2: np.ndarray
+    bh2: np.ndarray
+    W3: np.ndarray
+    b3: np.ndarray
+    _KEYS = ("Wi1", "Wh1", "bi1", "bh1", "Wi2", "Wh2", "bi2", "bh2", "W3", "b3")
+
+    def __post_init__(self):
+        for k in self._KEYS:
+            setattr(self, k, np.ascontiguousarray(getattr(self, k), dtype=np.float32))
+        h = self.Wh1.shape[0]
+        shapes = dict(Wi1=(6, 3 * h), Wh1=(h, 3 * h), bi1=(3 * h,), bh1=(3 * h,), Wi2=(h, 3 * h), Wh2=(h, 3 * h), bi2=(3 * h,),
+                      bh2=(3 * h,), W3=(h, 5), b3=(5,))
+        for k, shp in shapes.items():
+            if getattr(self, k).shape != shp:
+                raise ValueError(f"GRU predictor: {k} must have shape {shp}, got {getattr(self, k).shape}")
+        if h % 8 or not 8 <= h <= 32:
+            raise ValueError("GRU hidden width must be a multiple of 8 in [8, 32]")
+
+    @property
+    def hidden(self) -> int:
+        return int(self.Wh1.shape[0])
+
+    @staticmethod
+    def random_init(seed: int = 3, hidden: int = 32) -> "GRUSpec":
+        """weights N(0, 1/fan_in), biases N(0, 0.1^2), numpy default_rng(seed); the position read-out is scaled by 0.08 (the same
+        draws, in the same order, as oracle/spec.py GRUWeights.random_init -- written independently, compared in tests)."""
+        rng = np.random.default_rng(seed)
+
+        def w(i, o):
+            return (rng.standard_normal((i, o)) / math.sqrt(i)).astype(np.float32)
+
+        def b(o):
+            return (0.1 * rng.standard_normal(o)).astype(np.float32)
+
+        h = hidden
+        Wi1, Wh1, bi1, bh1 = w(6, 3 * h), w(h, 3 * h), b(3 * h), b(3 * h)
+        Wi2, Wh2, bi2, bh2 = w(h, 3 * h), w(h, 3 * h), b(3 * h), b(3 * h)
+        W3, b3 = w(h, 5), b(5)
+        W3[:, 3] *= np.float32(0.08)
+        b3[3] *= np.float32(0.08)
+        return GRUSpec(Wi1, Wh1, bi1, bh1, Wi2, Wh2, bi2, bh2, W3, b3)
+
+    def to_c(self) -> L.ctk_gru_weights:
+        w = L.ctk_gru_weights()
+        w.hidden = self.hidden
+        for k in self._KEYS:
+            setattr(w, k, L.fptr(getattr(self, k)))
+        return w
+
+
+GRU_REGISTRY: dict[str, GRUSpec] = {}
+
+
+def register_gru(predictor_specification: str, spec: GRUSpec) -> None:
+    """Make a recurrent predictor available under a predictor_specification name (e.g. 'GRU-6IN-32H1-32H2-5OUT-0')."""
+    GRU_REGISTRY[str(predictor_specification)] = spec
+
+
 def resolve_predictor(environment_name: str, predictor_specification: str):
-    """-> (PRED_ODE, CartPoleODE) or (PRED_MLP, MLPSpec).  ValueError if nothing is registered."""
+    """-> (PRED_ODE, CartPoleODE), (PRED_MLP, MLPSpec) or (PRED_GRU, GRUSpec).  ValueError if nothing is registered."""
     name = str(predictor_specification)
     if name.startswith("ODE"):
         if environment_name not in ODE_REGISTRY:
@@ -174,5 +244,7 @@ def resolve_predictor(environment_name: str, predictor_specification: str):
         return L.PRED_ODE, ODE_REGISTRY[environment_name]
     if name in MLP_REGISTRY:
         return L.PRED_MLP, MLP_REGISTRY[name]
+    if name in GRU_REGISTRY:
+        return L.PRED_GRU, GRU_REGISTRY[name]
     raise ValueError(f"predictor_specification {name!r} is neither 'ODE' nor a registered network "
-                     f"(register_mlp); registered networks: {sorted(MLP_REGISTRY)}")
+                     f"(register_mlp / register_gru); registered networks: {sorted(MLP_REGISTRY) + sorted(GRU_REGISTRY)}")

@@ -47,7 +47,10 @@ class PredictorWrapper:
                            "there is no host predict_core (and no CPU fallback)")
 
     def update(self, s=None, Q0=None):
-        pass  # RNN-state hook of the reference (optimizer_mppi.py:195-197); stateless predictors ignore it
+        # RNN-state hook of the reference (optimizer_mppi.py:195-197).  Stateless predictors ignore it; for a recurrent predictor
+        # (GRUSpec) the saved hidden state lives in the C handle and the hook runs on the device at the end of every MPPI tick
+        # (gru_update_kernel), so there is nothing to do on the host either.
+        pass
 
     def copy(self):
         return PredictorWrapper()

@@ -33,7 +33,7 @@ extern "C" {
 
 /* ---- enums -------------------------------------------------------------------------------------------------- */
 enum { CTK_OPT_MPPI = 0, CTK_OPT_CEM = 1, CTK_OPT_RPGD = 2 };            /* optimizer_mppi / optimizer_cem_tf / optimizer_rpgd */
-enum { CTK_PRED_ODE = 0, CTK_PRED_MLP = 1 };                             /* predictor_specification "ODE" / "Dense-..."        */
+enum { CTK_PRED_ODE = 0, CTK_PRED_MLP = 1, CTK_PRED_GRU = 2 };           /* predictor_specification "ODE" / "Dense-..." / "GRU-..." */
 enum { CTK_COST_DEFAULT = 0, CTK_COST_QUADRATIC_BOUNDARY_GRAD = 1 };     /* cost_function_specification                         */
 enum { CTK_DIST_NORMAL = 0, CTK_DIST_UNIFORM = 1 };                      /* RPGD SAMPLING_DISTRIBUTION                          */
 enum { CTK_ADAM_KERAS = 0, CTK_ADAM_TORCH = 1 };                         /* reference optimizer_rpgd.py:34-43 vs :56-82         */
@@ -45,14 +45,16 @@ enum { CTK_MLP_SIMT = 0, CTK_MLP_TCGEN05 = 1, CTK_MLP_TCGEN05_BF16 = 2, CTK_MLP_
 
 /* which = state arrays (get/set).  Layouts are the reference's: [1,H,nu] or [N,H,nu] row-major.                 */
 enum {
-  CTK_STATE_U_NOM = 0,      /* MPPI u_nom [H]            (optimizer_mppi.py:227-231)                              */
+  CTK_STATE_U_NOM = 0,      /* MPPI u_nom [H] ([num_clients][H] for a multi-client handle) (optimizer_mppi.py:227-231) */
   CTK_STATE_CEM_MU = 1,     /* CEM dist_mue [H]          (optimizer_cem_tf.py:114)                                */
   CTK_STATE_CEM_STD = 2,    /* CEM stdev [H]             (optimizer_cem_tf.py:115)                                */
   CTK_STATE_RPGD_Q = 3,     /* RPGD Q_tf [N,H]           (optimizer_rpgd.py:540-544)                              */
   CTK_STATE_RPGD_M = 4,     /* Adam m [N,H]              (optimizer_rpgd.py:84-131)                               */
   CTK_STATE_RPGD_V = 5,     /* Adam v [N,H]                                                                       */
   CTK_STATE_RPGD_AGES = 6,  /* trajectory_ages [N]       (optimizer_rpgd.py:548)                                  */
-  CTK_STATE_U_PREV = 7      /* self.u, the previous_input of the cost [1] (Optimizers/__init__.py:35)             */
+  CTK_STATE_U_PREV = 7,     /* self.u, the previous_input of the cost [1] (Optimizers/__init__.py:35)             */
+  CTK_STATE_RNN_H = 8       /* saved hidden state of the recurrent predictor [2 * hidden] (layer 1 | layer 2): what every rollout
+                               starts from and predictor.update advances (optimizer_mppi.py:195-197)                  */
 };
 /* which = integer counters */
 enum { CTK_COUNTER_COUNT = 0,      /* optimizer.count   (optimizer_cem_tf.py:116, optimizer_rpgd.py:545)          */
@@ -86,6 +88,13 @@ typedef struct ctk_mlp_weights {  /* Dense 6 -> hidden tanh -> hidden tanh -> 5 
   int32_t hidden;
   const float *W1, *b1, *W2, *b2, *W3, *b3;
 } ctk_mlp_weights;
+
+typedef struct ctk_gru_weights {  /* 6 -> GRU(hidden) -> GRU(hidden) -> Dense 5; row-major [in, 3*hidden], gate order [r, z, n];
+                                     r = sigmoid(gi_r + gh_r), z = sigmoid(gi_z + gh_z), n = tanh(gi_n + r * gh_n), h' = (1-z) n + z h
+                                     with gi = x Wi + bi, gh = h Wh + bh (torch.nn.GRU / Keras reset_after cell); host ptrs            */
+  int32_t hidden;                 /* multiple of 8, <= 32                                                        */
+  const float *Wi1, *Wh1, *bi1, *bh1, *Wi2, *Wh2, *bi2, *bh2, *W3, *b3;
+} ctk_gru_weights;
 
 typedef struct ctk_config {
   int32_t abi_version;            /* = CTK_ABI_VERSION                                                           */
@@ -134,7 +143,10 @@ typedef struct ctk_config {
                                      (reference optimizer_cem_grad_bharadhwaj_tf.py:93-178; moments persist per row).
                                      Modes 2/3 read the cem_* fields (outer_it, best_k, initial_action_stdev, stdev_min, warmup*)
                                      and rpgd_learning_rate / gradmax_clip / beta / epsilon; period must be 1                  */
-  int32_t reserved[5];
+  int32_t num_clients;            /* 0 / 1: one client (the reference's controller).  2 .. 16: the handle carries that many independent
+                                     MPPI clients -- own warm-start sequence, previous input, costs and Philox tick counter each -- whose
+                                     ticks ctk_step_batch runs in ONE launch (MPPI + ODE predictor, logging off, unsharded) */
+  int32_t reserved[4];
 } ctk_config;
 
 typedef struct ctk_handle ctk_handle;
@@ -150,6 +162,10 @@ int ctk_reset(ctk_handle *h);
 int ctk_set_cost_params(ctk_handle *h, const ctk_cost_params *cost);
 int ctk_set_ode_params(ctk_handle *h, const ctk_ode_params *ode);
 int ctk_set_mlp_weights(ctk_handle *h, const ctk_mlp_weights *w);
+/* recurrent predictor (CTK_PRED_GRU; MPPI and CEM): weights; the saved hidden state is zeroed.  Every MPPI tick ends with the
+   reference's predictor.update(s, Q0 = new u_nom[0]) (optimizer_mppi.py:192,195-197) as one small kernel on the handle's stream;
+   CEM never advances the state (optimizer_cem_tf.py has no such call).  CTK_STATE_RNN_H reads / writes the saved state.        */
+int ctk_set_gru_weights(ctk_handle *h, const ctk_gru_weights *w);
 /* run subsequent work on this cudaStream_t (0 = legacy default stream)                                          */
 int ctk_set_stream(ctk_handle *h, void *cuda_stream);
 
@@ -195,6 +211,16 @@ int ctk_step_device(ctk_handle *h, const float *s_dev, float *u_out_dev);
    be NULL): one call enqueues the whole chain, consecutive ticks overlap through programmatic dependent launch -- the next tick's
    in-kernel noise generation runs underneath the previous tick's finish / exchange / launch gap.                          */
 int ctk_step_device_n(ctk_handle *h, const float *s_dev, size_t s_stride, float *u_out_dev, size_t u_stride, int n);
+
+/* ---- multi-client batching behind the serving edge ------------------------------------------------ */
+/* replaces num_clients separate optimizer.step(s, time) calls of num_clients controllers (reference
+   controller_server/controller_server.py:55-86 serves one ctrl.step per request): s_host [num_clients][num_states]; active
+   [num_clients] (NULL: all) selects the clients that tick; u_out_host [num_clients] (entries of inactive clients untouched).  One
+   kernel launch (grid.y = client); every client's tick is bit-identical to the tick of a single-client handle with the same
+   configuration, seed and tick count.  Cost / ODE parameters are shared by the clients of a handle.                          */
+int ctk_step_batch(ctk_handle *h, const float *s_host, const int32_t *active, float *u_out_host);
+/* a new client takes over slot `client`: warm-start sequence to mid-range, previous input and tick counter to zero              */
+int ctk_reset_client(ctk_handle *h, int client);
 
 /* ---- fused cross-GPU exchange (MPPI) --------------------------------------------------------------- */
 /* Each shard owns a mailbox in its HBM; peers store their softmin record (n_ind + 2 values, each packed with the tick's

@@ -105,11 +105,16 @@ CASES = {
                          _c(MPPI_BASE, num_rollouts=256, mpc_horizon=100), 2, False),
     "mppi_mlp_h50_n64": ("mppi", "Dense-6IN-128H1-128H2-5OUT-0", "default",
                          _c(MPPI_BASE, num_rollouts=64, mpc_horizon=50), 2, True),
+    # recurrent predictor (two GRU layers + read-out) with the predictor.update state hook the reference calls every
+    # MPPI tick (optimizer_mppi.py:192,195-197); CEM never calls the hook (optimizer_cem_tf.py), its rollouts start from the zero state
+    "mppi_gru_n256": ("mppi", "GRU-6IN-32H1-32H2-5OUT-0", "default", _c(MPPI_BASE, num_rollouts=256), 4, True),
+    "cem_gru_n256_k16": ("cem-tf", "GRU-6IN-32H1-32H2-5OUT-0", "default", _c(CEM_BASE, num_rollouts=256, cem_best_k=16, mpc_horizon=30), 2, False),
 }
 RESET_BEFORE_TICK = {"mppi_reset_mid_n64": 2, "rpgd_reset_mid_n32": 3, "cem_reset_mid_n128": 2}  # controller_reset() before that tick
 NOISE_SEED = 1
 STATE_SEED = 0
 MLP_SEED = 2
+GRU_SEED = 3
 
 
 def run_reference_case(name: str) -> dict:
@@ -132,6 +137,8 @@ def run_reference_case(name: str) -> dict:
 
     if pred_spec.startswith("Dense"):
         pw.MLP_REGISTRY[pred_spec] = spec.MLPWeights.random_init(MLP_SEED)
+    if pred_spec.startswith("GRU"):
+        pw.GRU_REGISTRY[pred_spec] = spec.GRUWeights.random_init(GRU_SEED)
 
     from Control_Toolkit.Controllers import controller_mpc as cm  # noqa: the reference module
     cm.config_optimizers[opt_name] = copy.deepcopy(cfg)  # optimizer kwargs (module-global dict loaded at import)
@@ -166,7 +173,7 @@ def run_reference_case(name: str) -> dict:
     states = spec.synthetic_states(ticks, STATE_SEED)
     out = {"config": np.array(json.dumps(dict(case=name, optimizer=opt_name, predictor=pred_spec, cost=cost_name,
                                               cfg=cfg, ticks=ticks, noise_seed=NOISE_SEED, state_seed=STATE_SEED,
-                                              mlp_seed=MLP_SEED, reset_before_tick=RESET_BEFORE_TICK.get(name, -1)))),
+                                              mlp_seed=MLP_SEED, gru_seed=GRU_SEED, reset_before_tick=RESET_BEFORE_TICK.get(name, -1)))),
            "states": states}
     if opt_name in ("rpgd", "gradient-tf"):
         out["Q_init"] = opt.Q_tf.numpy().copy()
@@ -180,6 +187,9 @@ def run_reference_case(name: str) -> dict:
         if opt_name == "mppi":
             out[f"u_nom_{t}"] = opt.u_nom.numpy().copy()
             out[f"J_{t}"] = np.asarray(lv["J_logged"]).copy()
+            if pred_spec.startswith("GRU"):  # the saved hidden state after this tick's predictor.update
+                g = opt.predictor.predictor
+                out[f"rnn_h_{t}"] = np.concatenate([g.h1.numpy().ravel(), g.h2.numpy().ravel()]).astype(np.float32)
         elif opt_name == "cem-tf":
             out[f"dist_mue_{t}"] = opt.dist_mue.numpy().copy()
             out[f"stdev_{t}"] = opt.stdev.numpy().copy()

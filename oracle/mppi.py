@@ -83,6 +83,8 @@ class MPPIOracle:
         u_nom = torch.minimum(torch.maximum(u_nom + b, self.low), self.high)  # :190
         self.u_nom = u_nom
         self.u = u_nom[0, 0, :].squeeze().numpy().copy()  # :191,212
+        if hasattr(self.predictor, "update"):  # :192,195-197 RNN-state hook: the saved hidden state advances with (s, new u_nom[0])
+            self.predictor.update(s=s, Q0=u_nom[:, :1, :].repeat(self.N, 1, 1))
         self.last = dict(J=S.numpy(), Q=u_run.numpy(), rollouts=rollout.numpy(), delta_u=delta_u.numpy())
         return self.u
 

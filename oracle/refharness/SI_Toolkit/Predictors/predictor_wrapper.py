@@ -8,11 +8,13 @@ computation_library, variable_parameters, predictor_specification[, horizon])``
 
 The arithmetic is the build's pinned spec (oracle/spec.py).  ``predictor_specification``:
 ``"ODE"`` -> CartPole Euler ODE;  anything starting with ``"Dense"``/``"MLP"`` -> the MLP registered in
-``MLP_REGISTRY[predictor_specification]`` (an ``oracle.spec.MLPWeights``).
+``MLP_REGISTRY[predictor_specification]`` (an ``oracle.spec.MLPWeights``);  ``"GRU..."`` -> the stateful recurrent predictor
+registered in ``GRU_REGISTRY`` (an ``oracle.spec.GRUWeights``), whose ``update`` advances the saved hidden state.
 """
 from oracle import spec as _spec
 
 MLP_REGISTRY = {}
+GRU_REGISTRY = {}
 ODE_PARAMS = {"intermediate_steps": 1}
 
 
@@ -34,6 +36,8 @@ class PredictorWrapper:
             self.predictor = _spec.ODEPredictor(_spec.CartPoleParams(dt=dt, intermediate_steps=ODE_PARAMS["intermediate_steps"]))
         elif name.startswith(("Dense", "MLP")):
             self.predictor = _spec.MLPPredictor(MLP_REGISTRY[name])
+        elif name.startswith("GRU"):
+            self.predictor = _spec.GRUPredictor(GRU_REGISTRY[name])
         else:
             raise ValueError(f"unknown predictor_specification {predictor_specification}")
 
@@ -44,7 +48,9 @@ class PredictorWrapper:
         return self.predict_core(s, Q)
 
     def update(self, s=None, Q0=None):
-        pass  # RNN-state hook (reference optimizer_mppi.py:195-197); stateless predictors ignore it
+        # RNN-state hook (reference optimizer_mppi.py:195-197); stateless predictors ignore it
+        if hasattr(self.predictor, "update"):
+            self.predictor.update(s=s, Q0=Q0)
 
     def copy(self):
         return PredictorWrapper()

@@ -219,6 +219,110 @@ class MLPPredictor:
 
 
 # ----------------------------------------------------------------------------------------------
+# GRU autoregressive predictor (recurrent predictors + the predictor.update state hook,
+# reference Optimizers/optimizer_mppi.py:195-197)
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class GRUWeights:
+    """Two stacked GRU layers of width ``hidden`` and a linear read-out: 6 -> GRU(hidden) -> GRU(hidden) -> Dense 5
+    (naming pattern 'GRU-6IN-32H1-32H2-5OUT-0', cf. reference Control_Toolkit_ASF_Template/config_controllers.yml:8).
+    Row-major [in, 3*hidden] matrices (g = x @ W + b), gate order [r, z, n]; per layer
+        r = sigmoid(gi_r + gh_r)   z = sigmoid(gi_z + gh_z)   n = tanh(gi_n + r * gh_n)   h' = (1 - z) * n + z * h
+    with gi = x @ Wi + bi and gh = h @ Wh + bh (the torch.nn.GRU / Keras reset_after=True cell)."""
+    Wi1: np.ndarray
+    Wh1: np.ndarray
+    bi1: np.ndarray
+    bh1: np.ndarray
+    Wi2: np.ndarray
+    Wh2: np.ndarray
+    bi2: np.ndarray
+    bh2: np.ndarray
+    W3: np.ndarray
+    b3: np.ndarray
+
+    @property
+    def hidden(self) -> int:
+        return int(self.Wh1.shape[0])
+
+    @staticmethod
+    def random_init(seed: int = 3, hidden: int = 32) -> "GRUWeights":
+        """weights N(0, 1/fan_in), biases N(0, 0.1^2) (non-zero so that every bias term is exercised), default_rng(seed); the
+        read-out column / bias of the position output are scaled by 0.08 so that the predicted cart mostly stays on the track (0.198 m)
+        and the softmin / elite selection see a spread of ordinary costs instead of one rollout that escapes the 1e9 barrier term."""
+        rng = np.random.default_rng(seed)
+
+        def w(i, o):
+            return (rng.standard_normal((i, o)) / math.sqrt(i)).astype(np.float32)
+
+        def b(o):
+            return (0.1 * rng.standard_normal(o)).astype(np.float32)
+
+        h = hidden
+        g = GRUWeights(Wi1=w(6, 3 * h), Wh1=w(h, 3 * h), bi1=b(3 * h), bh1=b(3 * h),
+                       Wi2=w(h, 3 * h), Wh2=w(h, 3 * h), bi2=b(3 * h), bh2=b(3 * h), W3=w(h, 5), b3=b(5))
+        g.W3[:, 3] *= np.float32(0.08)
+        g.b3[3] *= np.float32(0.08)
+        return g
+
+
+class GRUPredictor:
+    """net input [Q, angleD, angle_cos, angle_sin, position, positionD] (normalisation = identity) -> next
+    [angleD, angle_cos, angle_sin, position, positionD]; angle = atan2(sin, cos).
+
+    Stateful like SI_Toolkit's autoregressive RNN predictor: ``predict_core`` starts every rollout from the SAVED hidden state and
+    leaves it untouched; ``update(s, Q0)`` advances the saved state by one step with the measured state and the control that is
+    about to be applied (the hook the reference calls at optimizer_mppi.py:192,195-197)."""
+
+    num_states = NUM_STATES
+    num_control_inputs = NUM_CONTROLS
+
+    def __init__(self, weights: GRUWeights, dtype=torch.float32):
+        self.w = weights
+        self.dtype = dtype
+        self.t = {k: torch.from_numpy(np.ascontiguousarray(getattr(weights, k))).to(dtype)
+                  for k in ("Wi1", "Wh1", "bi1", "bh1", "Wi2", "Wh2", "bi2", "bh2", "W3", "b3")}
+        self.hid = weights.hidden
+        self.reset_state()
+
+    def reset_state(self):
+        self.h1 = torch.zeros(1, self.hid, dtype=self.dtype)
+        self.h2 = torch.zeros(1, self.hid, dtype=self.dtype)
+
+    def _cell(self, x, h, Wi, Wh, bi, bh):
+        H = self.hid
+        gi = x @ Wi + bi
+        gh = h @ Wh + bh
+        r = torch.sigmoid(gi[:, :H] + gh[:, :H])
+        z = torch.sigmoid(gi[:, H:2 * H] + gh[:, H:2 * H])
+        n = torch.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:])
+        return (1.0 - z) * n + z * h
+
+    def _net(self, s, Q, h1, h2):
+        t = self.t
+        x = torch.cat([Q, s[:, 1:]], dim=1)  # [N,6]
+        h1 = self._cell(x, h1, t["Wi1"], t["Wh1"], t["bi1"], t["bh1"])
+        h2 = self._cell(h1, h2, t["Wi2"], t["Wh2"], t["bi2"], t["bh2"])
+        y = h2 @ t["W3"] + t["b3"]  # [N,5]
+        angle = torch.atan2(y[:, 2], y[:, 1])
+        return torch.cat([angle[:, None], y], dim=1), h1, h2
+
+    def predict_core(self, s: torch.Tensor, Q: torch.Tensor) -> torch.Tensor:
+        n = s.shape[0]
+        h1, h2 = self.h1.repeat(n, 1), self.h2.repeat(n, 1)
+        out = [s]
+        for t in range(Q.shape[1]):
+            s, h1, h2 = self._net(s, Q[:, t, :], h1, h2)
+            out.append(s)
+        return torch.stack(out, dim=1)
+
+    def update(self, s=None, Q0=None):
+        """s [N,6] (rows identical), Q0 [N,1,1] (rows identical): one step from the saved hidden state, saved back."""
+        s = torch.as_tensor(s).to(self.dtype).reshape(-1, NUM_STATES)[:1]
+        q = torch.as_tensor(Q0).to(self.dtype).reshape(-1, 1)[:1]
+        _, self.h1, self.h2 = self._net(s, q, self.h1, self.h2)
+
+
+# ----------------------------------------------------------------------------------------------
 # Cost functions
 # ----------------------------------------------------------------------------------------------
 def _distance_difference_cost(position, c):

@@ -19,6 +19,8 @@ def make_controller(meta, logging=True, rng="replay", shard=None, **optimizer_ov
 
     if meta["predictor"].startswith("Dense"):
         ctk.register_mlp(meta["predictor"], ctk.MLPSpec.random_init(meta["mlp_seed"]))
+    if meta["predictor"].startswith("GRU"):
+        ctk.register_gru(meta["predictor"], ctk.GRUSpec.random_init(meta["gru_seed"]))
     cfg = dict(meta["cfg"])
     cfg.update(optimizer_over)
     if shard is not None:

@@ -29,6 +29,8 @@ def load_golden(name):
 def make_predictor(meta):
     if meta["predictor"].startswith("ODE"):
         return spec.ODEPredictor(spec.CartPoleParams(dt=meta["cfg"]["mpc_timestep"]))
+    if meta["predictor"].startswith("GRU"):
+        return spec.GRUPredictor(spec.GRUWeights.random_init(meta["gru_seed"]))
     return spec.MLPPredictor(spec.MLPWeights.random_init(meta["mlp_seed"]))
 
 
@@ -94,6 +96,8 @@ def fp32_noise_floor(name, ticks=None, **over):
     o32, o64 = make_oracle(meta, **over), make_oracle(meta, dtype=torch.float64, **over)
     if meta["predictor"].startswith("Dense"):
         o64.predictor = spec.MLPPredictor(spec.MLPWeights.random_init(meta["mlp_seed"]), dtype=torch.float64)
+    if meta["predictor"].startswith("GRU"):
+        o64.predictor = spec.GRUPredictor(spec.GRUWeights.random_init(meta["gru_seed"]), dtype=torch.float64)
     r32, r64 = replay(meta), replay(meta)
     if meta["optimizer"] in ("rpgd", "random-action-tf", "gradient-tf"):
         o32.reset(r32)

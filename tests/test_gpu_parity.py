@@ -118,6 +118,11 @@ def test_mppi_matches_reference_golden(name):
         assert e_u < tol_u and e_nom < tol_s, (name, t, e_u, e_nom, floors[t])
         _assert_symmetric(opt.u_nom, floors[t], f"{name} tick {t}")
         _check_J(opt.logging_values["J_logged"], z[f"J_{t}"], floors[t], (name, t))
+        if f"rnn_h_{t}" in z:  # recurrent predictor: the saved hidden state after this tick's predictor.update (optimizer_mppi.py:195-197)
+            from control_toolkit_b200 import _lib as L
+            e_h = max_rel(opt._get_state(L.STATE_RNN_H, (z[f"rnn_h_{t}"].size,)), z[f"rnn_h_{t}"])
+            _report(f"{name} tick {t}: rnn hidden state {e_h:.2e}")
+            assert e_h < 1e-5, (name, t, e_h)
         if t == 0 and "rollouts_0" in z:
             # injected noise -> sampled controls are bit-exact up to the interpolation matmul's rounding
             e_Q = max_rel(opt.logging_values["Q_logged"], z["Q_logged_0"])
