@@ -70,6 +70,10 @@ class controller_mpc:
         cost_function_specification = self.config_controller.get("cost_function_specification", None)
         self.cost_function = CostFunctionWrapper(cost_cfg.get("cost_function_name_default", "default"))
         self.predictor = PredictorWrapper()
+        # the reference's PredictorWrapper takes the dimensions from SI_Toolkit's configuration; here: from the environment registry
+        from ..specs import environment_info
+        info = environment_info(self.environment_name)
+        self.predictor.num_states, self.predictor.num_control_inputs = info.num_states, info.num_control_inputs
 
         Optimizer = import_optimizer_by_name(optimizer_name)  # reference :56
         self.optimizer = Optimizer(

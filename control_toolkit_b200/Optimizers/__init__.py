@@ -118,7 +118,14 @@ class template_optimizer:
         overrides = dict(specs.cost_overrides_from_yaml(env, cost_name))
         overrides.update(getattr(self.cost_function, "weights", None) or {})
         self._cost_spec = specs.resolve_cost(env, cost_name, overrides)
+        info = specs.environment_info(env)
+        if (int(self.num_states), int(self.num_control_inputs)) != (info.num_states, info.num_control_inputs):
+            raise ValueError(f"environment {env!r} has {info.num_states} states and {info.num_control_inputs} control inputs, the controller "
+                             f"configured {self.num_states} / {self.num_control_inputs}")
+        self._env_info = info
         pred_kind, pred_spec = specs.resolve_predictor(env, predictor_specification)
+        if info.env_id != L.ENV_CARTPOLE and pred_kind != L.PRED_ODE:
+            raise ValueError("network predictors are registered for the CartPole environment only")
         ode_spec = pred_spec if pred_kind == L.PRED_ODE else specs.ODE_REGISTRY.get(env, specs.CartPoleODE())
         self._dt = float(dt)
         self._ode_spec = ode_spec
@@ -137,9 +144,13 @@ class template_optimizer:
         cfg.mpc_horizon = self.mpc_horizon
         cfg.num_states = int(self.num_states)
         cfg.num_control_inputs = int(self.num_control_inputs)
-        if self.action_low.size != 1 or self.action_high.size != 1:
-            raise ValueError("only single-input environments have registered CUDA functors")
-        cfg.action_low, cfg.action_high = float(self.action_low[0]), float(self.action_high[0])
+        nu = info.num_control_inputs
+        if self.action_low.size not in (1, nu) or self.action_high.size not in (1, nu):
+            raise ValueError(f"control_limits must have 1 or {nu} entries per side for environment {env!r}")
+        low = np.ascontiguousarray(np.broadcast_to(self.action_low, (nu,)), np.float32)
+        high = np.ascontiguousarray(np.broadcast_to(self.action_high, (nu,)), np.float32)
+        cfg.action_low, cfg.action_high = float(low[0]), float(high[0])
+        cfg.environment = info.env_id
         cfg.seed = self.seed & 0xFFFFFFFFFFFFFFFF
         cfg.logging = int(self.optimizer_logging)
         cfg.freeze_previous_input = int(self.freeze_previous_input)
@@ -152,7 +163,10 @@ class template_optimizer:
 
         tp, te = self._live_targets()
         self._cost_live = (tp, te)
-        ode_c, cost_c = ode_spec.to_c(self._dt), self._cost_spec.to_c(tp, te)
+        if info.env_id == L.ENV_CARTPOLE:
+            ode_c, cost_c = ode_spec.to_c(self._dt), self._cost_spec.to_c(tp, te)
+        else:  # the CartPole blocks of ctk_create are ignored for other environments (their constants go through ctk_set_env_params)
+            ode_c, cost_c = specs.CartPoleODE().to_c(self._dt), specs.CartPoleCost().to_c()
         if self._h is not None:
             lib.ctk_destroy(self._h)
             self._h = None
@@ -161,6 +175,10 @@ class template_optimizer:
         self._h = h
         self._cfg = cfg
         self._n_local = int(cfg.num_rollouts)
+        if info.env_id != L.ENV_CARTPOLE:
+            L.check(lib.ctk_set_control_limits(self._h, L.fptr(low), L.fptr(high), nu))
+            ep = np.ascontiguousarray(info.env_params(ode_spec, self._cost_spec, self._dt), np.float32)
+            L.check(lib.ctk_set_env_params(self._h, L.fptr(ep), ep.size))
         if pred_kind == L.PRED_MLP:
             self._mlp_keepalive = pred_spec
             w = pred_spec.to_c()
@@ -169,7 +187,7 @@ class template_optimizer:
             self._mlp_keepalive = pred_spec
             w = pred_spec.to_c()
             L.check(lib.ctk_set_gru_weights(self._h, C.byref(w)))
-        self._u_buf = np.zeros(1, np.float32)
+        self._u_buf = np.zeros(nu, np.float32)
         self._state_buf = None
 
     def _require_backend(self):
@@ -181,6 +199,8 @@ class template_optimizer:
         """target_position / target_equilibrium -- and the pole length L of the ODE predictor (reference
         controller_server/controller_server.py:21-28 lists it among the live attributes) -- may change between ticks
         (controller update_attributes, reference Controllers/__init__.py:106-107)."""
+        if self._env_info.env_id != L.ENV_CARTPOLE:
+            return  # (target_position / target_equilibrium / L are CartPole attributes)
         live = self._live_targets()
         if live != self._cost_live:
             c = self._cost_spec.to_c(*live)
@@ -207,8 +227,8 @@ class template_optimizer:
 
     def _tick(self, lib, s: np.ndarray, state_which=None, state_n=0) -> np.ndarray:
         s32 = np.ascontiguousarray(np.asarray(s, dtype=np.float32).reshape(-1))
-        if s32.size != 6:
-            raise ValueError(f"state must have {6} entries, got {s32.size}")
+        if s32.size != int(self.num_states):
+            raise ValueError(f"state must have {int(self.num_states)} entries, got {s32.size}")
         if self.shard is not None and self.shard.world_size > 1:
             return self.shard.run_tick(self, lib, s32, state_which, state_n)
         if state_which is not None:  # u and one [H] state array with a single device->host window and synchronisation

@@ -82,9 +82,9 @@ class optimizer_mppi(template_optimizer):
         self._refresh_live_cost(lib)
         self._feed_noise(lib, [("normal", (self.num_rollouts, self.number_of_interpolation_inducing_points,
                                            self.num_control_inputs))])
-        H, nu, ns, N = self.mpc_horizon, self.num_control_inputs, 6, self._n_local
-        u = self._tick(lib, s, L.STATE_U_NOM, H)
-        self.u = np.squeeze(u)  # :212 0-d for nu == 1
+        H, nu, ns, N = self.mpc_horizon, self.num_control_inputs, int(self.num_states), self._n_local
+        u = self._tick(lib, s, L.STATE_U_NOM, H * nu)
+        self.u = np.squeeze(u)  # :212 0-d for nu == 1, (nu,) otherwise
         if self._state_buf is not None:
             self.u_nom = self._state_buf.reshape(1, H, nu).copy()
         else:

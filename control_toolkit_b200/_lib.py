@@ -19,6 +19,7 @@ CTK_OK, CTK_EINVAL, CTK_ECUDA, CTK_ESTATE = 0, -1, -2, -3
 OPT_MPPI, OPT_CEM, OPT_RPGD = 0, 1, 2
 PRED_ODE, PRED_MLP, PRED_GRU = 0, 1, 2
 COST_DEFAULT, COST_QUADRATIC_BOUNDARY_GRAD = 0, 1
+ENV_CARTPOLE, ENV_DUBINS_CAR = 0, 1
 DIST_NORMAL, DIST_UNIFORM = 0, 1
 ADAM_KERAS, ADAM_TORCH = 0, 1
 MLP_SIMT, MLP_TCGEN05, MLP_TCGEN05_BF16, MLP_TCGEN05_FAST = 0, 1, 2, 3
@@ -69,7 +70,7 @@ class ctk_config(C.Structure):
         ("rpgd_sample_mean", C.c_float), ("rpgd_sample_stdev", C.c_float), ("rpgd_sample_min", C.c_float),
         ("rpgd_sample_max", C.c_float), ("rpgd_learning_rate", C.c_float), ("rpgd_gradmax_clip", C.c_float),
         ("rpgd_beta_1", C.c_double), ("rpgd_beta_2", C.c_double), ("rpgd_epsilon", C.c_double),
-        ("mlp_engine", C.c_int32), ("cem_uniform_actions", C.c_int32), ("rpgd_gradient_mode", C.c_int32), ("num_clients", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("mlp_engine", C.c_int32), ("cem_uniform_actions", C.c_int32), ("rpgd_gradient_mode", C.c_int32), ("num_clients", C.c_int32), ("environment", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 
@@ -82,6 +83,8 @@ SYMBOLS = {
     "ctk_reset": (C.c_int, [_H]),
     "ctk_set_cost_params": (C.c_int, [_H, C.POINTER(ctk_cost_params)]),
     "ctk_set_ode_params": (C.c_int, [_H, C.POINTER(ctk_ode_params)]),
+    "ctk_set_env_params": (C.c_int, [_H, _FP, C.c_int]),
+    "ctk_set_control_limits": (C.c_int, [_H, _FP, _FP, C.c_int]),
     "ctk_set_mlp_weights": (C.c_int, [_H, C.POINTER(ctk_mlp_weights)]),
     "ctk_set_gru_weights": (C.c_int, [_H, C.POINTER(ctk_gru_weights)]),
     "ctk_set_stream": (C.c_int, [_H, C.c_void_p]),

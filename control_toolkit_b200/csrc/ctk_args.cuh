@@ -345,6 +345,52 @@ struct GradCemRefitArgs {
   HostMirror host;         // last iteration: u mirrored to the host caller
 };
 
+// ---- environments registered through the functor registry (ctk_kernels_env.cuh) ----------------------------------------------
+constexpr int kEnvMaxStates = 8, kEnvMaxControls = 4;
+struct EnvParams { float p[24]; };           // environment-specific constants (layout: the Env struct in ctk_kernels_env.cuh)
+struct S0e { const float* p; float v[kEnvMaxStates]; };  // initial state: device pointer, or the values inside the kernel parameters
+struct EnvMppiArgs {
+  int N, off, H, period, n_ind;
+  S0e s0;
+  float* u_nom;          // [H][NU] in (unshifted, :184 shift on read) / out (update kernel)
+  float* u_prev;         // [NU]
+  NoiseSrc noise;        // per_rollout = n_ind * NU, C order over [n_ind, NU]
+  float stdev, k_du2, k_udu, k_uu, neg_inv_lbd;
+  float lo[kEnvMaxControls], hi[kEnvMaxControls];
+  EnvParams env;
+  float* J;              // [N] total MPPI cost S
+  float* log_traj;       // [N][H+1][NS] or null
+  float* log_Q;          // [N][H][NU] or null
+  float* u_out;          // [NU] or null
+  int freeze_prev;
+};
+struct EnvCemArgs {
+  int N, off, H;
+  S0e s0;
+  const float* mu;       // [H][NU]
+  const float* sd;       // [H][NU]
+  const float* u_prev;   // [NU]
+  NoiseSrc noise;        // per_rollout = H * NU
+  float lo[kEnvMaxControls], hi[kEnvMaxControls];
+  EnvParams env;
+  float* J;
+  float* log_traj;
+  float* log_Q;
+};
+struct EnvCemRefitArgs {
+  int H, nu, k, cnt;
+  const uint64_t* cand;  // [cnt] (ordered cost, global id)
+  NoiseSrc noise;
+  float lo[kEnvMaxControls], hi[kEnvMaxControls];
+  float *mu, *sd;        // [H][NU] in/out
+  int last;
+  float sd_min, sd_init;
+  float* u_prev;         // [NU]
+  float* u_out;          // [NU] or null
+  int freeze_prev;
+  int32_t* elite_idx_out;
+};
+
 constexpr int TOPK_THREADS = 1024;  // keys per top-k block
 
 }  // namespace ctk

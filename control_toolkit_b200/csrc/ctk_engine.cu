@@ -103,6 +103,11 @@ struct ctk_handle {
   void* d_mlp_tc = nullptr;  // tcgen05 engine blob (ctk_mlp_tc.cuh)
   float* d_rnn_h = nullptr;  // recurrent predictor: saved hidden state [2][2 hid] (row 0 current, row 1 before the last update)
   const float* step_s = nullptr;  // state pointer of the tick in flight (staged MPPI ticks: predictor.update runs in ctk_step_finish)
+  // environments beyond the CartPole (ctk_kernels_env.cuh): env id, dimensions, parameter block, per-input limits
+  int env = 0, ns = 6, nu = 1;
+  EnvParams env_p{};
+  bool env_p_set = false;
+  float lo_v[kEnvMaxControls] = {0}, hi_v[kEnvMaxControls] = {0};
   // multi-client batching (ctk_step_batch): per-client state sits behind the pointers of client 0 at fixed strides
   int nclients = 1;
   uint32_t client_tick[kMaxBatchClients] = {0};
@@ -152,6 +157,7 @@ static cudaError_t dalloc(T** p, size_t n) {
 static void mppi_ode_geometry(ctk_handle* h);
 static int pred_id(const ctk_handle* h);
 static cudaError_t upload_consts(ctk_handle* h) {
+  if (h->env != 0) return cudaSuccess;  // general environments carry their constants in the kernel parameters (EnvParams)
   h->cem_tick_per_sm = -1;  // the cost kind selects the persistent tick's instantiation (register count): re-query its occupancy
   if (h->cfg.optimizer == CTK_OPT_MPPI) {
     const ctk_config& c = h->cfg;
@@ -243,8 +249,16 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
   REQ(cfg->abi_version == CTK_ABI_VERSION, "abi_version mismatch");
   REQ(cfg->optimizer >= CTK_OPT_MPPI && cfg->optimizer <= CTK_OPT_RPGD, "unknown optimizer");
   REQ(cfg->predictor == CTK_PRED_ODE || cfg->predictor == CTK_PRED_MLP || cfg->predictor == CTK_PRED_GRU, "unknown predictor");
-  REQ(cfg->num_states == 6 && cfg->num_control_inputs == 1,
-      "only the registered CartPole environment (6 states, 1 control) has device functors");
+  REQ(cfg->environment == CTK_ENV_CARTPOLE || cfg->environment == CTK_ENV_DUBINS_CAR, "unregistered environment");
+  int env_ns = 6, env_nu = 1;
+  env_dims(cfg->environment, &env_ns, &env_nu);
+  REQ(cfg->num_states == env_ns && cfg->num_control_inputs == env_nu,
+      "num_states / num_control_inputs do not match the registered environment (CartPole: 6 / 1, Dubins car: 3 / 2)");
+  if (cfg->environment != CTK_ENV_CARTPOLE)
+    REQ((cfg->optimizer == CTK_OPT_MPPI || cfg->optimizer == CTK_OPT_CEM) && cfg->predictor == CTK_PRED_ODE &&
+            cfg->num_rollouts == cfg->num_rollouts_global && cfg->num_clients <= 1 && !cfg->cem_uniform_actions,
+        "environments other than the CartPole: MPPI and CEM with the environment's ODE, unsharded, one client (RPGD's adjoint and the "
+        "network predictors are CartPole functors)");
   REQ(cfg->num_rollouts >= 1 && cfg->mpc_horizon >= 1, "num_rollouts and mpc_horizon must be >= 1");
   REQ(cfg->num_rollouts_global >= cfg->num_rollouts && cfg->rollout_offset >= 0 &&
           cfg->rollout_offset + cfg->num_rollouts <= cfg->num_rollouts_global, "bad shard geometry");
@@ -268,6 +282,8 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
   h->N = cfg->num_rollouts; h->NG = cfg->num_rollouts_global; h->off = cfg->rollout_offset; h->H = cfg->mpc_horizon;
   h->ode_p = *ode; h->cost_p = *cost;
   h->nclients = B;
+  h->env = cfg->environment; h->ns = env_ns; h->nu = env_nu;
+  for (int c = 0; c < kEnvMaxControls; ++c) { h->lo_v[c] = cfg->action_low; h->hi_v[c] = cfg->action_high; }
   derive_ode(*ode, h->ode);
   derive_fwd(*ode, h->fwd);
   derive_cost(*cost, h->H, h->cost);
@@ -278,7 +294,7 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
   auto A = [&](cudaError_t e, const char* what) {
     if (e != cudaSuccess && rc == CTK_OK) rc = fail(CTK_ECUDA, std::string("cudaMalloc ") + what + ": " + cudaGetErrorString(e));
   };
-  A(dalloc(&h->d_s0, 8), "s0"); A(dalloc(&h->d_u_prev, (size_t)B), "u_prev"); A(dalloc(&h->d_u_out, 4 + 2 * (size_t)B), "u_out");
+  A(dalloc(&h->d_s0, 8), "s0"); A(dalloc(&h->d_u_prev, (size_t)(B > env_nu ? B : env_nu)), "u_prev"); A(dalloc(&h->d_u_out, 4 + 2 * (size_t)B), "u_out");
   A(dalloc(&h->d_J, (size_t)N * B), "J");
   if (B > 1) A(cudaHostAlloc((void**)&h->h_batch, 2 * (size_t)B * sizeof(float), cudaHostAllocDefault), "pinned (batch results)");
   A(cudaMalloc((void**)&h->d_kc, sizeof(DevConsts)), "consts");
@@ -286,16 +302,34 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
   A(cudaHostAlloc((void**)&h->h_pin, (32 + 2 * (size_t)H) * sizeof(float), cudaHostAllocMapped), "pinned");
   if (h->h_pin) { memset(h->h_pin, 0, (32 + 2 * (size_t)H) * sizeof(float)); A(cudaHostGetDevicePointer((void**)&h->d_pin, h->h_pin, 0), "pinned (device view)"); }
   if (cfg->logging) {
-    A(dalloc(&h->d_log_traj_soa, (size_t)(H + 1) * 6 * N), "log_traj");
-    A(dalloc(&h->d_log_Q_soa, (size_t)H * N), "log_Q");
-    A(dalloc(&h->d_log_tmp, (size_t)(H + 1) * 6 * N), "log_tmp");
+    A(dalloc(&h->d_log_traj_soa, (size_t)(H + 1) * env_ns * N), "log_traj");
+    A(dalloc(&h->d_log_Q_soa, (size_t)H * env_nu * N), "log_Q");
+    if (h->env == 0) A(dalloc(&h->d_log_tmp, (size_t)(H + 1) * 6 * N), "log_tmp");
   }
   if (cfg->optimizer == CTK_OPT_MPPI || cfg->optimizer == CTK_OPT_RPGD) {
     h->period = cfg->period_interpolation_inducing_points;
     if (h->period < 1) { ctk_destroy(h); return fail(CTK_EINVAL, "period_interpolation_inducing_points must be >= 1"); }
     h->n_ind = (int)std::ceil((double)(H - 1) / (double)h->period) + 1;  // Interpolator.py:79-84
   }
-  if (cfg->optimizer == CTK_OPT_MPPI) {
+  if (h->env != 0) {
+    // general-environment kernels: flat [H][nu] state arrays; CEM shares K4 (top-k levels) with the CartPole path
+    if (cfg->optimizer == CTK_OPT_MPPI) {
+      if (h->n_ind * env_nu > 32 || H * env_nu > 1024) { ctk_destroy(h); return fail(CTK_EINVAL, "environment MPPI: n_ind * nu <= 32 and H * nu <= 1024"); }
+      A(dalloc(&h->d_u_nom, (size_t)H * env_nu), "u_nom");
+    } else {
+      if (!(cfg->cem_best_k >= 1 && cfg->cem_best_k <= 512 && cfg->cem_best_k <= N && H * env_nu <= 1024 && cfg->cem_outer_it >= 1)) {
+        ctk_destroy(h);
+        return fail(CTK_EINVAL, "environment CEM needs 1 <= cem_best_k <= min(512, num_rollouts), H * nu <= 1024, cem_outer_it >= 1");
+      }
+      A(dalloc(&h->d_mu, (size_t)H * env_nu), "mu"); A(dalloc(&h->d_sd, (size_t)H * env_nu), "sd");
+      const size_t nk = (size_t)((N + 1023) / 1024) * cfg->cem_best_k + 1024;
+      A(dalloc(&h->d_keys[0], nk), "keys0"); A(dalloc(&h->d_keys[1], nk), "keys1");
+      int iters = cfg->cem_outer_it;
+      if (cfg->cem_warmup && cfg->cem_warmup_iterations > iters) iters = cfg->cem_warmup_iterations;
+      h->elite_log_cap = iters;
+      A(dalloc(&h->d_elite_idx, (size_t)iters * cfg->cem_best_k), "elite_idx");
+    }
+  } else if (cfg->optimizer == CTK_OPT_MPPI) {
     // K1 geometry: one CTA per SM, block sized so that every thread runs the same number of rollouts (no tail wave)
     cudaDeviceProp prop;
     A(cudaGetDeviceProperties(&prop, cfg->device), "props");
@@ -540,6 +574,22 @@ static RpgdSelectArgs rpgd_sample_args(ctk_handle* h, NoiseSrc ns) {
 extern "C" int ctk_reset(ctk_handle* h) {
   REQ(h, "null handle");
   CU(cudaSetDevice(h->cfg.device));
+  if (h->env != 0) {  // per-input mid-range warm start (optimizer_mppi.py:227-231, optimizer_cem_tf.py:113-117), flat [H][nu]
+    std::vector<float> mid_v((size_t)h->H * h->nu), sd_v((size_t)h->H * h->nu, h->cfg.cem_initial_action_stdev);
+    for (int t = 0; t < h->H; ++t) for (int c = 0; c < h->nu; ++c) mid_v[(size_t)t * h->nu + c] = 0.5f * (h->lo_v[c] + h->hi_v[c]);
+    if (h->cfg.optimizer == CTK_OPT_MPPI) {
+      CU(cudaMemcpyAsync(h->d_u_nom, mid_v.data(), sizeof(float) * mid_v.size(), cudaMemcpyHostToDevice, h->stream));
+    } else {
+      CU(cudaMemcpyAsync(h->d_mu, mid_v.data(), sizeof(float) * mid_v.size(), cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemcpyAsync(h->d_sd, sd_v.data(), sizeof(float) * sd_v.size(), cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemsetAsync(h->d_u_prev, 0, sizeof(float) * h->nu, h->stream));  // only optimizer_cem_tf.optimizer_reset zeroes self.u (:117)
+      h->cem_it = 0;
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    h->count = 0;
+    h->was_reset = true;
+    return CTK_OK;
+  }
   const float mid = 0.5f * (h->cfg.action_low + h->cfg.action_high);
   std::vector<float> tmp((size_t)h->H * h->nclients, mid);
   // self.u, the previous_input of the cost, is reset ONLY by optimizer_cem_tf.optimizer_reset (optimizer_cem_tf.py:117); MPPI (:227-231),
@@ -578,8 +628,117 @@ extern "C" int ctk_reset(ctk_handle* h) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// environments beyond the CartPole: parameter block, per-input limits, the tick as a plain launch sequence
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int ctk_set_env_params(ctk_handle* h, const float* p, int n) {
+  REQ(h && p && n >= 0 && n <= 24, "null pointer or more than 24 parameters");
+  REQ(h->env != 0, "ctk_set_env_params is for environments other than the CartPole (use ctk_set_ode_params / ctk_set_cost_params)");
+  for (int i = 0; i < 24; ++i) h->env_p.p[i] = i < n ? p[i] : 0.0f;
+  h->env_p_set = true;
+  return CTK_OK;
+}
+extern "C" int ctk_set_control_limits(ctk_handle* h, const float* low, const float* high, int nu) {
+  REQ(h && low && high && nu == h->nu, "null pointer or nu != num_control_inputs");
+  for (int c = 0; c < nu; ++c) REQ(low[c] <= high[c], "action_low > action_high");
+  REQ(h->env != 0 || (low[0] == h->cfg.action_low && high[0] == h->cfg.action_high), "the CartPole kernels take their limits from ctk_config");
+  for (int c = 0; c < nu; ++c) { h->lo_v[c] = low[c]; h->hi_v[c] = high[c]; }
+  return CTK_OK;
+}
+
+static S0e make_s0e(const ctk_handle* h, const float* s_dev, const float* s_host) {
+  S0e s{};
+  s.p = s_dev;
+  if (s_dev == nullptr) for (int i = 0; i < h->ns; ++i) s.v[i] = s_host[i];
+  return s;
+}
+
+static int env_tick(ctk_handle* h, const S0e& s0, float* u_out_dev) {
+  const ctk_config& c = h->cfg;
+  if (!h->env_p_set) return fail(CTK_ESTATE, "environment parameters not set (ctk_set_env_params)");
+  const int nu = h->nu;
+  h->tick++;
+  if (c.optimizer == CTK_OPT_MPPI) {
+    EnvMppiArgs a{};
+    int rcn = make_noise(h, STREAM_MPPI, h->n_ind * nu, 0, (size_t)h->NG, &a.noise);
+    if (rcn != CTK_OK) return rcn;
+    a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
+    a.s0 = s0; a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev;
+    a.stdev = c.mppi_stdev;
+    a.k_du2 = (float)((double)c.mppi_cc_weight * (double)c.mppi_coef_du2);
+    a.k_udu = (float)((double)c.mppi_cc_weight * (double)c.mppi_R);
+    a.k_uu = (float)((double)c.mppi_cc_weight * (double)c.mppi_half_R);
+    a.neg_inv_lbd = c.mppi_neg_inv_LBD;
+    for (int i = 0; i < kEnvMaxControls; ++i) { a.lo[i] = h->lo_v[i]; a.hi[i] = h->hi_v[i]; }
+    a.env = h->env_p; a.J = h->d_J; a.log_traj = h->d_log_traj_soa; a.log_Q = h->d_log_Q_soa;
+    a.u_out = u_out_dev; a.freeze_prev = c.freeze_previous_input;
+    h->launches += 2;
+    {
+      KernelTimer kt(h);
+      CU(launch_env_mppi(h->env, c.logging != 0, a, h->stream));
+    }
+    h->last_kernel = std::string("env_mppi_rollout_kernel<DubinsEnv,") + (c.logging ? "1" : "0") + ">" + (a.noise.inj ? " [injected noise]" : " [philox]");
+    return CTK_OK;
+  }
+  // CEM: optimizer_cem_tf.py:83-111
+  const int iters = (c.cem_warmup && h->count == 0) ? c.cem_warmup_iterations : c.cem_outer_it;
+  if (iters < 1) return fail(CTK_EINVAL, "CEM iteration count < 1");
+  h->elite_log_rows = 0;
+  h->cem_iters = iters;
+  for (int it = 0; it < iters; ++it) {
+    EnvCemArgs a{};
+    int rcn = make_noise(h, STREAM_CEM | ((uint32_t)it << 8), h->H * nu, 0, (size_t)h->NG, &a.noise);
+    if (rcn != CTK_OK) return rcn;
+    a.N = h->N; a.off = h->off; a.H = h->H; a.s0 = s0; a.mu = h->d_mu; a.sd = h->d_sd; a.u_prev = h->d_u_prev;
+    for (int i = 0; i < kEnvMaxControls; ++i) { a.lo[i] = h->lo_v[i]; a.hi[i] = h->hi_v[i]; }
+    a.env = h->env_p; a.J = h->d_J; a.log_traj = h->d_log_traj_soa; a.log_Q = h->d_log_Q_soa;
+    h->launches++;
+    {
+      KernelTimer kt(h);
+      CU(launch_env_cem_rollout(h->env, c.logging != 0, a, h->stream));
+    }
+    h->last_kernel = std::string("env_cem_rollout_kernel<DubinsEnv,") + (c.logging ? "1" : "0") + ">" + (a.noise.inj ? " [injected noise]" : " [philox]");
+    // K4: hierarchical bitonic top-k (tf.argsort(...)[:k], ties -> lower index)
+    const int k = c.cem_best_k;
+    int n = h->N, lvl = 0;
+    const float* cost = h->d_J;
+    const uint64_t* kin = nullptr;
+    while (true) {
+      const int nb = (n + TOPK_THREADS - 1) / TOPK_THREADS;
+      uint64_t* outk = h->d_keys[lvl & 1];
+      h->launches++;
+      CU(launch_topk_level(cost, kin, n, h->off, k, outk, h->stream));
+      n = nb * k; cost = nullptr; kin = outk; ++lvl;
+      if (n <= TOPK_THREADS) break;
+    }
+    EnvCemRefitArgs r{};
+    r.H = h->H; r.nu = nu; r.k = k; r.cnt = n; r.cand = kin; r.noise = a.noise;
+    for (int i = 0; i < kEnvMaxControls; ++i) { r.lo[i] = h->lo_v[i]; r.hi[i] = h->hi_v[i]; }
+    r.mu = h->d_mu; r.sd = h->d_sd; r.last = (it == iters - 1) ? 1 : 0;
+    r.sd_min = c.cem_stdev_min; r.sd_init = c.cem_initial_action_stdev;
+    r.u_prev = h->d_u_prev; r.u_out = u_out_dev; r.freeze_prev = c.freeze_previous_input;
+    r.elite_idx_out = (h->elite_log_rows < h->elite_log_cap) ? h->d_elite_idx + (size_t)h->elite_log_rows * k : nullptr;
+    h->launches++;
+    CU(launch_env_cem_refit(r, h->stream));
+    if (r.elite_idx_out) h->elite_log_rows++;
+  }
+  h->count++;
+  return CTK_OK;
+}
+
+// host-facing tick of a general environment: launch sequence, then ONE device->host copy of u (and the requested state array)
+static int env_step_host(ctk_handle* h, const float* s_host, float* u_out_host, const float* state_dev, float* state_out_host, size_t n_state) {
+  int rc = env_tick(h, make_s0e(h, nullptr, s_host), h->d_u_out);
+  if (rc != CTK_OK) return rc;
+  CU(cudaMemcpyAsync(u_out_host, h->d_u_out, sizeof(float) * h->nu, cudaMemcpyDeviceToHost, h->stream));
+  if (state_dev) CU(cudaMemcpyAsync(state_out_host, state_dev, n_state * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return CTK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // the tick
 // ---------------------------------------------------------------------------------------------------------------
+
 // 0 ODE, 1 MLP on the FP32 pipe, 2 MLP with the dense layer on tcgen05 (bf16 x 3 split, fp32-level), 3 one bf16 product, 4 + MUFU.TANH
 static int pred_id(const ctk_handle* h) {
   if (h->cfg.predictor == CTK_PRED_GRU) return 5;  // recurrent predictor on the FP32 pipe (GruSimtPred)
@@ -1121,6 +1280,7 @@ static int rpgd_tick(ctk_handle* h, const float* s_dev, float* u_out_dev) {
 
 extern "C" int ctk_step_local(ctk_handle* h, const float* s_dev) {
   REQ(h && s_dev, "null pointer");
+  REQ(h->env == 0, "the staged (sharded) tick is implemented for the CartPole environment");
   if (!h->was_reset) return fail(CTK_ESTATE, "ctk_step before ctk_reset");
   CU(cudaSetDevice(h->cfg.device));
   if (h->cfg.predictor != CTK_PRED_ODE && h->mlp.blob == nullptr) return fail(CTK_ESTATE, "network predictor without weights (ctk_set_mlp_weights / ctk_set_gru_weights)");
@@ -1175,7 +1335,7 @@ extern "C" int ctk_step_state(ctk_handle* h, const float* s_host, float* u_out_h
   float* p; size_t cnt; bool tm;
   int rc = state_ptr(h, which, &p, &cnt, &tm);
   if (rc != CTK_OK) return rc;
-  REQ(!tm && n == cnt && cnt <= (size_t)h->H, "ctk_step_state reads the [H] state arrays only");
+  REQ(!tm && n == cnt && cnt <= (size_t)h->H * h->nu, "ctk_step_state reads the [H, nu] state arrays only");
   return step_host(h, s_host, u_out_host, p, state_out_host, n);
 }
 // Wait until the kernel that finishes the tick has delivered the tagged slots [first, first + count) of the mapped result
@@ -1216,6 +1376,7 @@ static int step_host(ctk_handle* h, const float* s_host, float* u_out_host, cons
   REQ(h && s_host && u_out_host, "null pointer");
   if (!h->was_reset) return fail(CTK_ESTATE, "ctk_step before ctk_reset");
   CU(cudaSetDevice(h->cfg.device));
+  if (h->env != 0) return env_step_host(h, s_host, u_out_host, state_dev, state_out_host, n_state);
   if (h->cfg.predictor != CTK_PRED_ODE && h->mlp.blob == nullptr) return fail(CTK_ESTATE, "network predictor without weights (ctk_set_mlp_weights / ctk_set_gru_weights)");
   memcpy(h->h_pin, s_host, sizeof(float) * 6);
   // the mirror carries one [H] array: MPPI's u_nom / RPGD's best sequence; any other state array takes the copy path below
@@ -1275,6 +1436,7 @@ extern "C" int ctk_step_device(ctk_handle* h, const float* s_dev, float* u_out_d
   CU(cudaSetDevice(h->cfg.device));
   if (h->cfg.predictor != CTK_PRED_ODE && h->mlp.blob == nullptr) return fail(CTK_ESTATE, "network predictor without weights (ctk_set_mlp_weights / ctk_set_gru_weights)");
   float* uo = u_out_dev ? u_out_dev : h->d_u_out;
+  if (h->env != 0) return env_tick(h, make_s0e(h, s_dev, nullptr), uo);  // u_out_dev [nu]
   int rc = CTK_OK;
   h->tick++;
   if (h->cfg.optimizer == CTK_OPT_MPPI) {
@@ -1384,6 +1546,7 @@ extern "C" int ctk_reset_client(ctk_handle* h, int client) {
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int ctk_exchange_export(ctk_handle* h, void* ipc_handle_out64) {
   REQ(h && ipc_handle_out64, "null pointer");
+  REQ(h->env == 0, "the cross-GPU exchange is implemented for the CartPole environment");
   REQ(h->d_mbox != nullptr, "this optimizer has no exchange mailbox (RPGD is replicas-only)");
   CU(cudaSetDevice(h->cfg.device));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -1477,15 +1640,15 @@ static int state_ptr(ctk_handle* h, int which, float** p, size_t* n, bool* tmajo
   *tmajor = false;
   const size_t H = h->H, N = h->N;
   switch (which) {
-    case CTK_STATE_U_NOM: *p = (h->cfg.optimizer == CTK_OPT_RPGD) ? h->d_unom_log : h->d_u_nom; *n = H * (size_t)h->nclients; break;  // RPGD: Q[best] before the shift (:426)
-    case CTK_STATE_CEM_MU: *p = h->d_mu; *n = H; break;
-    case CTK_STATE_CEM_STD: *p = h->d_sd; *n = H; break;
+    case CTK_STATE_U_NOM: *p = (h->cfg.optimizer == CTK_OPT_RPGD) ? h->d_unom_log : h->d_u_nom; *n = H * (size_t)h->nclients * h->nu; break;  // RPGD: Q[best] before the shift (:426)
+    case CTK_STATE_CEM_MU: *p = h->d_mu; *n = H * h->nu; break;
+    case CTK_STATE_CEM_STD: *p = h->d_sd; *n = H * h->nu; break;
     case CTK_STATE_RPGD_Q: *p = h->d_Q[h->cur]; *n = N * H; *tmajor = true; break;
     // gradient-assisted CEM keeps its Adam moments attached to the population ROWS (never permuted): buffer 0
     case CTK_STATE_RPGD_M: *p = h->d_m[h->cfg.rpgd_gradient_mode >= 2 ? 0 : h->cur]; *n = N * H; *tmajor = true; break;
     case CTK_STATE_RPGD_V: *p = h->d_v[h->cfg.rpgd_gradient_mode >= 2 ? 0 : h->cur]; *n = N * H; *tmajor = true; break;
     case CTK_STATE_RPGD_AGES: *p = h->d_ages[h->cur]; *n = N; break;
-    case CTK_STATE_U_PREV: *p = h->d_u_prev; *n = (size_t)h->nclients; break;
+    case CTK_STATE_U_PREV: *p = h->d_u_prev; *n = (size_t)(h->nclients > h->nu ? h->nclients : h->nu); break;
     case CTK_STATE_RNN_H: *p = h->d_rnn_h; *n = 2 * (size_t)h->mlp.hidden; break;
     default: return fail(CTK_EINVAL, "unknown state id");
   }
@@ -1619,6 +1782,12 @@ static int log_source(ctk_handle* h, int which, const void** src_out, size_t* ne
   const size_t N = h->N, H = h->H;
   const void* src = nullptr;
   size_t need = 0;
+  if (h->env != 0 && (which == CTK_LOG_Q || which == CTK_LOG_ROLLOUTS)) {  // written in the reference's layout by the rollout kernel
+    REQ(h->cfg.logging, "logging disabled");
+    *src_out = which == CTK_LOG_Q ? h->d_log_Q_soa : h->d_log_traj_soa;
+    *need_out = which == CTK_LOG_Q ? N * H * h->nu * 4 : N * (H + 1) * h->ns * 4;
+    return CTK_OK;
+  }
   switch (which) {
     case CTK_LOG_J: src = h->d_J; need = N * 4; break;
     case CTK_LOG_Q:
@@ -1689,6 +1858,7 @@ extern "C" int ctk_get_log_view(ctk_handle* h, int which, const void** host_ptr,
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int ctk_rollout_single(ctk_handle* h, const float* s_host, const float* Q_host, float* traj_host, float* summed) {
   REQ(h && s_host && Q_host && traj_host, "null pointer");
+  REQ(h->env == 0, "the standalone nominal rollout is implemented for the CartPole environment");
   CU(cudaSetDevice(h->cfg.device));
   const int H = h->H;
   float* d = nullptr;

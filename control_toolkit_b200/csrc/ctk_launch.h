@@ -43,6 +43,11 @@ cudaError_t launch_mppi_combine(const float* in, int cnt, int n_ind, float neg_i
 cudaError_t launch_exchange_barrier(const MppiFuse& f, size_t bar_off, cudaStream_t st);
 cudaError_t launch_transpose(const float* in, float* out, int R, int C, cudaStream_t st);
 size_t mppi_pred_smem_floats(int pred, const MlpDev& m);
+// environments beyond the CartPole (ctk_env.cu): MPPI = rollout + update launches, CEM = rollout, K4 levels, refit
+cudaError_t launch_env_mppi(int env, bool log, const EnvMppiArgs& a, cudaStream_t st);
+cudaError_t launch_env_cem_rollout(int env, bool log, const EnvCemArgs& a, cudaStream_t st);
+cudaError_t launch_env_cem_refit(const EnvCemRefitArgs& a, cudaStream_t st);
+void env_dims(int env, int* ns, int* nu);
 // recurrent predictor (ctk_gru.cu)
 cudaError_t launch_mppi_rollout_gru(int kind, bool log, int nblocks, int block, size_t smem, cudaStream_t st, const MppiArgs& a);
 cudaError_t launch_cem_rollout_gru(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemArgs& a);

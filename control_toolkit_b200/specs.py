@@ -83,22 +83,80 @@ class CartPoleCost:
         return p
 
 
+@dataclass
+class DubinsCarODE:
+    """Second registered environment (SURVEY 8f.3): Dubins car, state [x, y, yaw], controls [throttle, steer] in [-1, 1]^2;
+    x += h v cos(yaw), y += h v sin(yaw), yaw = wrap(yaw + h w) with v = v_max Q0, w = omega_max Q1.  Pinned spec: oracle/spec.py
+    dubins_step (written independently, compared in tests/test_host_logic.py)."""
+    v_max: float = 1.0
+    omega_max: float = 2.0
+    intermediate_steps: int = 1
+
+
+@dataclass
+class DubinsCarCost:
+    """`default` cost of the Dubins car (oracle/spec.py DubinsCost): squared distance to the target, an indicator penalty inside a
+    circular obstacle, control effort, control change rate; terminal = weighted squared distance."""
+    kind: int = L.COST_DEFAULT
+    dd_weight: float = 10.0
+    obstacle_weight: float = 1.0e4
+    cc_weight: float = 1.0
+    ccrc_weight: float = 1.0
+    R: float = 0.1
+    terminal_weight: float = 100.0
+    MAX_COST: float = 0.0
+    target_x: float = 1.0
+    target_y: float = 0.5
+    obstacle_x: float = 0.5
+    obstacle_y: float = 0.2
+    obstacle_r: float = 0.15
+
+
+def dubins_env_params(ode: DubinsCarODE, cost: DubinsCarCost, dt: float) -> np.ndarray:
+    """The flat parameter block of DubinsEnv (ctk_kernels_env.cuh): compound constants in float64, rounded once."""
+    return np.array([dt, ode.v_max, ode.omega_max, cost.dd_weight, cost.obstacle_weight, _f32(cost.cc_weight) * _f32(cost.R),
+                     cost.ccrc_weight, cost.terminal_weight, cost.target_x, cost.target_y, cost.obstacle_x, cost.obstacle_y,
+                     cost.obstacle_r * cost.obstacle_r, cost.MAX_COST], np.float32)
+
+
+@dataclass(frozen=True)
+class EnvironmentInfo:
+    env_id: int
+    num_states: int
+    num_control_inputs: int
+    env_params: object = None  # (ode_spec, cost_spec, dt) -> flat fp32 parameter block, for environments on the general kernels
+
+
+# environment_name -> device functors.  CartPole: the fused kernels; anything else: the general-environment kernels (MPPI, CEM).
+ENVIRONMENTS = {
+    "CartPole": EnvironmentInfo(L.ENV_CARTPOLE, 6, 1),
+    "DubinsCar": EnvironmentInfo(L.ENV_DUBINS_CAR, 3, 2, dubins_env_params),
+}
+
 # (environment_name, cost_function_name) -> prototype
 COST_REGISTRY = {
     ("CartPole", "default"): CartPoleCost(kind=L.COST_DEFAULT),
     ("CartPole", "quadratic_boundary_grad"): CartPoleCost(kind=L.COST_QUADRATIC_BOUNDARY_GRAD),
+    ("DubinsCar", "default"): DubinsCarCost(),
 }
-ODE_REGISTRY = {"CartPole": CartPoleODE()}
-_WEIGHT_KEYS = ("dd_weight", "ep_weight", "ekp_weight", "cc_weight", "ccrc_weight", "R")
+ODE_REGISTRY = {"CartPole": CartPoleODE(), "DubinsCar": DubinsCarODE()}
 
 
-def resolve_cost(environment_name: str, cost_function_name: str, overrides: dict | None = None) -> CartPoleCost:
+def environment_info(environment_name: str) -> EnvironmentInfo:
+    if environment_name not in ENVIRONMENTS:
+        raise ValueError(f"environment {environment_name!r} has no registered CUDA functors (registered: {sorted(ENVIRONMENTS)}); "
+                         "this backend has no Python/CPU fallback")
+    return ENVIRONMENTS[environment_name]
+
+
+def resolve_cost(environment_name: str, cost_function_name: str, overrides: dict | None = None):
     key = (str(environment_name), str(cost_function_name).replace("-", "_"))
     if key not in COST_REGISTRY:
         raise ValueError(f"cost function {key[1]!r} of environment {key[0]!r} has no registered CUDA functor "
                          f"(registered: {sorted(COST_REGISTRY)}); this backend has no Python/CPU fallback")
     proto = COST_REGISTRY[key]
-    ov = {k: float(v) for k, v in (overrides or {}).items() if k in _WEIGHT_KEYS}
+    names = {f for f in proto.__dataclass_fields__ if f != "kind"}
+    ov = {k: float(v) for k, v in (overrides or {}).items() if k in names and k not in ("MAX_COST", "TrackHalfLength")}
     return replace(proto, **ov)
 
 

@@ -35,6 +35,11 @@ extern "C" {
 enum { CTK_OPT_MPPI = 0, CTK_OPT_CEM = 1, CTK_OPT_RPGD = 2 };            /* optimizer_mppi / optimizer_cem_tf / optimizer_rpgd */
 enum { CTK_PRED_ODE = 0, CTK_PRED_MLP = 1, CTK_PRED_GRU = 2 };           /* predictor_specification "ODE" / "Dense-..." / "GRU-..." */
 enum { CTK_COST_DEFAULT = 0, CTK_COST_QUADRATIC_BOUNDARY_GRAD = 1 };     /* cost_function_specification                         */
+/* environment_name (reference Controllers/__init__.py:33; the cost class is Control_Toolkit_ASF.Cost_Functions.<env>.<name>,
+   Cost_Functions/cost_function_wrapper.py:59-66).  CARTPOLE: 6 states, 1 control, every optimizer and predictor, the fused kernels.
+   DUBINS_CAR: 3 states [x, y, yaw], 2 controls [throttle, steer]; MPPI and CEM with its ODE and its `default` cost through the
+   general-environment kernels (ctk_kernels_env.cuh); parameters by ctk_set_env_params, per-input limits by ctk_set_control_limits. */
+enum { CTK_ENV_CARTPOLE = 0, CTK_ENV_DUBINS_CAR = 1 };
 enum { CTK_DIST_NORMAL = 0, CTK_DIST_UNIFORM = 1 };                      /* RPGD SAMPLING_DISTRIBUTION                          */
 enum { CTK_ADAM_KERAS = 0, CTK_ADAM_TORCH = 1 };                         /* reference optimizer_rpgd.py:34-43 vs :56-82         */
 /* MLP predictor engine.  SIMT: FP32 pipe (numerical anchor).  TCGEN05: 128 x 128 layer on the tensor cores as six products of
@@ -146,7 +151,8 @@ typedef struct ctk_config {
   int32_t num_clients;            /* 0 / 1: one client (the reference's controller).  2 .. 16: the handle carries that many independent
                                      MPPI clients -- own warm-start sequence, previous input, costs and Philox tick counter each -- whose
                                      ticks ctk_step_batch runs in ONE launch (MPPI + ODE predictor, logging off, unsharded) */
-  int32_t reserved[4];
+  int32_t environment;            /* CTK_ENV_*                                                                    */
+  int32_t reserved[3];
 } ctk_config;
 
 typedef struct ctk_handle ctk_handle;
@@ -161,6 +167,12 @@ int ctk_reset(ctk_handle *h);
 /* live cost / environment parameters (controller update_attributes, Controllers/__init__.py:106-107)            */
 int ctk_set_cost_params(ctk_handle *h, const ctk_cost_params *cost);
 int ctk_set_ode_params(ctk_handle *h, const ctk_ode_params *ode);
+/* environments other than the CartPole: the flat parameter block of the environment's device functors (Dubins car: h, v_max,
+   omega_max, dd_weight, obstacle_weight, cc_weight * R, ccrc_weight, terminal_weight, target_x, target_y, obstacle_x, obstacle_y,
+   obstacle_r^2, MAX_COST), and the per-input control limits (template_optimizer stores action_low / action_high as [nu] tensors,
+   Optimizers/__init__.py:42-44).  The ode / cost blocks of ctk_create are ignored for such handles.                            */
+int ctk_set_env_params(ctk_handle *h, const float *p, int n);
+int ctk_set_control_limits(ctk_handle *h, const float *low, const float *high, int nu);
 int ctk_set_mlp_weights(ctk_handle *h, const ctk_mlp_weights *w);
 /* recurrent predictor (CTK_PRED_GRU; MPPI and CEM): weights; the saved hidden state is zeroed.  Every MPPI tick ends with the
    reference's predictor.update(s, Q0 = new u_nom[0]) (optimizer_mppi.py:192,195-197) as one small kernel on the handle's stream;
@@ -180,7 +192,8 @@ int ctk_clear_injected_noise(ctk_handle *h);
 
 /* ---- the hot path ------------------------------------------------------------------------------------------- */
 /* replaces optimizer.step(s, time) (controller_mpc.py:104): one full tick, host in / host out.
-   s_host [num_states]; u_out_host [num_control_inputs].  The call issues no cudaMemcpy and no stream synchronisation:
+   s_host [num_states]; u_out_host [num_control_inputs].  (Environments other than the CartPole: a plain launch sequence with one
+   device->host copy of u; what follows describes the CartPole ticks.)  The call issues no cudaMemcpy and no stream synchronisation:
    the state travels inside the kernel parameters, the tick's last kernel stores u and a status word as tagged 8-byte
    slots (value | launch sequence number) into mapped pinned host memory, and the call polls the tags (a faulted or
    lost stream is detected through cudaStreamQuery after 50 ms; 60 s hard limit).  MPPI, CEM (unsharded populations up

@@ -27,13 +27,14 @@ class CEMOracle:
         self.std_min = float(cem_stdev_min)
         self.k = int(cem_best_k)
         self.warmup, self.warmup_iterations = bool(warmup), int(warmup_iterations)
-        self.low = torch.tensor([action_low], dtype=dtype)
-        self.high = torch.tensor([action_high], dtype=dtype)
+        self.low = torch.as_tensor(np.atleast_1d(np.asarray(action_low, np.float32))).to(dtype)
+        self.high = torch.as_tensor(np.atleast_1d(np.asarray(action_high, np.float32))).to(dtype)
+        self.nu = int(getattr(predictor, "num_control_inputs", 1))
         self.reset()
 
     def reset(self):  # optimizer_cem_tf.py:113-117
-        self.dist_mue = (self.low + self.high) * 0.5 * torch.ones([1, self.H, 1], dtype=self.dtype)
-        self.stdev = float(np.float32(self.init_std)) * torch.ones([1, self.H, 1], dtype=self.dtype)
+        self.dist_mue = (self.low + self.high) * 0.5 * torch.ones([1, self.H, self.nu], dtype=self.dtype)
+        self.stdev = float(np.float32(self.init_std)) * torch.ones([1, self.H, self.nu], dtype=self.dtype)
         self.count = 0
         self.u = 0.0
         self.last = {}
@@ -44,7 +45,7 @@ class CEMOracle:
         elite_log, cost_log = [], []
         for _ in range(iterations):  # :93-94 -> update_distribution :61-80
             Q = self.dist_mue.repeat(self.N, 1, 1) + torch.mul(
-                rng.normal(shape=(self.N, self.H, 1), dtype=torch.float32).to(self.dtype), self.stdev)  # :64-65
+                rng.normal(shape=(self.N, self.H, self.nu), dtype=torch.float32).to(self.dtype), self.stdev)  # :64-65
             Q = torch.minimum(torch.maximum(Q, self.low), self.high)  # :66
             rollout = self.predictor.predict_core(s, Q)  # :57
             traj_cost = spec.trajectory_cost(rollout, Q, self.u, self.cost)  # :58
@@ -58,9 +59,9 @@ class CEMOracle:
             cost_log.append(traj_cost.numpy().copy())
         # :99-102
         self.stdev = torch.minimum(torch.maximum(self.stdev, torch.tensor(float(np.float32(self.std_min)), dtype=self.dtype)), torch.tensor(1.0e8, dtype=self.dtype))
-        self.stdev = torch.cat([self.stdev[:, 1:, :], float(np.float32(self.init_std)) * torch.ones((1, 1, 1), dtype=self.dtype)], dim=1)
+        self.stdev = torch.cat([self.stdev[:, 1:, :], float(np.float32(self.init_std)) * torch.ones((1, 1, self.nu), dtype=self.dtype)], dim=1)
         self.u = elite_Q[0, 0, :].squeeze().numpy().copy()
-        self.dist_mue = torch.cat([self.dist_mue[:, 1:, :], (self.low + self.high) * 0.5 * torch.ones((1, 1, 1), dtype=self.dtype)], dim=1)
+        self.dist_mue = torch.cat([self.dist_mue[:, 1:, :], (self.low + self.high) * 0.5 * torch.ones((1, 1, self.nu), dtype=self.dtype)], dim=1)
         self.last = dict(J=traj_cost.numpy(), Q=Q.numpy(), rollouts=rollout.numpy(), elite_idx=np.stack(elite_log), J_iters=np.stack(cost_log))
         self.count += 1  # :110
         return self.u

@@ -109,7 +109,14 @@ CASES = {
     # MPPI tick (optimizer_mppi.py:192,195-197); CEM never calls the hook (optimizer_cem_tf.py), its rollouts start from the zero state
     "mppi_gru_n256": ("mppi", "GRU-6IN-32H1-32H2-5OUT-0", "default", _c(MPPI_BASE, num_rollouts=256), 4, True),
     "cem_gru_n256_k16": ("cem-tf", "GRU-6IN-32H1-32H2-5OUT-0", "default", _c(CEM_BASE, num_rollouts=256, cem_best_k=16, mpc_horizon=30), 2, False),
+    # a second environment through the functor registry -- Dubins car, 3 states, TWO control inputs
+    # (optimizer_mppi.py:173-175 / optimizer_cem_tf.py:64-65 sample [N, ., num_control_inputs])
+    "mppi_dubins_n512": ("mppi", "ODE", "default", _c(MPPI_BASE, num_rollouts=512, mpc_horizon=40, LBD=1.0, SQRTRHOINV=0.1, R=0.1), 4, True),
+    "mppi_dubins_h23_p5_n96": ("mppi", "ODE", "default", _c(MPPI_BASE, num_rollouts=96, mpc_horizon=23, LBD=0.5, SQRTRHOINV=0.08, R=0.1,
+                                                               period_interpolation_inducing_points=5), 3, False),
+    "cem_dubins_n512_k32": ("cem-tf", "ODE", "default", _c(CEM_BASE, num_rollouts=512, cem_best_k=32, mpc_horizon=40), 3, True),
 }
+ENV_OF_CASE = {"mppi_dubins_n512": "DubinsCar", "mppi_dubins_h23_p5_n96": "DubinsCar", "cem_dubins_n512_k32": "DubinsCar"}
 RESET_BEFORE_TICK = {"mppi_reset_mid_n64": 2, "rpgd_reset_mid_n32": 3, "cem_reset_mid_n128": 2}  # controller_reset() before that tick
 NOISE_SEED = 1
 STATE_SEED = 0
@@ -127,6 +134,9 @@ def run_reference_case(name: str) -> dict:
     import yaml
 
     opt_name, pred_spec, cost_name, cfg, ticks, keep_rollouts = CASES[name]
+    env = ENV_OF_CASE.get(name, "CartPole")
+    pw.ENVIRONMENT["name"] = env
+    nu = spec.DUBINS_NUM_CONTROLS if env == "DubinsCar" else 1
 
     # controller config is read at controller construction time (reference Controllers/__init__.py:39)
     cc = dict(mpc=dict(optimizer=opt_name, predictor_specification=pred_spec, cost_function_specification=cost_name,
@@ -144,8 +154,8 @@ def run_reference_case(name: str) -> dict:
     cm.config_optimizers[opt_name] = copy.deepcopy(cfg)  # optimizer kwargs (module-global dict loaded at import)
 
     ctrl = cm.controller_mpc(
-        environment_name="CartPole",
-        control_limits=(np.array([-1.0], np.float32), np.array([1.0], np.float32)),
+        environment_name=env,
+        control_limits=(np.full(nu, -1.0, np.float32), np.full(nu, 1.0, np.float32)),
         initial_environment_attributes={"target_position": 0.0, "target_equilibrium": 1.0},
     )
     ctrl.configure(optimizer_name=opt_name, predictor_specification=pred_spec)
@@ -170,8 +180,8 @@ def run_reference_case(name: str) -> dict:
 
         tfshim.argsort = _logging_argsort
 
-    states = spec.synthetic_states(ticks, STATE_SEED)
-    out = {"config": np.array(json.dumps(dict(case=name, optimizer=opt_name, predictor=pred_spec, cost=cost_name,
+    states = spec.dubins_synthetic_states(ticks, STATE_SEED) if env == "DubinsCar" else spec.synthetic_states(ticks, STATE_SEED)
+    out = {"config": np.array(json.dumps(dict(case=name, optimizer=opt_name, predictor=pred_spec, cost=cost_name, environment=env,
                                               cfg=cfg, ticks=ticks, noise_seed=NOISE_SEED, state_seed=STATE_SEED,
                                               mlp_seed=MLP_SEED, gru_seed=GRU_SEED, reset_before_tick=RESET_BEFORE_TICK.get(name, -1)))),
            "states": states}

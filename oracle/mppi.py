@@ -48,14 +48,15 @@ class MPPIOracle:
         self.n_ind = self.W.shape[0]
         # :130  SQRTRHODTINV = fp32( SQRTRHOINV * (1/sqrt(dt)) ) evaluated in float64
         self.SQRTRHODTINV = torch.tensor(np.float32(np.array(SQRTRHOINV) * (1 / np.sqrt(mpc_timestep))), dtype=dtype)
-        self.low = torch.tensor([action_low], dtype=dtype)
-        self.high = torch.tensor([action_high], dtype=dtype)
+        self.low = torch.as_tensor(np.atleast_1d(np.asarray(action_low, np.float32))).to(dtype)  # [nu] (Optimizers/__init__.py:42-44)
+        self.high = torch.as_tensor(np.atleast_1d(np.asarray(action_high, np.float32))).to(dtype)
+        self.nu = int(getattr(predictor, "num_control_inputs", 1))
         self.u = 0.0  # Optimizers/__init__.py:35 (constructor only)
         self.reset()
 
     def reset(self):
         # optimizer_mppi.py:227-231: ONLY u_nom is reset; self.u (the previous_input of the cost) keeps the last applied control
-        self.u_nom = 0.5 * (self.low + self.high) * torch.ones([1, self.H, 1], dtype=self.dtype)
+        self.u_nom = 0.5 * (self.low + self.high) * torch.ones([1, self.H, self.nu], dtype=self.dtype)
         self.last = {}
 
     def _interpolate(self, y):  # y [N, n_ind, 1] -> [N, H, 1]; Interpolator.py:97-106 (batched matmul per control)
@@ -66,7 +67,7 @@ class MPPIOracle:
         u_old = self.u
         s = s.repeat(self.N, 1)  # :182
         u_nom = torch.cat([self.u_nom[:, 1:, :], self.u_nom[:, -1:, :]], 1)  # :184
-        delta_u = rng.normal([self.N, self.n_ind, 1], dtype=torch.float32).to(self.dtype) * self.SQRTRHODTINV  # :173-175
+        delta_u = rng.normal([self.N, self.n_ind, self.nu], dtype=torch.float32).to(self.dtype) * self.SQRTRHODTINV  # :173-175
         delta_u = self._interpolate(delta_u)  # :177
         u_run = u_nom.repeat(self.N, 1, 1) + delta_u  # :186
         u_run = torch.minimum(torch.maximum(u_run, self.low), self.high)  # :187
@@ -96,7 +97,7 @@ class MPPIOracle:
         s1 = torch.as_tensor(np.asarray(s, np.float32)).to(self.dtype).reshape(1, -1)
         u_old = self.u
         u_nom = torch.cat([self.u_nom[:, 1:, :], self.u_nom[:, -1:, :]], 1)
-        z_all = rng.normal([self.N, self.n_ind, 1], dtype=torch.float32).to(self.dtype)
+        z_all = rng.normal([self.N, self.n_ind, self.nu], dtype=torch.float32).to(self.dtype)
         S_parts = []
         for c0 in range(0, self.N, chunk):
             z = z_all[c0:c0 + chunk]

@@ -15,13 +15,15 @@ from oracle import spec as _spec
 
 MLP_REGISTRY = {}
 GRU_REGISTRY = {}
+ENVIRONMENT = {"name": "CartPole"}  # SI_Toolkit takes the environment from its own configuration; the harness sets it per case
 ODE_PARAMS = {"intermediate_steps": 1}
 
 
 class PredictorWrapper:
     def __init__(self):
-        self.num_states = _spec.NUM_STATES
-        self.num_control_inputs = _spec.NUM_CONTROLS
+        dubins = ENVIRONMENT["name"] == "DubinsCar"
+        self.num_states = _spec.DUBINS_NUM_STATES if dubins else _spec.NUM_STATES
+        self.num_control_inputs = _spec.DUBINS_NUM_CONTROLS if dubins else _spec.NUM_CONTROLS
         self.predictor = None
         self.predictor_specification = None
 
@@ -32,7 +34,9 @@ class PredictorWrapper:
         self.dt = dt
         self.predictor_specification = predictor_specification
         name = str(predictor_specification)
-        if name.startswith("ODE"):
+        if name.startswith("ODE") and ENVIRONMENT["name"] == "DubinsCar":
+            self.predictor = _spec.DubinsPredictor(_spec.DubinsParams(dt=dt))
+        elif name.startswith("ODE"):
             self.predictor = _spec.ODEPredictor(_spec.CartPoleParams(dt=dt, intermediate_steps=ODE_PARAMS["intermediate_steps"]))
         elif name.startswith(("Dense", "MLP")):
             self.predictor = _spec.MLPPredictor(MLP_REGISTRY[name])

@@ -323,6 +323,108 @@ class GRUPredictor:
 
 
 # ----------------------------------------------------------------------------------------------
+# Second environment: a Dubins car (SURVEY 8f.3 "a second environment's ODE + cost to prove the functor registry"; the reference's
+# contract is any Control_Toolkit_ASF.Cost_Functions.<env>.<name>, Cost_Functions/cost_function_wrapper.py:59-66, and any
+# num_states / num_control_inputs, Optimizers/optimizer_mppi.py:173-175).  3 states [x, y, yaw], 2 controls [throttle, steer] in
+# [-1, 1]^2 -- so it also exercises num_control_inputs > 1.  Like the CartPole spec this arithmetic is the build's own pinned
+# specification (no environment code lives in /root/reference): parity unpinned upstream, pinned between oracle and CUDA.
+# ----------------------------------------------------------------------------------------------
+DUBINS_NUM_STATES = 3
+DUBINS_NUM_CONTROLS = 2
+
+
+@dataclass
+class DubinsParams:
+    v_max: float = 1.0
+    omega_max: float = 2.0
+    dt: float = 0.02
+
+    def f32(self) -> dict:
+        return dict(v_max=_f32(self.v_max), omega_max=_f32(self.omega_max), h=_f32(self.dt))
+
+
+def dubins_step(s: torch.Tensor, Q: torch.Tensor, c: dict) -> torch.Tensor:
+    """s [N,3] = [x, y, yaw], Q [N,2] = [throttle, steer]; explicit Euler with the OLD yaw, then the yaw is wrapped to (-pi, pi]."""
+    x, y, yaw = s.unbind(dim=1)
+    v = c["v_max"] * Q[:, 0]
+    w = c["omega_max"] * Q[:, 1]
+    x = x + (v * torch.cos(yaw)) * c["h"]
+    y = y + (v * torch.sin(yaw)) * c["h"]
+    yaw = yaw + w * c["h"]
+    yaw = torch.atan2(torch.sin(yaw), torch.cos(yaw))
+    return torch.stack([x, y, yaw], dim=1)
+
+
+class DubinsPredictor:
+    num_states = DUBINS_NUM_STATES
+    num_control_inputs = DUBINS_NUM_CONTROLS
+
+    def __init__(self, params: DubinsParams | None = None):
+        self.params = params or DubinsParams()
+        self.c = self.params.f32()
+
+    def predict_core(self, s: torch.Tensor, Q: torch.Tensor) -> torch.Tensor:
+        out = [s]
+        for t in range(Q.shape[1]):
+            s = dubins_step(s, Q[:, t, :], self.c)
+            out.append(s)
+        return torch.stack(out, dim=1)
+
+
+@dataclass
+class DubinsCost:
+    """``default`` cost of the Dubins car: squared distance to the target, a hard penalty inside a circular obstacle (an indicator,
+    like the CartPole track barrier), control effort and control change rate; terminal cost = weighted squared distance."""
+    name: str = "default"
+    dd_weight: float = 10.0
+    obstacle_weight: float = 1.0e4
+    cc_weight: float = 1.0
+    ccrc_weight: float = 1.0
+    R: float = 0.1
+    terminal_weight: float = 100.0
+    MAX_COST: float = 0.0
+    target_x: float = 1.0
+    target_y: float = 0.5
+    obstacle_x: float = 0.5
+    obstacle_y: float = 0.2
+    obstacle_r: float = 0.15
+
+    def f32(self) -> dict:
+        return dict(dd_weight=_f32(self.dd_weight), obstacle_weight=_f32(self.obstacle_weight), cc_weight=_f32(self.cc_weight),
+                    ccrc_weight=_f32(self.ccrc_weight), R=_f32(self.R), terminal_weight=_f32(self.terminal_weight),
+                    MAX_COST=_f32(self.MAX_COST), target_x=_f32(self.target_x), target_y=_f32(self.target_y),
+                    obstacle_x=_f32(self.obstacle_x), obstacle_y=_f32(self.obstacle_y), obstacle_r2=_f32(self.obstacle_r * self.obstacle_r))
+
+    def stage_cost(self, states: torch.Tensor, inputs: torch.Tensor, previous_input) -> torch.Tensor:
+        """states [N,H,3], inputs [N,H,2], previous_input scalar / [2] -> [N,H]."""
+        c = self.f32()
+        previous_input = torch.as_tensor(previous_input).to(states.dtype)
+        dx = states[:, :, 0] - c["target_x"]
+        dy = states[:, :, 1] - c["target_y"]
+        dd = c["dd_weight"] * (dx * dx + dy * dy)
+        ox = states[:, :, 0] - c["obstacle_x"]
+        oy = states[:, :, 1] - c["obstacle_y"]
+        obs = c["obstacle_weight"] * ((ox * ox + oy * oy) < c["obstacle_r2"]).to(states.dtype)
+        cc = c["cc_weight"] * _CC_cost(inputs, c)
+        ccrc = c["ccrc_weight"] * _control_change_rate_cost(inputs, previous_input)
+        return dd + obs + cc + ccrc
+
+    def terminal_cost(self, terminal_states: torch.Tensor) -> torch.Tensor:
+        c = self.f32()
+        dx = terminal_states[:, 0] - c["target_x"]
+        dy = terminal_states[:, 1] - c["target_y"]
+        return c["terminal_weight"] * (dx * dx + dy * dy)
+
+
+def dubins_synthetic_states(n: int, seed: int = 0) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-0.2, 0.2, n)
+    y = rng.uniform(-0.2, 0.2, n)
+    yaw = rng.uniform(-math.pi, math.pi, n)
+    return np.stack([x, y, yaw], 1).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------
 # Cost functions
 # ----------------------------------------------------------------------------------------------
 def _distance_difference_cost(position, c):
@@ -374,6 +476,10 @@ def terminal_cost(terminal_states: torch.Tensor, cp: CostParams) -> torch.Tensor
 def trajectory_cost(state_horizon: torch.Tensor, inputs: torch.Tensor, previous_input, cp: CostParams) -> torch.Tensor:
     """Restates reference ``Cost_Functions/__init__.py:74-93``:
     mean over H+1 of [stage costs (s_0..s_{H-1} with u_0..u_{H-1}) - MAX_COST, terminal cost(s_H)]."""
+    if hasattr(cp, "stage_cost"):  # an environment that brings its own cost class (DubinsCost)
+        sc = cp.stage_cost(state_horizon[:, :-1, :], inputs, previous_input) - cp.f32()["MAX_COST"]
+        tc = cp.terminal_cost(state_horizon[:, -1, :]).reshape(-1, 1)
+        return torch.mean(torch.cat([sc, tc], 1), 1)
     sc = stage_cost(state_horizon[:, :-1, :], inputs, previous_input, cp) - cp.f32()["MAX_COST"]
     tc = terminal_cost(state_horizon[:, -1, :], cp).reshape(-1, 1)
     return torch.mean(torch.cat([sc, tc], 1), 1)

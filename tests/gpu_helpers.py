@@ -25,9 +25,11 @@ def make_controller(meta, logging=True, rng="replay", shard=None, **optimizer_ov
     cfg.update(optimizer_over)
     if shard is not None:
         cfg["shard"] = shard
+    env = meta.get("environment", "CartPole")
+    nu = 2 if env == "DubinsCar" else 1
     ctrl = controller_mpc(
-        environment_name="CartPole",
-        control_limits=(np.array([-1.0], np.float32), np.array([1.0], np.float32)),
+        environment_name=env,
+        control_limits=(np.full(nu, -1.0, np.float32), np.full(nu, 1.0, np.float32)),
         initial_environment_attributes={"target_position": 0.0, "target_equilibrium": 1.0},
         config_controller=dict(optimizer=meta["optimizer"], predictor_specification=meta["predictor"],
                                cost_function_specification=meta["cost"], controller_logging=logging,

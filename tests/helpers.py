@@ -27,6 +27,8 @@ def load_golden(name):
 
 
 def make_predictor(meta):
+    if meta.get("environment", "CartPole") == "DubinsCar":
+        return spec.DubinsPredictor(spec.DubinsParams(dt=meta["cfg"]["mpc_timestep"]))
     if meta["predictor"].startswith("ODE"):
         return spec.ODEPredictor(spec.CartPoleParams(dt=meta["cfg"]["mpc_timestep"]))
     if meta["predictor"].startswith("GRU"):
@@ -39,6 +41,11 @@ def make_oracle(meta, **over):
     cost = spec.CostParams(name=meta["cost"])
     cfg = dict(meta["cfg"])
     cfg.update(over)
+    if meta.get("environment", "CartPole") == "DubinsCar":
+        cost = spec.DubinsCost(name=meta["cost"])
+        nu = spec.DUBINS_NUM_CONTROLS
+        cfg.setdefault("action_low", np.full(nu, -1.0, np.float32))
+        cfg.setdefault("action_high", np.full(nu, 1.0, np.float32))
     cls = {"mppi": MPPIOracle, "cem-tf": CEMOracle, "rpgd": RPGDOracle, "random-action-tf": RandomActionOracle,
            "gradient-tf": GradientOracle, "cem-naive-grad-tf": CEMNaiveGradOracle, "cem-grad-bharadhwaj-tf": CEMBharadhwajOracle}[meta["optimizer"]]
     return cls(pred, cost, **cfg)

@@ -114,7 +114,7 @@ def test_mppi_matches_reference_golden(name):
         e_J = max_elem_rel(opt.logging_values["J_logged"], z[f"J_{t}"])
         _report(f"{name} tick {t}: u {e_u:.2e} u_nom {e_nom:.2e} J {e_J:.2e} | fp32 floor: u {floors[t]['u']:.2e} "
                 f"state {floors[t]['state']:.2e} J {floors[t]['J']:.2e}")
-        assert np.ndim(u) == 0  # reference optimizer_mppi.py:212 squeezes to 0-d
+        assert np.shape(u) == np.shape(np.squeeze(z[f"u_{t}"]))  # reference optimizer_mppi.py:212 squeezes: 0-d for nu == 1, (nu,) otherwise
         assert e_u < tol_u and e_nom < tol_s, (name, t, e_u, e_nom, floors[t])
         _assert_symmetric(opt.u_nom, floors[t], f"{name} tick {t}")
         _check_J(opt.logging_values["J_logged"], z[f"J_{t}"], floors[t], (name, t))
@@ -127,12 +127,12 @@ def test_mppi_matches_reference_golden(name):
             # injected noise -> sampled controls are bit-exact up to the interpolation matmul's rounding
             e_Q = max_rel(opt.logging_values["Q_logged"], z["Q_logged_0"])
             e_tr = max(max_rel(opt.logging_values["rollout_trajectories_logged"][..., c], z["rollouts_0"][..., c])
-                       for c in range(6))
+                       for c in range(z["rollouts_0"].shape[-1]))
             _report(f"{name} tick 0: Q_logged {e_Q:.2e} rollouts {e_tr:.2e}")
             assert e_Q < 1e-6 and e_tr < TOL_TRAJ, (e_Q, e_tr)
     out = ctrl.get_outputs()
-    assert out["Q_logged"].shape == (meta["ticks"], opt.num_rollouts, opt.mpc_horizon, 1)
-    assert out["rollout_trajectories_logged"].shape == (meta["ticks"], opt.num_rollouts, opt.mpc_horizon + 1, 6)
+    assert out["Q_logged"].shape == (meta["ticks"], opt.num_rollouts, opt.mpc_horizon, opt.num_control_inputs)
+    assert out["rollout_trajectories_logged"].shape == (meta["ticks"], opt.num_rollouts, opt.mpc_horizon + 1, opt.num_states)
 
 
 @pytest.mark.parametrize("name", [n for n in golden_names("mppi_") if "mlp" in n])

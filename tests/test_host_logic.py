@@ -28,7 +28,7 @@ def test_registry_fails_loudly_for_unregistered_names():
     with pytest.raises(ValueError):
         specs.resolve_cost("Pendulum", "default")
     with pytest.raises(ValueError):
-        specs.resolve_predictor("CartPole", "GRU-6IN-32H1-32H2-5OUT-0")
+        specs.resolve_predictor("CartPole", "LSTM-6IN-32H1-32H2-5OUT-0")
     assert specs.resolve_cost("CartPole", "quadratic-boundary-grad").kind == 1  # '-' <-> '_' like the reference
 
 
@@ -123,3 +123,35 @@ def test_interpolation_inducing_point_count():
     """reference others/Interpolator.py:79-84"""
     for H, p, n in ((50, 10, 6), (100, 10, 11), (43, 10, 6), (20, 1, 20), (35, 10, 5), (41, 10, 5), (1, 10, 1)):
         assert int(math.ceil((H - 1) / p) + 1) == n
+
+
+def test_environment_registry_second_environment_and_recurrent_predictor():
+    """SURVEY 8f.3: the functor registry knows a second environment (Dubins car: 3 states, 2 control inputs) and a recurrent predictor;
+    the product-side specs (control_toolkit_b200.specs) and the oracle's (oracle/spec.py) are written independently and must agree;
+    anything unregistered raises instead of falling back."""
+    import pytest
+    from control_toolkit_b200 import specs
+    from oracle import spec as ospec
+    info = specs.environment_info("DubinsCar")
+    assert (info.num_states, info.num_control_inputs) == (ospec.DUBINS_NUM_STATES, ospec.DUBINS_NUM_CONTROLS) == (3, 2)
+    with pytest.raises(ValueError):
+        specs.environment_info("Acrobot")
+    with pytest.raises(ValueError):
+        specs.resolve_cost("DubinsCar", "quadratic_boundary_grad")  # registered for the CartPole only
+    kind, ode = specs.resolve_predictor("DubinsCar", "ODE")
+    cost = specs.resolve_cost("DubinsCar", "default", {"dd_weight": 12.0, "unknown_key": 1.0})
+    assert cost.dd_weight == 12.0
+    p = specs.dubins_env_params(ode, specs.resolve_cost("DubinsCar", "default"), 0.02)
+    oc, od = ospec.DubinsCost().f32(), ospec.DubinsParams(dt=0.02).f32()
+    expect = [od["h"], od["v_max"], od["omega_max"], oc["dd_weight"], oc["obstacle_weight"], np.float32(oc["cc_weight"]) * np.float32(oc["R"]),
+              oc["ccrc_weight"], oc["terminal_weight"], oc["target_x"], oc["target_y"], oc["obstacle_x"], oc["obstacle_y"], oc["obstacle_r2"], oc["MAX_COST"]]
+    np.testing.assert_array_equal(p, np.array(expect, np.float32))
+    # recurrent predictor: same draws, same order, same scaling on both sides
+    a, b = specs.GRUSpec.random_init(3), ospec.GRUWeights.random_init(3)
+    for k in ("Wi1", "Wh1", "bi1", "bh1", "Wi2", "Wh2", "bi2", "bh2", "W3", "b3"):
+        np.testing.assert_array_equal(getattr(a, k), getattr(b, k))
+    specs.register_gru("GRU-6IN-32H1-32H2-5OUT-0", a)
+    from control_toolkit_b200 import _lib as L
+    assert specs.resolve_predictor("CartPole", "GRU-6IN-32H1-32H2-5OUT-0")[0] == L.PRED_GRU
+    with pytest.raises(ValueError):
+        specs.GRUSpec(**{**{k: getattr(a, k) for k in a._KEYS}, "W3": np.zeros((32, 4), np.float32)})
