@@ -354,13 +354,14 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
     }
     h->mppi_rpb = h->mppi_block;
     if (pred_id(h) >= 2 && pred_id(h) <= 4) {  // tcgen05 MLP engines: 16 worker warps + 1 MMA-issuer warp on the 128 rollouts of one MMA tile (ctk_mlp_tc.cuh)
-      h->mppi_block = mppi_max_block_threads(2); h->mppi_rpb = 128;
-      const int per_sm = pred_id(h) >= 3 ? 2 : 1;  // the single-product engines keep two tiles (CTAs) in flight per SM
-      h->mppi_grid = (int)std::min<long long>((long long)per_sm * h->num_sms, ((long long)N + 127) / 128);
+      const bool pipe = pred_id(h) >= 3;  // single-product engines: one CTA per SM, four 128-rollout tiles in flight (one per warp group),
+                                          // every CTA an equal contiguous share of the population (MlpTcFastPredT::kBalanced)
+      h->mppi_block = mppi_max_block_threads(pred_id(h)); h->mppi_rpb = pipe ? 512 : 128;
+      h->mppi_grid = (int)std::min<long long>((long long)h->num_sms, ((long long)N + 127) / 128);
       if (h->mppi_grid < 1) h->mppi_grid = 1;
-      h->mppi_iters = (int)((N + (long long)h->mppi_grid * 128 - 1) / ((long long)h->mppi_grid * 128));
-      h->mppi_stash = ((size_t)h->n_ind * 128 * sizeof(float) <= 8 * 1024) ? 1 : 0;
-      if ((size_t)h->n_ind * 128 * sizeof(float) > 8 * 1024) { ctk_destroy(h); return fail(CTK_EINVAL, "tcgen05 MLP engine: too many inducing points (shared memory is taken by the operand tiles)"); }
+      h->mppi_iters = (int)((N + (long long)h->mppi_grid * h->mppi_rpb - 1) / ((long long)h->mppi_grid * h->mppi_rpb));
+      h->mppi_stash = (!pipe && (size_t)h->n_ind * 128 * sizeof(float) <= 8 * 1024) ? 1 : 0;
+      if ((size_t)h->n_ind * h->mppi_rpb * sizeof(float) > (pipe ? 32 : 8) * 1024) { ctk_destroy(h); return fail(CTK_EINVAL, "tcgen05 MLP engine: too many inducing points (shared memory is taken by the operand tiles)"); }
     }
     A(dalloc(&h->d_u_nom, (size_t)H * B), "u_nom");
     h->partials_stride = (size_t)(h->num_sms > h->mppi_grid ? h->num_sms : h->mppi_grid) * (h->mppi_iters + 1) * (h->n_ind + 2);
@@ -496,6 +497,29 @@ extern "C" int ctk_set_mlp_weights(ctk_handle* h, const ctk_mlp_weights* w) {
     for (int k = 0; k < 5; ++k) for (int j = 0; j < 128; ++j) f[k * 128 + j] = w->W3[j * 5 + k];
     f += 5 * 128;
     memcpy(f, w->b3, sizeof(float) * 5);
+    {  // B1: layer 1 on the tensor core (single-product engines).  Row n = hidden unit, K = 48: [w1 w1 w1 w2 w2 w3] of W1[:, n] (six
+       // inputs each), the three terms of b1[n], zeros -- against the operand row [x1 x2 x3 x1 x2 x1 | 1 1 1 | 0 ..] of the kernel
+      uint8_t* b1t = tc.data() + 3 * kTcTileBytes + kTcBlobFloats * 4;
+      auto put = [&](int n, int k, uint16_t v) { memcpy(b1t + tc_tile_offset(n, k), &v, 2); };
+      for (int n = 0; n < 128; ++n) {
+        uint16_t t[6][3];
+        for (int i = 0; i < 6; ++i) {
+          const float wv = w->W1[i * 128 + n];
+          t[i][0] = bf16_rn(wv); const float r1 = wv - bf16_f(t[i][0]);
+          t[i][1] = bf16_rn(r1); const float r2 = r1 - bf16_f(t[i][1]);
+          t[i][2] = bf16_rn(r2);
+        }
+        for (int i = 0; i < 6; ++i) {
+          put(n, i, t[i][0]); put(n, 6 + i, t[i][0]); put(n, 12 + i, t[i][0]);
+          put(n, 18 + i, t[i][1]); put(n, 24 + i, t[i][1]);
+          put(n, 30 + i, t[i][2]);
+        }
+        const float bv = w->b1[n];
+        const uint16_t c1 = bf16_rn(bv); const float q1 = bv - bf16_f(c1);
+        const uint16_t c2 = bf16_rn(q1); const float q2 = q1 - bf16_f(c2);
+        put(n, 36, c1); put(n, 37, c2); put(n, 38, bf16_rn(q2));
+      }
+    }
     if (h->d_mlp_tc) { cudaFree(h->d_mlp_tc); h->d_mlp_tc = nullptr; }
     CU(cudaMalloc(&h->d_mlp_tc, kTcBlobBytes));
     CU(cudaMemcpy(h->d_mlp_tc, tc.data(), kTcBlobBytes, cudaMemcpyHostToDevice));

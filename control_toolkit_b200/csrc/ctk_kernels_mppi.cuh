@@ -299,15 +299,19 @@ __global__ void __launch_bounds__(Pred::kMaxThreads, Pred::kMinBlocks) mppi_roll
   float rho_t = INFINITY, a_t = 0.0f;
   const uint32_t a_unom = smem_u32(sh_unom), a_w = smem_u32(sh_w);
 
-  for (int base = blockIdx.x * rpb; base < a.N; base += stride) {
+  // rollouts of this block: grid-stride passes of rpb rollouts, or (kBalanced) the block's contiguous, equal share of the population
+  const int r_end = Pred::kBalanced ? (int)(((long long)blockIdx.x + 1) * a.N / gridDim.x) : a.N;
+  const int r_first = Pred::kBalanced ? (int)((long long)blockIdx.x * a.N / gridDim.x) : (int)blockIdx.x * rpb;
+  const int r_stride = Pred::kBalanced ? rpb : stride;
+  for (int base = r_first; base < r_end; base += r_stride) {
     const int n = base + tid;
-    const bool active = owner && n < a.N;
+    const bool active = owner && n < r_end;
     const uint32_t ng = (uint32_t)(a.off + (active ? n : 0));
     float S = INFINITY;
-    if (active || Pred::kCooperative) {
+    if (active || (Pred::kCooperative && pred.group_active(base, r_end))) {
       State z = z0;
       float omc = omc0, u_last = u_prev0, acc = 0.0f;
-      pred.begin_rollout();  // recurrent predictors: restore the saved hidden state
+      pred.begin_rollout(active);  // recurrent predictors: restore the saved hidden state; tile engines: is this row a real rollout
       const int nlog = active ? n : 0;
       // inducing-point draws arrive four at a time (one Philox block); zq is a rotating window, zq[0] = next draw
       float zq[4];

@@ -35,7 +35,10 @@ constexpr uint32_t kTcMnStride = 128;             // bytes between 8-row groups 
 __host__ __device__ inline uint32_t tc_tile_offset(int row, int k) { return (uint32_t)(k >> 3) * kTcKStride + (uint32_t)row * 16u + (uint32_t)(k & 7) * 2u; }
 // device blob: W2 split tiles [3][32768 B] | W1 [6][128] | b1 [128] | b2 [128] | W3T [5][128] | b3 [8]   (floats after the tiles)
 constexpr uint32_t kTcBlobFloats = 6 * 128 + 128 + 128 + 5 * 128 + 8;
-constexpr uint32_t kTcBlobBytes = 3 * kTcTileBytes + kTcBlobFloats * 4;
+// ... | B1 [6 k-groups][128 n][8] bf16 (single-product engines: layer 1 on the tensor core, see MlpTcFastPredT): rows of
+// K = 48: W1 term 1 three times (x1, x2, x3), W1 term 2 twice (x1, x2), W1 term 3 (x1), the three terms of b1 (against 1.0), zeros
+constexpr uint32_t kTcB1Bytes = 6 * kTcKStride;
+constexpr uint32_t kTcBlobBytes = 3 * kTcTileBytes + kTcBlobFloats * 4 + kTcB1Bytes;
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
@@ -51,6 +54,7 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 
 struct MlpTcPred {
   static constexpr bool kCooperative = true;  // every thread of the CTA must call step() the same number of times
+  static constexpr bool kBalanced = false;
   static constexpr int kMaxThreads = 544;  // 16 worker warps + 1 MMA-issuer warp
   static constexpr int kMinBlocks = 1;
   static constexpr int kRolloutsPerBlock = 128;  // threads 128..543 are helpers: they own no rollout
@@ -113,7 +117,8 @@ struct MlpTcPred {
   __device__ __forceinline__ void substep(State& z, float u, float& omc) { step(z, u, omc); }
   __device__ __forceinline__ bool single_substep() const { return false; }
   __device__ __forceinline__ void use_uniform(const HotUK&) {}
-  __device__ __forceinline__ void begin_rollout() {}
+  __device__ __forceinline__ void begin_rollout(bool = true) {}
+  __device__ __forceinline__ bool group_active(int, int) const { return true; }
 
   // tanh(x) = 1 - 2 / (exp(2x) + 1) for either sign (x -> -inf: e -> 0, t -> -1; x -> +inf: e -> inf, r -> 0, t -> 1):
   // FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA.  Absolute error <= ~3e-7 (the two MUFU approximations), the same bound the
@@ -303,38 +308,62 @@ struct MlpTcPred {
 // ---------------------------------------------------------------------------------------------------------------
 // Opt-in reduced-precision engines of the same predictor (SURVEY section 7 hard part 4: "ship exact and fast variants, report both"):
 // layer 2 as ONE bf16 product (h1 and W2 rounded to bfloat16, round to nearest even; fp32 accumulation in TMEM) -- 8 UMMAs per
-// step instead of 48, one 32 KB operand tile per side instead of three, so TWO CTAs (two 128-rollout tiles) are resident per SM
-// and one tile's MMAs / barriers run underneath the other's FP32 and MUFU stages.  APPROX = false ("tcgen05_bf16"): tanh as in
-// the exact engine; parity is defined against an oracle that applies the same operand rounding (oracle/spec.py MLPPredictor
-// bf16_layer2).  APPROX = true ("tcgen05_fast"): tanh by the single-instruction MUFU.TANH (tanh.approx.f32, ~2^-11 relative):
-// half the MUFU work; reported against the exact engine, not held to a parity bound.
+// step instead of 48, one 32 KB operand tile per side instead of three.  APPROX = false ("tcgen05_bf16"): tanh as in the exact
+// engine; parity is defined against an oracle that applies the same operand rounding (oracle/spec.py MLPPredictor bf16_layer2).
+// APPROX = true ("tcgen05_fast"): tanh by the single-instruction MUFU.TANH (tanh.approx.f32, ~2^-11 relative): half the MUFU work;
+// reported against the exact engine, not held to a parity bound.
+//
+// Structure (round 2): ONE CTA per SM with FOUR 128-rollout tiles in flight, one per warp group (4 warps = 128 threads = the M
+// dimension of an MMA).  A thread owns its rollout completely -- layer 1 for all 128 hidden units of its row, its row of the A tile,
+// its accumulator row out of TMEM, layer 3, the state update and the cost -- so there is no partial-sum exchange, no input broadcast
+// and NO block-wide barrier inside a step: a group synchronises only with itself (two named barriers of 128 threads and the
+// mbarrier its own MMAs commit to).  The four groups drift apart by construction, so one group's MUFU / FP32 stages run underneath
+// another's UMMAs and TMEM loads (the first version of this engine ran the tensor core, the MUFU and the FP32 pipe mostly one after
+// another: 27 % of the stall samples on block barriers, profiles/prof_mlp_tc_r01c_summary.txt).  Each CTA takes an equal share of the
+// population (kBalanced: 65536 rollouts / 148 SMs = 442.8 -> 14 warps of rows per SM; warps without rows skip the arithmetic), which
+// removes the 3.46-waves tail of 512 tiles on 148 SMs.  TMEM: the CTA allocates all 512 columns, 128 per group.
+// Layer 1 (6 -> 128) runs on the tensor core too, at fp32-level accuracy: the thread splits its six inputs into three bf16 terms and
+// writes ONE 96-byte operand row [x1 x2 x3 x1 x2 x1 | 1 1 1 | 0..] (K = 48); against B1 = [w1 w1 w1 w2 w2 w3 | b1 terms | 0..] three
+// K16 UMMAs deliver the six significant products of the split plus the bias -- 900 FP32-pipe instructions per rollout-step less
+// (the loaded SM sub-partitions were issue-bound: 4 warps x 2700 instructions per step, profiles/prof_mlp_tc_r02a_pipe_fast_summary.txt).
 // ---------------------------------------------------------------------------------------------------------------
 template <bool APPROX>
 struct MlpTcFastPredT {
-  static constexpr bool kCooperative = true;
-  static constexpr int kMaxThreads = 544;  // 16 worker warps + 1 MMA-issuer warp
-  static constexpr int kMinBlocks = 2;     // two tiles in flight per SM
-  static constexpr int kRolloutsPerBlock = 128;
-  uint8_t* sA;        // [32768] bf16 tile of h1 (written per step); reused for the layer-3 partial sums
-  float* sx;          // [128][8] network inputs of the rows (owners -> helpers)
-  uint8_t* sB;        // [32768] W2 rounded to bf16 (resident)
+  static constexpr bool kCooperative = true;   // every thread of an ACTIVE group must call step() the same number of times
+  static constexpr bool kBalanced = true;      // CTA b rolls out the contiguous share [b N / grid, (b + 1) N / grid) of the population
+  static constexpr int kMaxThreads = 512;      // 4 warp groups x 128 threads, every thread owns a rollout
+  static constexpr int kMinBlocks = 1;
+  static constexpr int kRolloutsPerBlock = 512;
+  uint8_t* sA;        // this group's bf16 tile of h1 [32768]
+  uint8_t* sB;        // [32768] W2 rounded to bf16 (resident, shared by the groups)
   const float *W1, *b1, *b2, *W3T, *b3;
-  uint64_t* mbar;
+  uint64_t* mbar;     // this group's MMA-completion barrier
   uint32_t* tmem_slot;
   uint32_t phase;
+  bool row_on;        // this thread's rollout is a real one (warps without any skip the arithmetic of a step)
 
-  static size_t smem_floats(const MlpDev&) { return (2 * (size_t)kTcTileBytes + kTcBlobFloats * 4 + 64 + 128 * 8 * 4 + 1024) / 4; }
+  uint8_t* sB1;       // [12288] layer-1 operand (W1 / b1 split terms, resident, shared by the groups)
+
+  static size_t smem_floats(const MlpDev&) { return (5 * (size_t)kTcTileBytes + kTcB1Bytes + kTcBlobFloats * 4 + 64 + 1024) / 4; }
 
   __device__ __forceinline__ MlpTcFastPredT(const DevConsts*, const MlpDev& m, float* sm) {
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)sm + 1023) & ~(uintptr_t)1023);
-    sA = base;
-    sB = base + kTcTileBytes;
-    float* f = reinterpret_cast<float*>(sB + kTcTileBytes);
+    const int g = threadIdx.x >> 7;
+    sA = base + (size_t)g * kTcTileBytes;
+    sB = base + 4 * (size_t)kTcTileBytes;
+    sB1 = sB + kTcTileBytes;
+    {
+      const uint4* src1 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(m.tc_blob) + 3 * kTcTileBytes + kTcBlobFloats * 4);
+      uint4* dst1 = reinterpret_cast<uint4*>(sB1);
+      for (int i = threadIdx.x; i < (int)(kTcB1Bytes / 16); i += blockDim.x) dst1[i] = src1[i];
+    }
+    float* f = reinterpret_cast<float*>(sB1 + kTcB1Bytes);
     W1 = f; b1 = W1 + 6 * 128; b2 = b1 + 128; W3T = b2 + 128; b3 = W3T + 5 * 128;
-    mbar = reinterpret_cast<uint64_t*>(f + kTcBlobFloats);
-    tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
-    sx = f + kTcBlobFloats + 16;
+    uint64_t* mb0 = reinterpret_cast<uint64_t*>(f + kTcBlobFloats);  // [4]
+    mbar = mb0 + g;
+    tmem_slot = reinterpret_cast<uint32_t*>(mb0 + 4);
     phase = 0;
+    row_on = true;
     // blob: [3 split tiles of W2][floats]; tile 0 is bf16_rn(W2), the float block follows the three tiles
     const uint4* src = reinterpret_cast<const uint4*>(m.tc_blob);
     uint4* dst = reinterpret_cast<uint4*>(sB);
@@ -342,12 +371,10 @@ struct MlpTcFastPredT {
     const uint4* srcf = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(m.tc_blob) + 3 * kTcTileBytes);
     uint4* dstf = reinterpret_cast<uint4*>(f);
     for (int i = threadIdx.x; i < (int)(kTcBlobFloats * 4 / 16); i += blockDim.x) dstf[i] = srcf[i];
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if ((threadIdx.x >> 5) == 0) {  // 128 TMEM columns per CTA (two CTAs per SM: 256 of 512)
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    if (threadIdx.x < 4) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mb0 + threadIdx.x)) : "memory");
+    if (threadIdx.x == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if ((threadIdx.x >> 5) == 0) {  // the CTA owns the SM: all 512 TMEM columns, 128 per group
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -359,13 +386,15 @@ struct MlpTcFastPredT {
     __syncthreads();
     if ((threadIdx.x >> 5) == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(*tmem_slot) : "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*tmem_slot) : "memory");
     }
   }
   __device__ __forceinline__ void substep(State& z, float u, float& omc) { step(z, u, omc); }
   __device__ __forceinline__ bool single_substep() const { return false; }
   __device__ __forceinline__ void use_uniform(const HotUK&) {}
-  __device__ __forceinline__ void begin_rollout() {}
+  __device__ __forceinline__ void begin_rollout(bool active = true) { row_on = active; }
+  // a group runs a pass of the rollout loop iff its first row is a real rollout (group-uniform: the group's barriers stay matched)
+  __device__ __forceinline__ bool group_active(int base, int end) const { return base + (int)(threadIdx.x & ~127u) < end; }
 
   static __device__ __forceinline__ float act(float x) {
     if (APPROX) {
@@ -382,100 +411,98 @@ struct MlpTcFastPredT {
   }
 
   __device__ __forceinline__ void step(State& z, float u, float& omc) {
-    const int tid = threadIdx.x, row = tid & 127, q = tid >> 7;
-    const uint32_t aW1 = smem_u32(W1), ab1 = smem_u32(b1), ab2 = smem_u32(b2), aW3 = smem_u32(W3T);
-    if (tid >= 512) {
-      // ===== MMA issuer warp: 2 UMMAs (K = 32) per quarter of the operand tile, as soon as the workers have written it =====
-      __syncthreads();  // (S1)
-      const uint32_t tmem_i = *tmem_slot;
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-      uint32_t acc = 0;
-#pragma unroll 1
-      for (int p = 0; p < 4; ++p) {
-        asm volatile("bar.sync %0, 544;" ::"r"(1 + p) : "memory");
-        if (tid == 512) {
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-          for (int kq = 0; kq < 2; ++kq) {
-            const uint32_t ks = (uint32_t)(2 * p + kq);
-            umma_bf16(tmem_i, umma_smem_desc(a0 + ks * 2 * kTcKStride), umma_smem_desc(b0 + ks * 2 * kTcKStride), idesc, acc);
-            acc = 1;
+    const int tid = threadIdx.x, g = tid >> 7, row = tid & 127, wq = (tid >> 5) & 3;
+    const uint32_t ab2 = smem_u32(b2), aW3 = smem_u32(W3T);
+    const bool warp_on = __any_sync(0xffffffffu, row_on);
+    const uint32_t arow = smem_u32(sA) + (uint32_t)row * 16u;
+    const uint32_t tmem_g = *tmem_slot + (uint32_t)g * 128u;
+    const uint32_t trow = tmem_g + ((uint32_t)(wq * 32) << 16);
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    // the group's first thread issues nk K16 UMMAs (A from the group's tile, B from b_base) and commits them to the group's mbarrier;
+    // one lane of the group's first warp waits for them, the other three warps sleep in the hardware barrier that follows
+    auto mma_round = [&](uint32_t b_base, int nk) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // operand rows -> visible to the tensor core (async proxy)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // (also orders this thread's TMEM loads before the new MMAs)
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");        // the group's operand tile is complete
+      if (row == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = smem_u32(sA);
+        for (int ks = 0; ks < nk; ++ks)
+          umma_bf16(tmem_g, umma_smem_desc(a0 + (uint32_t)ks * 2u * kTcKStride), umma_smem_desc(b_base + (uint32_t)ks * 2u * kTcKStride), idesc, ks > 0 ? 1u : 0u);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+      }
+      if (wq == 0) {
+        if ((tid & 31) == 0) {
+          uint32_t done = 0;
+          const uint32_t bar = smem_u32(mbar);
+          while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                         : "=r"(done) : "r"(bar), "r"(phase) : "memory");
           }
-          if (p == 3)
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
         }
         __syncwarp();
       }
-      {
-        uint32_t done = 0;
-        const uint32_t bar = smem_u32(mbar);
-        while (!done) {
-          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
-                       : "=r"(done) : "r"(bar), "r"(phase) : "memory");
-        }
-        phase ^= 1u;
-      }
+      phase ^= 1u;
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncthreads();  // (S2) accumulator complete
-      __syncthreads();  // (S3) partial sums exchanged
-      return;
+      asm volatile("bar.sync %0, 128;" ::"r"(5 + g) : "memory");        // the group's accumulator is complete
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+    // ---- layer 1 on the tensor core: this thread's operand row [x1 x2 x3 x1 x2 x1 | 1 1 1 | 0 ...] (three-term bf16 split of the
+    //      six inputs, K = 48 = six 16-byte k-groups of the K-major core-matrix layout) ----
+    if (warp_on) {
+      uint32_t p1[3], p2[3], p3[3];
+      MlpTcPred::split3(u, z.om, p1[0], p2[0], p3[0]);
+      MlpTcPred::split3(z.c, z.s, p1[1], p2[1], p3[1]);
+      MlpTcPred::split3(z.x, z.v, p1[2], p2[2], p3[2]);
+      auto sts4 = [&](int kg, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(arow + (uint32_t)kg * kTcKStride), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+      };
+      sts4(0, p1[0], p1[1], p1[2], p2[0]);          // k  0.. 7: x1[0..5] x2[0..1]
+      sts4(1, p2[1], p2[2], p3[0], p3[1]);          // k  8..15: x2[2..5] x3[0..3]
+      sts4(2, p3[2], p1[0], p1[1], p1[2]);          // k 16..23: x3[4..5] x1[0..5]
+      sts4(3, p2[0], p2[1], p2[2], p1[0]);          // k 24..31: x2[0..5] x1[0..1]
+      sts4(4, p1[1], p1[2], 0x3f803f80u, 0x00003f80u);  // k 32..39: x1[2..5] 1 1 1 0
+      sts4(5, 0u, 0u, 0u, 0u);                      // k 40..47
     }
-    if (q == 0) {
-      float4* d = reinterpret_cast<float4*>(sx + row * 8);
-      d[0] = make_float4(u, z.om, z.c, z.s);
-      d[1] = make_float4(z.x, z.v, 0.f, 0.f);
-    }
-    __syncthreads();  // (S1)
-    float x[6];
-    {
-      const float4 v0 = MlpTcPred::lds4(smem_u32(sx + row * 8)), v1 = MlpTcPred::lds4(smem_u32(sx + row * 8 + 4));
-      x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y;
-    }
-    const uint32_t arow = smem_u32(sA) + (uint32_t)row * 16u;
+    mma_round(smem_u32(sB1), 3);
+    // ---- accumulator row (x W1 + b1) -> activation -> bf16 -> this thread's row of the group's A tile ----
+    if (warp_on) {
+#pragma unroll 2
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        uint32_t v[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(trow + (uint32_t)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t pk[8];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const int kg = 4 * p + q;
-      uint32_t pk[4];
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const uint32_t jo = (uint32_t)(kg * 8 + half * 4) * 4u;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const float4 w = MlpTcPred::lds4(aW1 + (uint32_t)i * 512u + jo);
-          acc.x = fmaf(x[i], w.x, acc.x); acc.y = fmaf(x[i], w.y, acc.y); acc.z = fmaf(x[i], w.z, acc.z); acc.w = fmaf(x[i], w.w, acc.w);
-        }
-        const float4 bb = MlpTcPred::lds4(ab1 + jo);
-        pk[2 * half] = pack2(act(acc.x + bb.x), act(acc.y + bb.y));
-        pk[2 * half + 1] = pack2(act(acc.z + bb.z), act(acc.w + bb.w));
+        for (int j = 0; j < 8; ++j) pk[j] = pack2(act(__uint_as_float(v[2 * j])), act(__uint_as_float(v[2 * j + 1])));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(arow + (uint32_t)(c0 >> 3) * kTcKStride), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(arow + (uint32_t)((c0 >> 3) + 1) * kTcKStride), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
       }
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(arow + (uint32_t)kg * kTcKStride), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.arrive %0, 544;" ::"r"(1 + p) : "memory");
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();  // (S2)
-    const uint32_t tmem = *tmem_slot;
+    // ---- layer 2 on the tensor core: 8 UMMAs (M128 N128 K16) ----
+    mma_round(smem_u32(sB), 8);
+    if (!warp_on) return;
+    // ---- this thread's accumulator row -> bias + activation -> layer 3 -> next state ----
     float y[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    const uint32_t trow = tmem + ((uint32_t)(((tid >> 5) & 3) * 32) << 16);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-    for (int hh = 0; hh < 2; ++hh) {
-      const int c0 = q * 32 + hh * 16;
+#pragma unroll 2
+    for (int c0 = 0; c0 < 128; c0 += 16) {
       uint32_t v[16];
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
           : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
             "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-          : "r"(trow + c0));
+          : "r"(trow + (uint32_t)c0));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const uint32_t jo = (uint32_t)(c0 + g * 4) * 4u;
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint32_t jo = (uint32_t)(c0 + q4 * 4) * 4u;
         const float4 bb = MlpTcPred::lds4(ab2 + jo);
-        const float h0 = act(__uint_as_float(v[4 * g]) + bb.x), h1 = act(__uint_as_float(v[4 * g + 1]) + bb.y);
-        const float h2 = act(__uint_as_float(v[4 * g + 2]) + bb.z), h3 = act(__uint_as_float(v[4 * g + 3]) + bb.w);
+        const float h0 = act(__uint_as_float(v[4 * q4]) + bb.x), h1 = act(__uint_as_float(v[4 * q4 + 1]) + bb.y);
+        const float h2 = act(__uint_as_float(v[4 * q4 + 2]) + bb.z), h3 = act(__uint_as_float(v[4 * q4 + 3]) + bb.w);
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
           const float4 w = MlpTcPred::lds4(aW3 + (uint32_t)k * 512u + jo);
@@ -483,28 +510,13 @@ struct MlpTcFastPredT {
         }
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    float* sy = reinterpret_cast<float*>(sA);  // [3][128][8]: the operand tile is free (all MMAs of this step have completed)
-    if (q > 0) {
-      float4* d = reinterpret_cast<float4*>(sy + ((q - 1) * 128 + row) * 8);
-      d[0] = make_float4(y[0], y[1], y[2], y[3]);
-      d[1] = make_float4(y[4], 0.f, 0.f, 0.f);
-    }
-    __syncthreads();  // (S3)
-    if (q == 0) {
-#pragma unroll
-      for (int p = 0; p < 3; ++p) {
-        const float4 v0 = MlpTcPred::lds4(smem_u32(sy + (p * 128 + row) * 8)), v1 = MlpTcPred::lds4(smem_u32(sy + (p * 128 + row) * 8 + 4));
-        y[0] += v0.x; y[1] += v0.y; y[2] += v0.z; y[3] += v0.w; y[4] += v1.x;
-      }
-      z.om = y[0] + b3[0];
-      z.c = y[1] + b3[1];
-      z.s = y[2] + b3[2];
-      z.x = y[3] + b3[3];
-      z.v = y[4] + b3[4];
-      z.th = atan2f(z.s, z.c);
-      omc = 1.0f - z.c * rsqrtf(fmaf(z.c, z.c, z.s * z.s));
-    }
+    z.om = y[0] + b3[0];
+    z.c = y[1] + b3[1];
+    z.s = y[2] + b3[2];
+    z.x = y[3] + b3[3];
+    z.v = y[4] + b3[4];
+    z.th = atan2f(z.s, z.c);
+    omc = 1.0f - z.c * rsqrtf(fmaf(z.c, z.c, z.s * z.s));
   }
 };
 using MlpTcBf16Pred = MlpTcFastPredT<false>;

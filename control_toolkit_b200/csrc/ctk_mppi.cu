@@ -34,6 +34,7 @@ cudaError_t launch_mppi_rollout(int pred, int kind, bool log, int nblocks, int b
 // 5: the recurrent (GRU) predictor on the FP32 pipe
 int mppi_max_block_threads(int pred) {
   if (pred == 5) return GruSimtPred::kMaxThreads;
+  if (pred == 3 || pred == 4) return MlpTcBf16Pred::kMaxThreads;
   return pred == 0 ? OdePred::kMaxThreads : (pred >= 2 ? MlpTcPred::kMaxThreads : MlpSimtPred::kMaxThreads);
 }
 size_t mppi_pred_smem_floats(int pred, const MlpDev& m) {

@@ -26,7 +26,9 @@ struct OdePred {
   // intermediate_steps == 1 fast path (no sub-step loop in the rollout's inner loop)
   __device__ __forceinline__ void substep(State& z, float u, float& omc) const { ode_substep(z, u, p, omc); }
   __device__ __forceinline__ bool single_substep() const { return p.isteps == 1; }
-  __device__ __forceinline__ void begin_rollout() {}  // stateless predictor
+  __device__ __forceinline__ void begin_rollout(bool = true) {}  // stateless predictor
+  __device__ __forceinline__ bool group_active(int, int) const { return true; }
+  static constexpr bool kBalanced = false;
   static size_t smem_floats(const MlpDev&) { return 0; }
 };
 
@@ -65,7 +67,9 @@ struct MlpSimtPred {
   __device__ __forceinline__ void substep(State& z, float u, float& omc) const { step(z, u, omc); }
   __device__ __forceinline__ bool single_substep() const { return false; }
   __device__ __forceinline__ void use_uniform(const HotUK&) {}
-  __device__ __forceinline__ void begin_rollout() {}  // stateless predictor
+  __device__ __forceinline__ void begin_rollout(bool = true) {}  // stateless predictor
+  __device__ __forceinline__ bool group_active(int, int) const { return true; }
+  static constexpr bool kBalanced = false;
 
   // net input [Q, angleD, cos, sin, position, positionD] -> next [angleD, cos, sin, position, positionD];
   // angle = atan2(sin, cos)  (oracle/spec.py MLPPredictor.step)
@@ -155,8 +159,10 @@ struct GruSimtPred {
   __device__ __forceinline__ void substep(State& z, float u, float& omc) { step(z, u, omc); }
   __device__ __forceinline__ bool single_substep() const { return false; }
   __device__ __forceinline__ void use_uniform(const HotUK&) {}
+  __device__ __forceinline__ bool group_active(int, int) const { return true; }
+  static constexpr bool kBalanced = false;
   // every rollout starts from the saved hidden state (SI_Toolkit's autoregressive RNN predictor restores it before predict_core)
-  __device__ __forceinline__ void begin_rollout() {
+  __device__ __forceinline__ void begin_rollout(bool = true) {
     for (int l = 0; l < 2; ++l)
       for (int j = 0; j < hid; ++j) hs[(l * HMAX + j) * kMaxThreads] = h_saved[l * hid + j];
   }
