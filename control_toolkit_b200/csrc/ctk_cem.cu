@@ -1,5 +1,6 @@
 // ctk_cem.cu -- translation unit owning the CEM kernels (K3 rollout, K4 top-k levels, K5 refit).
 #include "ctk_kernels_cem.cuh"
+#include "ctk_mlp_tc.cuh"
 #include "ctk_launch.h"
 
 namespace ctk {
@@ -11,7 +12,7 @@ static cudaError_t launch_cem_t(int nblocks, size_t smem, cudaStream_t st, const
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  return launch_pdl(k, dim3(nblocks), dim3(128), smem, st, a);
+  return launch_pdl(k, dim3(nblocks), dim3(Pred::kCemThreads), smem, st, a);
 }
 template <class Pred>
 static cudaError_t launch_cem_p(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemArgs& a) {
@@ -20,6 +21,9 @@ static cudaError_t launch_cem_p(int kind, bool log, int nblocks, size_t smem, cu
 }
 cudaError_t launch_cem_rollout(int pred, int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemArgs& a) {
   if (pred == 5) return launch_cem_rollout_gru(kind, log, nblocks, smem, st, a);  // ctk_gru.cu
+  if (pred == 2) return launch_cem_p<MlpTcPred>(kind, log, nblocks, smem, st, a);      // the MLP predictor on the tcgen05 engines
+  if (pred == 3) return launch_cem_p<MlpTcBf16Pred>(kind, log, nblocks, smem, st, a);
+  if (pred == 4) return launch_cem_p<MlpTcFastPred>(kind, log, nblocks, smem, st, a);
   return pred == 0 ? launch_cem_p<OdePred>(kind, log, nblocks, smem, st, a) : launch_cem_p<MlpSimtPred>(kind, log, nblocks, smem, st, a);
 }
 cudaError_t launch_cem_ode(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemOdeArgs& a) {
@@ -61,6 +65,11 @@ cudaError_t launch_cem_tick(int kind, bool log, int nblocks, size_t smem, cudaSt
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, k, a);
+}
+// grid of the generic CEM rollout kernel: one block per 128 rollouts; the single-product tile engines run one CTA per SM with equal shares
+int cem_rollout_grid(int pred, int N, int num_sms) {
+  const int nb = (N + 127) / 128;
+  return (pred == 3 || pred == 4) ? (nb < num_sms ? nb : num_sms) : nb;
 }
 int cem_tick_rollouts_per_block() { return kCemTickRollouts; }
 // resident blocks per SM of the persistent tick kernel (its blocks wait for each other: the whole grid must be resident)

@@ -471,7 +471,7 @@ extern "C" int ctk_set_mlp_weights(ctk_handle* h, const ctk_mlp_weights* w) {
   if (h->cfg.mlp_engine != CTK_MLP_SIMT) {
     REQ(h->cfg.mlp_engine >= CTK_MLP_TCGEN05 && h->cfg.mlp_engine <= CTK_MLP_TCGEN05_FAST, "unknown mlp_engine");
     REQ(hid == kTcHidden, "the tcgen05 MLP engines are built for hidden == 128 (use mlp_engine=simt otherwise)");
-    REQ(h->cfg.optimizer == CTK_OPT_MPPI, "the tcgen05 MLP engines are implemented for MPPI (use mlp_engine=simt for CEM)");
+    REQ(h->cfg.optimizer == CTK_OPT_MPPI || h->cfg.optimizer == CTK_OPT_CEM, "the tcgen05 MLP engines are implemented for MPPI and CEM");
     // W2 as three bf16 terms (w = w1 + w2 + w3, round-to-nearest-even each), B operand tiles: row n = output unit, k = input unit
     std::vector<uint8_t> tc(kTcBlobBytes, 0);
     auto bf16_rn = [](float f) -> uint16_t {
@@ -767,7 +767,7 @@ static int env_step_host(ctk_handle* h, const float* s_host, float* u_out_host, 
 static int pred_id(const ctk_handle* h) {
   if (h->cfg.predictor == CTK_PRED_GRU) return 5;  // recurrent predictor on the FP32 pipe (GruSimtPred)
   if (h->cfg.predictor != CTK_PRED_MLP) return 0;
-  if (h->cfg.optimizer != CTK_OPT_MPPI) return 1;
+  if (h->cfg.optimizer == CTK_OPT_RPGD) return 1;
   switch (h->cfg.mlp_engine) {
     case CTK_MLP_TCGEN05: return 2;
     case CTK_MLP_TCGEN05_BF16: return 3;
@@ -1084,7 +1084,10 @@ static int cem_local(ctk_handle* h, const float* s_dev, bool to_k) {
     a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
     const size_t smem = sizeof(float) * (2 * (size_t)h->H + pred_smem_floats(h));
     KernelTimer kt(h);
-    e = launch_cem_rollout(pred_id(h), h->cost.kind, c.logging != 0, h->nblocks, smem, h->stream, a);
+    if (pred_id(h) >= 2 && pred_id(h) <= 4 && h->mlp.tc_blob == nullptr) return fail(CTK_ESTATE, "tcgen05 MLP engine without weights");
+    e = launch_cem_rollout(pred_id(h), h->cost.kind, c.logging != 0, cem_rollout_grid(pred_id(h), h->N, h->num_sms), smem, h->stream, a);
+    h->last_kernel = std::string("cem_rollout_kernel<") + (pred_id(h) == 5 ? "GruSimtPred" : pred_id(h) == 4 ? "MlpTcFastPred" : pred_id(h) == 3 ? "MlpTcBf16Pred" : pred_id(h) == 2 ? "MlpTcPred" : pred_id(h) == 1 ? "MlpSimtPred" : "OdePred") + "," +
+                     std::to_string(h->cost.kind) + "," + (c.logging ? "1" : "0") + ">" + (ns.inj ? " [injected noise]" : " [philox]");
   }
   if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("cem_rollout_kernel: ") + cudaGetErrorString(e));
   // K4: hierarchical bitonic top-k

@@ -28,7 +28,7 @@ static cudaError_t launch_cem_gru_t(int nblocks, size_t smem, cudaStream_t st, c
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  return launch_pdl(k, dim3(nblocks), dim3(128), smem, st, a);
+  return launch_pdl(k, dim3(nblocks), dim3(GruSimtPred::kCemThreads), smem, st, a);
 }
 cudaError_t launch_cem_rollout_gru(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemArgs& a) {
   if (kind == 0) return log ? launch_cem_gru_t<0, true>(nblocks, smem, st, a) : launch_cem_gru_t<0, false>(nblocks, smem, st, a);

@@ -13,8 +13,11 @@ __device__ __forceinline__ float cem_sample(float mu, float sd, float z, float l
   return fminf(fmaxf(__fadd_rn(mu, __fmul_rn(z, sd)), lo), hi);
 }
 
+// Block geometry comes from the predictor: one thread per rollout (ODE, FP32-pipe networks: 128 threads), or the tile engines of
+// ctk_mlp_tc.cuh (MlpTcPred: 128 rollouts + helper threads per block; MlpTcFastPredT: 512 rollouts per block, every block an equal
+// contiguous share of the population) -- the same mapping as mppi_rollout_kernel.
 template <class Pred, int KIND, bool LOG>
-__global__ void __launch_bounds__(128) cem_rollout_kernel(const CemArgs a) {
+__global__ void __launch_bounds__(Pred::kCemThreads) cem_rollout_kernel(const CemArgs a) {
   extern __shared__ float smem[];
   float* sh_mu = smem;         // [H]
   float* sh_sd = smem + a.H;   // [H]
@@ -28,42 +31,51 @@ __global__ void __launch_bounds__(128) cem_rollout_kernel(const CemArgs a) {
   }
   __syncthreads();
 
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = n < a.N;
-  if (!active && !Pred::kCooperative) return;
-  const uint32_t ng = (uint32_t)(a.off + (active ? n : 0));
-
-  State z;
-  z.th = a.s0.ld(0); z.om = a.s0.ld(1); z.c = a.s0.ld(2); z.s = a.s0.ld(3); z.x = a.s0.ld(4); z.v = a.s0.ld(5);
-  float omc = 1.0f - cosf(z.th);
-  float u_last = a.u_prev[0];
-  float jsum = 0.0f;
-  pred.begin_rollout();  // recurrent predictors: restore the saved hidden state
-  for (int t0 = 0; t0 < a.H; t0 += 4) {
-    float zz[4];
-    noise4(a.noise, ng, (uint32_t)(t0 >> 2), zz);
+  const int tid = threadIdx.x;
+  const int rpb = Pred::kRolloutsPerBlock > 0 ? Pred::kRolloutsPerBlock : (int)blockDim.x;
+  const bool owner = tid < rpb;
+  const int r_first = Pred::kBalanced ? (int)((long long)blockIdx.x * a.N / gridDim.x) : (int)blockIdx.x * rpb;
+  const int r_end = Pred::kBalanced ? (int)(((long long)blockIdx.x + 1) * a.N / gridDim.x) : min(a.N, r_first + rpb);
+  const State z0 = {a.s0.ld(0), a.s0.ld(1), a.s0.ld(2), a.s0.ld(3), a.s0.ld(4), a.s0.ld(5)};
+  const float omc0 = 1.0f - cosf(z0.th);
+  const float u_prev0 = a.u_prev[0];
+  for (int base = r_first; base < r_end; base += rpb) {
+    const int n = base + tid;
+    const bool active = owner && n < r_end;
+    if (!(active || (Pred::kCooperative && pred.group_active(base, r_end)))) continue;
+    const uint32_t ng = (uint32_t)(a.off + (active ? n : 0));
+    State z = z0;
+    float omc = omc0;
+    float u_last = u_prev0;
+    float jsum = 0.0f;
+    pred.begin_rollout(active);  // recurrent predictors: restore the saved hidden state; tile engines: is this row a real rollout
+    for (int t0 = 0; t0 < a.H; t0 += 4) {
+      float zz[4];
+      noise4(a.noise, ng, (uint32_t)(t0 >> 2), zz);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int t = t0 + q;
-      if (t < a.H) {
-        const float u = cem_sample(sh_mu[t], sh_sd[t], zz[q], a.lo, a.hi);
-        if (LOG && active) {
-          float* p = a.log_traj_soa + (size_t)t * 6 * a.N + n;
-          p[0] = z.th; p[a.N] = z.om; p[2 * a.N] = z.c; p[3 * a.N] = z.s; p[4 * (size_t)a.N] = z.x; p[5 * (size_t)a.N] = z.v;
-          a.log_Q_soa[(size_t)t * a.N + n] = u;
+      for (int q = 0; q < 4; ++q) {
+        const int t = t0 + q;
+        if (t < a.H) {
+          const float u = cem_sample(sh_mu[t], sh_sd[t], zz[q], a.lo, a.hi);
+          if (LOG && active) {
+            float* p = a.log_traj_soa + (size_t)t * 6 * a.N + n;
+            p[0] = z.th; p[a.N] = z.om; p[2 * a.N] = z.c; p[3 * a.N] = z.s; p[4 * (size_t)a.N] = z.x; p[5 * (size_t)a.N] = z.v;
+            a.log_Q_soa[(size_t)t * a.N + n] = u;
+          }
+          jsum += stage_cost<KIND>(z, omc, u, u_last, cost);
+          pred.step(z, u, omc);
+          u_last = u;
         }
-        jsum += stage_cost<KIND>(z, omc, u, u_last, cost);
-        pred.step(z, u, omc);
-        u_last = u;
       }
     }
+    if (active) {
+      if (LOG) {
+        float* p = a.log_traj_soa + (size_t)a.H * 6 * a.N + n;
+        p[0] = z.th; p[a.N] = z.om; p[2 * a.N] = z.c; p[3 * a.N] = z.s; p[4 * (size_t)a.N] = z.x; p[5 * (size_t)a.N] = z.v;
+      }
+      a.J[n] = (jsum + terminal_cost(z, cost)) - cost.shift;
+    }
   }
-  if (!active) return;
-  if (LOG) {
-    float* p = a.log_traj_soa + (size_t)a.H * 6 * a.N + n;
-    p[0] = z.th; p[a.N] = z.om; p[2 * a.N] = z.c; p[3 * a.N] = z.s; p[4 * (size_t)a.N] = z.x; p[5 * (size_t)a.N] = z.v;
-  }
-  a.J[n] = (jsum + terminal_cost(z, cost)) - cost.shift;
 }
 
 // One block of 1024 threads: merge candidates -> global top-k (bitonic), regenerate elite Q, refit mu / sd.

@@ -56,6 +56,7 @@ cudaError_t launch_single_rollout_gru(const float* s0, const float* Q, int H, co
 cudaError_t launch_gru_update(const S0& s0, const float* u_nom, const MlpDev& mlp, float* rnn_h, cudaStream_t st);
 
 cudaError_t launch_cem_rollout(int pred, int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemArgs& a);
+int cem_rollout_grid(int pred, int N, int num_sms);
 cudaError_t launch_cem_ode(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemOdeArgs& a);
 cudaError_t launch_cem_tick(int kind, bool log, int nblocks, size_t smem, cudaStream_t st, const CemTickArgs& a);
 int cem_tick_rollouts_per_block();

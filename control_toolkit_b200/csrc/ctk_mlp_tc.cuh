@@ -56,6 +56,7 @@ struct MlpTcPred {
   static constexpr bool kCooperative = true;  // every thread of the CTA must call step() the same number of times
   static constexpr bool kBalanced = false;
   static constexpr int kMaxThreads = 544;  // 16 worker warps + 1 MMA-issuer warp
+  static constexpr int kCemThreads = 544;
   static constexpr int kMinBlocks = 1;
   static constexpr int kRolloutsPerBlock = 128;  // threads 128..543 are helpers: they own no rollout
   uint8_t* sA;        // [3][32768] activation split tiles (written per step); reused for the layer-3 partial sums
@@ -88,7 +89,7 @@ struct MlpTcPred {
 #endif
     const uint4* src = reinterpret_cast<const uint4*>(m.tc_blob);
     uint4* dst = reinterpret_cast<uint4*>(sB);
-    for (int i = threadIdx.x; i < (int)(kTcBlobBytes / 16); i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < (int)((3 * kTcTileBytes + kTcBlobFloats * 4) / 16); i += blockDim.x) dst[i] = src[i];  // (not the B1 tile behind them)
     if (threadIdx.x == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)) : "memory");
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar + 1)) : "memory");
@@ -332,6 +333,7 @@ struct MlpTcFastPredT {
   static constexpr bool kCooperative = true;   // every thread of an ACTIVE group must call step() the same number of times
   static constexpr bool kBalanced = true;      // CTA b rolls out the contiguous share [b N / grid, (b + 1) N / grid) of the population
   static constexpr int kMaxThreads = 512;      // 4 warp groups x 128 threads, every thread owns a rollout
+  static constexpr int kCemThreads = 512;
   static constexpr int kMinBlocks = 1;
   static constexpr int kRolloutsPerBlock = 512;
   uint8_t* sA;        // this group's bf16 tile of h1 [32768]

@@ -16,6 +16,7 @@ struct OdePred {
 #define CTK_ODE_MAX_THREADS 1024
 #endif
   static constexpr int kMaxThreads = CTK_ODE_MAX_THREADS;
+  static constexpr int kCemThreads = 128;  // block size of the generic CEM rollout kernel
   static constexpr int kMinBlocks = 1;
   FwdK p;  // forward constants, register-resident (ctk_device.cuh load_fwd)
   __device__ __forceinline__ OdePred(const DevConsts* kc, const MlpDev&, float*) : p(load_fwd(kc)) {}
@@ -47,6 +48,7 @@ struct MlpSimtPred {
   static constexpr bool kCooperative = false;
   static constexpr int kRolloutsPerBlock = 0;
   static constexpr int kMaxThreads = 128;
+  static constexpr int kCemThreads = 128;
   static constexpr int kMinBlocks = 1;
   int hid;
   const float *W1, *b1, *W2, *b2, *W3T, *b3;  // shared memory
@@ -137,6 +139,7 @@ struct GruSimtPred {
   static constexpr bool kCooperative = false;
   static constexpr int kRolloutsPerBlock = 0;
   static constexpr int kMaxThreads = 128;
+  static constexpr int kCemThreads = 128;
   static constexpr int kMinBlocks = 1;
   static constexpr int HMAX = 32;
   int hid;

@@ -947,3 +947,49 @@ def test_full_size_properties_1m_rollouts():
     Jh = half._get_log(1, (500_000,))
     np.testing.assert_array_equal(Jh, Ja[500_000:])
     assert np.isfinite(Ja).all()
+
+
+@pytest.mark.parametrize("engine", ["simt", "tcgen05", "tcgen05_bf16", "tcgen05_fast"])
+def test_cem_mlp_predictor_engines(engine):
+    """CEM with the MLP predictor on every engine (the tcgen05 engines used to be MPPI-only: reference optimizer_cem_tf.py:57 drives the
+    same predict_core).  FP32-level engines (simt, tcgen05): elite index lists, distribution and u against the oracle on injected noise
+    at a ragged population (300 = 2 tiles + 44 rows).  Reduced-precision engines: the kernel runs the tile mapping (equal shares per
+    block), costs stay within the bf16 rounding distance of the exact engine's and most elites coincide."""
+    from oracle import spec
+    from oracle.replay_rng import ReplayRNG
+    _, meta = load_golden("mppi_mlp_c4_n256")
+    cfg = dict(seed=42, mpc_horizon=30, mpc_timestep=0.02, cem_outer_it=2, cem_initial_action_stdev=0.5, num_rollouts=300,
+               cem_stdev_min=0.01, cem_best_k=16, warmup=False, warmup_iterations=250)
+    meta = dict(meta, optimizer="cem-tf", cfg=cfg)
+    ctrl = make_controller(meta, rng=None, logging=True, mlp_engine=engine)
+    ctrl.optimizer.rng = ReplayRNG(9, as_torch=False)
+    ctrl.optimizer.optimizer_reset()
+    exact = engine in ("simt", "tcgen05")
+    o = make_oracle(meta)
+    rng = ReplayRNG(9)
+    names = {"simt": "MlpSimtPred", "tcgen05": "MlpTcPred", "tcgen05_bf16": "MlpTcBf16Pred", "tcgen05_fast": "MlpTcFastPred"}
+    for t, s0 in enumerate(spec.synthetic_states(2, seed=17)):
+        u = ctrl.step(s0)
+        uo = o.step(s0, rng)
+        assert names[engine] in ctrl.optimizer.last_kernel, ctrl.optimizer.last_kernel
+        got, ref = ctrl.optimizer.elite_indices, o.last["elite_idx"]
+        J = ctrl.optimizer.logging_values["J_logged"]
+        assert np.isfinite(J).all()
+        if exact:
+            for it in range(ref.shape[0]):
+                assert set(got[it].tolist()) == set(ref[it].tolist()), (engine, t, it)
+            assert max_rel(ctrl.optimizer.dist_mue, o.dist_mue.numpy(), floor=1e-2) < 1e-5
+            assert abs(float(u) - float(uo)) < 1e-5
+            eJ = max_elem_rel(J, o.last["J"])
+            _report(f"cem + mlp [{engine}] tick {t}: J {eJ:.2e}")
+            assert eJ < 5e-5
+        else:
+            overlap = len(set(got[-1].tolist()) & set(ref[-1].tolist())) / ref.shape[1]
+            eJ = np.abs(J.astype(np.float64) - o.last["J"]) / (np.abs(o.last["J"]) + 1e-3)
+            _report(f"cem + mlp [{engine}] tick {t}: elite overlap with the fp32 oracle {overlap:.2f}, J median {np.median(eJ):.2e}")
+            assert np.median(eJ) < 2e-2
+            # keep the oracle on the device's trajectory of optimizer states (per-tick comparison)
+            import torch
+            o.dist_mue = torch.from_numpy(ctrl.optimizer.dist_mue.copy())
+            o.stdev = torch.from_numpy(ctrl.optimizer.stdev.copy())
+            o.u = np.float32(u)
