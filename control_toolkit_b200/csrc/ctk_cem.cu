@@ -69,7 +69,7 @@ cudaError_t launch_cem_tick(int kind, bool log, int nblocks, size_t smem, cudaSt
 // grid of the generic CEM rollout kernel: one block per 128 rollouts; the single-product tile engines run one CTA per SM with equal shares
 int cem_rollout_grid(int pred, int N, int num_sms) {
   const int nb = (N + 127) / 128;
-  return (pred == 3 || pred == 4) ? (nb < num_sms ? nb : num_sms) : nb;
+  return (pred >= 2 && pred <= 4) ? (nb < num_sms ? nb : num_sms) : nb;  // tile engines: one CTA per SM, equal shares (kBalanced)
 }
 int cem_tick_rollouts_per_block() { return kCemTickRollouts; }
 // resident blocks per SM of the persistent tick kernel (its blocks wait for each other: the whole grid must be resident)

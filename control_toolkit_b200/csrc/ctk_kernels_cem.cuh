@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(Pred::kCemThreads) cem_rollout_kernel(const Ce
   for (int base = r_first; base < r_end; base += rpb) {
     const int n = base + tid;
     const bool active = owner && n < r_end;
-    if (!(active || (Pred::kCooperative && pred.group_active(base, r_end)))) continue;
+    const bool grp = Pred::kCooperative && pred.group_active(base, r_end);  // (every thread: the tile engines note the tile's row count)
+    if (!(active || grp)) continue;
     const uint32_t ng = (uint32_t)(a.off + (active ? n : 0));
     State z = z0;
     float omc = omc0;

@@ -308,7 +308,8 @@ __global__ void __launch_bounds__(Pred::kMaxThreads, Pred::kMinBlocks) mppi_roll
     const bool active = owner && n < r_end;
     const uint32_t ng = (uint32_t)(a.off + (active ? n : 0));
     float S = INFINITY;
-    if (active || (Pred::kCooperative && pred.group_active(base, r_end))) {
+    const bool grp = Pred::kCooperative && pred.group_active(base, r_end);  // (every thread: the tile engines note the tile's row count)
+    if (active || grp) {
       State z = z0;
       float omc = omc0, u_last = u_prev0, acc = 0.0f;
       pred.begin_rollout(active);  // recurrent predictors: restore the saved hidden state; tile engines: is this row a real rollout

@@ -54,7 +54,9 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 
 struct MlpTcPred {
   static constexpr bool kCooperative = true;  // every thread of the CTA must call step() the same number of times
-  static constexpr bool kBalanced = false;
+  static constexpr bool kBalanced = true;     // CTA b rolls out the contiguous share [b N / grid, (b + 1) N / grid): with one CTA per SM every
+                                              // SM gets 442.8 of C4's 65536 rollouts (3 tiles + a 59-row tile whose idle warps skip the
+                                              // arithmetic) instead of 3 or 4 whole tiles (512 tiles on 148 SMs = 3.46 waves)
   static constexpr int kMaxThreads = 544;  // 16 worker warps + 1 MMA-issuer warp
   static constexpr int kCemThreads = 544;
   static constexpr int kMinBlocks = 1;
@@ -66,6 +68,7 @@ struct MlpTcPred {
   uint64_t* mbar;
   uint32_t* tmem_slot;
   uint32_t phase;
+  int rows_on;        // real rollouts of the tile in flight (rows >= rows_on are padding: their warps skip the FP32 / MUFU stages)
 #ifdef CTK_TC_TRACE
   long long tr[8];  // accumulated clock64 deltas of the step phases (diagnostics build)
   long long tl;
@@ -83,6 +86,7 @@ struct MlpTcPred {
     tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
     sx = f + kTcBlobFloats + 16;
     phase = 0;
+    rows_on = 128;
 #ifdef CTK_TC_TRACE
     for (int i = 0; i < 8; ++i) tr[i] = 0;
     tl = 0;
@@ -119,7 +123,8 @@ struct MlpTcPred {
   __device__ __forceinline__ bool single_substep() const { return false; }
   __device__ __forceinline__ void use_uniform(const HotUK&) {}
   __device__ __forceinline__ void begin_rollout(bool = true) {}
-  __device__ __forceinline__ bool group_active(int, int) const { return true; }
+  // called by every thread at the top of a pass of the rollout loop: the whole CTA works on the tile [base, base + 128)
+  __device__ __forceinline__ bool group_active(int base, int end) { rows_on = end - base; return true; }
 
   // tanh(x) = 1 - 2 / (exp(2x) + 1) for either sign (x -> -inf: e -> 0, t -> -1; x -> +inf: e -> inf, r -> 0, t -> 1):
   // FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA.  Absolute error <= ~3e-7 (the two MUFU approximations), the same bound the
@@ -217,9 +222,14 @@ struct MlpTcPred {
     // ---- layer 1 + tanh + 3-term bf16 split -> operand tiles.  In phase p this thread produces k-group 4 p + q of its row, so
     //      that after phase p the K-quarter [32 p, 32 p + 32) is complete for all rows and its MMAs can start ----
     const uint32_t arow = smem_u32(sA) + (uint32_t)row * 16u;
+    const bool warp_on = (row & ~31) < rows_on;  // warp-uniform: this warp's 32 rows hold at least one real rollout
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const int kg = 4 * p + q;
+      if (!warp_on) {  // padding rows: keep the barrier protocol, skip the arithmetic (their accumulator rows are never read)
+        asm volatile("bar.arrive %0, 544;" ::"r"(1 + p) : "memory");
+        continue;
+      }
       uint32_t p1[4], p2[4], p3[4];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -253,7 +263,7 @@ struct MlpTcPred {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     TCT(4)
 #pragma unroll 1
-    for (int hh = 0; hh < 2; ++hh) {
+    for (int hh = 0; hh < (warp_on ? 2 : 0); ++hh) {
       const int c0 = q * 32 + hh * 16;
       uint32_t v[16];
       asm volatile(
