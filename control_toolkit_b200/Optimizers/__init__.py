@@ -65,6 +65,12 @@ class template_optimizer:
         # until the next step(); controller_mpc.update_logs copies them like the reference, Controllers/__init__.py:159-178);
         # smaller logs are fresh copies.  None: always copy.
         self.log_view_min_bytes = kwargs.pop("log_view_min_bytes", 16 << 20)
+        # Optional top-M-only logging: with optimizer_logging on and logging_top_m = M, Q_logged / J_logged /
+        # rollout_trajectories_logged hold only the M lowest-cost rollouts of the tick, best first (ties to the lower index), plus
+        # their global rollout ids in "top_m_indices_logged" -- selected and gathered on the device, so the host receives
+        # M x ((H+1) ns + H nu + 2) floats instead of the whole population's logs.  None (default): the reference's full logs.
+        m = kwargs.pop("logging_top_m", None)
+        self.logging_top_m = None if m in (None, 0) else int(m)
         # > 1: the handle carries that many independent clients whose ticks run in ONE launch (optimizer_mppi.step_batch; the
         # serving edge of SURVEY 8f.4).  1: the reference's single controller.
         self.num_clients = int(kwargs.pop("num_clients", 1))
@@ -275,6 +281,35 @@ class template_optimizer:
         out = np.empty(count, dtype)
         L.check(lib.ctk_get_log(self._h, which, out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out.reshape(shape)
+
+    def _get_log_top(self, m: int, with_rows: bool = True) -> dict:
+        """The logs of the m lowest-cost rollouts of the last tick (ctk_get_log_top): {"idx" [m] int32 global rollout ids, "J" [m],
+        "Q" [m, H, nu], "traj" [m, H+1, ns]} -- Q / traj only when the handle logs (with_rows)."""
+        lib = self._require_backend()
+        H, nu, ns = self.mpc_horizon, int(self.num_control_inputs), int(self.num_states)
+        idx, J = np.empty(m, np.int32), np.empty(m, np.float32)
+        Q = np.empty((m, H, nu), np.float32) if with_rows else None
+        traj = np.empty((m, H + 1, ns), np.float32) if with_rows else None
+        L.check(lib.ctk_get_log_top(self._h, int(m), idx.ctypes.data_as(C.POINTER(C.c_int32)), L.fptr(J),
+                                    L.fptr(Q) if with_rows else None, L.fptr(traj) if with_rows else None))
+        return {"idx": idx, "J": J, "Q": Q, "traj": traj}
+
+    def _collect_rollout_logs(self, N: int) -> np.ndarray:
+        """Fills logging_values' Q_logged / J_logged / rollout_trajectories_logged (reference optimizer_mppi.py:214-218,
+        optimizer_cem_tf.py:104-108) -- the whole population, or its logging_top_m best rollouts -- and returns the trajectories."""
+        H, nu, ns = self.mpc_horizon, int(self.num_control_inputs), int(self.num_states)
+        if self.logging_top_m is not None:
+            top = self._get_log_top(min(self.logging_top_m, N))
+            self.logging_values["Q_logged"] = top["Q"]
+            self.logging_values["J_logged"] = top["J"]
+            self.logging_values["rollout_trajectories_logged"] = top["traj"]
+            self.logging_values["top_m_indices_logged"] = top["idx"]
+            return top["traj"]
+        traj = self._get_log(L.LOG_ROLLOUTS, (N, H + 1, ns))
+        self.logging_values["Q_logged"] = self._get_log(L.LOG_Q, (N, H, nu))
+        self.logging_values["J_logged"] = self._get_log(L.LOG_J, (N,))
+        self.logging_values["rollout_trajectories_logged"] = traj
+        return traj
 
     def export_philox(self, stream: int, tick: int, per_rollout: int, rows: int, uniform: bool = False, row0: int = 0,
                       sub: int = 0) -> np.ndarray:

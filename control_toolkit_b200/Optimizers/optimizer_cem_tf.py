@@ -78,9 +78,7 @@ class optimizer_cem_tf(template_optimizer):
         self.u = np.squeeze(u)  # :101
         H, nu, N = self.mpc_horizon, self.num_control_inputs, self._n_local
         if self.optimizer_logging:
-            self.logging_values["Q_logged"] = self._get_log(L.LOG_Q, (N, H, nu))
-            self.logging_values["J_logged"] = self._get_log(L.LOG_J, (N,))
-            self.logging_values["rollout_trajectories_logged"] = self._get_log(L.LOG_ROLLOUTS, (N, H + 1, int(self.num_states)))
+            self._collect_rollout_logs(N)
             self.logging_values["u_logged"] = self.u
             self.elite_indices = self._get_log(L.LOG_ELITE_IDX, (iterations, self.cem_best_k), np.int32)
         self.count += 1  # :110

@@ -90,10 +90,7 @@ class optimizer_mppi(template_optimizer):
         else:
             self.u_nom = self._get_state(L.STATE_U_NOM, (1, H, nu))
         if self.optimizer_logging:
-            self.rollout_trajectories = self._get_log(L.LOG_ROLLOUTS, (N, H + 1, ns))
-            self.logging_values["Q_logged"] = self._get_log(L.LOG_Q, (N, H, nu))
-            self.logging_values["J_logged"] = self._get_log(L.LOG_J, (N,))
-            self.logging_values["rollout_trajectories_logged"] = self.rollout_trajectories
+            self.rollout_trajectories = self._collect_rollout_logs(N)
             self.logging_values["u_logged"] = self.u
         self.optimal_control_sequence = self.u_nom.copy()
         if self.calculate_optimal_trajectory:

@@ -137,10 +137,7 @@ class optimizer_rpgd(template_optimizer):
         self.u_nom = (self._state_buf.reshape(1, H, nu).copy() if self._state_buf is not None
                       else self._get_log(L.LOG_U_NOM, (1, H, nu)))
         if self.optimizer_logging:
-            self.rollout_trajectories = self._get_log(L.LOG_ROLLOUTS, (N, H + 1, 6))
-            self.logging_values["Q_logged"] = self._get_log(L.LOG_Q, (N, H, nu))
-            self.logging_values["J_logged"] = self._get_log(L.LOG_J, (N,))
-            self.logging_values["rollout_trajectories_logged"] = self.rollout_trajectories
+            self.rollout_trajectories = self._collect_rollout_logs(N)
             self.logging_values["trajectory_ages_logged"] = self._get_log(L.LOG_AGES, (N,))
             self.logging_values["u_logged"] = u_before  # :416 logs the PREVIOUS u
         self.optimal_control_sequence = self.u_nom.copy()

@@ -110,6 +110,7 @@ SYMBOLS = {
     "ctk_set_counter": (C.c_int, [_H, C.c_int, C.c_int64]),
     "ctk_get_log": (C.c_int, [_H, C.c_int, C.c_void_p, C.c_size_t]),
     "ctk_get_log_view": (C.c_int, [_H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "ctk_get_log_top": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int32), _FP, _FP, _FP]),
     "ctk_last_kernel": (C.c_char_p, [_H]),
     "ctk_get_launch_count": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "ctk_enable_kernel_timing": (C.c_int, [_H, C.c_int]),

@@ -481,4 +481,21 @@ static __global__ void transpose_kernel(const float* __restrict__ in, float* __r
   }
 }
 
+// Top-M logging (SURVEY 8f.2 "optional top-M-only logging"; consumer: reference Controllers/__init__.py:159-178): rows of the M
+// lowest-cost rollouts out of the logs of the last tick.  keys: the M sorted (ordered cost | global id) keys of K4.  src is either
+// the SoA log [R][N] the CartPole kernels write (soa != 0) or a log in the reference's layout [N][R]; out is [M][R].
+// Block j gathers rollout keys[j]; also J[j] and the global rollout id.
+static __global__ void log_gather_kernel(const uint64_t* __restrict__ keys, int off, const float* __restrict__ J, size_t N, const float* __restrict__ src,
+                                         int R, int soa, float* __restrict__ out, float* __restrict__ J_out, int32_t* __restrict__ idx_out) {
+  const int j = blockIdx.x;
+  const uint32_t g = (uint32_t)(keys[j] & 0xffffffffull);
+  const size_t n = (size_t)g - (size_t)off;
+  if (src != nullptr)
+    for (int r = threadIdx.x; r < R; r += blockDim.x) out[(size_t)j * R + r] = soa ? src[(size_t)r * N + n] : src[n * R + r];
+  if (threadIdx.x == 0) {
+    if (J_out != nullptr) J_out[j] = J[n];
+    if (idx_out != nullptr) idx_out[j] = (int32_t)g;
+  }
+}
+
 }  // namespace ctk

@@ -42,6 +42,9 @@ cudaError_t launch_mppi_combine(const float* in, int cnt, int n_ind, float neg_i
                                 const MppiFinalize& fin, cudaStream_t st);
 cudaError_t launch_exchange_barrier(const MppiFuse& f, size_t bar_off, cudaStream_t st);
 cudaError_t launch_transpose(const float* in, float* out, int R, int C, cudaStream_t st);
+// top-M logging: gather the rows of the rollouts named by m sorted K4 keys out of an SoA [R][N] or reference-layout [N][R] log
+cudaError_t launch_log_gather(const uint64_t* keys, int m, int off, const float* J, size_t N, const float* src, int R, int soa, float* out,
+                              float* J_out, int32_t* idx_out, cudaStream_t st);
 size_t mppi_pred_smem_floats(int pred, const MlpDev& m);
 // environments beyond the CartPole (ctk_env.cu): MPPI = rollout + update launches, CEM = rollout, K4 levels, refit
 cudaError_t launch_env_mppi(int env, bool log, const EnvMppiArgs& a, cudaStream_t st);

@@ -124,6 +124,12 @@ cudaError_t launch_transpose(const float* in, float* out, int R, int C, cudaStre
   return cudaGetLastError();
 }
 
+cudaError_t launch_log_gather(const uint64_t* keys, int m, int off, const float* J, size_t N, const float* src, int R, int soa, float* out,
+                              float* J_out, int32_t* idx_out, cudaStream_t st) {
+  log_gather_kernel<<<m, 128, 0, st>>>(keys, off, J, N, src, R, soa, out, J_out, idx_out);
+  return cudaGetLastError();
+}
+
 // nominal single rollout (reference optimizer_mppi.py:199-202 predict_optimal_trajectory, optimizer_rpgd.py:382-386)
 template <class Pred>
 __global__ void single_rollout_kernel(const float* s0, const float* Q, int H, const DevConsts* kc, MlpDev mlp,

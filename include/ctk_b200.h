@@ -261,6 +261,11 @@ int ctk_get_log(ctk_handle *h, int which, void *dst_host, size_t n_bytes);
    same log id, ctk_step or ctk_destroy.  Replaces the `.numpy()` hand-over of the logged tensors (reference
    optimizer_mppi.py:214-218, Controllers/__init__.py:159-178 copies them into the controller's own history).           */
 int ctk_get_log_view(ctk_handle *h, int which, const void **host_ptr, size_t *n_bytes);
+/* Optional top-M-only logging (the producer it replaces is reference optimizer_mppi.py:214-218 / optimizer_cem_tf.py:
+   104-108, the consumer Controllers/__init__.py:159-178): the m lowest-cost rollouts of the last tick, best first, ties to the
+   lower index -- selected (K4) and gathered on the device.  idx_out [m] global rollout ids, J_out [m], Q_out [m,H,nu],
+   traj_out [m,H+1,ns]; any pointer may be null; Q_out / traj_out need cfg.logging.  1 <= m <= min(num_rollouts, 512).          */
+int ctk_get_log_top(ctk_handle *h, int m, int32_t *idx_out_host, float *J_out_host, float *Q_out_host, float *traj_out_host);
 /* number of CUDA kernels this handle has launched since create (bench.py "gpu_launches")                         */
 int ctk_get_launch_count(ctk_handle *h, int64_t *value);
 /* template instantiation of this handle's last rollout-kernel launch, e.g. "mppi_ode_kernel<0,0,10,2,1024,0>" (the parity tests

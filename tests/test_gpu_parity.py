@@ -373,6 +373,32 @@ def test_log_views_equal_copies():
     np.testing.assert_array_equal(hist[0], first)
 
 
+@pytest.mark.parametrize("fixture,M,over", [("mppi_c1_n2000", 32, {}), ("mppi_c1_n64", 64, {}), ("mppi_c1_n64", 500, {}), ("cem_c2_n4096_k64", 100, {}),
+                                            ("rpgd_c3", 8, {"adam_form": "torch"}), ("mppi_dubins_n512", 17, {}), ("cem_dubins_n512_k32", 512, {})])
+def test_top_m_logging_equals_the_best_rows_of_the_full_logs(fixture, M, over):
+    """Optional top-M-only logging: with logging_top_m = M the plugin hands out the M lowest-cost rollouts of the tick
+    -- selected and gathered on the device (ctk_get_log_top) -- and they are bit-identical to rows argsort(J, stable)[:M] of the
+    full logs of a twin controller on the same injected noise (ties to the lower index)."""
+    z, meta = load_golden(fixture)
+    full = make_controller(meta, **over)
+    top = make_controller(meta, logging_top_m=M, **over)
+    N = full.optimizer.num_rollouts
+    m = min(M, N)
+    for t in range(2):
+        uf = full.step(z["states"][t])
+        ut = top.step(z["states"][t])
+        np.testing.assert_array_equal(np.asarray(uf), np.asarray(ut))
+        lf, lt = full.optimizer.logging_values, top.optimizer.logging_values
+        order = np.argsort(np.asarray(lf["J_logged"]), kind="stable")[:m]
+        np.testing.assert_array_equal(lt["top_m_indices_logged"], order.astype(np.int32))
+        np.testing.assert_array_equal(lt["J_logged"], np.asarray(lf["J_logged"])[order])
+        np.testing.assert_array_equal(lt["Q_logged"], np.asarray(lf["Q_logged"])[order])
+        np.testing.assert_array_equal(lt["rollout_trajectories_logged"], np.asarray(lf["rollout_trajectories_logged"])[order])
+        assert lt["rollout_trajectories_logged"].shape == (m,) + np.asarray(lf["rollout_trajectories_logged"]).shape[1:]
+    # the controller's history (reference Controllers/__init__.py:159-178) takes the reduced logs like any other
+    assert np.asarray(top.get_outputs()["rollout_trajectories_logged"][0]).shape[0] == m
+
+
 @pytest.mark.parametrize("N,H,k,iters", [(4096, 50, 64, 3), (16000, 30, 64, 2), (300, 21, 100, 4), (65, 7, 1, 1), (9000, 12, 128, 2)])
 def test_cem_persistent_tick_equals_multi_launch(N, H, k, iters):
     """The one-launch CEM tick (cem_tick_kernel: in-kernel grid synchronisation, merge tree) against the multi-launch path
