@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libctk_b200.so")
+LIB_PATH = os.environ.get("CTK_LIB") or os.path.join(HERE, "libctk_b200.so")  # CTK_LIB: diagnostics builds (tools/build_variants.sh)
 
 CTK_ABI_VERSION = 1
 CTK_OK, CTK_EINVAL, CTK_ECUDA, CTK_ESTATE = 0, -1, -2, -3

@@ -161,6 +161,7 @@ static cudaError_t dalloc(T** p, size_t n) {
 
 static void mppi_ode_geometry(ctk_handle* h);
 static int pred_id(const ctk_handle* h);
+static bool tile_engine(int pred);
 static cudaError_t upload_consts(ctk_handle* h) {
   if (h->env != 0) return cudaSuccess;  // general environments carry their constants in the kernel parameters (EnvParams)
   h->cem_tick_per_sm = -1;  // the cost kind selects the persistent tick's instantiation (register count): re-query its occupancy
@@ -362,15 +363,19 @@ extern "C" int ctk_create(const ctk_config* cfg, const ctk_ode_params* ode, cons
       h->mppi_stash = 0;
     }
     h->mppi_rpb = h->mppi_block;
-    if (pred_id(h) >= 2 && pred_id(h) <= 4) {  // tcgen05 MLP engines: 16 worker warps + 1 MMA-issuer warp on the 128 rollouts of one MMA tile (ctk_mlp_tc.cuh)
-      const bool pipe = pred_id(h) >= 3;  // single-product engines: one CTA per SM, four 128-rollout tiles in flight (one per warp group),
-                                          // every CTA an equal contiguous share of the population (MlpTcFastPredT::kBalanced)
-      h->mppi_block = mppi_max_block_threads(pred_id(h)); h->mppi_rpb = pipe ? 512 : 128;
+    if (tile_engine(pred_id(h))) {
+      // tcgen05 MLP engines (ctk_mlp_tc.cuh): one CTA per SM, every CTA an equal contiguous share of the population (kBalanced); rollouts per
+      // block = tiles in flight x 128: the single-product engines run four tiles (one per warp group), the exact engine two, its round-1
+      // structure (pred 6) one tile with 16 worker warps + 1 MMA-issuer warp
+      const int pid = pred_id(h);
+      h->mppi_block = mppi_max_block_threads(pid); h->mppi_rpb = pid == 6 ? 128 : (pid == 2 ? 256 : 512);
       h->mppi_grid = (int)std::min<long long>((long long)h->num_sms, ((long long)N + 127) / 128);
       if (h->mppi_grid < 1) h->mppi_grid = 1;
       h->mppi_iters = (int)((N + (long long)h->mppi_grid * h->mppi_rpb - 1) / ((long long)h->mppi_grid * h->mppi_rpb));
-      h->mppi_stash = (!pipe && (size_t)h->n_ind * 128 * sizeof(float) <= 8 * 1024) ? 1 : 0;
-      if ((size_t)h->n_ind * h->mppi_rpb * sizeof(float) > (pipe ? 32 : 8) * 1024) { ctk_destroy(h); return fail(CTK_EINVAL, "tcgen05 MLP engine: too many inducing points (shared memory is taken by the operand tiles)"); }
+      h->mppi_stash = (pid == 6 && (size_t)h->n_ind * 128 * sizeof(float) <= 8 * 1024) ? 1 : 0;
+      // what the operand tiles leave of the 227 KB for the per-rollout accumulators [n_ind][rollouts per block]
+      const size_t acc_limit = pid == 6 ? 8 * 1024 : (pid == 2 ? 12 * 1024 : 32 * 1024);
+      if ((size_t)h->n_ind * h->mppi_rpb * sizeof(float) > acc_limit) { ctk_destroy(h); return fail(CTK_EINVAL, "tcgen05 MLP engine: too many inducing points (shared memory is taken by the operand tiles)"); }
     }
     A(dalloc(&h->d_u_nom, (size_t)H * B), "u_nom");
     h->partials_stride = (size_t)(h->num_sms > h->mppi_grid ? h->num_sms : h->mppi_grid) * (h->mppi_iters + 1) * (h->n_ind + 2);
@@ -773,12 +778,13 @@ static int env_step_host(ctk_handle* h, const float* s_host, float* u_out_host, 
 // ---------------------------------------------------------------------------------------------------------------
 
 // 0 ODE, 1 MLP on the FP32 pipe, 2 MLP with the dense layer on tcgen05 (bf16 x 3 split, fp32-level), 3 one bf16 product, 4 + MUFU.TANH
+static bool tile_engine(int pred) { return (pred >= 2 && pred <= 4) || pred == 6; }  // the tcgen05 engines of ctk_mlp_tc.cuh
 static int pred_id(const ctk_handle* h) {
   if (h->cfg.predictor == CTK_PRED_GRU) return 5;  // recurrent predictor on the FP32 pipe (GruSimtPred)
   if (h->cfg.predictor != CTK_PRED_MLP) return 0;
   if (h->cfg.optimizer == CTK_OPT_RPGD) return 1;
   switch (h->cfg.mlp_engine) {
-    case CTK_MLP_TCGEN05: return 2;
+    case CTK_MLP_TCGEN05: return getenv("CTK_TC_EXACT_V1") != nullptr ? 6 : 2;  // 6: the round-1 structure of the exact engine (A/B runs)
     case CTK_MLP_TCGEN05_BF16: return 3;
     case CTK_MLP_TCGEN05_FAST: return 4;
     default: return 1;
@@ -798,7 +804,7 @@ static void mppi_ode_geometry(ctk_handle* h) {
   // (<= 1024 per SM) more warps hide the step latency better than more chains per warp (measured, profiles/)
   int ilp = (N <= sms * 1024) ? 1 : 2;
   if (const char* e = getenv("CTK_K1_ILP")) { const int v = atoi(e); if (v == 1 || v == 2) ilp = v; }
-  int maxb = mppi_ode_max_block(ilp);
+  int maxb = mppi_ode_max_block(ilp, c.logging != 0);
   if (const char* e = getenv("CTK_K1_BLOCK")) { const int v = atoi(e) / 32 * 32; if (v >= 32 && v <= maxb) maxb = v; }
   // shared memory: draws stash [n_ind][ilp*T] + accumulators [n_ind][T] + small fixed part, <= 200 KB
   const long long fixed = (long long)mppi_ode_smem_bytes(h->H, h->period, h->n_ind, ilp, 0);
@@ -937,10 +943,10 @@ static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_
                                        pred_smem_floats(h));
   h->launches++;
   KernelTimer kt(h);
-  if (pred_id(h) >= 2 && pred_id(h) <= 4 && h->mlp.tc_blob == nullptr) return fail(CTK_ESTATE, "tcgen05 MLP engine without weights");
+  if (tile_engine(pred_id(h)) && h->mlp.tc_blob == nullptr) return fail(CTK_ESTATE, "tcgen05 MLP engine without weights");
   cudaError_t e = launch_mppi_rollout(pred_id(h), h->cost.kind, log, h->mppi_grid, h->mppi_block, smem,
                                       h->stream, a);
-  h->last_kernel = std::string("mppi_rollout_kernel<") + (pred_id(h) == 5 ? "GruSimtPred" : pred_id(h) == 4 ? "MlpTcFastPred" : pred_id(h) == 3 ? "MlpTcBf16Pred" : pred_id(h) == 2 ? "MlpTcPred" : pred_id(h) == 1 ? "MlpSimtPred" : "OdePred") + "," +
+  h->last_kernel = std::string("mppi_rollout_kernel<") + (pred_id(h) == 5 ? "GruSimtPred" : pred_id(h) == 4 ? "MlpTcFastPred" : pred_id(h) == 3 ? "MlpTcBf16Pred" : pred_id(h) == 2 ? "MlpTcPred" : pred_id(h) == 6 ? "MlpTcPredV1" : pred_id(h) == 1 ? "MlpSimtPred" : "OdePred") + "," +
                    std::to_string(h->cost.kind) + "," + (log ? "1" : "0") + ">" + (ns.inj ? " [injected noise]" : " [philox]");
   if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("mppi_rollout_kernel: ") + cudaGetErrorString(e));
   h->step_s = s_dev;
@@ -1093,9 +1099,9 @@ static int cem_local(ctk_handle* h, const float* s_dev, bool to_k) {
     a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
     const size_t smem = sizeof(float) * (2 * (size_t)h->H + pred_smem_floats(h));
     KernelTimer kt(h);
-    if (pred_id(h) >= 2 && pred_id(h) <= 4 && h->mlp.tc_blob == nullptr) return fail(CTK_ESTATE, "tcgen05 MLP engine without weights");
+    if (tile_engine(pred_id(h)) && h->mlp.tc_blob == nullptr) return fail(CTK_ESTATE, "tcgen05 MLP engine without weights");
     e = launch_cem_rollout(pred_id(h), h->cost.kind, c.logging != 0, cem_rollout_grid(pred_id(h), h->N, h->num_sms), smem, h->stream, a);
-    h->last_kernel = std::string("cem_rollout_kernel<") + (pred_id(h) == 5 ? "GruSimtPred" : pred_id(h) == 4 ? "MlpTcFastPred" : pred_id(h) == 3 ? "MlpTcBf16Pred" : pred_id(h) == 2 ? "MlpTcPred" : pred_id(h) == 1 ? "MlpSimtPred" : "OdePred") + "," +
+    h->last_kernel = std::string("cem_rollout_kernel<") + (pred_id(h) == 5 ? "GruSimtPred" : pred_id(h) == 4 ? "MlpTcFastPred" : pred_id(h) == 3 ? "MlpTcBf16Pred" : pred_id(h) == 2 ? "MlpTcPred" : pred_id(h) == 6 ? "MlpTcPredV1" : pred_id(h) == 1 ? "MlpSimtPred" : "OdePred") + "," +
                      std::to_string(h->cost.kind) + "," + (c.logging ? "1" : "0") + ">" + (ns.inj ? " [injected noise]" : " [philox]");
   }
   if (e != cudaSuccess) return fail(CTK_ECUDA, std::string("cem_rollout_kernel: ") + cudaGetErrorString(e));
@@ -1808,7 +1814,7 @@ extern "C" int ctk_debug_trace(ctk_handle* h, int enable, uint64_t* out_host, si
   if (!enable && h->d_trace) { cudaFree(h->d_trace); h->d_trace = nullptr; }
   return CTK_OK;
 }
-// instantiation of the last rollout-kernel launch of this handle, e.g. "mppi_ode_kernel<0,0,10,2,1024,0>" (verification: the parity
+// instantiation of the last rollout-kernel launch of this handle, e.g. "mppi_ode_kernel<0,0,10,2,896,0>" (verification: the parity
 // tests assert that the kernel they compared with the oracle is the one bench.py times)
 extern "C" const char* ctk_last_kernel(ctk_handle* h) { return h ? h->last_kernel.c_str() : ""; }
 extern "C" int ctk_get_launch_count(ctk_handle* h, int64_t* v) { REQ(h && v, "null pointer"); *v = h->launches; return CTK_OK; }

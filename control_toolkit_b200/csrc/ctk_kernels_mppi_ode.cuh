@@ -27,18 +27,29 @@ namespace ctk {
 
 struct Roll : ScaledState {  // one rollout's registers
   float ul, acc, y0, dy, y1;
-  float tot, comp;  // compensated running total of the per-segment cost sums (see fold_segment)
+#ifdef CTK_K1_DSUM
+  double dtot;
+#endif
+  float tot, comp;  // running total of the per-segment cost sums (+ its compensation term under CTK_K1_KAHAN; see fold_segment)
 };
 
 // The total cost S ~ 5e3 enters the softmin as exp(-(S - rho) / lambda) with lambda = 100: one ulp of S (4.9e-4) is 5e-6 relative
-// in the weight, and a 100-term sequential fp32 sum wanders by several ulp -- more than the reference's torch.mean over [H + 1]
+// in the weight, and a 100-term sequential fp32 sum wanders by ~3 ulp rms -- more than the reference's torch.mean over [H + 1]
 // (vectorised pairwise summation).  The stage costs are therefore summed per inducing-point segment (partial sums an order of
-// magnitude below S) and the segment sums enter the total through a compensated (Kahan) addition: 4 FADD per SEGMENT.
+// magnitude below S) and the segment sums enter the total through a compensated (Kahan) addition: 4 FADD per SEGMENT, ~0.5 ulp.
+// (-DCTK_K1_PLAIN_SUM adds the segment sums up plainly, ~0.9 ulp rms: the pinned C1 ticks then miss the 1e-5 bound -- measured,
+// tests/test_gpu_production_pinning.py c1 / c1_ilp2 -- so the compensation stays.)
 __device__ __forceinline__ void fold_segment(Roll& r) {
+#if defined(CTK_K1_DSUM)
+  r.dtot += (double)r.acc;  // (experiment) second level in double: exact, one conversion + one DADD per segment
+#elif !defined(CTK_K1_PLAIN_SUM)
   const float y = r.acc - r.comp;
   const float t = r.tot + y;
   r.comp = (t - r.tot) - y;
   r.tot = t;
+#else
+  r.tot += r.acc;
+#endif
   r.acc = 0.0f;
 }
 
@@ -164,6 +175,9 @@ __device__ __forceinline__ void mppi_ode_body(const MppiOdeArgs& a) {
       r[q].ul = upv;
       r[q].acc = (k.k_ccrc * upv) * upv;  // telescoped ccrc term of u_{-1}
       r[q].tot = 0.0f; r[q].comp = 0.0f;
+#ifdef CTK_K1_DSUM
+      r[q].dtot = 0.0;
+#endif
       r[q].y0 = 0.0f; r[q].dy = 0.0f;
       r[q].y1 = sz[0] * k.stdev;  // y0 of segment 0   (:173-175 normal * stdev before interpolation)
     }
@@ -220,7 +234,11 @@ __device__ __forceinline__ void mppi_ode_body(const MppiOdeArgs& a) {
         p[4 * (size_t)a.N] = r[q].x; p[5 * (size_t)a.N] = r[q].V * k.inv_cFg;
       }
       // Cost_Functions/__init__.py:90-92 (mean over H+1 incl. the terminal cost); optimizer_mppi.py:160
+#ifdef CTK_K1_DSUM
+      const float S = finish_cost_scaled((float)r[q].dtot, r[q], r[q].ul, k);
+#else
       const float S = finish_cost_scaled(r[q].tot - r[q].comp, r[q], r[q].ul, k);
+#endif
       if (active[q]) {
         a.J[n[q]] = S;
         if (S < INFINITY) {

@@ -33,7 +33,7 @@ int mppi_max_block_threads(int pred);
 // K1 for the ODE predictor with intermediate_steps == 1 (scaled variables, ILP rollouts per thread)
 cudaError_t launch_mppi_ode(int kind, bool log, int period_t, int ilp, int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a,
                             const char** name = nullptr);
-int mppi_ode_max_block(int ilp);
+int mppi_ode_max_block(int ilp, bool log);
 // several clients' ticks in one launch: grid (grid, nclients); Philox noise, logging off, ILP 1 (ctk_batch.cu)
 cudaError_t launch_mppi_ode_batch(int kind, int period_t, int grid, int nclients, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a,
                                   const MppiBatch& b);

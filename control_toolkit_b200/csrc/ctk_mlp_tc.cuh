@@ -52,7 +52,7 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       : "memory");
 }
 
-struct MlpTcPred {
+struct MlpTcPredV1 {
   static constexpr bool kCooperative = true;  // every thread of the CTA must call step() the same number of times
   static constexpr bool kBalanced = true;     // CTA b rolls out the contiguous share [b N / grid, (b + 1) N / grid): with one CTA per SM every
                                               // SM gets 442.8 of C4's 65536 rollouts (3 tiles + a 59-row tile whose idle warps skip the
@@ -76,7 +76,7 @@ struct MlpTcPred {
 
   static size_t smem_floats(const MlpDev&) { return (6 * (size_t)kTcTileBytes + kTcBlobFloats * 4 + 64 + 128 * 8 * 4 + 1024) / 4; }
 
-  __device__ __forceinline__ MlpTcPred(const DevConsts*, const MlpDev& m, float* sm) {
+  __device__ __forceinline__ MlpTcPredV1(const DevConsts*, const MlpDev& m, float* sm) {
     uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)sm + 1023) & ~(uintptr_t)1023);
     sA = base;
     sB = base + 3 * kTcTileBytes;
@@ -107,7 +107,7 @@ struct MlpTcPred {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     // caller issues __syncthreads() after construction
   }
-  __device__ __forceinline__ ~MlpTcPred() {
+  __device__ __forceinline__ ~MlpTcPredV1() {
 #ifdef CTK_TC_TRACE
     if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 200))
       printf("tc trace tid %d: B1 %lld  L1 %lld  B2 %lld  issue %lld  mma-wait %lld  epilogue %lld  B3+update %lld  outside %lld (cycles, summed)\n", (int)threadIdx.x, tr[0], tr[1], tr[2], tr[3], tr[4], tr[5], tr[6], tr[7]);
@@ -414,7 +414,7 @@ struct MlpTcFastPredT {
       asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
       return t;
     }
-    return MlpTcPred::tanh5(x);
+    return MlpTcPredV1::tanh5(x);
   }
   static __device__ __forceinline__ uint32_t pack2(float lo, float hi) {  // two floats -> bf16x2 (RN-even), first element in the low half
     uint32_t d;
@@ -463,9 +463,9 @@ struct MlpTcFastPredT {
     //      six inputs, K = 48 = six 16-byte k-groups of the K-major core-matrix layout) ----
     if (warp_on) {
       uint32_t p1[3], p2[3], p3[3];
-      MlpTcPred::split3(u, z.om, p1[0], p2[0], p3[0]);
-      MlpTcPred::split3(z.c, z.s, p1[1], p2[1], p3[1]);
-      MlpTcPred::split3(z.x, z.v, p1[2], p2[2], p3[2]);
+      MlpTcPredV1::split3(u, z.om, p1[0], p2[0], p3[0]);
+      MlpTcPredV1::split3(z.c, z.s, p1[1], p2[1], p3[1]);
+      MlpTcPredV1::split3(z.x, z.v, p1[2], p2[2], p3[2]);
       auto sts4 = [&](int kg, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(arow + (uint32_t)kg * kTcKStride), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
       };
@@ -512,12 +512,12 @@ struct MlpTcFastPredT {
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const uint32_t jo = (uint32_t)(c0 + q4 * 4) * 4u;
-        const float4 bb = MlpTcPred::lds4(ab2 + jo);
+        const float4 bb = MlpTcPredV1::lds4(ab2 + jo);
         const float h0 = act(__uint_as_float(v[4 * q4]) + bb.x), h1 = act(__uint_as_float(v[4 * q4 + 1]) + bb.y);
         const float h2 = act(__uint_as_float(v[4 * q4 + 2]) + bb.z), h3 = act(__uint_as_float(v[4 * q4 + 3]) + bb.w);
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-          const float4 w = MlpTcPred::lds4(aW3 + (uint32_t)k * 512u + jo);
+          const float4 w = MlpTcPredV1::lds4(aW3 + (uint32_t)k * 512u + jo);
           y[k] = fmaf(h3, w.w, fmaf(h2, w.z, fmaf(h1, w.y, fmaf(h0, w.x, y[k]))));
         }
       }
@@ -533,6 +533,250 @@ struct MlpTcFastPredT {
 };
 using MlpTcBf16Pred = MlpTcFastPredT<false>;
 using MlpTcFastPred = MlpTcFastPredT<true>;
+
+// ---------------------------------------------------------------------------------------------------------------
+// The exact (fp32-level) engine, round-2 structure: the tile-per-warp-group organisation of the single-product engines above with
+// the six-product bf16 x 3 arithmetic of MlpTcPredV1.  TWO 128-rollout tiles in flight per SM (groups), each worked on by 256 threads:
+// the 128 OWNER threads (one per rollout: operand row of layer 1, state, cost) and 128 HELPER threads; owner and helper of a row split
+// the row's columns in the FP32 / MUFU stages (the row's 512 MUFU operations per step at 8 cycles per warp instruction are the longest
+// link of a tile's serial chain: with one thread per row the two tiles ran the tensor core, the MUFU and the FP32 pipe one after
+// another -- 2.20 ms per C4 tick, profiles/prof_mlp_tc_r02_exact_v2_summary.txt: tensor 34 %, XU 37 %, issue 34 %, 27 % barrier stalls).
+//   layer 1 : on the tensor core (three K16 UMMAs on the K = 48 split operand row, B1 resident) -> L1 accumulator, TMEM columns
+//             [0, 128) of the group;
+//   layer 2 : K is processed in QUARTERS: owner and helper read 16 columns each of the row's L1 accumulator, apply tanh, split the
+//             values into three bf16 terms and write them into one of the group's two quarter buffers (3 terms x 4 k-groups = 24 KB;
+//             the three full A tiles of the V1 engine, 96 KB per tile in flight, are what kept it at one tile per SM); the group's first
+//             thread then issues that quarter's 12 UMMAs (six products x two K16 slices, smallest products first) into the L2
+//             accumulator, TMEM columns [128, 256), and commits them to the buffer's mbarrier -- the tensor core works on quarter p
+//             while the group's threads produce quarter p + 1 (TMEM load, MUFU, split) and while the OTHER group is in any phase;
+//   layer 3 : owner and helper fold 64 columns each of the row's L2 accumulator (bias, tanh, five FMAs per column); the helper hands
+//             its five partial sums to the owner through shared memory (aliasing quarter buffer 1, free by then).
+// Shared memory: 2 groups x 2 x 24 KB quarter buffers + W2 split tiles 96 KB + B1 12 KB + 6.5 KB of fp32 weights = 211 KB.
+// TMEM: 512 columns, 256 per group.  Synchronisation per step and group: six 256-thread named barriers and the mbarrier waits
+// (one polling lane per warp; a quarter's MMAs have normally completed by the time its buffer is needed again).
+// ---------------------------------------------------------------------------------------------------------------
+struct MlpTcPred {
+  static constexpr bool kCooperative = true;   // every thread of an ACTIVE group must call step() the same number of times
+  static constexpr bool kBalanced = true;      // CTA b rolls out the contiguous share [b N / grid, (b + 1) N / grid) of the population
+  static constexpr int kGroups = 2;
+  static constexpr int kMaxThreads = 256 * kGroups;  // threads [0, 128 kGroups) own a rollout, the rest are the rows' helpers
+  static constexpr int kCemThreads = 256 * kGroups;
+  static constexpr int kMinBlocks = 1;
+  static constexpr int kRolloutsPerBlock = 128 * kGroups;
+  static constexpr uint32_t kQBuf = 3u * 4u * kTcKStride;  // one K-quarter (four k-groups) of the three split terms: 24 KB
+  uint8_t* sA;        // this group's two quarter buffers [2][kQBuf]; buffer 0 also takes the layer-1 operand rows (six k-groups)
+  uint8_t* sB;        // [3][32768] W2 split tiles (resident, shared by the groups)
+  uint8_t* sB1;       // [12288] layer-1 operand (W1 / b1 split terms, resident)
+  const float *W1, *b1, *b2, *W3T, *b3;
+  uint64_t* mbar;     // this group's barriers: [0] layer-1 MMAs, [1] / [2] the MMAs reading quarter buffer 0 / 1
+  uint32_t* tmem_slot;
+  uint32_t phase;     // parity of the layer-1 barrier (the quarter barriers complete two phases per step: parities 0, 1 every step)
+  int grp, half;      // tile of this thread; 0 = owner of row (tid & 127), 1 = its helper
+  int tile_rows;      // real rollouts of the pass in flight over the whole CTA (rows >= tile_rows are padding)
+  bool row_on;        // this thread's row is a real rollout (warps without any skip the arithmetic of a step)
+
+  static size_t smem_floats(const MlpDev&) { return (kGroups * 2 * (size_t)kQBuf + kTcBlobBytes + 128 + 1024) / 4; }
+
+  __device__ __forceinline__ MlpTcPred(const DevConsts*, const MlpDev& m, float* sm) {
+    uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)sm + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x;
+    half = tid >= 128 * kGroups ? 1 : 0;
+    grp = ((tid - half * 128 * kGroups) >> 7);
+    sA = base + (size_t)grp * 2 * kQBuf;
+    sB = base + (size_t)kGroups * 2 * kQBuf;
+    float* f = reinterpret_cast<float*>(sB + 3 * kTcTileBytes);
+    W1 = f; b1 = W1 + 6 * 128; b2 = b1 + 128; W3T = b2 + 128; b3 = W3T + 5 * 128;
+    sB1 = reinterpret_cast<uint8_t*>(f + kTcBlobFloats);
+    uint64_t* mb0 = reinterpret_cast<uint64_t*>(sB1 + kTcB1Bytes);  // [kGroups][4]
+    mbar = mb0 + 4 * grp;
+    tmem_slot = reinterpret_cast<uint32_t*>(mb0 + 4 * kGroups);
+    phase = 0;
+    tile_rows = 128 * kGroups;
+    row_on = true;
+    // the blob has the resident layout: W2 split tiles | fp32 weights | B1
+    const uint4* src = reinterpret_cast<const uint4*>(m.tc_blob);
+    uint4* dst = reinterpret_cast<uint4*>(sB);
+    for (int i = threadIdx.x; i < (int)(kTcBlobBytes / 16); i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x < 4 * kGroups) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mb0 + threadIdx.x)) : "memory");
+    if (threadIdx.x == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if ((threadIdx.x >> 5) == 0) {  // the CTA owns the SM: all 512 TMEM columns, 256 per group (layer-1 and layer-2 accumulators)
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    // caller issues __syncthreads() after construction
+  }
+  __device__ __forceinline__ ~MlpTcPred() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*tmem_slot) : "memory");
+    }
+  }
+  __device__ __forceinline__ void substep(State& z, float u, float& omc) { step(z, u, omc); }
+  __device__ __forceinline__ bool single_substep() const { return false; }
+  __device__ __forceinline__ void use_uniform(const HotUK&) {}
+  // (helpers are never `active` in the kernels' sense: their row's state follows from the pass's row count)
+  __device__ __forceinline__ void begin_rollout(bool = true) { row_on = grp * 128 + (int)(threadIdx.x & 127u) < tile_rows; }
+  // a group runs a pass of the rollout loop iff its first row is a real rollout (group-uniform: the group's barriers stay matched)
+  __device__ __forceinline__ bool group_active(int base, int end) { tile_rows = end - base; return grp * 128 < tile_rows; }
+
+  static __device__ __forceinline__ float tanh5(float x) { return MlpTcPredV1::tanh5(x); }
+
+  __device__ __forceinline__ void step(State& z, float u, float& omc) {
+    const int tid = threadIdx.x, g = grp, row = tid & 127, wq = (tid >> 5) & 3;
+    const uint32_t ab2 = smem_u32(b2), aW3 = smem_u32(W3T);
+    const bool warp_on = __any_sync(0xffffffffu, row_on);
+    const uint32_t a_grp = smem_u32(sA);
+    const uint32_t arow = a_grp + (uint32_t)row * 16u;
+    const uint32_t tmem_g = *tmem_slot + (uint32_t)g * 256u;
+    const uint32_t trow = tmem_g + ((uint32_t)(wq * 32) << 16);
+    const uint32_t bar0 = smem_u32(mbar);
+    const bool issuer = (row == 0) && (half == 0);
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    // operand rows written by this group -> visible to the tensor core; then the group's named barrier
+    auto publish = [&]() {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // (also orders this thread's TMEM loads before the new MMAs)
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+    };
+    // one lane per warp polls the mbarrier, the warp's other lanes wait at the warp barrier
+    auto wait_mbar = [&](uint32_t bar, uint32_t parity) {
+      if ((tid & 31) == 0) {
+        uint32_t done = 0;
+        while (!done) {
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                       : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        }
+      }
+      __syncwarp();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    };
+    // ---- layer 1 on the tensor core: the owner's operand row [x1 x2 x3 x1 x2 x1 | 1 1 1 | 0 ...] (three-term bf16 split of the six
+    //      inputs, K = 48 = six k-groups at the start of quarter buffer 0, which the previous step's MMAs have released) ----
+    if (warp_on && half == 0) {
+      uint32_t p1[3], p2[3], p3[3];
+      MlpTcPredV1::split3(u, z.om, p1[0], p2[0], p3[0]);
+      MlpTcPredV1::split3(z.c, z.s, p1[1], p2[1], p3[1]);
+      MlpTcPredV1::split3(z.x, z.v, p1[2], p2[2], p3[2]);
+      auto sts4 = [&](int kg, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(arow + (uint32_t)kg * kTcKStride), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+      };
+      sts4(0, p1[0], p1[1], p1[2], p2[0]);          // k  0.. 7: x1[0..5] x2[0..1]
+      sts4(1, p2[1], p2[2], p3[0], p3[1]);          // k  8..15: x2[2..5] x3[0..3]
+      sts4(2, p3[2], p1[0], p1[1], p1[2]);          // k 16..23: x3[4..5] x1[0..5]
+      sts4(3, p2[0], p2[1], p2[2], p1[0]);          // k 24..31: x2[0..5] x1[0..1]
+      sts4(4, p1[1], p1[2], 0x3f803f80u, 0x00003f80u);  // k 32..39: x1[2..5] 1 1 1 0
+      sts4(5, 0u, 0u, 0u, 0u);                      // k 40..47
+    }
+    publish();
+    if (issuer) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t b1a = smem_u32(sB1);
+#pragma unroll
+      for (int ks = 0; ks < 3; ++ks)
+        umma_bf16(tmem_g, umma_smem_desc(a_grp + (uint32_t)ks * 2u * kTcKStride), umma_smem_desc(b1a + (uint32_t)ks * 2u * kTcKStride), idesc, ks > 0 ? 1u : 0u);
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0) : "memory");
+    }
+    wait_mbar(bar0, phase);
+    phase ^= 1u;
+    // ---- layer 2, one K-quarter at a time: L1 accumulator columns [32 p + 16 half, + 16) -> tanh -> three bf16 terms -> quarter
+    //      buffer p & 1 -> 12 UMMAs into the L2 accumulator (TMEM columns [128, 256)) ----
+    const uint32_t b2t = smem_u32(sB);
+#pragma unroll 1
+    for (int p = 0; p < 4; ++p) {
+      const uint32_t bsel = (uint32_t)(p & 1);
+      if (p >= 2) wait_mbar(bar0 + 8u * (1u + bsel), 0u);  // the MMAs of quarter p - 2 have released this buffer
+      const uint32_t brow = arow + bsel * kQBuf;
+      if (warp_on) {
+        uint32_t v[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(trow + (uint32_t)(32 * p + 16 * half)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t q1[8], q2[8], q3[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          MlpTcPredV1::split3(tanh5(__uint_as_float(v[2 * j])), tanh5(__uint_as_float(v[2 * j + 1])), q1[j], q2[j], q3[j]);
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const uint32_t dst = brow + (uint32_t)(2 * half + kk) * kTcKStride;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(q1[4 * kk]), "r"(q1[4 * kk + 1]), "r"(q1[4 * kk + 2]), "r"(q1[4 * kk + 3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 4u * kTcKStride), "r"(q2[4 * kk]), "r"(q2[4 * kk + 1]), "r"(q2[4 * kk + 2]), "r"(q2[4 * kk + 3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 8u * kTcKStride), "r"(q3[4 * kk]), "r"(q3[4 * kk + 1]), "r"(q3[4 * kk + 2]), "r"(q3[4 * kk + 3]) : "memory");
+        }
+      }
+      publish();
+      if (issuer) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t abuf = a_grp + bsel * kQBuf;
+#pragma unroll
+        for (int term = 0; term < 6; ++term) {  // smallest products first: (a3 w1) (a2 w2) (a1 w3) (a2 w1) (a1 w2) (a1 w1)
+          constexpr int ta[6] = {2, 1, 0, 1, 0, 0}, tb[6] = {0, 1, 2, 0, 1, 0};
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            umma_bf16(tmem_g + 128u, umma_smem_desc(abuf + (uint32_t)ta[term] * 4u * kTcKStride + (uint32_t)ks * 2u * kTcKStride),
+                      umma_smem_desc(b2t + (uint32_t)tb[term] * kTcTileBytes + (uint32_t)(2 * p + ks) * 2u * kTcKStride), idesc,
+                      (p > 0 || term > 0 || ks > 0) ? 1u : 0u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8u * (1u + bsel)) : "memory");
+      }
+    }
+    wait_mbar(bar0 + 8u, 1u);   // quarter 2 (buffer 0 is free for the next step's layer-1 rows)
+    wait_mbar(bar0 + 16u, 1u);  // quarter 3: the L2 accumulator is complete (and quarter buffer 1 is free: partial-sum exchange)
+    // ---- the row's L2 accumulator, columns [64 half, + 64) -> bias + tanh -> layer 3 partial sums ----
+    float y[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (warp_on) {
+#pragma unroll 2
+      for (int c0 = 64 * half; c0 < 64 * half + 64; c0 += 16) {
+        uint32_t v[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(trow + 128u + (uint32_t)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint32_t jo = (uint32_t)(c0 + q4 * 4) * 4u;
+          const float4 bb = MlpTcPredV1::lds4(ab2 + jo);
+          const float h0 = tanh5(__uint_as_float(v[4 * q4]) + bb.x), h1 = tanh5(__uint_as_float(v[4 * q4 + 1]) + bb.y);
+          const float h2 = tanh5(__uint_as_float(v[4 * q4 + 2]) + bb.z), h3 = tanh5(__uint_as_float(v[4 * q4 + 3]) + bb.w);
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const float4 w = MlpTcPredV1::lds4(aW3 + (uint32_t)k * 512u + jo);
+            y[k] = fmaf(h3, w.w, fmaf(h2, w.z, fmaf(h1, w.y, fmaf(h0, w.x, y[k]))));
+          }
+        }
+      }
+    }
+    // helper -> owner: five partial sums per row through quarter buffer 1 ([128 rows][8 floats])
+    float* sy = reinterpret_cast<float*>(sA + kQBuf) + row * 8;
+    if (half == 1 && warp_on) {
+      reinterpret_cast<float4*>(sy)[0] = make_float4(y[0], y[1], y[2], y[3]);
+      sy[4] = y[4];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+    if (half == 1 || !warp_on) return;
+    {
+      const float4 v0 = reinterpret_cast<const float4*>(sy)[0];
+      y[0] += v0.x; y[1] += v0.y; y[2] += v0.z; y[3] += v0.w; y[4] += sy[4];
+    }
+    z.om = y[0] + b3[0];
+    z.c = y[1] + b3[1];
+    z.s = y[2] + b3[2];
+    z.x = y[3] + b3[3];
+    z.v = y[4] + b3[4];
+    z.th = atan2f(z.s, z.c);
+    // the network's (cos, sin) outputs are not normalised: cos(atan2(s, c)) = c / hypot(s, c)
+    omc = 1.0f - z.c * rsqrtf(fmaf(z.c, z.c, z.s * z.s));
+  }
+};
 #endif  // __CUDACC__
 
 

@@ -23,6 +23,7 @@ static cudaError_t launch_mppi_p(int kind, bool log, int nblocks, int block, siz
 }
 cudaError_t launch_mppi_rollout(int pred, int kind, bool log, int nblocks, int block, size_t smem, cudaStream_t st, const MppiArgs& a) {
   if (pred == 2) return launch_mppi_p<MlpTcPred>(kind, log, nblocks, block, smem, st, a);
+  if (pred == 6) return launch_mppi_p<MlpTcPredV1>(kind, log, nblocks, block, smem, st, a);
   if (pred == 3) return launch_mppi_p<MlpTcBf16Pred>(kind, log, nblocks, block, smem, st, a);
   if (pred == 4) return launch_mppi_p<MlpTcFastPred>(kind, log, nblocks, block, smem, st, a);
   if (pred == 5) return launch_mppi_rollout_gru(kind, log, nblocks, block, smem, st, a);  // ctk_gru.cu
@@ -31,21 +32,30 @@ cudaError_t launch_mppi_rollout(int pred, int kind, bool log, int nblocks, int b
 }
 // pred: 0 ODE, 1 MLP on the FP32 pipe, 2 MLP with layer 2 on the tensor cores (tcgen05, bf16 x 3 split: fp32-level), 3 / 4 the opt-in
 // single-bf16-product engines (3: exact tanh, 4: MUFU.TANH)
-// 5: the recurrent (GRU) predictor on the FP32 pipe
+// 5: the recurrent (GRU) predictor on the FP32 pipe; 6: the round-1 structure of engine 2 (one tile in flight, CTK_TC_EXACT_V1=1: A/B runs)
 int mppi_max_block_threads(int pred) {
   if (pred == 5) return GruSimtPred::kMaxThreads;
+  if (pred == 6) return MlpTcPredV1::kMaxThreads;
   if (pred == 3 || pred == 4) return MlpTcBf16Pred::kMaxThreads;
   return pred == 0 ? OdePred::kMaxThreads : (pred >= 2 ? MlpTcPred::kMaxThreads : MlpSimtPred::kMaxThreads);
 }
 size_t mppi_pred_smem_floats(int pred, const MlpDev& m) {
   if (pred == 5) return GruSimtPred::smem_floats(m);
+  if (pred == 6) return MlpTcPredV1::smem_floats(m);
   return pred == 0 ? 0 : (pred == 2 ? MlpTcPred::smem_floats(m) : (pred >= 3 ? MlpTcBf16Pred::smem_floats(m) : MlpSimtPred::smem_floats(m)));
 }
 
+#ifndef CTK_K1_MAXT2
+#define CTK_K1_MAXT2 896
+#endif
+constexpr int k1_maxt(bool log, int ilp) { return ilp == 2 ? (log ? 768 : CTK_K1_MAXT2) : 1024; }
 // K1 for the ODE predictor (ctk_kernels_mppi_ode.cuh).  period_t: 10 -> the segment-unrolled instantiation, else runtime period.
 template <int KIND, bool LOG, int PERIOD, int ILP, bool INJ>
 static cudaError_t launch_mppi_ode_t(int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a) {
-  auto k = mppi_ode_kernel<KIND, LOG, PERIOD, ILP, 1024, INJ>;
+  // __launch_bounds__ caps the registers at 65536 / MAXT.  Two rollouts per thread need ~70 registers, the logging instantiations more
+  // (seven store addresses per rollout): under a bound of 1024 threads ptxas spilled inside the step loop (measured on the same box
+  // against the round-1 build: -3 % at C5, -13 % with logging on) -> ILP = 2: blocks of at most 896 threads, logging: 768.
+  auto k = mppi_ode_kernel<KIND, LOG, PERIOD, ILP, k1_maxt(LOG, ILP), INJ>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -59,10 +69,11 @@ static cudaError_t launch_mppi_ode_t(int grid, int block, size_t smem, cudaStrea
 template <int KIND>
 static cudaError_t launch_mppi_ode_k(bool log, int period_t, int ilp, int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a,
                                      const char** name) {
-  // template arguments after KIND: LOG, PERIOD, ILP, (MAXT = 1024), INJ
+  // template arguments after KIND: LOG, PERIOD, ILP, MAXT (k1_maxt), INJ
 #define CTK_ODE_CASE(LOG_, P_, I_, INJ_)                                                  \
   do {                                                                                    \
-    if (name) *name = "," #LOG_ "," #P_ "," #I_ ",1024," #INJ_ ">";                        \
+    if (name) *name = (I_ == 2) ? ((LOG_) ? "," #LOG_ "," #P_ "," #I_ ",768," #INJ_ ">" : "," #LOG_ "," #P_ "," #I_ ",896," #INJ_ ">") \
+                                : "," #LOG_ "," #P_ "," #I_ ",1024," #INJ_ ">";                       \
     return launch_mppi_ode_t<KIND, LOG_, P_, I_, INJ_>(grid, block, smem, st, a);         \
   } while (0)
   if (a.noise.inj != nullptr) {
@@ -84,12 +95,12 @@ static cudaError_t launch_mppi_ode_k(bool log, int period_t, int ilp, int grid, 
   CTK_ODE_CASE(0, 0, 1, 0);
 #undef CTK_ODE_CASE
 }
-// name (optional): the template-argument tail of the instantiation that was launched, e.g. ",0,10,2,1024,0>" (after KIND)
+// name (optional): the template-argument tail of the instantiation that was launched, e.g. ",0,10,2,896,0>" (after KIND)
 cudaError_t launch_mppi_ode(int kind, bool log, int period_t, int ilp, int grid, int block, size_t smem, cudaStream_t st, const MppiOdeArgs& a,
                             const char** name) {
   return kind == 0 ? launch_mppi_ode_k<0>(log, period_t, ilp, grid, block, smem, st, a, name) : launch_mppi_ode_k<1>(log, period_t, ilp, grid, block, smem, st, a, name);
 }
-int mppi_ode_max_block(int ilp) { (void)ilp; return 1024; }
+int mppi_ode_max_block(int ilp, bool log) { return k1_maxt(log, ilp); }
 size_t mppi_ode_smem_bytes(int H, int period, int n_ind, int ilp, int block) {
   return sizeof(float) * ((size_t)((H + 3) & ~3) + 2 * ((period + 3) & ~3) + 32 + 12 * (size_t)(n_ind + 2) + (size_t)(n_ind * ilp > 2 ? n_ind * ilp : 2) * block + (size_t)n_ind * block);
 }

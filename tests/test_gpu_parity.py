@@ -396,7 +396,7 @@ def test_top_m_logging_equals_the_best_rows_of_the_full_logs(fixture, M, over):
         np.testing.assert_array_equal(lt["rollout_trajectories_logged"], np.asarray(lf["rollout_trajectories_logged"])[order])
         assert lt["rollout_trajectories_logged"].shape == (m,) + np.asarray(lf["rollout_trajectories_logged"]).shape[1:]
     # the controller's history (reference Controllers/__init__.py:159-178) takes the reduced logs like any other
-    assert np.asarray(top.get_outputs()["rollout_trajectories_logged"][0]).shape[0] == m
+    assert np.asarray(top.logs["rollout_trajectories_logged"][0]).shape[0] == m
 
 
 @pytest.mark.parametrize("N,H,k,iters", [(4096, 50, 64, 3), (16000, 30, 64, 2), (300, 21, 100, 4), (65, 7, 1, 1), (9000, 12, 128, 2)])

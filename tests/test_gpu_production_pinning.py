@@ -2,7 +2,7 @@
 the FAST persistent CEM tick, the one-launch RPGD tick, the tcgen05 MLP engine -- pinned to the oracle at the BASELINE sizes.
 
 The golden / injected-noise tests (test_gpu_parity.py) run ``mppi_ode_kernel<KIND,LOG,0,1,1024,1>`` (runtime period, one rollout
-per thread, injected-noise branch); bench.py times ``mppi_ode_kernel<0,0,10,2,1024,0>``.  Here the optimizer runs with
+per thread, injected-noise branch); bench.py times ``mppi_ode_kernel<0,0,10,2,896,0>``.  Here the optimizer runs with
 ``rng = None`` (the production path), the standard draws the kernels generated are exported with ``ctk_philox_export`` (same key,
 counter words and device function) and replayed through the oracle's rng (``oracle.replay_rng.QueueRNG``), so both sides consume
 identical numbers.  Every test asserts ``optimizer.last_kernel`` -- the instantiation that actually ran.
@@ -57,10 +57,10 @@ def _assert_state(tag, e32, e64, floor, hard):
 MPPI_CASES = [
     # id, fixture for the config, N, H, period, env, expected kernel, ticks, hard 1e-5
     ("c1", "mppi_c1_n2000", 2000, 50, 10, {}, "mppi_ode_kernel<0,0,10,1,1024,0>", 3, True),
-    ("c1_ilp2", "mppi_c1_n2000", 2000, 50, 10, {"CTK_K1_ILP": "2"}, "mppi_ode_kernel<0,0,10,2,1024,0>", 3, True),
-    ("c1_period7", "mppi_c1_n2000", 2000, 50, 7, {"CTK_K1_ILP": "2"}, "mppi_ode_kernel<0,0,0,2,1024,0>", 2, True),
-    ("h100_ragged", "mppi_h100_n256", 30011, 97, 10, {"CTK_K1_ILP": "2"}, "mppi_ode_kernel<0,0,10,2,1024,0>", 2, False),
-    ("c5_1m", "mppi_h100_n256", 1_000_000, 100, 10, {}, "mppi_ode_kernel<0,0,10,2,1024,0>", 2, True),
+    ("c1_ilp2", "mppi_c1_n2000", 2000, 50, 10, {"CTK_K1_ILP": "2"}, "mppi_ode_kernel<0,0,10,2,896,0>", 3, True),
+    ("c1_period7", "mppi_c1_n2000", 2000, 50, 7, {"CTK_K1_ILP": "2"}, "mppi_ode_kernel<0,0,0,2,896,0>", 2, True),
+    ("h100_ragged", "mppi_h100_n256", 30011, 97, 10, {"CTK_K1_ILP": "2"}, "mppi_ode_kernel<0,0,10,2,896,0>", 2, False),
+    ("c5_1m", "mppi_h100_n256", 1_000_000, 100, 10, {}, "mppi_ode_kernel<0,0,10,2,896,0>", 2, True),
 ]
 
 
