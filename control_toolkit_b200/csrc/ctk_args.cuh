@@ -165,7 +165,6 @@ struct OdeHot {
 
 struct MppiOdeArgs {
   int N, off, H, period, n_ind;
-  int t0;               // threads of block 0 that carry rollouts (multiple of 32, <= blockDim.x): the finisher block gets a smaller share
   S0 s0;                // initial state
   const float* u_nom;   // [H] unshifted
   const float* u_prev;  // [1]

@@ -60,7 +60,6 @@ struct ctk_handle {
   unsigned long long* d_mbox = nullptr;           // local mailbox (layout: MppiFuse)
   unsigned int bseq = 0;                          // sequence number of the exchange barrier (ctk_exchange_barrier)
   bool chain_hint = false;                        // set by ctk_step_device_n for ticks 1.. of a chain: the tick may poll the hand-over
-  int ode_t0 = 0;                                 // rollout-carrying threads of block 0 (the finisher's reduced share)
   unsigned long long* mbox_peer[CTK_MAX_PEERS] = {nullptr};
   bool mbox_ipc[CTK_MAX_PEERS] = {false};
   int xworld = 1, xrank = 0;
@@ -812,42 +811,29 @@ static void mppi_ode_geometry(ctk_handle* h) {
   const long long tmax_smem = (200 * 1024 - fixed) / per_thread / 32 * 32;
   if (tmax_smem < 32) return;  // too many inducing points: generic kernel (regenerates the draws)
   if (maxb > tmax_smem) maxb = (int)tmax_smem;
-  // Block 0 is the tick's finisher: in a back-to-back chain of ticks its SM is the last to be handed to the next launch (it is still
-  // combining the records when the other blocks' SMs are already running the next tick's prologue), so it carries a smaller share
-  // of the rollouts (t0 = share x T threads) and is through them when the others are.  Only when every SM has a block.
-  double share = 0.75;
-  if (const char* e = getenv("CTK_K1_FINISHER_SHARE")) { const double v = atof(e); if (v >= 0.1 && v <= 1.0) share = v; }
-  auto t0_of = [&](long long T) { long long t0 = (long long)(share * (double)T) / 32 * 32; return t0 < 32 ? 32ll : (t0 > T ? T : t0); };
-  const long long r0 = (N + sms * maxb * ilp - 1) / (sms * maxb * ilp);
-  long long best_cap = -1; int best_T = 32;
-  for (long long r = r0; r < r0 + 4; ++r) {
-    long long T = (long long)((double)N / ((double)r * ilp * ((double)sms - 1.0 + share)));
-    T = (T + 31) / 32 * 32;
-    if (T < 32) T = 32;
-    while (T <= maxb && r * ilp * (t0_of(T) + (sms - 1) * T) < N) T += 32;
-    if (T > maxb) continue;
-    const long long cap = r * T * ilp;  // per-SM time is proportional to iterations x (warps resident)
-    if (best_cap < 0 || cap < best_cap) { best_cap = cap; best_T = (int)T; }
-  }
+  // Every block takes an equal contiguous share of the population, cut into units of 32 x ilp rollouts dealt round-robin to its warps
+  // (ctk_kernels_mppi_ode.cuh).  Blocks of whole warp quads (warp w runs on SM sub-partition w % 4, and the kernel's duration is the
+  // instruction count of the busiest sub-partition); as many warps as there are units, up to the register / shared-memory bound.
   // Small populations: a block narrower than 4 warps leaves the tick finish (block 0 polls and combines gridDim x (n_ind+2)
   // records, then updates u_nom[H]) to one or two warps while the rollout phase gains nothing from spreading single warps over
   // more SMs -- measured at N = 2000: rollouts 5.5 us, finish 19 us with 63 blocks x 32 threads.
   int min_T = 128;
   if (const char* e = getenv("CTK_K1_MIN_BLOCK")) { const int v = atoi(e) / 32 * 32; if (v >= 32) min_T = v; }
   if (min_T > maxb) min_T = maxb;
-  if (best_T < min_T) best_T = (int)std::min<long long>(min_T, (N + 31) / 32 * 32);
+  const long long unit = 32ll * ilp;
+  long long G = std::min<long long>(sms, (N + (long long)min_T * ilp - 1) / ((long long)min_T * ilp));
+  if (G < 1) G = 1;
+  const long long per_block = (N + G - 1) / G;                   // rollouts of the largest share
+  const long long U = (per_block + unit - 1) / unit;             // its units
+  const long long Wmax = maxb / 32 >= 1 ? maxb / 32 : 1;
+  const long long rounds = (U + Wmax - 1) / Wmax;                // units per warp (at most)
+  long long W = (U + rounds - 1) / rounds;                       // as few warps as that many rounds need: equal loads
+  if (W * 32 < min_T) W = min_T / 32;
+  if (W % 4 != 0 && (W + 3) / 4 * 4 * 32 <= maxb) W = (W + 3) / 4 * 4;
   h->ode_ilp = ilp;
-  h->ode_block = best_T;
-  // the reduced share only when every SM carries a block of at least 8 warps (T came out of the search above, so the grid fills the
-  // device); smaller populations: equal shares (t0 = T), as many blocks as there are groups of T x ilp rollouts
-  if (best_T >= 256 && best_cap > 0) {
-    h->ode_grid = (int)sms;
-    h->ode_t0 = (int)t0_of(best_T);
-  } else {
-    h->ode_grid = (int)std::min<long long>(sms, (N + (long long)best_T * ilp - 1) / ((long long)best_T * ilp));
-    if (h->ode_grid < 1) h->ode_grid = 1;
-    h->ode_t0 = best_T;
-  }
+  h->ode_block = (int)(W * 32);
+  h->ode_grid = (int)G;
+  const int best_T = h->ode_block;
   h->ode_period_t = (h->period == 10) ? 10 : 0;
   if (getenv("CTK_K1_NO_UNROLL")) h->ode_period_t = 0;
   h->ode_smem = mppi_ode_smem_bytes(h->H, h->period, h->n_ind, ilp, best_T);
@@ -906,7 +892,6 @@ static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_
   if (h->ode_kernel) {
     MppiOdeArgs a{};
     a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
-    a.t0 = h->ode_t0;
     a.trace = h->d_trace;
     a.s0 = make_s0(h, s_dev); a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = ns; a.k = h->ode_hot;
     a.J = h->d_J; a.partials = h->d_partials; a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
@@ -1544,7 +1529,6 @@ extern "C" int ctk_step_batch(ctk_handle* h, const float* s_host, const int32_t*
   fuse.handover = h->d_mbox + mbox_handover_offset(h->n_ind);
   MppiOdeArgs a{};
   a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
-  a.t0 = h->ode_t0;
   a.trace = nullptr;
   a.s0 = S0{}; a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = nsrc; a.k = h->ode_hot;
   a.J = h->d_J; a.partials = h->d_partials; a.log_traj_soa = nullptr; a.log_Q_soa = nullptr;

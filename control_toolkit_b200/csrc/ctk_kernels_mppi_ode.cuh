@@ -16,8 +16,11 @@
 //  * the state-independent part of the prologue (the Philox draws of the first rollout group) runs BEFORE griddepcontrol.wait: in a
 //    back-to-back chain of ticks (programmatic dependent launch) it overlaps the previous tick's finish / exchange / launch gap;
 //    the global reads of the prologue (s0, u_prev, u_nom) follow the wait and were prefetched into L2 before the draws;
-//  * block 0, the finisher of the tick, carries fewer rollouts (t0 of blockDim.x threads): in a chain it is the block that starts
-//    last (its SM is the one the previous tick's finisher occupied) and it has to be through its rollouts when the others are.
+//  * work distribution: every block takes an equal contiguous share of the population, cut into UNITS of 32 ILP consecutive rollouts
+//    that go round-robin over the block's warps.  The kernel is issue-bound, so its duration is the instruction count of the busiest
+//    SM sub-partition (warp w runs on sub-partition w % 4): with 27 warps of four whole iterations each (7 / 7 / 7 / 6 warps: 28 units
+//    on three sub-partitions, round 1) the ideal 26.4 units per sub-partition at C5 became 28; with 28 warps and the units dealt out
+//    one by one it is 27.
 #pragma once
 #include "ctk_device.cuh"
 #include "ctk_kernels_mppi.cuh"
@@ -107,12 +110,19 @@ __device__ __forceinline__ void mppi_ode_body(const MppiOdeArgs& a) {
   }
   const OdeHot& k = a.k;
   const int nblk = (a.n_ind + 3) >> 2;
-  const int Ta_ = (blockIdx.x == 0) ? a.t0 : T_;
+  // this block's share [r_first, r_end) of the population; unit u of it = rollouts r_first + u * UNIT + [0, UNIT), warp w takes units
+  // w, w + nw, w + 2 nw, ...; a thread's ILP rollouts of a unit are 32 apart (coalesced cost / log stores per warp)
+  // LOG: the trajectory log is HBM-write bound and wants all SMs inside one contiguous window of rollouts at a time (with contiguous
+  // per-block shares the 148 x 7 write streams are scattered over the whole log: 0.62 -> 1.37 ms per C5 tick, measured), so there the
+  // units are dealt out over the whole GRID instead: unit (it * gridDim + block) * nw + w.
+  constexpr int UNIT = 32 * ILP;
+  const int r_first = LOG ? 0 : (int)((long long)blockIdx.x * a.N / (long long)gridDim.x);
+  const int r_end = LOG ? a.N : (int)(((long long)blockIdx.x + 1) * a.N / (long long)gridDim.x);
   auto gen_noise = [&](int base) {  // K0: draws of the ILP rollouts of a group -> shared-memory stash
 #pragma unroll
     for (int q = 0; q < ILP; ++q) {
-      const int nq = base + q * Ta_ + tid;
-      const uint32_t ng = (uint32_t)(a.off + (nq < a.N ? nq : 0));
+      const int nq = base + q * 32;
+      const uint32_t ng = (uint32_t)(a.off + (nq < r_end ? nq : r_first));
       float* sz = sh_z + q * T_ + tid;
       for (int blk = 0; blk < nblk; ++blk) {
         float zz[4];
@@ -123,11 +133,9 @@ __device__ __forceinline__ void mppi_ode_body(const MppiOdeArgs& a) {
       }
     }
   };
-  // rollouts of this block: groups of ILP * Ta consecutive ids, Ta = the block's rollout-carrying threads (block 0: a.t0)
-  const int Ta = (blockIdx.x == 0) ? a.t0 : T_;
-  const int boff = (blockIdx.x == 0) ? 0 : ILP * (a.t0 + ((int)blockIdx.x - 1) * T_);
-  const int stride = ILP * (a.t0 + ((int)gridDim.x - 1) * T_);
-  if (tid < Ta) gen_noise(boff);
+  const int boff = (LOG ? ((int)blockIdx.x * nw + w) * UNIT : r_first + w * UNIT) + lane;  // this thread's first rollout (q = 0)
+  const int stride = (LOG ? (int)gridDim.x : 1) * nw * UNIT;
+  if (boff - lane < r_end) gen_noise(boff);
   for (int j = tid; j < period; j += T_) interp_weights(j, period, &sh_w[j].x, &sh_w[j].y);  // Interpolator.py:63-74
   for (int i = 0; i < a.n_ind; ++i) sh_acc[(size_t)i * T_ + tid] = 0.0f;
   if (chained) {
@@ -160,16 +168,15 @@ __device__ __forceinline__ void mppi_ode_body(const MppiOdeArgs& a) {
   float rho_t = INFINITY, a_t = 0.0f;  // per-thread online softmin (optimizer_mppi.py:163-168, exact combine later)
   float* sa = sh_acc + tid;
 
-  if (tid < Ta)  // (warp-uniform: Ta is a multiple of 32; no block barrier inside the loop)
-  for (int base = boff; base < a.N; base += stride) {
+  for (int base = boff; base - lane < r_end; base += stride) {  // (warp-uniform bound; no block barrier inside the loop)
     Roll r[ILP];
     int n[ILP];
     bool active[ILP];
     if (base != boff) gen_noise(base);  // the first group's draws were generated in the prologue
 #pragma unroll
     for (int q = 0; q < ILP; ++q) {
-      n[q] = base + q * Ta + tid;
-      active[q] = n[q] < a.N;
+      n[q] = base + q * 32;
+      active[q] = n[q] < r_end;
       const float* sz = sh_z + q * T_ + tid;
       r[q].T = T0; r[q].W = W0; r[q].c = c0; r[q].s = sn0; r[q].x = x0; r[q].V = V0; r[q].omc = omc0;
       r[q].ul = upv;
