@@ -165,6 +165,7 @@ struct OdeHot {
 
 struct MppiOdeArgs {
   int N, off, H, period, n_ind;
+  int fshare16;         // share of block 0, the tick's finisher, in sixteenths of an ordinary block's share (16: equal shares)
   S0 s0;                // initial state
   const float* u_nom;   // [H] unshifted
   const float* u_prev;  // [1]

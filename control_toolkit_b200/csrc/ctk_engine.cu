@@ -53,7 +53,7 @@ struct ctk_handle {
   ctk_cost_params cost_p{};
   OdeHot ode_hot{};
   bool ode_kernel = false;     // MPPI + ODE predictor + intermediate_steps == 1 + few inducing points
-  int ode_ilp = 2, ode_period_t = 0, ode_grid = 0, ode_block = 0;
+  int ode_ilp = 2, ode_period_t = 0, ode_grid = 0, ode_block = 0, ode_fshare16 = 16;
   unsigned long long* d_trace = nullptr;  // optional per-block phase timeline of the last ODE-kernel launch
   size_t ode_smem = 0;
   // fused tick finish / cross-GPU exchange (MppiFuse)
@@ -833,6 +833,11 @@ static void mppi_ode_geometry(ctk_handle* h) {
   h->ode_ilp = ilp;
   h->ode_block = (int)(W * 32);
   h->ode_grid = (int)G;
+  // the finisher's reduced share (ctk_kernels_mppi_ode.cuh) only when every SM carries a block of at least 8 warps
+  double share = 0.75;
+  if (const char* e = getenv("CTK_K1_FINISHER_SHARE")) { const double v = atof(e); if (v >= 0.1 && v <= 1.0) share = v; }
+  h->ode_fshare16 = (G == sms && h->ode_block >= 256) ? (int)(share * 16.0 + 0.5) : 16;
+  if (h->ode_fshare16 < 1) h->ode_fshare16 = 1;
   const int best_T = h->ode_block;
   h->ode_period_t = (h->period == 10) ? 10 : 0;
   if (getenv("CTK_K1_NO_UNROLL")) h->ode_period_t = 0;
@@ -892,6 +897,7 @@ static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_
   if (h->ode_kernel) {
     MppiOdeArgs a{};
     a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
+    a.fshare16 = h->ode_fshare16;
     a.trace = h->d_trace;
     a.s0 = make_s0(h, s_dev); a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = ns; a.k = h->ode_hot;
     a.J = h->d_J; a.partials = h->d_partials; a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
@@ -1529,6 +1535,7 @@ extern "C" int ctk_step_batch(ctk_handle* h, const float* s_host, const int32_t*
   fuse.handover = h->d_mbox + mbox_handover_offset(h->n_ind);
   MppiOdeArgs a{};
   a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
+  a.fshare16 = h->ode_fshare16;
   a.trace = nullptr;
   a.s0 = S0{}; a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = nsrc; a.k = h->ode_hot;
   a.J = h->d_J; a.partials = h->d_partials; a.log_traj_soa = nullptr; a.log_Q_soa = nullptr;

@@ -199,33 +199,37 @@ __device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float*
     const int r = m / G, b = m - r * G;
     return mb + (size_t)r * shard + (size_t)b * RS;
   };
-  if (nrec * P <= big_floats) {
-    // records staged in shared memory by the poll; hops == 2: only this grid's records now, the shard records of the peers after
-    const int hops2 = (world > 1 && f.hops == 2) ? 1 : 0;
-    const int n1 = hops2 ? G : nrec;
-    auto rec1 = [&](int m) -> const unsigned long long* { return hops2 ? mb + (size_t)rank * shard + (size_t)m * RS : rec_ptr(m); };
-    const int lost = poll_records(rec1, n1, P, f.seq, t0, big);
-    staged_combine(big, n1, P, neg_inv_lbd, lost, sh_min, sh_rec, sh_half, &status);
-    if (f.trace != nullptr && tid == 0) f.trace[6] = globaltimer_ns();
-    if (hops2) {
-      // second hop: this shard's combined record -> every shard's mailbox (slot of block CTK_MBOX_BLOCKS - 1), then the world's
-      const size_t mine2 = base + (size_t)rank * shard + (size_t)(CTK_MBOX_BLOCKS - 1) * RS;
-      for (int i = tid; i < world * P; i += blockDim.x) {
-        const int r = i / P, c = i - r * P;
-        st_tagged(f.mbox_peer[r] + mine2 + c, sh_rec[c], f.seq);
-      }
-      if (tid == 0) sh_min[0] = 0xffffffffu;
-      __syncthreads();
-      auto rec2 = [&](int m) -> const unsigned long long* { return mb + (size_t)m * shard + (size_t)(CTK_MBOX_BLOCKS - 1) * RS; };
-      const int lost2 = poll_records(rec2, world, P, f.seq, t0, big);
-      staged_combine(big, world, P, neg_inv_lbd, lost2, sh_min, sh_rec, sh_half, &status);
+  // hops == 2: first this grid's G block records, then (after forwarding the shard's combined record) the world's shard records;
+  // hops == 1 / one shard: all world x G block records at once.  A stage whose records fit into `big` is staged in shared memory by the
+  // poll itself; otherwise the poll only waits and the combine reads the low words through L2.
+  const int hops2 = (world > 1 && f.hops == 2) ? 1 : 0;
+  auto stage = [&](auto rec, int n) {
+    if (n * P <= big_floats) {
+      const int lost = poll_records(rec, n, P, f.seq, t0, big);
+      staged_combine(big, n, P, neg_inv_lbd, lost, sh_min, sh_rec, sh_half, &status);
+    } else {
+      const int lost = poll_records(rec, n, P, f.seq, t0, nullptr);
+      if (__syncthreads_or(lost)) status = 1;
+      combine_records([&](int b, int c) { return __ldcg(reinterpret_cast<const float*>(rec(b) + c)); }, n, P, neg_inv_lbd, sh_rec);
     }
-    if (f.trace != nullptr && tid == 0) f.trace[7] = globaltimer_ns();
-  } else {  // records do not fit in shared memory: wait for all of them, then combine from global memory (low words, through L2)
-    const int lost = poll_records(rec_ptr, nrec, P, f.seq, t0, nullptr);
-    if (__syncthreads_or(lost)) status = 1;
-    combine_records([&](int b, int c) { return __ldcg(reinterpret_cast<const float*>(rec_ptr(b) + c)); }, nrec, P, neg_inv_lbd, sh_rec);
+  };
+  if (hops2) {
+    stage([&](int m) -> const unsigned long long* { return mb + (size_t)rank * shard + (size_t)m * RS; }, G);
+    if (f.trace != nullptr && tid == 0) f.trace[6] = globaltimer_ns();
+    // second hop: this shard's combined record -> every shard's mailbox (slot of block CTK_MBOX_BLOCKS - 1), then the world's
+    const size_t mine2 = base + (size_t)rank * shard + (size_t)(CTK_MBOX_BLOCKS - 1) * RS;
+    for (int i = tid; i < world * P; i += blockDim.x) {
+      const int r = i / P, c = i - r * P;
+      st_tagged(f.mbox_peer[r] + mine2 + c, sh_rec[c], f.seq);
+    }
+    if (tid == 0) sh_min[0] = 0xffffffffu;
+    __syncthreads();
+    stage([&](int m) -> const unsigned long long* { return mb + (size_t)m * shard + (size_t)(CTK_MBOX_BLOCKS - 1) * RS; }, world);
+  } else {
+    stage(rec_ptr, nrec);
+    if (f.trace != nullptr && tid == 0) f.trace[6] = globaltimer_ns();
   }
+  if (f.trace != nullptr && tid == 0) f.trace[7] = globaltimer_ns();
   if (f.record_out != nullptr)
     for (int c = tid; c < P; c += blockDim.x) f.record_out[c] = sh_rec[c];
   if (f.mode < 2) return;

@@ -116,8 +116,14 @@ __device__ __forceinline__ void mppi_ode_body(const MppiOdeArgs& a) {
   // per-block shares the 148 x 7 write streams are scattered over the whole log: 0.62 -> 1.37 ms per C5 tick, measured), so there the
   // units are dealt out over the whole GRID instead: unit (it * gridDim + block) * nw + w.
   constexpr int UNIT = 32 * ILP;
-  const int r_first = LOG ? 0 : (int)((long long)blockIdx.x * a.N / (long long)gridDim.x);
-  const int r_end = LOG ? a.N : (int)(((long long)blockIdx.x + 1) * a.N / (long long)gridDim.x);
+  // Block 0 is the tick's finisher: in a back-to-back chain of ticks it is the block that starts its rollouts last (it was still
+  // combining the previous tick's records when the other SMs were already in the new tick's prologue), so its share is smaller
+  // (a.fshare16 sixteenths of an ordinary share): shares are cut at N cum(b) / tot with cum(b) = fshare16 + 16 (b - 1), cum(0) = 0.
+  const long long fs16 = a.fshare16 > 0 ? a.fshare16 : 16;
+  const long long tot16 = fs16 + 16ll * ((long long)gridDim.x - 1);
+  const long long cum0 = blockIdx.x == 0 ? 0ll : fs16 + 16ll * ((long long)blockIdx.x - 1);
+  const int r_first = LOG ? 0 : (int)(cum0 * a.N / tot16);
+  const int r_end = LOG ? a.N : (int)((cum0 + (blockIdx.x == 0 ? fs16 : 16ll)) * a.N / tot16);
   auto gen_noise = [&](int base) {  // K0: draws of the ILP rollouts of a group -> shared-memory stash
 #pragma unroll
     for (int q = 0; q < ILP; ++q) {

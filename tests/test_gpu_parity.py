@@ -816,8 +816,12 @@ def test_two_shards_equal_one(name):
             assert np.abs(shards[0].dist_mue - full.optimizer.dist_mue).max() < 1e-6
 
 
-@pytest.mark.parametrize("fixture,over", [("mppi_c1_n2000", {}), ("mppi_mlp_c4_n256", {"mlp_engine": "tcgen05"}), ("mppi_mlp_c4_n256", {"mlp_engine": "simt"})],
-                         ids=["ode_c1", "mlp_c4_tcgen05", "mlp_c4_simt"])
+@pytest.mark.parametrize("fixture,over", [("mppi_c1_n2000", {}), ("mppi_mlp_c4_n256", {"mlp_engine": "tcgen05"}), ("mppi_mlp_c4_n256", {"mlp_engine": "simt"}),
+                                          # full grids whose 148 block records do NOT fit into the finisher's shared-memory staging area
+                                          # (2 inducing points: 512 floats): the poll only waits and the combine reads through L2
+                                          ("mppi_mlp_c4_n256", {"mlp_engine": "tcgen05", "num_rollouts": 40000, "mpc_horizon": 11}),
+                                          ("mppi_mlp_c4_n256", {"mlp_engine": "tcgen05_fast", "num_rollouts": 80000, "mpc_horizon": 11})],
+                         ids=["ode_c1", "mlp_c4_tcgen05", "mlp_c4_simt", "mlp_tcgen05_full_grid", "mlp_fast_full_grid"])
 def test_fused_exchange_two_shards_one_launch_each(fixture, over):
     """The fused cross-GPU exchange (MppiFuse: peer-memory mailboxes, ctk_exchange_connect_ptrs + ctk_step_device), driven
     by two handles that own the two halves of the population -- for the ODE predictor (K1) and for the MLP predictor on both
