@@ -862,7 +862,7 @@ def test_fused_exchange_two_shards_one_launch_each(fixture, over):
         assert us[0][1] == 0.0 and us[1][1] == 0.0  # exchange status: no timeout
         assert us[0][0] == us[1][0]  # replicated update
         assert abs(float(us[0][0]) - float(u_full)) < 2e-6, (t, us, u_full)
-        H = meta["cfg"]["mpc_horizon"]
+        H = over.get("mpc_horizon", meta["cfg"]["mpc_horizon"])
         a, b, c = shards[0]._get_state(0, (H,)), shards[1]._get_state(0, (H,)), full.optimizer.u_nom.ravel()
         np.testing.assert_array_equal(a, b)
         assert np.abs(a - c).max() < 2e-6
