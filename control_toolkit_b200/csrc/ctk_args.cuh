@@ -105,7 +105,8 @@ struct MppiFuse {
   float* record_out;         // [2 + n_ind] shard record (mode >= 1)
   unsigned long long* mbox_local;                 // this shard's mailbox
   unsigned long long* mbox_peer[CTK_MAX_PEERS];   // every shard's mailbox (mbox_peer[rank] == mbox_local)
-  unsigned long long* handover;                   // [1 + H] tagged u_prev, u_nom[H] of the tick (local)
+  unsigned long long* handover;                   // [1 + H] tagged u_prev, u_nom[H] of the tick (local); a chained tick READS its predecessor's
+  int publish_handover;                           // 1: a chained tick follows this one, publish the hand-over
   unsigned long long* trace; // diagnostics: block 0's row of the phase timeline (slots 6, 7: records polled, records combined) or null
   int hops;                  // cross-GPU exchange: 1 every block stores its record into every shard's mailbox; 2 the finisher forwards the shard record
   int chained;               // 1: the previous launch of the stream is the previous tick of this handle's chain: poll its hand-over
@@ -166,6 +167,7 @@ struct OdeHot {
 struct MppiOdeArgs {
   int N, off, H, period, n_ind;
   int fshare16;         // share of block 0, the tick's finisher, in sixteenths of an ordinary block's share (16: equal shares)
+  double per16;         // N / (fshare16 + 16 (grid - 1)): rollouts per sixteenth of a share (0: the kernel derives it)
   S0 s0;                // initial state
   const float* u_nom;   // [H] unshifted
   const float* u_prev;  // [1]

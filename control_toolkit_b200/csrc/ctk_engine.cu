@@ -60,6 +60,7 @@ struct ctk_handle {
   unsigned long long* d_mbox = nullptr;           // local mailbox (layout: MppiFuse)
   unsigned int bseq = 0;                          // sequence number of the exchange barrier (ctk_exchange_barrier)
   bool chain_hint = false;                        // set by ctk_step_device_n for ticks 1.. of a chain: the tick may poll the hand-over
+  bool chain_next = false;                        // set by ctk_step_device_n for ticks that a chained tick follows: publish the hand-over
   unsigned long long* mbox_peer[CTK_MAX_PEERS] = {nullptr};
   bool mbox_ipc[CTK_MAX_PEERS] = {false};
   int xworld = 1, xrank = 0;
@@ -862,6 +863,8 @@ static int make_fuse(ctk_handle* h, int mode, float* u_out_dev, MppiFuse* out) {
   f.record_out = h->d_record;
   f.mbox_local = h->d_mbox;
   f.handover = h->d_mbox + mbox_handover_offset(h->n_ind);
+  f.publish_handover = h->chain_next ? 1 : 0;  // only a following chained tick reads it
+  h->chain_next = false;
   {
     static const int hops_env = getenv("CTK_EXCHANGE_HOPS") ? atoi(getenv("CTK_EXCHANGE_HOPS")) : 0;
     f.hops = (hops_env == 1 || hops_env == 2) ? hops_env : 2;  // measured at 8 GPUs (profiles/): two hops 32.0 us per chained tick, one hop 33.4
@@ -898,6 +901,7 @@ static int mppi_local(ctk_handle* h, const float* s_dev, int mode, float* u_out_
     MppiOdeArgs a{};
     a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
     a.fshare16 = h->ode_fshare16;
+    a.per16 = (double)h->N / (double)(h->ode_fshare16 + 16 * (h->ode_grid - 1));
     a.trace = h->d_trace;
     a.s0 = make_s0(h, s_dev); a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = ns; a.k = h->ode_hot;
     a.J = h->d_J; a.partials = h->d_partials; a.log_traj_soa = h->d_log_traj_soa; a.log_Q_soa = h->d_log_Q_soa;
@@ -1497,8 +1501,10 @@ extern "C" int ctk_step_device_n(ctk_handle* h, const float* s_dev, size_t s_str
     // ticks 1.. of the chain: nothing but this handle's previous tick precedes them on the stream, and the caller's states were
     // complete before tick 0 was launched, so they may take u_nom from the previous finisher's tagged hand-over
     h->chain_hint = i > 0 && handover && h->cfg.optimizer == CTK_OPT_MPPI;
+    h->chain_next = i + 1 < n && handover && h->cfg.optimizer == CTK_OPT_MPPI;
     int rc = ctk_step_device(h, s_dev + (size_t)i * s_stride, u_out_dev ? u_out_dev + (size_t)i * u_stride : nullptr);
     h->chain_hint = false;
+    h->chain_next = false;
     if (rc != CTK_OK) return rc;
   }
   return CTK_OK;
@@ -1532,10 +1538,11 @@ extern "C" int ctk_step_batch(ctk_handle* h, const float* s_host, const int32_t*
   MppiFuse fuse{};
   make_fuse(h, 2, h->d_u_out, &fuse);
   fuse.host = HostMirror{nullptr, 0};
-  fuse.handover = h->d_mbox + mbox_handover_offset(h->n_ind);
+  fuse.handover = nullptr;  // (no chained tick follows a batch launch)
   MppiOdeArgs a{};
   a.N = h->N; a.off = h->off; a.H = h->H; a.period = h->period; a.n_ind = h->n_ind;
   a.fshare16 = h->ode_fshare16;
+  a.per16 = (double)h->N / (double)(h->ode_fshare16 + 16 * (h->ode_grid - 1));
   a.trace = nullptr;
   a.s0 = S0{}; a.u_nom = h->d_u_nom; a.u_prev = h->d_u_prev; a.noise = nsrc; a.k = h->ode_hot;
   a.J = h->d_J; a.partials = h->d_partials; a.log_traj_soa = nullptr; a.log_Q_soa = nullptr;

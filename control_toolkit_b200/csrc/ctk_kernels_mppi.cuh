@@ -243,7 +243,7 @@ __device__ __forceinline__ void mppi_tick_finish(const MppiFuse& f, const float*
     const float bz1 = (j > 0) ? sh_rec[2 + seg + 1] : 0.0f;
     const float b = (fmaf(bz1, wt.y, bz0 * w0) * stdev) / a;
     const float un = fminf(fmaxf(sh_unom[t] + b, lo), hi);
-    if (f.handover != nullptr) {  // first: the next tick of a chain is polling these
+    if (f.handover != nullptr && f.publish_handover) {  // first: the next tick of a chain is polling these
       st_tagged(f.handover + 1 + t, un, f.seq);
       if (t == 0) st_tagged(f.handover, f.freeze_prev ? f.u_prev[0] : un, f.seq);
     }
