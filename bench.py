@@ -299,11 +299,14 @@ def run_ours(args):
 
     fused = getattr(opt, "_exchange", "none") in ("p2p", "none")  # the tick is ctk_step_device (one C call, no NCCL in between)
 
+    n_align = [0]  # alignment-barrier launches (outside the timed event pairs; not part of a tick)
+
     def align():
         """Device-side barrier across the shards (mailbox flags, one tiny kernel) enqueued BEFORE a timed tick: the shards' L2
         flushes run un-synchronised, and without it their skew would be spent waiting inside the timed tick's exchange."""
         if world > 1 and getattr(opt, "_exchange", "") == "p2p":
             L.check(lib.ctk_exchange_barrier(opt._h))
+            n_align[0] += 1
 
     for i in range(W):
         tick(i)
@@ -325,7 +328,7 @@ def run_ours(args):
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     per_tick_ms = [a.elapsed_time(b) for a, b in ev]
-    launches = opt.gpu_launches - launches0
+    launches = opt.gpu_launches - launches0 - n_align[0]  # kernels of the K timed ticks
     # ---- second pass, same ticks: CUDA events around the rollout kernel only (roofline.achieved); kept out of the pass
     #      above so that the extra event records do not sit inside the timed ticks ----
     single_launch_tick = launches == K
@@ -476,9 +479,13 @@ def run_ours(args):
                         "hbm": {"algorithmic_bytes_per_launch": 4.0 * n_local, "achieved_gbs": 4.0 * n_local / (k1_ms * 1e-3) / 1e9,
                                 "peak_gbs": peaks.get("hbm_gbs", 6650.0)}}
         # measured DRAM traffic of that kernel (ncu --set full capture, per launch), when a capture of this workload is on file
-        tpath = os.path.join(REPO, "profiles", "ncu_traffic_r01.json")
-        tr = (json.load(open(tpath)) if os.path.exists(tpath) else {}).get(args.workload if args.rollouts is None else "", None)
-        if tr and world == 1 and not (is_mlp and args.mlp_engine != "tcgen05"):
+        tpath = os.path.join(REPO, "profiles", "ncu_traffic_r02.json")
+        if not os.path.exists(tpath):
+            tpath = os.path.join(REPO, "profiles", "ncu_traffic_r01.json")
+        ttab = json.load(open(tpath)) if os.path.exists(tpath) else {}
+        tkey = args.workload if args.rollouts is None else ""
+        tr = ttab.get(f"{tkey}:{args.mlp_engine}" if is_mlp and args.mlp_engine != "tcgen05" else tkey, None)
+        if tr and world == 1:
             roofline["traffic"] = tr["bytes"]
             roofline["traffic_source"] = tr["source"]
         roofline["tick_ms_same_pass"] = tick2_ms

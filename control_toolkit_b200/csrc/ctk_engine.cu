@@ -1390,8 +1390,10 @@ static int wait_host_slots(ctk_handle* h, unsigned int seq, int first, int count
 #endif
       if ((++spins & 0xffu) != 0) continue;
       const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-      // short ticks (C1-C3: 15-50 us) are caught by the pause loop; a long one (logging: tens of ms) gives the core away between polls
-      if (el > 100e-6) { struct timespec ts = {0, el > 2e-3 ? 50000 : 5000}; nanosleep(&ts, nullptr); }
+      // ticks up to a few milliseconds (every BASELINE config: 15 us .. 1.9 ms) are caught by the pause loop -- a nanosleep of 5 us
+      // returns after 50-60 us (timer slack), which put C5's p50 at 0.240 ms for a 0.196 ms tick; only a long wait (logging: tens of
+      // ms) gives the core away between polls
+      if (el > 3e-3) { struct timespec ts = {0, 50000}; nanosleep(&ts, nullptr); }
       if (el < 0.05) continue;
       const cudaError_t e = cudaStreamQuery(h->stream);  // a faulted or finished stream will never publish
       if (e == cudaSuccess) {
