@@ -176,3 +176,35 @@ def test_queue_rng_replays_given_blocks():
     np.testing.assert_allclose(y.numpy().ravel(), b * 2 - 1)
     with pytest.raises(RuntimeError):
         r.normal([1])
+
+
+def test_philox4x32_10_known_answers():
+    """oracle/philox.py (the CPU restatement of the generator behind the reference's rng, others/globals_and_utils.py:95-97, and
+    of the device generator K0) against the known-answer vectors Random123 1.09 ships for philox4x32-10 (examples/kat_vectors:
+    counter, key -> output), plus the structural properties the kernels rely on."""
+    from oracle import philox as P
+    kat = [
+        ([0x00000000] * 4, [0x00000000] * 2, [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+        ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+        ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0], [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]),
+    ]
+    for ctr, key, out in kat:
+        np.testing.assert_array_equal(P.philox4x32_10(np.array(ctr, np.uint32), np.array(key, np.uint32)), np.array(out, np.uint32))
+    # vectorised evaluation == one counter at a time
+    ctr = np.random.default_rng(0).integers(0, 2**32, (7, 4), dtype=np.uint64).astype(np.uint32)
+    key = np.array([123, 456], np.uint32)
+    batch = P.philox4x32_10(ctr, key)
+    for i in range(7):
+        np.testing.assert_array_equal(batch[i], P.philox4x32_10(ctr[i], key))
+    # counter layout of a noise block: draw i of rollout n is word i % 4 of counter (i // 4, n, tick, stream)
+    w = P.draw_words(seed=(7 << 32) | 42, stream=1, tick=5, rows=[3, 1000000], per_rollout=10)
+    assert w.shape == (2, 10)
+    one = P.philox4x32_10(np.array([2, 1000000, 5, 1], np.uint32), np.array([42, 7], np.uint32))
+    np.testing.assert_array_equal(w[1, 8:10], one[:2])
+    # word -> uniform: 24 bits, [0, 1), exact in fp32
+    u = P.uniform24(np.array([0, 0xFF, 0x100, 0xFFFFFFFF], np.uint32))
+    np.testing.assert_array_equal(u, np.array([0.0, 0.0, 2.0 ** -24, 1.0 - 2.0 ** -24], np.float32))
+    # word -> normal: the mapping covers (0, 1] x [-pi, pi) and gives standard normals
+    z, u1 = P.box_muller(P.draw_words(seed=42, stream=0, tick=1, rows=np.arange(4096), per_rollout=16))
+    assert u1.min() > 0.0 and u1.max() <= 1.0 and np.isfinite(z).all()
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02
