@@ -6,6 +6,7 @@ torch-CPU fp32 with the build's pinned predictor / cost spec and INJECTED noise,
 outputs as small fixtures.  Must be run in the build container (needs /root/reference):
 
     python -m oracle.gen_golden            # writes tests/golden/*.npz
+    python -m oracle.gen_golden --out DIR mppi_c1_n64 rpgd_c3   # some cases, into another directory
 
 Each fixture holds: the case config (json), the per-tick states, the noise seed (noise is regenerated from
 ``numpy.random.default_rng(seed)`` by oracle.replay_rng.ReplayRNG; a checksum of the draws is stored), and
@@ -263,14 +264,20 @@ def run_reference_case(name: str) -> dict:
 
 def main(argv=None):
     from oracle.refharness.workspace import enter_workspace
-    names = (argv or sys.argv[1:]) or list(CASES)
+    args = list(argv if argv is not None else sys.argv[1:])
+    out_dir = GOLDEN
+    if "--out" in args:  # write somewhere else (tests/test_oracle_golden.py regenerates fixtures and compares them bit for bit)
+        i = args.index("--out")
+        out_dir = os.path.abspath(args[i + 1])
+        del args[i:i + 2]
+    names = args or list(CASES)
     enter_workspace()
     import logging
     logging.disable(logging.INFO)
-    os.makedirs(GOLDEN, exist_ok=True)
+    os.makedirs(out_dir, exist_ok=True)
     for name in names:
         out = run_reference_case(name)
-        path = os.path.join(GOLDEN, f"{name}.npz")
+        path = os.path.join(out_dir, f"{name}.npz")
         np.savez_compressed(path, **out)
         print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)  u0={out['u_0']}")
 

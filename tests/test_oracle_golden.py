@@ -2,6 +2,9 @@
 produced by the reference's UNMODIFIED files (oracle/gen_golden.py).  Both run torch-CPU fp32 with the same op
 order, so agreement is expected at rounding level; tolerance 2e-6 relative (fixtures were generated
 single-threaded, the test may run with several threads -> different reduction order)."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -208,3 +211,31 @@ def test_philox4x32_10_known_answers():
     z, u1 = P.box_muller(P.draw_words(seed=42, stream=0, tick=1, rows=np.arange(4096), per_rollout=16))
     assert u1.min() > 0.0 and u1.max() <= 1.0 and np.isfinite(z).all()
     assert abs(z.mean()) < 0.02 and abs(z.std() - 1.0) < 0.02
+
+
+REGEN_CASES = ["mppi_c1_n64", "mppi_h43_p10_n64", "mppi_gru_n256", "mppi_dubins_h23_p5_n96", "cem_warmup_n128", "cem_reset_mid_n128", "rpgd_c3",
+               "gradient_warmup_n33", "gradcem_bharadhwaj_n32", "random_action_n512"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Optimizers"), reason="needs the reference checkout (build container only)")
+def test_committed_fixtures_are_what_the_unmodified_reference_produces(tmp_path):
+    """Pinning of the fixtures themselves: re-run the reference's UNMODIFIED optimizer files (oracle/gen_golden.py, in a process of
+    its own because the harness changes the working directory and the module table) and compare every array of a committed fixture
+    with the regenerated one BIT FOR BIT; the json config on the keys both hold (later fixtures carry more metadata keys)."""
+    import json
+    import subprocess
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "oracle.gen_golden", "--out", str(tmp_path)] + REGEN_CASES, cwd=repo, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for name in REGEN_CASES:
+        new = np.load(os.path.join(str(tmp_path), name + ".npz"), allow_pickle=False)
+        old = np.load(os.path.join(repo, "tests", "golden", name + ".npz"), allow_pickle=False)
+        assert sorted(new.files) == sorted(old.files), name
+        for k in old.files:
+            if k == "config":
+                a, b = json.loads(str(new[k])), json.loads(str(old[k]))
+                assert all(a[q] == b[q] for q in b), (name, a, b)
+                continue
+            assert new[k].dtype == old[k].dtype and new[k].shape == old[k].shape, (name, k)
+            assert new[k].tobytes() == old[k].tobytes(), (name, k, "regenerated fixture differs from the committed one")
