@@ -60,6 +60,23 @@ def _worker(rank, world, port, q):
     u_nom = np.clip(u_nom_prev + b, -1, 1)
     err = np.abs(u_nom - o.u_nom.numpy()[0, :, 0]).max() / np.abs(o.u_nom.numpy()).max()
 
+    # ---- the two forms of the fused exchange (ctk_kernels_mppi.cuh mppi_tick_finish): every shard's grid emits one record per BLOCK;
+    #      two hops = blocks -> shard record -> world's shard records, one hop = all world x G block records at once.  Both must
+    #      give the unsharded result (the rescaling to the common minimum is exact up to rounding, in any grouping) ----
+    G = 5  # blocks of this shard's grid, ragged shares
+    cuts = np.linspace(0, cnt, G + 1).astype(int)
+    cuts[1:-1] += np.array([3, -2, 1, 0])[: G - 1]
+    blocks = np.stack([_mppi_record(S_all[off + a:off + b], z_all[off + a:off + b], nil) for a, b in zip(cuts[:-1], cuts[1:])])
+    rho_s, a_s, bz_s = _mppi_combine(blocks, nil)  # first hop, on this shard
+    shard_rec = np.concatenate([[rho_s, a_s], bz_s]).astype(np.float32)
+    two = _mppi_combine(plan.all_gather(torch.from_numpy(shard_rec)).numpy().reshape(world, -1), nil)
+    one = _mppi_combine(plan.all_gather(torch.from_numpy(blocks.ravel().copy())).numpy().reshape(world * G, -1), nil)
+    ref = _mppi_record(S_all, z_all, nil)
+    for got in (two, one):
+        assert got[0] == ref[0]  # the global minimum is exact
+        assert abs(got[1] - ref[1]) <= 2e-6 * abs(ref[1])
+        assert np.abs(got[2] - ref[2:]).max() <= 2e-6 * max(np.abs(ref[2:]).max(), 1e-6) + 2e-6 * abs(ref[1])
+
     # ---- CEM: per-shard top-k candidates (cost, GLOBAL id) -> all-gather -> merge == global stable argsort[:k] ----
     z2, meta2 = load_golden("cem_c2_n4096_k64")
     J = z2["J_0"]
