@@ -13,7 +13,9 @@ in-kernel Philox noise, sharded by sample over the N GPUs ("strong" scaling: the
   roofline : the fused rollout kernel (K1) against the measured FP32 FMA-chain peak (the kernel is FP32-pipe bound:
              < 1 byte of HBM traffic per rollout-step), algorithmic 80 FLOP per rollout-step.
   cpu_baseline : the oracle port of the reference's MPPI (torch-CPU fp32, all host threads) on a bounded sample.
-Reference arm (--impl reference): the same oracle port timed on the host cores, K steps of a bounded sample each.
+Reference arm (--impl reference): the reference's UNMODIFIED optimizer file through controller_mpc and the oracle/refharness shims
+where the checkout (/root/reference) exists, the oracle port on the GPU box where it does not (cpu_baseline.kind says which), timed on
+the host cores, K steps of a bounded sample each; under torchrun rank 0 alone runs it.
 """
 from __future__ import annotations
 
@@ -284,7 +286,7 @@ def run_ours(args):
                                   mlp_engine=args.mlp_engine, logging=logging_on)
     opt = ctrl.optimizer
     plan.attach(opt, lib)  # handle runs on torch's current stream (events + NCCL ordering)
-    K, W = args.steps, args.warmup
+    K, W = max(args.steps, 1), max(args.warmup, 3)  # timing rule: at least three untimed warm-up ticks (the line reports the W used)
     states = torch.from_numpy(synthetic_states(K + W, 0)).to(dev)
     u_dev = torch.zeros(4, dtype=torch.float32, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
