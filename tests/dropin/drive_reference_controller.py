@@ -32,7 +32,9 @@ def main():
     logging.disable(logging.INFO)
     from control_toolkit_b200._lib import BackendUnavailable
     results = []
-    for name, fixture in (("mppi-b200", "mppi_c1_n2000"), ("cem-tf-b200", "cem_c2_n4096_k64"), ("rpgd-b200", "rpgd_c3")):
+    for name, fixture in (("mppi-b200", "mppi_c1_n2000"), ("cem-tf-b200", "cem_c2_n4096_k64"), ("rpgd-b200", "rpgd_c3"),
+                          ("random-action-tf-b200", "random_action_n512"), ("gradient-tf-b200", "gradient_n40"),
+                          ("cem-naive-grad-tf-b200", "gradcem_naive_n200"), ("cem-grad-bharadhwaj-tf-b200", "gradcem_bharadhwaj_n32")):
         base, pred_spec, cost_name, cfg, _, _ = CASES[fixture]
         cc = dict(mpc=dict(optimizer=name, predictor_specification=pred_spec, cost_function_specification=cost_name,
                            computation_library="pytorch", device="cpu", controller_logging=False, calculate_optimal_trajectory=False))
@@ -58,6 +60,7 @@ def main():
         rec["module_file"] = os.path.relpath(sys.modules[type(opt).__module__].__file__, ws)
         rec["bases"] = [b.__module__ + "." + b.__name__ for b in type(opt).__mro__[1:3]]
         rec["num_rollouts"], rec["mpc_horizon"] = int(opt.num_rollouts), int(opt.mpc_horizon)
+        rec["yaml_num_rollouts"], rec["yaml_mpc_horizon"] = int(cfg["num_rollouts"]), int(cfg["mpc_horizon"])
         rec["predictor_is_reference_wrapper"] = type(opt.predictor).__module__.startswith("SI_Toolkit")
         rec["cost_is_reference_wrapper"] = type(opt.cost_function).__module__.startswith("Control_Toolkit.")
         rec["num_states"], rec["num_control_inputs"] = opt.num_states, opt.num_control_inputs
