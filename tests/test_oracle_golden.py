@@ -239,3 +239,20 @@ def test_committed_fixtures_are_what_the_unmodified_reference_produces(tmp_path)
                 continue
             assert new[k].dtype == old[k].dtype and new[k].shape == old[k].shape, (name, k)
             assert new[k].tobytes() == old[k].tobytes(), (name, k, "regenerated fixture differs from the committed one")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/others"), reason="needs the reference checkout (build container only)")
+def test_interpolation_matrix_equals_the_unmodified_reference_interpolator():
+    """a2 (others/Interpolator.py:53-84,97-106) pinned directly: oracle.mppi.interpolation_matrix against the reference class over 1152
+    geometries (H = 1 .. 101, period = 1 .. 12, one and two control inputs; includes H < period, period 1, and H - 1 a multiple of the
+    period, where the last-point quirk shows): weights bit for bit, applied interpolation to one ulp."""
+    import json
+    import subprocess
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(repo, "tests", "dropin", "drive_reference_interpolator.py")], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("INTERP_RESULT ")]
+    assert line, r.stdout[-2000:]
+    res = json.loads(line[-1][len("INTERP_RESULT "):])
+    assert res["checked"] == 1152 and res["n_bad"] == 0, res
