@@ -155,3 +155,38 @@ def test_environment_registry_second_environment_and_recurrent_predictor():
     assert specs.resolve_predictor("CartPole", "GRU-6IN-32H1-32H2-5OUT-0")[0] == L.PRED_GRU
     with pytest.raises(ValueError):
         specs.GRUSpec(**{**{k: getattr(a, k) for k in a._KEYS}, "W3": np.zeros((32, 4), np.float32)})
+
+
+@pytest.mark.skipif(not __import__("os").path.isfile("/root/reference/Control_Toolkit_ASF_Template/config_optimizers.yml"),
+                    reason="needs the reference checkout (build container only)")
+@pytest.mark.parametrize("key", ["mppi", "cem-tf", "random-action-tf", "gradient-tf", "cem-naive-grad-tf", "cem-grad-bharadhwaj-tf"])
+def test_reference_template_yaml_blocks_feed_the_plugins_unchanged(key):
+    """The reference's OWN template blocks (Control_Toolkit_ASF_Template/config_optimizers.yml) go into the plugin constructors exactly as
+    controller_mpc passes them (**config_optimizer, Controllers/controller_mpc.py:56-65) -- every key accepted, values arrive -- and
+    configure() gets as far as ctk_create (no GPU here: BackendUnavailable, the first thing that can fail).  Only mpc_timestep is added:
+    the reference reads config_optimizer["mpc_timestep"] (:68,85) but its template blocks do not carry the key (an application adds it).
+    ('rpgd' has no usable template block: 'rpgd-tf' is a stale key without the constructor's sample_mean / uniform_dist_* arguments.)"""
+    import yaml
+    import control_toolkit_b200 as ctk
+    from control_toolkit_b200._lib import BackendUnavailable
+    from control_toolkit_b200.Controllers.controller_mpc import controller_mpc
+    with open("/root/reference/Control_Toolkit_ASF_Template/config_optimizers.yml") as f:
+        block = dict(yaml.safe_load(f)[key])
+    block["mpc_timestep"] = 0.02
+    predictor = "ODE"
+    ctrl = controller_mpc(
+        environment_name="CartPole", control_limits=(np.array([-1.0], np.float32), np.array([1.0], np.float32)),
+        initial_environment_attributes={"target_position": 0.0, "target_equilibrium": 1.0},
+        config_controller=dict(optimizer=key, predictor_specification=predictor, cost_function_specification="default",
+                               controller_logging=False, calculate_optimal_trajectory=False),
+        config_optimizers={key: block}, config_cost_function={"cost_function_name_default": "default"})
+    try:
+        ctrl.configure(optimizer_name=key, predictor_specification=predictor)
+    except BackendUnavailable:
+        pass  # no CUDA device: everything above ctk_create has run
+    opt = ctrl.optimizer
+    assert type(opt).__name__ == "optimizer_" + key.replace("-", "_") and opt.optimizer_name == key
+    assert (opt.num_rollouts, opt.mpc_horizon) == (int(block["num_rollouts"]), int(block["mpc_horizon"]))
+    for k, v in block.items():  # constructor arguments the plugin keeps under the reference's attribute names
+        if hasattr(opt, k) and isinstance(v, (int, float)) and not isinstance(v, bool) and k != "seed":
+            assert float(getattr(opt, k)) == pytest.approx(float(v)), k
